@@ -1,0 +1,225 @@
+/*
+ * yinyang_b200.h -- C ABI of the B200-native Yin-Yang self-play engine.
+ *
+ * This is the drop-in boundary for the self-play hot path of
+ * Arash-san/YinYang-Game-AlphaZero.  Every entry point names the reference
+ * interface (file:line, relative to the upstream repository root) it replaces.
+ * Plain pointers and sizes only; no torch / C++ types.  All `*_dev` pointers
+ * are CUDA device pointers owned by the caller; `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  Every function returns 0 on
+ * success or a negative yy_status; yy_last_error() gives the message.  Nothing
+ * here has a CPU fallback: without a CUDA device the compute calls fail.
+ *
+ * Board encoding ("bitboards"): cell (x, y) of an n x m board is action
+ * a = x*m + y (yin_yang_game.py:180-186); bit (a & 63) of 64-bit word (a >> 6).
+ * A board is W = ceil(n*m/64) words of black followed (in a separate array) by
+ * W words of white; arrays are board-major: word w of board i at [i*W + w].
+ * Supported: n, m <= 32 and n*m <= 256 (6x6, 8x8, 16x16 of BASELINE.json).
+ * Players are +1 (black) / -1 (white) (yin_yang_logic.py:8-11).
+ */
+#ifndef YINYANG_B200_H
+#define YINYANG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YY_ABI_VERSION 1
+
+typedef enum {
+  YY_OK = 0,
+  YY_ERR_INVALID = -1,   /* bad argument / unsupported board size            */
+  YY_ERR_CUDA = -2,      /* CUDA runtime error (message in yy_last_error)    */
+  YY_ERR_NO_DEVICE = -3, /* no CUDA device: there is no CPU fallback         */
+  YY_ERR_CAPACITY = -4,  /* a tree arena overflowed (raise edges_per_game)   */
+  YY_ERR_STATE = -5      /* call sequence error (e.g. NN mode without weights) */
+} yy_status;
+
+/* rule_flags */
+#define YY_RULE_ROWCOL 1u /* also ban completed single-colour rows/columns:
+                             src/gui/static/js/yin_yang_game.js:338-384.  OFF
+                             (default) == the Python rules used by self-play,
+                             yin_yang_logic.py:31-56. */
+
+/* Terminal codes written by yy_ended / yy_env_step (getGameEnded,
+ * yin_yang_game.py:80-110): the host maps them to the reference's return
+ * values 0 / +1 / -1 / 0.0001. */
+#define YY_RESULT_ONGOING 0
+#define YY_RESULT_WIN 1
+#define YY_RESULT_LOSS (-1)
+#define YY_RESULT_DRAW 2
+
+int yy_abi_version(void);
+const char *yy_last_error(void);
+/* Number of CUDA devices visible (0 on a CPU-only box). */
+int yy_device_count(void);
+/* Kernels launched by this library in this process since load (bench.py's gpu_launches). */
+int64_t yy_launch_count(void);
+
+/* ------------------------------------------------------------------ rules --
+ * Batched, stateless.  `count` boards; one thread per board. */
+
+/* YinYangGame.getValidMoves (yin_yang_game.py:60-78) = YinYangLogic.get_valid_moves
+ * (yin_yang_logic.py:111-120) over is_valid_move (:31-56): out_mask bit a = 1 iff
+ * action a is legal for players[i]. */
+int yy_legal_mask(int rows, int cols, uint32_t rule_flags, const uint64_t *black_dev, const uint64_t *white_dev,
+                  const int8_t *players_dev, uint64_t *out_mask_dev, int64_t count, void *stream);
+
+/* YinYangGame.getNextState (yin_yang_game.py:39-58) + place_piece (yin_yang_logic.py:24-29):
+ * places players[i]'s piece at actions[i] if legal, otherwise leaves the board unchanged
+ * (silent no-op); the turn passes either way.  In place. */
+int yy_step(int rows, int cols, uint32_t rule_flags, uint64_t *black_dev, uint64_t *white_dev, int8_t *players_dev,
+            const int32_t *actions_dev, int64_t count, void *stream);
+
+/* YinYangGame.getGameEnded (yin_yang_game.py:80-110): YY_RESULT_* from players[i]'s perspective. */
+int yy_ended(int rows, int cols, uint32_t rule_flags, const uint64_t *black_dev, const uint64_t *white_dev,
+             const int8_t *players_dev, int8_t *out_result_dev, int64_t count, void *stream);
+
+/* One environment step of BASELINE.md (getValidMoves + getNextState + getGameEnded fused):
+ * out_mask = legal mask of the side to move BEFORE the action; boards/players updated in
+ * place; out_result = YY_RESULT_* of the successor from the next player's perspective. */
+int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t *black_dev, uint64_t *white_dev,
+                int8_t *players_dev, const int32_t *actions_dev, uint64_t *out_mask_dev, int8_t *out_result_dev,
+                int64_t count, void *stream);
+
+/* Synthetic-board generator of SURVEY 8d / BASELINE.json configs[1]: board i = empty board
+ * advanced by plies[i] uniformly random legal plies (passes as in the rules), Philox stream
+ * keyed by (seed, i).  Also the random-play opponent of evaluate mode (RandomPlayer.play,
+ * yin_yang_players.py:14-42). */
+int yy_random_playout(int rows, int cols, uint32_t rule_flags, uint64_t seed, const int32_t *plies_dev,
+                      uint64_t *black_dev, uint64_t *white_dev, int8_t *players_dev, int64_t count, void *stream);
+
+/* ----------------------------------------------------------------- engine --
+ * Batched MCTS + evaluator + self-play driver for n_games concurrent games.
+ * Replaces MCTS (src/yin_yang/ai/mcts.py:227-505) driven by SelfPlayWorker.play_game
+ * (src/yin_yang/ai/self_play.py:72-192). */
+
+typedef struct yy_engine yy_engine;
+
+/* evaluator */
+#define YY_EVAL_STUB 0 /* deterministic dyadic hash priors/values (parity mode)  */
+#define YY_EVAL_NN 1   /* bf16 tcgen05 policy/value network (yy_engine_load_weights) */
+#define YY_EVAL_EXTERNAL 2 /* caller fills priors/values between yy_search_* calls
+                              (duck-typed neural_net.predict seam, mcts.py:295,394) */
+
+/* mode_flags */
+#define YY_MODE_SEARCH_AS_BLACK 1u /* self-play searches every position as player 1 and applies the move
+                                      with the real player (self_play.py:99,135-137,163).
+                                      Default ON in the reference-compatible facade. */
+
+typedef struct {
+  int32_t rows, cols;
+  int32_t n_games;          /* concurrent games (trees) on this GPU                       */
+  int32_t n_sims;           /* num_simulations (mcts.py:231)                              */
+  float cpuct;              /* mcts.py:231 (default 1.0)                                  */
+  uint32_t rule_flags;
+  uint32_t mode_flags;
+  int32_t evaluator;        /* YY_EVAL_*                                                  */
+  int32_t edges_per_game;   /* child-slot capacity per tree; 0 = worst case (n_sims+1)*A  */
+  float dirichlet_alpha;    /* mcts.py:233 (0.3)                                          */
+  float dirichlet_epsilon;  /* mcts.py:233 (0.25)                                         */
+  int32_t temperature_threshold; /* self_play.py:27 (10)                                  */
+  uint64_t seed;            /* Philox key for noise / action sampling                     */
+  int32_t replay_capacity;  /* self-play example ring (records)                           */
+  int32_t nn_channels;      /* 128 (neural_network.py:39)                                 */
+  int32_t nn_blocks;        /* 10                                                         */
+  int32_t device;           /* CUDA device ordinal                                        */
+} yy_engine_config;
+
+/* Bytes of device workspace the engine needs for cfg (caller allocates, 256-B aligned). */
+int64_t yy_engine_workspace_bytes(const yy_engine_config *cfg);
+/* Creates an engine over caller-owned device memory.  NULL on failure (see yy_last_error). */
+yy_engine *yy_engine_create(const yy_engine_config *cfg, void *workspace_dev, int64_t workspace_bytes);
+void yy_engine_destroy(yy_engine *e);
+
+/* Bytes of the packed bf16 weight image for (rows, cols, channels, blocks); the image itself is
+ * produced by the host-side packer (BN folded: neural_network.py:94-123 eval semantics) and
+ * uploaded by the caller; the engine keeps the pointer.  Layout: csrc/yy_nn.cuh. */
+int64_t yy_nn_weight_bytes(int rows, int cols, int channels, int blocks);
+int yy_engine_load_weights(yy_engine *e, const void *weights_dev, int64_t bytes);
+
+/* MCTS.search (mcts.py:275-343) for all games at once.  Roots: one board per game.
+ * noise_dev (may be NULL): float64 [n_games][A], one Dirichlet sample per legal root action in
+ * ascending action order (mcts.py:298-312), mixed only for games with noise_mask_dev[g] != 0.
+ * Runs root evaluation + n_sims simulations per game with the engine's evaluator and writes
+ * root.get_children_visit_counts() (mcts.py:168-181) into out_counts_dev int32[n_games][A]. */
+int yy_search(yy_engine *e, const uint64_t *root_black_dev, const uint64_t *root_white_dev,
+              const int8_t *root_players_dev, const double *noise_dev, const uint8_t *noise_mask_dev,
+              int32_t *out_counts_dev, void *stream);
+
+/* External-evaluator stepping (YY_EVAL_EXTERNAL): yy_search_begin selects the root leaves;
+ * the caller reads yy_engine_leaf_* , fills priors float32[n_games][A] (raw softmax entries,
+ * mcts.py:77-78) and values float32[n_games], then calls yy_search_advance, which expands +
+ * backs up and selects the next leaves.  Returns in *out_active the number of games that
+ * still need an evaluation (0 = search finished; then call yy_search_counts). */
+int yy_search_begin(yy_engine *e, const uint64_t *root_black_dev, const uint64_t *root_white_dev,
+                    const int8_t *root_players_dev, const double *noise_dev, const uint8_t *noise_mask_dev,
+                    void *stream);
+int yy_search_advance(yy_engine *e, const float *priors_dev, const float *values_dev, int32_t *out_active,
+                      void *stream);
+int yy_search_counts(yy_engine *e, int32_t *out_counts_dev, float *out_child_w_dev, void *stream);
+/* Device pointers (owned by the engine) of the pending leaf batch: boards to evaluate and a
+ * per-game flag (1 = needs evaluation). */
+const uint64_t *yy_engine_leaf_black(yy_engine *e);
+const uint64_t *yy_engine_leaf_white(yy_engine *e);
+const uint8_t *yy_engine_leaf_active(yy_engine *e);
+
+/* Runs the engine's evaluator once on `count` boards (batch inference entry point; replaces
+ * YinYangNeuralNetwork.predict, neural_network.py:125-154, batched): out_policy float32[count][A]
+ * = softmax over all A logits (no masking, :152), out_value float32[count], optional
+ * out_logits float32[count][A]. */
+int yy_evaluate(yy_engine *e, const uint64_t *black_dev, const uint64_t *white_dev, int64_t count,
+                float *out_policy_dev, float *out_value_dev, float *out_logits_dev, void *stream);
+
+/* Self-play driver (SelfPlayWorker.play_game, self_play.py:72-192, for n_games games in
+ * lock-step; finished games restart from the empty board).  Plays `n_moves` moves per game
+ * slot (one move = one full search + action selection + state update).  Examples are appended
+ * to the replay ring. */
+int yy_selfplay_reset(yy_engine *e, void *stream);
+int yy_selfplay_run(yy_engine *e, int32_t n_moves, void *stream);
+
+typedef struct {
+  int64_t moves;          /* searches completed                         */
+  int64_t evals;          /* leaf evaluations requested                 */
+  int64_t games_finished;
+  int64_t examples;       /* records appended to the replay ring        */
+  int64_t sims;           /* simulations completed                      */
+  int32_t overflow;       /* non-zero if a tree arena overflowed        */
+  int32_t max_depth;
+} yy_selfplay_stats;
+int yy_selfplay_get_stats(yy_engine *e, yy_selfplay_stats *out, void *stream);
+
+/* Replay record i (i < min(examples, replay_capacity)), struct-of-arrays on the device:
+ *   black/white  uint64[cap][W]   position before the move (self_play.py:140)
+ *   counts       uint16[cap][A]   root visit counts; pi = counts / sum in float64 (mcts.py:209)
+ *   game_serial  int32[cap]       index into the results table
+ *   ply          int16[cap], player int8[cap]
+ * results: int8[n_results] YY_RESULT_* per finished game serial, from the perspective the
+ * reference assigns to every example of that game (self_play.py:170-181). */
+typedef struct {
+  const uint64_t *black, *white;
+  const uint16_t *counts;
+  const int32_t *game_serial;
+  const int16_t *ply;
+  const int8_t *player;
+  const int8_t *results;
+  int32_t results_capacity;
+} yy_replay_view;
+int yy_selfplay_replay(yy_engine *e, yy_replay_view *out);
+
+/* Current live boards of the n_games slots (device pointers owned by the engine). */
+const uint64_t *yy_engine_game_black(yy_engine *e);
+const uint64_t *yy_engine_game_white(yy_engine *e);
+const int8_t *yy_engine_game_player(yy_engine *e);
+
+/* tcgen05 self-test used by tests/ (C = A[M,K] * B[N,K]^T, bf16 in / fp32 out, operands in the
+ * same no-swizzle K-major core-matrix layout the tower kernel uses).  Layout: csrc/yy_probe.cu. */
+int yy_probe_umma(const void *a_dev, const void *b_dev, float *c_dev, int M, int N, int K, int a_row_offset,
+                  int swap_lbo_sbo, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YINYANG_B200_H */

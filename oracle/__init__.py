@@ -1,0 +1,157 @@
+"""CPU oracle for the Yin-Yang self-play hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package, and only as the checker.  The
+product package (``yinyang-game-alphazero_b200/``) never imports it.
+
+Contents
+  yy_oracle.c   plain-C restatement (int8 boards, BFS) of the reference rules
+                (src/yin_yang/yin_yang_logic.py, yin_yang_game.py) and of the
+                sequential MCTS (src/yin_yang/ai/mcts.py) in numpy>=2 float32
+                op order, plus the deterministic hash-stub evaluator.
+  port.py       Python/numpy/torch port of the reference's CPU self-play path
+                (same algorithmic structure and cost profile: per-cell BFS
+                legality, object tree, batch-1 fp32 torch forward).  This is what
+                ``cpu_baseline`` / ``--impl reference`` time (kind "port").
+
+Parity pin: tests/golden/*.npz were produced by the *unmodified* Python reference
+(imported from /root/reference in the build container) by
+tests/golden/make_golden.py; tests/test_oracle_golden.py checks this oracle
+against them bit-for-bit.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libyy_oracle.so")
+RULE_ROWCOL = 1
+
+
+def build(force: bool = False) -> str:
+    """Compile yy_oracle.c with gcc (seconds).  Strict IEEE float32: no FMA contraction."""
+    src = os.path.join(_HERE, "yy_oracle.c")
+    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= os.path.getmtime(src):
+        return _SO
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+           "-o", _SO, src, "-lm"]
+    subprocess.run(cmd, check=True)
+    return _SO
+
+
+_lib = None
+EVAL_FN = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_int8), ctypes.c_int, ctypes.c_int,
+                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_void_p)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        i8p, u8p, i32p = (ctypes.POINTER(ctypes.c_int8), ctypes.POINTER(ctypes.c_uint8),
+                          ctypes.POINTER(ctypes.c_int32))
+        f32p, f64p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+        L.yo_legal_mask_batch.argtypes = [i8p, i8p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p]
+        L.yo_next_state_batch.argtypes = [i8p, i8p, i32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.yo_game_ended_batch.argtypes = [i8p, i8p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, f64p]
+        L.yo_env_step_batch.argtypes = [i8p, i8p, i32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        u8p, f64p]
+        L.yo_stub_predict.argtypes = [i8p, ctypes.c_int, f32p, f32p]
+        L.yo_stub_key.argtypes = [i8p, ctypes.c_int]
+        L.yo_stub_key.restype = ctypes.c_uint64
+        L.yo_mcts_search.argtypes = [i8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_float, f64p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                     i32p, f32p, i32p]
+        L.yo_mcts_search.restype = ctypes.c_int64
+        _lib = L
+    return _lib
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+def _boards(boards, n, m):
+    b = np.ascontiguousarray(boards, dtype=np.int8).reshape(-1, n * m)
+    return b
+
+
+def legal_mask(boards, players, n, m, rule_flags=0) -> np.ndarray:
+    """boards int8[B,n,m] (0/+1/-1), players int8[B] -> uint8[B, n*m] (1 = legal)."""
+    b = _boards(boards, n, m)
+    p = np.ascontiguousarray(players, dtype=np.int8)
+    out = np.zeros((b.shape[0], n * m), dtype=np.uint8)
+    lib().yo_legal_mask_batch(_p(b, ctypes.c_int8), _p(p, ctypes.c_int8), b.shape[0], n, m, rule_flags,
+                              _p(out, ctypes.c_uint8))
+    return out
+
+
+def next_state(boards, players, actions, n, m, rule_flags=0):
+    """Value semantics: returns (new boards int8[B,n,m], next players int8[B])."""
+    b = _boards(boards, n, m).copy()
+    p = np.ascontiguousarray(players, dtype=np.int8).copy()
+    a = np.ascontiguousarray(actions, dtype=np.int32)
+    lib().yo_next_state_batch(_p(b, ctypes.c_int8), _p(p, ctypes.c_int8), _p(a, ctypes.c_int32), b.shape[0], n, m,
+                              rule_flags)
+    return b.reshape(-1, n, m), p
+
+
+def game_ended(boards, players, n, m, rule_flags=0) -> np.ndarray:
+    b = _boards(boards, n, m)
+    p = np.ascontiguousarray(players, dtype=np.int8)
+    out = np.zeros(b.shape[0], dtype=np.float64)
+    lib().yo_game_ended_batch(_p(b, ctypes.c_int8), _p(p, ctypes.c_int8), b.shape[0], n, m, rule_flags,
+                              _p(out, ctypes.c_double))
+    return out
+
+
+def env_step(boards, players, actions, n, m, rule_flags=0):
+    """mask(side to move) + apply + ended(successor).  Returns (masks, boards', players', results)."""
+    b = _boards(boards, n, m).copy()
+    p = np.ascontiguousarray(players, dtype=np.int8).copy()
+    a = np.ascontiguousarray(actions, dtype=np.int32)
+    masks = np.zeros((b.shape[0], n * m), dtype=np.uint8)
+    res = np.zeros(b.shape[0], dtype=np.float64)
+    lib().yo_env_step_batch(_p(b, ctypes.c_int8), _p(p, ctypes.c_int8), _p(a, ctypes.c_int32), b.shape[0], n, m,
+                            rule_flags, _p(masks, ctypes.c_uint8), _p(res, ctypes.c_double))
+    return masks, b.reshape(-1, n, m), p, res
+
+
+def stub_predict(board, n, m):
+    """Deterministic hash-stub evaluator: (float32[A] dyadic priors, float32 value)."""
+    b = np.ascontiguousarray(board, dtype=np.int8).reshape(-1)
+    pol = np.zeros(n * m, dtype=np.float32)
+    val = ctypes.c_float(0)
+    lib().yo_stub_predict(_p(b, ctypes.c_int8), n * m, _p(pol, ctypes.c_float), ctypes.byref(val))
+    return pol, np.float32(val.value)
+
+
+def mcts_search(board, player, n, m, num_sims, cpuct=1.0, rule_flags=0, noise=None, eps=0.25, evaluator=None):
+    """Sequential MCTS (mcts.py:275-343).  evaluator: None = hash stub, else a Python callable
+    evaluator(board_int8[n,m]) -> (policy float32[A], value).  Returns dict(counts, child_w, n_evals, stats)."""
+    b = np.ascontiguousarray(board, dtype=np.int8).reshape(-1)
+    counts = np.zeros(n * m, dtype=np.int32)
+    cw = np.zeros(n * m, dtype=np.float32)
+    stats = np.zeros(3, dtype=np.int32)
+    nz = None
+    if noise is not None:
+        nz = np.ascontiguousarray(noise, dtype=np.float64)
+    cb = None
+    if evaluator is not None:
+        def _cb(bp, nn, mm, pol, val, ctx):
+            arr = np.ctypeslib.as_array(bp, shape=(nn * mm,)).reshape(nn, mm).copy()
+            p, v = evaluator(arr)
+            np.ctypeslib.as_array(pol, shape=(nn * mm,))[:] = np.asarray(p, dtype=np.float32)
+            val[0] = float(np.float32(v))
+        cb = EVAL_FN(_cb)
+    ne = lib().yo_mcts_search(_p(b, ctypes.c_int8), n, m, int(player), rule_flags, int(num_sims),
+                              ctypes.c_float(cpuct), _p(nz, ctypes.c_double) if nz is not None else None,
+                              float(eps), ctypes.cast(cb, ctypes.c_void_p) if cb else None, None,
+                              _p(counts, ctypes.c_int32), _p(cw, ctypes.c_float), _p(stats, ctypes.c_int32))
+    return {"counts": counts, "child_w": cw, "n_evals": int(ne),
+            "n_nodes": int(stats[0]), "max_depth": int(stats[1]), "root_visits": int(stats[2])}
