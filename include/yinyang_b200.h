@@ -113,19 +113,19 @@ typedef struct {
   int32_t rows, cols;
   int32_t n_games;          /* concurrent games (trees) on this GPU                       */
   int32_t n_sims;           /* num_simulations (mcts.py:231)                              */
-  float cpuct;              /* mcts.py:231 (default 1.0)                                  */
   uint32_t rule_flags;
   uint32_t mode_flags;
   int32_t evaluator;        /* YY_EVAL_*                                                  */
   int32_t edges_per_game;   /* child-slot capacity per tree; 0 = worst case (n_sims+1)*A  */
-  float dirichlet_alpha;    /* mcts.py:233 (0.3)                                          */
-  float dirichlet_epsilon;  /* mcts.py:233 (0.25)                                         */
   int32_t temperature_threshold; /* self_play.py:27 (10)                                  */
-  uint64_t seed;            /* Philox key for noise / action sampling                     */
   int32_t replay_capacity;  /* self-play example ring (records)                           */
   int32_t nn_channels;      /* 128 (neural_network.py:39)                                 */
   int32_t nn_blocks;        /* 10                                                         */
   int32_t device;           /* CUDA device ordinal                                        */
+  float cpuct;              /* mcts.py:231 (default 1.0; weak-promoted to float32)        */
+  double dirichlet_alpha;   /* mcts.py:233 (0.3)                                          */
+  double dirichlet_epsilon; /* mcts.py:233 (0.25; used in float64, mcts.py:309-311)       */
+  uint64_t seed;            /* Philox key for noise / action sampling                     */
 } yy_engine_config;
 
 /* Bytes of device workspace the engine needs for cfg (caller allocates, 256-B aligned). */
@@ -196,7 +196,7 @@ int yy_selfplay_get_stats(yy_engine *e, yy_selfplay_stats *out, void *stream);
  *   counts       uint16[cap][A]   root visit counts; pi = counts / sum in float64 (mcts.py:209)
  *   game_serial  int32[cap]       index into the results table
  *   ply          int16[cap], player int8[cap]
- * results: int8[n_results] YY_RESULT_* per finished game serial, from the perspective the
+ * results: int8[results_capacity] YY_RESULT_* of game serial s at [s % results_capacity], from the perspective the
  * reference assigns to every example of that game (self_play.py:170-181). */
 typedef struct {
   const uint64_t *black, *white;

@@ -1,0 +1,243 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Every check calls the CUDA path through the C ABI
+(ctypes) and compares with the oracle / the golden fixtures.  Integer work is bit-exact; the bf16 network is
+checked against the fp32 torch restatement at the stated tolerance and against the numpy emulation of the
+kernel's own dataflow at a much tighter one."""
+import numpy as np
+import pytest
+
+from conftest import golden_files, load_golden, random_play_boards, randomise_bn
+
+pytestmark = pytest.mark.gpu
+
+
+def _code(e):
+    return np.where(e == 0.0001, 2, e).astype(np.int8)
+
+
+@pytest.fixture(scope="module")
+def eng(yy):
+    from yinyang_game_alphazero_b200 import engine
+    return engine
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 probe
+@pytest.mark.parametrize("N,K,off", [(128, 64, 0), (128, 128, 0), (64, 64, 0), (128, 64, 8), (128, 64, 1),
+                                      (128, 64, 9), (128, 64, 23), (256, 32, 5), (16, 16, 3)])
+def test_umma_descriptor_probe(yy, N, K, off):
+    """C = A[off:off+128] @ B^T on tcgen05 with the tower kernel's no-swizzle K-major descriptors, including
+    start addresses that are NOT multiples of 8 rows (what a 3x3 tap shift produces)."""
+    import ctypes
+    import torch
+    rows = 160
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + K + off)
+    A = (torch.randn(rows, K, generator=g)).to(torch.bfloat16).cuda()
+    B = (torch.randn(N, K, generator=g)).to(torch.bfloat16).cuda()
+    C = torch.zeros(128, N, dtype=torch.float32, device="cuda")
+    lib = yy._lib.lib()
+    rc = lib.yy_probe_umma(ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()), ctypes.c_void_p(C.data_ptr()),
+                           rows, N, K, off, 0, None)
+    assert rc == 0, lib.yy_last_error()
+    torch.cuda.synchronize()
+    ref = A[off:off + 128].float() @ B.float().t()
+    err = (C - ref).abs().max().item()
+    assert err < 1e-3 * max(1.0, ref.abs().max().item()), err
+
+
+# ------------------------------------------------------------------------------------------------ rules
+@pytest.mark.parametrize("name", golden_files("rules_"))
+def test_rules_match_reference_golden(eng, name):
+    g = load_golden(name)
+    n, m, B = int(g["n"]), int(g["m"]), g["boards"]
+    N = len(B)
+    one = np.ones(N, np.int8)
+    assert np.array_equal(eng.legal_mask_host(B, one, n, m), g["mask_black"])
+    assert np.array_equal(eng.legal_mask_host(B, -one, n, m), g["mask_white"])
+    nb, npl = eng.next_state_host(B, g["players"], g["actions"], n, m)
+    assert np.array_equal(nb, g["next_boards"]) and np.array_equal(npl, g["next_players"])
+    assert np.array_equal(eng.ended_host(B, one, n, m), g["ended_black"])
+    assert np.array_equal(eng.ended_host(B, -one, n, m), g["ended_white"])
+
+
+@pytest.mark.parametrize("shape,flags", [((8, 8), 0), ((8, 8), 1), ((6, 6), 0), ((16, 16), 0), ((10, 10), 1), ((5, 7), 0)])
+def test_env_step_matches_oracle(eng, oracle_mod, shape, flags):
+    n, m = shape
+    N = 4096 if n * m <= 64 else 512
+    rng = np.random.default_rng(7 + n)
+    boards, players = random_play_boards(oracle_mod, n, m, N, seed=11 + n)
+    arb = rng.random((N // 4, n, m))
+    boards[: N // 4] = np.where(arb < 0.2, 1, np.where(arb < 0.4, -1, 0))        # arbitrary (non-legal-play) boards too
+    masks_o = oracle_mod.legal_mask(boards, players, n, m, flags)
+    actions = np.array([rng.choice(np.flatnonzero(mk)) if mk.any() and rng.random() < 0.8 else rng.integers(-1, n * m)
+                        for mk in masks_o], dtype=np.int32)
+    mo, bo, po, ro = oracle_mod.env_step(boards, players, actions, n, m, flags)
+    mg, bg, pg, rg = eng.env_step_host(boards, players, actions, n, m, flags)
+    assert np.array_equal(mg, mo) and np.array_equal(bg, bo) and np.array_equal(pg, po) and np.array_equal(rg, ro)
+
+
+def test_env_step_full_config2(eng, oracle_mod):
+    """BASELINE.json configs[1]: 65,536 synthetic random-play 8x8 boards (device generator), whole set checked
+    bit-exact against the C oracle; plus empty and ragged (count = 1, 0) batches."""
+    import torch
+    n = m = 8
+    N = 65536
+    plies = torch.arange(N, dtype=torch.int32) % 52
+    black, white, players = eng.random_playout(N, plies, n, m, seed=0xC0FFEE)
+    bl, wh = black.cpu().numpy().view(np.uint64), white.cpu().numpy().view(np.uint64)
+    from yinyang_game_alphazero_b200 import bitboard
+    boards = bitboard.unpack_boards(bl, wh, n, m)
+    pl = players.cpu().numpy()
+    stones = np.abs(boards).sum(axis=(1, 2))
+    assert stones.max() <= 51 and stones.mean() > 15                      # really are mid-game positions
+    assert np.all((boards == 1).sum(axis=(1, 2)) >= (boards == -1).sum(axis=(1, 2)) - 26)
+    masks_o = oracle_mod.legal_mask(boards, pl, n, m)
+    rng = np.random.default_rng(0)
+    actions = np.array([rng.choice(np.flatnonzero(mk)) if mk.any() else -1 for mk in masks_o], dtype=np.int32)
+    mo, bo, po, ro = oracle_mod.env_step(boards, pl, actions, n, m)
+    act_d = torch.from_numpy(actions).cuda()
+    mask_d, res_d = eng.env_step(black, white, players, act_d, n, m)
+    assert np.array_equal(bitboard.unpack_bits(mask_d.cpu().numpy().view(np.uint64), n, m), mo)
+    assert np.array_equal(bitboard.unpack_boards(black.cpu().numpy().view(np.uint64), white.cpu().numpy().view(np.uint64), n, m), bo)
+    assert np.array_equal(players.cpu().numpy(), po)
+    assert np.array_equal(eng.result_from_code(res_d.cpu().numpy()), ro)
+    for cnt in (0, 1):
+        out = eng.env_step_host(boards[:cnt], pl[:cnt], actions[:cnt], n, m)
+        assert out[0].shape[0] == cnt
+
+
+# ------------------------------------------------------------------------------------------------ MCTS (deterministic-prior mode)
+@pytest.mark.parametrize("name", golden_files("mcts_"))
+def test_mcts_visit_counts_match_reference_golden(eng, name):
+    g = load_golden(name)
+    n, m = int(g["n"]), int(g["m"])
+    e = eng.Engine(rows=n, cols=m, n_games=1, n_sims=int(g["sims"]), evaluator="stub", cpuct=float(g["cpuct"]))
+    noise = [g["noise"]] if g["noise"].size else None
+    counts, cw = e.search_host(g["board"][None], np.array([int(g["player"])], np.int8), noise=noise)
+    assert np.array_equal(counts[0], g["counts"])
+    assert np.array_equal(cw[0], g["child_w"])                            # float32 value sums, bit for bit
+    e.close()
+
+
+@pytest.mark.parametrize("shape,sims,games", [((8, 8), 200, 96), ((6, 6), 150, 64), ((4, 4), 300, 64), ((16, 16), 40, 8)])
+def test_mcts_matches_oracle_many_games(eng, oracle_mod, shape, sims, games):
+    n, m = shape
+    boards, players = random_play_boards(oracle_mod, n, m, games, seed=5 + n)
+    rng = np.random.default_rng(1)
+    noise = []
+    for i in range(games):
+        k = int(oracle_mod.legal_mask(boards[i][None], players[i:i + 1], n, m).sum())
+        noise.append(rng.dirichlet([0.3] * k) if (i % 3 == 0 and k > 0) else None)
+    e = eng.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="stub", cpuct=1.25)
+    counts, cw = e.search_host(boards, players, noise=noise)
+    for i in range(games):
+        r = oracle_mod.mcts_search(boards[i], int(players[i]), n, m, sims, cpuct=1.25, noise=noise[i])
+        assert np.array_equal(counts[i], r["counts"]), i
+        assert np.array_equal(cw[i], r["child_w"]), i
+    e.close()
+
+
+def test_mcts_external_evaluator_seam(eng, oracle_mod):
+    """The duck-typed predict seam: priors/values supplied by the caller each step (here: the oracle's stub,
+    computed on the host) must give the same visit counts as the fused stub evaluator."""
+    import torch
+    from yinyang_game_alphazero_b200 import bitboard
+    n = m = 6
+    games, sims = 8, 60
+    boards, players = random_play_boards(oracle_mod, n, m, games, seed=2)
+    e = eng.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="external")
+    b, w = bitboard.pack_boards(boards, n, m)
+    bd, wd = torch.from_numpy(b.view(np.int64)).cuda(), torch.from_numpy(w.view(np.int64)).cuda()
+    e.search_begin(bd, wd, torch.from_numpy(players).cuda())
+    active = games
+    steps = 0
+    while active:
+        lb, lw, act = e.leaf_batch()
+        leaf = bitboard.unpack_boards(lb.cpu().numpy().view(np.uint64), lw.cpu().numpy().view(np.uint64), n, m)
+        pr = np.zeros((games, n * m), np.float32); va = np.zeros(games, np.float32)
+        for i in range(games):
+            pr[i], va[i] = oracle_mod.stub_predict(leaf[i], n, m)
+        active = e.search_advance(torch.from_numpy(pr).cuda(), torch.from_numpy(va).cuda())
+        steps += 1
+        assert steps <= sims + 2
+    counts, _ = e.search_counts()
+    for i in range(games):
+        r = oracle_mod.mcts_search(boards[i], int(players[i]), n, m, sims)
+        assert np.array_equal(counts[i].cpu().numpy(), r["counts"])
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------ network
+@pytest.mark.parametrize("cfg", [(8, 8, 128, 10, 300), (6, 6, 128, 3, 64), (8, 8, 32, 2, 50), (16, 16, 128, 1, 9), (5, 7, 64, 2, 33)])
+def test_network_matches_fp32_reference(eng, oracle_mod, cfg):
+    """bf16 tcgen05 tower + heads vs (a) the numpy emulation of the same dataflow from the same packed image
+    (tolerance 4e-3: only fp32 summation order differs) and (b) the fp32 torch network (tolerance: logits
+    6e-2 abs at logit scale ~2-3, value 3e-2, top-1 agreement >= 90 %)."""
+    import torch
+    import emulate_tower as emu
+    from oracle import port
+    from yinyang_game_alphazero_b200 import weights
+    n, m, C, blocks, count = cfg
+    torch.manual_seed(0)
+    net = randomise_bn(port.build_net(n, m, C, blocks))
+    e = eng.Engine(rows=n, cols=m, n_games=max(count, 4), n_sims=1, evaluator="nn", state_dict=net.state_dict())
+    boards, _ = random_play_boards(oracle_mod, n, m, count, seed=9)
+    policy, value, logits = e.evaluate_host(boards, want_logits=True)
+    with torch.no_grad():
+        rl, rv = net(net.planes(boards))
+        rp = torch.softmax(rl, dim=1).numpy()
+    rl, rv = rl.numpy(), rv.numpy()[:, 0]
+    img = weights.pack_state_dict(net.state_dict(), n, m)
+    lay = weights.layout(n, m, C, blocks)
+    k = min(count, 24)
+    el, ev, _ = emu.forward(img, lay, n, m, blocks, boards[:k])
+    np.testing.assert_allclose(logits[:k], el, rtol=0, atol=4e-3)
+    np.testing.assert_allclose(value[:k], ev, rtol=0, atol=4e-3)
+    np.testing.assert_allclose(logits, rl, rtol=0, atol=6e-2)
+    np.testing.assert_allclose(value, rv, rtol=0, atol=3e-2)
+    np.testing.assert_allclose(policy.sum(axis=1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(policy, rp, rtol=0, atol=5e-3)
+    assert (logits.argmax(1) == rl.argmax(1)).mean() >= 0.9
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------ self-play driver
+def test_selfplay_records_match_oracle_search(eng, oracle_mod):
+    """Every replay record's visit counts must equal the oracle's search from that record's board (noise off,
+    stub evaluator), games must progress by legal single-stone moves, results must be terminal codes."""
+    n = m = 6
+    games, sims, moves = 24, 40, 30
+    e = eng.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="stub", dirichlet_epsilon=0.0, seed=123,
+                   search_as_black=False)
+    e.selfplay_run(moves)
+    st = e.stats()
+    assert st.moves == games * moves and st.examples == games * moves and st.overflow == 0
+    rp = e.replay()
+    assert rp["boards"].shape[0] == games * moves
+    for i in range(0, games * moves, 3):
+        r = oracle_mod.mcts_search(rp["boards"][i], int(rp["player"][i]), n, m, sims)
+        assert np.array_equal(rp["counts"][i].astype(np.int32), r["counts"]), i
+    # per-game trajectories: consecutive plies add exactly one stone of the mover's colour
+    order = np.lexsort((rp["ply"], rp["game_serial"]))
+    for a, b in zip(order[:-1], order[1:]):
+        if rp["game_serial"][a] == rp["game_serial"][b] and rp["ply"][b] == rp["ply"][a] + 1:
+            diff = rp["boards"][b].astype(int) - rp["boards"][a].astype(int)
+            assert np.abs(diff).sum() == 1 and diff.sum() == rp["player"][a]
+    assert st.games_finished > 0
+    z = rp["z"][rp["finished"]]
+    assert np.all(np.isin(z, [1.0, -1.0, 0.0001]))
+    fin = np.unique(rp["game_serial"][rp["finished"]])
+    assert len(fin) >= st.games_finished - games
+    e.close()
+
+
+def test_selfplay_reference_player_semantics(eng, oracle_mod):
+    """SURVEY Q5 (self_play.py:99,135-137,163): default mode searches every position as player 1 and applies
+    the chosen action with the real player -- an action illegal for the real player is silently dropped."""
+    n = m = 6
+    games, sims, moves = 16, 24, 12
+    e = eng.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="stub", dirichlet_epsilon=0.0, seed=5)
+    e.selfplay_run(moves)
+    rp = e.replay()
+    for i in range(0, games * moves, 5):
+        r = oracle_mod.mcts_search(rp["boards"][i], 1, n, m, sims)       # searched as black whatever the mover
+        assert np.array_equal(rp["counts"][i].astype(np.int32), r["counts"]), i
+    e.close()

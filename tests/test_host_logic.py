@@ -1,0 +1,154 @@
+"""CPU suite: bitboard packing, the product's bitboard rules header compiled for the host vs the oracle,
+C-ABI surface, weight packer + emulated tower dataflow vs the fp32 network.  No compute call needs a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_files, load_golden, randomise_bn
+
+
+def _host_rules(lib, bbm, boards, players, actions, n, m, flags=0, stub=False):
+    bl, wh = bbm.pack_boards(boards, n, m)
+    N, W = bl.shape[0], bbm.words_for(n, m)
+    players = np.ascontiguousarray(players, np.int8)
+    actions = np.ascontiguousarray(actions, np.int32)
+    mask, nb, nw = (np.zeros((N, W), np.uint64) for _ in range(3))
+    npl, ended = np.zeros(N, np.int8), np.zeros(N, np.int8)
+    st = np.zeros((N, n * m + 1), np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    rc = lib.yyh_rules(n, m, flags, p(bl), p(wh), p(players), p(actions), ctypes.c_long(N), p(mask), p(nb), p(nw),
+                       p(npl), p(ended), p(st) if stub else None)
+    assert rc == 0
+    return bbm.unpack_bits(mask, n, m), bbm.unpack_boards(nb, nw, n, m), npl, ended, st
+
+
+def _code(e):
+    return np.where(e == 0.0001, 2, e).astype(np.int8)
+
+
+def test_bitboard_roundtrip(yy):
+    rng = np.random.default_rng(0)
+    for n, m in [(4, 4), (6, 6), (8, 8), (5, 7), (16, 16), (9, 14)]:
+        b = rng.integers(-1, 2, size=(37, n, m)).astype(np.int8)
+        bl, wh = yy.bitboard.pack_boards(b, n, m)
+        assert bl.shape == (37, yy.bitboard.words_for(n, m))
+        assert np.array_equal(yy.bitboard.unpack_boards(bl, wh, n, m), b)
+        a = 3 * m + 2
+        assert ((int(bl[0, a >> 6]) >> (a & 63)) & 1) == int(b[0, 3, 2] == 1)   # bit a = action x*m+y
+
+
+@pytest.mark.parametrize("name", golden_files("rules_"))
+def test_bitboard_rules_match_reference(yy, host_rules_lib, name):
+    g = load_golden(name)
+    n, m, B = int(g["n"]), int(g["m"]), g["boards"]
+    N = len(B)
+    for pl, mk, ek in ((1, "mask_black", "ended_black"), (-1, "mask_white", "ended_white")):
+        mask, _, _, ended, _ = _host_rules(host_rules_lib, yy.bitboard, B, np.full(N, pl, np.int8), g["actions"], n, m)
+        assert np.array_equal(mask, g[mk]) and np.array_equal(ended, _code(g[ek]))
+    _, nb, npl, _, _ = _host_rules(host_rules_lib, yy.bitboard, B, g["players"], g["actions"], n, m)
+    assert np.array_equal(nb, g["next_boards"]) and np.array_equal(npl, g["next_players"])
+
+
+@pytest.mark.parametrize("shape", [(3, 3), (6, 6), (8, 8), (7, 9), (10, 10), (16, 16), (8, 32), (32, 8), (1, 5)])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_bitboard_rules_match_oracle_on_arbitrary_boards(yy, host_rules_lib, oracle_mod, shape, flags):
+    n, m = shape
+    rng = np.random.default_rng(n * 100 + m + flags)
+    N = 1500 if n * m <= 64 else 300
+    fill = rng.uniform(0, 1, size=(N, 1, 1))
+    r = rng.random((N, n, m))
+    B = np.where(r < fill / 2, 1, np.where(r < fill, -1, 0)).astype(np.int8)
+    pl = rng.choice([1, -1], size=N).astype(np.int8)
+    ac = rng.integers(-1, n * m + 1, size=N).astype(np.int32)          # includes out-of-range actions
+    mask, nb, npl, ended, st = _host_rules(host_rules_lib, yy.bitboard, B, pl, ac, n, m, flags, stub=True)
+    ac_o = np.where(ac >= n * m, -1, ac).astype(np.int32)
+    assert np.array_equal(mask, oracle_mod.legal_mask(B, pl, n, m, flags))
+    onb, onp = oracle_mod.next_state(B, pl, ac_o, n, m, flags)
+    assert np.array_equal(nb, onb) and np.array_equal(npl, onp)
+    assert np.array_equal(ended, _code(oracle_mod.game_ended(B, pl, n, m, flags)))
+    for i in range(20):
+        p, v = oracle_mod.stub_predict(B[i], n, m)
+        assert np.array_equal(st[i, :-1], p) and st[i, -1] == v
+
+
+def test_rowcol_rule_flag(oracle_mod):
+    """JS-only rule (yin_yang_game.js:338-384): completing a single-colour row is banned only with the flag."""
+    b = np.zeros((1, 4, 4), np.int8)
+    b[0, 0, :3] = 1
+    b[0, 1, 0] = -1
+    one = np.ones(1, np.int8)
+    assert oracle_mod.legal_mask(b, one, 4, 4, 0)[0, 3] == 1
+    assert oracle_mod.legal_mask(b, one, 4, 4, 1)[0, 3] == 0
+
+
+def test_abi_exports_every_declared_symbol(yy):
+    hdr = open(os.path.join(ROOT, "include", "yinyang_b200.h")).read()
+    declared = set(re.findall(r"\b(yy_[a-z0-9_]+)\s*\(", hdr))
+    declared |= {"yy_nn_weight_layout"}
+    lib = yy._lib.lib()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(yy._lib.SIGNATURES) >= declared - {"yy_nn_weight_layout"} | {"yy_nn_weight_layout"}
+    assert lib.yy_abi_version() == 1
+    assert ctypes.sizeof(yy._lib.EngineConfig) == 80
+
+
+def test_no_cpu_fallback(yy):
+    """Without a CUDA device every compute entry point must fail loudly (no silent CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = yy._lib.lib()
+    assert lib.yy_device_count() == 0
+    rc = lib.yy_legal_mask(8, 8, 0, None, None, None, None, 4, None)
+    assert rc == -3 and b"no CPU fallback" in lib.yy_last_error()
+    from yinyang_game_alphazero_b200 import engine
+    with pytest.raises(yy.YinYangError):
+        engine.Engine(rows=8, cols=8, n_games=1, n_sims=4)
+    with pytest.raises(yy.YinYangError):
+        engine.legal_mask_host(np.zeros((1, 8, 8), np.int8), np.ones(1, np.int8), 8, 8)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "yinyang-game-alphazero_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import oracle|from oracle)|#include\s*[\"<][^\n]*oracle|dlopen[^\n]*oracle",
+                                     src, flags=re.M), f
+
+
+@pytest.mark.parametrize("cfg", [(6, 6, 16, 2), (8, 8, 128, 1), (5, 7, 32, 1)])
+def test_weight_image_and_tower_dataflow(yy, oracle_mod, cfg):
+    """Packed image decoded + emulated flat-position tower (bf16 activations) vs the fp32 torch network.
+    Tolerance: logits 3e-2 abs (scale ~2), value 1.5e-2 -- bf16 rounding of weights and activations."""
+    import torch
+    import emulate_tower as emu
+    from conftest import random_play_boards
+    from oracle import port
+    from yinyang_game_alphazero_b200 import weights
+    n, m, C, blocks = cfg
+    torch.manual_seed(0)
+    net = randomise_bn(port.build_net(n, m, C, blocks))
+    img = weights.pack_state_dict(net.state_dict(), n, m)
+    lay = weights.layout(n, m, C, blocks)
+    assert img.size == lay["total"] == yy._lib.lib().yy_nn_weight_bytes(n, m, C, blocks)
+    boards, _ = random_play_boards(oracle_mod, n, m, 13, seed=3)
+    lg, v, _ = emu.forward(img, lay, n, m, blocks, boards)
+    with torch.no_grad():
+        rl, rv = net(net.planes(boards))
+    np.testing.assert_allclose(lg, rl.numpy(), rtol=0, atol=3e-2)
+    np.testing.assert_allclose(v, rv.numpy()[:, 0], rtol=0, atol=1.5e-2)
+    assert (lg.argmax(1) == rl.numpy().argmax(1)).mean() >= 0.9
+
+
+def test_bf16_rounding_helper(yy):
+    import torch
+    from yinyang_game_alphazero_b200 import weights
+    x = np.random.default_rng(0).standard_normal(4096).astype(np.float32)
+    ref = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(weights.to_bf16_bits(x), ref)

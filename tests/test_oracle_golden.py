@@ -1,0 +1,84 @@
+"""Pins the oracle (C restatement + Python port) against fixtures produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden_files, load_golden
+
+
+@pytest.mark.parametrize("name", golden_files("rules_"))
+def test_c_oracle_rules_match_reference(oracle_mod, name):
+    g = load_golden(name)
+    n, m, B = int(g["n"]), int(g["m"]), g["boards"]
+    N = len(B)
+    one = np.ones(N, np.int8)
+    assert np.array_equal(oracle_mod.legal_mask(B, one, n, m), g["mask_black"])
+    assert np.array_equal(oracle_mod.legal_mask(B, -one, n, m), g["mask_white"])
+    nb, npl = oracle_mod.next_state(B, g["players"], g["actions"], n, m)
+    assert np.array_equal(nb, g["next_boards"]) and np.array_equal(npl, g["next_players"])
+    assert np.array_equal(oracle_mod.game_ended(B, one, n, m), g["ended_black"])
+    assert np.array_equal(oracle_mod.game_ended(B, -one, n, m), g["ended_white"])
+
+
+@pytest.mark.parametrize("name", golden_files("mcts_"))
+def test_c_oracle_mcts_matches_reference(oracle_mod, name):
+    g = load_golden(name)
+    noise = g["noise"] if g["noise"].size else None
+    r = oracle_mod.mcts_search(g["board"], int(g["player"]), int(g["n"]), int(g["m"]), int(g["sims"]),
+                               cpuct=float(g["cpuct"]), noise=noise)
+    assert np.array_equal(r["counts"], g["counts"])
+    assert np.array_equal(r["child_w"], g["child_w"])          # float32 value sums, bit for bit
+    assert r["n_evals"] == int(g["n_evals"])
+
+
+def test_python_port_rules_match_reference():
+    from oracle import port
+    g = load_golden("rules_6x6.npz")
+    game = port.Game(6, 6)
+    for i in range(0, len(g["boards"]), 7):
+        b = port.Board(6, 6, g["boards"][i])
+        assert np.array_equal(game.getValidMoves(b, 1).astype(np.uint8), g["mask_black"][i])
+        assert np.array_equal(game.getValidMoves(b, -1).astype(np.uint8), g["mask_white"][i])
+        nb, npl = game.getNextState(b, int(g["players"][i]), int(g["actions"][i]))
+        assert np.array_equal(nb.board, g["next_boards"][i]) and npl == g["next_players"][i]
+        assert game.getGameEnded(b, 1) == g["ended_black"][i]
+
+
+@pytest.mark.parametrize("name", ["mcts_4x4_s300.npz", "mcts_6x6_s100_noise.npz", "mcts_4x4_s300_mid.npz"])
+def test_python_port_mcts_matches_reference(oracle_mod, name):
+    from oracle import port
+    g = load_golden(name)
+    n, m = int(g["n"]), int(g["m"])
+    noise = g["noise"] if g["noise"].size else None
+    counts, root = port.search(port.Game(n, m), port.HashStubNet(n, m), port.Board(n, m, g["board"]), int(g["player"]),
+                               int(g["sims"]), cpuct=float(g["cpuct"]), noise=noise)
+    assert np.array_equal(counts.astype(np.int32), g["counts"])
+
+
+@pytest.mark.parametrize("name", golden_files("net_"))
+def test_python_port_network_matches_reference(name):
+    import torch
+    from oracle import port
+    g = load_golden(name)
+    n, m = int(g["n"]), int(g["m"])
+    net = port.build_net(n, m, int(g["channels"]), int(g["blocks"]))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    net.load_state_dict(sd)
+    net.eval()
+    x = net.planes(g["boards"])
+    assert np.array_equal(x.numpy(), g["planes"])               # board_to_input, exact
+    with torch.no_grad():
+        lg, v = net(x)
+    np.testing.assert_allclose(lg.numpy(), g["logits"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(v.numpy()[:, 0], g["values"], rtol=0, atol=2e-6)
+    p, pv = net.predict(port.Board(n, m, g["boards"][3]))
+    np.testing.assert_allclose(p, g["policies"][3], rtol=0, atol=1e-6)
+
+
+def test_stub_evaluator_spec(oracle_mod):
+    """The hash stub used for the MCTS goldens (pure Python ints in make_golden.py) == the C one."""
+    g = load_golden("mcts_6x6_s400.npz")
+    pol, val = oracle_mod.stub_predict(g["board"], 6, 6)
+    assert pol.dtype == np.float32 and np.all(pol > 0) and np.all(pol <= 4096 / 65536)
+    assert np.all(pol * 65536 == np.round(pol * 65536))        # dyadic
+    assert -1.0 <= float(val) < 1.0 and float(val) * 65536 == round(float(val) * 65536)

@@ -1,0 +1,38 @@
+"""yinyang-game-alphazero_b200 -- B200-native batched AlphaZero self-play engine for the Yin-Yang game.
+
+A drop-in for the self-play hot path of Arash-san/YinYang-Game-AlphaZero (rules -> MCTS -> policy/value
+inference), written from scratch as hand-written sm_100a CUDA kernels behind a C ABI
+(``include/yinyang_b200.h``, ``lib/libyinyang_b200.so``).  The directory name contains a hyphen, so import
+it through the root-level shim::
+
+    import yy_b200                      # registers this package as ``yinyang_game_alphazero_b200``
+    from yinyang_game_alphazero_b200 import Engine, YinYangGame, MCTS
+
+Layout
+  csrc/        CUDA kernels + the C ABI (rules bitboards, HBM tree, tcgen05 inference)
+  _lib.py      nvcc build + ctypes binding
+  engine.py    device/host buffer API over the C ABI
+  weights.py   reference checkpoint -> packed bf16 weight image (BN folded)
+  game.py, mcts.py, self_play.py, players.py   host-side mirror of the reference's Python interface
+"""
+from . import _lib, bitboard  # noqa: F401
+from ._lib import YinYangError, build  # noqa: F401
+
+__all__ = ["build", "YinYangError", "bitboard"]
+
+
+def __getattr__(name):
+    # torch-dependent modules are imported lazily so that `build()` works in a bare interpreter
+    import importlib
+    for mod in ("engine", "game", "mcts", "self_play", "players", "weights", "distributed"):
+        try:
+            m = importlib.import_module(f"{__name__}.{mod}")
+        except ModuleNotFoundError as e:
+            if e.name and e.name.endswith(mod):
+                continue
+            raise
+        if name == mod:
+            return m
+        if hasattr(m, name):
+            return getattr(m, name)
+    raise AttributeError(name)

@@ -1,0 +1,217 @@
+// yy_gemm.cu -- tcgen05 GEMM building block: C[M,N] = act(A[M,K] * B[N,K]^T + bias), bf16 in, fp32 accumulate
+// in TMEM.  Used for the policy / value fully-connected heads (neural_network.py:113-121) and, through
+// yy_probe_umma, as the self-test that pins the shared-memory descriptor conventions of the tower kernel.
+//
+// Operands are plain row-major in global memory; cp.async (16 B = 8 bf16 along K) scatters them into the
+// no-swizzle K-major core-matrix layout [k/8][row][8] in shared memory, which is exactly what the UMMA
+// descriptor (yy_ptx.cuh: smem_desc) describes with LBO = rows*16 and SBO = 128.
+#include <cuda_bf16.h>
+
+#include "yy_common.cuh"
+#include "yy_gemm.cuh"
+#include "yy_ptx.cuh"
+
+namespace yy {
+using namespace ptx;
+
+// ------------------------------------------------------------------------------------------------ probe
+// Single CTA, everything resident: C[128,N] = A[row_off : row_off+128, :] * B^T.  rowsA >= row_off + 128.
+__global__ void __launch_bounds__(128) probe_umma_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                                                        float* __restrict__ C, int rowsA, int N, int K, int row_off, int swap) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int KC = K / 8;
+  uint8_t* a_s = smem;
+  uint8_t* b_s = smem + (size_t)KC * rowsA * 16;
+  for (int i = threadIdx.x; i < KC * rowsA; i += blockDim.x) {
+    int kc = i / rowsA, r = i % rowsA;
+    *reinterpret_cast<uint4*>(a_s + (size_t)i * 16) = *reinterpret_cast<const uint4*>(A + (size_t)r * K + kc * 8);
+  }
+  for (int i = threadIdx.x; i < KC * N; i += blockDim.x) {
+    int kc = i / N, r = i % N;
+    *reinterpret_cast<uint4*>(b_s + (size_t)i * 16) = *reinterpret_cast<const uint4*>(B + (size_t)r * K + kc * 8);
+  }
+  uint32_t ncols = 32; while ((int)ncols < N) ncols <<= 1;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&tmem_base_s), ncols);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = idesc_bf16(128, N);
+    for (int k16 = 0; k16 < K / 16; ++k16) {
+      uint32_t a_addr = smem_u32(a_s) + (uint32_t)((2 * k16 * rowsA + row_off) * 16);
+      uint32_t b_addr = smem_u32(b_s) + (uint32_t)(2 * k16 * N * 16);
+      uint64_t ad = swap ? smem_desc(a_addr, 128, rowsA * 16) : smem_desc(a_addr, rowsA * 16, 128);
+      uint64_t bd = swap ? smem_desc(b_addr, 128, N * 16) : smem_desc(b_addr, N * 16, 128);
+      tc_mma_bf16(tmem_base, ad, bd, idesc, k16 > 0 ? 1u : 0u);
+    }
+    tc_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < N; c += 16) {
+    uint32_t r[16];
+    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, r);
+    tc_wait_ld();
+    for (int j = 0; j < 16; ++j) C[(size_t)row * N + c + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------ tiled GEMM
+// grid = (ceil(M/128), N/BN).  128 threads.  BK = 64 per stage, 3-stage cp.async ring; thread 0 issues the
+// MMAs and frees a stage with tcgen05.commit; all four warps drain TMEM in the epilogue.
+constexpr int kGemmBK = 64;
+constexpr int kGemmStages = 3;
+
+template <int BN>
+__global__ void __launch_bounds__(128) gemm_bf16_tn_kernel(GemmArgs g) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mma_done[kGemmStages];
+  __shared__ __align__(8) uint64_t acc_done;
+  __shared__ uint32_t tmem_base_s;
+  constexpr int A_STAGE = (kGemmBK / 8) * 128 * 16;  // 16 KB
+  constexpr int B_STAGE = (kGemmBK / 8) * BN * 16;
+  uint8_t* a_s = smem;
+  uint8_t* b_s = smem + kGemmStages * A_STAGE;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t NCOLS = BN < 32 ? 32 : BN;
+  if (tid == 0) {
+    for (int s = 0; s < kGemmStages; ++s) mbar_init(smem_u32(&mma_done[s]), 1);
+    mbar_init(smem_u32(&acc_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), NCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int nkb = (g.K + kGemmBK - 1) / kGemmBK;
+
+  auto load_stage = [&](int kb, int s) {
+    const int k0 = kb * kGemmBK;
+    // A: 8 k-chunks x 128 rows of 16 B; thread t handles row t for all 8 chunks (coalescing is per row:
+    // 128 B contiguous per thread, rows lda apart -- fine for L2-resident operands).
+    {
+      const int r = tid;
+      const bool rv = (m0 + r) < g.M;
+      const __nv_bfloat16* src = g.A + (size_t)(rv ? (m0 + r) : 0) * g.lda + k0;
+#pragma unroll
+      for (int kc = 0; kc < kGemmBK / 8; ++kc)
+        cp_async16(smem_u32(a_s + s * A_STAGE + (kc * 128 + r) * 16), src + kc * 8, rv && (k0 + kc * 8) < g.K);
+    }
+    for (int r = tid; r < BN; r += 128) {
+      const bool rv = (n0 + r) < g.N;
+      const __nv_bfloat16* src = g.B + (size_t)(rv ? (n0 + r) : 0) * g.ldb + k0;
+#pragma unroll
+      for (int kc = 0; kc < kGemmBK / 8; ++kc)
+        cp_async16(smem_u32(b_s + s * B_STAGE + (kc * BN + r) * 16), src + kc * 8, rv && (k0 + kc * 8) < g.K);
+    }
+    cp_async_commit();
+  };
+
+  // prologue
+  for (int p = 0; p < kGemmStages - 1; ++p) { if (p < nkb) load_stage(p, p); else cp_async_commit(); }
+  uint32_t done_phase[kGemmStages] = {0, 0, 0};
+  const uint32_t idesc = idesc_bf16(128, BN);
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % kGemmStages;
+    // issue the load for k-block kb + stages - 1 into the stage that k-block kb-1 used
+    {
+      const int nk = kb + kGemmStages - 1, ns = nk % kGemmStages;
+      if (nk < nkb) {
+        if (kb >= 1) { mbar_wait(smem_u32(&mma_done[ns]), done_phase[ns]); done_phase[ns] ^= 1; }
+        load_stage(nk, ns);
+      } else {
+        cp_async_commit();
+      }
+    }
+    cp_async_wait<kGemmStages - 1>();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k16 = 0; k16 < kGemmBK / 16; ++k16) {
+        uint64_t ad = smem_desc(smem_u32(a_s + s * A_STAGE) + 2 * k16 * 128 * 16, 128 * 16, 128);
+        uint64_t bd = smem_desc(smem_u32(b_s + s * B_STAGE) + 2 * k16 * BN * 16, BN * 16, 128);
+        tc_mma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+      }
+      tc_commit(smem_u32(&mma_done[s]));
+      if (kb == nkb - 1) tc_commit(smem_u32(&acc_done));
+    }
+  }
+  mbar_wait(smem_u32(&acc_done), 0);
+  tc_fence_after();
+  const int row = m0 + warp * 32 + lane;
+  for (int c = 0; c < BN; c += 16) {
+    uint32_t r[16];
+    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, r);
+    tc_wait_ld();
+    if (row < g.M) {
+      float out[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float v = __uint_as_float(r[j]);
+        if (g.bias) v += g.bias[n0 + c + j];
+        if (g.relu) v = fmaxf(v, 0.0f);
+        out[j] = v;
+      }
+      float4* dst = reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n0 + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, NCOLS);
+}
+
+template <int BN>
+static int launch_gemm(const GemmArgs& g, cudaStream_t s) {
+  constexpr int smem = kGemmStages * ((kGemmBK / 8) * 128 * 16 + (kGemmBK / 8) * BN * 16);
+  static bool attr_done = false;
+  if (!attr_done) {
+    YY_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)(g.N / BN));
+  gemm_bf16_tn_kernel<BN><<<grid, 128, smem, s>>>(g);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int gemm_bf16_tn(const GemmArgs& g, cudaStream_t s) {
+  if (g.M <= 0) return YY_OK;
+  if (g.K % 8 || g.lda % 8 || g.ldb % 8 || g.ldc % 4) return set_error(YY_ERR_INVALID, "gemm: K, lda, ldb must be multiples of 8, ldc of 4");
+  if (g.N % 64 == 0) return launch_gemm<64>(g, s);
+  if (g.N % 32 == 0) return launch_gemm<32>(g, s);
+  if (g.N % 16 == 0) return launch_gemm<16>(g, s);
+  return set_error(YY_ERR_INVALID, "gemm: N must be a multiple of 16 (got %d)", g.N);
+}
+
+}  // namespace yy
+
+extern "C" int yy_probe_umma(const void* a, const void* b, float* c, int M, int N, int K, int a_row_offset,
+                             int swap_lbo_sbo, void* stream) {
+  using namespace yy;
+  if (yy_device_count() == 0) return set_error(YY_ERR_NO_DEVICE, "no CUDA device");
+  if (M < 128 + a_row_offset || a_row_offset < 0) return set_error(YY_ERR_INVALID, "probe: A needs a_row_offset+128 rows");
+  if (N < 16 || N > 256 || N % 16 || K < 16 || K % 16) return set_error(YY_ERR_INVALID, "probe: N in [16,256] step 16, K multiple of 16");
+  size_t smem = (size_t)(K / 8) * 16 * ((size_t)M + N);
+  if (smem > 200 * 1024) return set_error(YY_ERR_INVALID, "probe: operands too large for one CTA");
+  YY_CUDA_OK(cudaFuncSetAttribute(probe_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, c, M, N, K,
+                                                            a_row_offset, swap_lbo_sbo);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}

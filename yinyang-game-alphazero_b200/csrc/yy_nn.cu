@@ -1,0 +1,449 @@
+// yy_nn.cu -- bf16 tcgen05 inference of the reference policy/value network on a batch of leaf boards.
+//
+// Network (src/yin_yang/ai/neural_network.py:39-123, eval mode, BatchNorm folded into the convolutions by
+// the host packer):  board_to_input (:156-196) -> conv3x3(5->C)+ReLU -> blocks x [conv3x3+ReLU, conv3x3 +
+// skip + ReLU] -> {policy: conv1x1(C->32)+ReLU -> FC(32A->A)} , {value: conv1x1(C->32)+ReLU -> FC(32A->256)
+// +ReLU -> FC(256->1) -> tanh};  predict() applies softmax over all A logits (:152).
+//
+// Kernel 1  tower_kernel (this file's hot spot; >99 % of the FLOPs):
+//   One persistent CTA per SM walks "groups" of boards.  A group is laid out as a flat list of up to 512
+//   padded positions: each board contributes (n+1) x (m+1) positions -- its n x m cells plus one zero column
+//   on the right and one zero row below -- so that the 3x3 tap (dy,dx) of EVERY position is the position
+//   dy*(m+1)+dx further along the list and zero padding comes for free.  The whole residual tower runs with
+//   the group's activations resident in shared memory ([C/8 chunks][560 rows][8 ch] bf16 = no-swizzle
+//   K-major core matrices, so a tap shift is just a +16 B/row move of the UMMA descriptor start address);
+//   only the weights stream in (16 KB stages, cp.async.bulk into a 5-deep mbarrier ring, shared by the 4
+//   M=128 tiles of the group).  Accumulators live in TMEM (4 tiles x 128 fp32 columns = all 512 columns).
+//   The skip connection never touches shared memory: conv1's epilogue re-loads the block input into the
+//   TMEM accumulator (tcgen05.st) before overwriting it in place, and conv2 accumulates on top of it.
+//   Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one thread), warps 2-9 = epilogue.
+//   Roofline: tensor.  Algorithmic FLOPs per board: 2*A*(9*16*C + blocks*2*9*C*C + C*64)  (+ FC heads).
+// Kernel 2/3  gemm_bf16_tn (yy_gemm.cu): policy FC and value FC1 on tensor cores over the whole batch.
+// Kernel 4  heads_finish_kernel: softmax, value FC2 + tanh.
+#include <cuda_bf16.h>
+
+#include "yy_gemm.cuh"
+#include "yy_nn.cuh"
+#include "yy_ptx.cuh"
+
+namespace yy {
+using namespace ptx;
+
+constexpr int TW_C = 128;              // tower width the kernel is specialised for (narrower nets are zero-padded)
+constexpr int TW_CHUNKS = TW_C / 8;    // 16-byte channel chunks per position
+constexpr int TW_HEADC = 64;           // policy 32 + value 32 head-conv channels
+constexpr int TW_INC = 16;             // stem input channels after padding (K = 16 per tap)
+constexpr int TW_MAXT = 4;             // tiles (of 128 positions) per group
+constexpr int TW_PAD = 24;             // zero rows before/after the group's positions (>= m+2)
+constexpr int TW_ROWS = 128 * TW_MAXT + 2 * TW_PAD;  // 560
+constexpr int TW_STAGES = 5;
+constexpr int TW_STAGE_BYTES = 16384;
+constexpr int TW_THREADS = 320;
+constexpr int TW_EPI_THREADS = 256;
+
+constexpr int SM_ACT = 0;
+constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 143360
+constexpr int SM_POS = SM_RING + TW_STAGES * TW_STAGE_BYTES;          // 225280
+constexpr int SM_BAR = SM_POS + 128 * TW_MAXT * 2;                    // 226304
+constexpr int SM_TMEM = SM_BAR + 8 * (2 * TW_STAGES + 2);
+constexpr int SM_TOTAL = SM_TMEM + 16;
+
+struct TowerGeo {
+  int n, m, A, W, pitch, PB;  // PB = padded positions per board
+  int T, Gb;                  // tiles per group, boards per group
+  int blocks;
+};
+
+struct TowerArgs {
+  TowerGeo g;
+  const uint8_t* conv_stream;  // stage-ordered bf16 weight blocks
+  const float* conv_bias;      // [1 + 2*blocks][128] then head [64]
+  const uint64_t* black; const uint64_t* white;
+  long long count;
+  int n_groups;
+  __nv_bfloat16* headfeat;     // [count][64*A], index c*A + cell (matches .view(-1, 32*n*m), neural_network.py:112,117)
+};
+
+// ---- weight-stream geometry shared by producer and MMA issuer ----
+struct LayerInfo { int n_stages, stage_bytes, nk16, N; long long stream_off; };
+__host__ __device__ inline LayerInfo layer_info(int l, int blocks) {
+  LayerInfo li;
+  const long long stem = 9ll * (2 * 128 * 16);
+  if (l == 0) { li.n_stages = 9; li.stage_bytes = 2 * 128 * 16; li.nk16 = 1; li.N = 128; li.stream_off = 0; }
+  else if (l <= 2 * blocks) { li.n_stages = 18; li.stage_bytes = TW_STAGE_BYTES; li.nk16 = 4; li.N = 128; li.stream_off = stem + (long long)(l - 1) * 18 * TW_STAGE_BYTES; }
+  else { li.n_stages = 2; li.stage_bytes = 8 * TW_HEADC * 16; li.nk16 = 4; li.N = TW_HEADC; li.stream_off = stem + (long long)(2 * blocks) * 18 * TW_STAGE_BYTES; }
+  return li;
+}
+__host__ __device__ inline long long conv_stream_bytes(int blocks) {
+  LayerInfo li = layer_info(2 * blocks + 1, blocks);
+  return li.stream_off + (long long)li.n_stages * li.stage_bytes;
+}
+// stage j of layer l: which 3x3 tap and which first activation chunk it covers
+__device__ __forceinline__ void stage_info(int l, int j, int blocks, int pitch, int& tapshift, int& chunk0) {
+  int tap, slab;
+  if (l == 0) { tap = j; slab = 0; }
+  else if (l <= 2 * blocks) { tap = j >> 1; slab = j & 1; }
+  else { tap = 4; slab = j; }
+  tapshift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
+  chunk0 = slab * 8;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const TowerGeo& g = a.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = 2 * g.blocks + 2;  // stem + 2*blocks tower convs + head conv
+  int16_t* pos_tab = reinterpret_cast<int16_t*>(smem + SM_POS);
+  const uint32_t bar0 = smem_u32(smem + SM_BAR);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (TW_STAGES + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * TW_STAGES), act_ready = bar0 + 8u * (2 * TW_STAGES + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
+
+  // ---- one-time setup ----
+  for (int i = tid; i < TW_CHUNKS * TW_ROWS * 4; i += TW_THREADS) reinterpret_cast<uint32_t*>(smem + SM_ACT)[i] = 0u;
+  for (int p = tid; p < 128 * TW_MAXT; p += TW_THREADS) {
+    int v = -1;
+    int b = p / g.PB, rem = p % g.PB, y = rem / g.pitch, x = rem % g.pitch;
+    if (b < g.Gb && y < g.n && x < g.m) v = b * 256 + y * g.m + x;
+    pos_tab[p] = (int16_t)v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < TW_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(act_ready, TW_EPI_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t act_base = smem_u32(smem + SM_ACT);
+  const uint32_t ring_base = smem_u32(smem + SM_RING);
+
+  if (warp == 0) {
+    // =========================================================== weight producer (one thread)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+        for (int l = 0; l < L; ++l) {
+          const LayerInfo li = layer_info(l, g.blocks);
+          for (int j = 0; j < li.n_stages; ++j, ++it) {
+            const uint32_t slot = it % TW_STAGES;
+            if (it >= TW_STAGES) mbar_wait(empty_bar(slot), ((it / TW_STAGES) - 1) & 1);
+            mbar_arrive_expect_tx(full_bar(slot), (uint32_t)li.stage_bytes);
+            bulk_g2s(ring_base + slot * TW_STAGE_BYTES, a.conv_stream + li.stream_off + (long long)j * li.stage_bytes,
+                     (uint32_t)li.stage_bytes, full_bar(slot));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t it = 0, act_phase = 0;
+      for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+        for (int l = 0; l < L; ++l) {
+          const LayerInfo li = layer_info(l, g.blocks);
+          const bool preloaded = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 0);  // conv2: accumulator holds the skip input
+          const uint32_t idesc = idesc_bf16(128, li.N);
+          mbar_wait(act_ready, act_phase); act_phase ^= 1;
+          tc_fence_after();
+          for (int j = 0; j < li.n_stages; ++j, ++it) {
+            const uint32_t slot = it % TW_STAGES;
+            int tapshift, chunk0;
+            stage_info(l, j, g.blocks, g.pitch, tapshift, chunk0);
+            mbar_wait(full_bar(slot), (it / TW_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t b_stage = ring_base + slot * TW_STAGE_BYTES;
+            for (int t = 0; t < g.T; ++t) {
+              const uint32_t a_row = act_base + (uint32_t)((TW_PAD + t * 128 + tapshift) * 16);
+              for (int k = 0; k < li.nk16; ++k) {
+                const uint64_t ad = smem_desc(a_row + (uint32_t)((chunk0 + 2 * k) * TW_ROWS * 16), TW_ROWS * 16, 128);
+                const uint64_t bd = smem_desc(b_stage + (uint32_t)(2 * k * li.N * 16), (uint32_t)li.N * 16, 128);
+                tc_mma_bf16(tmem_base + (uint32_t)(t * 128), ad, bd, idesc, (preloaded || j > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            tc_commit(empty_bar(slot));
+          }
+          tc_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    // =========================================================== epilogue warps (2..9)
+    const int ew = warp - 2;
+    const int quarter = warp & 3;        // TMEM lanes a warp may touch: 32*(warp_id % 4) ..
+    const int set = ew >> 2;             // tiles set, set+2
+    uint32_t acc_phase = 0;
+    uint8_t* act = smem + SM_ACT;
+    for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+      // ---- stem input planes (board_to_input, neural_network.py:156-196) for my rows ----
+      for (int t = set; t < g.T; t += 2) {
+        const int p = t * 128 + quarter * 32 + lane;
+        const int info = pos_tab[p];
+        uint4 c0 = make_uint4(0, 0, 0, 0);
+        const long long board = (long long)grp * g.Gb + (info >= 0 ? (info >> 8) : 0);
+        if (info >= 0 && board < a.count) {
+          const int cell = info & 255, y = cell / g.m, x = cell % g.m;
+          const uint64_t* bb = a.black + board * g.W; const uint64_t* wb = a.white + board * g.W;
+          auto bit = [&](const uint64_t* v, int c) { return (int)((v[c >> 6] >> (c & 63)) & 1ull); };
+          const int isb = bit(bb, cell), isw = bit(wb, cell);
+          int rc = 0, cc = 0;
+          for (int xx = 0; xx < g.m; ++xx) { int c = y * g.m + xx; rc += bit(bb, c) | bit(wb, c); }
+          for (int yy = 0; yy < g.n; ++yy) { int c = yy * g.m + x; cc += bit(bb, c) | bit(wb, c); }
+          const float rf = (float)((double)rc / (double)g.m), cf = (float)((double)cc / (double)g.n);
+          const float rf_hi = __bfloat162float(__float2bfloat16_rn(rf)), cf_hi = __bfloat162float(__float2bfloat16_rn(cf));
+          // channels: 0 empty, 1 black, 2 white, 3 row fill, 4 col fill, 5/6 = bf16 residuals of 3/4 (same weights)
+          c0.x = pack_bf16x2((isb | isw) ? 0.0f : 1.0f, isb ? 1.0f : 0.0f);
+          c0.y = pack_bf16x2(isw ? 1.0f : 0.0f, rf_hi);
+          c0.z = pack_bf16x2(cf_hi, rf - rf_hi);
+          c0.w = pack_bf16x2(cf - cf_hi, 0.0f);
+        }
+        *reinterpret_cast<uint4*>(act + (size_t)(0 * TW_ROWS + TW_PAD + p) * 16) = c0;
+        *reinterpret_cast<uint4*>(act + (size_t)(1 * TW_ROWS + TW_PAD + p) * 16) = make_uint4(0, 0, 0, 0);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(act_ready);
+
+      for (int l = 0; l < L; ++l) {
+        const bool is_head = (l == L - 1);
+        const bool is_conv1 = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 1);
+        const float* bias = a.conv_bias + (size_t)l * TW_C;
+        mbar_wait(acc_full, acc_phase); acc_phase ^= 1;
+        tc_fence_after();
+        for (int t = set; t < g.T; t += 2) {
+          const int p = t * 128 + quarter * 32 + lane;
+          const int info = pos_tab[p];
+          const long long board = (long long)grp * g.Gb + (info >= 0 ? (info >> 8) : 0);
+          const bool real = info >= 0 && board < a.count;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 128);
+          uint8_t* rowp = act + (size_t)(TW_PAD + p) * 16;
+          if (!is_head) {
+#pragma unroll 1
+            for (int cc = 0; cc < TW_C / 16; ++cc) {
+              uint32_t r[16];
+              tc_ld16(taddr + cc * 16, r);
+              tc_wait_ld();
+              uint4* d0 = reinterpret_cast<uint4*>(rowp + (size_t)(2 * cc) * TW_ROWS * 16);
+              uint4* d1 = reinterpret_cast<uint4*>(rowp + (size_t)(2 * cc + 1) * TW_ROWS * 16);
+              if (is_conv1) {  // skip connection: park the block input in the accumulator conv2 will add to
+                const uint4 x0 = *d0, x1 = *d1;
+                uint32_t xr[16];
+                const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { xr[2 * q] = xs[q] << 16; xr[2 * q + 1] = xs[q] & 0xffff0000u; }
+                tc_st16(taddr + cc * 16, xr);
+              }
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = real ? fmaxf(__uint_as_float(r[j]) + __ldg(bias + cc * 16 + j), 0.0f) : 0.0f;
+              *d0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              *d1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+            }
+            if (is_conv1) tc_wait_st();
+          } else {
+            __nv_bfloat16* dst = a.headfeat + (size_t)board * (TW_HEADC * g.A) + (info & 255);
+#pragma unroll 1
+            for (int cc = 0; cc < TW_HEADC / 16; ++cc) {
+              uint32_t r[16];
+              tc_ld16(taddr + cc * 16, r);
+              tc_wait_ld();
+              if (real) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  dst[(size_t)(cc * 16 + j) * g.A] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + __ldg(bias + cc * 16 + j), 0.0f));
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        if (!is_head) { fence_proxy_async_smem(); mbar_arrive(act_ready); }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// softmax over all A logits (neural_network.py:152) and value FC2 + tanh (:121).  One warp per board.
+__global__ void __launch_bounds__(128) heads_finish_kernel(const float* __restrict__ logits_buf, int ld_logits,
+                                                          const float* __restrict__ hidden, const float* __restrict__ w2,
+                                                          const float* __restrict__ b2, long long count, int A,
+                                                          float* __restrict__ policy, float* __restrict__ value,
+                                                          float* __restrict__ logits_out) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= count) return;
+  const float* lg = logits_buf + i * ld_logits;
+  float mx = -INFINITY;
+  for (int a = lane; a < A; a += 32) mx = fmaxf(mx, lg[a]);
+  for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float sum = 0.0f;
+  for (int a = lane; a < A; a += 32) sum += expf(lg[a] - mx);
+  for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  for (int a = lane; a < A; a += 32) {
+    policy[i * A + a] = expf(lg[a] - mx) / sum;
+    if (logits_out) logits_out[i * A + a] = lg[a];
+  }
+  float acc = 0.0f;
+  for (int k = lane; k < 256; k += 32) acc += hidden[i * 256 + k] * w2[k];
+  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) value[i] = tanhf(acc + b2[0]);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct WeightLayout {
+  int64_t conv_stream, conv_bias, fc_policy_w, fc_policy_b, fc_value1_w, fc_value1_b, fc_value2_w, fc_value2_b, total;
+  int a_pad;
+};
+static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+static WeightLayout weight_layout(int rows, int cols, int blocks) {
+  WeightLayout w;
+  const int A = rows * cols;
+  w.a_pad = (A + 15) / 16 * 16;
+  int64_t off = 0;
+  w.conv_stream = off; off = align256(off + conv_stream_bytes(blocks));
+  w.conv_bias = off; off = align256(off + (int64_t)((2 * blocks + 1) * TW_C + TW_HEADC) * 4);
+  w.fc_policy_w = off; off = align256(off + (int64_t)w.a_pad * 32 * A * 2);
+  w.fc_policy_b = off; off = align256(off + (int64_t)w.a_pad * 4);
+  w.fc_value1_w = off; off = align256(off + (int64_t)256 * 32 * A * 2);
+  w.fc_value1_b = off; off = align256(off + 256 * 4);
+  w.fc_value2_w = off; off = align256(off + 256 * 4);
+  w.fc_value2_b = off; off = align256(off + 4);
+  w.total = off;
+  return w;
+}
+
+static bool nn_geometry_ok(int rows, int cols) {
+  return rows >= 1 && cols >= 1 && cols + 2 <= TW_PAD && (rows + 1) * (cols + 1) <= 128 * TW_MAXT && rows * cols <= 256;
+}
+
+static TowerGeo make_tower_geo(int rows, int cols, int blocks) {
+  TowerGeo g;
+  g.n = rows; g.m = cols; g.A = rows * cols; g.W = words_for_cells(g.A); g.pitch = cols + 1; g.PB = (rows + 1) * (cols + 1);
+  g.blocks = blocks;
+  double best = -1.0; g.T = TW_MAXT; g.Gb = 1;
+  for (int T = 1; T <= TW_MAXT; ++T) {
+    int Gb = (128 * T) / g.PB;
+    if (Gb < 1) continue;
+    if (Gb > 127) Gb = 127;
+    double eff = (double)Gb * g.A / (128.0 * T);
+    if (eff >= best - 1e-12) { best = eff; g.T = T; g.Gb = Gb; }
+  }
+  return g;
+}
+
+int64_t nn_weight_bytes(int rows, int cols, int channels, int blocks) {
+  if (!nn_geometry_ok(rows, cols) || channels < 1 || channels > TW_C || blocks < 0)
+    return set_error(YY_ERR_INVALID, "network geometry unsupported: %dx%d, %d channels, %d blocks (need cols<=%d, channels<=%d)",
+                     rows, cols, channels, blocks, TW_PAD - 2, TW_C);
+  return weight_layout(rows, cols, blocks).total;
+}
+
+static void nn_scratch_layout(int rows, int cols, int max_boards, int64_t& headfeat, int64_t& logits, int64_t& hidden, int64_t& total) {
+  const int A = rows * cols, a_pad = (A + 15) / 16 * 16;
+  int64_t off = 0;
+  headfeat = off; off = align256(off + (int64_t)max_boards * TW_HEADC * A * 2);
+  logits = off; off = align256(off + (int64_t)max_boards * a_pad * 4);
+  hidden = off; off = align256(off + (int64_t)max_boards * 256 * 4);
+  total = off;
+}
+
+size_t nn_workspace_bytes(const yy_engine_config& cfg) {
+  if (cfg.evaluator != YY_EVAL_NN) return 0;
+  int64_t a, b, c, total;
+  nn_scratch_layout(cfg.rows, cfg.cols, cfg.n_games, a, b, c, total);
+  return (size_t)total;
+}
+
+int nn_init(NNState& nn, const yy_engine_config& cfg, void* scratch) {
+  nn = NNState{};
+  nn.rows = cfg.rows; nn.cols = cfg.cols; nn.A = cfg.rows * cfg.cols; nn.W = words_for_cells(nn.A);
+  nn.channels = cfg.nn_channels; nn.blocks = cfg.nn_blocks; nn.max_boards = cfg.n_games; nn.device = cfg.device;
+  if (cfg.evaluator != YY_EVAL_NN) return YY_OK;
+  if (!nn_geometry_ok(cfg.rows, cfg.cols) || cfg.nn_channels > TW_C)
+    return set_error(YY_ERR_INVALID, "network geometry unsupported: %dx%d, %d channels", cfg.rows, cfg.cols, cfg.nn_channels);
+  nn.scratch = scratch; nn.scratch_bytes = (int64_t)nn_workspace_bytes(cfg);
+  YY_CUDA_OK(cudaDeviceGetAttribute(&nn.num_sms, cudaDevAttrMultiProcessorCount, cfg.device));
+  int major = 0;
+  YY_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cfg.device));
+  if (major != 10) return set_error(YY_ERR_NO_DEVICE, "the inference kernels are sm_100a-only (device reports sm_%d*)", major);
+  YY_CUDA_OK(cudaFuncSetAttribute(tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+  nn.attrs_set = true;
+  return YY_OK;
+}
+void nn_destroy(NNState&) {}
+
+int nn_load_weights(NNState& nn, const void* weights, int64_t bytes) {
+  int64_t need = nn_weight_bytes(nn.rows, nn.cols, nn.channels, nn.blocks);
+  if (need < 0) return (int)need;
+  if (!weights || bytes < need) return set_error(YY_ERR_INVALID, "weight image too small: %lld < %lld", (long long)bytes, (long long)need);
+  if (((uintptr_t)weights & 255) != 0) return set_error(YY_ERR_INVALID, "weight image must be 256-byte aligned");
+  nn.weights = weights; nn.weight_bytes = bytes;
+  return YY_OK;
+}
+
+int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_t count, float* policy, float* value,
+               float* logits, cudaStream_t s) {
+  if (!nn.attrs_set) return set_error(YY_ERR_STATE, "engine was not created with the NN evaluator");
+  if (!nn.weights) return set_error(YY_ERR_STATE, "no weights loaded (yy_engine_load_weights)");
+  const WeightLayout wl = weight_layout(nn.rows, nn.cols, nn.blocks);
+  const uint8_t* wimg = static_cast<const uint8_t*>(nn.weights);
+  int64_t o_feat, o_logits, o_hidden, total;
+  nn_scratch_layout(nn.rows, nn.cols, nn.max_boards, o_feat, o_logits, o_hidden, total);
+  uint8_t* sc = static_cast<uint8_t*>(nn.scratch);
+  __nv_bfloat16* headfeat = reinterpret_cast<__nv_bfloat16*>(sc + o_feat);
+  float* logits_buf = reinterpret_cast<float*>(sc + o_logits);
+  float* hidden = reinterpret_cast<float*>(sc + o_hidden);
+  const int A = nn.A;
+  for (int64_t done = 0; done < count; done += nn.max_boards) {
+    const int64_t n = (count - done) < nn.max_boards ? (count - done) : nn.max_boards;
+    TowerArgs ta;
+    ta.g = make_tower_geo(nn.rows, nn.cols, nn.blocks);
+    ta.conv_stream = wimg + wl.conv_stream;
+    ta.conv_bias = reinterpret_cast<const float*>(wimg + wl.conv_bias);
+    ta.black = black + done * nn.W; ta.white = white + done * nn.W;
+    ta.count = n; ta.n_groups = (int)((n + ta.g.Gb - 1) / ta.g.Gb);
+    ta.headfeat = headfeat;
+    const int grid = ta.n_groups < nn.num_sms ? ta.n_groups : nn.num_sms;
+    tower_kernel<<<grid, TW_THREADS, SM_TOTAL, s>>>(ta);
+    YY_LAUNCH_CHECK();
+    GemmArgs gp{headfeat, TW_HEADC * A, reinterpret_cast<const __nv_bfloat16*>(wimg + wl.fc_policy_w), 32 * A, logits_buf, wl.a_pad,
+                reinterpret_cast<const float*>(wimg + wl.fc_policy_b), (int)n, wl.a_pad, 32 * A, 0};
+    int rc = gemm_bf16_tn(gp, s); if (rc) return rc;
+    GemmArgs gv{headfeat + 32 * A, TW_HEADC * A, reinterpret_cast<const __nv_bfloat16*>(wimg + wl.fc_value1_w), 32 * A, hidden, 256,
+                reinterpret_cast<const float*>(wimg + wl.fc_value1_b), (int)n, 256, 32 * A, 1};
+    rc = gemm_bf16_tn(gv, s); if (rc) return rc;
+    const unsigned grid2 = (unsigned)((n * 32 + 127) / 128);
+    heads_finish_kernel<<<grid2, 128, 0, s>>>(logits_buf, wl.a_pad, hidden, reinterpret_cast<const float*>(wimg + wl.fc_value2_w),
+                                              reinterpret_cast<const float*>(wimg + wl.fc_value2_b), n, A,
+                                              policy + done * A, value + done, logits ? logits + done * A : nullptr);
+    YY_LAUNCH_CHECK();
+  }
+  return YY_OK;
+}
+
+}  // namespace yy
+
+// Section offsets of the packed weight image, for the host-side packer:
+// out[0..8] = conv_stream, conv_bias, fc_policy_w, fc_policy_b, fc_value1_w, fc_value1_b, fc_value2_w, fc_value2_b, total;
+// out[9] = padded policy rows (A rounded up to 16).
+extern "C" int yy_nn_weight_layout(int rows, int cols, int channels, int blocks, int64_t* out) {
+  using namespace yy;
+  int64_t t = nn_weight_bytes(rows, cols, channels, blocks);
+  if (t < 0) return (int)t;
+  WeightLayout w = weight_layout(rows, cols, blocks);
+  out[0] = w.conv_stream; out[1] = w.conv_bias; out[2] = w.fc_policy_w; out[3] = w.fc_policy_b; out[4] = w.fc_value1_w;
+  out[5] = w.fc_value1_b; out[6] = w.fc_value2_w; out[7] = w.fc_value2_b; out[8] = w.total; out[9] = w.a_pad;
+  return YY_OK;
+}

@@ -1,0 +1,29 @@
+// yy_nn.cuh -- policy/value network inference on the leaf batch (interface used by yy_tree.cu).
+// Implementation and memory layouts: yy_nn.cu.
+#pragma once
+#include "yy_common.cuh"
+
+namespace yy {
+
+struct NNState {
+  int rows, cols, A, W, channels, blocks;
+  int max_boards;            // capacity of the head-feature scratch (>= n_games)
+  const void* weights;       // packed image (device), owned by the caller
+  int64_t weight_bytes;
+  void* scratch;             // head features etc. (inside the engine workspace)
+  int64_t scratch_bytes;
+  int device, num_sms;
+  bool attrs_set;
+};
+
+int64_t nn_weight_bytes(int rows, int cols, int channels, int blocks);
+size_t nn_workspace_bytes(const yy_engine_config& cfg);
+int nn_init(NNState& nn, const yy_engine_config& cfg, void* scratch);
+void nn_destroy(NNState& nn);
+int nn_load_weights(NNState& nn, const void* weights_dev, int64_t bytes);
+// black/white: [count][W] bitboards on the device.  policy [count][A] = softmax(logits) (neural_network.py:152),
+// value [count] = tanh head, logits [count][A] optional.  count <= max_boards per call is chunked internally.
+int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_t count, float* policy, float* value,
+               float* logits, cudaStream_t stream);
+
+}  // namespace yy

@@ -1,0 +1,181 @@
+// yy_rules_kernels.cu -- batched, stateless rules entry points of the C ABI (one thread per board).
+// Replaces YinYangGame.getValidMoves / getNextState / getGameEnded (src/yin_yang/yin_yang_game.py:39-110)
+// over YinYangLogic (src/yin_yang/yin_yang_logic.py:24-134).
+//
+// Roofline: HBM.  Algorithmic bytes per env step = 6*ceil(A/8)+4 (52 B at 8x8); the kernels are
+// a few hundred integer ops per board, so at 65,536 boards they are launch/latency bound, not bandwidth bound.
+#include "yy_common.cuh"
+
+namespace yy {
+
+static thread_local char t_err[512];
+char* error_buffer() { return t_err; }
+int set_error(int status, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(t_err, sizeof(t_err), fmt, ap); va_end(ap);
+  return status;
+}
+std::atomic<long long> g_launches{0};
+
+constexpr int kRulesBlock = 128;
+
+template <int NW>
+__global__ void __launch_bounds__(kRulesBlock)
+legal_mask_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint64_t* __restrict__ white,
+                  const int8_t* __restrict__ players, uint64_t* __restrict__ out_mask, long long count) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  BB<NW> b = load_bb<NW>(black, i, W) & g.full, w = load_bb<NW>(white, i, W) & g.full;
+  store_bb<NW>(out_mask, i, W, legal_for(g, b, w, players[i] == 1 ? 1 : -1));
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kRulesBlock)
+step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __restrict__ white, int8_t* __restrict__ players,
+            const int32_t* __restrict__ actions, long long count) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  BB<NW> b = load_bb<NW>(black, i, W) & g.full, w = load_bb<NW>(white, i, W) & g.full;
+  int p = players[i] == 1 ? 1 : -1;
+  if (apply_action(g, b, w, p, actions[i])) {
+    if (p == 1) store_bb<NW>(black, i, W, b); else store_bb<NW>(white, i, W, w);
+  }
+  players[i] = (int8_t)(-players[i]);  // yin_yang_game.py:58 returns -player whatever it was
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kRulesBlock)
+ended_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint64_t* __restrict__ white,
+             const int8_t* __restrict__ players, int8_t* __restrict__ out, long long count) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  BB<NW> b = load_bb<NW>(black, i, W) & g.full, w = load_bb<NW>(white, i, W) & g.full;
+  out[i] = (int8_t)ended_code(g, b, w, players[i] == 1 ? 1 : -1);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kRulesBlock)
+env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __restrict__ white,
+                int8_t* __restrict__ players, const int32_t* __restrict__ actions, uint64_t* __restrict__ out_mask,
+                int8_t* __restrict__ out_result, long long count) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  BB<NW> b = load_bb<NW>(black, i, W) & g.full, w = load_bb<NW>(white, i, W) & g.full;
+  int p = players[i] == 1 ? 1 : -1;
+  BB<NW> lm = legal_for(g, b, w, p);
+  store_bb<NW>(out_mask, i, W, lm);
+  int a = actions[i];
+  if (a >= 0 && a < g.cells && test(lm, a)) {
+    if (p == 1) { setbit(b, a); store_bb<NW>(black, i, W, b); }
+    else        { setbit(w, a); store_bb<NW>(white, i, W, w); }
+  }
+  players[i] = (int8_t)(-players[i]);
+  out_result[i] = (int8_t)ended_code(g, b, w, -p);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kRulesBlock)
+random_playout_kernel(Geo<NW> g, int W, uint64_t seed, const int32_t* __restrict__ plies, uint64_t* __restrict__ black,
+                      uint64_t* __restrict__ white, int8_t* __restrict__ players, long long count) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  BB<NW> b = bb_zero<NW>(), w = bb_zero<NW>();
+  int p = 1;
+  Philox rng(seed, (uint64_t)i, 0x706c6179ull);
+  int n = plies[i];
+  for (int k = 0; k < n; ++k) {
+    BB<NW> lm = legal_for(g, b, w, p);
+    int c = popcount(lm);
+    if (c) {
+      int a = kth_bit(lm, (int)rng.below((uint32_t)c));
+      if (p == 1) setbit(b, a); else setbit(w, a);
+    }
+    p = -p;  // a side without a legal move passes
+  }
+  store_bb<NW>(black, i, W, b); store_bb<NW>(white, i, W, w);
+  players[i] = (int8_t)p;
+}
+
+static int check_rules_args(int rows, int cols, long long count) {
+  if (!board_supported(rows, cols)) return set_error(YY_ERR_INVALID, "unsupported board %dx%d (need <=32 per side, <=256 cells)", rows, cols);
+  if (count < 0) return set_error(YY_ERR_INVALID, "negative count");
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) { cudaGetLastError(); return set_error(YY_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback"); }
+  return YY_OK;
+}
+
+}  // namespace yy
+
+using namespace yy;
+
+extern "C" {
+
+int yy_abi_version(void) { return YY_ABI_VERSION; }
+const char* yy_last_error(void) { return yy::error_buffer(); }
+int yy_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+int64_t yy_launch_count(void) { return (int64_t)yy::g_launches.load(); }
+
+int yy_legal_mask(int rows, int cols, uint32_t rule_flags, const uint64_t* black, const uint64_t* white,
+                  const int8_t* players, uint64_t* out_mask, int64_t count, void* stream) {
+  int rc = check_rules_args(rows, cols, count); if (rc) return rc;
+  if (count == 0) return YY_OK;
+  int cells = rows * cols, W = words_for_cells(cells);
+  unsigned grid = (unsigned)((count + kRulesBlock - 1) / kRulesBlock);
+  YY_DISPATCH_NW(cells, legal_mask_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
+      make_geo<NW>(rows, cols, rule_flags), W, black, white, players, out_mask, count));
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64_t* white, int8_t* players,
+            const int32_t* actions, int64_t count, void* stream) {
+  int rc = check_rules_args(rows, cols, count); if (rc) return rc;
+  if (count == 0) return YY_OK;
+  int cells = rows * cols, W = words_for_cells(cells);
+  unsigned grid = (unsigned)((count + kRulesBlock - 1) / kRulesBlock);
+  YY_DISPATCH_NW(cells, step_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
+      make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, count));
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_ended(int rows, int cols, uint32_t rule_flags, const uint64_t* black, const uint64_t* white,
+             const int8_t* players, int8_t* out_result, int64_t count, void* stream) {
+  int rc = check_rules_args(rows, cols, count); if (rc) return rc;
+  if (count == 0) return YY_OK;
+  int cells = rows * cols, W = words_for_cells(cells);
+  unsigned grid = (unsigned)((count + kRulesBlock - 1) / kRulesBlock);
+  YY_DISPATCH_NW(cells, ended_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
+      make_geo<NW>(rows, cols, rule_flags), W, black, white, players, out_result, count));
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64_t* white, int8_t* players,
+                const int32_t* actions, uint64_t* out_mask, int8_t* out_result, int64_t count, void* stream) {
+  int rc = check_rules_args(rows, cols, count); if (rc) return rc;
+  if (count == 0) return YY_OK;
+  int cells = rows * cols, W = words_for_cells(cells);
+  unsigned grid = (unsigned)((count + kRulesBlock - 1) / kRulesBlock);
+  YY_DISPATCH_NW(cells, env_step_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
+      make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count));
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_random_playout(int rows, int cols, uint32_t rule_flags, uint64_t seed, const int32_t* plies, uint64_t* black,
+                      uint64_t* white, int8_t* players, int64_t count, void* stream) {
+  int rc = check_rules_args(rows, cols, count); if (rc) return rc;
+  if (count == 0) return YY_OK;
+  int cells = rows * cols, W = words_for_cells(cells);
+  unsigned grid = (unsigned)((count + kRulesBlock - 1) / kRulesBlock);
+  YY_DISPATCH_NW(cells, random_playout_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
+      make_geo<NW>(rows, cols, rule_flags), W, seed, plies, black, white, players, count));
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,664 @@
+// yy_tree.cu -- HBM-resident batched MCTS (one warp per game) + self-play episode driver.
+//
+// Restates src/yin_yang/ai/mcts.py (Node.expand :50-91, select_child :97-145, update :147-156,
+// MCTS.search :275-343, _simulate :345-414) for n_games independent trees at once, and
+// SelfPlayWorker.play_game (src/yin_yang/ai/self_play.py:72-192) as device kernels.
+//
+// Exactness contract (deterministic mode): simulations of one game are strictly sequential (one leaf
+// per game per step, no virtual loss), PUCT is evaluated in the reference's numpy>=2 float32 operation
+// order with explicit round-to-nearest intrinsics (no FMA contraction), ties resolve to the lowest
+// action index (strict '>' scan in ascending action order) => root visit counts are bit-identical to
+// the unmodified reference driven through a value-semantics Game adapter (tests/golden/mcts_*.npz).
+//
+// Roofline: HBM (latency-bound pointer chasing in practice).  Algorithmic bytes per simulation:
+// sum over levels of 12*A_l (N,W,P per child read) + 17*A_leaf (edge slots written) + 8 per path edge
+// (N,W read-modify-write) + 2*16*W node state -- ~1.5-4 KB at 8x8.
+#include "yy_engine.cuh"
+#include "yy_nn.cuh"
+
+#include <math.h>
+#include <new>
+
+namespace yy {
+
+constexpr int kTreeBlock = 128;  // 4 games per CTA
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int NW>
+__device__ __forceinline__ int rank_below(const BB<NW>& m, int a) {
+  int r = 0;
+  int wi = a >> 6, bi = a & 63;
+#pragma unroll
+  for (int k = 0; k < NW; ++k) {
+    if (k < wi) r += popc64(m.w[k]);
+    else if (k == wi) r += popc64(m.w[k] & ((1ull << bi) - 1ull));
+  }
+  return r;
+}
+
+__device__ __forceinline__ float terminal_value_f32(int code) {
+  // yin_yang_game.py:101-107: +1 / -1 / 0.0001 (Python scalars, weak-promoted to float32 in Node.update)
+  return code == 1 ? 1.0f : (code == -1 ? -1.0f : (float)0.0001);
+}
+
+// Node.update along the recorded path (mcts.py:406-412): the leaf's own slot gets +v, alternating upwards.
+__device__ __forceinline__ void backup_path(const EngineDev& e, int gi, long long eb, int plen, float v, int lane) {
+  const int32_t* path = e.g_path + (long long)gi * e.max_depth;
+  for (int i = lane; i < plen; i += 32) {
+    long long ei = eb + path[i];
+    float sv = ((plen - 1 - i) & 1) ? -v : v;
+    e.edge_N[ei] += 1;
+    e.edge_W[ei] = __fadd_rn(e.edge_W[ei], sv);
+  }
+}
+
+// Writes the state of node `id`, evaluates the rules for it (terminal code + legal mask of the side to
+// move) and publishes it as this game's pending leaf.  All lanes hold identical arguments.
+template <int NW>
+__device__ __forceinline__ void publish_leaf(const EngineDev& e, const Geo<NW>& g, int gi, int lane, int id,
+                                             const BB<NW>& black, const BB<NW>& white, int player, int plen) {
+  BB<NW> mask = legal_for(g, black, white, player);
+  int code = ended_code_with_mask(g, black, white, player, mask);
+  if (lane == 0) {
+    long long ni = (long long)gi * e.max_nodes + id;
+    store_bb<NW>(e.node_black, ni, e.W, black);
+    store_bb<NW>(e.node_white, ni, e.W, white);
+    e.node_player[ni] = (int8_t)player;
+    e.node_flags[ni] = 0;
+    e.node_n_edges[ni] = 0;
+    e.node_edge_base[ni] = 0;
+    store_bb<NW>(e.leaf_black, gi, e.W, black);
+    store_bb<NW>(e.leaf_white, gi, e.W, white);
+    store_bb<NW>(e.leaf_mask, gi, e.W, mask);
+    e.leaf_code[gi] = (int8_t)code;
+    e.g_leaf[gi] = id;
+    e.g_path_len[gi] = plen;
+  }
+  if (e.evaluator == YY_EVAL_STUB) {  // deterministic-prior mode: evaluator fused into the tree kernel
+    uint64_t key = stub_key(g, black, white);
+    for (int a = lane; a < e.A; a += 32) e.eval_prior[(long long)gi * e.A + a] = stub_prior(key, a);
+    if (lane == 0) e.eval_value[gi] = stub_value(key);
+  }
+}
+
+// MCTS.search prologue (mcts.py:288-292): fresh tree per game, root = node 0, pending leaf = root.
+template <int NW>
+__global__ void __launch_bounds__(kTreeBlock) tree_root_kernel(EngineDev e, Geo<NW> g) {
+  int gi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (gi >= e.n_games) return;
+  BB<NW> b = load_bb<NW>(e.root_black, gi, e.W) & g.full, w = load_bb<NW>(e.root_white, gi, e.W) & g.full;
+  int player = e.root_player[gi] == 1 ? 1 : -1;
+  if (lane == 0) {
+    e.g_n_nodes[gi] = 1; e.g_n_edges[gi] = 0; e.g_sims_done[gi] = 0;
+    e.leaf_active[gi] = 1;
+  }
+  publish_leaf<NW>(e, g, gi, lane, 0, b, w, player, 0);
+  if (gi == 0 && lane == 0) *e.active_count = e.n_games;
+}
+
+// One lock-step of every tree: (1) expand the pending leaf with the evaluator's output and back its value
+// up (mcts.py:394-412); (2) run simulations from the root until one needs an evaluation (selection,
+// mcts.py:360-362; revisited terminal leaves complete on the spot, :365-367) and publish that leaf.
+template <int NW>
+__global__ void __launch_bounds__(kTreeBlock) tree_step_kernel(EngineDev e, Geo<NW> g) {
+  int gi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (gi >= e.n_games) return;
+  const long long nb = (long long)gi * e.max_nodes;
+  const long long eb = (long long)gi * e.edges_cap;
+  int32_t* path = e.g_path + (long long)gi * e.max_depth;
+  int sims_done = e.g_sims_done[gi];
+  int sims_here = 0, evals_here = 0, deepest = 0;
+  const int leaf = e.g_leaf[gi];
+
+  // ---------------------------------------------------------------- (1) expand + backup
+  if (leaf >= 0) {
+    const int code = e.leaf_code[gi];
+    const float v = e.eval_value[gi];
+    uint8_t flags = NODE_EXPANDED;
+    float nodeval = 0.0f;
+    if (code != 0) {                       // Node.expand terminal branch (mcts.py:63-68)
+      flags |= NODE_TERMINAL; nodeval = terminal_value_f32(code);
+    } else {
+      BB<NW> mask = load_bb<NW>(e.leaf_mask, gi, e.W);
+      int cnt = popcount(mask);
+      int base = e.g_n_edges[gi];
+      __syncwarp();
+      if (cnt > 0 && base + cnt > e.edges_cap) { if (lane == 0) atomicExch(&e.stats->overflow, 1); cnt = 0; }
+      if (cnt == 0) {                      // no legal move, not terminal: child-less node, re-evaluated on every
+        flags |= NODE_NOCHILD; nodeval = v;  // visit by the reference (is_expanded() stays False) -> same value
+      } else {
+        const bool noisy = (leaf == 0) && e.noise != nullptr && e.noise_mask != nullptr && e.noise_mask[gi] != 0;
+        for (int a = lane; a < e.A; a += 32) {
+          if (!test(mask, a)) continue;
+          int r = rank_below(mask, a);     // children are created in ascending action order (mcts.py:75-89)
+          float p = e.eval_prior[(long long)gi * e.A + a];
+          if (noisy) {                     // mcts.py:309-311: f32( f64(f32(f32(1-eps)*p)) + eps*noise_i )
+            float keep = __fmul_rn(e.keep_f32, p);
+            p = (float)__dadd_rn((double)keep, __dmul_rn(e.eps, e.noise[(long long)gi * e.A + r]));
+          }
+          long long ei = eb + base + r;
+          e.edge_N[ei] = 0; e.edge_W[ei] = 0.0f; e.edge_P[ei] = p; e.edge_child[ei] = -1;
+          e.edge_action[ei] = (uint8_t)a;
+        }
+        __syncwarp();
+        if (lane == 0) { e.node_edge_base[nb + leaf] = base; e.node_n_edges[nb + leaf] = (int16_t)cnt; e.g_n_edges[gi] = base + cnt; }
+      }
+    }
+    if (lane == 0) { e.node_flags[nb + leaf] = flags; e.node_value[nb + leaf] = nodeval; }
+    const int plen = e.g_path_len[gi];
+    backup_path(e, gi, eb, plen, v, lane);   // first visit always backs up the evaluator's value (mcts.py:394)
+    if (leaf != 0) { ++sims_done; ++sims_here; }
+    __syncwarp();
+  }
+
+  // ---------------------------------------------------------------- (2) select
+  bool pending = false;
+  while (sims_done < e.n_sims && !pending) {
+    int node = 0, depth = 0;
+    for (;;) {
+      const uint8_t fl = e.node_flags[nb + node];
+      if (fl & (NODE_TERMINAL | NODE_NOCHILD)) {   // revisited terminal (mcts.py:365-367) / child-less node
+        __syncwarp();                              // path[] written by lane 0 above
+        backup_path(e, gi, eb, depth, e.node_value[nb + node], lane);
+        ++sims_done; ++sims_here;
+        __syncwarp();
+        break;
+      }
+      const int base = e.node_edge_base[nb + node], cnt = e.node_n_edges[nb + node];
+      // Node.select_child (mcts.py:97-145)
+      int sum = 0;
+      for (int k = lane; k < cnt; k += 32) sum += e.edge_N[eb + base + k];
+#pragma unroll
+      for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(kFull, sum, off);
+      const float sq = (float)sqrt((double)sum);
+      float best = -INFINITY; int besti = 0x7fffffff;
+      for (int k = lane; k < cnt; k += 32) {
+        const long long ei = eb + base + k;
+        const int n = e.edge_N[ei];
+        const float u = __fdiv_rn(__fmul_rn(__fmul_rn(e.cpuct, e.edge_P[ei]), sq), (float)(1 + n));
+        const float q = n > 0 ? __fdiv_rn(e.edge_W[ei], (float)n) : 0.0f;
+        const float ucb = __fadd_rn(q, u);
+        if (ucb > best) { best = ucb; besti = k; }
+      }
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        float ov = __shfl_xor_sync(kFull, best, off); int oi = __shfl_xor_sync(kFull, besti, off);
+        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+      }
+      if (besti == 0x7fffffff) besti = 0;
+      const int eoff = base + besti;
+      if (lane == 0) path[depth] = eoff;
+      ++depth;
+      const int child = e.edge_child[eb + eoff];
+      if (child < 0) {                      // unexpanded child: getNextState on the parent's state (mcts.py:385-391)
+        BB<NW> b = load_bb<NW>(e.node_black, nb + node, e.W), w = load_bb<NW>(e.node_white, nb + node, e.W);
+        const int pp = e.node_player[nb + node];
+        const int a = e.edge_action[eb + eoff];
+        if (pp == 1) setbit(b, a); else setbit(w, a);   // the slot exists only for a legal action
+        const int id = e.g_n_nodes[gi];
+        __syncwarp();
+        if (lane == 0) { e.g_n_nodes[gi] = id + 1; e.edge_child[eb + eoff] = id; }
+        publish_leaf<NW>(e, g, gi, lane, id, b, w, -pp, depth);
+        if (depth > deepest) deepest = depth;
+        pending = true; ++evals_here;
+        break;
+      }
+      node = child;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    e.g_sims_done[gi] = sims_done;
+    if (!pending) e.g_leaf[gi] = -1;
+    e.leaf_active[gi] = pending ? 1 : 0;
+    if (pending) atomicAdd(e.active_count, 1);
+    if (sims_here) atomicAdd(&e.stats->sims, (unsigned long long)sims_here);
+    if (evals_here) atomicAdd(&e.stats->evals, (unsigned long long)evals_here);
+    if (deepest > e.stats->max_depth) atomicMax(&e.stats->max_depth, deepest);
+  }
+}
+
+// root.get_children_visit_counts (mcts.py:168-181) + child value sums
+__global__ void tree_counts_kernel(EngineDev e, int32_t* counts, float* child_w) {
+  int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= e.n_games) return;
+  for (int a = 0; a < e.A; ++a) { counts[(long long)gi * e.A + a] = 0; if (child_w) child_w[(long long)gi * e.A + a] = 0.0f; }
+  const long long nb = (long long)gi * e.max_nodes, eb = (long long)gi * e.edges_cap;
+  if (!(e.node_flags[nb] & NODE_EXPANDED)) return;
+  int base = e.node_edge_base[nb], cnt = e.node_n_edges[nb];
+  for (int k = 0; k < cnt; ++k) {
+    int a = e.edge_action[eb + base + k];
+    counts[(long long)gi * e.A + a] = e.edge_N[eb + base + k];
+    if (child_w) child_w[(long long)gi * e.A + a] = e.edge_W[eb + base + k];
+  }
+}
+
+__global__ void zero_i32_kernel(int32_t* p) { *p = 0; }
+
+// stub evaluator on an arbitrary batch (yy_evaluate in YY_EVAL_STUB mode)
+template <int NW>
+__global__ void stub_eval_kernel(Geo<NW> g, int W, const uint64_t* black, const uint64_t* white, long long count,
+                                 float* policy, float* value) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  BB<NW> b = load_bb<NW>(black, i, W) & g.full, w = load_bb<NW>(white, i, W) & g.full;
+  uint64_t key = stub_key(g, b, w);
+  for (int a = 0; a < g.cells; ++a) policy[i * g.cells + a] = stub_prior(key, a);
+  value[i] = stub_value(key);
+}
+
+// ------------------------------------------------------------------------------------------------ self-play
+__device__ __forceinline__ void finish_game(const EngineDev& e, int gi, int code) {
+  int serial = e.sp_serial[gi];
+  if (serial >= 0) e.rp_results[serial % e.results_cap] = (int8_t)code;
+  atomicAdd(&e.stats->games_finished, 1ull);
+  e.sp_new_game[gi] = 1;
+}
+
+// Top of the play_game loop (self_play.py:91-125): new game if needed, pass / double-pass handling, then the
+// root of the next search.  search player = 1 always under YY_MODE_SEARCH_AS_BLACK (self_play.py:99,135-137).
+template <int NW>
+__global__ void __launch_bounds__(128) sp_prepare_kernel(EngineDev e, Geo<NW> g) {
+  int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= e.n_games) return;
+  BB<NW> b = load_bb<NW>(e.sp_black, gi, e.W), w = load_bb<NW>(e.sp_white, gi, e.W);
+  int player = e.sp_player[gi], step = e.sp_step[gi], passes = e.sp_passes[gi];
+  int sp = 1;
+  for (;;) {
+    if (e.sp_new_game[gi]) {
+      b = bb_zero<NW>(); w = bb_zero<NW>(); player = 1; step = 0; passes = 0;
+      e.sp_serial[gi] = atomicAdd(e.sp_next_serial, 1);
+      e.sp_new_game[gi] = 0;
+    }
+    sp = (e.mode_flags & YY_MODE_SEARCH_AS_BLACK) ? 1 : player;
+    if (any(legal_for(g, b, w, sp))) { passes = 0; break; }
+    ++passes;                                             // self_play.py:103-106
+    if (passes >= 2) {                                    // self_play.py:108-121
+      int code = ended_code(g, b, w, player);
+      if (code == 0) code = YY_RESULT_DRAW;
+      finish_game(e, gi, code);
+      continue;
+    }
+    player = -player;                                     // self_play.py:124-125
+  }
+  store_bb<NW>(e.sp_black, gi, e.W, b); store_bb<NW>(e.sp_white, gi, e.W, w);
+  e.sp_player[gi] = (int8_t)player; e.sp_step[gi] = step; e.sp_passes[gi] = passes;
+  store_bb<NW>(e.root_black, gi, e.W, b); store_bb<NW>(e.root_white, gi, e.W, w);
+  e.root_player[gi] = (int8_t)sp;
+  e.noise_mask[gi] = (step == 0) ? 1 : 0;                 // add_noise = (step == 0), self_play.py:131
+}
+
+__device__ inline double gamma_sample(Philox& rng, double a) {
+  // Marsaglia-Tsang; for a < 1: G(a) = G(a+1) * U^(1/a)
+  double boost = 1.0;
+  if (a < 1.0) { boost = pow(rng.uniform(), 1.0 / a); a += 1.0; }
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (;;) {
+    double u1 = rng.uniform(), u2 = rng.uniform();
+    double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    double u = rng.uniform();
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
+  }
+}
+
+// np.random.dirichlet([alpha]*k) for the legal root actions of games at step 0 (mcts.py:303-306)
+template <int NW>
+__global__ void __launch_bounds__(128) sp_noise_kernel(EngineDev e, Geo<NW> g) {
+  int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= e.n_games || !e.noise_mask[gi]) return;
+  BB<NW> b = load_bb<NW>(e.root_black, gi, e.W), w = load_bb<NW>(e.root_white, gi, e.W);
+  int k = popcount(legal_for(g, b, w, e.root_player[gi]));
+  Philox rng(e.seed, (uint64_t)(uint32_t)e.sp_serial[gi], 0x6e6f697365ull);
+  double sum = 0.0;
+  double* out = e.noise + (long long)gi * e.A;
+  for (int i = 0; i < k; ++i) { double x = gamma_sample(rng, e.alpha); out[i] = x; sum += x; }
+  if (sum <= 0.0) { for (int i = 0; i < k; ++i) out[i] = 1.0 / k; }
+  else { for (int i = 0; i < k; ++i) out[i] /= sum; }
+}
+
+// After the search (self_play.py:139-190): store the example, pick the action (temperature 1 for the first
+// `temperature_threshold` moves, then argmax with random tie-break), apply it with the REAL player
+// (illegal -> silently dropped, yin_yang_logic.py:24-29), test for the end of the game.
+template <int NW>
+__global__ void __launch_bounds__(128) sp_move_kernel(EngineDev e, Geo<NW> g) {
+  int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= e.n_games) return;
+  const long long nb = (long long)gi * e.max_nodes, eb = (long long)gi * e.edges_cap;
+  BB<NW> b = load_bb<NW>(e.sp_black, gi, e.W), w = load_bb<NW>(e.sp_white, gi, e.W);
+  int player = e.sp_player[gi], step = e.sp_step[gi];
+  const int base = e.node_edge_base[nb], cnt = (e.node_flags[nb] & NODE_EXPANDED) ? e.node_n_edges[nb] : 0;
+  // example record (board before the move, visit counts; pi = counts/sum on the host in float64)
+  unsigned long long slot64 = atomicAdd(&e.stats->examples, 1ull);
+  long long slot = (long long)(slot64 % (unsigned long long)e.replay_cap);
+  store_bb<NW>(e.rp_black, slot, e.W, b); store_bb<NW>(e.rp_white, slot, e.W, w);
+  uint16_t* rc = e.rp_counts + slot * e.A;
+  for (int a = 0; a < e.A; ++a) rc[a] = 0;
+  long long total = 0; int maxn = -1, nmax = 0;
+  for (int k = 0; k < cnt; ++k) {
+    int n = e.edge_N[eb + base + k];
+    rc[e.edge_action[eb + base + k]] = (uint16_t)(n > 65535 ? 65535 : n);
+    total += n;
+    if (n > maxn) { maxn = n; nmax = 1; } else if (n == maxn) ++nmax;
+  }
+  e.rp_serial[slot] = e.sp_serial[gi]; e.rp_ply[slot] = (int16_t)step; e.rp_player[slot] = (int8_t)player;
+  // action selection
+  Philox rng(e.seed, (uint64_t)(uint32_t)e.sp_serial[gi], 0x1000ull + (uint64_t)step);
+  int action = -1;
+  if (cnt > 0) {
+    if (step < e.temperature_threshold && total > 0) {       // temperature 1: sample proportional to visits
+      long long r = (long long)(rng.uniform() * (double)total);
+      if (r >= total) r = total - 1;
+      long long acc = 0;
+      for (int k = 0; k < cnt; ++k) { acc += e.edge_N[eb + base + k]; if (r < acc) { action = e.edge_action[eb + base + k]; break; } }
+    } else if (total > 0) {                                    // temperature 0: random choice among the maxima
+      int pick = (int)rng.below((uint32_t)nmax);
+      for (int k = 0; k < cnt; ++k) if (e.edge_N[eb + base + k] == maxn) { if (pick-- == 0) { action = e.edge_action[eb + base + k]; break; } }
+    } else {                                                   // no visits at all: uniform over legal moves
+      action = e.edge_action[eb + base + (int)rng.below((uint32_t)cnt)];
+    }
+  }
+  if (action >= 0) apply_action(g, b, w, player, action);    // getNextState with the real player (self_play.py:163)
+  player = -player; ++step;
+  store_bb<NW>(e.sp_black, gi, e.W, b); store_bb<NW>(e.sp_white, gi, e.W, w);
+  e.sp_player[gi] = (int8_t)player; e.sp_step[gi] = step;
+  atomicAdd(&e.stats->moves, 1ull);
+  int code = ended_code(g, b, w, player);                    // self_play.py:167-168
+  if (code != 0) finish_game(e, gi, code);
+}
+
+__global__ void sp_reset_kernel(EngineDev e) {
+  int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi == 0) { *e.sp_next_serial = 0; Stats z = {}; *e.stats = z; }
+  if (gi >= e.n_games) return;
+  e.sp_new_game[gi] = 1; e.sp_serial[gi] = -1; e.sp_step[gi] = 0; e.sp_passes[gi] = 0; e.sp_player[gi] = 1;
+  for (int k = 0; k < e.W; ++k) { e.sp_black[(long long)gi * e.W + k] = 0; e.sp_white[(long long)gi * e.W + k] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct Carver {
+  char* base; size_t off;
+  template <typename T> T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static int normalise_cfg(yy_engine_config& c) {
+  if (!board_supported(c.rows, c.cols)) return set_error(YY_ERR_INVALID, "unsupported board %dx%d", c.rows, c.cols);
+  if (c.n_games < 1 || c.n_sims < 0) return set_error(YY_ERR_INVALID, "n_games >= 1 and n_sims >= 0 required");
+  int A = c.rows * c.cols;
+  if (c.edges_per_game <= 0) c.edges_per_game = (c.n_sims + 1) * A;
+  if (c.cpuct <= 0.0f) c.cpuct = 1.0f;
+  if (c.replay_capacity <= 0) c.replay_capacity = 1;
+  if (c.temperature_threshold < 0) c.temperature_threshold = 0;
+  if (c.nn_channels <= 0) c.nn_channels = 128;
+  if (c.nn_blocks < 0) c.nn_blocks = 10;
+  return YY_OK;
+}
+
+static void carve(const yy_engine_config& c, Carver& k, EngineDev& d) {
+  const int A = c.rows * c.cols, W = words_for_cells(A);
+  const size_t G = (size_t)c.n_games, MN = (size_t)c.n_sims + 2, EC = (size_t)c.edges_per_game;
+  d.rows = c.rows; d.cols = c.cols; d.A = A; d.W = W; d.n_games = c.n_games; d.n_sims = c.n_sims;
+  d.max_nodes = (int)MN; d.edges_cap = (int)EC; d.max_depth = A + 2;
+  d.node_black = k.take<uint64_t>(G * MN * W); d.node_white = k.take<uint64_t>(G * MN * W);
+  d.node_edge_base = k.take<int32_t>(G * MN); d.node_n_edges = k.take<int16_t>(G * MN);
+  d.node_player = k.take<int8_t>(G * MN); d.node_flags = k.take<uint8_t>(G * MN); d.node_value = k.take<float>(G * MN);
+  d.edge_N = k.take<int32_t>(G * EC); d.edge_W = k.take<float>(G * EC); d.edge_P = k.take<float>(G * EC);
+  d.edge_child = k.take<int32_t>(G * EC); d.edge_action = k.take<uint8_t>(G * EC);
+  d.g_n_nodes = k.take<int32_t>(G); d.g_n_edges = k.take<int32_t>(G); d.g_sims_done = k.take<int32_t>(G);
+  d.g_leaf = k.take<int32_t>(G); d.g_path_len = k.take<int32_t>(G); d.g_path = k.take<int32_t>(G * (size_t)d.max_depth);
+  d.leaf_black = k.take<uint64_t>(G * W); d.leaf_white = k.take<uint64_t>(G * W); d.leaf_mask = k.take<uint64_t>(G * W);
+  d.leaf_code = k.take<int8_t>(G); d.leaf_active = k.take<uint8_t>(G);
+  d.eval_prior = k.take<float>(G * A); d.eval_value = k.take<float>(G); d.active_count = k.take<int32_t>(1);
+  d.root_black = k.take<uint64_t>(G * W); d.root_white = k.take<uint64_t>(G * W); d.root_player = k.take<int8_t>(G);
+  d.noise = k.take<double>(G * A); d.noise_mask = k.take<uint8_t>(G);
+  d.sp_black = k.take<uint64_t>(G * W); d.sp_white = k.take<uint64_t>(G * W); d.sp_player = k.take<int8_t>(G);
+  d.sp_step = k.take<int32_t>(G); d.sp_passes = k.take<int32_t>(G); d.sp_serial = k.take<int32_t>(G);
+  d.sp_new_game = k.take<uint8_t>(G); d.sp_next_serial = k.take<int32_t>(1);
+  const size_t RC = (size_t)c.replay_capacity;
+  d.replay_cap = (int)RC; d.results_cap = (int)(RC + G + 16);
+  d.rp_black = k.take<uint64_t>(RC * W); d.rp_white = k.take<uint64_t>(RC * W); d.rp_counts = k.take<uint16_t>(RC * A);
+  d.rp_serial = k.take<int32_t>(RC); d.rp_ply = k.take<int16_t>(RC); d.rp_player = k.take<int8_t>(RC);
+  d.rp_results = k.take<int8_t>((size_t)d.results_cap);
+  d.stats = k.take<Stats>(1);
+}
+
+}  // namespace yy
+
+using namespace yy;
+
+struct yy_engine {
+  yy_engine_config cfg;
+  EngineDev dev;
+  NNState nn;
+  bool search_open;
+  // scratch pointers for caller-supplied noise in yy_search
+  const double* user_noise; const uint8_t* user_noise_mask;
+};
+
+namespace {
+
+inline unsigned warp_grid(int n_games) { return (unsigned)(((long long)n_games * 32 + kTreeBlock - 1) / kTreeBlock); }
+inline unsigned thread_grid(int n, int block) { return (unsigned)((n + block - 1) / block); }
+
+int launch_root(yy_engine* e, cudaStream_t s) {
+  YY_DISPATCH_NW(e->dev.A, tree_root_kernel<NW><<<warp_grid(e->dev.n_games), kTreeBlock, 0, s>>>(
+      e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+int launch_step(yy_engine* e, cudaStream_t s) {
+  zero_i32_kernel<<<1, 1, 0, s>>>(e->dev.active_count);
+  YY_LAUNCH_CHECK();
+  YY_DISPATCH_NW(e->dev.A, tree_step_kernel<NW><<<warp_grid(e->dev.n_games), kTreeBlock, 0, s>>>(
+      e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+// evaluator on the pending leaf batch (STUB is fused into the tree kernels)
+int run_evaluator(yy_engine* e, cudaStream_t s) {
+  if (e->cfg.evaluator == YY_EVAL_STUB) return YY_OK;
+  if (e->cfg.evaluator == YY_EVAL_NN)
+    return nn_forward(e->nn, e->dev.leaf_black, e->dev.leaf_white, e->dev.n_games, e->dev.eval_prior, e->dev.eval_value,
+                      nullptr, s);
+  return set_error(YY_ERR_STATE, "external evaluator: use yy_search_begin / yy_search_advance");
+}
+// full search over the roots already stored in dev.root_* (noise pointers already set in dev)
+int search_core(yy_engine* e, cudaStream_t s) {
+  int rc = launch_root(e, s); if (rc) return rc;
+  for (int i = 0; i <= e->cfg.n_sims; ++i) {
+    rc = run_evaluator(e, s); if (rc) return rc;
+    rc = launch_step(e, s); if (rc) return rc;
+  }
+  return YY_OK;
+}
+int copy_roots(yy_engine* e, const uint64_t* rb, const uint64_t* rw, const int8_t* rp, const double* noise,
+               const uint8_t* noise_mask, cudaStream_t s) {
+  const size_t G = (size_t)e->dev.n_games, W = (size_t)e->dev.W, A = (size_t)e->dev.A;
+  if (!rb || !rw || !rp) return set_error(YY_ERR_INVALID, "null root pointer");
+  YY_CUDA_OK(cudaMemcpyAsync(e->dev.root_black, rb, G * W * 8, cudaMemcpyDeviceToDevice, s));
+  YY_CUDA_OK(cudaMemcpyAsync(e->dev.root_white, rw, G * W * 8, cudaMemcpyDeviceToDevice, s));
+  YY_CUDA_OK(cudaMemcpyAsync(e->dev.root_player, rp, G, cudaMemcpyDeviceToDevice, s));
+  if (noise && noise_mask) {
+    YY_CUDA_OK(cudaMemcpyAsync(e->dev.noise, noise, G * A * 8, cudaMemcpyDeviceToDevice, s));
+    YY_CUDA_OK(cudaMemcpyAsync(e->dev.noise_mask, noise_mask, G, cudaMemcpyDeviceToDevice, s));
+  } else {
+    YY_CUDA_OK(cudaMemsetAsync(e->dev.noise_mask, 0, G, s));
+  }
+  return YY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t yy_engine_workspace_bytes(const yy_engine_config* cfg) {
+  if (!cfg) { set_error(YY_ERR_INVALID, "null config"); return YY_ERR_INVALID; }
+  yy_engine_config c = *cfg;
+  int rc = normalise_cfg(c); if (rc) return rc;
+  Carver k{nullptr, 0}; EngineDev d{};
+  carve(c, k, d);
+  size_t total = ((k.off + 255) & ~(size_t)255) + nn_workspace_bytes(c);
+  return (int64_t)total;
+}
+
+yy_engine* yy_engine_create(const yy_engine_config* cfg, void* workspace, int64_t workspace_bytes) {
+  if (!cfg || !workspace) { set_error(YY_ERR_INVALID, "null config/workspace"); return nullptr; }
+  yy_engine_config c = *cfg;
+  if (normalise_cfg(c)) return nullptr;
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) { cudaGetLastError(); set_error(YY_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback"); return nullptr; }
+  if (cudaSetDevice(c.device) != cudaSuccess) { set_error(YY_ERR_CUDA, "cudaSetDevice(%d) failed", c.device); return nullptr; }
+  int64_t need = yy_engine_workspace_bytes(&c);
+  if (workspace_bytes < need) { set_error(YY_ERR_INVALID, "workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)need); return nullptr; }
+  if (((uintptr_t)workspace & 255) != 0) { set_error(YY_ERR_INVALID, "workspace must be 256-byte aligned"); return nullptr; }
+  yy_engine* e = new (std::nothrow) yy_engine();
+  if (!e) { set_error(YY_ERR_INVALID, "out of host memory"); return nullptr; }
+  e->cfg = c; e->search_open = false; e->user_noise = nullptr; e->user_noise_mask = nullptr;
+  Carver k{(char*)workspace, 0};
+  carve(c, k, e->dev);
+  e->dev.cpuct = c.cpuct; e->dev.eps = (double)c.dirichlet_epsilon; e->dev.alpha = (double)c.dirichlet_alpha;
+  e->dev.keep_f32 = (float)(1.0 - (double)c.dirichlet_epsilon);
+  e->dev.evaluator = c.evaluator; e->dev.mode_flags = c.mode_flags; e->dev.temperature_threshold = c.temperature_threshold;
+  e->dev.seed = c.seed;
+  size_t off = (k.off + 255) & ~(size_t)255;
+  if (nn_init(e->nn, c, (char*)workspace + off) != YY_OK) { delete e; return nullptr; }
+  sp_reset_kernel<<<thread_grid(c.n_games, 128), 128>>>(e->dev);
+  count_launch();
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error(YY_ERR_CUDA, "engine init: %s", cudaGetErrorString(cudaGetLastError())); delete e; return nullptr; }
+  return e;
+}
+
+void yy_engine_destroy(yy_engine* e) { if (e) { nn_destroy(e->nn); delete e; } }
+
+int64_t yy_nn_weight_bytes(int rows, int cols, int channels, int blocks) { return nn_weight_bytes(rows, cols, channels, blocks); }
+int yy_engine_load_weights(yy_engine* e, const void* weights, int64_t bytes) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  return nn_load_weights(e->nn, weights, bytes);
+}
+
+int yy_search(yy_engine* e, const uint64_t* rb, const uint64_t* rw, const int8_t* rp, const double* noise,
+              const uint8_t* noise_mask, int32_t* out_counts, void* stream) {
+  if (!e || !out_counts) return set_error(YY_ERR_INVALID, "null argument");
+  if (e->cfg.evaluator == YY_EVAL_EXTERNAL) return set_error(YY_ERR_STATE, "external evaluator: use yy_search_begin / yy_search_advance");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = copy_roots(e, rb, rw, rp, noise, noise_mask, s); if (rc) return rc;
+  rc = search_core(e, s); if (rc) return rc;
+  tree_counts_kernel<<<thread_grid(e->dev.n_games, 128), 128, 0, s>>>(e->dev, out_counts, nullptr);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_search_begin(yy_engine* e, const uint64_t* rb, const uint64_t* rw, const int8_t* rp, const double* noise,
+                    const uint8_t* noise_mask, void* stream) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = copy_roots(e, rb, rw, rp, noise, noise_mask, s); if (rc) return rc;
+  rc = launch_root(e, s); if (rc) return rc;
+  e->search_open = true;
+  return YY_OK;
+}
+
+int yy_search_advance(yy_engine* e, const float* priors, const float* values, int32_t* out_active, void* stream) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  if (!e->search_open) return set_error(YY_ERR_STATE, "yy_search_advance without yy_search_begin");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t G = (size_t)e->dev.n_games, A = (size_t)e->dev.A;
+  if (priors && values) {
+    YY_CUDA_OK(cudaMemcpyAsync(e->dev.eval_prior, priors, G * A * 4, cudaMemcpyDeviceToDevice, s));
+    YY_CUDA_OK(cudaMemcpyAsync(e->dev.eval_value, values, G * 4, cudaMemcpyDeviceToDevice, s));
+  } else if (e->cfg.evaluator != YY_EVAL_STUB) {
+    int rc = run_evaluator(e, s); if (rc) return rc;
+  }
+  int rc = launch_step(e, s); if (rc) return rc;
+  if (out_active) {
+    YY_CUDA_OK(cudaMemcpyAsync(out_active, e->dev.active_count, 4, cudaMemcpyDeviceToHost, s));
+    YY_CUDA_OK(cudaStreamSynchronize(s));
+    if (*out_active == 0) e->search_open = false;
+  }
+  return YY_OK;
+}
+
+int yy_search_counts(yy_engine* e, int32_t* out_counts, float* out_child_w, void* stream) {
+  if (!e || !out_counts) return set_error(YY_ERR_INVALID, "null argument");
+  tree_counts_kernel<<<thread_grid(e->dev.n_games, 128), 128, 0, (cudaStream_t)stream>>>(e->dev, out_counts, out_child_w);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+const uint64_t* yy_engine_leaf_black(yy_engine* e) { return e ? e->dev.leaf_black : nullptr; }
+const uint64_t* yy_engine_leaf_white(yy_engine* e) { return e ? e->dev.leaf_white : nullptr; }
+const uint8_t* yy_engine_leaf_active(yy_engine* e) { return e ? e->dev.leaf_active : nullptr; }
+const uint64_t* yy_engine_game_black(yy_engine* e) { return e ? e->dev.sp_black : nullptr; }
+const uint64_t* yy_engine_game_white(yy_engine* e) { return e ? e->dev.sp_white : nullptr; }
+const int8_t* yy_engine_game_player(yy_engine* e) { return e ? e->dev.sp_player : nullptr; }
+
+int yy_evaluate(yy_engine* e, const uint64_t* black, const uint64_t* white, int64_t count, float* out_policy,
+                float* out_value, float* out_logits, void* stream) {
+  if (!e || !black || !white || !out_policy || !out_value) return set_error(YY_ERR_INVALID, "null argument");
+  if (count <= 0) return YY_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e->cfg.evaluator == YY_EVAL_NN) return nn_forward(e->nn, black, white, count, out_policy, out_value, out_logits, s);
+  if (e->cfg.evaluator == YY_EVAL_STUB) {
+    YY_DISPATCH_NW(e->dev.A, stub_eval_kernel<NW><<<thread_grid((int)count, 128), 128, 0, s>>>(
+        make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags), e->dev.W, black, white, count, out_policy, out_value));
+    YY_LAUNCH_CHECK();
+    return YY_OK;
+  }
+  return set_error(YY_ERR_STATE, "yy_evaluate needs the STUB or NN evaluator");
+}
+
+int yy_selfplay_reset(yy_engine* e, void* stream) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  sp_reset_kernel<<<thread_grid(e->dev.n_games, 128), 128, 0, (cudaStream_t)stream>>>(e->dev);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_selfplay_run(yy_engine* e, int32_t n_moves, void* stream) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  if (e->cfg.evaluator == YY_EVAL_EXTERNAL) return set_error(YY_ERR_STATE, "self-play needs the STUB or NN evaluator");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = thread_grid(e->dev.n_games, 128);
+  for (int mv = 0; mv < n_moves; ++mv) {
+    YY_DISPATCH_NW(e->dev.A, sp_prepare_kernel<NW><<<grid, 128, 0, s>>>(e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
+    YY_LAUNCH_CHECK();
+    if (e->cfg.dirichlet_epsilon > 0.0) {
+      YY_DISPATCH_NW(e->dev.A, sp_noise_kernel<NW><<<grid, 128, 0, s>>>(e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
+      YY_LAUNCH_CHECK();
+    } else {
+      YY_CUDA_OK(cudaMemsetAsync(e->dev.noise_mask, 0, (size_t)e->dev.n_games, s));
+    }
+    int rc = search_core(e, s); if (rc) return rc;
+    YY_DISPATCH_NW(e->dev.A, sp_move_kernel<NW><<<grid, 128, 0, s>>>(e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
+    YY_LAUNCH_CHECK();
+  }
+  return YY_OK;
+}
+
+int yy_selfplay_get_stats(yy_engine* e, yy_selfplay_stats* out, void* stream) {
+  if (!e || !out) return set_error(YY_ERR_INVALID, "null argument");
+  Stats h;
+  YY_CUDA_OK(cudaMemcpyAsync(&h, e->dev.stats, sizeof(Stats), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  YY_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  out->moves = (int64_t)h.moves; out->evals = (int64_t)h.evals; out->games_finished = (int64_t)h.games_finished;
+  out->examples = (int64_t)h.examples; out->sims = (int64_t)h.sims; out->overflow = h.overflow; out->max_depth = h.max_depth;
+  if (h.overflow) return set_error(YY_ERR_CAPACITY, "a tree arena overflowed: raise edges_per_game");
+  return YY_OK;
+}
+
+int yy_selfplay_replay(yy_engine* e, yy_replay_view* out) {
+  if (!e || !out) return set_error(YY_ERR_INVALID, "null argument");
+  out->black = e->dev.rp_black; out->white = e->dev.rp_white; out->counts = e->dev.rp_counts;
+  out->game_serial = e->dev.rp_serial; out->ply = e->dev.rp_ply; out->player = e->dev.rp_player;
+  out->results = e->dev.rp_results; out->results_capacity = e->dev.results_cap;
+  return YY_OK;
+}
+
+}  // extern "C"

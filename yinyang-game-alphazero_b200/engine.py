@@ -1,0 +1,366 @@
+"""Thin Python binding over the C ABI: device buffers come from torch, every computation is a CUDA kernel
+of ``libyinyang_b200.so``.  Nothing here computes on the CPU; without a CUDA device the calls raise.
+
+Device-tensor API (inputs already resident in HBM):
+  legal_mask / step / ended / env_step / random_playout   -- batched rules (yin_yang_game.py:39-110)
+  Engine.search / evaluate / selfplay_run                  -- mcts.py:275-343, neural_network.py:125-154,
+                                                              self_play.py:72-192
+Host-buffer API (numpy in, numpy out, copies inside): the ``*_host`` functions and ``Engine.search_host``.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, bitboard, weights as _weights
+
+RULE_ROWCOL = 1
+EVAL_STUB, EVAL_NN, EVAL_EXTERNAL = 0, 1, 2
+MODE_SEARCH_AS_BLACK = 1
+RESULT_DRAW_CODE = 2
+DRAW_VALUE = 0.0001  # yin_yang_game.py:107
+
+
+def _require_cuda():
+    if not torch.cuda.is_available() or _lib.lib().yy_device_count() == 0:
+        raise _lib.YinYangError("no CUDA device: the B200 engine has no CPU fallback")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def result_from_code(code):
+    """YY_RESULT_* -> the reference's getGameEnded return value (0 / 1 / -1 / 0.0001)."""
+    code = np.asarray(code)
+    out = code.astype(np.float64)
+    out[code == RESULT_DRAW_CODE] = DRAW_VALUE
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ rules (device)
+def _check_boards(black, white, players):
+    assert black.is_cuda and white.is_cuda and players.is_cuda
+    assert black.dtype == torch.int64 or black.dtype == torch.uint64
+    assert players.dtype == torch.int8
+    assert black.is_contiguous() and white.is_contiguous() and players.is_contiguous()
+
+
+def legal_mask(black, white, players, rows, cols, rule_flags=0, out=None):
+    """getValidMoves for every board: returns mask words int64[B, W] (bit a = action a legal)."""
+    _require_cuda(); _check_boards(black, white, players)
+    if out is None:
+        out = torch.empty_like(black)
+    _lib.check(_lib.lib().yy_legal_mask(rows, cols, rule_flags, _ptr(black), _ptr(white), _ptr(players), _ptr(out),
+                                        players.numel(), _stream()))
+    return out
+
+
+def step(black, white, players, actions, rows, cols, rule_flags=0):
+    """getNextState in place (illegal action = silent no-op; the turn passes either way)."""
+    _require_cuda(); _check_boards(black, white, players)
+    assert actions.dtype == torch.int32 and actions.is_cuda
+    _lib.check(_lib.lib().yy_step(rows, cols, rule_flags, _ptr(black), _ptr(white), _ptr(players), _ptr(actions),
+                                  players.numel(), _stream()))
+
+
+def ended(black, white, players, rows, cols, rule_flags=0, out=None):
+    """getGameEnded codes int8[B] (0 ongoing, 1 win, -1 loss, 2 draw) from players' perspective."""
+    _require_cuda(); _check_boards(black, white, players)
+    if out is None:
+        out = torch.empty_like(players)
+    _lib.check(_lib.lib().yy_ended(rows, cols, rule_flags, _ptr(black), _ptr(white), _ptr(players), _ptr(out),
+                                   players.numel(), _stream()))
+    return out
+
+
+def env_step(black, white, players, actions, rows, cols, rule_flags=0, out_mask=None, out_result=None):
+    """One fused environment step (mask of the side to move, apply, terminal code of the successor). In place."""
+    _require_cuda(); _check_boards(black, white, players)
+    if out_mask is None:
+        out_mask = torch.empty_like(black)
+    if out_result is None:
+        out_result = torch.empty_like(players)
+    _lib.check(_lib.lib().yy_env_step(rows, cols, rule_flags, _ptr(black), _ptr(white), _ptr(players), _ptr(actions),
+                                      _ptr(out_mask), _ptr(out_result), players.numel(), _stream()))
+    return out_mask, out_result
+
+
+def random_playout(count, plies, rows, cols, seed=0xC0FFEE, rule_flags=0, device="cuda"):
+    """Synthetic boards: board i = empty board advanced by plies[i] uniformly random legal plies."""
+    _require_cuda()
+    W = bitboard.words_for(rows, cols)
+    black = torch.empty((count, W), dtype=torch.int64, device=device)
+    white = torch.empty((count, W), dtype=torch.int64, device=device)
+    players = torch.empty(count, dtype=torch.int8, device=device)
+    plies = plies.to(device=device, dtype=torch.int32).contiguous()
+    _lib.check(_lib.lib().yy_random_playout(rows, cols, rule_flags, ctypes.c_uint64(seed), _ptr(plies), _ptr(black),
+                                            _ptr(white), _ptr(players), count, _stream()))
+    return black, white, players
+
+
+# ------------------------------------------------------------------------------------------------ rules (host buffers)
+def _to_dev(a, dtype):
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint64:
+        a = a.view(np.int64)
+    t = torch.from_numpy(a)
+    return t.pin_memory().to("cuda", non_blocking=True).view(dtype) if t.numel() else t.to("cuda").view(dtype)
+
+
+def legal_mask_host(boards, players, rows, cols, rule_flags=0):
+    """numpy int8[B,n,m] boards, int8[B] players -> uint8[B, A] masks.  H2D + kernel + D2H."""
+    _require_cuda()
+    b, w = bitboard.pack_boards(boards, rows, cols)
+    mask = legal_mask(_to_dev(b, torch.int64), _to_dev(w, torch.int64),
+                      _to_dev(np.asarray(players, np.int8), torch.int8), rows, cols, rule_flags)
+    return bitboard.unpack_bits(mask.cpu().numpy().view(np.uint64), rows, cols)
+
+
+def env_step_host(boards, players, actions, rows, cols, rule_flags=0):
+    """Host-buffer env step: returns (masks uint8[B,A], boards' int8[B,n,m], players' int8[B], results f64[B])."""
+    _require_cuda()
+    b, w = bitboard.pack_boards(boards, rows, cols)
+    bd, wd = _to_dev(b, torch.int64), _to_dev(w, torch.int64)
+    pd = _to_dev(np.asarray(players, np.int8), torch.int8)
+    ad = _to_dev(np.asarray(actions, np.int32), torch.int32)
+    mask, res = env_step(bd, wd, pd, ad, rows, cols, rule_flags)
+    return (bitboard.unpack_bits(mask.cpu().numpy().view(np.uint64), rows, cols),
+            bitboard.unpack_boards(bd.cpu().numpy().view(np.uint64), wd.cpu().numpy().view(np.uint64), rows, cols),
+            pd.cpu().numpy(), result_from_code(res.cpu().numpy()))
+
+
+def next_state_host(boards, players, actions, rows, cols, rule_flags=0):
+    _require_cuda()
+    b, w = bitboard.pack_boards(boards, rows, cols)
+    bd, wd = _to_dev(b, torch.int64), _to_dev(w, torch.int64)
+    pd = _to_dev(np.asarray(players, np.int8), torch.int8)
+    step(bd, wd, pd, _to_dev(np.asarray(actions, np.int32), torch.int32), rows, cols, rule_flags)
+    return (bitboard.unpack_boards(bd.cpu().numpy().view(np.uint64), wd.cpu().numpy().view(np.uint64), rows, cols),
+            pd.cpu().numpy())
+
+
+def ended_host(boards, players, rows, cols, rule_flags=0):
+    _require_cuda()
+    b, w = bitboard.pack_boards(boards, rows, cols)
+    code = ended(_to_dev(b, torch.int64), _to_dev(w, torch.int64), _to_dev(np.asarray(players, np.int8), torch.int8),
+                 rows, cols, rule_flags)
+    return result_from_code(code.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------ engine
+@dataclass
+class Stats:
+    moves: int
+    evals: int
+    games_finished: int
+    examples: int
+    sims: int
+    overflow: int
+    max_depth: int
+
+
+class Engine:
+    """n_games concurrent MCTS trees + evaluator + self-play slots on one GPU (yy_engine)."""
+
+    def __init__(self, rows=8, cols=8, n_games=1, n_sims=800, evaluator="stub", cpuct=1.0, rule_flags=0,
+                 search_as_black=True, edges_per_game=0, dirichlet_alpha=0.3, dirichlet_epsilon=0.25,
+                 temperature_threshold=10, seed=0, replay_capacity=0, state_dict=None, nn_channels=128, nn_blocks=10,
+                 device=None):
+        _require_cuda()
+        self.L = _lib.lib()
+        self.rows, self.cols, self.A, self.W = rows, cols, rows * cols, bitboard.words_for(rows, cols)
+        self.n_games, self.n_sims = n_games, n_sims
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.tdev = torch.device("cuda", self.device)
+        ev = {"stub": EVAL_STUB, "nn": EVAL_NN, "external": EVAL_EXTERNAL}[evaluator]
+        self.evaluator = evaluator
+        if evaluator == "nn":
+            if state_dict is None:
+                raise ValueError("evaluator='nn' needs a reference state_dict / checkpoint dict")
+            sd = state_dict["state_dict"] if "state_dict" in state_dict else state_dict
+            nn_channels, nn_blocks = _weights.infer_arch(sd)
+        if replay_capacity <= 0:
+            replay_capacity = max(1, n_games * (self.A + 8))
+        self.cfg = _lib.EngineConfig(rows=rows, cols=cols, n_games=n_games, n_sims=n_sims, rule_flags=rule_flags,
+                                     mode_flags=MODE_SEARCH_AS_BLACK if search_as_black else 0, evaluator=ev,
+                                     edges_per_game=edges_per_game, temperature_threshold=temperature_threshold,
+                                     replay_capacity=replay_capacity, nn_channels=nn_channels, nn_blocks=nn_blocks,
+                                     device=self.device, cpuct=cpuct, dirichlet_alpha=dirichlet_alpha,
+                                     dirichlet_epsilon=dirichlet_epsilon, seed=seed)
+        need = self.L.yy_engine_workspace_bytes(ctypes.byref(self.cfg))
+        if need < 0:
+            _lib.check(int(need))
+        with torch.cuda.device(self.device):
+            self.workspace = torch.zeros(int(need) + 256, dtype=torch.uint8, device=self.tdev)
+            base = self.workspace.data_ptr()
+            self._ws_ptr = (base + 255) & ~255
+            torch.cuda.synchronize()
+            self.handle = self.L.yy_engine_create(ctypes.byref(self.cfg), ctypes.c_void_p(self._ws_ptr), int(need))
+        if not self.handle:
+            _lib.check(-1)
+        self.weight_image = None
+        if evaluator == "nn":
+            self.load_state_dict(state_dict)
+        self.replay_capacity = replay_capacity
+        self.workspace_bytes = int(need)
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize(self.device)
+            self.L.yy_engine_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights (yy_engine_load_weights)
+    def load_state_dict(self, state_dict):
+        img = _weights.pack_state_dict(state_dict, self.rows, self.cols)
+        with torch.cuda.device(self.device):
+            buf = torch.zeros(img.size + 256, dtype=torch.uint8, device=self.tdev)
+            off = (-buf.data_ptr()) & 255
+            view = buf[off: off + img.size]
+            view.copy_(torch.from_numpy(img))
+            torch.cuda.synchronize()
+        self.weight_image, self._weight_buf = view, buf
+        _lib.check(self.L.yy_engine_load_weights(self.handle, _ptr(view), img.size))
+
+    def load_weight_image(self, image_u8: torch.Tensor):
+        """Adopt an already-packed device image (e.g. one received over an NCCL broadcast)."""
+        assert image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.data_ptr() % 256 == 0
+        self.weight_image = image_u8
+        _lib.check(self.L.yy_engine_load_weights(self.handle, _ptr(image_u8), image_u8.numel()))
+
+    # -- search (MCTS.search for all games)
+    def search(self, black, white, players, noise=None, noise_mask=None, out_counts=None):
+        """Device tensors in, root visit counts int32[n_games, A] out (mcts.py:168-181)."""
+        _check_boards(black, white, players)
+        assert players.numel() == self.n_games
+        if out_counts is None:
+            out_counts = torch.empty((self.n_games, self.A), dtype=torch.int32, device=self.tdev)
+        _lib.check(self.L.yy_search(self.handle, _ptr(black), _ptr(white), _ptr(players), _ptr(noise), _ptr(noise_mask),
+                                    _ptr(out_counts), _stream()))
+        return out_counts
+
+    def search_host(self, boards, players, noise=None):
+        """numpy int8[n_games,n,m] boards + players -> (counts int32[n_games,A], child value sums f32)."""
+        b, w = bitboard.pack_boards(boards, self.rows, self.cols)
+        bd, wd = _to_dev(b, torch.int64), _to_dev(w, torch.int64)
+        pd = _to_dev(np.asarray(players, np.int8), torch.int8)
+        nz = nm = None
+        if noise is not None:
+            full = np.zeros((self.n_games, self.A), dtype=np.float64)
+            mask = np.zeros(self.n_games, dtype=np.uint8)
+            for g, nzg in enumerate(noise):
+                if nzg is not None and len(nzg):
+                    full[g, : len(nzg)] = nzg
+                    mask[g] = 1
+            nz, nm = _to_dev(full, torch.float64), _to_dev(mask, torch.uint8)
+        counts = self.search(bd, wd, pd, nz, nm)
+        cw = torch.empty((self.n_games, self.A), dtype=torch.float32, device=self.tdev)
+        c2 = torch.empty_like(counts)
+        _lib.check(self.L.yy_search_counts(self.handle, _ptr(c2), _ptr(cw), _stream()))
+        return counts.cpu().numpy(), cw.cpu().numpy()
+
+    # -- external-evaluator stepping
+    def search_begin(self, black, white, players, noise=None, noise_mask=None):
+        _lib.check(self.L.yy_search_begin(self.handle, _ptr(black), _ptr(white), _ptr(players), _ptr(noise),
+                                          _ptr(noise_mask), _stream()))
+
+    def search_advance(self, priors=None, values=None) -> int:
+        active = ctypes.c_int32(0)
+        _lib.check(self.L.yy_search_advance(self.handle, _ptr(priors), _ptr(values), ctypes.byref(active), _stream()))
+        return int(active.value)
+
+    def leaf_batch(self):
+        """(black int64[n_games,W], white, active uint8[n_games]) views of the pending leaf batch."""
+        def view(ptr, n, dtype):
+            off = ptr - self.workspace.data_ptr()
+            return self.workspace[off: off + n].view(dtype)
+        nb = self.n_games * self.W * 8
+        return (view(self.L.yy_engine_leaf_black(self.handle), nb, torch.int64).view(self.n_games, self.W),
+                view(self.L.yy_engine_leaf_white(self.handle), nb, torch.int64).view(self.n_games, self.W),
+                view(self.L.yy_engine_leaf_active(self.handle), self.n_games, torch.uint8))
+
+    def search_counts(self):
+        counts = torch.empty((self.n_games, self.A), dtype=torch.int32, device=self.tdev)
+        cw = torch.empty((self.n_games, self.A), dtype=torch.float32, device=self.tdev)
+        _lib.check(self.L.yy_search_counts(self.handle, _ptr(counts), _ptr(cw), _stream()))
+        return counts, cw
+
+    # -- evaluator on an arbitrary batch (batched predict)
+    def evaluate(self, black, white, want_logits=False):
+        n = black.shape[0]
+        policy = torch.empty((n, self.A), dtype=torch.float32, device=self.tdev)
+        value = torch.empty(n, dtype=torch.float32, device=self.tdev)
+        logits = torch.empty((n, self.A), dtype=torch.float32, device=self.tdev) if want_logits else None
+        _lib.check(self.L.yy_evaluate(self.handle, _ptr(black), _ptr(white), n, _ptr(policy), _ptr(value), _ptr(logits),
+                                      _stream()))
+        return (policy, value, logits) if want_logits else (policy, value)
+
+    def evaluate_host(self, boards, want_logits=False):
+        b, w = bitboard.pack_boards(boards, self.rows, self.cols)
+        out = self.evaluate(_to_dev(b, torch.int64), _to_dev(w, torch.int64), want_logits)
+        return tuple(o.cpu().numpy() for o in out)
+
+    # -- self-play
+    def selfplay_reset(self):
+        _lib.check(self.L.yy_selfplay_reset(self.handle, _stream()))
+
+    def selfplay_run(self, n_moves: int):
+        """Asynchronous: enqueues n_moves full searches + moves per game slot on the current stream."""
+        _lib.check(self.L.yy_selfplay_run(self.handle, int(n_moves), _stream()))
+
+    def stats(self) -> Stats:
+        s = _lib.SelfPlayStats()
+        _lib.check(self.L.yy_selfplay_get_stats(self.handle, ctypes.byref(s), _stream()))
+        return Stats(s.moves, s.evals, s.games_finished, s.examples, s.sims, s.overflow, s.max_depth)
+
+    def replay(self):
+        """Copies the replay ring to the host: dict(boards int8[N,n,m], counts uint16[N,A], pi float64[N,A],
+        game_serial, ply, player, z float64[N] (NaN while the game is unfinished))."""
+        st = self.stats()
+        n = min(st.examples, self.replay_capacity)
+        v = _lib.ReplayView()
+        _lib.check(self.L.yy_selfplay_replay(self.handle, ctypes.byref(v)))
+        base = self.workspace.data_ptr()
+
+        def view(ptr, nbytes):
+            return self.workspace[ptr - base: ptr - base + nbytes]
+        bl = view(v.black, n * self.W * 8).cpu().numpy().view(np.uint64).reshape(n, self.W)
+        wh = view(v.white, n * self.W * 8).cpu().numpy().view(np.uint64).reshape(n, self.W)
+        counts = view(v.counts, n * self.A * 2).cpu().numpy().view(np.uint16).reshape(n, self.A)
+        serial = view(v.game_serial, n * 4).cpu().numpy().view(np.int32)
+        ply = view(v.ply, n * 2).cpu().numpy().view(np.int16)
+        player = view(v.player, n).cpu().numpy().view(np.int8)
+        results = view(v.results, v.results_capacity).cpu().numpy().view(np.int8)
+        tot = counts.sum(axis=1, keepdims=True).astype(np.float64)
+        pi = np.where(tot > 0, counts.astype(np.float64) / np.maximum(tot, 1), 1.0 / self.A)  # mcts.py:209-213
+        finished = np.zeros(v.results_capacity, dtype=bool)
+        z = np.full(n, np.nan)
+        code = results[serial % v.results_capacity]
+        z = np.where(code == 0, np.nan, result_from_code(code))
+        return {"boards": bitboard.unpack_boards(bl, wh, self.rows, self.cols), "counts": counts, "pi": pi,
+                "game_serial": serial, "ply": ply, "player": player, "z": z, "finished": ~np.isnan(z)}
+
+    def live_boards(self):
+        nb = self.n_games * self.W * 8
+        base = self.workspace.data_ptr()
+        pb, pw, pp = (self.L.yy_engine_game_black(self.handle), self.L.yy_engine_game_white(self.handle),
+                      self.L.yy_engine_game_player(self.handle))
+        bl = self.workspace[pb - base: pb - base + nb].cpu().numpy().view(np.uint64).reshape(self.n_games, self.W)
+        wh = self.workspace[pw - base: pw - base + nb].cpu().numpy().view(np.uint64).reshape(self.n_games, self.W)
+        pl = self.workspace[pp - base: pp - base + self.n_games].cpu().numpy().view(np.int8)
+        return bitboard.unpack_boards(bl, wh, self.rows, self.cols), pl
