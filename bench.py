@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- self-play moves/sec (8x8, 800 sims) on N B200s, plus env steps/sec (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[2] -- 8x8 board, default 128x10 network with the
+reference's random initialisation (torch.manual_seed(0)), 800 MCTS simulations per move, 4,096 concurrent
+self-play games per GPU.  One timed "step" = one move for every game slot = 4,096 full searches
+(801 leaf evaluations each) + action selection + state update, all enqueued by ONE C-ABI call
+(yy_selfplay_run).  value = moves/s of the whole job, state resident in HBM.  e2e = the same metric through
+the host-buffer search API (numpy boards in -> H2D -> 800-sim search -> visit counts D2H -> host-side action
+choice -> host-buffer state update), copies inside the timed region.  Weak scaling: 4,096 games per GPU at
+every N (N=8 is configs[3]'s 32,768 games); games are independent, so there is no data-path collective --
+NCCL only broadcasts the packed weight image before, and gathers replay records after, the timed region.
+
+--impl reference times the reference's CPU implementation of the same path (oracle/port.py, kind "port":
+the upstream code is pure Python and cannot travel to the GPU box) with one worker process per host core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS = COLS = 8
+GAMES_PER_GPU = int(os.environ.get("YY_BENCH_GAMES", 4096))
+SIMS = int(os.environ.get("YY_BENCH_SIMS", 800))
+CHANNELS, BLOCKS = 128, 10
+A = ROWS * COLS
+# algorithmic FLOPs (2*MAC) per leaf evaluation, SURVEY 8d / BASELINE.md section 3
+FLOPS_TOWER_PER_BOARD = 2 * A * (9 * 5 * CHANNELS + BLOCKS * 2 * 9 * CHANNELS * CHANNELS + CHANNELS * 64)   # conv layers
+FLOPS_PER_LEAF = FLOPS_TOWER_PER_BOARD + 2 * (32 * A * A + 32 * A * 256 + 256)                               # + FC heads = 380,584,448
+ENV_BYTES_PER_STEP = 6 * ((A + 7) // 8) + 4                                                                  # 52 B
+ENV_BOARDS = 65536
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="yyclk", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(s for s, p in zip(sm, pw) if p > 0.5 * max(pw)) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_selfplay_sample(workers, searches_per_worker=1, sims=SIMS):
+    """(moves/s, cores, description): oracle port, one process per core, 1 torch thread each, empty 8x8 root."""
+    from oracle import port
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        times = pool.map(port._worker, [(ROWS, COLS, sims, searches_per_worker, CHANNELS, BLOCKS, 1, i) for i in range(workers)])
+    total = workers * searches_per_worker
+    return total / max(times), workers, (f"{total} searches of {sims} sims from the empty 8x8 board, {workers} worker processes x 1 torch thread "
+                                        f"(reference scaling axis: --workers), slowest worker {max(times):.1f}s")
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    workers = max(1, min(cpu_cores(), int(os.environ.get("YY_CPU_WORKERS", 64))))
+    sims = SIMS
+    vals = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_selfplay_sample(workers, 1, sims)
+        if i >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "self-play moves/sec (8x8, 800 sims)", "value": value, "unit": "moves/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * workers / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "moves/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": f"BASELINE.json configs[2]: 8x8, {SIMS} sims/move, {GAMES_PER_GPU} concurrent self-play games per GPU, "
+                        f"128ch x 10 residual blocks, reference random init (torch.manual_seed(0)); weak scaling",
+            "board": "8x8", "sims_per_move": SIMS, "games_per_gpu": GAMES_PER_GPU, "global_games": GAMES_PER_GPU * n_gpus,
+            "network": "128x10", "parallelism": f"games sharded over {n_gpus} GPU(s), no data-path collective",
+            "semantics": "deterministic sequential MCTS per game (1 leaf/game/step), search-as-black (reference self_play.py:99,135)",
+            "l2_policy": "inputs larger than L2: per step the kernels stream 801 x 7.3 MB of weights from L2 and the tree arenas (3.8 GB) live in HBM"}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import yy_b200  # noqa: F401
+    from yinyang_game_alphazero_b200 import engine, weights, distributed as yyd
+    from oracle import port  # only build_net (the reference initialisation) and the cpu_baseline leg use it
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = measured_peaks()
+
+    # weights: reference init on rank 0, packed, broadcast over NCCL (north star: weights broadcast)
+    torch.manual_seed(0)
+    sd = port.build_net(ROWS, COLS, CHANNELS, BLOCKS).state_dict()
+    eng = engine.Engine(rows=ROWS, cols=COLS, n_games=GAMES_PER_GPU, n_sims=SIMS, evaluator="nn", state_dict=sd,
+                        seed=0xC0FFEE + rank, replay_capacity=GAMES_PER_GPU * (args.steps + args.warmup + 2))
+    t_bcast = yyd.broadcast_weights(eng) if world > 1 else 0.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = engine._lib.lib().yy_launch_count()
+    for _ in range(args.warmup):
+        eng.selfplay_run(1)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.set_profiling(True)
+    launches1 = engine._lib.lib().yy_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        eng.selfplay_run(1)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = eng.get_profile()
+    eng.set_profiling(False)
+    clocks = sampler.stop()
+    launches = engine._lib.lib().yy_launch_count() - launches1
+    st = eng.stats()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    moves = GAMES_PER_GPU * world * args.steps
+    value = moves / (ms * 1e-3)
+
+    # replay gather (north star: gather replay samples over NCCL), outside the timed region
+    t_gather, n_records = (yyd.gather_replay_counts(eng) if world > 1 else (0.0, min(st.examples, eng.replay_capacity)))
+
+    # ---- e2e: host-buffer search API, copies inside the timed region
+    e2e_steps = max(1, min(args.steps, 2))
+    boards, players = eng.live_boards()
+    players_s = np.ones_like(players)            # reference semantics: search as player 1 (self_play.py:135)
+    rng = np.random.default_rng(rank)
+    h2d = boards.shape[0] * (2 * 8 + 1) * 2 + boards.shape[0] * 4
+    d2h = boards.shape[0] * A * 4 + boards.shape[0] * (2 * 8 + 1)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        counts, _ = eng.search_host(boards, players_s)
+        tot = counts.sum(axis=1)
+        acts = np.array([rng.choice(A, p=c / t) if t > 0 else -1 for c, t in zip(counts, tot)], dtype=np.int32)
+        boards, players = engine.next_state_host(boards, players, acts, ROWS, COLS)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = GAMES_PER_GPU * world * e2e_steps / e2e_s
+
+    # ---- env steps/s (BASELINE.json configs[1]): 65,536 synthetic random-play boards on this GPU
+    env = bench_env(engine, torch, peaks) if rank == 0 else None
+
+    if rank == 0:
+        tower_s = prof["ms"] * 1e-3 / max(1, prof["launches"])
+        boards_per_launch = prof["boards"] / max(1, prof["launches"])
+        achieved = FLOPS_TOWER_PER_BOARD * boards_per_launch / tower_s / 1e12 if prof["launches"] else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "tower_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roof = {"bound": "tensor", "kernel": "tower_kernel", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_tflops_sustained"]) if achieved else None, "traffic": traffic,
+                "peak_source": f"bf16_tflops_sustained of {peaks['source']} (kernel timed inside a long step)",
+                "launches_timed": prof["launches"], "avg_launch_ms": tower_s * 1e3,
+                "share_of_step": prof["ms"] / ms if ms else None,
+                "algorithmic_flops_per_launch": FLOPS_TOWER_PER_BOARD * boards_per_launch}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            workers = max(1, min(cpu_cores(), int(os.environ.get("YY_CPU_WORKERS", 64))))
+            v, cores, sample = cpu_selfplay_sample(workers, 1, SIMS)
+            cpu = {"value": v, "unit": "moves/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {"metric": "self-play moves/sec (8x8, 800 sims)", "value": value, "unit": "moves/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "steps": e2e_steps, "api": "Engine.search_host + next_state_host (numpy in/out)"},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "env": env,
+                "moves_per_s_roofline": peaks["bf16_tflops_sustained"] * 1e12 / ((SIMS + 1) * FLOPS_PER_LEAF) * world,
+                "leaf_evals_per_s": (SIMS + 1) * value,
+                "nccl": {"weight_broadcast_s": t_bcast, "replay_gather_s": t_gather, "replay_records_gathered": int(n_records)},
+                "selfplay_stats": st.__dict__}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_env(engine, torch, peaks):
+    import numpy as np
+    plies = torch.arange(ENV_BOARDS, dtype=torch.int32) % 52
+    black0, white0, players0 = engine.random_playout(ENV_BOARDS, plies, ROWS, COLS, seed=0xC0FFEE)
+    mask0 = engine.legal_mask(black0, white0, players0, ROWS, COLS)
+    from yinyang_game_alphazero_b200 import bitboard
+    bits = bitboard.unpack_bits(mask0.cpu().numpy().view(np.uint64), ROWS, COLS)
+    acts_h = np.where(bits.any(axis=1), bits.argmax(axis=1), -1).astype(np.int32)   # lowest legal move, else -1
+    acts = torch.from_numpy(acts_h).cuda()
+    out_mask, out_res = torch.empty_like(black0), torch.empty_like(players0)
+    reps, inner = 20, 8
+    bufs = [(black0.clone(), white0.clone(), players0.clone()) for _ in range(inner)]
+    for b, w, p in bufs[:3]:
+        engine.env_step(b, w, p, acts, ROWS, COLS, out_mask=out_mask, out_result=out_res)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total_ms = 0.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for r in range(reps):
+        bufs = [(black0.clone(), white0.clone(), players0.clone()) for _ in range(inner)]
+        flush.fill_(r)                                  # L2 flush: write a buffer larger than L2 (126 MB)
+        torch.cuda.synchronize()
+        ev0.record()
+        for b, w, p in bufs:
+            engine.env_step(b, w, p, acts, ROWS, COLS, out_mask=out_mask, out_result=out_res)
+        ev1.record(); torch.cuda.synchronize()
+        total_ms += ev0.elapsed_time(ev1)
+    per_launch_s = total_ms * 1e-3 / (reps * inner)
+    steps_s = ENV_BOARDS / per_launch_s
+    # e2e: host buffers
+    boards = bitboard.unpack_boards(black0.cpu().numpy().view(np.uint64), white0.cpu().numpy().view(np.uint64), ROWS, COLS)
+    pl, ac = players0.cpu().numpy(), acts.cpu().numpy()
+    engine.env_step_host(boards, pl, ac, ROWS, COLS)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        engine.env_step_host(boards, pl, ac, ROWS, COLS)
+    e2e = 3 * ENV_BOARDS / (time.perf_counter() - t0)
+    gbs = ENV_BYTES_PER_STEP * ENV_BOARDS / per_launch_s / 1e9
+    return {"metric": "env steps/sec (8x8)", "workload": "BASELINE.json configs[1]: 65,536 synthetic random-play boards, fused mask+step+ended",
+            "value": steps_s, "unit": "steps/s", "us_per_launch": per_launch_s * 1e6,
+            "e2e": {"value": e2e, "unit": "steps/s", "api": "env_step_host (int8 numpy boards in/out, pack/unpack on host)"},
+            "roofline": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                         "note": "3.4 MB of algorithmic traffic per launch: launch/latency bound at this batch size"},
+            "l2_policy": "L2 flushed (256 MB write) before each timed group of 8 launches on fresh copies"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -173,6 +173,12 @@ const uint8_t *yy_engine_leaf_active(yy_engine *e);
 int yy_evaluate(yy_engine *e, const uint64_t *black_dev, const uint64_t *white_dev, int64_t count,
                 float *out_policy_dev, float *out_value_dev, float *out_logits_dev, void *stream);
 
+/* Optional CUDA-event timing of the dominant kernel (the residual-tower kernel), recorded on the launching
+ * stream around every launch while enabled.  yy_engine_get_profile synchronises on the recorded events and
+ * returns totals since profiling was enabled: launches, summed device milliseconds, boards evaluated. */
+int yy_engine_set_profiling(yy_engine *e, int enable);
+int yy_engine_get_profile(yy_engine *e, int64_t *tower_launches, double *tower_ms, int64_t *tower_boards);
+
 /* Self-play driver (SelfPlayWorker.play_game, self_play.py:72-192, for n_games games in
  * lock-step; finished games restart from the empty board).  Plays `n_moves` moves per game
  * slot (one move = one full search + action selection + state update).  Examples are appended

@@ -382,7 +382,35 @@ int nn_init(NNState& nn, const yy_engine_config& cfg, void* scratch) {
   nn.attrs_set = true;
   return YY_OK;
 }
-void nn_destroy(NNState&) {}
+static int nn_drain_events(NNState& nn) {
+  for (int i = 0; i < nn.ev_used; ++i) {
+    YY_CUDA_OK(cudaEventSynchronize(nn.ev[2 * i + 1]));
+    float ms = 0.0f;
+    YY_CUDA_OK(cudaEventElapsedTime(&ms, nn.ev[2 * i], nn.ev[2 * i + 1]));
+    nn.tower_ms += ms;
+  }
+  nn.ev_used = 0;
+  return YY_OK;
+}
+void nn_destroy(NNState& nn) {
+  if (nn.ev) { for (int i = 0; i < 2 * nn.ev_cap; ++i) cudaEventDestroy(nn.ev[i]); delete[] nn.ev; nn.ev = nullptr; }
+}
+int nn_set_profiling(NNState& nn, int enable) {
+  if (enable && !nn.ev) {
+    nn.ev_cap = 1024;
+    nn.ev = new cudaEvent_t[2 * nn.ev_cap];
+    for (int i = 0; i < 2 * nn.ev_cap; ++i) YY_CUDA_OK(cudaEventCreate(&nn.ev[i]));
+  }
+  nn.profiling = enable != 0; nn.ev_used = 0; nn.tower_launches = 0; nn.tower_ms = 0.0; nn.tower_boards = 0;
+  return YY_OK;
+}
+int nn_get_profile(NNState& nn, long long* launches, double* total_ms, long long* boards) {
+  int rc = nn_drain_events(nn); if (rc) return rc;
+  if (launches) *launches = nn.tower_launches;
+  if (total_ms) *total_ms = nn.tower_ms;
+  if (boards) *boards = nn.tower_boards;
+  return YY_OK;
+}
 
 int nn_load_weights(NNState& nn, const void* weights, int64_t bytes) {
   int64_t need = nn_weight_bytes(nn.rows, nn.cols, nn.channels, nn.blocks);
@@ -416,8 +444,16 @@ int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_
     ta.count = n; ta.n_groups = (int)((n + ta.g.Gb - 1) / ta.g.Gb);
     ta.headfeat = headfeat;
     const int grid = ta.n_groups < nn.num_sms ? ta.n_groups : nn.num_sms;
+    if (nn.profiling) {
+      if (nn.ev_used == nn.ev_cap) { int rc = nn_drain_events(nn); if (rc) return rc; }
+      YY_CUDA_OK(cudaEventRecord(nn.ev[2 * nn.ev_used], s));
+    }
     tower_kernel<<<grid, TW_THREADS, SM_TOTAL, s>>>(ta);
     YY_LAUNCH_CHECK();
+    if (nn.profiling) {
+      YY_CUDA_OK(cudaEventRecord(nn.ev[2 * nn.ev_used + 1], s));
+      ++nn.ev_used; ++nn.tower_launches; nn.tower_boards += n;
+    }
     GemmArgs gp{headfeat, TW_HEADC * A, reinterpret_cast<const __nv_bfloat16*>(wimg + wl.fc_policy_w), 32 * A, logits_buf, wl.a_pad,
                 reinterpret_cast<const float*>(wimg + wl.fc_policy_b), (int)n, wl.a_pad, 32 * A, 0};
     int rc = gemm_bf16_tn(gp, s); if (rc) return rc;

@@ -14,6 +14,11 @@ struct NNState {
   int64_t scratch_bytes;
   int device, num_sms;
   bool attrs_set;
+  // optional CUDA-event timing of the tower kernel (bench.py's live roofline figure)
+  bool profiling;
+  cudaEvent_t* ev;           // 2 * ev_cap events
+  int ev_cap, ev_used;
+  long long tower_launches; double tower_ms; long long tower_boards;
 };
 
 int64_t nn_weight_bytes(int rows, int cols, int channels, int blocks);
@@ -21,6 +26,9 @@ size_t nn_workspace_bytes(const yy_engine_config& cfg);
 int nn_init(NNState& nn, const yy_engine_config& cfg, void* scratch);
 void nn_destroy(NNState& nn);
 int nn_load_weights(NNState& nn, const void* weights_dev, int64_t bytes);
+int nn_set_profiling(NNState& nn, int enable);
+// drains recorded event pairs (synchronises) and returns totals since profiling was enabled
+int nn_get_profile(NNState& nn, long long* launches, double* total_ms, long long* boards);
 // black/white: [count][W] bitboards on the device.  policy [count][A] = softmax(logits) (neural_network.py:152),
 // value [count] = tanh head, logits [count][A] optional.  count <= max_boards per call is chunked internally.
 int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_t count, float* policy, float* value,

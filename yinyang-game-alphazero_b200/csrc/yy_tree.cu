@@ -614,6 +614,20 @@ int yy_evaluate(yy_engine* e, const uint64_t* black, const uint64_t* white, int6
   return set_error(YY_ERR_STATE, "yy_evaluate needs the STUB or NN evaluator");
 }
 
+int yy_engine_set_profiling(yy_engine* e, int enable) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  return nn_set_profiling(e->nn, enable);
+}
+int yy_engine_get_profile(yy_engine* e, int64_t* tower_launches, double* tower_ms, int64_t* tower_boards) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  long long l = 0, b = 0; double ms = 0.0;
+  int rc = nn_get_profile(e->nn, &l, &ms, &b); if (rc) return rc;
+  if (tower_launches) *tower_launches = l;
+  if (tower_ms) *tower_ms = ms;
+  if (tower_boards) *tower_boards = b;
+  return YY_OK;
+}
+
 int yy_selfplay_reset(yy_engine* e, void* stream) {
   if (!e) return set_error(YY_ERR_INVALID, "null engine");
   sp_reset_kernel<<<thread_grid(e->dev.n_games, 128), 128, 0, (cudaStream_t)stream>>>(e->dev);

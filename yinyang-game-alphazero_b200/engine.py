@@ -315,6 +315,16 @@ class Engine:
         out = self.evaluate(_to_dev(b, torch.int64), _to_dev(w, torch.int64), want_logits)
         return tuple(o.cpu().numpy() for o in out)
 
+    # -- profiling of the dominant kernel
+    def set_profiling(self, enable=True):
+        _lib.check(self.L.yy_engine_set_profiling(self.handle, 1 if enable else 0))
+
+    def get_profile(self):
+        """-> dict(launches, ms, boards) of the tower kernel since set_profiling(True)."""
+        l, b, ms = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_double(0)
+        _lib.check(self.L.yy_engine_get_profile(self.handle, ctypes.byref(l), ctypes.byref(ms), ctypes.byref(b)))
+        return {"launches": int(l.value), "ms": float(ms.value), "boards": int(b.value)}
+
     # -- self-play
     def selfplay_reset(self):
         _lib.check(self.L.yy_selfplay_reset(self.handle, _stream()))
