@@ -178,6 +178,9 @@ int yy_evaluate(yy_engine *e, const uint64_t *black_dev, const uint64_t *white_d
  * returns totals since profiling was enabled: launches, summed device milliseconds, boards evaluated. */
 int yy_engine_set_profiling(yy_engine *e, int enable);
 int yy_engine_get_profile(yy_engine *e, int64_t *tower_launches, double *tower_ms, int64_t *tower_boards);
+/* Developer tool: while dbg_dev != NULL the tower kernel's CTA 0 writes, for its first group, four clock64
+ * stamps per layer (MMA issue start / end, epilogue start / end) into dbg_dev[4*layer .. 4*layer+3]. */
+int yy_engine_set_debug_stamps(yy_engine *e, long long *dbg_dev);
 
 /* Self-play driver (SelfPlayWorker.play_game, self_play.py:72-192, for n_games games in
  * lock-step; finished games restart from the empty board).  Plays `n_moves` moves per game

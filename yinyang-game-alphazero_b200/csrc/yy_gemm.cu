@@ -215,3 +215,66 @@ extern "C" int yy_probe_umma(const void* a, const void* b, float* c, int M, int 
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ UMMA rate bench
+// Developer tool: issues `iters` rounds of `per_round` back-to-back tcgen05.mma (M=128, N, K=16) from one thread on
+// zero-filled shared memory, with caller-chosen descriptor strides / swizzle mode, on every SM, and reports the
+// SM cycles per MMA.  Used to choose the shared-memory layouts of the tower kernel (operand-fetch rate).
+namespace yy {
+__global__ void __launch_bounds__(128) umma_rate_kernel(int N, int layout_type, uint32_t lbo_a, uint32_t sbo_a, uint32_t lbo_b,
+                                                       uint32_t sbo_b, uint32_t a_step, uint32_t b_step, int per_round, int iters,
+                                                       long long* out_cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x < 32) {   // whole warp runs the loop; one elected lane issues (the pattern the tower kernel uses)
+    const uint32_t idesc = idesc_bf16(128, N);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 150 * 1024;
+    const uint64_t lt = (uint64_t)layout_type << 61;
+    const uint64_t ad0 = smem_desc(a0, lbo_a, sbo_a) | lt, bd0 = smem_desc(b0, lbo_b, sbo_b) | lt;
+    const uint64_t da = a_step >> 4, db = b_step >> 4;
+    const uint32_t dcol = N > 128 ? 0u : 128u;
+    uint32_t phase = 0;
+    long long total = 0;
+    for (int it = 0; it < iters; ++it) {
+      long long t0 = clock64();
+      for (int i = 0; i < per_round; i += 16) {
+        if (elect_one()) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            tc_mma_bf16(tmem_base + (uint32_t)(u & 3) * dcol, ad0 + (uint64_t)(u & 7) * da, bd0 + (uint64_t)(u >> 2) * db, idesc, 1u);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(smem_u32(&bar));
+      __syncwarp();
+      mbar_wait(smem_u32(&bar), phase); phase ^= 1;
+      total += clock64() - t0;
+    }
+    if (threadIdx.x == 0) out_cycles[blockIdx.x] = total;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
+}
+}  // namespace yy
+
+extern "C" int yy_umma_rate(int N, int layout_type, int lbo_a, int sbo_a, int lbo_b, int sbo_b, int a_step, int b_step,
+                            int per_round, int iters, int n_ctas, long long* out_cycles_dev, void* stream) {
+  using namespace yy;
+  if (yy_device_count() == 0) return set_error(YY_ERR_NO_DEVICE, "no CUDA device");
+  const int smem = 200 * 1024;
+  YY_CUDA_OK(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_rate_kernel<<<n_ctas, 128, smem, (cudaStream_t)stream>>>(N, layout_type, lbo_a, sbo_a, lbo_b, sbo_b, a_step, b_step,
+                                                                 per_round, iters, out_cycles_dev);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}

@@ -16,7 +16,8 @@
 //   M=128 tiles of the group).  Accumulators live in TMEM (4 tiles x 128 fp32 columns = all 512 columns).
 //   The skip connection never touches shared memory: conv1's epilogue re-loads the block input into the
 //   TMEM accumulator (tcgen05.st) before overwriting it in place, and conv2 accumulates on top of it.
-//   Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one thread), warps 2-9 = epilogue.
+//   Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one elected thread), warps 2-17 = epilogue
+//   (one warp per tile x TMEM lane quarter, software-pipelined tcgen05.ld).
 //   Roofline: tensor.  Algorithmic FLOPs per board: 2*A*(9*16*C + blocks*2*9*C*C + C*64)  (+ FC heads).
 // Kernel 2/3  gemm_bf16_tn (yy_gemm.cu): policy FC and value FC1 on tensor cores over the whole batch.
 // Kernel 4  heads_finish_kernel: softmax, value FC2 + tanh.
@@ -38,8 +39,9 @@ constexpr int TW_PAD = 24;             // zero rows before/after the group's pos
 constexpr int TW_ROWS = 128 * TW_MAXT + 2 * TW_PAD;  // 560
 constexpr int TW_STAGES = 5;
 constexpr int TW_STAGE_BYTES = 16384;
-constexpr int TW_THREADS = 320;
-constexpr int TW_EPI_THREADS = 256;
+constexpr int TW_EPI_WARPS = 16;           // one (tile, TMEM-lane-quarter) pair per warp
+constexpr int TW_THREADS = 64 + 32 * TW_EPI_WARPS;
+constexpr int TW_EPI_THREADS = 32 * TW_EPI_WARPS;
 
 constexpr int SM_ACT = 0;
 constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 143360
@@ -62,6 +64,7 @@ struct TowerArgs {
   long long count;
   int n_groups;
   __nv_bfloat16* headfeat;     // [count][64*A], index c*A + cell (matches .view(-1, 32*n*m), neural_network.py:112,117)
+  long long* dbg;              // optional per-layer clock64 stamps of CTA 0's first group (developer tool), else nullptr
 };
 
 // ---- weight-stream geometry shared by producer and MMA issuer ----
@@ -129,64 +132,80 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
   const uint32_t ring_base = smem_u32(smem + SM_RING);
 
   if (warp == 0) {
-    // =========================================================== weight producer (one thread)
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
-        for (int l = 0; l < L; ++l) {
-          const LayerInfo li = layer_info(l, g.blocks);
-          for (int j = 0; j < li.n_stages; ++j, ++it) {
-            const uint32_t slot = it % TW_STAGES;
-            if (it >= TW_STAGES) mbar_wait(empty_bar(slot), ((it / TW_STAGES) - 1) & 1);
+    // =========================================================== weight producer (whole warp walks the loop with
+    // warp-uniform state; one elected lane issues the bulk copies -- keeps everything on the uniform datapath)
+    uint32_t it = 0;
+    for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+      for (int l = 0; l < L; ++l) {
+        const LayerInfo li = layer_info(l, g.blocks);
+        const uint8_t* src = a.conv_stream + li.stream_off;
+        for (int j = 0; j < li.n_stages; ++j, ++it) {
+          const uint32_t slot = it % TW_STAGES;
+          if (it >= TW_STAGES) mbar_wait(empty_bar(slot), ((it / TW_STAGES) - 1) & 1);
+          if (elect_one()) {
             mbar_arrive_expect_tx(full_bar(slot), (uint32_t)li.stage_bytes);
-            bulk_g2s(ring_base + slot * TW_STAGE_BYTES, a.conv_stream + li.stream_off + (long long)j * li.stage_bytes,
-                     (uint32_t)li.stage_bytes, full_bar(slot));
+            bulk_g2s(ring_base + slot * TW_STAGE_BYTES, src + (long long)j * li.stage_bytes, (uint32_t)li.stage_bytes, full_bar(slot));
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // =========================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      uint32_t it = 0, act_phase = 0;
-      for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
-        for (int l = 0; l < L; ++l) {
-          const LayerInfo li = layer_info(l, g.blocks);
-          const bool preloaded = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 0);  // conv2: accumulator holds the skip input
-          const uint32_t idesc = idesc_bf16(128, li.N);
-          mbar_wait(act_ready, act_phase); act_phase ^= 1;
+    // =========================================================== MMA issuer (whole warp runs the control flow, the
+    // tcgen05.mma / commit instructions are issued by one elected lane; descriptors are base + constant deltas)
+    uint32_t it = 0, act_phase = 0;
+    constexpr uint64_t kTileDelta = (128u * 16u) >> 4;           // next M=128 tile: +128 rows of 16 B
+    constexpr uint64_t kK16DeltaA = (2u * TW_ROWS * 16u) >> 4;   // next K=16 slice: +2 channel chunks
+    for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+      for (int l = 0; l < L; ++l) {
+        const LayerInfo li = layer_info(l, g.blocks);
+        const bool preloaded = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 0);  // conv2: accumulator holds the skip input
+        const uint32_t idesc = idesc_bf16(128, li.N);
+        const uint64_t k16_delta_b = (uint64_t)((2u * (uint32_t)li.N * 16u) >> 4);
+        mbar_wait(act_ready, act_phase); act_phase ^= 1;
+        tc_fence_after();
+        if (a.dbg && blockIdx.x == 0 && grp == 0 && lane == 0) a.dbg[l * 4 + 0] = clock64();
+        for (int j = 0; j < li.n_stages; ++j, ++it) {
+          const uint32_t slot = it % TW_STAGES;
+          int tapshift, chunk0;
+          stage_info(l, j, g.blocks, g.pitch, tapshift, chunk0);
+          mbar_wait(full_bar(slot), (it / TW_STAGES) & 1);
           tc_fence_after();
-          for (int j = 0; j < li.n_stages; ++j, ++it) {
-            const uint32_t slot = it % TW_STAGES;
-            int tapshift, chunk0;
-            stage_info(l, j, g.blocks, g.pitch, tapshift, chunk0);
-            mbar_wait(full_bar(slot), (it / TW_STAGES) & 1);
-            tc_fence_after();
-            const uint32_t b_stage = ring_base + slot * TW_STAGE_BYTES;
-            for (int t = 0; t < g.T; ++t) {
-              const uint32_t a_row = act_base + (uint32_t)((TW_PAD + t * 128 + tapshift) * 16);
-              for (int k = 0; k < li.nk16; ++k) {
-                const uint64_t ad = smem_desc(a_row + (uint32_t)((chunk0 + 2 * k) * TW_ROWS * 16), TW_ROWS * 16, 128);
-                const uint64_t bd = smem_desc(b_stage + (uint32_t)(2 * k * li.N * 16), (uint32_t)li.N * 16, 128);
-                tc_mma_bf16(tmem_base + (uint32_t)(t * 128), ad, bd, idesc, (preloaded || j > 0 || k > 0) ? 1u : 0u);
+          const uint64_t ad0 = smem_desc(act_base + (uint32_t)((chunk0 * TW_ROWS + TW_PAD + tapshift) * 16), TW_ROWS * 16, 128);
+          const uint64_t bd0 = smem_desc(ring_base + slot * TW_STAGE_BYTES, (uint32_t)li.N * 16, 128);
+          const uint32_t acc0 = (preloaded || j > 0) ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < TW_MAXT; ++t) {
+              if (t < g.T) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < li.nk16)
+                    tc_mma_bf16(tmem_base + (uint32_t)(t * 128), ad0 + (uint64_t)t * kTileDelta + (uint64_t)k * kK16DeltaA,
+                                bd0 + (uint64_t)k * k16_delta_b, idesc, k > 0 ? 1u : acc0);
+                }
               }
             }
             tc_commit(empty_bar(slot));
           }
-          tc_commit(acc_full);
+          __syncwarp();
         }
+        if (elect_one()) tc_commit(acc_full);
+        __syncwarp();
+        if (a.dbg && blockIdx.x == 0 && grp == 0 && lane == 0) a.dbg[l * 4 + 1] = clock64();
       }
     }
   } else {
-    // =========================================================== epilogue warps (2..9)
+    // =========================================================== epilogue warps (2..17): warp -> (tile, lane quarter)
     const int ew = warp - 2;
     const int quarter = warp & 3;        // TMEM lanes a warp may touch: 32*(warp_id % 4) ..
-    const int set = ew >> 2;             // tiles set, set+2
+    const int tile0 = ew >> 2;           // with 16 warps every tile of the group has its own 4 warps
+    constexpr int kTileStride = TW_EPI_WARPS / 4;
     uint32_t acc_phase = 0;
     uint8_t* act = smem + SM_ACT;
     for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
       // ---- stem input planes (board_to_input, neural_network.py:156-196) for my rows ----
-      for (int t = set; t < g.T; t += 2) {
+      for (int t = tile0; t < g.T; t += kTileStride) {
         const int p = t * 128 + quarter * 32 + lane;
         const int info = pos_tab[p];
         uint4 c0 = make_uint4(0, 0, 0, 0);
@@ -220,7 +239,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
         const float* bias = a.conv_bias + (size_t)l * TW_C;
         mbar_wait(acc_full, acc_phase); acc_phase ^= 1;
         tc_fence_after();
-        for (int t = set; t < g.T; t += 2) {
+        if (a.dbg && blockIdx.x == 0 && grp == 0 && tid == 64) a.dbg[l * 4 + 2] = clock64();
+        for (int t = tile0; t < g.T; t += kTileStride) {
           const int p = t * 128 + quarter * 32 + lane;
           const int info = pos_tab[p];
           const long long board = (long long)grp * g.Gb + (info >= 0 ? (info >> 8) : 0);
@@ -228,14 +248,11 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 128);
           uint8_t* rowp = act + (size_t)(TW_PAD + p) * 16;
           if (!is_head) {
-#pragma unroll 1
-            for (int cc = 0; cc < TW_C / 16; ++cc) {
-              uint32_t r[16];
-              tc_ld16(taddr + cc * 16, r);
-              tc_wait_ld();
+            // one 16-column chunk: bias + ReLU (+ park the skip input in TMEM) -> two 16-byte channel chunks in place
+            auto process = [&](const uint32_t (&r)[16], int cc) {
               uint4* d0 = reinterpret_cast<uint4*>(rowp + (size_t)(2 * cc) * TW_ROWS * 16);
               uint4* d1 = reinterpret_cast<uint4*>(rowp + (size_t)(2 * cc + 1) * TW_ROWS * 16);
-              if (is_conv1) {  // skip connection: park the block input in the accumulator conv2 will add to
+              if (is_conv1) {  // skip connection: conv2 will accumulate on top of the block input
                 const uint4 x0 = *d0, x1 = *d1;
                 uint32_t xr[16];
                 const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
@@ -243,11 +260,34 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
                 for (int q = 0; q < 8; ++q) { xr[2 * q] = xs[q] << 16; xr[2 * q + 1] = xs[q] & 0xffff0000u; }
                 tc_st16(taddr + cc * 16, xr);
               }
+              const float4* b4 = reinterpret_cast<const float4*>(bias + cc * 16);
               float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = real ? fmaxf(__uint_as_float(r[j]) + __ldg(bias + cc * 16 + j), 0.0f) : 0.0f;
+              for (int q = 0; q < 4; ++q) {
+                const float4 bq = __ldg(b4 + q);
+                v[4 * q + 0] = fmaxf(__uint_as_float(r[4 * q + 0]) + bq.x, 0.0f);
+                v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + bq.y, 0.0f);
+                v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + bq.z, 0.0f);
+                v[4 * q + 3] = fmaxf(__uint_as_float(r[4 * q + 3]) + bq.w, 0.0f);
+              }
+              if (!real) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+              }
               *d0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
               *d1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+            };
+            // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+            uint32_t ra[16], rb[16];
+            tc_ld16(taddr, ra);
+#pragma unroll 1
+            for (int cc = 0; cc < TW_C / 16; cc += 2) {
+              tc_wait_ld();
+              tc_ld16(taddr + (cc + 1) * 16, rb);
+              process(ra, cc);
+              tc_wait_ld();
+              if (cc + 2 < TW_C / 16) tc_ld16(taddr + (cc + 2) * 16, ra);
+              process(rb, cc + 1);
             }
             if (is_conv1) tc_wait_st();
           } else {
@@ -266,6 +306,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
           }
         }
         tc_fence_before();
+        if (a.dbg && blockIdx.x == 0 && grp == 0 && tid == 64) a.dbg[l * 4 + 3] = clock64();
         if (!is_head) { fence_proxy_async_smem(); mbar_arrive(act_ready); }
       }
     }
@@ -443,6 +484,7 @@ int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_
     ta.black = black + done * nn.W; ta.white = white + done * nn.W;
     ta.count = n; ta.n_groups = (int)((n + ta.g.Gb - 1) / ta.g.Gb);
     ta.headfeat = headfeat;
+    ta.dbg = nn.dbg;
     const int grid = ta.n_groups < nn.num_sms ? ta.n_groups : nn.num_sms;
     if (nn.profiling) {
       if (nn.ev_used == nn.ev_cap) { int rc = nn_drain_events(nn); if (rc) return rc; }

@@ -19,6 +19,7 @@ struct NNState {
   cudaEvent_t* ev;           // 2 * ev_cap events
   int ev_cap, ev_used;
   long long tower_launches; double tower_ms; long long tower_boards;
+  long long* dbg;            // device buffer for per-layer clock stamps (developer tool), usually nullptr
 };
 
 int64_t nn_weight_bytes(int rows, int cols, int channels, int blocks);

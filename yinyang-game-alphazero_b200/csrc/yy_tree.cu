@@ -618,6 +618,12 @@ int yy_engine_set_profiling(yy_engine* e, int enable) {
   if (!e) return set_error(YY_ERR_INVALID, "null engine");
   return nn_set_profiling(e->nn, enable);
 }
+// developer tool: per-layer clock64 stamps of the tower kernel's CTA 0 / first group into dbg_dev (>= 4*(2*blocks+2) int64)
+int yy_engine_set_debug_stamps(yy_engine* e, long long* dbg_dev) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  e->nn.dbg = dbg_dev;
+  return YY_OK;
+}
 int yy_engine_get_profile(yy_engine* e, int64_t* tower_launches, double* tower_ms, int64_t* tower_boards) {
   if (!e) return set_error(YY_ERR_INVALID, "null engine");
   long long l = 0, b = 0; double ms = 0.0;
