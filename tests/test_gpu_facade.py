@@ -1,0 +1,113 @@
+"""GPU tests of the reference-facing Python interface: they read like the reference's own usage
+(YinYangGame / MCTS.search / generate_self_play_data / train_alphazero.py modes)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_files, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg(yy):
+    from yinyang_game_alphazero_b200 import game, mcts, network, players, self_play
+    return dict(game=game, mcts=mcts, network=network, players=players, self_play=self_play)
+
+
+def test_game_surface_matches_reference_golden(pkg):
+    g = load_golden("rules_6x6.npz")
+    game = pkg["game"].YinYangGame(6, 6)
+    assert game.getBoardSize() == (6, 6) and game.getActionSize() == 36
+    for i in range(0, len(g["boards"]), 40):
+        b = game.getInitBoard()
+        b.board = g["boards"][i].copy()
+        vm = game.getValidMoves(b, 1)
+        assert vm.dtype == np.float64 and np.array_equal(vm.astype(np.uint8), g["mask_black"][i])
+        nb, npl = game.getNextState(b, int(g["players"][i]), int(g["actions"][i]))
+        assert np.array_equal(nb.board, g["next_boards"][i]) and npl == g["next_players"][i]
+        assert np.array_equal(b.board, g["boards"][i])                       # value semantics: input untouched
+        r = game.getGameEnded(b, -1)
+        assert r == g["ended_white"][i] and (isinstance(r, int) or r == 0.0001)
+        assert b.has_valid_move(1) == bool(g["mask_black"][i].any())
+        assert sorted(b.get_valid_moves(-1)) == [(a // 6, a % 6) for a in np.flatnonzero(g["mask_white"][i])]
+    e = game.getInitBoard()
+    assert e.place_piece(2, 3, 1) and e.board[2, 3] == 1 and not e.place_piece(2, 3, -1)
+    assert game._coords_to_action(*game._action_to_coords(17)) == 17
+    assert len(game.getSymmetries(e, np.arange(36) / 630.0)) == 8
+    assert isinstance(game.stringRepresentation(e), bytes)
+
+
+@pytest.mark.parametrize("name", ["mcts_6x6_s400.npz", "mcts_4x4_s300.npz", "mcts_8x8_s200_mid_white.npz"])
+def test_mcts_facade_matches_reference_golden(pkg, name):
+    """MCTS(game, evaluator, num_simulations=...).search(board, player) -> (probs, root), like mcts_tests.py."""
+    g = load_golden(name)
+    n, m = int(g["n"]), int(g["m"])
+    game = pkg["game"].YinYangGame(n, m)
+    board = game.getInitBoard()
+    board.board = g["board"].copy()
+    mcts = pkg["mcts"].MCTS(game, pkg["network"].HashStubEvaluator(game), num_simulations=int(g["sims"]),
+                            cpuct=float(g["cpuct"]), dirichlet_noise=False, verbose=0)
+    probs, root = mcts.search(board, int(g["player"]))
+    assert np.array_equal(root.get_children_visit_counts().astype(np.int32), g["counts"])
+    assert probs.dtype == np.float64 and np.array_equal(probs, g["probs"])   # float64 counts / sum (mcts.py:209)
+    assert abs(probs.sum() - 1.0) < 1e-12 and root.visits == int(g["root_visits"])
+    for a, ch in root.children.items():
+        assert ch.visits == g["counts"][a] and ch.value_sum == g["child_w"][a]
+    assert np.array_equal(board.board, g["board"])
+    mcts.close()
+
+
+def test_mcts_external_python_evaluator(pkg, oracle_mod):
+    """Any object with predict(board) plugs in (the reference's duck-typed seam, mcts_tests.py:22-32)."""
+    class PyStub:
+        calls = 0
+
+        def predict(self, board):
+            PyStub.calls += 1
+            return oracle_mod.stub_predict(board.get_board(), 6, 6)
+    game = pkg["game"].YinYangGame(6, 6)
+    mcts = pkg["mcts"].MCTS(game, PyStub(), num_simulations=50, dirichlet_noise=False, verbose=0)
+    probs, root = mcts.search(game.getInitBoard(), 1)
+    r = oracle_mod.mcts_search(np.zeros((6, 6), np.int8), 1, 6, 6, 50)
+    assert np.array_equal(root.get_children_visit_counts().astype(np.int32), r["counts"]) and PyStub.calls == 51
+    a = mcts.select_action(game.getInitBoard(), 1, temperature=0)
+    assert a == int(np.argmax(r["counts"]))
+    mcts.close()
+
+
+def test_network_predict_contract(pkg):
+    import torch
+    game = pkg["game"].YinYangGame(6, 6)
+    torch.manual_seed(0)
+    net = pkg["network"].YinYangNeuralNetwork(game, num_channels=32, num_res_blocks=2)
+    p, v = net.predict(game.getInitBoard())
+    assert p.shape == (36,) and p.dtype == np.float32 and abs(p.sum() - 1) < 1e-5 and -1 <= float(v) <= 1
+    assert isinstance(v, np.float32)
+
+
+def test_generate_self_play_data_and_cli(pkg, tmp_path):
+    import torch
+    import train_alphazero
+    game = pkg["game"].YinYangGame(4, 4)
+    model_dir, data_dir = tmp_path / "models", tmp_path / "data"
+    torch.manual_seed(0)
+    pkg["network"].YinYangNeuralNetwork(game).save_model(str(model_dir / "best_model.pth.tar"))
+    path = pkg["self_play"].generate_self_play_data(game, str(model_dir / "best_model.pth.tar"), str(data_dir),
+                                                    num_games=6, num_workers=2, num_simulations=16)
+    d = np.load(path, allow_pickle=True)
+    assert set(d.files) == {"boards", "policies", "values"}                     # self_play.py:379-384
+    N = len(d["values"])
+    assert N >= 6 and d["policies"].shape == (N, 16) and d["policies"].dtype == np.float64
+    np.testing.assert_allclose(d["policies"].sum(axis=1), 1.0, atol=1e-12)
+    assert np.all(np.isin(d["values"], [1.0, -1.0, 0.0001]))
+    assert d["boards"][0].get_board().shape == (4, 4) and hasattr(d["boards"][0], "board")
+    assert np.abs(d["boards"][0].board).sum() == 0                              # first example of game 0: empty board
+    # CLI modes
+    assert train_alphazero.main(["--mode", "self-play", "--rows", "4", "--cols", "4", "--simulations", "8", "--episodes", "3",
+                                 "--model-dir", str(model_dir), "--data-dir", str(data_dir)]) == 0
+    assert train_alphazero.main(["--mode", "evaluate", "--rows", "4", "--cols", "4", "--simulations", "8", "--eval-games", "2",
+                                 "--model-dir", str(model_dir), "--data-dir", str(data_dir)]) == 0
+    assert train_alphazero.main(["--mode", "self-play", "--model-dir", str(tmp_path / "none"), "--data-dir", str(data_dir)]) == 1
+    assert len([f for f in os.listdir(data_dir) if f.endswith(".npz")]) >= 1
