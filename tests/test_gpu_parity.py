@@ -43,6 +43,28 @@ def test_umma_descriptor_probe(yy, N, K, off):
     assert err < 1e-3 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("grp,off", [(9, 0), (9, 10), (9, 19), (10, 3), (17, 1)])
+def test_umma_strided_row_groups(yy, grp, off):
+    """SBO != 128: the MMA's 8-row groups start every `grp` rows (SBO = grp*16 B), so C row m reads A row
+    off + (m/8)*grp + m%8 -- the row-aligned tower layout (one board row per group, zero column skipped)."""
+    import ctypes
+    import torch
+    N, K = 128, 64
+    rows = off + 15 * grp + 8 + 3
+    g = torch.Generator(device="cpu").manual_seed(grp * 100 + off)
+    A = torch.randn(rows, K, generator=g).to(torch.bfloat16).cuda()
+    B = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
+    C = torch.zeros(128, N, dtype=torch.float32, device="cuda")
+    lib = yy._lib.lib()
+    rc = lib.yy_probe_umma(ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()), ctypes.c_void_p(C.data_ptr()),
+                           rows, N, K, off, grp, None)
+    assert rc == 0, lib.yy_last_error()
+    torch.cuda.synchronize()
+    idx = torch.tensor([off + (m // 8) * grp + m % 8 for m in range(128)], device="cuda")
+    ref = A[idx].float() @ B.float().t()
+    assert (C - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------------ rules
 @pytest.mark.parametrize("name", golden_files("rules_"))
 def test_rules_match_reference_golden(eng, name):

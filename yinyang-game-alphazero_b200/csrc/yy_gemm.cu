@@ -18,6 +18,9 @@ using namespace ptx;
 // Single CTA, everything resident: C[128,N] = A[row_off : row_off+128, :] * B^T.  rowsA >= row_off + 128.
 __global__ void __launch_bounds__(128) probe_umma_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
                                                         float* __restrict__ C, int rowsA, int N, int K, int row_off, int swap) {
+  // swap >= 2: 'strided-group' mode -- the MMA's 8-row groups start every `swap` rows of A (SBO = swap*16 B), i.e.
+  // C row m = A[row_off + (m/8)*swap + m%8]: what the tower kernel's row-aligned layout relies on (SBO = 9*16).
+  const int grp = swap >= 2 ? swap : 8;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -45,8 +48,8 @@ __global__ void __launch_bounds__(128) probe_umma_kernel(const __nv_bfloat16* __
     for (int k16 = 0; k16 < K / 16; ++k16) {
       uint32_t a_addr = smem_u32(a_s) + (uint32_t)((2 * k16 * rowsA + row_off) * 16);
       uint32_t b_addr = smem_u32(b_s) + (uint32_t)(2 * k16 * N * 16);
-      uint64_t ad = swap ? smem_desc(a_addr, 128, rowsA * 16) : smem_desc(a_addr, rowsA * 16, 128);
-      uint64_t bd = swap ? smem_desc(b_addr, 128, N * 16) : smem_desc(b_addr, N * 16, 128);
+      uint64_t ad = swap == 1 ? smem_desc(a_addr, 128, rowsA * 16) : smem_desc(a_addr, rowsA * 16, grp * 16);
+      uint64_t bd = swap == 1 ? smem_desc(b_addr, 128, N * 16) : smem_desc(b_addr, N * 16, 128);
       tc_mma_bf16(tmem_base, ad, bd, idesc, k16 > 0 ? 1u : 0u);
     }
     tc_commit(smem_u32(&bar));
@@ -205,7 +208,7 @@ extern "C" int yy_probe_umma(const void* a, const void* b, float* c, int M, int 
                              int swap_lbo_sbo, void* stream) {
   using namespace yy;
   if (yy_device_count() == 0) return set_error(YY_ERR_NO_DEVICE, "no CUDA device");
-  if (M < 128 + a_row_offset || a_row_offset < 0) return set_error(YY_ERR_INVALID, "probe: A needs a_row_offset+128 rows");
+  if (M < (swap_lbo_sbo >= 2 ? 15 * swap_lbo_sbo + 8 : 128) + a_row_offset || a_row_offset < 0) return set_error(YY_ERR_INVALID, "probe: A has too few rows");
   if (N < 16 || N > 256 || N % 16 || K < 16 || K % 16) return set_error(YY_ERR_INVALID, "probe: N in [16,256] step 16, K multiple of 16");
   size_t smem = (size_t)(K / 8) * 16 * ((size_t)M + N);
   if (smem > 200 * 1024) return set_error(YY_ERR_INVALID, "probe: operands too large for one CTA");
@@ -275,6 +278,48 @@ extern "C" int yy_umma_rate(int N, int layout_type, int lbo_a, int sbo_a, int lb
   YY_CUDA_OK(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_rate_kernel<<<n_ctas, 128, smem, (cudaStream_t)stream>>>(N, layout_type, lbo_a, sbo_a, lbo_b, sbo_b, a_step, b_step,
                                                                  per_round, iters, out_cycles_dev);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ L2 stream bench
+// Developer tool: every CTA streams `total_bytes` from a shared `src_bytes` buffer (wrapping) through a ring of
+// `slots` x `chunk` bytes with cp.async.bulk, no compute.  Reports SM cycles per CTA -> achievable L2->smem rate
+// when all SMs pull the same weight image (what the tower kernel's producer does).
+namespace yy {
+__global__ void __launch_bounds__(256) l2_stream_kernel(const uint8_t* __restrict__ src, long long src_bytes, long long total_bytes,
+                                                       int chunk, int slots, int warps, long long* out_cycles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full[8][16];
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { for (int w = 0; w < 8; ++w) for (int s = 0; s < slots; ++s) mbar_init(smem_u32(&full[w][s]), 1); fence_barrier_init(); }
+  __syncthreads();
+  if (warp < warps) {   // each issuing warp streams its own share through its own sub-ring
+    const long long n = total_bytes / chunk / warps;
+    uint8_t* ring = smem + (size_t)warp * slots * chunk;
+    const long long t0 = clock64();
+    for (long long i = 0; i < n + slots; ++i) {
+      if (i >= slots) mbar_wait(smem_u32(&full[warp][(i - slots) % slots]), (uint32_t)(((i - slots) / slots) & 1));
+      if (i < n && elect_one()) {
+        const int s = (int)(i % slots);
+        mbar_arrive_expect_tx(smem_u32(&full[warp][s]), (uint32_t)chunk);
+        bulk_g2s(smem_u32(ring + (size_t)s * chunk), src + ((i * warps + warp) * chunk) % src_bytes, (uint32_t)chunk, smem_u32(&full[warp][s]));
+      }
+      __syncwarp();
+    }
+    if (threadIdx.x == 0) out_cycles[blockIdx.x] = clock64() - t0;
+  }
+}
+}  // namespace yy
+
+extern "C" int yy_l2_stream(const void* src_dev, long long src_bytes, long long total_bytes, int chunk, int slots, int warps, int n_ctas,
+                            long long* out_cycles_dev, void* stream) {
+  using namespace yy;
+  if (yy_device_count() == 0) return set_error(YY_ERR_NO_DEVICE, "no CUDA device");
+  if (slots < 1 || slots > 16 || warps < 1 || warps > 8 || chunk % 16 || (long long)chunk * slots * warps > 200 * 1024) return set_error(YY_ERR_INVALID, "bad ring");
+  const int smem = chunk * slots * warps;
+  YY_CUDA_OK(cudaFuncSetAttribute(l2_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  l2_stream_kernel<<<n_ctas, 256, smem, (cudaStream_t)stream>>>((const uint8_t*)src_dev, src_bytes, total_bytes, chunk, slots, warps, out_cycles_dev);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }

@@ -62,7 +62,7 @@ struct TowerArgs {
   const float* conv_bias;      // [1 + 2*blocks][128] then head [64]
   const uint64_t* black; const uint64_t* white;
   long long count;
-  int n_groups;
+  int boards_per_cta;          // boards are dealt to CTAs in contiguous runs; the last group of a run may be short
   __nv_bfloat16* headfeat;     // [count][64*A], index c*A + cell (matches .view(-1, 32*n*m), neural_network.py:112,117)
   long long* dbg;              // optional per-layer clock64 stamps of CTA 0's first group (developer tool), else nullptr
 };
@@ -130,12 +130,21 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t act_base = smem_u32(smem + SM_ACT);
   const uint32_t ring_base = smem_u32(smem + SM_RING);
+  // this CTA's run of boards [run_lo, run_hi); groups of Gb boards, the last one possibly shorter -> fewer tiles
+  const long long run_lo = (long long)blockIdx.x * a.boards_per_cta;
+  const long long run_hi = (run_lo + a.boards_per_cta < a.count) ? run_lo + a.boards_per_cta : a.count;
+  // (+pitch+1: the taps of the last real position read that far; rows beyond the group's tiles may be stale)
+  auto tiles_for = [&](long long b0) {
+    long long nb = run_hi - b0; if (nb > g.Gb) nb = g.Gb;
+    int t = (int)((nb * g.PB + g.pitch + 1 + 127) >> 7);
+    return t < g.T ? t : g.T;
+  };
 
   if (warp == 0) {
     // =========================================================== weight producer (whole warp walks the loop with
     // warp-uniform state; one elected lane issues the bulk copies -- keeps everything on the uniform datapath)
     uint32_t it = 0;
-    for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+    for (long long b0 = run_lo; b0 < run_hi; b0 += g.Gb) {
       for (int l = 0; l < L; ++l) {
         const LayerInfo li = layer_info(l, g.blocks);
         const uint8_t* src = a.conv_stream + li.stream_off;
@@ -156,7 +165,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
     uint32_t it = 0, act_phase = 0;
     constexpr uint64_t kTileDelta = (128u * 16u) >> 4;           // next M=128 tile: +128 rows of 16 B
     constexpr uint64_t kK16DeltaA = (2u * TW_ROWS * 16u) >> 4;   // next K=16 slice: +2 channel chunks
-    for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+    for (long long b0 = run_lo; b0 < run_hi; b0 += g.Gb) {
+      const int T = tiles_for(b0);
       for (int l = 0; l < L; ++l) {
         const LayerInfo li = layer_info(l, g.blocks);
         const bool preloaded = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 0);  // conv2: accumulator holds the skip input
@@ -164,7 +174,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
         const uint64_t k16_delta_b = (uint64_t)((2u * (uint32_t)li.N * 16u) >> 4);
         mbar_wait(act_ready, act_phase); act_phase ^= 1;
         tc_fence_after();
-        if (a.dbg && blockIdx.x == 0 && grp == 0 && lane == 0) a.dbg[l * 4 + 0] = clock64();
+        if (a.dbg && blockIdx.x == 0 && b0 == run_lo && lane == 0) a.dbg[l * 4 + 0] = clock64();
         for (int j = 0; j < li.n_stages; ++j, ++it) {
           const uint32_t slot = it % TW_STAGES;
           int tapshift, chunk0;
@@ -177,7 +187,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
           if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < TW_MAXT; ++t) {
-              if (t < g.T) {
+              if (t < T) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   if (k < li.nk16)
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
         }
         if (elect_one()) tc_commit(acc_full);
         __syncwarp();
-        if (a.dbg && blockIdx.x == 0 && grp == 0 && lane == 0) a.dbg[l * 4 + 1] = clock64();
+        if (a.dbg && blockIdx.x == 0 && b0 == run_lo && lane == 0) a.dbg[l * 4 + 1] = clock64();
       }
     }
   } else {
@@ -203,14 +213,15 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
     constexpr int kTileStride = TW_EPI_WARPS / 4;
     uint32_t acc_phase = 0;
     uint8_t* act = smem + SM_ACT;
-    for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+    for (long long b0 = run_lo; b0 < run_hi; b0 += g.Gb) {
+      const int T = tiles_for(b0);
       // ---- stem input planes (board_to_input, neural_network.py:156-196) for my rows ----
-      for (int t = tile0; t < g.T; t += kTileStride) {
+      for (int t = tile0; t < T; t += kTileStride) {
         const int p = t * 128 + quarter * 32 + lane;
         const int info = pos_tab[p];
         uint4 c0 = make_uint4(0, 0, 0, 0);
-        const long long board = (long long)grp * g.Gb + (info >= 0 ? (info >> 8) : 0);
-        if (info >= 0 && board < a.count) {
+        const long long board = b0 + (info >= 0 ? (info >> 8) : 0);
+        if (info >= 0 && board < run_hi) {
           const int cell = info & 255, y = cell / g.m, x = cell % g.m;
           const uint64_t* bb = a.black + board * g.W; const uint64_t* wb = a.white + board * g.W;
           auto bit = [&](const uint64_t* v, int c) { return (int)((v[c >> 6] >> (c & 63)) & 1ull); };
@@ -239,12 +250,12 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
         const float* bias = a.conv_bias + (size_t)l * TW_C;
         mbar_wait(acc_full, acc_phase); acc_phase ^= 1;
         tc_fence_after();
-        if (a.dbg && blockIdx.x == 0 && grp == 0 && tid == 64) a.dbg[l * 4 + 2] = clock64();
-        for (int t = tile0; t < g.T; t += kTileStride) {
+        if (a.dbg && blockIdx.x == 0 && b0 == run_lo && tid == 64) a.dbg[l * 4 + 2] = clock64();
+        for (int t = tile0; t < T; t += kTileStride) {
           const int p = t * 128 + quarter * 32 + lane;
           const int info = pos_tab[p];
-          const long long board = (long long)grp * g.Gb + (info >= 0 ? (info >> 8) : 0);
-          const bool real = info >= 0 && board < a.count;
+          const long long board = b0 + (info >= 0 ? (info >> 8) : 0);
+          const bool real = info >= 0 && board < run_hi;
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 128);
           uint8_t* rowp = act + (size_t)(TW_PAD + p) * 16;
           if (!is_head) {
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
           }
         }
         tc_fence_before();
-        if (a.dbg && blockIdx.x == 0 && grp == 0 && tid == 64) a.dbg[l * 4 + 3] = clock64();
+        if (a.dbg && blockIdx.x == 0 && b0 == run_lo && tid == 64) a.dbg[l * 4 + 3] = clock64();
         if (!is_head) { fence_proxy_async_smem(); mbar_arrive(act_ready); }
       }
     }
@@ -482,10 +493,15 @@ int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_
     ta.conv_stream = wimg + wl.conv_stream;
     ta.conv_bias = reinterpret_cast<const float*>(wimg + wl.conv_bias);
     ta.black = black + done * nn.W; ta.white = white + done * nn.W;
-    ta.count = n; ta.n_groups = (int)((n + ta.g.Gb - 1) / ta.g.Gb);
+    ta.count = n;
     ta.headfeat = headfeat;
     ta.dbg = nn.dbg;
-    const int grid = ta.n_groups < nn.num_sms ? ta.n_groups : nn.num_sms;
+    // deal boards to CTAs in equal contiguous runs (wave balance: every SM gets the same number of boards; a run's
+    // last group is short and uses fewer tiles), but never fewer than one full group per CTA
+    long long per = (n + nn.num_sms - 1) / nn.num_sms;
+    if (per < ta.g.Gb) per = ta.g.Gb;
+    ta.boards_per_cta = (int)per;
+    const int grid = (int)((n + per - 1) / per);
     if (nn.profiling) {
       if (nn.ev_used == nn.ev_cap) { int rc = nn_drain_events(nn); if (rc) return rc; }
       YY_CUDA_OK(cudaEventRecord(nn.ev[2 * nn.ev_used], s));
