@@ -10,10 +10,11 @@
 //   padded positions: each board contributes (n+1) x (m+1) positions -- its n x m cells plus one zero column
 //   on the right and one zero row below -- so that the 3x3 tap (dy,dx) of EVERY position is the position
 //   dy*(m+1)+dx further along the list and zero padding comes for free.  The whole residual tower runs with
-//   the group's activations resident in shared memory ([C/8 chunks][560 rows][8 ch] bf16 = no-swizzle
+//   the group's activations resident in shared memory ([C/8 chunks][616 rows][8 ch] bf16 = no-swizzle
 //   K-major core matrices, so a tap shift is just a +16 B/row move of the UMMA descriptor start address);
-//   only the weights stream in (16 KB stages, cp.async.bulk into a 5-deep mbarrier ring, shared by the 4
-//   M=128 tiles of the group).  Accumulators live in TMEM (4 tiles x 128 fp32 columns = all 512 columns).
+//   only the weights stream in (16 KB stages, cp.async.bulk into a 4-deep mbarrier ring, shared by the 4
+//   M=128 tiles of the group).  For 8-wide boards the MMA's 8-row groups are the board rows themselves
+//   (descriptor SBO = 9*16 B skips the zero column): 7 boards per group, 87.5 % of the MMA rows are real cells.  Accumulators live in TMEM (4 tiles x 128 fp32 columns = all 512 columns).
 //   The skip connection never touches shared memory: conv1's epilogue re-loads the block input into the
 //   TMEM accumulator (tcgen05.st) before overwriting it in place, and conv2 accumulates on top of it.
 //   Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one elected thread), warps 2-17 = epilogue
@@ -36,17 +37,17 @@ constexpr int TW_HEADC = 64;           // policy 32 + value 32 head-conv channel
 constexpr int TW_INC = 16;             // stem input channels after padding (K = 16 per tap)
 constexpr int TW_MAXT = 4;             // tiles (of 128 positions) per group
 constexpr int TW_PAD = 24;             // zero rows before/after the group's positions (>= m+2)
-constexpr int TW_ROWS = 128 * TW_MAXT + 2 * TW_PAD;  // 560
-constexpr int TW_STAGES = 5;
+constexpr int TW_ROWS = 616;            // activation rows: flat layout needs 512+2*24, row-aligned 24+64*9+10
+constexpr int TW_STAGES = 4;
 constexpr int TW_STAGE_BYTES = 16384;
 constexpr int TW_EPI_WARPS = 16;           // one (tile, TMEM-lane-quarter) pair per warp
 constexpr int TW_THREADS = 64 + 32 * TW_EPI_WARPS;
 constexpr int TW_EPI_THREADS = 32 * TW_EPI_WARPS;
 
 constexpr int SM_ACT = 0;
-constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 143360
-constexpr int SM_POS = SM_RING + TW_STAGES * TW_STAGE_BYTES;          // 225280
-constexpr int SM_BAR = SM_POS + 128 * TW_MAXT * 2;                    // 226304
+constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 157696
+constexpr int SM_POS = SM_RING + TW_STAGES * TW_STAGE_BYTES;          // position tables: padded position + (board, cell)
+constexpr int SM_BAR = SM_POS + 2 * 128 * TW_MAXT * 2;
 constexpr int SM_TMEM = SM_BAR + 8 * (2 * TW_STAGES + 2);
 constexpr int SM_TOTAL = SM_TMEM + 16;
 
@@ -54,6 +55,11 @@ struct TowerGeo {
   int n, m, A, W, pitch, PB;  // PB = padded positions per board
   int T, Gb;                  // tiles per group, boards per group
   int blocks;
+  // Two layouts of a group's positions (both keep a zero column right of and a zero row below every board):
+  //  flat        : M row r of tile t is padded position t*128 + r            (SBO 128 B, any board width)
+  //  row-aligned : (cols == 8) an 8-row MMA group is exactly one board row: M row r of tile t is padded position
+  //                (16t + r/8)*pitch + r%8, SBO = pitch*16 B -- the zero column is skipped, 7 boards per 4 tiles
+  int row_aligned, sbo_bytes, tile_adv, rows_per_board;
 };
 
 struct TowerArgs {
@@ -101,7 +107,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
   const TowerGeo& g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = 2 * g.blocks + 2;  // stem + 2*blocks tower convs + head conv
-  int16_t* pos_tab = reinterpret_cast<int16_t*>(smem + SM_POS);
+  int16_t* pos_p = reinterpret_cast<int16_t*>(smem + SM_POS);                       // M row -> padded position
+  int16_t* pos_tab = reinterpret_cast<int16_t*>(smem + SM_POS + 128 * TW_MAXT * 2);    // M row -> board*256 + cell, or -1
   const uint32_t bar0 = smem_u32(smem + SM_BAR);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (TW_STAGES + s); };
@@ -110,11 +117,17 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
 
   // ---- one-time setup ----
   for (int i = tid; i < TW_CHUNKS * TW_ROWS * 4; i += TW_THREADS) reinterpret_cast<uint32_t*>(smem + SM_ACT)[i] = 0u;
-  for (int p = tid; p < 128 * TW_MAXT; p += TW_THREADS) {
-    int v = -1;
-    int b = p / g.PB, rem = p % g.PB, y = rem / g.pitch, x = rem % g.pitch;
+  for (int i = tid; i < 128 * TW_MAXT; i += TW_THREADS) {
+    int v = -1, p, b, y, x;
+    if (g.row_aligned) {
+      const int R = (i >> 7) * 16 + ((i & 127) >> 3);
+      x = i & 7; p = R * g.pitch + x; b = R / g.rows_per_board; y = R % g.rows_per_board;
+    } else {
+      p = i; b = p / g.PB; const int rem = p % g.PB; y = rem / g.pitch; x = rem % g.pitch;
+    }
     if (b < g.Gb && y < g.n && x < g.m) v = b * 256 + y * g.m + x;
-    pos_tab[p] = (int16_t)v;
+    pos_p[i] = (int16_t)p;
+    pos_tab[i] = (int16_t)v;
   }
   if (tid == 0) {
     for (int s = 0; s < TW_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -136,7 +149,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
   // (+pitch+1: the taps of the last real position read that far; rows beyond the group's tiles may be stale)
   auto tiles_for = [&](long long b0) {
     long long nb = run_hi - b0; if (nb > g.Gb) nb = g.Gb;
-    int t = (int)((nb * g.PB + g.pitch + 1 + 127) >> 7);
+    int t = g.row_aligned ? (int)((nb * g.rows_per_board + 15) >> 4) : (int)((nb * g.PB + g.pitch + 1 + 127) >> 7);
     return t < g.T ? t : g.T;
   };
 
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
     // =========================================================== MMA issuer (whole warp runs the control flow, the
     // tcgen05.mma / commit instructions are issued by one elected lane; descriptors are base + constant deltas)
     uint32_t it = 0, act_phase = 0;
-    constexpr uint64_t kTileDelta = (128u * 16u) >> 4;           // next M=128 tile: +128 rows of 16 B
+    const uint64_t kTileDelta = (uint64_t)g.tile_adv;            // next M=128 tile, in 16-byte rows
     constexpr uint64_t kK16DeltaA = (2u * TW_ROWS * 16u) >> 4;   // next K=16 slice: +2 channel chunks
     for (long long b0 = run_lo; b0 < run_hi; b0 += g.Gb) {
       const int T = tiles_for(b0);
@@ -181,7 +194,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
           stage_info(l, j, g.blocks, g.pitch, tapshift, chunk0);
           mbar_wait(full_bar(slot), (it / TW_STAGES) & 1);
           tc_fence_after();
-          const uint64_t ad0 = smem_desc(act_base + (uint32_t)((chunk0 * TW_ROWS + TW_PAD + tapshift) * 16), TW_ROWS * 16, 128);
+          const uint64_t ad0 = smem_desc(act_base + (uint32_t)((chunk0 * TW_ROWS + TW_PAD + tapshift) * 16), TW_ROWS * 16, (uint32_t)g.sbo_bytes);
           const uint64_t bd0 = smem_desc(ring_base + slot * TW_STAGE_BYTES, (uint32_t)li.N * 16, 128);
           const uint32_t acc0 = (preloaded || j > 0) ? 1u : 0u;
           if (elect_one()) {
@@ -217,8 +230,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
       const int T = tiles_for(b0);
       // ---- stem input planes (board_to_input, neural_network.py:156-196) for my rows ----
       for (int t = tile0; t < T; t += kTileStride) {
-        const int p = t * 128 + quarter * 32 + lane;
-        const int info = pos_tab[p];
+        const int mi = t * 128 + quarter * 32 + lane;
+        const int p = pos_p[mi];
+        const int info = pos_tab[mi];
         uint4 c0 = make_uint4(0, 0, 0, 0);
         const long long board = b0 + (info >= 0 ? (info >> 8) : 0);
         if (info >= 0 && board < run_hi) {
@@ -252,8 +266,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
         tc_fence_after();
         if (a.dbg && blockIdx.x == 0 && b0 == run_lo && tid == 64) a.dbg[l * 4 + 2] = clock64();
         for (int t = tile0; t < T; t += kTileStride) {
-          const int p = t * 128 + quarter * 32 + lane;
-          const int info = pos_tab[p];
+          const int mi = t * 128 + quarter * 32 + lane;
+          const int p = pos_p[mi];
+          const int info = pos_tab[mi];
           const long long board = b0 + (info >= 0 ? (info >> 8) : 0);
           const bool real = info >= 0 && board < run_hi;
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 128);
@@ -384,6 +399,13 @@ static TowerGeo make_tower_geo(int rows, int cols, int blocks) {
   TowerGeo g;
   g.n = rows; g.m = cols; g.A = rows * cols; g.W = words_for_cells(g.A); g.pitch = cols + 1; g.PB = (rows + 1) * (cols + 1);
   g.blocks = blocks;
+  g.row_aligned = 0; g.sbo_bytes = 128; g.tile_adv = 128; g.rows_per_board = rows + 1;
+  if (cols == 8 && rows + 1 <= 16 * TW_MAXT) {   // one board row == one 8-row MMA group
+    g.row_aligned = 1; g.sbo_bytes = g.pitch * 16; g.tile_adv = 16 * g.pitch;
+    g.T = TW_MAXT; g.Gb = (16 * TW_MAXT) / (rows + 1);
+    if (g.Gb > 127) g.Gb = 127;
+    return g;
+  }
   double best = -1.0; g.T = TW_MAXT; g.Gb = 1;
   for (int T = 1; T <= TW_MAXT; ++T) {
     int Gb = (128 * T) / g.PB;
