@@ -73,19 +73,36 @@ __global__ void __launch_bounds__(128) probe_umma_kernel(const __nv_bfloat16* __
 // grid = (ceil(M/128), N/BN).  128 threads.  BK = 64 per stage, 3-stage cp.async ring; thread 0 issues the
 // MMAs and frees a stage with tcgen05.commit; all four warps drain TMEM in the epilogue.
 constexpr int kGemmBK = 64;
-constexpr int kGemmStages = 3;
+constexpr int kGemmStages = 4;   // 96 KB: two CTAs per SM, so the 160 head tiles of a 4,096-board batch are one wave
+
+struct GemmPair { GemmArgs p[2]; int ytiles0; };
 
 template <int BN>
-__global__ void __launch_bounds__(128) gemm_bf16_tn_kernel(GemmArgs g) {
+__device__ __forceinline__ void gemm_tile(const GemmArgs& g, int tile_m, int tile_n);
+
+template <int BN>
+__global__ void __launch_bounds__(128) gemm_bf16_tn_kernel(GemmArgs g) { gemm_tile<BN>(g, blockIdx.x, blockIdx.y); }
+
+template <int BN>
+__global__ void __launch_bounds__(128) gemm_bf16_tn_pair_kernel(GemmPair gp) {
+  if ((int)blockIdx.y < gp.ytiles0) gemm_tile<BN>(gp.p[0], blockIdx.x, blockIdx.y);
+  else gemm_tile<BN>(gp.p[1], blockIdx.x, blockIdx.y - gp.ytiles0);
+}
+
+template <int BN>
+__device__ __forceinline__ void gemm_tile(const GemmArgs& g, int tile_m, int tile_n) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t mma_done[kGemmStages];
   __shared__ __align__(8) uint64_t acc_done;
   __shared__ uint32_t tmem_base_s;
-  constexpr int A_STAGE = (kGemmBK / 8) * 128 * 16;  // 16 KB
-  constexpr int B_STAGE = (kGemmBK / 8) * BN * 16;
+  // k-chunk planes are padded by one 16-byte row (LBO = (rows+1)*16) so that the 8 chunks of one global 128-byte
+  // line, fetched by 8 consecutive threads, land in 8 different bank groups
+  constexpr int A_LBO = (128 + 1) * 16, B_LBO = (BN + 1) * 16;
+  constexpr int A_STAGE = (kGemmBK / 8) * A_LBO;
+  constexpr int B_STAGE = (kGemmBK / 8) * B_LBO;
   uint8_t* a_s = smem;
   uint8_t* b_s = smem + kGemmStages * A_STAGE;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const int m0 = tile_m * 128, n0 = tile_n * BN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t NCOLS = BN < 32 ? 32 : BN;
   if (tid == 0) {
@@ -102,29 +119,27 @@ __global__ void __launch_bounds__(128) gemm_bf16_tn_kernel(GemmArgs g) {
 
   auto load_stage = [&](int kb, int s) {
     const int k0 = kb * kGemmBK;
-    // A: 8 k-chunks x 128 rows of 16 B; thread t handles row t for all 8 chunks (coalescing is per row:
-    // 128 B contiguous per thread, rows lda apart -- fine for L2-resident operands).
-    {
-      const int r = tid;
+    // 8 consecutive threads fetch the 8 chunks (one contiguous 128-byte line) of one row
+    const int kc = tid & 7;
+    const bool kv = (k0 + kc * 8) < g.K;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = (tid >> 3) + 16 * i;
       const bool rv = (m0 + r) < g.M;
-      const __nv_bfloat16* src = g.A + (size_t)(rv ? (m0 + r) : 0) * g.lda + k0;
-#pragma unroll
-      for (int kc = 0; kc < kGemmBK / 8; ++kc)
-        cp_async16(smem_u32(a_s + s * A_STAGE + (kc * 128 + r) * 16), src + kc * 8, rv && (k0 + kc * 8) < g.K);
+      cp_async16(smem_u32(a_s + s * A_STAGE + kc * A_LBO + r * 16), g.A + (size_t)(rv ? (m0 + r) : 0) * g.lda + k0 + kc * 8, rv && kv);
     }
-    for (int r = tid; r < BN; r += 128) {
-      const bool rv = (n0 + r) < g.N;
-      const __nv_bfloat16* src = g.B + (size_t)(rv ? (n0 + r) : 0) * g.ldb + k0;
 #pragma unroll
-      for (int kc = 0; kc < kGemmBK / 8; ++kc)
-        cp_async16(smem_u32(b_s + s * B_STAGE + (kc * BN + r) * 16), src + kc * 8, rv && (k0 + kc * 8) < g.K);
+    for (int i = 0; i < BN / 16; ++i) {
+      const int r = (tid >> 3) + 16 * i;
+      const bool rv = (n0 + r) < g.N;
+      cp_async16(smem_u32(b_s + s * B_STAGE + kc * B_LBO + r * 16), g.B + (size_t)(rv ? (n0 + r) : 0) * g.ldb + k0 + kc * 8, rv && kv);
     }
     cp_async_commit();
   };
 
   // prologue
   for (int p = 0; p < kGemmStages - 1; ++p) { if (p < nkb) load_stage(p, p); else cp_async_commit(); }
-  uint32_t done_phase[kGemmStages] = {0, 0, 0};
+  uint32_t done_phase_bits = 0;   // bit s = parity to wait for on mma_done[s]
   const uint32_t idesc = idesc_bf16(128, BN);
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb % kGemmStages;
@@ -132,7 +147,7 @@ __global__ void __launch_bounds__(128) gemm_bf16_tn_kernel(GemmArgs g) {
     {
       const int nk = kb + kGemmStages - 1, ns = nk % kGemmStages;
       if (nk < nkb) {
-        if (kb >= 1) { mbar_wait(smem_u32(&mma_done[ns]), done_phase[ns]); done_phase[ns] ^= 1; }
+        if (kb >= 1) { mbar_wait(smem_u32(&mma_done[ns]), (done_phase_bits >> ns) & 1u); done_phase_bits ^= 1u << ns; }
         load_stage(nk, ns);
       } else {
         cp_async_commit();
@@ -145,8 +160,8 @@ __global__ void __launch_bounds__(128) gemm_bf16_tn_kernel(GemmArgs g) {
       tc_fence_after();
 #pragma unroll
       for (int k16 = 0; k16 < kGemmBK / 16; ++k16) {
-        uint64_t ad = smem_desc(smem_u32(a_s + s * A_STAGE) + 2 * k16 * 128 * 16, 128 * 16, 128);
-        uint64_t bd = smem_desc(smem_u32(b_s + s * B_STAGE) + 2 * k16 * BN * 16, BN * 16, 128);
+        uint64_t ad = smem_desc(smem_u32(a_s + s * A_STAGE) + 2 * k16 * A_LBO, A_LBO, 128);
+        uint64_t bd = smem_desc(smem_u32(b_s + s * B_STAGE) + 2 * k16 * B_LBO, B_LBO, 128);
         tc_mma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
       }
       tc_commit(smem_u32(&mma_done[s]));
@@ -181,7 +196,7 @@ __global__ void __launch_bounds__(128) gemm_bf16_tn_kernel(GemmArgs g) {
 
 template <int BN>
 static int launch_gemm(const GemmArgs& g, cudaStream_t s) {
-  constexpr int smem = kGemmStages * ((kGemmBK / 8) * 128 * 16 + (kGemmBK / 8) * BN * 16);
+  constexpr int smem = kGemmStages * (kGemmBK / 8) * ((128 + 1) * 16 + (BN + 1) * 16);
   static bool attr_done = false;
   if (!attr_done) {
     YY_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -189,6 +204,24 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t s) {
   }
   dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)(g.N / BN));
   gemm_bf16_tn_kernel<BN><<<grid, 128, smem, s>>>(g);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int gemm_bf16_tn_pair(const GemmArgs& p0, const GemmArgs& p1, cudaStream_t s) {
+  if (p0.M <= 0) return YY_OK;
+  if (p0.M != p1.M || p0.N % 64 || p1.N % 64 || p0.K % 8 || p1.K % 8 || p0.lda % 8 || p1.lda % 8 || p0.ldb % 8 || p1.ldb % 8)
+    return set_error(YY_ERR_INVALID, "gemm pair: equal M, N multiples of 64, K/lda/ldb multiples of 8 required");
+  constexpr int BN = 64;
+  constexpr int smem = kGemmStages * (kGemmBK / 8) * ((128 + 1) * 16 + (BN + 1) * 16);
+  static bool attr_done = false;
+  if (!attr_done) {
+    YY_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  GemmPair gp; gp.p[0] = p0; gp.p[1] = p1; gp.ytiles0 = p0.N / BN;
+  dim3 grid((unsigned)((p0.M + 127) / 128), (unsigned)(p0.N / BN + p1.N / BN));
+  gemm_bf16_tn_pair_kernel<BN><<<grid, 128, smem, s>>>(gp);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }

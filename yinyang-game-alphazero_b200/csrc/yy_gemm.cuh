@@ -16,5 +16,8 @@ struct GemmArgs {
 
 // C = act(A * B^T + bias).  N multiple of 16; K, lda, ldb multiples of 8.
 int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream);
+// Two independent problems with the same M in ONE launch (policy FC + value FC1 of the heads): grid.y covers
+// p0's N tiles then p1's.  Both N multiples of 64.
+int gemm_bf16_tn_pair(const GemmArgs& p0, const GemmArgs& p1, cudaStream_t stream);
 
 }  // namespace yy

@@ -536,10 +536,12 @@ int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_
     }
     GemmArgs gp{headfeat, TW_HEADC * A, reinterpret_cast<const __nv_bfloat16*>(wimg + wl.fc_policy_w), 32 * A, logits_buf, wl.a_pad,
                 reinterpret_cast<const float*>(wimg + wl.fc_policy_b), (int)n, wl.a_pad, 32 * A, 0};
-    int rc = gemm_bf16_tn(gp, s); if (rc) return rc;
     GemmArgs gv{headfeat + 32 * A, TW_HEADC * A, reinterpret_cast<const __nv_bfloat16*>(wimg + wl.fc_value1_w), 32 * A, hidden, 256,
                 reinterpret_cast<const float*>(wimg + wl.fc_value1_b), (int)n, 256, 32 * A, 1};
-    rc = gemm_bf16_tn(gv, s); if (rc) return rc;
+    int rc;
+    if (wl.a_pad % 64 == 0) rc = gemm_bf16_tn_pair(gp, gv, s);          // policy FC + value FC1 in one launch
+    else { rc = gemm_bf16_tn(gp, s); if (rc) return rc; rc = gemm_bf16_tn(gv, s); }
+    if (rc) return rc;
     const unsigned grid2 = (unsigned)((n * 32 + 127) / 128);
     heads_finish_kernel<<<grid2, 128, 0, s>>>(logits_buf, wl.a_pad, hidden, reinterpret_cast<const float*>(wimg + wl.fc_value2_w),
                                               reinterpret_cast<const float*>(wimg + wl.fc_value2_b), n, A,

@@ -93,16 +93,18 @@ __global__ void __launch_bounds__(kTreeBlock) tree_root_kernel(EngineDev e, Geo<
     e.leaf_active[gi] = 1;
   }
   publish_leaf<NW>(e, g, gi, lane, 0, b, w, player, 0);
-  if (gi == 0 && lane == 0) *e.active_count = e.n_games;
+  if (gi == 0 && lane == 0) { e.active_count[0] = e.n_games; e.active_count[1] = 0; }
 }
 
 // One lock-step of every tree: (1) expand the pending leaf with the evaluator's output and back its value
 // up (mcts.py:394-412); (2) run simulations from the root until one needs an evaluation (selection,
 // mcts.py:360-362; revisited terminal leaves complete on the spot, :365-367) and publish that leaf.
 template <int NW>
-__global__ void __launch_bounds__(kTreeBlock) tree_step_kernel(EngineDev e, Geo<NW> g) {
+__global__ void __launch_bounds__(kTreeBlock) tree_step_kernel(EngineDev e, Geo<NW> g, int parity) {
   int gi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (gi >= e.n_games) return;
+  // pending-leaf counter is double buffered: this step counts into [parity] and clears the other one for the next step
+  if (gi == 0 && lane == 0) e.active_count[parity ^ 1] = 0;
   const long long nb = (long long)gi * e.max_nodes;
   const long long eb = (long long)gi * e.edges_cap;
   int32_t* path = e.g_path + (long long)gi * e.max_depth;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(kTreeBlock) tree_step_kernel(EngineDev e, Geo<
     e.g_sims_done[gi] = sims_done;
     if (!pending) e.g_leaf[gi] = -1;
     e.leaf_active[gi] = pending ? 1 : 0;
-    if (pending) atomicAdd(e.active_count, 1);
+    if (pending) atomicAdd(e.active_count + parity, 1);
     if (sims_here) atomicAdd(&e.stats->sims, (unsigned long long)sims_here);
     if (evals_here) atomicAdd(&e.stats->evals, (unsigned long long)evals_here);
     if (deepest > e.stats->max_depth) atomicMax(&e.stats->max_depth, deepest);
@@ -233,7 +235,6 @@ __global__ void tree_counts_kernel(EngineDev e, int32_t* counts, float* child_w)
   }
 }
 
-__global__ void zero_i32_kernel(int32_t* p) { *p = 0; }
 
 // stub evaluator on an arbitrary batch (yy_evaluate in YY_EVAL_STUB mode)
 template <int NW>
@@ -415,7 +416,7 @@ static void carve(const yy_engine_config& c, Carver& k, EngineDev& d) {
   d.g_leaf = k.take<int32_t>(G); d.g_path_len = k.take<int32_t>(G); d.g_path = k.take<int32_t>(G * (size_t)d.max_depth);
   d.leaf_black = k.take<uint64_t>(G * W); d.leaf_white = k.take<uint64_t>(G * W); d.leaf_mask = k.take<uint64_t>(G * W);
   d.leaf_code = k.take<int8_t>(G); d.leaf_active = k.take<uint8_t>(G);
-  d.eval_prior = k.take<float>(G * A); d.eval_value = k.take<float>(G); d.active_count = k.take<int32_t>(1);
+  d.eval_prior = k.take<float>(G * A); d.eval_value = k.take<float>(G); d.active_count = k.take<int32_t>(2);
   d.root_black = k.take<uint64_t>(G * W); d.root_white = k.take<uint64_t>(G * W); d.root_player = k.take<int8_t>(G);
   d.noise = k.take<double>(G * A); d.noise_mask = k.take<uint8_t>(G);
   d.sp_black = k.take<uint64_t>(G * W); d.sp_white = k.take<uint64_t>(G * W); d.sp_player = k.take<int8_t>(G);
@@ -438,6 +439,7 @@ struct yy_engine {
   EngineDev dev;
   NNState nn;
   bool search_open;
+  int step_parity;   // which half of the double-buffered pending-leaf counter the last tree step used
   // scratch pointers for caller-supplied noise in yy_search
   const double* user_noise; const uint8_t* user_noise_mask;
 };
@@ -451,13 +453,13 @@ int launch_root(yy_engine* e, cudaStream_t s) {
   YY_DISPATCH_NW(e->dev.A, tree_root_kernel<NW><<<warp_grid(e->dev.n_games), kTreeBlock, 0, s>>>(
       e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
   YY_LAUNCH_CHECK();
+  e->step_parity = 0;   // root wrote [0] = n_games, [1] = 0; the first step counts into [1]
   return YY_OK;
 }
 int launch_step(yy_engine* e, cudaStream_t s) {
-  zero_i32_kernel<<<1, 1, 0, s>>>(e->dev.active_count);
-  YY_LAUNCH_CHECK();
+  e->step_parity ^= 1;
   YY_DISPATCH_NW(e->dev.A, tree_step_kernel<NW><<<warp_grid(e->dev.n_games), kTreeBlock, 0, s>>>(
-      e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
+      e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags), e->step_parity));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -520,7 +522,7 @@ yy_engine* yy_engine_create(const yy_engine_config* cfg, void* workspace, int64_
   if (((uintptr_t)workspace & 255) != 0) { set_error(YY_ERR_INVALID, "workspace must be 256-byte aligned"); return nullptr; }
   yy_engine* e = new (std::nothrow) yy_engine();
   if (!e) { set_error(YY_ERR_INVALID, "out of host memory"); return nullptr; }
-  e->cfg = c; e->search_open = false; e->user_noise = nullptr; e->user_noise_mask = nullptr;
+  e->cfg = c; e->search_open = false; e->step_parity = 0; e->user_noise = nullptr; e->user_noise_mask = nullptr;
   Carver k{(char*)workspace, 0};
   carve(c, k, e->dev);
   e->dev.cpuct = c.cpuct; e->dev.eps = (double)c.dirichlet_epsilon; e->dev.alpha = (double)c.dirichlet_alpha;
@@ -578,7 +580,7 @@ int yy_search_advance(yy_engine* e, const float* priors, const float* values, in
   }
   int rc = launch_step(e, s); if (rc) return rc;
   if (out_active) {
-    YY_CUDA_OK(cudaMemcpyAsync(out_active, e->dev.active_count, 4, cudaMemcpyDeviceToHost, s));
+    YY_CUDA_OK(cudaMemcpyAsync(out_active, e->dev.active_count + e->step_parity, 4, cudaMemcpyDeviceToHost, s));
     YY_CUDA_OK(cudaStreamSynchronize(s));
     if (*out_active == 0) e->search_open = false;
   }
