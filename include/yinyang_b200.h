@@ -122,6 +122,8 @@ typedef struct {
   int32_t nn_channels;      /* 128 (neural_network.py:39)                                 */
   int32_t nn_blocks;        /* 10                                                         */
   int32_t device;           /* CUDA device ordinal                                        */
+  int32_t leaves_per_step;  /* K: leaves selected per game per step. 1 (default) = deterministic mode,
+                               exact sequential MCTS; K>1 = throughput mode with virtual loss */
   float cpuct;              /* mcts.py:231 (default 1.0; weak-promoted to float32)        */
   double dirichlet_alpha;   /* mcts.py:233 (0.3)                                          */
   double dirichlet_epsilon; /* mcts.py:233 (0.25; used in float64, mcts.py:309-311)       */
@@ -150,8 +152,9 @@ int yy_search(yy_engine *e, const uint64_t *root_black_dev, const uint64_t *root
               int32_t *out_counts_dev, void *stream);
 
 /* External-evaluator stepping (YY_EVAL_EXTERNAL): yy_search_begin selects the root leaves;
- * the caller reads yy_engine_leaf_* , fills priors float32[n_games][A] (raw softmax entries,
- * mcts.py:77-78) and values float32[n_games], then calls yy_search_advance, which expands +
+ * the caller reads yy_engine_leaf_* (n_slots = n_games * leaves_per_step entries, slot = game*K + k), fills
+ * priors float32[n_slots][A] (raw softmax entries, mcts.py:77-78) and values float32[n_slots], then calls
+ * yy_search_advance, which expands +
  * backs up and selects the next leaves.  Returns in *out_active the number of games that
  * still need an evaluation (0 = search finished; then call yy_search_counts). */
 int yy_search_begin(yy_engine *e, const uint64_t *root_black_dev, const uint64_t *root_white_dev,

@@ -157,6 +157,30 @@ def test_mcts_matches_oracle_many_games(eng, oracle_mod, shape, sims, games):
     e.close()
 
 
+@pytest.mark.parametrize("K", [4, 16])
+def test_mcts_virtual_loss_throughput_mode(eng, oracle_mod, K):
+    """leaves_per_step = K > 1: K in-flight simulations per game per step with virtual loss.  Not bit-exact by
+    design; invariants: every simulation is accounted for (root child visits sum to n_sims), value sums stay
+    bounded, the arena does not overflow, and the search still concentrates on the deterministic search's
+    preferred moves (the 3 most visited actions overlap)."""
+    n = m = 8
+    games, sims = 32, 256
+    boards, players = random_play_boards(oracle_mod, n, m, games, seed=21, max_frac=0.5)
+    e1 = eng.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="stub")
+    c1, _ = e1.search_host(boards, players)
+    e1.close()
+    ek = eng.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="stub", leaves_per_step=K)
+    ck, wk = ek.search_host(boards, players)
+    st = ek.stats()
+    ek.close()
+    assert st.overflow == 0
+    has_moves = c1.sum(axis=1) > 0
+    assert np.array_equal(ck.sum(axis=1)[has_moves], np.full(has_moves.sum(), sims))
+    assert np.all(np.abs(wk) <= ck + 1e-3)                      # |W| <= N: every virtual loss was taken back
+    agree = [len(set(np.argsort(-c1[i])[:3]) & set(np.argsort(-ck[i])[:3])) for i in np.flatnonzero(has_moves)]
+    assert np.mean(agree) >= 1.5
+
+
 def test_mcts_external_evaluator_seam(eng, oracle_mod):
     """The duck-typed predict seam: priors/values supplied by the caller each step (here: the oracle's stub,
     computed on the host) must give the same visit counts as the fused stub evaluator."""

@@ -93,7 +93,7 @@ def test_abi_exports_every_declared_symbol(yy):
     assert not missing, missing
     assert set(yy._lib.SIGNATURES) >= declared - {"yy_nn_weight_layout"} | {"yy_nn_weight_layout"}
     assert lib.yy_abi_version() == 1
-    assert ctypes.sizeof(yy._lib.EngineConfig) == 80
+    assert ctypes.sizeof(yy._lib.EngineConfig) == 88
 
 
 def test_no_cpu_fallback(yy):

@@ -63,7 +63,7 @@ class EngineConfig(ctypes.Structure):
         ("rule_flags", ctypes.c_uint32), ("mode_flags", ctypes.c_uint32), ("evaluator", ctypes.c_int32),
         ("edges_per_game", ctypes.c_int32), ("temperature_threshold", ctypes.c_int32),
         ("replay_capacity", ctypes.c_int32), ("nn_channels", ctypes.c_int32), ("nn_blocks", ctypes.c_int32),
-        ("device", ctypes.c_int32), ("cpuct", ctypes.c_float), ("dirichlet_alpha", ctypes.c_double),
+        ("device", ctypes.c_int32), ("leaves_per_step", ctypes.c_int32), ("cpuct", ctypes.c_float), ("dirichlet_alpha", ctypes.c_double),
         ("dirichlet_epsilon", ctypes.c_double), ("seed", ctypes.c_uint64),
     ]
 

@@ -24,6 +24,7 @@ struct EngineDev {
   // geometry / config
   int rows, cols, A, W;
   int n_games, n_sims, max_nodes, edges_cap, max_depth;
+  int K, n_slots;   // leaves per game per step (1 = deterministic mode), evaluation slots = n_games * K
   float cpuct;
   float keep_f32;   // f32(1 - eps)            (mcts.py:309-311 under numpy>=2)
   double eps;       // dirichlet epsilon
@@ -38,11 +39,12 @@ struct EngineDev {
   // edges
   int32_t* edge_N; float* edge_W; float* edge_P; int32_t* edge_child; uint8_t* edge_action;
   // per game search state
-  int32_t* g_n_nodes; int32_t* g_n_edges; int32_t* g_sims_done; int32_t* g_leaf; int32_t* g_path_len; int32_t* g_path;
-  // pending leaf batch (evaluator input) and evaluator output
+  int32_t* g_n_nodes; int32_t* g_n_edges; int32_t* g_sims_done; int32_t* g_npending;
+  // pending leaf batch (evaluator input), slot = game*K + k: node id, recorded path, state, rules result
+  int32_t* leaf_node; int32_t* leaf_path_len; int32_t* leaf_path;
   uint64_t* leaf_black; uint64_t* leaf_white; uint64_t* leaf_mask; int8_t* leaf_code; uint8_t* leaf_active;
-  float* eval_prior;  // [n_games][A] raw softmax entries (mcts.py:77-78: unmasked, un-normalised)
-  float* eval_value;  // [n_games]
+  float* eval_prior;  // [n_slots][A] raw softmax entries (mcts.py:77-78: unmasked, un-normalised)
+  float* eval_value;  // [n_slots]
   int32_t* active_count;
   // root inputs for the current search
   uint64_t* root_black; uint64_t* root_white; int8_t* root_player;

@@ -436,14 +436,15 @@ static void nn_scratch_layout(int rows, int cols, int max_boards, int64_t& headf
 size_t nn_workspace_bytes(const yy_engine_config& cfg) {
   if (cfg.evaluator != YY_EVAL_NN) return 0;
   int64_t a, b, c, total;
-  nn_scratch_layout(cfg.rows, cfg.cols, cfg.n_games, a, b, c, total);
+  nn_scratch_layout(cfg.rows, cfg.cols, cfg.n_games * (cfg.leaves_per_step > 0 ? cfg.leaves_per_step : 1), a, b, c, total);
   return (size_t)total;
 }
 
 int nn_init(NNState& nn, const yy_engine_config& cfg, void* scratch) {
   nn = NNState{};
   nn.rows = cfg.rows; nn.cols = cfg.cols; nn.A = cfg.rows * cfg.cols; nn.W = words_for_cells(nn.A);
-  nn.channels = cfg.nn_channels; nn.blocks = cfg.nn_blocks; nn.max_boards = cfg.n_games; nn.device = cfg.device;
+  nn.channels = cfg.nn_channels; nn.blocks = cfg.nn_blocks;
+  nn.max_boards = cfg.n_games * (cfg.leaves_per_step > 0 ? cfg.leaves_per_step : 1); nn.device = cfg.device;
   if (cfg.evaluator != YY_EVAL_NN) return YY_OK;
   if (!nn_geometry_ok(cfg.rows, cfg.cols) || cfg.nn_channels > TW_C)
     return set_error(YY_ERR_INVALID, "network geometry unsupported: %dx%d, %d channels", cfg.rows, cfg.cols, cfg.nn_channels);

@@ -41,21 +41,27 @@ __device__ __forceinline__ float terminal_value_f32(int code) {
   return code == 1 ? 1.0f : (code == -1 ? -1.0f : (float)0.0001);
 }
 
-// Node.update along the recorded path (mcts.py:406-412): the leaf's own slot gets +v, alternating upwards.
-__device__ __forceinline__ void backup_path(const EngineDev& e, int gi, long long eb, int plen, float v, int lane) {
-  const int32_t* path = e.g_path + (long long)gi * e.max_depth;
+// Node.update along a recorded path (mcts.py:406-412): the leaf's own slot gets +v, alternating upwards.
+// `vl_pending`: the path already carries a virtual visit and a virtual loss of 1 (multi-leaf mode) -- the visit
+// stays, the loss is taken back.
+__device__ __forceinline__ void backup_path(const EngineDev& e, const int32_t* path, long long eb, int plen, float v, int lane,
+                                            bool vl_pending) {
   for (int i = lane; i < plen; i += 32) {
     long long ei = eb + path[i];
     float sv = ((plen - 1 - i) & 1) ? -v : v;
-    e.edge_N[ei] += 1;
-    e.edge_W[ei] = __fadd_rn(e.edge_W[ei], sv);
+    if (vl_pending) {
+      e.edge_W[ei] = __fadd_rn(__fadd_rn(e.edge_W[ei], 1.0f), sv);
+    } else {
+      e.edge_N[ei] += 1;
+      e.edge_W[ei] = __fadd_rn(e.edge_W[ei], sv);
+    }
   }
 }
 
 // Writes the state of node `id`, evaluates the rules for it (terminal code + legal mask of the side to
-// move) and publishes it as this game's pending leaf.  All lanes hold identical arguments.
+// move) and publishes it in leaf slot `slot` of the evaluation batch.  All lanes hold identical arguments.
 template <int NW>
-__device__ __forceinline__ void publish_leaf(const EngineDev& e, const Geo<NW>& g, int gi, int lane, int id,
+__device__ __forceinline__ void publish_leaf(const EngineDev& e, const Geo<NW>& g, int gi, int lane, int slot, int id,
                                              const BB<NW>& black, const BB<NW>& white, int player, int plen) {
   BB<NW> mask = legal_for(g, black, white, player);
   int code = ended_code_with_mask(g, black, white, player, mask);
@@ -67,21 +73,22 @@ __device__ __forceinline__ void publish_leaf(const EngineDev& e, const Geo<NW>& 
     e.node_flags[ni] = 0;
     e.node_n_edges[ni] = 0;
     e.node_edge_base[ni] = 0;
-    store_bb<NW>(e.leaf_black, gi, e.W, black);
-    store_bb<NW>(e.leaf_white, gi, e.W, white);
-    store_bb<NW>(e.leaf_mask, gi, e.W, mask);
-    e.leaf_code[gi] = (int8_t)code;
-    e.g_leaf[gi] = id;
-    e.g_path_len[gi] = plen;
+    store_bb<NW>(e.leaf_black, slot, e.W, black);
+    store_bb<NW>(e.leaf_white, slot, e.W, white);
+    store_bb<NW>(e.leaf_mask, slot, e.W, mask);
+    e.leaf_code[slot] = (int8_t)code;
+    e.leaf_node[slot] = id;
+    e.leaf_path_len[slot] = plen;
+    e.leaf_active[slot] = 1;
   }
   if (e.evaluator == YY_EVAL_STUB) {  // deterministic-prior mode: evaluator fused into the tree kernel
     uint64_t key = stub_key(g, black, white);
-    for (int a = lane; a < e.A; a += 32) e.eval_prior[(long long)gi * e.A + a] = stub_prior(key, a);
-    if (lane == 0) e.eval_value[gi] = stub_value(key);
+    for (int a = lane; a < e.A; a += 32) e.eval_prior[(long long)slot * e.A + a] = stub_prior(key, a);
+    if (lane == 0) e.eval_value[slot] = stub_value(key);
   }
 }
 
-// MCTS.search prologue (mcts.py:288-292): fresh tree per game, root = node 0, pending leaf = root.
+// MCTS.search prologue (mcts.py:288-292): fresh tree per game, root = node 0, pending leaf = root (slot g*K).
 template <int NW>
 __global__ void __launch_bounds__(kTreeBlock) tree_root_kernel(EngineDev e, Geo<NW> g) {
   int gi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
@@ -89,16 +96,62 @@ __global__ void __launch_bounds__(kTreeBlock) tree_root_kernel(EngineDev e, Geo<
   BB<NW> b = load_bb<NW>(e.root_black, gi, e.W) & g.full, w = load_bb<NW>(e.root_white, gi, e.W) & g.full;
   int player = e.root_player[gi] == 1 ? 1 : -1;
   if (lane == 0) {
-    e.g_n_nodes[gi] = 1; e.g_n_edges[gi] = 0; e.g_sims_done[gi] = 0;
-    e.leaf_active[gi] = 1;
+    e.g_n_nodes[gi] = 1; e.g_n_edges[gi] = 0; e.g_sims_done[gi] = 0; e.g_npending[gi] = 1;
+    for (int k = 1; k < e.K; ++k) e.leaf_active[gi * e.K + k] = 0;
   }
-  publish_leaf<NW>(e, g, gi, lane, 0, b, w, player, 0);
+  publish_leaf<NW>(e, g, gi, lane, gi * e.K, 0, b, w, player, 0);
   if (gi == 0 && lane == 0) { e.active_count[0] = e.n_games; e.active_count[1] = 0; }
 }
 
-// One lock-step of every tree: (1) expand the pending leaf with the evaluator's output and back its value
-// up (mcts.py:394-412); (2) run simulations from the root until one needs an evaluation (selection,
-// mcts.py:360-362; revisited terminal leaves complete on the spot, :365-367) and publish that leaf.
+// Node.expand (mcts.py:50-91) of the node in `slot` with the evaluator's output + backup of its value.
+template <int NW>
+__device__ __forceinline__ void expand_and_backup(const EngineDev& e, const Geo<NW>& g, int gi, int lane, int slot, long long nb,
+                                                  long long eb, bool multi) {
+  const int leaf = e.leaf_node[slot];
+  const int code = e.leaf_code[slot];
+  const float v = e.eval_value[slot];
+  uint8_t flags = NODE_EXPANDED;
+  float nodeval = 0.0f;
+  if (code != 0) {                       // terminal branch (mcts.py:63-68)
+    flags |= NODE_TERMINAL; nodeval = terminal_value_f32(code);
+  } else {
+    BB<NW> mask = load_bb<NW>(e.leaf_mask, slot, e.W);
+    int cnt = popcount(mask);
+    int base = e.g_n_edges[gi];
+    __syncwarp();
+    if (cnt > 0 && base + cnt > e.edges_cap) { if (lane == 0) atomicExch(&e.stats->overflow, 1); cnt = 0; }
+    if (cnt == 0) {                      // no legal move, not terminal: child-less node, re-evaluated on every
+      flags |= NODE_NOCHILD; nodeval = v;  // visit by the reference (is_expanded() stays False) -> same value
+    } else {
+      const bool noisy = (leaf == 0) && e.noise != nullptr && e.noise_mask != nullptr && e.noise_mask[gi] != 0;
+      for (int a = lane; a < e.A; a += 32) {
+        if (!test(mask, a)) continue;
+        int r = rank_below(mask, a);     // children are created in ascending action order (mcts.py:75-89)
+        float p = e.eval_prior[(long long)slot * e.A + a];
+        if (noisy) {                     // mcts.py:309-311: f32( f64(f32(f32(1-eps)*p)) + eps*noise_i )
+          float keep = __fmul_rn(e.keep_f32, p);
+          p = (float)__dadd_rn((double)keep, __dmul_rn(e.eps, e.noise[(long long)gi * e.A + r]));
+        }
+        long long ei = eb + base + r;
+        e.edge_N[ei] = 0; e.edge_W[ei] = 0.0f; e.edge_P[ei] = p; e.edge_child[ei] = -1;
+        e.edge_action[ei] = (uint8_t)a;
+      }
+      __syncwarp();
+      if (lane == 0) { e.node_edge_base[nb + leaf] = base; e.node_n_edges[nb + leaf] = (int16_t)cnt; e.g_n_edges[gi] = base + cnt; }
+    }
+  }
+  if (lane == 0) { e.node_flags[nb + leaf] = flags; e.node_value[nb + leaf] = nodeval; e.leaf_active[slot] = 0; }
+  // first visit always backs up the evaluator's value (mcts.py:394)
+  backup_path(e, e.leaf_path + (long long)slot * e.max_depth, eb, e.leaf_path_len[slot], v, lane, multi && leaf != 0);
+  __syncwarp();
+}
+
+// One lock-step of every tree: (1) expand the pending leaves with the evaluator's output and back their values
+// up (mcts.py:394-412); (2) run simulations from the root until K of them need an evaluation (selection,
+// mcts.py:360-362; revisited terminal leaves complete on the spot, :365-367) and publish those leaves.
+//   K == 1 : deterministic mode -- exactly the reference's sequential search per game.
+//   K  > 1 : throughput mode -- each in-flight simulation leaves a virtual visit and a virtual loss on its path so
+//            that the next descent of the same step diverges; a descent that runs into an in-flight node stops.
 template <int NW>
 __global__ void __launch_bounds__(kTreeBlock) tree_step_kernel(EngineDev e, Geo<NW> g, int parity) {
   int gi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
@@ -107,61 +160,32 @@ __global__ void __launch_bounds__(kTreeBlock) tree_step_kernel(EngineDev e, Geo<
   if (gi == 0 && lane == 0) e.active_count[parity ^ 1] = 0;
   const long long nb = (long long)gi * e.max_nodes;
   const long long eb = (long long)gi * e.edges_cap;
-  int32_t* path = e.g_path + (long long)gi * e.max_depth;
+  const bool multi = e.K > 1;
   int sims_done = e.g_sims_done[gi];
   int sims_here = 0, evals_here = 0, deepest = 0;
-  const int leaf = e.g_leaf[gi];
 
   // ---------------------------------------------------------------- (1) expand + backup
-  if (leaf >= 0) {
-    const int code = e.leaf_code[gi];
-    const float v = e.eval_value[gi];
-    uint8_t flags = NODE_EXPANDED;
-    float nodeval = 0.0f;
-    if (code != 0) {                       // Node.expand terminal branch (mcts.py:63-68)
-      flags |= NODE_TERMINAL; nodeval = terminal_value_f32(code);
-    } else {
-      BB<NW> mask = load_bb<NW>(e.leaf_mask, gi, e.W);
-      int cnt = popcount(mask);
-      int base = e.g_n_edges[gi];
-      __syncwarp();
-      if (cnt > 0 && base + cnt > e.edges_cap) { if (lane == 0) atomicExch(&e.stats->overflow, 1); cnt = 0; }
-      if (cnt == 0) {                      // no legal move, not terminal: child-less node, re-evaluated on every
-        flags |= NODE_NOCHILD; nodeval = v;  // visit by the reference (is_expanded() stays False) -> same value
-      } else {
-        const bool noisy = (leaf == 0) && e.noise != nullptr && e.noise_mask != nullptr && e.noise_mask[gi] != 0;
-        for (int a = lane; a < e.A; a += 32) {
-          if (!test(mask, a)) continue;
-          int r = rank_below(mask, a);     // children are created in ascending action order (mcts.py:75-89)
-          float p = e.eval_prior[(long long)gi * e.A + a];
-          if (noisy) {                     // mcts.py:309-311: f32( f64(f32(f32(1-eps)*p)) + eps*noise_i )
-            float keep = __fmul_rn(e.keep_f32, p);
-            p = (float)__dadd_rn((double)keep, __dmul_rn(e.eps, e.noise[(long long)gi * e.A + r]));
-          }
-          long long ei = eb + base + r;
-          e.edge_N[ei] = 0; e.edge_W[ei] = 0.0f; e.edge_P[ei] = p; e.edge_child[ei] = -1;
-          e.edge_action[ei] = (uint8_t)a;
-        }
-        __syncwarp();
-        if (lane == 0) { e.node_edge_base[nb + leaf] = base; e.node_n_edges[nb + leaf] = (int16_t)cnt; e.g_n_edges[gi] = base + cnt; }
-      }
-    }
-    if (lane == 0) { e.node_flags[nb + leaf] = flags; e.node_value[nb + leaf] = nodeval; }
-    const int plen = e.g_path_len[gi];
-    backup_path(e, gi, eb, plen, v, lane);   // first visit always backs up the evaluator's value (mcts.py:394)
-    if (leaf != 0) { ++sims_done; ++sims_here; }
-    __syncwarp();
+  const int np_in = e.g_npending[gi];
+  for (int k = 0; k < np_in; ++k) {
+    const int slot = gi * e.K + k;
+    const bool is_root = e.leaf_node[slot] == 0;
+    expand_and_backup<NW>(e, g, gi, lane, slot, nb, eb, multi);
+    if (!is_root) { ++sims_done; ++sims_here; }
   }
 
   // ---------------------------------------------------------------- (2) select
-  bool pending = false;
-  while (sims_done < e.n_sims && !pending) {
+  int np = 0;
+  bool blocked = false;
+  while (sims_done + np < e.n_sims && np < e.K && !blocked) {
+    const int slot = gi * e.K + np;
+    int32_t* path = e.leaf_path + (long long)slot * e.max_depth;
     int node = 0, depth = 0;
     for (;;) {
       const uint8_t fl = e.node_flags[nb + node];
+      if (!(fl & NODE_EXPANDED)) { blocked = true; break; }  // in-flight node of this step (K > 1 only): give up
       if (fl & (NODE_TERMINAL | NODE_NOCHILD)) {   // revisited terminal (mcts.py:365-367) / child-less node
         __syncwarp();                              // path[] written by lane 0 above
-        backup_path(e, gi, eb, depth, e.node_value[nb + node], lane);
+        backup_path(e, path, eb, depth, e.node_value[nb + node], lane, false);
         ++sims_done; ++sims_here;
         __syncwarp();
         break;
@@ -200,9 +224,18 @@ __global__ void __launch_bounds__(kTreeBlock) tree_step_kernel(EngineDev e, Geo<
         const int id = e.g_n_nodes[gi];
         __syncwarp();
         if (lane == 0) { e.g_n_nodes[gi] = id + 1; e.edge_child[eb + eoff] = id; }
-        publish_leaf<NW>(e, g, gi, lane, id, b, w, -pp, depth);
+        publish_leaf<NW>(e, g, gi, lane, slot, id, b, w, -pp, depth);
+        if (multi) {                        // virtual visit + virtual loss along the in-flight path
+          __syncwarp();
+          for (int i = lane; i < depth; i += 32) {
+            long long ei = eb + path[i];
+            e.edge_N[ei] += 1;
+            e.edge_W[ei] = __fadd_rn(e.edge_W[ei], -1.0f);
+          }
+        }
         if (depth > deepest) deepest = depth;
-        pending = true; ++evals_here;
+        ++np; ++evals_here;
+        __syncwarp();
         break;
       }
       node = child;
@@ -211,9 +244,8 @@ __global__ void __launch_bounds__(kTreeBlock) tree_step_kernel(EngineDev e, Geo<
   __syncwarp();
   if (lane == 0) {
     e.g_sims_done[gi] = sims_done;
-    if (!pending) e.g_leaf[gi] = -1;
-    e.leaf_active[gi] = pending ? 1 : 0;
-    if (pending) atomicAdd(e.active_count + parity, 1);
+    e.g_npending[gi] = np;
+    if (np) atomicAdd(e.active_count + parity, np);
     if (sims_here) atomicAdd(&e.stats->sims, (unsigned long long)sims_here);
     if (evals_here) atomicAdd(&e.stats->evals, (unsigned long long)evals_here);
     if (deepest > e.stats->max_depth) atomicMax(&e.stats->max_depth, deepest);
@@ -399,6 +431,9 @@ static int normalise_cfg(yy_engine_config& c) {
   if (c.temperature_threshold < 0) c.temperature_threshold = 0;
   if (c.nn_channels <= 0) c.nn_channels = 128;
   if (c.nn_blocks < 0) c.nn_blocks = 10;
+  if (c.leaves_per_step < 1) c.leaves_per_step = 1;
+  if (c.leaves_per_step > 64) return set_error(YY_ERR_INVALID, "leaves_per_step must be <= 64");
+  // in-flight simulations each own a node: keep the worst case inside the node arena
   return YY_OK;
 }
 
@@ -413,10 +448,13 @@ static void carve(const yy_engine_config& c, Carver& k, EngineDev& d) {
   d.edge_N = k.take<int32_t>(G * EC); d.edge_W = k.take<float>(G * EC); d.edge_P = k.take<float>(G * EC);
   d.edge_child = k.take<int32_t>(G * EC); d.edge_action = k.take<uint8_t>(G * EC);
   d.g_n_nodes = k.take<int32_t>(G); d.g_n_edges = k.take<int32_t>(G); d.g_sims_done = k.take<int32_t>(G);
-  d.g_leaf = k.take<int32_t>(G); d.g_path_len = k.take<int32_t>(G); d.g_path = k.take<int32_t>(G * (size_t)d.max_depth);
-  d.leaf_black = k.take<uint64_t>(G * W); d.leaf_white = k.take<uint64_t>(G * W); d.leaf_mask = k.take<uint64_t>(G * W);
-  d.leaf_code = k.take<int8_t>(G); d.leaf_active = k.take<uint8_t>(G);
-  d.eval_prior = k.take<float>(G * A); d.eval_value = k.take<float>(G); d.active_count = k.take<int32_t>(2);
+  d.K = c.leaves_per_step; d.n_slots = c.n_games * c.leaves_per_step;
+  const size_t S = (size_t)d.n_slots;
+  d.g_npending = k.take<int32_t>(G);
+  d.leaf_node = k.take<int32_t>(S); d.leaf_path_len = k.take<int32_t>(S); d.leaf_path = k.take<int32_t>(S * (size_t)d.max_depth);
+  d.leaf_black = k.take<uint64_t>(S * W); d.leaf_white = k.take<uint64_t>(S * W); d.leaf_mask = k.take<uint64_t>(S * W);
+  d.leaf_code = k.take<int8_t>(S); d.leaf_active = k.take<uint8_t>(S);
+  d.eval_prior = k.take<float>(S * A); d.eval_value = k.take<float>(S); d.active_count = k.take<int32_t>(2);
   d.root_black = k.take<uint64_t>(G * W); d.root_white = k.take<uint64_t>(G * W); d.root_player = k.take<int8_t>(G);
   d.noise = k.take<double>(G * A); d.noise_mask = k.take<uint8_t>(G);
   d.sp_black = k.take<uint64_t>(G * W); d.sp_white = k.take<uint64_t>(G * W); d.sp_player = k.take<int8_t>(G);
@@ -467,16 +505,30 @@ int launch_step(yy_engine* e, cudaStream_t s) {
 int run_evaluator(yy_engine* e, cudaStream_t s) {
   if (e->cfg.evaluator == YY_EVAL_STUB) return YY_OK;
   if (e->cfg.evaluator == YY_EVAL_NN)
-    return nn_forward(e->nn, e->dev.leaf_black, e->dev.leaf_white, e->dev.n_games, e->dev.eval_prior, e->dev.eval_value,
+    return nn_forward(e->nn, e->dev.leaf_black, e->dev.leaf_white, e->dev.n_slots, e->dev.eval_prior, e->dev.eval_value,
                       nullptr, s);
   return set_error(YY_ERR_STATE, "external evaluator: use yy_search_begin / yy_search_advance");
 }
 // full search over the roots already stored in dev.root_* (noise pointers already set in dev)
 int search_core(yy_engine* e, cudaStream_t s) {
   int rc = launch_root(e, s); if (rc) return rc;
+  if (e->cfg.leaves_per_step <= 1) {      // deterministic mode: exactly n_sims + 1 lock-steps, no host synchronisation
+    for (int i = 0; i <= e->cfg.n_sims; ++i) {
+      rc = run_evaluator(e, s); if (rc) return rc;
+      rc = launch_step(e, s); if (rc) return rc;
+    }
+    return YY_OK;
+  }
+  // throughput mode: a step retires up to K simulations per game; poll the pending-leaf counter every few steps
   for (int i = 0; i <= e->cfg.n_sims; ++i) {
     rc = run_evaluator(e, s); if (rc) return rc;
     rc = launch_step(e, s); if (rc) return rc;
+    if ((i & 3) == 3 || i == e->cfg.n_sims) {
+      int32_t active = 0;
+      YY_CUDA_OK(cudaMemcpyAsync(&active, e->dev.active_count + e->step_parity, 4, cudaMemcpyDeviceToHost, s));
+      YY_CUDA_OK(cudaStreamSynchronize(s));
+      if (active == 0) break;
+    }
   }
   return YY_OK;
 }
@@ -571,7 +623,7 @@ int yy_search_advance(yy_engine* e, const float* priors, const float* values, in
   if (!e) return set_error(YY_ERR_INVALID, "null engine");
   if (!e->search_open) return set_error(YY_ERR_STATE, "yy_search_advance without yy_search_begin");
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t G = (size_t)e->dev.n_games, A = (size_t)e->dev.A;
+  const size_t G = (size_t)e->dev.n_slots, A = (size_t)e->dev.A;
   if (priors && values) {
     YY_CUDA_OK(cudaMemcpyAsync(e->dev.eval_prior, priors, G * A * 4, cudaMemcpyDeviceToDevice, s));
     YY_CUDA_OK(cudaMemcpyAsync(e->dev.eval_value, values, G * 4, cudaMemcpyDeviceToDevice, s));

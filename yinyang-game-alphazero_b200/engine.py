@@ -173,11 +173,13 @@ class Engine:
     def __init__(self, rows=8, cols=8, n_games=1, n_sims=800, evaluator="stub", cpuct=1.0, rule_flags=0,
                  search_as_black=True, edges_per_game=0, dirichlet_alpha=0.3, dirichlet_epsilon=0.25,
                  temperature_threshold=10, seed=0, replay_capacity=0, state_dict=None, nn_channels=128, nn_blocks=10,
-                 device=None):
+                 device=None, leaves_per_step=1):
         _require_cuda()
         self.L = _lib.lib()
         self.rows, self.cols, self.A, self.W = rows, cols, rows * cols, bitboard.words_for(rows, cols)
         self.n_games, self.n_sims = n_games, n_sims
+        self.leaves_per_step = max(1, int(leaves_per_step))
+        self.n_slots = n_games * self.leaves_per_step
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.tdev = torch.device("cuda", self.device)
         ev = {"stub": EVAL_STUB, "nn": EVAL_NN, "external": EVAL_EXTERNAL}[evaluator]
@@ -193,7 +195,7 @@ class Engine:
                                      mode_flags=MODE_SEARCH_AS_BLACK if search_as_black else 0, evaluator=ev,
                                      edges_per_game=edges_per_game, temperature_threshold=temperature_threshold,
                                      replay_capacity=replay_capacity, nn_channels=nn_channels, nn_blocks=nn_blocks,
-                                     device=self.device, cpuct=cpuct, dirichlet_alpha=dirichlet_alpha,
+                                     device=self.device, leaves_per_step=self.leaves_per_step, cpuct=cpuct, dirichlet_alpha=dirichlet_alpha,
                                      dirichlet_epsilon=dirichlet_epsilon, seed=seed)
         need = self.L.yy_engine_workspace_bytes(ctypes.byref(self.cfg))
         if need < 0:
@@ -285,14 +287,14 @@ class Engine:
         return int(active.value)
 
     def leaf_batch(self):
-        """(black int64[n_games,W], white, active uint8[n_games]) views of the pending leaf batch."""
+        """(black int64[n_slots,W], white, active uint8[n_slots]) views of the pending leaf batch (slot = game*K + k)."""
         def view(ptr, n, dtype):
             off = ptr - self.workspace.data_ptr()
             return self.workspace[off: off + n].view(dtype)
-        nb = self.n_games * self.W * 8
-        return (view(self.L.yy_engine_leaf_black(self.handle), nb, torch.int64).view(self.n_games, self.W),
-                view(self.L.yy_engine_leaf_white(self.handle), nb, torch.int64).view(self.n_games, self.W),
-                view(self.L.yy_engine_leaf_active(self.handle), self.n_games, torch.uint8))
+        nb = self.n_slots * self.W * 8
+        return (view(self.L.yy_engine_leaf_black(self.handle), nb, torch.int64).view(self.n_slots, self.W),
+                view(self.L.yy_engine_leaf_white(self.handle), nb, torch.int64).view(self.n_slots, self.W),
+                view(self.L.yy_engine_leaf_active(self.handle), self.n_slots, torch.uint8))
 
     def search_counts(self):
         counts = torch.empty((self.n_games, self.A), dtype=torch.int32, device=self.tdev)
