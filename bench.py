@@ -135,7 +135,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "moves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -261,7 +261,7 @@ def run_b200(args):
                 "leaf_evals_per_s": (SIMS + 1) * value,
                 "nccl": {"weight_broadcast_s": t_bcast, "replay_gather_s": t_gather, "replay_records_gathered": int(n_records)},
                 "selfplay_stats": st.__dict__}
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -314,7 +314,24 @@ def bench_env(engine, torch, peaks):
             "l2_policy": "L2 flushed (256 MB write) before each timed group of 8 launches on fresh copies"}
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner,
+    torchrun notices) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)

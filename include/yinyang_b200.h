@@ -108,6 +108,10 @@ typedef struct yy_engine yy_engine;
 #define YY_MODE_SEARCH_AS_BLACK 1u /* self-play searches every position as player 1 and applies the move
                                       with the real player (self_play.py:99,135-137,163).
                                       Default ON in the reference-compatible facade. */
+#define YY_MODE_STEP_KERNELS 2u    /* run a search as one tree-step kernel launch (+ network launches) per
+                                      simulation instead of ONE persistent kernel per search.  The persistent
+                                      kernel (csrc/yy_fused.cu) is the default for the STUB and NN evaluators with
+                                      leaves_per_step == 1; both produce identical trees. */
 
 typedef struct {
   int32_t rows, cols;

@@ -139,8 +139,13 @@ def test_mcts_visit_counts_match_reference_golden(eng, name):
     e.close()
 
 
-@pytest.mark.parametrize("shape,sims,games", [((8, 8), 200, 96), ((6, 6), 150, 64), ((4, 4), 300, 64), ((16, 16), 40, 8)])
-def test_mcts_matches_oracle_many_games(eng, oracle_mod, shape, sims, games):
+@pytest.mark.parametrize("step_kernels", [False, True])
+@pytest.mark.parametrize("shape,sims,games", [((8, 8), 200, 96), ((6, 6), 150, 64), ((4, 4), 300, 64), ((16, 16), 40, 8),
+                                              ((8, 8), 60, 700)])
+def test_mcts_matches_oracle_many_games(eng, oracle_mod, shape, sims, games, step_kernels):
+    """Both search drivers -- ONE persistent kernel per search (default, csrc/yy_fused.cu) and one tree-step launch
+    per simulation (YY_MODE_STEP_KERNELS) -- must reproduce the oracle bit for bit.  700 games: several games per
+    CTA and more than one heads batch per CTA in the persistent kernel."""
     n, m = shape
     boards, players = random_play_boards(oracle_mod, n, m, games, seed=5 + n)
     rng = np.random.default_rng(1)
@@ -148,9 +153,9 @@ def test_mcts_matches_oracle_many_games(eng, oracle_mod, shape, sims, games):
     for i in range(games):
         k = int(oracle_mod.legal_mask(boards[i][None], players[i:i + 1], n, m).sum())
         noise.append(rng.dirichlet([0.3] * k) if (i % 3 == 0 and k > 0) else None)
-    e = eng.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="stub", cpuct=1.25)
+    e = eng.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="stub", cpuct=1.25, step_kernels=step_kernels)
     counts, cw = e.search_host(boards, players, noise=noise)
-    for i in range(games):
+    for i in range(0, games, 1 if games <= 100 else 7):
         r = oracle_mod.mcts_search(boards[i], int(players[i]), n, m, sims, cpuct=1.25, noise=noise[i])
         assert np.array_equal(counts[i], r["counts"]), i
         assert np.array_equal(cw[i], r["child_w"]), i
@@ -215,7 +220,8 @@ def test_mcts_external_evaluator_seam(eng, oracle_mod):
 @pytest.mark.parametrize("cfg", [(8, 8, 128, 10, 300, False), (8, 8, 128, 10, 64, True), (8, 8, 128, 0, 40, True),
                                  (8, 8, 128, 1, 40, True), (6, 6, 128, 3, 64, True), (8, 8, 32, 2, 50, True),
                                  (16, 16, 128, 1, 9, True), (5, 7, 64, 2, 33, True)])
-def test_network_matches_fp32_reference(eng, oracle_mod, cfg):
+@pytest.mark.parametrize("step_kernels", [False, True])
+def test_network_matches_fp32_reference(eng, oracle_mod, cfg, step_kernels):
     """bf16 tcgen05 tower + heads vs the fp32 torch network (reference semantics, neural_network.py:94-154).
     Stated tolerance (bf16 weights + bf16 inter-layer activations, fp32 accumulate), measured headroom ~2x:
         logits  max|err| <= 0.015 * max|logit| + 0.01      value  max|err| <= 0.06
@@ -231,7 +237,8 @@ def test_network_matches_fp32_reference(eng, oracle_mod, cfg):
     torch.manual_seed(0)
     net = port.build_net(n, m, C, blocks)
     net = randomise_bn(net) if rnd else net.eval()
-    e = eng.Engine(rows=n, cols=m, n_games=max(count, 4), n_sims=1, evaluator="nn", state_dict=net.state_dict())
+    e = eng.Engine(rows=n, cols=m, n_games=max(count, 4), n_sims=1, evaluator="nn", state_dict=net.state_dict(),
+                   step_kernels=step_kernels)
     boards, _ = random_play_boards(oracle_mod, n, m, count, seed=9)
     policy, value, logits = e.evaluate_host(boards, want_logits=True)
     with torch.no_grad():
@@ -254,6 +261,38 @@ def test_network_matches_fp32_reference(eng, oracle_mod, cfg):
     p2, v2, l2 = e.evaluate_host(boards, want_logits=True)
     assert np.array_equal(l2, logits) and np.array_equal(v2, value)
     e.close()
+
+
+def test_network_search_persistent_vs_step_kernels(eng, oracle_mod):
+    """Network-driven search: the persistent kernel (tower + FC heads + tree step fused) against the per-simulation
+    launches.  The two FC implementations sum in a different order, so priors differ in the last bits and a
+    near-tie in PUCT may flip; the trees must still agree almost everywhere and every simulation must be accounted for."""
+    import torch
+    from oracle import port
+    n = m = 8
+    games, sims = 300, 48
+    torch.manual_seed(3)
+    net = randomise_bn(port.build_net(n, m, 128, 2))
+    boards, players = random_play_boards(oracle_mod, n, m, games, seed=77, max_frac=0.6)
+    res = []
+    for sk in (False, True):
+        e = eng.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="nn", state_dict=net.state_dict(), step_kernels=sk)
+        c, w = e.search_host(boards, players)
+        st = e.stats()
+        assert st.overflow == 0
+        res.append((c, w))
+        pol, val = e.evaluate_host(boards)[:2]
+        res.append((pol, val))
+        e.close()
+    (c0, w0), (p0, v0), (c1, w1), (p1, v1) = res
+    np.testing.assert_allclose(p0, p1, rtol=0, atol=2e-4)
+    np.testing.assert_allclose(v0, v1, rtol=0, atol=2e-4)
+    has_moves = c1.sum(axis=1) > 0
+    assert np.array_equal(c0.sum(axis=1), c1.sum(axis=1))
+    assert np.all(c0.sum(axis=1)[has_moves] == sims)
+    same = (c0 == c1).all(axis=1)
+    assert same.mean() >= 0.9, same.mean()
+    assert np.abs(c0 - c1).sum(axis=1).max() <= sims
 
 
 # ------------------------------------------------------------------------------------------------ self-play driver

@@ -1,0 +1,511 @@
+// yy_fused.cu -- ONE persistent kernel for a whole MCTS search: residual tower + FC heads + tree step, per CTA.
+//
+// Games are independent (self_play.py:288-335), so a CTA can own a fixed run of games for the whole search and
+// never needs a grid-wide synchronisation: for every simulation it
+//   (1) evaluates the pending leaves of its games on the tensor cores -- the residual tower of yy_nn.cu
+//       (neural_network.py:94-123) group by group, activations resident in shared memory, then the two FC heads
+//       (policy_fc, value_fc1: :112-121) for all of its <= 32 boards at once, the FC weights streamed through the
+//       same bulk-copy ring as the conv weights and used as the M = 128 UMMA operand (boards are the N operand);
+//   (2) finishes the heads on the CUDA cores (softmax over all A logits, predict() :152; value_fc2 + tanh :121);
+//   (3) runs Node.expand / backup / select (mcts.py:50-156, 345-414) for each of its games, one warp per game
+//       (tree_step_game, yy_tree_dev.cuh), which publishes the next leaves.
+// Nothing returns to the host between simulations: a search is one launch instead of 4 x (n_sims + 1).
+// The same kernel with iterations = 1 and the tree step off is the batched network forward (yy_evaluate).
+//
+// Warp roles (as in tower_kernel): warp 0 weight producer, warp 1 MMA issuer, warps 2-17 epilogue / heads / tree.
+// Roofline: tensor (the tower's conv MMAs are > 99 % of the FLOPs; see yy_nn.cu for the tower layout).
+#include "yy_nn.cuh"
+#include "yy_tower.cuh"
+#include "yy_tree_dev.cuh"
+
+namespace yy {
+using namespace ptx;
+
+struct FusedArgs {
+  TowerGeo g;
+  FcGeo fc;
+  const uint8_t* conv_stream;  // stage-ordered bf16 conv weight blocks
+  const float* conv_bias;      // [1 + 2*blocks][128] then head [64]
+  const uint8_t* fc_stream;    // stage-ordered bf16 FC weight blocks (policy_fc, value_fc1)
+  const float* fc_policy_b; const float* fc_value1_b; const float* fc_value2_w; const float* fc_value2_b;
+  const uint64_t* black; const uint64_t* white;   // [count][W] boards to evaluate (search: the leaf batch)
+  long long count;
+  int boards_per_cta;          // contiguous run of boards (= games in a search) owned by a CTA
+  int batch_boards;            // <= FC_N boards per heads pass; a multiple of g.Gb
+  __nv_bfloat16* headfeat;     // [count][64*A] head-conv features, index c*A + cell (L2-resident round trip)
+  float* policy; float* value; float* logits;     // [count][A], [count], optional [count][A]
+  int iterations;              // 1 = plain forward; n_sims + 1 = whole search
+  int do_tree;                 // run tree_step_game after every evaluation
+  int use_nn;                  // 0 = deterministic-prior (stub) evaluator: tree steps only
+  long long* dbg;
+};
+
+constexpr int kEpiBarrier = 1;   // named barrier of the 16 epilogue warps
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(TW_EPI_THREADS) : "memory"); }
+
+template <int NW>
+__global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a, const EngineDev e, const Geo<NW> geo) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const TowerGeo& g = a.g;
+  const FcGeo& fc = a.fc;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = 2 * g.blocks + 2;  // stem + 2*blocks tower convs + head conv
+  int16_t* pos_p = reinterpret_cast<int16_t*>(smem + SM_POS);                       // M row -> padded position
+  int16_t* pos_tab = reinterpret_cast<int16_t*>(smem + SM_POS + 128 * TW_MAXT * 2);    // M row -> board*256 + cell, or -1
+  const uint32_t bar0 = smem_u32(smem + SM_BAR);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (TW_STAGES + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * TW_STAGES), act_ready = bar0 + 8u * (2 * TW_STAGES + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
+
+  // ---- one-time setup ----
+  for (int i = tid; i < (SM_POS - SM_ACT) / 4; i += TW_THREADS) reinterpret_cast<uint32_t*>(smem + SM_ACT)[i] = 0u;   // act + ring
+  for (int i = tid; i < 128 * TW_MAXT; i += TW_THREADS) {
+    int v = -1, p, b, y, x;
+    if (g.row_aligned) {
+      const int R = (i >> 7) * 16 + ((i & 127) >> 3);
+      x = i & 7; p = R * g.pitch + x; b = R / g.rows_per_board; y = R % g.rows_per_board;
+    } else {
+      p = i; b = p / g.PB; const int rem = p % g.PB; y = rem / g.pitch; x = rem % g.pitch;
+    }
+    if (b < g.Gb && y < g.n && x < g.m) v = b * 256 + y * g.m + x;
+    pos_p[i] = (int16_t)p;
+    pos_tab[i] = (int16_t)v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < TW_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(act_ready, TW_EPI_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (a.dbg && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.dbg[128 + 2 * blockIdx.x] = (long long)gt; }
+  const uint32_t act_base = smem_u32(smem + SM_ACT);
+  const uint32_t ring_base = smem_u32(smem + SM_RING);
+  // this CTA's run of boards [run_lo, run_hi), walked in batches of <= FC_N boards; a batch in groups of Gb boards
+  const long long run_lo = (long long)blockIdx.x * a.boards_per_cta;
+  const long long run_hi = (run_lo + a.boards_per_cta < a.count) ? run_lo + a.boards_per_cta : a.count;
+  // tiles a group starting at board b0 needs when its batch ends at `lim`
+  // (+pitch+1: the taps of the last real position read that far; rows beyond the group's tiles may be stale)
+  auto tiles_for = [&](long long b0, long long lim) {
+    long long nb = lim - b0; if (nb > g.Gb) nb = g.Gb;
+    int t = g.row_aligned ? (int)((nb * g.rows_per_board + 15) >> 4) : (int)((nb * g.PB + g.pitch + 1 + 127) >> 7);
+    return t < g.T ? t : g.T;
+  };
+  auto batch_end = [&](long long bb0) { return (bb0 + a.batch_boards < run_hi) ? bb0 + a.batch_boards : run_hi; };
+  // FC stage geometry: rows of M tile t of head h
+  auto fc_tiles = [&](int h) { return h ? 2 : fc.Tp; };
+  auto fc_rows = [&](int h, int t) { return (h || t < fc.Tp - 1) ? 128 : fc.Rp_last; };
+  auto panel_stages = [&](int p) { const int r = fc.KS - p * FC_PANEL_STAGES; return r < FC_PANEL_STAGES ? r : FC_PANEL_STAGES; };
+
+  if (warp == 0) {
+    // =========================================================== weight producer (whole warp walks the loop with
+    // warp-uniform state; one elected lane issues the bulk copies -- keeps everything on the uniform datapath)
+    if (a.use_nn) {
+      uint32_t it = 0;
+      auto push = [&](const uint8_t* src, uint32_t bytes) {
+        const uint32_t slot = it % TW_STAGES;
+        if (it >= TW_STAGES) mbar_wait(empty_bar(slot), ((it / TW_STAGES) - 1) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(slot), bytes);
+          bulk_g2s(ring_base + slot * TW_STAGE_BYTES, src, bytes, full_bar(slot));
+        }
+        __syncwarp();
+        ++it;
+      };
+      for (int iter = 0; iter < a.iterations; ++iter) {
+        for (long long bb0 = run_lo; bb0 < run_hi; bb0 += a.batch_boards) {
+          const long long lim = batch_end(bb0);
+          for (long long b0 = bb0; b0 < lim; b0 += g.Gb) {
+            for (int l = 0; l < L; ++l) {
+              const LayerInfo li = layer_info(l, g.blocks);
+              const uint8_t* src = a.conv_stream + li.stream_off;
+              for (int j = 0; j < li.n_stages; ++j) push(src + (long long)j * li.stage_bytes, (uint32_t)li.stage_bytes);
+            }
+          }
+          const uint8_t* src = a.fc_stream;
+          for (int h = 0; h < 2; ++h)
+            for (int p = 0; p < fc.n_panels; ++p) {
+              const int ns = panel_stages(p);
+              for (int t = 0; t < fc_tiles(h); ++t) {
+                const uint32_t bytes = 128u * (uint32_t)fc_rows(h, t);
+                for (int s = 0; s < ns; ++s) { push(src, bytes); src += bytes; }
+              }
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer (whole warp runs the control flow, the
+    // tcgen05.mma / commit instructions are issued by one elected lane; descriptors are base + constant deltas)
+    if (a.use_nn) {
+      uint32_t it = 0, act_phase = 0;
+      const uint64_t kTileDelta = (uint64_t)g.tile_adv;            // next M=128 tile, in 16-byte rows
+      constexpr uint64_t kK16DeltaA = (2u * TW_ROWS * 16u) >> 4;   // next K=16 slice: +2 channel chunks
+      constexpr uint64_t kK16DeltaF = (2u * FC_LBO) >> 4;          // same for the FC feature panel
+      for (int iter = 0; iter < a.iterations; ++iter) {
+        for (long long bb0 = run_lo; bb0 < run_hi; bb0 += a.batch_boards) {
+          const long long lim = batch_end(bb0);
+          for (long long b0 = bb0; b0 < lim; b0 += g.Gb) {
+            const int T = tiles_for(b0, lim);
+            for (int l = 0; l < L; ++l) {
+              const LayerInfo li = layer_info(l, g.blocks);
+              const bool preloaded = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 0);  // conv2: accumulator holds the skip input
+              const uint32_t idesc = idesc_bf16(128, li.N);
+              const uint64_t k16_delta_b = (uint64_t)((2u * (uint32_t)li.N * 16u) >> 4);
+              mbar_wait(act_ready, act_phase); act_phase ^= 1;
+              tc_fence_after();
+              for (int j = 0; j < li.n_stages; ++j, ++it) {
+                const uint32_t slot = it % TW_STAGES;
+                int tapshift, chunk0;
+                stage_info(l, j, g.blocks, g.pitch, tapshift, chunk0);
+                mbar_wait(full_bar(slot), (it / TW_STAGES) & 1);
+                tc_fence_after();
+                const uint64_t ad0 = smem_desc(act_base + (uint32_t)((chunk0 * TW_ROWS + TW_PAD + tapshift) * 16), TW_ROWS * 16, (uint32_t)g.sbo_bytes);
+                const uint64_t bd0 = smem_desc(ring_base + slot * TW_STAGE_BYTES, (uint32_t)li.N * 16, 128);
+                const uint32_t acc0 = (preloaded || j > 0) ? 1u : 0u;
+                if (elect_one()) {
+#pragma unroll
+                  for (int t = 0; t < TW_MAXT; ++t) {
+                    if (t < T) {
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                        if (k < li.nk16)
+                          tc_mma_bf16(tmem_base + (uint32_t)(t * 128), ad0 + (uint64_t)t * kTileDelta + (uint64_t)k * kK16DeltaA,
+                                      bd0 + (uint64_t)k * k16_delta_b, idesc, k > 0 ? 1u : acc0);
+                      }
+                    }
+                  }
+                  tc_commit(empty_bar(slot));
+                }
+                __syncwarp();
+              }
+              if (elect_one()) tc_commit(acc_full);
+              __syncwarp();
+            }
+          }
+          // ---- FC heads: D[o][board] (+)= Wfc[o][k] * feat[board][k]; A = weight stage in the ring, B = feature panel
+          const uint32_t idesc_fc = idesc_bf16(128, FC_N);
+          for (int h = 0; h < 2; ++h)
+            for (int p = 0; p < fc.n_panels; ++p) {
+              const int ns = panel_stages(p);
+              mbar_wait(act_ready, act_phase); act_phase ^= 1;
+              tc_fence_after();
+              for (int t = 0; t < fc_tiles(h); ++t) {
+                const uint32_t R = (uint32_t)fc_rows(h, t);
+                const uint32_t dcol = (uint32_t)((h ? fc.Tp + t : t) * FC_N);
+                const uint64_t k16_delta_w = (uint64_t)((2u * R * 16u) >> 4);
+                for (int s = 0; s < ns; ++s, ++it) {
+                  const uint32_t slot = it % TW_STAGES;
+                  mbar_wait(full_bar(slot), (it / TW_STAGES) & 1);
+                  tc_fence_after();
+                  const uint64_t wd0 = smem_desc(ring_base + slot * TW_STAGE_BYTES, R * 16, 128);
+                  const uint64_t fd0 = smem_desc(act_base + (uint32_t)(s * 8 * FC_LBO), FC_LBO, 128);
+                  const uint32_t acc0 = (p > 0 || s > 0) ? 1u : 0u;
+                  if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      tc_mma_bf16(tmem_base + dcol, wd0 + (uint64_t)k * k16_delta_w, fd0 + (uint64_t)k * kK16DeltaF, idesc_fc,
+                                  k > 0 ? 1u : acc0);
+                    tc_commit(empty_bar(slot));
+                  }
+                  __syncwarp();
+                }
+              }
+              if (elect_one()) tc_commit(acc_full);
+              __syncwarp();
+            }
+        }
+      }
+    }
+  } else {
+    // =========================================================== epilogue warps (2..17): warp -> (tile, lane quarter)
+    const int ew = warp - 2;
+    const int etid = tid - 64;
+    const int quarter = warp & 3;        // TMEM lanes a warp may touch: 32*(warp_id % 4) ..
+    const int tile0 = ew >> 2;           // with 16 warps every tile of the group has its own 4 warps
+    constexpr int kTileStride = TW_EPI_WARPS / 4;
+    uint32_t acc_phase = 0;
+    uint8_t* act = smem + SM_ACT;
+    float* sc_logit = reinterpret_cast<float*>(act);                 // [FC_N][256] heads scratch (act region is free then)
+    float* sc_hidden = reinterpret_cast<float*>(act) + FC_N * 256;   // [FC_N][256] relu(fc1) * w2
+    for (int iter = 0; iter < a.iterations; ++iter) {
+      for (long long bb0 = run_lo; bb0 < run_hi; bb0 += a.batch_boards) {
+        const long long lim = batch_end(bb0);
+        const int nbb = (int)(lim - bb0);
+        if (a.use_nn) {
+          for (long long b0 = bb0; b0 < lim; b0 += g.Gb) {
+            const int T = tiles_for(b0, lim);
+            // ---- stem input planes (board_to_input, neural_network.py:156-196) for my rows ----
+            for (int t = tile0; t < T; t += kTileStride) {
+              const int mi = t * 128 + quarter * 32 + lane;
+              const int p = pos_p[mi];
+              const int info = pos_tab[mi];
+              uint4 c0 = make_uint4(0, 0, 0, 0);
+              const long long board = b0 + (info >= 0 ? (info >> 8) : 0);
+              if (info >= 0 && board < lim) {
+                const int cell = info & 255, y = cell / g.m, x = cell % g.m;
+                const uint64_t* bb = a.black + board * g.W; const uint64_t* wb = a.white + board * g.W;
+                auto bit = [&](const uint64_t* v, int c) { return (int)((v[c >> 6] >> (c & 63)) & 1ull); };
+                const int isb = bit(bb, cell), isw = bit(wb, cell);
+                int rc = 0, cc = 0;
+                for (int xx = 0; xx < g.m; ++xx) { int c = y * g.m + xx; rc += bit(bb, c) | bit(wb, c); }
+                for (int yy = 0; yy < g.n; ++yy) { int c = yy * g.m + x; cc += bit(bb, c) | bit(wb, c); }
+                const float rf = (float)((double)rc / (double)g.m), cf = (float)((double)cc / (double)g.n);
+                const float rf_hi = __bfloat162float(__float2bfloat16_rn(rf)), cf_hi = __bfloat162float(__float2bfloat16_rn(cf));
+                // channels: 0 empty, 1 black, 2 white, 3 row fill, 4 col fill, 5/6 = bf16 residuals of 3/4 (same weights)
+                c0.x = pack_bf16x2((isb | isw) ? 0.0f : 1.0f, isb ? 1.0f : 0.0f);
+                c0.y = pack_bf16x2(isw ? 1.0f : 0.0f, rf_hi);
+                c0.z = pack_bf16x2(cf_hi, rf - rf_hi);
+                c0.w = pack_bf16x2(cf - cf_hi, 0.0f);
+              }
+              *reinterpret_cast<uint4*>(act + (size_t)(0 * TW_ROWS + TW_PAD + p) * 16) = c0;
+              *reinterpret_cast<uint4*>(act + (size_t)(1 * TW_ROWS + TW_PAD + p) * 16) = make_uint4(0, 0, 0, 0);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(act_ready);
+
+            for (int l = 0; l < L; ++l) {
+              const bool is_head = (l == L - 1);
+              const bool is_conv1 = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 1);
+              const float* bias = a.conv_bias + (size_t)l * TW_C;
+              mbar_wait(acc_full, acc_phase); acc_phase ^= 1;
+              tc_fence_after();
+              for (int t = tile0; t < T; t += kTileStride) {
+                const int mi = t * 128 + quarter * 32 + lane;
+                const int p = pos_p[mi];
+                const int info = pos_tab[mi];
+                const long long board = b0 + (info >= 0 ? (info >> 8) : 0);
+                const bool real = info >= 0 && board < lim;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 128);
+                uint8_t* rowp = act + (size_t)(TW_PAD + p) * 16;
+                if (!is_head) {
+                  // one 16-column chunk: bias + ReLU (+ park the skip input in TMEM) -> two 16-byte channel chunks in place
+                  auto process = [&](const uint32_t (&r)[16], int cc) {
+                    uint4* d0 = reinterpret_cast<uint4*>(rowp + (size_t)(2 * cc) * TW_ROWS * 16);
+                    uint4* d1 = reinterpret_cast<uint4*>(rowp + (size_t)(2 * cc + 1) * TW_ROWS * 16);
+                    if (is_conv1) {  // skip connection: conv2 will accumulate on top of the block input
+                      const uint4 x0 = *d0, x1 = *d1;
+                      uint32_t xr[16];
+                      const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                      for (int q = 0; q < 8; ++q) { xr[2 * q] = xs[q] << 16; xr[2 * q + 1] = xs[q] & 0xffff0000u; }
+                      tc_st16(taddr + cc * 16, xr);
+                    }
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + cc * 16);
+                    float v[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const float4 bq = __ldg(b4 + q);
+                      v[4 * q + 0] = fmaxf(__uint_as_float(r[4 * q + 0]) + bq.x, 0.0f);
+                      v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + bq.y, 0.0f);
+                      v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + bq.z, 0.0f);
+                      v[4 * q + 3] = fmaxf(__uint_as_float(r[4 * q + 3]) + bq.w, 0.0f);
+                    }
+                    if (!real) {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+                    }
+                    *d0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                    *d1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                  };
+                  // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+                  uint32_t ra[16], rb[16];
+                  tc_ld16(taddr, ra);
+#pragma unroll 1
+                  for (int cc = 0; cc < TW_C / 16; cc += 2) {
+                    tc_wait_ld();
+                    tc_ld16(taddr + (cc + 1) * 16, rb);
+                    process(ra, cc);
+                    tc_wait_ld();
+                    if (cc + 2 < TW_C / 16) tc_ld16(taddr + (cc + 2) * 16, ra);
+                    process(rb, cc + 1);
+                  }
+                  if (is_conv1) tc_wait_st();
+                } else {
+                  __nv_bfloat16* dst = a.headfeat + (size_t)board * (TW_HEADC * g.A) + (info & 255);
+#pragma unroll 1
+                  for (int cc = 0; cc < TW_HEADC / 16; ++cc) {
+                    uint32_t r[16];
+                    tc_ld16(taddr + cc * 16, r);
+                    tc_wait_ld();
+                    if (real) {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j)
+                        dst[(size_t)(cc * 16 + j) * g.A] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + __ldg(bias + cc * 16 + j), 0.0f));
+                    }
+                  }
+                }
+              }
+              tc_fence_before();
+              if (!is_head) { fence_proxy_async_smem(); mbar_arrive(act_ready); }
+            }
+          }
+
+          // ---- FC heads for the batch: feature panels (global/L2 -> shared, K-major core matrices, boards = rows)
+          epi_sync();   // every board's head features are written and visible CTA-wide
+          for (int q = 0; q < 2 * fc.n_panels; ++q) {
+            const int h = q / fc.n_panels, p = q % fc.n_panels;
+            if (q > 0) { mbar_wait(acc_full, acc_phase); acc_phase ^= 1; tc_fence_after(); }   // previous panel consumed
+            const int nchunks = panel_stages(p) * 8;
+            const int kbase = p * FC_PANEL_STAGES * 64;
+            const __nv_bfloat16* src0 = a.headfeat + (size_t)bb0 * (TW_HEADC * g.A) + (size_t)h * fc.Kh + kbase;
+            for (int idx = etid; idx < nbb * nchunks; idx += TW_EPI_THREADS) {
+              const int b = idx / nchunks, j = idx - b * nchunks;
+              const bool valid = kbase + j * 8 < fc.Kh;      // K padding up to the stage boundary must be zero
+              cp_async16(act_base + (uint32_t)(j * FC_LBO + b * 16), src0 + (size_t)b * (TW_HEADC * g.A) + (valid ? j * 8 : 0), valid);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(act_ready);
+          }
+          mbar_wait(acc_full, acc_phase); acc_phase ^= 1;
+          tc_fence_after();
+          // D tiles -> scratch: policy logits (+bias), value hidden units relu(.+b1) * w2   (lane = output unit)
+          if (tile0 < fc.Tp + 2) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile0 * FC_N);
+            uint32_t r0[16], r1[16];
+            tc_ld16(taddr, r0);
+            tc_ld16(taddr + 16, r1);
+            tc_wait_ld();
+            const int row = quarter * 32 + lane;
+            if (tile0 < fc.Tp) {
+              const int o = tile0 * 128 + row;
+              if (o < g.A) {
+                const float bo = __ldg(a.fc_policy_b + o);
+#pragma unroll
+                for (int b = 0; b < 16; ++b) { sc_logit[b * 256 + o] = __uint_as_float(r0[b]) + bo; sc_logit[(b + 16) * 256 + o] = __uint_as_float(r1[b]) + bo; }
+              }
+            } else {
+              const int o = (tile0 - fc.Tp) * 128 + row;
+              const float b1 = __ldg(a.fc_value1_b + o), w2 = __ldg(a.fc_value2_w + o);
+#pragma unroll
+              for (int b = 0; b < 16; ++b) {
+                sc_hidden[b * 256 + o] = fmaxf(__uint_as_float(r0[b]) + b1, 0.0f) * w2;
+                sc_hidden[(b + 16) * 256 + o] = fmaxf(__uint_as_float(r1[b]) + b1, 0.0f) * w2;
+              }
+            }
+          }
+          tc_fence_before();
+          epi_sync();
+        }
+
+        // ---- per board: softmax over all A logits (predict, neural_network.py:152), value_fc2 + tanh (:121), tree step
+        for (int b = ew; b < nbb; b += TW_EPI_WARPS) {
+          const long long board = bb0 + b;
+          if (a.use_nn) {
+            const float* lg = sc_logit + b * 256;
+            float mx = -INFINITY;
+            for (int k = lane; k < g.A; k += 32) mx = fmaxf(mx, lg[k]);
+            for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            float sum = 0.0f;
+            for (int k = lane; k < g.A; k += 32) sum += expf(lg[k] - mx);
+            for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            for (int k = lane; k < g.A; k += 32) {
+              a.policy[board * g.A + k] = expf(lg[k] - mx) / sum;
+              if (a.logits) a.logits[board * g.A + k] = lg[k];
+            }
+            float acc = 0.0f;
+            for (int k = lane; k < 256; k += 32) acc += sc_hidden[b * 256 + k];
+            for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) a.value[board] = tanhf(acc + __ldg(a.fc_value2_b));
+            __syncwarp();
+          }
+          if (a.do_tree) tree_step_game<NW>(e, geo, (int)board, lane, nullptr);
+        }
+        if (a.use_nn) {
+          epi_sync();     // scratch consumed, new leaves published
+          for (int i = etid; i < TW_CHUNKS * TW_ROWS; i += TW_EPI_THREADS) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
+          epi_sync();     // zero padding rows restored before the next stem writes its planes
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (a.dbg && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.dbg[129 + 2 * blockIdx.x] = (long long)gt; }
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int fused_batch_boards(const TowerGeo& g) {
+  int per = (FC_N / g.Gb) * g.Gb;
+  return per > 0 ? per : g.Gb;
+}
+
+template <int NW>
+static int launch_fused(NNState& nn, const FusedArgs& fa, const EngineDev& dev, uint32_t rule_flags, int grid, cudaStream_t s) {
+  static bool attr_set[8] = {};
+  if (!attr_set[nn.device & 7]) {
+    YY_CUDA_OK(cudaFuncSetAttribute(fused_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    attr_set[nn.device & 7] = true;
+  }
+  fused_kernel<NW><<<grid, TW_THREADS, SM_TOTAL, s>>>(fa, dev, make_geo<NW>(nn.rows, nn.cols, rule_flags));
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+// Runs `iterations` evaluation (+ tree) steps over boards [0, count) in ONE launch.
+//   dev == nullptr : plain forward (do_tree off); policy/value/logits are the caller's output arrays.
+//   dev != nullptr : whole search over dev->leaf_* / eval_* (slot = game; leaves_per_step must be 1).
+int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const uint64_t* black, const uint64_t* white, int64_t count,
+                 float* policy, float* value, float* logits, int iterations, bool use_nn, cudaStream_t s) {
+  if (use_nn) {
+    if (!nn.attrs_set) return set_error(YY_ERR_STATE, "engine was not created with the NN evaluator");
+    if (!nn.weights) return set_error(YY_ERR_STATE, "no weights loaded (yy_engine_load_weights)");
+  }
+  if (count <= 0 || iterations <= 0) return YY_OK;
+  if (count > nn.max_boards) return set_error(YY_ERR_INVALID, "fused run: %lld boards exceed the head-feature scratch (%d)", (long long)count, nn.max_boards);
+  FusedArgs fa{};
+  fa.g = make_tower_geo(nn.rows, nn.cols, nn.blocks);
+  if (fa.g.Gb > FC_N) fa.g.Gb = FC_N;
+  fa.fc = make_fc_geo(nn.A);
+  if (use_nn) {
+    const WeightLayout wl = weight_layout(nn.rows, nn.cols, nn.blocks);
+    const uint8_t* wimg = static_cast<const uint8_t*>(nn.weights);
+    fa.conv_stream = wimg + wl.conv_stream;
+    fa.conv_bias = reinterpret_cast<const float*>(wimg + wl.conv_bias);
+    fa.fc_stream = wimg + wl.fc_stream;
+    fa.fc_policy_b = reinterpret_cast<const float*>(wimg + wl.fc_policy_b);
+    fa.fc_value1_b = reinterpret_cast<const float*>(wimg + wl.fc_value1_b);
+    fa.fc_value2_w = reinterpret_cast<const float*>(wimg + wl.fc_value2_w);
+    fa.fc_value2_b = reinterpret_cast<const float*>(wimg + wl.fc_value2_b);
+    fa.headfeat = reinterpret_cast<__nv_bfloat16*>(nn.scratch);
+  }
+  fa.black = black; fa.white = white; fa.count = count;
+  fa.policy = policy; fa.value = value; fa.logits = logits;
+  fa.iterations = iterations; fa.do_tree = dev ? 1 : 0; fa.use_nn = use_nn ? 1 : 0;
+  fa.dbg = nn.dbg;
+  fa.batch_boards = fused_batch_boards(fa.g);
+  // equal contiguous runs of boards per CTA (a search keeps its games on the same SM from the first to the last simulation)
+  int sms = nn.num_sms > 0 ? nn.num_sms : 148;
+  long long per = (count + sms - 1) / sms;
+  if (per < fa.g.Gb && use_nn) per = fa.g.Gb;
+  if (per < 1) per = 1;
+  fa.boards_per_cta = (int)per;
+  const int grid = (int)((count + per - 1) / per);
+  EngineDev d{};
+  if (dev) d = *dev;
+  if (nn.profiling) {
+    if (nn.ev_used == nn.ev_cap) { int rc = nn_get_profile(nn, nullptr, nullptr, nullptr); if (rc) return rc; }
+    YY_CUDA_OK(cudaEventRecord(nn.ev[2 * nn.ev_used], s));
+  }
+  int rc = YY_OK;
+  YY_DISPATCH_NW(nn.A, rc = launch_fused<NW>(nn, fa, d, rule_flags, grid, s));
+  if (rc) return rc;
+  if (nn.profiling) {
+    YY_CUDA_OK(cudaEventRecord(nn.ev[2 * nn.ev_used + 1], s));
+    ++nn.ev_used; ++nn.tower_launches; nn.tower_boards += count * iterations;
+  }
+  return YY_OK;
+}
+
+}  // namespace yy

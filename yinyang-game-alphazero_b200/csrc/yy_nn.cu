@@ -27,80 +27,10 @@
 #include "yy_gemm.cuh"
 #include "yy_nn.cuh"
 #include "yy_ptx.cuh"
+#include "yy_tower.cuh"
 
 namespace yy {
 using namespace ptx;
-
-constexpr int TW_C = 128;              // tower width the kernel is specialised for (narrower nets are zero-padded)
-constexpr int TW_CHUNKS = TW_C / 8;    // 16-byte channel chunks per position
-constexpr int TW_HEADC = 64;           // policy 32 + value 32 head-conv channels
-constexpr int TW_INC = 16;             // stem input channels after padding (K = 16 per tap)
-constexpr int TW_MAXT = 4;             // tiles (of 128 positions) per group
-constexpr int TW_PAD = 24;             // zero rows before/after the group's positions (>= m+2)
-constexpr int TW_ROWS = 616;            // activation rows: flat layout needs 512+2*24, row-aligned 24+64*9+10
-constexpr int TW_STAGES = 4;
-constexpr int TW_STAGE_BYTES = 16384;
-constexpr int TW_EPI_WARPS = 16;           // one (tile, TMEM-lane-quarter) pair per warp
-constexpr int TW_THREADS = 64 + 32 * TW_EPI_WARPS;
-constexpr int TW_EPI_THREADS = 32 * TW_EPI_WARPS;
-
-constexpr int SM_ACT = 0;
-constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 157696
-constexpr int SM_POS = SM_RING + TW_STAGES * TW_STAGE_BYTES;          // position tables: padded position + (board, cell)
-constexpr int SM_BAR = SM_POS + 2 * 128 * TW_MAXT * 2;
-constexpr int SM_TMEM = SM_BAR + 8 * (2 * TW_STAGES + 2);
-constexpr int SM_TOTAL = SM_TMEM + 16;
-
-struct TowerGeo {
-  int n, m, A, W, pitch, PB;  // PB = padded positions per board
-  int T, Gb;                  // tiles per group, boards per group
-  int blocks;
-  // Two layouts of a group's positions (both keep a zero column right of and a zero row below every board):
-  //  flat        : M row r of tile t is padded position t*128 + r            (SBO 128 B, any board width)
-  //  row-aligned : (cols == 8) an 8-row MMA group is exactly one board row: M row r of tile t is padded position
-  //                (16t + r/8)*pitch + r%8, SBO = pitch*16 B -- the zero column is skipped, 7 boards per 4 tiles
-  int row_aligned, sbo_bytes, tile_adv, rows_per_board;
-};
-
-struct TowerArgs {
-  TowerGeo g;
-  const uint8_t* conv_stream;  // stage-ordered bf16 weight blocks
-  const float* conv_bias;      // [1 + 2*blocks][128] then head [64]
-  const uint64_t* black; const uint64_t* white;
-  long long count;
-  int boards_per_cta;          // boards are dealt to CTAs in contiguous runs; the last group of a run may be short
-  __nv_bfloat16* headfeat;     // [count][64*A], index c*A + cell (matches .view(-1, 32*n*m), neural_network.py:112,117)
-  long long* dbg;              // optional per-layer clock64 stamps of CTA 0's first group (developer tool), else nullptr
-};
-
-// ---- weight-stream geometry shared by producer and MMA issuer ----
-struct LayerInfo { int n_stages, stage_bytes, nk16, N; long long stream_off; };
-__host__ __device__ inline LayerInfo layer_info(int l, int blocks) {
-  LayerInfo li;
-  const long long stem = 9ll * (2 * 128 * 16);
-  if (l == 0) { li.n_stages = 9; li.stage_bytes = 2 * 128 * 16; li.nk16 = 1; li.N = 128; li.stream_off = 0; }
-  else if (l <= 2 * blocks) { li.n_stages = 18; li.stage_bytes = TW_STAGE_BYTES; li.nk16 = 4; li.N = 128; li.stream_off = stem + (long long)(l - 1) * 18 * TW_STAGE_BYTES; }
-  else { li.n_stages = 2; li.stage_bytes = 8 * TW_HEADC * 16; li.nk16 = 4; li.N = TW_HEADC; li.stream_off = stem + (long long)(2 * blocks) * 18 * TW_STAGE_BYTES; }
-  return li;
-}
-__host__ __device__ inline long long conv_stream_bytes(int blocks) {
-  LayerInfo li = layer_info(2 * blocks + 1, blocks);
-  return li.stream_off + (long long)li.n_stages * li.stage_bytes;
-}
-// stage j of layer l: which 3x3 tap and which first activation chunk it covers
-__device__ __forceinline__ void stage_info(int l, int j, int blocks, int pitch, int& tapshift, int& chunk0) {
-  int tap, slab;
-  if (l == 0) { tap = j; slab = 0; }
-  else if (l <= 2 * blocks) { tap = j >> 1; slab = j & 1; }
-  else { tap = 4; slab = j; }
-  tapshift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
-  chunk0 = slab * 8;
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
 
 __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -141,6 +71,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (a.dbg && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.dbg[128 + 2 * blockIdx.x] = (long long)gt; }
   const uint32_t act_base = smem_u32(smem + SM_ACT);
   const uint32_t ring_base = smem_u32(smem + SM_RING);
   // this CTA's run of boards [run_lo, run_hi); groups of Gb boards, the last one possibly shorter -> fewer tiles
@@ -180,6 +111,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
     constexpr uint64_t kK16DeltaA = (2u * TW_ROWS * 16u) >> 4;   // next K=16 slice: +2 channel chunks
     for (long long b0 = run_lo; b0 < run_hi; b0 += g.Gb) {
       const int T = tiles_for(b0);
+      if (a.dbg && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 100)) a.dbg[512 + (blockIdx.x ? 16 : 0) + (int)((b0 - run_lo) / g.Gb)] = clock64();
       for (int l = 0; l < L; ++l) {
         const LayerInfo li = layer_info(l, g.blocks);
         const bool preloaded = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 0);  // conv2: accumulator holds the skip input
@@ -339,6 +271,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tower_kernel(const TowerArgs a)
   }
   tc_fence_before();
   __syncthreads();
+  if (a.dbg && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.dbg[129 + 2 * blockIdx.x] = (long long)gt; a.dbg[544 + (blockIdx.x & 255)] = clock64(); }
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -369,54 +302,6 @@ __global__ void __launch_bounds__(128) heads_finish_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct WeightLayout {
-  int64_t conv_stream, conv_bias, fc_policy_w, fc_policy_b, fc_value1_w, fc_value1_b, fc_value2_w, fc_value2_b, total;
-  int a_pad;
-};
-static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
-static WeightLayout weight_layout(int rows, int cols, int blocks) {
-  WeightLayout w;
-  const int A = rows * cols;
-  w.a_pad = (A + 15) / 16 * 16;
-  int64_t off = 0;
-  w.conv_stream = off; off = align256(off + conv_stream_bytes(blocks));
-  w.conv_bias = off; off = align256(off + (int64_t)((2 * blocks + 1) * TW_C + TW_HEADC) * 4);
-  w.fc_policy_w = off; off = align256(off + (int64_t)w.a_pad * 32 * A * 2);
-  w.fc_policy_b = off; off = align256(off + (int64_t)w.a_pad * 4);
-  w.fc_value1_w = off; off = align256(off + (int64_t)256 * 32 * A * 2);
-  w.fc_value1_b = off; off = align256(off + 256 * 4);
-  w.fc_value2_w = off; off = align256(off + 256 * 4);
-  w.fc_value2_b = off; off = align256(off + 4);
-  w.total = off;
-  return w;
-}
-
-static bool nn_geometry_ok(int rows, int cols) {
-  return rows >= 1 && cols >= 1 && cols + 2 <= TW_PAD && (rows + 1) * (cols + 1) <= 128 * TW_MAXT && rows * cols <= 256;
-}
-
-static TowerGeo make_tower_geo(int rows, int cols, int blocks) {
-  TowerGeo g;
-  g.n = rows; g.m = cols; g.A = rows * cols; g.W = words_for_cells(g.A); g.pitch = cols + 1; g.PB = (rows + 1) * (cols + 1);
-  g.blocks = blocks;
-  g.row_aligned = 0; g.sbo_bytes = 128; g.tile_adv = 128; g.rows_per_board = rows + 1;
-  if (cols == 8 && rows + 1 <= 16 * TW_MAXT) {   // one board row == one 8-row MMA group
-    g.row_aligned = 1; g.sbo_bytes = g.pitch * 16; g.tile_adv = 16 * g.pitch;
-    g.T = TW_MAXT; g.Gb = (16 * TW_MAXT) / (rows + 1);
-    if (g.Gb > 127) g.Gb = 127;
-    return g;
-  }
-  double best = -1.0; g.T = TW_MAXT; g.Gb = 1;
-  for (int T = 1; T <= TW_MAXT; ++T) {
-    int Gb = (128 * T) / g.PB;
-    if (Gb < 1) continue;
-    if (Gb > 127) Gb = 127;
-    double eff = (double)Gb * g.A / (128.0 * T);
-    if (eff >= best - 1e-12) { best = eff; g.T = T; g.Gb = Gb; }
-  }
-  return g;
-}
-
 int64_t nn_weight_bytes(int rows, int cols, int channels, int blocks) {
   if (!nn_geometry_ok(rows, cols) || channels < 1 || channels > TW_C || blocks < 0)
     return set_error(YY_ERR_INVALID, "network geometry unsupported: %dx%d, %d channels, %d blocks (need cols<=%d, channels<=%d)",
@@ -556,7 +441,7 @@ int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_
 
 // Section offsets of the packed weight image, for the host-side packer:
 // out[0..8] = conv_stream, conv_bias, fc_policy_w, fc_policy_b, fc_value1_w, fc_value1_b, fc_value2_w, fc_value2_b, total;
-// out[9] = padded policy rows (A rounded up to 16).
+// out[9] = padded policy rows (A rounded up to 16); out[10], out[11] = offset / bytes of the stage-ordered FC stream.
 extern "C" int yy_nn_weight_layout(int rows, int cols, int channels, int blocks, int64_t* out) {
   using namespace yy;
   int64_t t = nn_weight_bytes(rows, cols, channels, blocks);
@@ -564,5 +449,6 @@ extern "C" int yy_nn_weight_layout(int rows, int cols, int channels, int blocks,
   WeightLayout w = weight_layout(rows, cols, blocks);
   out[0] = w.conv_stream; out[1] = w.conv_bias; out[2] = w.fc_policy_w; out[3] = w.fc_policy_b; out[4] = w.fc_value1_w;
   out[5] = w.fc_value1_b; out[6] = w.fc_value2_w; out[7] = w.fc_value2_b; out[8] = w.total; out[9] = w.a_pad;
+  out[10] = w.fc_stream; out[11] = w.fc_stream_bytes;
   return YY_OK;
 }

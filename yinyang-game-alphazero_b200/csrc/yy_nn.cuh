@@ -35,4 +35,11 @@ int nn_get_profile(NNState& nn, long long* launches, double* total_ms, long long
 int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_t count, float* policy, float* value,
                float* logits, cudaStream_t stream);
 
+struct EngineDev;
+// Persistent kernel (yy_fused.cu): `iterations` x (network forward on boards [0,count) -> heads -> optional tree step)
+// in ONE launch.  dev == nullptr: plain forward into policy/value/logits.  dev != nullptr: whole search over the
+// engine's leaf batch (slot = game), use_nn = false runs the deterministic-prior evaluator (tree steps only).
+int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const uint64_t* black, const uint64_t* white,
+                 int64_t count, float* policy, float* value, float* logits, int iterations, bool use_nn, cudaStream_t stream);
+
 }  // namespace yy

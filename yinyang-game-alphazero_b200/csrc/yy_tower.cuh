@@ -1,0 +1,158 @@
+// yy_tower.cuh -- geometry, weight-stream layout and shared-memory map of the tcgen05 residual-tower kernels
+// (shared by yy_nn.cu and the persistent search kernel in yy_fused.cu).  Layout rationale: yy_nn.cu header.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "yy_common.cuh"
+#include "yy_ptx.cuh"
+
+namespace yy {
+
+constexpr int TW_C = 128;              // tower width the kernel is specialised for (narrower nets are zero-padded)
+constexpr int TW_CHUNKS = TW_C / 8;    // 16-byte channel chunks per position
+constexpr int TW_HEADC = 64;           // policy 32 + value 32 head-conv channels
+constexpr int TW_INC = 16;             // stem input channels after padding (K = 16 per tap)
+constexpr int TW_MAXT = 4;             // tiles (of 128 positions) per group
+constexpr int TW_PAD = 24;             // zero rows before/after the group's positions (>= m+2)
+constexpr int TW_ROWS = 616;            // activation rows: flat layout needs 512+2*24, row-aligned 24+64*9+10
+constexpr int TW_STAGES = 4;
+constexpr int TW_STAGE_BYTES = 16384;
+constexpr int TW_EPI_WARPS = 16;           // one (tile, TMEM-lane-quarter) pair per warp
+constexpr int TW_THREADS = 64 + 32 * TW_EPI_WARPS;
+constexpr int TW_EPI_THREADS = 32 * TW_EPI_WARPS;
+
+constexpr int SM_ACT = 0;
+constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 157696
+constexpr int SM_POS = SM_RING + TW_STAGES * TW_STAGE_BYTES;          // position tables: padded position + (board, cell)
+constexpr int SM_BAR = SM_POS + 2 * 128 * TW_MAXT * 2;
+constexpr int SM_TMEM = SM_BAR + 8 * (2 * TW_STAGES + 2);
+constexpr int SM_TOTAL = SM_TMEM + 16;
+
+struct TowerGeo {
+  int n, m, A, W, pitch, PB;  // PB = padded positions per board
+  int T, Gb;                  // tiles per group, boards per group
+  int blocks;
+  // Two layouts of a group's positions (both keep a zero column right of and a zero row below every board):
+  //  flat        : M row r of tile t is padded position t*128 + r            (SBO 128 B, any board width)
+  //  row-aligned : (cols == 8) an 8-row MMA group is exactly one board row: M row r of tile t is padded position
+  //                (16t + r/8)*pitch + r%8, SBO = pitch*16 B -- the zero column is skipped, 7 boards per 4 tiles
+  int row_aligned, sbo_bytes, tile_adv, rows_per_board;
+};
+
+struct TowerArgs {
+  TowerGeo g;
+  const uint8_t* conv_stream;  // stage-ordered bf16 weight blocks
+  const float* conv_bias;      // [1 + 2*blocks][128] then head [64]
+  const uint64_t* black; const uint64_t* white;
+  long long count;
+  int boards_per_cta;          // boards are dealt to CTAs in contiguous runs; the last group of a run may be short
+  __nv_bfloat16* headfeat;     // [count][64*A], index c*A + cell (matches .view(-1, 32*n*m), neural_network.py:112,117)
+  long long* dbg;              // optional per-layer clock64 stamps of CTA 0's first group (developer tool), else nullptr
+};
+
+// ---- weight-stream geometry shared by producer and MMA issuer ----
+struct LayerInfo { int n_stages, stage_bytes, nk16, N; long long stream_off; };
+__host__ __device__ inline LayerInfo layer_info(int l, int blocks) {
+  LayerInfo li;
+  const long long stem = 9ll * (2 * 128 * 16);
+  if (l == 0) { li.n_stages = 9; li.stage_bytes = 2 * 128 * 16; li.nk16 = 1; li.N = 128; li.stream_off = 0; }
+  else if (l <= 2 * blocks) { li.n_stages = 18; li.stage_bytes = TW_STAGE_BYTES; li.nk16 = 4; li.N = 128; li.stream_off = stem + (long long)(l - 1) * 18 * TW_STAGE_BYTES; }
+  else { li.n_stages = 2; li.stage_bytes = 8 * TW_HEADC * 16; li.nk16 = 4; li.N = TW_HEADC; li.stream_off = stem + (long long)(2 * blocks) * 18 * TW_STAGE_BYTES; }
+  return li;
+}
+__host__ __device__ inline long long conv_stream_bytes(int blocks) {
+  LayerInfo li = layer_info(2 * blocks + 1, blocks);
+  return li.stream_off + (long long)li.n_stages * li.stage_bytes;
+}
+// stage j of layer l: which 3x3 tap and which first activation chunk it covers
+__device__ __forceinline__ void stage_info(int l, int j, int blocks, int pitch, int& tapshift, int& chunk0) {
+  int tap, slab;
+  if (l == 0) { tap = j; slab = 0; }
+  else if (l <= 2 * blocks) { tap = j >> 1; slab = j & 1; }
+  else { tap = 4; slab = j; }
+  tapshift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
+  chunk0 = slab * 8;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct WeightLayout {
+  int64_t conv_stream, conv_bias, fc_policy_w, fc_policy_b, fc_value1_w, fc_value1_b, fc_value2_w, fc_value2_b, total;
+  int a_pad;
+  int64_t fc_stream, fc_stream_bytes;   // stage-ordered policy FC + value FC1 weights for the persistent kernel
+};
+
+// ---- FC heads inside the persistent kernel (yy_fused.cu): out[o][board] = W[o][:] . feat[board][:] as UMMA with the
+// weights as the M=128 operand (streamed through the same ring as the conv weights) and up to FC_N boards as N.
+constexpr int FC_N = 32;                              // boards per FC batch (UMMA N)
+constexpr int FC_LBO = FC_N * 16 + 16;                // K-chunk stride of the feature panel (+16 B: conflict-free scatter)
+constexpr int FC_PANEL_STAGES = 32;                   // K = 64 per stage -> K = 2048 per panel (135 KB of the act region)
+struct FcGeo {
+  int Kh;        // K per head = 32 * A (flatten order c*A + cell, neural_network.py:112,117)
+  int KS;        // K = 64 stages per (head, M tile)
+  int n_panels;  // feature panels per head
+  int Tp;        // policy M tiles (A <= 256 -> 1 or 2); the value head always has 2 (256 hidden units)
+  int Rp_last;   // rows of the last policy tile, rounded up to 8
+};
+__host__ __device__ inline FcGeo make_fc_geo(int A) {
+  FcGeo f;
+  f.Kh = 32 * A; f.KS = (f.Kh + 63) / 64; f.n_panels = (f.KS + FC_PANEL_STAGES - 1) / FC_PANEL_STAGES;
+  f.Tp = (A + 127) / 128; f.Rp_last = ((A - 128 * (f.Tp - 1)) + 7) / 8 * 8;
+  return f;
+}
+// stream order: head (policy, value) > panel > M tile > stage; a stage block is [8 K-chunks][R rows][8] bf16
+__host__ __device__ inline long long fc_stream_bytes(int A) {
+  const FcGeo f = make_fc_geo(A);
+  return (long long)f.KS * 128 * ((f.Tp - 1) * 128 + f.Rp_last + 256);
+}
+inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+inline WeightLayout weight_layout(int rows, int cols, int blocks) {
+  WeightLayout w;
+  const int A = rows * cols;
+  w.a_pad = (A + 15) / 16 * 16;
+  int64_t off = 0;
+  w.conv_stream = off; off = align256(off + conv_stream_bytes(blocks));
+  w.conv_bias = off; off = align256(off + (int64_t)((2 * blocks + 1) * TW_C + TW_HEADC) * 4);
+  w.fc_policy_w = off; off = align256(off + (int64_t)w.a_pad * 32 * A * 2);
+  w.fc_policy_b = off; off = align256(off + (int64_t)w.a_pad * 4);
+  w.fc_value1_w = off; off = align256(off + (int64_t)256 * 32 * A * 2);
+  w.fc_value1_b = off; off = align256(off + 256 * 4);
+  w.fc_value2_w = off; off = align256(off + 256 * 4);
+  w.fc_value2_b = off; off = align256(off + 4);
+  w.fc_stream = off; w.fc_stream_bytes = fc_stream_bytes(A); off = align256(off + w.fc_stream_bytes);
+  w.total = off;
+  return w;
+}
+
+inline bool nn_geometry_ok(int rows, int cols) {
+  return rows >= 1 && cols >= 1 && cols + 2 <= TW_PAD && (rows + 1) * (cols + 1) <= 128 * TW_MAXT && rows * cols <= 256;
+}
+
+inline TowerGeo make_tower_geo(int rows, int cols, int blocks) {
+  TowerGeo g;
+  g.n = rows; g.m = cols; g.A = rows * cols; g.W = words_for_cells(g.A); g.pitch = cols + 1; g.PB = (rows + 1) * (cols + 1);
+  g.blocks = blocks;
+  g.row_aligned = 0; g.sbo_bytes = 128; g.tile_adv = 128; g.rows_per_board = rows + 1;
+  if (cols == 8 && rows + 1 <= 16 * TW_MAXT) {   // one board row == one 8-row MMA group
+    g.row_aligned = 1; g.sbo_bytes = g.pitch * 16; g.tile_adv = 16 * g.pitch;
+    g.T = TW_MAXT; g.Gb = (16 * TW_MAXT) / (rows + 1);
+    if (g.Gb > 127) g.Gb = 127;
+    return g;
+  }
+  double best = -1.0; g.T = TW_MAXT; g.Gb = 1;
+  for (int T = 1; T <= TW_MAXT; ++T) {
+    int Gb = (128 * T) / g.PB;
+    if (Gb < 1) continue;
+    if (Gb > 127) Gb = 127;
+    double eff = (double)Gb * g.A / (128.0 * T);
+    if (eff >= best - 1e-12) { best = eff; g.T = T; g.Gb = Gb; }
+  }
+  return g;
+}
+
+
+}  // namespace yy

@@ -13,80 +13,14 @@
 // Roofline: HBM (latency-bound pointer chasing in practice).  Algorithmic bytes per simulation:
 // sum over levels of 12*A_l (N,W,P per child read) + 17*A_leaf (edge slots written) + 8 per path edge
 // (N,W read-modify-write) + 2*16*W node state -- ~1.5-4 KB at 8x8.
-#include "yy_engine.cuh"
+#include "yy_tree_dev.cuh"
 #include "yy_nn.cuh"
 
-#include <math.h>
 #include <new>
 
 namespace yy {
 
 constexpr int kTreeBlock = 128;  // 4 games per CTA
-constexpr unsigned kFull = 0xffffffffu;
-
-template <int NW>
-__device__ __forceinline__ int rank_below(const BB<NW>& m, int a) {
-  int r = 0;
-  int wi = a >> 6, bi = a & 63;
-#pragma unroll
-  for (int k = 0; k < NW; ++k) {
-    if (k < wi) r += popc64(m.w[k]);
-    else if (k == wi) r += popc64(m.w[k] & ((1ull << bi) - 1ull));
-  }
-  return r;
-}
-
-__device__ __forceinline__ float terminal_value_f32(int code) {
-  // yin_yang_game.py:101-107: +1 / -1 / 0.0001 (Python scalars, weak-promoted to float32 in Node.update)
-  return code == 1 ? 1.0f : (code == -1 ? -1.0f : (float)0.0001);
-}
-
-// Node.update along a recorded path (mcts.py:406-412): the leaf's own slot gets +v, alternating upwards.
-// `vl_pending`: the path already carries a virtual visit and a virtual loss of 1 (multi-leaf mode) -- the visit
-// stays, the loss is taken back.
-__device__ __forceinline__ void backup_path(const EngineDev& e, const int32_t* path, long long eb, int plen, float v, int lane,
-                                            bool vl_pending) {
-  for (int i = lane; i < plen; i += 32) {
-    long long ei = eb + path[i];
-    float sv = ((plen - 1 - i) & 1) ? -v : v;
-    if (vl_pending) {
-      e.edge_W[ei] = __fadd_rn(__fadd_rn(e.edge_W[ei], 1.0f), sv);
-    } else {
-      e.edge_N[ei] += 1;
-      e.edge_W[ei] = __fadd_rn(e.edge_W[ei], sv);
-    }
-  }
-}
-
-// Writes the state of node `id`, evaluates the rules for it (terminal code + legal mask of the side to
-// move) and publishes it in leaf slot `slot` of the evaluation batch.  All lanes hold identical arguments.
-template <int NW>
-__device__ __forceinline__ void publish_leaf(const EngineDev& e, const Geo<NW>& g, int gi, int lane, int slot, int id,
-                                             const BB<NW>& black, const BB<NW>& white, int player, int plen) {
-  BB<NW> mask = legal_for(g, black, white, player);
-  int code = ended_code_with_mask(g, black, white, player, mask);
-  if (lane == 0) {
-    long long ni = (long long)gi * e.max_nodes + id;
-    store_bb<NW>(e.node_black, ni, e.W, black);
-    store_bb<NW>(e.node_white, ni, e.W, white);
-    e.node_player[ni] = (int8_t)player;
-    e.node_flags[ni] = 0;
-    e.node_n_edges[ni] = 0;
-    e.node_edge_base[ni] = 0;
-    store_bb<NW>(e.leaf_black, slot, e.W, black);
-    store_bb<NW>(e.leaf_white, slot, e.W, white);
-    store_bb<NW>(e.leaf_mask, slot, e.W, mask);
-    e.leaf_code[slot] = (int8_t)code;
-    e.leaf_node[slot] = id;
-    e.leaf_path_len[slot] = plen;
-    e.leaf_active[slot] = 1;
-  }
-  if (e.evaluator == YY_EVAL_STUB) {  // deterministic-prior mode: evaluator fused into the tree kernel
-    uint64_t key = stub_key(g, black, white);
-    for (int a = lane; a < e.A; a += 32) e.eval_prior[(long long)slot * e.A + a] = stub_prior(key, a);
-    if (lane == 0) e.eval_value[slot] = stub_value(key);
-  }
-}
 
 // MCTS.search prologue (mcts.py:288-292): fresh tree per game, root = node 0, pending leaf = root (slot g*K).
 template <int NW>
@@ -103,153 +37,14 @@ __global__ void __launch_bounds__(kTreeBlock) tree_root_kernel(EngineDev e, Geo<
   if (gi == 0 && lane == 0) { e.active_count[0] = e.n_games; e.active_count[1] = 0; }
 }
 
-// Node.expand (mcts.py:50-91) of the node in `slot` with the evaluator's output + backup of its value.
-template <int NW>
-__device__ __forceinline__ void expand_and_backup(const EngineDev& e, const Geo<NW>& g, int gi, int lane, int slot, long long nb,
-                                                  long long eb, bool multi) {
-  const int leaf = e.leaf_node[slot];
-  const int code = e.leaf_code[slot];
-  const float v = e.eval_value[slot];
-  uint8_t flags = NODE_EXPANDED;
-  float nodeval = 0.0f;
-  if (code != 0) {                       // terminal branch (mcts.py:63-68)
-    flags |= NODE_TERMINAL; nodeval = terminal_value_f32(code);
-  } else {
-    BB<NW> mask = load_bb<NW>(e.leaf_mask, slot, e.W);
-    int cnt = popcount(mask);
-    int base = e.g_n_edges[gi];
-    __syncwarp();
-    if (cnt > 0 && base + cnt > e.edges_cap) { if (lane == 0) atomicExch(&e.stats->overflow, 1); cnt = 0; }
-    if (cnt == 0) {                      // no legal move, not terminal: child-less node, re-evaluated on every
-      flags |= NODE_NOCHILD; nodeval = v;  // visit by the reference (is_expanded() stays False) -> same value
-    } else {
-      const bool noisy = (leaf == 0) && e.noise != nullptr && e.noise_mask != nullptr && e.noise_mask[gi] != 0;
-      for (int a = lane; a < e.A; a += 32) {
-        if (!test(mask, a)) continue;
-        int r = rank_below(mask, a);     // children are created in ascending action order (mcts.py:75-89)
-        float p = e.eval_prior[(long long)slot * e.A + a];
-        if (noisy) {                     // mcts.py:309-311: f32( f64(f32(f32(1-eps)*p)) + eps*noise_i )
-          float keep = __fmul_rn(e.keep_f32, p);
-          p = (float)__dadd_rn((double)keep, __dmul_rn(e.eps, e.noise[(long long)gi * e.A + r]));
-        }
-        long long ei = eb + base + r;
-        e.edge_N[ei] = 0; e.edge_W[ei] = 0.0f; e.edge_P[ei] = p; e.edge_child[ei] = -1;
-        e.edge_action[ei] = (uint8_t)a;
-      }
-      __syncwarp();
-      if (lane == 0) { e.node_edge_base[nb + leaf] = base; e.node_n_edges[nb + leaf] = (int16_t)cnt; e.g_n_edges[gi] = base + cnt; }
-    }
-  }
-  if (lane == 0) { e.node_flags[nb + leaf] = flags; e.node_value[nb + leaf] = nodeval; e.leaf_active[slot] = 0; }
-  // first visit always backs up the evaluator's value (mcts.py:394)
-  backup_path(e, e.leaf_path + (long long)slot * e.max_depth, eb, e.leaf_path_len[slot], v, lane, multi && leaf != 0);
-  __syncwarp();
-}
-
-// One lock-step of every tree: (1) expand the pending leaves with the evaluator's output and back their values
-// up (mcts.py:394-412); (2) run simulations from the root until K of them need an evaluation (selection,
-// mcts.py:360-362; revisited terminal leaves complete on the spot, :365-367) and publish those leaves.
-//   K == 1 : deterministic mode -- exactly the reference's sequential search per game.
-//   K  > 1 : throughput mode -- each in-flight simulation leaves a virtual visit and a virtual loss on its path so
-//            that the next descent of the same step diverges; a descent that runs into an in-flight node stops.
+// One lock-step of every tree (see tree_step_game, yy_tree_dev.cuh); one warp per game.
 template <int NW>
 __global__ void __launch_bounds__(kTreeBlock) tree_step_kernel(EngineDev e, Geo<NW> g, int parity) {
   int gi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (gi >= e.n_games) return;
   // pending-leaf counter is double buffered: this step counts into [parity] and clears the other one for the next step
   if (gi == 0 && lane == 0) e.active_count[parity ^ 1] = 0;
-  const long long nb = (long long)gi * e.max_nodes;
-  const long long eb = (long long)gi * e.edges_cap;
-  const bool multi = e.K > 1;
-  int sims_done = e.g_sims_done[gi];
-  int sims_here = 0, evals_here = 0, deepest = 0;
-
-  // ---------------------------------------------------------------- (1) expand + backup
-  const int np_in = e.g_npending[gi];
-  for (int k = 0; k < np_in; ++k) {
-    const int slot = gi * e.K + k;
-    const bool is_root = e.leaf_node[slot] == 0;
-    expand_and_backup<NW>(e, g, gi, lane, slot, nb, eb, multi);
-    if (!is_root) { ++sims_done; ++sims_here; }
-  }
-
-  // ---------------------------------------------------------------- (2) select
-  int np = 0;
-  bool blocked = false;
-  while (sims_done + np < e.n_sims && np < e.K && !blocked) {
-    const int slot = gi * e.K + np;
-    int32_t* path = e.leaf_path + (long long)slot * e.max_depth;
-    int node = 0, depth = 0;
-    for (;;) {
-      const uint8_t fl = e.node_flags[nb + node];
-      if (!(fl & NODE_EXPANDED)) { blocked = true; break; }  // in-flight node of this step (K > 1 only): give up
-      if (fl & (NODE_TERMINAL | NODE_NOCHILD)) {   // revisited terminal (mcts.py:365-367) / child-less node
-        __syncwarp();                              // path[] written by lane 0 above
-        backup_path(e, path, eb, depth, e.node_value[nb + node], lane, false);
-        ++sims_done; ++sims_here;
-        __syncwarp();
-        break;
-      }
-      const int base = e.node_edge_base[nb + node], cnt = e.node_n_edges[nb + node];
-      // Node.select_child (mcts.py:97-145)
-      int sum = 0;
-      for (int k = lane; k < cnt; k += 32) sum += e.edge_N[eb + base + k];
-#pragma unroll
-      for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(kFull, sum, off);
-      const float sq = (float)sqrt((double)sum);
-      float best = -INFINITY; int besti = 0x7fffffff;
-      for (int k = lane; k < cnt; k += 32) {
-        const long long ei = eb + base + k;
-        const int n = e.edge_N[ei];
-        const float u = __fdiv_rn(__fmul_rn(__fmul_rn(e.cpuct, e.edge_P[ei]), sq), (float)(1 + n));
-        const float q = n > 0 ? __fdiv_rn(e.edge_W[ei], (float)n) : 0.0f;
-        const float ucb = __fadd_rn(q, u);
-        if (ucb > best) { best = ucb; besti = k; }
-      }
-#pragma unroll
-      for (int off = 16; off; off >>= 1) {
-        float ov = __shfl_xor_sync(kFull, best, off); int oi = __shfl_xor_sync(kFull, besti, off);
-        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
-      }
-      if (besti == 0x7fffffff) besti = 0;
-      const int eoff = base + besti;
-      if (lane == 0) path[depth] = eoff;
-      ++depth;
-      const int child = e.edge_child[eb + eoff];
-      if (child < 0) {                      // unexpanded child: getNextState on the parent's state (mcts.py:385-391)
-        BB<NW> b = load_bb<NW>(e.node_black, nb + node, e.W), w = load_bb<NW>(e.node_white, nb + node, e.W);
-        const int pp = e.node_player[nb + node];
-        const int a = e.edge_action[eb + eoff];
-        if (pp == 1) setbit(b, a); else setbit(w, a);   // the slot exists only for a legal action
-        const int id = e.g_n_nodes[gi];
-        __syncwarp();
-        if (lane == 0) { e.g_n_nodes[gi] = id + 1; e.edge_child[eb + eoff] = id; }
-        publish_leaf<NW>(e, g, gi, lane, slot, id, b, w, -pp, depth);
-        if (multi) {                        // virtual visit + virtual loss along the in-flight path
-          __syncwarp();
-          for (int i = lane; i < depth; i += 32) {
-            long long ei = eb + path[i];
-            e.edge_N[ei] += 1;
-            e.edge_W[ei] = __fadd_rn(e.edge_W[ei], -1.0f);
-          }
-        }
-        if (depth > deepest) deepest = depth;
-        ++np; ++evals_here;
-        __syncwarp();
-        break;
-      }
-      node = child;
-    }
-  }
-  __syncwarp();
-  if (lane == 0) {
-    e.g_sims_done[gi] = sims_done;
-    e.g_npending[gi] = np;
-    if (np) atomicAdd(e.active_count + parity, np);
-    if (sims_here) atomicAdd(&e.stats->sims, (unsigned long long)sims_here);
-    if (evals_here) atomicAdd(&e.stats->evals, (unsigned long long)evals_here);
-    if (deepest > e.stats->max_depth) atomicMax(&e.stats->max_depth, deepest);
-  }
+  tree_step_game<NW>(e, g, gi, lane, e.active_count + parity);
 }
 
 // root.get_children_visit_counts (mcts.py:168-181) + child value sums
@@ -501,17 +296,33 @@ int launch_step(yy_engine* e, cudaStream_t s) {
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
+// network forward: the persistent kernel with one iteration and no tree step, or the per-layer-group legacy kernels
+int engine_forward(yy_engine* e, const uint64_t* black, const uint64_t* white, int64_t count, float* policy, float* value,
+                   float* logits, cudaStream_t s) {
+  if (e->cfg.mode_flags & YY_MODE_STEP_KERNELS) return nn_forward(e->nn, black, white, count, policy, value, logits, s);
+  for (int64_t done = 0; done < count; done += e->nn.max_boards) {
+    const int64_t n = (count - done) < e->nn.max_boards ? (count - done) : e->nn.max_boards;
+    int rc = nn_fused_run(e->nn, nullptr, e->cfg.rule_flags, black + done * e->dev.W, white + done * e->dev.W, n, policy + done * e->dev.A,
+                          value + done, logits ? logits + done * e->dev.A : nullptr, 1, true, s);
+    if (rc) return rc;
+  }
+  return YY_OK;
+}
 // evaluator on the pending leaf batch (STUB is fused into the tree kernels)
 int run_evaluator(yy_engine* e, cudaStream_t s) {
   if (e->cfg.evaluator == YY_EVAL_STUB) return YY_OK;
   if (e->cfg.evaluator == YY_EVAL_NN)
-    return nn_forward(e->nn, e->dev.leaf_black, e->dev.leaf_white, e->dev.n_slots, e->dev.eval_prior, e->dev.eval_value,
-                      nullptr, s);
+    return engine_forward(e, e->dev.leaf_black, e->dev.leaf_white, e->dev.n_slots, e->dev.eval_prior, e->dev.eval_value, nullptr, s);
   return set_error(YY_ERR_STATE, "external evaluator: use yy_search_begin / yy_search_advance");
 }
 // full search over the roots already stored in dev.root_* (noise pointers already set in dev)
 int search_core(yy_engine* e, cudaStream_t s) {
   int rc = launch_root(e, s); if (rc) return rc;
+  if (e->cfg.leaves_per_step <= 1 && !(e->cfg.mode_flags & YY_MODE_STEP_KERNELS) && e->cfg.evaluator != YY_EVAL_EXTERNAL) {
+    // the whole search in ONE persistent kernel: every CTA owns a run of games from the first to the last simulation
+    return nn_fused_run(e->nn, &e->dev, e->cfg.rule_flags, e->dev.leaf_black, e->dev.leaf_white, e->dev.n_slots, e->dev.eval_prior,
+                        e->dev.eval_value, nullptr, e->cfg.n_sims + 1, e->cfg.evaluator == YY_EVAL_NN, s);
+  }
   if (e->cfg.leaves_per_step <= 1) {      // deterministic mode: exactly n_sims + 1 lock-steps, no host synchronisation
     for (int i = 0; i <= e->cfg.n_sims; ++i) {
       rc = run_evaluator(e, s); if (rc) return rc;
@@ -658,7 +469,7 @@ int yy_evaluate(yy_engine* e, const uint64_t* black, const uint64_t* white, int6
   if (!e || !black || !white || !out_policy || !out_value) return set_error(YY_ERR_INVALID, "null argument");
   if (count <= 0) return YY_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (e->cfg.evaluator == YY_EVAL_NN) return nn_forward(e->nn, black, white, count, out_policy, out_value, out_logits, s);
+  if (e->cfg.evaluator == YY_EVAL_NN) return engine_forward(e, black, white, count, out_policy, out_value, out_logits, s);
   if (e->cfg.evaluator == YY_EVAL_STUB) {
     YY_DISPATCH_NW(e->dev.A, stub_eval_kernel<NW><<<thread_grid((int)count, 128), 128, 0, s>>>(
         make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags), e->dev.W, black, white, count, out_policy, out_value));

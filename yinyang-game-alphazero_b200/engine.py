@@ -20,6 +20,7 @@ from . import _lib, bitboard, weights as _weights
 RULE_ROWCOL = 1
 EVAL_STUB, EVAL_NN, EVAL_EXTERNAL = 0, 1, 2
 MODE_SEARCH_AS_BLACK = 1
+MODE_STEP_KERNELS = 2
 RESULT_DRAW_CODE = 2
 DRAW_VALUE = 0.0001  # yin_yang_game.py:107
 
@@ -173,7 +174,7 @@ class Engine:
     def __init__(self, rows=8, cols=8, n_games=1, n_sims=800, evaluator="stub", cpuct=1.0, rule_flags=0,
                  search_as_black=True, edges_per_game=0, dirichlet_alpha=0.3, dirichlet_epsilon=0.25,
                  temperature_threshold=10, seed=0, replay_capacity=0, state_dict=None, nn_channels=128, nn_blocks=10,
-                 device=None, leaves_per_step=1):
+                 device=None, leaves_per_step=1, step_kernels=False):
         _require_cuda()
         self.L = _lib.lib()
         self.rows, self.cols, self.A, self.W = rows, cols, rows * cols, bitboard.words_for(rows, cols)
@@ -192,7 +193,7 @@ class Engine:
         if replay_capacity <= 0:
             replay_capacity = max(1, n_games * (self.A + 8))
         self.cfg = _lib.EngineConfig(rows=rows, cols=cols, n_games=n_games, n_sims=n_sims, rule_flags=rule_flags,
-                                     mode_flags=MODE_SEARCH_AS_BLACK if search_as_black else 0, evaluator=ev,
+                                     mode_flags=(MODE_SEARCH_AS_BLACK if search_as_black else 0) | (MODE_STEP_KERNELS if step_kernels else 0), evaluator=ev,
                                      edges_per_game=edges_per_game, temperature_threshold=temperature_threshold,
                                      replay_capacity=replay_capacity, nn_channels=nn_channels, nn_blocks=nn_blocks,
                                      device=self.device, leaves_per_step=self.leaves_per_step, cpuct=cpuct, dirichlet_alpha=dirichlet_alpha,

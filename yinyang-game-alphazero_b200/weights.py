@@ -56,6 +56,30 @@ def _stage_blocks(w2d: np.ndarray, slab: int) -> np.ndarray:
     return np.ascontiguousarray(bits.transpose(1, 2, 0, 3)).reshape(-1)  # [stage][kc][oc][j]
 
 
+FC_PANEL_STAGES = 32
+
+
+def fc_stream_blocks(wp: np.ndarray, wv: np.ndarray, A: int) -> np.ndarray:
+    """policy_fc [A][32A] and value_fc1 [256][32A] -> the FC weight stream of the persistent kernel
+    (csrc/yy_tower.cuh make_fc_geo / csrc/yy_fused.cu): order head > K panel (32 stages of K = 64) > M tile (128
+    output units; the last policy tile is rounded up to 8 rows) > stage; a stage block is [8][rows][8] bf16 bits."""
+    kh = 32 * A
+    ks = (kh + 63) // 64
+    n_panels = (ks + FC_PANEL_STAGES - 1) // FC_PANEL_STAGES
+    out = []
+    for w in (wp, wv):
+        rows_total = w.shape[0]
+        tiles = (rows_total + 127) // 128
+        wk = np.zeros((tiles * 128, ks * 64), dtype=np.float32)
+        wk[:rows_total, :kh] = w
+        for p in range(n_panels):
+            s0, s1 = p * FC_PANEL_STAGES, min(ks, (p + 1) * FC_PANEL_STAGES)
+            for t in range(tiles):
+                r = 128 if t < tiles - 1 or rows_total % 128 == 0 else (rows_total - 128 * t + 7) // 8 * 8
+                out.append(_stage_blocks(wk[t * 128: t * 128 + r, s0 * 64: s1 * 64], 64))
+    return np.concatenate(out)
+
+
 def infer_arch(sd):
     channels = int(_np(sd["conv1.weight"]).shape[0])
     blocks = 0
@@ -65,10 +89,10 @@ def infer_arch(sd):
 
 
 def layout(rows: int, cols: int, channels: int, blocks: int):
-    out = (ctypes.c_int64 * 10)()
+    out = (ctypes.c_int64 * 12)()
     _lib.check(_lib.lib().yy_nn_weight_layout(rows, cols, channels, blocks, out))
     names = ["conv_stream", "conv_bias", "fc_policy_w", "fc_policy_b", "fc_value1_w", "fc_value1_b",
-             "fc_value2_w", "fc_value2_b", "total", "a_pad"]
+             "fc_value2_w", "fc_value2_b", "total", "a_pad", "fc_stream", "fc_stream_bytes"]
     return dict(zip(names, [int(v) for v in out]))
 
 
@@ -131,6 +155,9 @@ def pack_state_dict(state_dict, rows: int, cols: int) -> np.ndarray:
     put(lay["fc_value1_b"], _np(sd["value_fc1.bias"]).astype(np.float32))
     put(lay["fc_value2_w"], _np(sd["value_fc2.weight"]).astype(np.float32).reshape(-1))
     put(lay["fc_value2_b"], _np(sd["value_fc2.bias"]).astype(np.float32).reshape(-1))
+    fcs = fc_stream_blocks(_np(sd["policy_fc.weight"]).astype(np.float32), _np(sd["value_fc1.weight"]).astype(np.float32), A)
+    assert fcs.size * 2 == lay["fc_stream_bytes"], (fcs.size * 2, lay)
+    put(lay["fc_stream"], fcs)
     return img
 
 
