@@ -234,17 +234,19 @@ def run_b200(args):
     if rank == 0:
         tower_s = prof["ms"] * 1e-3 / max(1, prof["launches"])
         boards_per_launch = prof["boards"] / max(1, prof["launches"])
-        achieved = FLOPS_TOWER_PER_BOARD * boards_per_launch / tower_s / 1e12 if prof["launches"] else None
+        # the persistent search kernel runs tower + FC heads + tree steps of every simulation: one launch per move step
+        achieved = FLOPS_PER_LEAF * boards_per_launch / tower_s / 1e12 if prof["launches"] else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "tower_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roof = {"bound": "tensor", "kernel": "tower_kernel", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
+        roof = {"bound": "tensor", "kernel": "fused_kernel (persistent search: tower + FC heads + tree step, yy_fused.cu)", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_tflops_sustained"]) if achieved else None, "traffic": traffic,
                 "peak_source": f"bf16_tflops_sustained of {peaks['source']} (kernel timed inside a long step)",
                 "launches_timed": prof["launches"], "avg_launch_ms": tower_s * 1e3,
                 "share_of_step": prof["ms"] / ms if ms else None,
-                "algorithmic_flops_per_launch": FLOPS_TOWER_PER_BOARD * boards_per_launch}
+                "algorithmic_flops_per_launch": FLOPS_PER_LEAF * boards_per_launch,
+                "leaf_evaluations_per_launch": boards_per_launch}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             workers = max(1, min(cpu_cores(), int(os.environ.get("YY_CPU_WORKERS", 64))))

@@ -37,7 +37,7 @@ struct EngineDev {
   uint64_t* node_black; uint64_t* node_white;
   int32_t* node_edge_base; int16_t* node_n_edges; int8_t* node_player; uint8_t* node_flags; float* node_value;
   // edges
-  int32_t* edge_N; float* edge_W; float* edge_P; int32_t* edge_child; uint8_t* edge_action;
+  int32_t* edge_N; float* edge_W; float* edge_P; uint64_t* edge_cmeta; uint8_t* edge_action;
   // per game search state
   int32_t* g_n_nodes; int32_t* g_n_edges; int32_t* g_sims_done; int32_t* g_npending;
   // pending leaf batch (evaluator input), slot = game*K + k: node id, recorded path, state, rules result

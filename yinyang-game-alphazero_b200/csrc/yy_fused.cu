@@ -234,6 +234,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     uint8_t* act = smem + SM_ACT;
     float* sc_logit = reinterpret_cast<float*>(act);                 // [FC_N][256] heads scratch (act region is free then)
     float* sc_hidden = reinterpret_cast<float*>(act) + FC_N * 256;   // [FC_N][256] relu(fc1) * w2
+    long long ph_t = clock64(), ph_acc[5] = {0, 0, 0, 0, 0};             // developer stamps: tower / FC / heads+tree / barrier / zero
+    auto phase = [&](int k) { if (a.dbg) { const long long now = clock64(); ph_acc[k] += now - ph_t; ph_t = now; } };
     for (int iter = 0; iter < a.iterations; ++iter) {
       for (long long bb0 = run_lo; bb0 < run_hi; bb0 += a.batch_boards) {
         const long long lim = batch_end(bb0);
@@ -350,6 +352,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
 
           // ---- FC heads for the batch: feature panels (global/L2 -> shared, K-major core matrices, boards = rows)
           epi_sync();   // every board's head features are written and visible CTA-wide
+          phase(0);
           for (int q = 0; q < 2 * fc.n_panels; ++q) {
             const int h = q / fc.n_panels, p = q % fc.n_panels;
             if (q > 0) { mbar_wait(acc_full, acc_phase); acc_phase ^= 1; tc_fence_after(); }   // previous panel consumed
@@ -396,6 +399,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           }
           tc_fence_before();
           epi_sync();
+          phase(1);
         }
 
         // ---- per board: softmax over all A logits (predict, neural_network.py:152), value_fc2 + tanh (:121), tree step
@@ -421,13 +425,18 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           }
           if (a.do_tree) tree_step_game<NW>(e, geo, (int)board, lane, nullptr);
         }
+        phase(2);
         if (a.use_nn) {
           epi_sync();     // scratch consumed, new leaves published
+          phase(3);
           for (int i = etid; i < TW_CHUNKS * TW_ROWS; i += TW_EPI_THREADS) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
           epi_sync();     // zero padding rows restored before the next stem writes its planes
+          phase(4);
         }
       }
     }
+    if (a.dbg && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 100))
+      for (int k = 0; k < 5; ++k) a.dbg[600 + (blockIdx.x ? 100 : 0) + ew * 5 + k] = ph_acc[k];
   }
   tc_fence_before();
   __syncthreads();

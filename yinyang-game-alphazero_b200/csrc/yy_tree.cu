@@ -219,6 +219,7 @@ struct Carver {
 static int normalise_cfg(yy_engine_config& c) {
   if (!board_supported(c.rows, c.cols)) return set_error(YY_ERR_INVALID, "unsupported board %dx%d", c.rows, c.cols);
   if (c.n_games < 1 || c.n_sims < 0) return set_error(YY_ERR_INVALID, "n_games >= 1 and n_sims >= 0 required");
+  if (c.n_sims > 65000) return set_error(YY_ERR_INVALID, "n_sims must be <= 65000 (16-bit node ids in the edge summaries)");
   int A = c.rows * c.cols;
   if (c.edges_per_game <= 0) c.edges_per_game = (c.n_sims + 1) * A;
   if (c.cpuct <= 0.0f) c.cpuct = 1.0f;
@@ -241,7 +242,7 @@ static void carve(const yy_engine_config& c, Carver& k, EngineDev& d) {
   d.node_edge_base = k.take<int32_t>(G * MN); d.node_n_edges = k.take<int16_t>(G * MN);
   d.node_player = k.take<int8_t>(G * MN); d.node_flags = k.take<uint8_t>(G * MN); d.node_value = k.take<float>(G * MN);
   d.edge_N = k.take<int32_t>(G * EC); d.edge_W = k.take<float>(G * EC); d.edge_P = k.take<float>(G * EC);
-  d.edge_child = k.take<int32_t>(G * EC); d.edge_action = k.take<uint8_t>(G * EC);
+  d.edge_cmeta = k.take<uint64_t>(G * EC); d.edge_action = k.take<uint8_t>(G * EC);
   d.g_n_nodes = k.take<int32_t>(G); d.g_n_edges = k.take<int32_t>(G); d.g_sims_done = k.take<int32_t>(G);
   d.K = c.leaves_per_step; d.n_slots = c.n_games * c.leaves_per_step;
   const size_t S = (size_t)d.n_slots;

@@ -24,6 +24,18 @@ __device__ __forceinline__ int rank_below(const BB<NW>& m, int a) {
   return r;
 }
 
+// Summary of a child node cached in its parent's edge slot, so that a descent needs ONE dependent memory round trip
+// per level (the children's N/W/P and these summaries arrive together):
+//   bits [0,32) first edge slot of the child, [32,48) child node id + 1 (0 = not created yet),
+//   [48,57) number of children, [57,60) NODE_* flags.
+__device__ __forceinline__ uint64_t cmeta_pack(int base, int id, int cnt, int flags) {
+  return (uint64_t)(uint32_t)base | ((uint64_t)(uint32_t)(id + 1) << 32) | ((uint64_t)(uint32_t)cnt << 48) | ((uint64_t)(uint32_t)flags << 57);
+}
+__device__ __forceinline__ int cmeta_base(uint64_t m) { return (int)(uint32_t)m; }
+__device__ __forceinline__ int cmeta_child(uint64_t m) { return (int)((m >> 32) & 0xffffu) - 1; }
+__device__ __forceinline__ int cmeta_cnt(uint64_t m) { return (int)((m >> 48) & 0x1ffu); }
+__device__ __forceinline__ int cmeta_flags(uint64_t m) { return (int)((m >> 57) & 7u); }
+
 __device__ __forceinline__ float terminal_value_f32(int code) {
   // yin_yang_game.py:101-107: +1 / -1 / 0.0001 (Python scalars, weak-promoted to float32 in Node.update)
   return code == 1 ? 1.0f : (code == -1 ? -1.0f : (float)0.0001);
@@ -85,6 +97,7 @@ __device__ __forceinline__ void expand_and_backup(const EngineDev& e, const Geo<
   const float v = e.eval_value[slot];
   uint8_t flags = NODE_EXPANDED;
   float nodeval = 0.0f;
+  int sum_base = 0, sum_cnt = 0;         // what the parent's edge slot will cache about this node
   if (code != 0) {                       // terminal branch (mcts.py:63-68)
     flags |= NODE_TERMINAL; nodeval = terminal_value_f32(code);
   } else {
@@ -106,16 +119,22 @@ __device__ __forceinline__ void expand_and_backup(const EngineDev& e, const Geo<
           p = (float)__dadd_rn((double)keep, __dmul_rn(e.eps, e.noise[(long long)gi * e.A + r]));
         }
         long long ei = eb + base + r;
-        e.edge_N[ei] = 0; e.edge_W[ei] = 0.0f; e.edge_P[ei] = p; e.edge_child[ei] = -1;
+        e.edge_N[ei] = 0; e.edge_W[ei] = 0.0f; e.edge_P[ei] = p; e.edge_cmeta[ei] = 0ull;
         e.edge_action[ei] = (uint8_t)a;
       }
       __syncwarp();
       if (lane == 0) { e.node_edge_base[nb + leaf] = base; e.node_n_edges[nb + leaf] = (int16_t)cnt; e.g_n_edges[gi] = base + cnt; }
+      sum_base = base; sum_cnt = cnt;
     }
   }
-  if (lane == 0) { e.node_flags[nb + leaf] = flags; e.node_value[nb + leaf] = nodeval; e.leaf_active[slot] = 0; }
+  const int plen = e.leaf_path_len[slot];
+  const int32_t* path = e.leaf_path + (long long)slot * e.max_depth;
+  if (lane == 0) {
+    e.node_flags[nb + leaf] = flags; e.node_value[nb + leaf] = nodeval; e.leaf_active[slot] = 0;
+    if (plen > 0) e.edge_cmeta[eb + path[plen - 1]] = cmeta_pack(sum_base, leaf, sum_cnt, flags);
+  }
   // first visit always backs up the evaluator's value (mcts.py:394)
-  backup_path(e, e.leaf_path + (long long)slot * e.max_depth, eb, e.leaf_path_len[slot], v, lane, multi && leaf != 0);
+  backup_path(e, path, eb, plen, v, lane, multi && leaf != 0);
   __syncwarp();
 }
 
@@ -150,8 +169,9 @@ __device__ __forceinline__ void tree_step_game(const EngineDev& e, const Geo<NW>
     const int slot = gi * e.K + np;
     int32_t* path = e.leaf_path + (long long)slot * e.max_depth;
     int node = 0, depth = 0;
+    // root summary from the node arrays; every deeper level gets it from the parent's edge slot (cmeta)
+    int fl = e.node_flags[nb], base = e.node_edge_base[nb], cnt = e.node_n_edges[nb];
     for (;;) {
-      const uint8_t fl = e.node_flags[nb + node];
       if (!(fl & NODE_EXPANDED)) { blocked = true; break; }  // in-flight node of this step (K > 1 only): give up
       if (fl & (NODE_TERMINAL | NODE_NOCHILD)) {   // revisited terminal (mcts.py:365-367) / child-less node
         __syncwarp();                              // path[] written by lane 0 above
@@ -160,22 +180,26 @@ __device__ __forceinline__ void tree_step_game(const EngineDev& e, const Geo<NW>
         __syncwarp();
         break;
       }
-      const int base = e.node_edge_base[nb + node], cnt = e.node_n_edges[nb + node];
-      // Node.select_child (mcts.py:97-145)
-      int sum = 0;
-      for (int k = lane; k < cnt; k += 32) sum += e.edge_N[eb + base + k];
+      // Node.select_child (mcts.py:97-145).  The first 64 children live in registers (two per lane): one round trip.
+      const long long e0 = eb + base;
+      int n0 = 0, n1 = 0; float w0 = 0.0f, w1 = 0.0f, p0 = 0.0f, p1 = 0.0f; uint64_t m0 = 0ull, m1 = 0ull;
+      if (lane < cnt) { n0 = e.edge_N[e0 + lane]; w0 = e.edge_W[e0 + lane]; p0 = e.edge_P[e0 + lane]; m0 = e.edge_cmeta[e0 + lane]; }
+      if (lane + 32 < cnt) { n1 = e.edge_N[e0 + lane + 32]; w1 = e.edge_W[e0 + lane + 32]; p1 = e.edge_P[e0 + lane + 32]; m1 = e.edge_cmeta[e0 + lane + 32]; }
+      int sum = n0 + n1;
+      for (int k = lane + 64; k < cnt; k += 32) sum += e.edge_N[e0 + k];
 #pragma unroll
       for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(kFull, sum, off);
       const float sq = (float)sqrt((double)sum);
       float best = -INFINITY; int besti = 0x7fffffff;
-      for (int k = lane; k < cnt; k += 32) {
-        const long long ei = eb + base + k;
-        const int n = e.edge_N[ei];
-        const float u = __fdiv_rn(__fmul_rn(__fmul_rn(e.cpuct, e.edge_P[ei]), sq), (float)(1 + n));
-        const float q = n > 0 ? __fdiv_rn(e.edge_W[ei], (float)n) : 0.0f;
+      auto consider = [&](int k, int n, float w, float p) {
+        const float u = __fdiv_rn(__fmul_rn(__fmul_rn(e.cpuct, p), sq), (float)(1 + n));
+        const float q = n > 0 ? __fdiv_rn(w, (float)n) : 0.0f;
         const float ucb = __fadd_rn(q, u);
         if (ucb > best) { best = ucb; besti = k; }
-      }
+      };
+      if (lane < cnt) consider(lane, n0, w0, p0);
+      if (lane + 32 < cnt) consider(lane + 32, n1, w1, p1);
+      for (int k = lane + 64; k < cnt; k += 32) consider(k, e.edge_N[e0 + k], e.edge_W[e0 + k], e.edge_P[e0 + k]);
 #pragma unroll
       for (int off = 16; off; off >>= 1) {
         float ov = __shfl_xor_sync(kFull, best, off); int oi = __shfl_xor_sync(kFull, besti, off);
@@ -183,17 +207,24 @@ __device__ __forceinline__ void tree_step_game(const EngineDev& e, const Geo<NW>
       }
       if (besti == 0x7fffffff) besti = 0;
       const int eoff = base + besti;
+      uint64_t cm;
+      if (besti < 64) {
+        const uint64_t mine = (besti & 32) ? m1 : m0;
+        cm = __shfl_sync(kFull, mine, besti & 31);
+      } else {
+        cm = e.edge_cmeta[eb + eoff];
+      }
       if (lane == 0) path[depth] = eoff;
       ++depth;
-      const int child = e.edge_child[eb + eoff];
+      const int child = cmeta_child(cm);
       if (child < 0) {                      // unexpanded child: getNextState on the parent's state (mcts.py:385-391)
         BB<NW> b = load_bb<NW>(e.node_black, nb + node, e.W), w = load_bb<NW>(e.node_white, nb + node, e.W);
         const int pp = e.node_player[nb + node];
         const int a = e.edge_action[eb + eoff];
-        if (pp == 1) setbit(b, a); else setbit(w, a);   // the slot exists only for a legal action
         const int id = e.g_n_nodes[gi];
+        if (pp == 1) setbit(b, a); else setbit(w, a);   // the slot exists only for a legal action
         __syncwarp();
-        if (lane == 0) { e.g_n_nodes[gi] = id + 1; e.edge_child[eb + eoff] = id; }
+        if (lane == 0) { e.g_n_nodes[gi] = id + 1; e.edge_cmeta[eb + eoff] = cmeta_pack(0, id, 0, 0); }
         publish_leaf<NW>(e, g, gi, lane, slot, id, b, w, -pp, depth);
         if (multi) {                        // virtual visit + virtual loss along the in-flight path
           __syncwarp();
@@ -208,7 +239,7 @@ __device__ __forceinline__ void tree_step_game(const EngineDev& e, const Geo<NW>
         __syncwarp();
         break;
       }
-      node = child;
+      node = child; fl = cmeta_flags(cm); base = cmeta_base(cm); cnt = cmeta_cnt(cm);
     }
   }
   __syncwarp();
