@@ -14,6 +14,8 @@
 //
 // Warp roles (as in tower_kernel): warp 0 weight producer, warp 1 MMA issuer, warps 2-17 epilogue / heads / tree.
 // Roofline: tensor (the tower's conv MMAs are > 99 % of the FLOPs; see yy_nn.cu for the tower layout).
+#include <stdlib.h>
+
 #include "yy_nn.cuh"
 #include "yy_tower.cuh"
 #include "yy_tree_dev.cuh"
@@ -24,7 +26,7 @@ using namespace ptx;
 struct FusedArgs {
   TowerGeo g;
   FcGeo fc;
-  const uint8_t* conv_stream;  // stage-ordered bf16 conv weight blocks
+  const uint8_t* conv_stream;  // stage-ordered bf16 conv weight blocks (CTA-pair kernel: each stage split in two N halves)
   const float* conv_bias;      // [1 + 2*blocks][128] then head [64]
   const uint8_t* fc_stream;    // stage-ordered bf16 FC weight blocks (policy_fc, value_fc1)
   const float* fc_policy_b; const float* fc_value1_b; const float* fc_value2_w; const float* fc_value2_b;
@@ -43,7 +45,11 @@ struct FusedArgs {
 constexpr int kEpiBarrier = 1;   // named barrier of the 16 epilogue warps
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(TW_EPI_THREADS) : "memory"); }
 
-template <int NW>
+// CG = 1: one CTA per SM, M = 128 MMAs.  CG = 2: CTA pairs (cluster of 2, tcgen05 cta_group::2): the leader issues M = 256
+// MMAs over both CTAs' activation tiles, each CTA stages only its half of the weight slice's output channels -- halves
+// the weight bytes every SM pulls from L2 and takes the B-operand fetch off the shared-memory port, which a 128x128x16
+// SS-MMA otherwise saturates (8 KB per 64 cycles = 128 B/clk).
+template <int NW, int CG>
 __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a, const EngineDev e, const Geo<NW> geo) {
   extern __shared__ __align__(128) uint8_t smem[];
   const TowerGeo& g = a.g;
@@ -55,7 +61,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   const uint32_t bar0 = smem_u32(smem + SM_BAR);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (TW_STAGES + s); };
+  auto peer_full_bar = [&](int s) { return bar0 + 8u * (2 * TW_STAGES + 2 + s); };   // leader: the follower's stage s landed
   const uint32_t acc_full = bar0 + 8u * (2 * TW_STAGES), act_ready = bar0 + 8u * (2 * TW_STAGES + 1);
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
 
   // ---- one-time setup ----
@@ -73,23 +81,29 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     pos_tab[i] = (int16_t)v;
   }
   if (tid == 0) {
-    for (int s = 0; s < TW_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < TW_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(peer_full_bar(s), 1); }
     mbar_init(acc_full, 1);
-    mbar_init(act_ready, TW_EPI_THREADS);
+    mbar_init(act_ready, CG * TW_EPI_THREADS);   // pair: the leader's barrier also collects the follower's epilogue threads
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 1) { if (CG == 2) tmem_alloc2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
   fence_proxy_async_smem();
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (a.dbg && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.dbg[128 + 2 * blockIdx.x] = (long long)gt; }
   const uint32_t act_base = smem_u32(smem + SM_ACT);
   const uint32_t ring_base = smem_u32(smem + SM_RING);
   // this CTA's run of boards [run_lo, run_hi), walked in batches of <= FC_N boards; a batch in groups of Gb boards
+  // In a pair both CTAs must walk the same batches / groups / tiles: the loop structure comes from the leader's run
+  // (never shorter than the follower's); boards past this CTA's own run are simply not real.
+  auto clampl = [](long long v, long long hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
   const long long run_lo = (long long)blockIdx.x * a.boards_per_cta;
-  const long long run_hi = (run_lo + a.boards_per_cta < a.count) ? run_lo + a.boards_per_cta : a.count;
+  const long long my_len = clampl(a.count - run_lo, a.boards_per_cta);
+  const long long st_len = clampl(a.count - (long long)(blockIdx.x - rank) * a.boards_per_cta, a.boards_per_cta);
+  const long long run_hi = run_lo + my_len;      // my real boards
+  const long long run_end = run_lo + st_len;     // structural end of the walk
   // tiles a group starting at board b0 needs when its batch ends at `lim`
   // (+pitch+1: the taps of the last real position read that far; rows beyond the group's tiles may be stale)
   auto tiles_for = [&](long long b0, long long lim) {
@@ -97,7 +111,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     int t = g.row_aligned ? (int)((nb * g.rows_per_board + 15) >> 4) : (int)((nb * g.PB + g.pitch + 1 + 127) >> 7);
     return t < g.T ? t : g.T;
   };
-  auto batch_end = [&](long long bb0) { return (bb0 + a.batch_boards < run_hi) ? bb0 + a.batch_boards : run_hi; };
+  auto batch_end = [&](long long bb0) { return (bb0 + a.batch_boards < run_end) ? bb0 + a.batch_boards : run_end; };   // structural
+  auto real_end = [&](long long slim) { return slim < run_hi ? slim : run_hi; };                                         // my boards
   // FC stage geometry: rows of M tile t of head h
   auto fc_tiles = [&](int h) { return h ? 2 : fc.Tp; };
   auto fc_rows = [&](int h, int t) { return (h || t < fc.Tp - 1) ? 128 : fc.Rp_last; };
@@ -119,13 +134,14 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         ++it;
       };
       for (int iter = 0; iter < a.iterations; ++iter) {
-        for (long long bb0 = run_lo; bb0 < run_hi; bb0 += a.batch_boards) {
-          const long long lim = batch_end(bb0);
-          for (long long b0 = bb0; b0 < lim; b0 += g.Gb) {
+        for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
+          const long long slim = batch_end(bb0);
+          for (long long b0 = bb0; b0 < slim; b0 += g.Gb) {
             for (int l = 0; l < L; ++l) {
               const LayerInfo li = layer_info(l, g.blocks);
-              const uint8_t* src = a.conv_stream + li.stream_off;
-              for (int j = 0; j < li.n_stages; ++j) push(src + (long long)j * li.stage_bytes, (uint32_t)li.stage_bytes);
+              const uint32_t bytes = (uint32_t)li.stage_bytes / CG;     // pair: my half of the stage's output channels
+              const uint8_t* src = a.conv_stream + li.stream_off + (long long)rank * bytes;
+              for (int j = 0; j < li.n_stages; ++j) push(src + (long long)j * li.stage_bytes, bytes);
             }
           }
           const uint8_t* src = a.fc_stream;
@@ -143,31 +159,60 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   } else if (warp == 1) {
     // =========================================================== MMA issuer (whole warp runs the control flow, the
     // tcgen05.mma / commit instructions are issued by one elected lane; descriptors are base + constant deltas)
-    if (a.use_nn) {
+    if (a.use_nn && rank != 0) {
+      // follower of a pair: no MMAs to issue -- relay "my half of stage s has landed" to the leader's peer-full ring
+      uint32_t it = 0;
+      auto relay = [&]() {
+        const uint32_t slot = it % TW_STAGES;
+        mbar_wait(full_bar(slot), (it / TW_STAGES) & 1);
+        if (elect_one()) mbar_arrive_cluster(mapa_u32(peer_full_bar(slot), 0));
+        __syncwarp();
+        ++it;
+      };
+      for (int iter = 0; iter < a.iterations; ++iter) {
+        for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
+          const long long slim = batch_end(bb0);
+          for (long long b0 = bb0; b0 < slim; b0 += g.Gb)
+            for (int l = 0; l < L; ++l) { const int ns = layer_info(l, g.blocks).n_stages; for (int j = 0; j < ns; ++j) relay(); }
+          for (int h = 0; h < 2; ++h)
+            for (int p = 0; p < fc.n_panels; ++p) { const int ns = panel_stages(p) * fc_tiles(h); for (int j = 0; j < ns; ++j) relay(); }
+        }
+      }
+    } else if (a.use_nn) {
       uint32_t it = 0, act_phase = 0;
+      auto wait_stage = [&](uint32_t slot, uint32_t parity) {
+        mbar_wait(full_bar(slot), parity);
+        if (CG == 2) mbar_wait_cluster(peer_full_bar(slot), parity);
+      };
+      auto wait_act = [&](uint32_t parity) { if (CG == 2) mbar_wait_cluster(act_ready, parity); else mbar_wait(act_ready, parity); };
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+        if (CG == 2) tc_mma_bf16_2(d, ad, bd, idesc, acc); else tc_mma_bf16(d, ad, bd, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) { if (CG == 2) tc_commit2(bar); else tc_commit(bar); };
       const uint64_t kTileDelta = (uint64_t)g.tile_adv;            // next M=128 tile, in 16-byte rows
       constexpr uint64_t kK16DeltaA = (2u * TW_ROWS * 16u) >> 4;   // next K=16 slice: +2 channel chunks
       constexpr uint64_t kK16DeltaF = (2u * FC_LBO) >> 4;          // same for the FC feature panel
       for (int iter = 0; iter < a.iterations; ++iter) {
-        for (long long bb0 = run_lo; bb0 < run_hi; bb0 += a.batch_boards) {
-          const long long lim = batch_end(bb0);
-          for (long long b0 = bb0; b0 < lim; b0 += g.Gb) {
-            const int T = tiles_for(b0, lim);
+        for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
+          const long long slim = batch_end(bb0);
+          for (long long b0 = bb0; b0 < slim; b0 += g.Gb) {
+            const int T = tiles_for(b0, slim);
             for (int l = 0; l < L; ++l) {
               const LayerInfo li = layer_info(l, g.blocks);
               const bool preloaded = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 0);  // conv2: accumulator holds the skip input
-              const uint32_t idesc = idesc_bf16(128, li.N);
-              const uint64_t k16_delta_b = (uint64_t)((2u * (uint32_t)li.N * 16u) >> 4);
-              mbar_wait(act_ready, act_phase); act_phase ^= 1;
+              const uint32_t idesc = idesc_bf16(128 * CG, li.N);
+              const uint32_t nrows_b = (uint32_t)li.N / CG;                          // weight rows staged per CTA
+              const uint64_t k16_delta_b = (uint64_t)((2u * nrows_b * 16u) >> 4);
+              wait_act(act_phase); act_phase ^= 1;
               tc_fence_after();
               for (int j = 0; j < li.n_stages; ++j, ++it) {
                 const uint32_t slot = it % TW_STAGES;
                 int tapshift, chunk0;
                 stage_info(l, j, g.blocks, g.pitch, tapshift, chunk0);
-                mbar_wait(full_bar(slot), (it / TW_STAGES) & 1);
+                wait_stage(slot, (it / TW_STAGES) & 1);
                 tc_fence_after();
                 const uint64_t ad0 = smem_desc(act_base + (uint32_t)((chunk0 * TW_ROWS + TW_PAD + tapshift) * 16), TW_ROWS * 16, (uint32_t)g.sbo_bytes);
-                const uint64_t bd0 = smem_desc(ring_base + slot * TW_STAGE_BYTES, (uint32_t)li.N * 16, 128);
+                const uint64_t bd0 = smem_desc(ring_base + slot * TW_STAGE_BYTES, nrows_b * 16, 128);
                 const uint32_t acc0 = (preloaded || j > 0) ? 1u : 0u;
                 if (elect_one()) {
 #pragma unroll
@@ -176,33 +221,34 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
 #pragma unroll
                       for (int k = 0; k < 4; ++k) {
                         if (k < li.nk16)
-                          tc_mma_bf16(tmem_base + (uint32_t)(t * 128), ad0 + (uint64_t)t * kTileDelta + (uint64_t)k * kK16DeltaA,
-                                      bd0 + (uint64_t)k * k16_delta_b, idesc, k > 0 ? 1u : acc0);
+                          mma(tmem_base + (uint32_t)(t * 128), ad0 + (uint64_t)t * kTileDelta + (uint64_t)k * kK16DeltaA,
+                              bd0 + (uint64_t)k * k16_delta_b, idesc, k > 0 ? 1u : acc0);
                       }
                     }
                   }
-                  tc_commit(empty_bar(slot));
+                  commit(empty_bar(slot));
                 }
                 __syncwarp();
               }
-              if (elect_one()) tc_commit(acc_full);
+              if (elect_one()) commit(acc_full);
               __syncwarp();
             }
           }
           // ---- FC heads: D[o][board] (+)= Wfc[o][k] * feat[board][k]; A = weight stage in the ring, B = feature panel
-          const uint32_t idesc_fc = idesc_bf16(128, FC_N);
+          // (pair: both CTAs stage the same weight tile, so both get D for all 2 x FC_N boards; column block `rank` is mine)
+          const uint32_t idesc_fc = idesc_bf16(128 * CG, FC_N * CG);
           for (int h = 0; h < 2; ++h)
             for (int p = 0; p < fc.n_panels; ++p) {
               const int ns = panel_stages(p);
-              mbar_wait(act_ready, act_phase); act_phase ^= 1;
+              wait_act(act_phase); act_phase ^= 1;
               tc_fence_after();
               for (int t = 0; t < fc_tiles(h); ++t) {
                 const uint32_t R = (uint32_t)fc_rows(h, t);
-                const uint32_t dcol = (uint32_t)((h ? fc.Tp + t : t) * FC_N);
+                const uint32_t dcol = (uint32_t)((h ? fc.Tp + t : t) * FC_N * CG);
                 const uint64_t k16_delta_w = (uint64_t)((2u * R * 16u) >> 4);
                 for (int s = 0; s < ns; ++s, ++it) {
                   const uint32_t slot = it % TW_STAGES;
-                  mbar_wait(full_bar(slot), (it / TW_STAGES) & 1);
+                  wait_stage(slot, (it / TW_STAGES) & 1);
                   tc_fence_after();
                   const uint64_t wd0 = smem_desc(ring_base + slot * TW_STAGE_BYTES, R * 16, 128);
                   const uint64_t fd0 = smem_desc(act_base + (uint32_t)(s * 8 * FC_LBO), FC_LBO, 128);
@@ -210,14 +256,13 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                   if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                      tc_mma_bf16(tmem_base + dcol, wd0 + (uint64_t)k * k16_delta_w, fd0 + (uint64_t)k * kK16DeltaF, idesc_fc,
-                                  k > 0 ? 1u : acc0);
-                    tc_commit(empty_bar(slot));
+                      mma(tmem_base + dcol, wd0 + (uint64_t)k * k16_delta_w, fd0 + (uint64_t)k * kK16DeltaF, idesc_fc, k > 0 ? 1u : acc0);
+                    commit(empty_bar(slot));
                   }
                   __syncwarp();
                 }
               }
-              if (elect_one()) tc_commit(acc_full);
+              if (elect_one()) commit(acc_full);
               __syncwarp();
             }
         }
@@ -236,13 +281,16 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     float* sc_hidden = reinterpret_cast<float*>(act) + FC_N * 256;   // [FC_N][256] relu(fc1) * w2
     long long ph_t = clock64(), ph_acc[5] = {0, 0, 0, 0, 0};             // developer stamps: tower / FC / heads+tree / barrier / zero
     auto phase = [&](int k) { if (a.dbg) { const long long now = clock64(); ph_acc[k] += now - ph_t; ph_t = now; } };
+    const uint32_t act_ready_leader = CG == 2 ? mapa_u32(act_ready, 0) : act_ready;
+    auto arrive_act = [&]() { if (CG == 2) mbar_arrive_cluster(act_ready_leader); else mbar_arrive(act_ready); };
     for (int iter = 0; iter < a.iterations; ++iter) {
-      for (long long bb0 = run_lo; bb0 < run_hi; bb0 += a.batch_boards) {
-        const long long lim = batch_end(bb0);
-        const int nbb = (int)(lim - bb0);
+      for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
+        const long long slim = batch_end(bb0);
+        const long long lim = real_end(slim);                    // boards at or past `lim` are padding of the walk
+        const int nbb = lim > bb0 ? (int)(lim - bb0) : 0;
         if (a.use_nn) {
-          for (long long b0 = bb0; b0 < lim; b0 += g.Gb) {
-            const int T = tiles_for(b0, lim);
+          for (long long b0 = bb0; b0 < slim; b0 += g.Gb) {
+            const int T = tiles_for(b0, slim);
             // ---- stem input planes (board_to_input, neural_network.py:156-196) for my rows ----
             for (int t = tile0; t < T; t += kTileStride) {
               const int mi = t * 128 + quarter * 32 + lane;
@@ -271,7 +319,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
             }
             tc_fence_before();
             fence_proxy_async_smem();
-            mbar_arrive(act_ready);
+            arrive_act();
 
             for (int l = 0; l < L; ++l) {
               const bool is_head = (l == L - 1);
@@ -346,7 +394,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                 }
               }
               tc_fence_before();
-              if (!is_head) { fence_proxy_async_smem(); mbar_arrive(act_ready); }
+              if (!is_head) { fence_proxy_async_smem(); arrive_act(); }
             }
           }
 
@@ -368,13 +416,13 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
             cp_async_wait<0>();
             tc_fence_before();
             fence_proxy_async_smem();
-            mbar_arrive(act_ready);
+            arrive_act();
           }
           mbar_wait(acc_full, acc_phase); acc_phase ^= 1;
           tc_fence_after();
           // D tiles -> scratch: policy logits (+bias), value hidden units relu(.+b1) * w2   (lane = output unit)
           if (tile0 < fc.Tp + 2) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile0 * FC_N);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile0 * FC_N * CG + rank * FC_N);
             uint32_t r0[16], r1[16];
             tc_ld16(taddr, r0);
             tc_ld16(taddr + 16, r1);
@@ -439,9 +487,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
       for (int k = 0; k < 5; ++k) a.dbg[600 + (blockIdx.x ? 100 : 0) + ew * 5 + k] = ph_acc[k];
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (a.dbg && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.dbg[129 + 2 * blockIdx.x] = (long long)gt; }
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) { if (CG == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -450,14 +498,21 @@ static int fused_batch_boards(const TowerGeo& g) {
   return per > 0 ? per : g.Gb;
 }
 
-template <int NW>
+template <int NW, int CG>
 static int launch_fused(NNState& nn, const FusedArgs& fa, const EngineDev& dev, uint32_t rule_flags, int grid, cudaStream_t s) {
   static bool attr_set[8] = {};
   if (!attr_set[nn.device & 7]) {
-    YY_CUDA_OK(cudaFuncSetAttribute(fused_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    YY_CUDA_OK(cudaFuncSetAttribute(fused_kernel<NW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     attr_set[nn.device & 7] = true;
   }
-  fused_kernel<NW><<<grid, TW_THREADS, SM_TOTAL, s>>>(fa, dev, make_geo<NW>(nn.rows, nn.cols, rule_flags));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TW_THREADS); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const Geo<NW> geo = make_geo<NW>(nn.rows, nn.cols, rule_flags);
+  YY_CUDA_OK(cudaLaunchKernelEx(&cfg, fused_kernel<NW, CG>, fa, dev, geo));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -473,6 +528,8 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
   }
   if (count <= 0 || iterations <= 0) return YY_OK;
   if (count > nn.max_boards) return set_error(YY_ERR_INVALID, "fused run: %lld boards exceed the head-feature scratch (%d)", (long long)count, nn.max_boards);
+  static const bool pair_default = [] { const char* v = getenv("YY_CTA_PAIR"); return !(v && v[0] == '0'); }();
+  const bool pair = pair_default;
   FusedArgs fa{};
   fa.g = make_tower_geo(nn.rows, nn.cols, nn.blocks);
   if (fa.g.Gb > FC_N) fa.g.Gb = FC_N;
@@ -480,7 +537,7 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
   if (use_nn) {
     const WeightLayout wl = weight_layout(nn.rows, nn.cols, nn.blocks);
     const uint8_t* wimg = static_cast<const uint8_t*>(nn.weights);
-    fa.conv_stream = wimg + wl.conv_stream;
+    fa.conv_stream = wimg + (pair ? wl.conv_stream_pair : wl.conv_stream);
     fa.conv_bias = reinterpret_cast<const float*>(wimg + wl.conv_bias);
     fa.fc_stream = wimg + wl.fc_stream;
     fa.fc_policy_b = reinterpret_cast<const float*>(wimg + wl.fc_policy_b);
@@ -500,7 +557,8 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
   if (per < fa.g.Gb && use_nn) per = fa.g.Gb;
   if (per < 1) per = 1;
   fa.boards_per_cta = (int)per;
-  const int grid = (int)((count + per - 1) / per);
+  int grid = (int)((count + per - 1) / per);
+  if (pair) grid = (grid + 1) & ~1;      // whole pairs; a trailing follower without boards only mirrors its leader's walk
   EngineDev d{};
   if (dev) d = *dev;
   if (nn.profiling) {
@@ -508,7 +566,8 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
     YY_CUDA_OK(cudaEventRecord(nn.ev[2 * nn.ev_used], s));
   }
   int rc = YY_OK;
-  YY_DISPATCH_NW(nn.A, rc = launch_fused<NW>(nn, fa, d, rule_flags, grid, s));
+  if (pair) { YY_DISPATCH_NW(nn.A, rc = (launch_fused<NW, 2>(nn, fa, d, rule_flags, grid, s))); }
+  else { YY_DISPATCH_NW(nn.A, rc = (launch_fused<NW, 1>(nn, fa, d, rule_flags, grid, s))); }
   if (rc) return rc;
   if (nn.profiling) {
     YY_CUDA_OK(cudaEventRecord(nn.ev[2 * nn.ev_used + 1], s));

@@ -441,7 +441,8 @@ int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_
 
 // Section offsets of the packed weight image, for the host-side packer:
 // out[0..8] = conv_stream, conv_bias, fc_policy_w, fc_policy_b, fc_value1_w, fc_value1_b, fc_value2_w, fc_value2_b, total;
-// out[9] = padded policy rows (A rounded up to 16); out[10], out[11] = offset / bytes of the stage-ordered FC stream.
+// out[9] = padded policy rows (A rounded up to 16); out[10], out[11] = offset / bytes of the stage-ordered FC stream;
+// out[12] = conv stream with N-halved stages (CTA-pair kernel).
 extern "C" int yy_nn_weight_layout(int rows, int cols, int channels, int blocks, int64_t* out) {
   using namespace yy;
   int64_t t = nn_weight_bytes(rows, cols, channels, blocks);
@@ -449,6 +450,6 @@ extern "C" int yy_nn_weight_layout(int rows, int cols, int channels, int blocks,
   WeightLayout w = weight_layout(rows, cols, blocks);
   out[0] = w.conv_stream; out[1] = w.conv_bias; out[2] = w.fc_policy_w; out[3] = w.fc_policy_b; out[4] = w.fc_value1_w;
   out[5] = w.fc_value1_b; out[6] = w.fc_value2_w; out[7] = w.fc_value2_b; out[8] = w.total; out[9] = w.a_pad;
-  out[10] = w.fc_stream; out[11] = w.fc_stream_bytes;
+  out[10] = w.fc_stream; out[11] = w.fc_stream_bytes; out[12] = w.conv_stream_pair;
   return YY_OK;
 }

@@ -25,7 +25,7 @@ constexpr int SM_ACT = 0;
 constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 157696
 constexpr int SM_POS = SM_RING + TW_STAGES * TW_STAGE_BYTES;          // position tables: padded position + (board, cell)
 constexpr int SM_BAR = SM_POS + 2 * 128 * TW_MAXT * 2;
-constexpr int SM_TMEM = SM_BAR + 8 * (2 * TW_STAGES + 2);
+constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_STAGES + 2);   // full, empty, peer-full rings + acc_full, act_ready
 constexpr int SM_TOTAL = SM_TMEM + 16;
 
 struct TowerGeo {
@@ -84,6 +84,7 @@ struct WeightLayout {
   int64_t conv_stream, conv_bias, fc_policy_w, fc_policy_b, fc_value1_w, fc_value1_b, fc_value2_w, fc_value2_b, total;
   int a_pad;
   int64_t fc_stream, fc_stream_bytes;   // stage-ordered policy FC + value FC1 weights for the persistent kernel
+  int64_t conv_stream_pair;             // conv stream with every stage split into two N halves (CTA-pair kernel)
 };
 
 // ---- FC heads inside the persistent kernel (yy_fused.cu): out[o][board] = W[o][:] . feat[board][:] as UMMA with the
@@ -124,6 +125,7 @@ inline WeightLayout weight_layout(int rows, int cols, int blocks) {
   w.fc_value2_w = off; off = align256(off + 256 * 4);
   w.fc_value2_b = off; off = align256(off + 4);
   w.fc_stream = off; w.fc_stream_bytes = fc_stream_bytes(A); off = align256(off + w.fc_stream_bytes);
+  w.conv_stream_pair = off; off = align256(off + conv_stream_bytes(blocks));
   w.total = off;
   return w;
 }

@@ -89,10 +89,10 @@ def infer_arch(sd):
 
 
 def layout(rows: int, cols: int, channels: int, blocks: int):
-    out = (ctypes.c_int64 * 12)()
+    out = (ctypes.c_int64 * 13)()
     _lib.check(_lib.lib().yy_nn_weight_layout(rows, cols, channels, blocks, out))
     names = ["conv_stream", "conv_bias", "fc_policy_w", "fc_policy_b", "fc_value1_w", "fc_value1_b",
-             "fc_value2_w", "fc_value2_b", "total", "a_pad", "fc_stream", "fc_stream_bytes"]
+             "fc_value2_w", "fc_value2_b", "total", "a_pad", "fc_stream", "fc_stream_bytes", "conv_stream_pair"]
     return dict(zip(names, [int(v) for v in out]))
 
 
@@ -140,6 +140,16 @@ def pack_state_dict(state_dict, rows: int, cols: int) -> np.ndarray:
     s = np.concatenate(stream).view(np.uint8)
     assert s.size <= lay["conv_bias"] - lay["conv_stream"], (s.size, lay)
     img[lay["conv_stream"]: lay["conv_stream"] + s.size] = s
+    # CTA-pair kernel: every stage block [kc][oc][8] becomes [half][kc][oc/2][8] (each CTA stages its half of the output channels)
+    halves = []
+    for i, blk in enumerate(stream):
+        oc = HEAD_C if i == len(stream) - 1 else TOWER_C
+        kc = 2 if i < 9 else 8                               # K chunks per stage: stem taps have K = 16, the rest K = 64
+        b4 = blk.reshape(-1, kc, oc, 8)                      # [stage][kc][oc][8]
+        halves.append(np.ascontiguousarray(np.stack([b4[:, :, : oc // 2], b4[:, :, oc // 2:]], axis=1)).reshape(-1))
+    s2 = np.concatenate(halves).view(np.uint8)
+    assert s2.size == s.size
+    img[lay["conv_stream_pair"]: lay["conv_stream_pair"] + s2.size] = s2
     cb = np.concatenate(biases + [head_bias]).astype(np.float32).view(np.uint8)
     img[lay["conv_bias"]: lay["conv_bias"] + cb.size] = cb
 
