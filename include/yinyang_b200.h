@@ -180,13 +180,15 @@ const uint8_t *yy_engine_leaf_active(yy_engine *e);
 int yy_evaluate(yy_engine *e, const uint64_t *black_dev, const uint64_t *white_dev, int64_t count,
                 float *out_policy_dev, float *out_value_dev, float *out_logits_dev, void *stream);
 
-/* Optional CUDA-event timing of the dominant kernel (the residual-tower kernel), recorded on the launching
- * stream around every launch while enabled.  yy_engine_get_profile synchronises on the recorded events and
- * returns totals since profiling was enabled: launches, summed device milliseconds, boards evaluated. */
+/* Optional CUDA-event timing of the dominant kernel (the persistent search / forward kernel, csrc/yy_fused.cu),
+ * recorded on the launching stream around every launch while enabled.  yy_engine_get_profile synchronises on the
+ * recorded events and returns totals since profiling was enabled: launches, summed device milliseconds, leaf
+ * evaluations (boards x simulations) those launches performed. */
 int yy_engine_set_profiling(yy_engine *e, int enable);
 int yy_engine_get_profile(yy_engine *e, int64_t *tower_launches, double *tower_ms, int64_t *tower_boards);
-/* Developer tool: while dbg_dev != NULL the tower kernel's CTA 0 writes, for its first group, four clock64
- * stamps per layer (MMA issue start / end, epilogue start / end) into dbg_dev[4*layer .. 4*layer+3]. */
+/* Developer tool: while dbg_dev != NULL (>= 1024 int64) the persistent kernel records per-CTA start / end
+ * %globaltimer stamps at dbg_dev[128 + 2*cta ..] and, for CTAs 0 and 100, the cycles its epilogue warps spent in
+ * each phase (tower, FC heads, softmax + tree step, barrier, re-zero) at dbg_dev[600 ..] / [700 ..]. */
 int yy_engine_set_debug_stamps(yy_engine *e, long long *dbg_dev);
 
 /* Self-play driver (SelfPlayWorker.play_game, self_play.py:72-192, for n_games games in

@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libyinyang_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "yinyang_b200.h")
-SOURCES = ["yy_rules_kernels.cu", "yy_tree.cu", "yy_gemm.cu", "yy_nn.cu", "yy_fused.cu"]
+SOURCES = ["yy_rules_kernels.cu", "yy_tree.cu", "yy_probe.cu", "yy_nn.cu", "yy_fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 

@@ -14,7 +14,7 @@ struct NNState {
   int64_t scratch_bytes;
   int device, num_sms;
   bool attrs_set;
-  // optional CUDA-event timing of the tower kernel (bench.py's live roofline figure)
+  // optional CUDA-event timing of the persistent kernel launches (bench.py's live roofline figure)
   bool profiling;
   cudaEvent_t* ev;           // 2 * ev_cap events
   int ev_cap, ev_used;
@@ -30,11 +30,6 @@ int nn_load_weights(NNState& nn, const void* weights_dev, int64_t bytes);
 int nn_set_profiling(NNState& nn, int enable);
 // drains recorded event pairs (synchronises) and returns totals since profiling was enabled
 int nn_get_profile(NNState& nn, long long* launches, double* total_ms, long long* boards);
-// black/white: [count][W] bitboards on the device.  policy [count][A] = softmax(logits) (neural_network.py:152),
-// value [count] = tanh head, logits [count][A] optional.  count <= max_boards per call is chunked internally.
-int nn_forward(NNState& nn, const uint64_t* black, const uint64_t* white, int64_t count, float* policy, float* value,
-               float* logits, cudaStream_t stream);
-
 struct EngineDev;
 // Persistent kernel (yy_fused.cu): `iterations` x (network forward on boards [0,count) -> heads -> optional tree step)
 // in ONE launch.  dev == nullptr: plain forward into policy/value/logits.  dev != nullptr: whole search over the

@@ -1,14 +1,12 @@
-// yy_gemm.cu -- tcgen05 GEMM building block: C[M,N] = act(A[M,K] * B[N,K]^T + bias), bf16 in, fp32 accumulate
-// in TMEM.  Used for the policy / value fully-connected heads (neural_network.py:113-121) and, through
-// yy_probe_umma, as the self-test that pins the shared-memory descriptor conventions of the tower kernel.
-//
-// Operands are plain row-major in global memory; cp.async (16 B = 8 bf16 along K) scatters them into the
-// no-swizzle K-major core-matrix layout [k/8][row][8] in shared memory, which is exactly what the UMMA
-// descriptor (yy_ptx.cuh: smem_desc) describes with LBO = rows*16 and SBO = 128.
+// yy_probe.cu -- tcgen05 self-tests and micro-benchmarks (developer tools; nothing here is on the product path).
+//   yy_probe_umma : one-CTA C[128,N] = A[M,K] * B[N,K]^T with the no-swizzle K-major core-matrix layout [k/8][row][8]
+//                   and descriptor strides the persistent kernel uses (LBO = rows*16, SBO = 128 or a board-row pitch);
+//                   tests/ pin the descriptor conventions with it, including start addresses a 3x3 tap shift produces.
+//   yy_umma_rate  : cycles per tcgen05.mma vs shared-memory layout (operand-fetch rate: 128 B/clk shared-memory port).
+//   yy_l2_stream  : achievable L2 -> shared-memory bulk-copy rate when every SM streams the same weight image.
 #include <cuda_bf16.h>
 
 #include "yy_common.cuh"
-#include "yy_gemm.cuh"
 #include "yy_ptx.cuh"
 
 namespace yy {
@@ -67,172 +65,6 @@ __global__ void __launch_bounds__(128) probe_umma_kernel(const __nv_bfloat16* __
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32) tmem_dealloc(tmem_base, ncols);
-}
-
-// ------------------------------------------------------------------------------------------------ tiled GEMM
-// grid = (ceil(M/128), N/BN).  128 threads.  BK = 64 per stage, 3-stage cp.async ring; thread 0 issues the
-// MMAs and frees a stage with tcgen05.commit; all four warps drain TMEM in the epilogue.
-constexpr int kGemmBK = 64;
-constexpr int kGemmStages = 4;   // 96 KB: two CTAs per SM, so the 160 head tiles of a 4,096-board batch are one wave
-
-struct GemmPair { GemmArgs p[2]; int ytiles0; };
-
-template <int BN>
-__device__ __forceinline__ void gemm_tile(const GemmArgs& g, int tile_m, int tile_n);
-
-template <int BN>
-__global__ void __launch_bounds__(128) gemm_bf16_tn_kernel(GemmArgs g) { gemm_tile<BN>(g, blockIdx.x, blockIdx.y); }
-
-template <int BN>
-__global__ void __launch_bounds__(128) gemm_bf16_tn_pair_kernel(GemmPair gp) {
-  if ((int)blockIdx.y < gp.ytiles0) gemm_tile<BN>(gp.p[0], blockIdx.x, blockIdx.y);
-  else gemm_tile<BN>(gp.p[1], blockIdx.x, blockIdx.y - gp.ytiles0);
-}
-
-template <int BN>
-__device__ __forceinline__ void gemm_tile(const GemmArgs& g, int tile_m, int tile_n) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t mma_done[kGemmStages];
-  __shared__ __align__(8) uint64_t acc_done;
-  __shared__ uint32_t tmem_base_s;
-  // k-chunk planes are padded by one 16-byte row (LBO = (rows+1)*16) so that the 8 chunks of one global 128-byte
-  // line, fetched by 8 consecutive threads, land in 8 different bank groups
-  constexpr int A_LBO = (128 + 1) * 16, B_LBO = (BN + 1) * 16;
-  constexpr int A_STAGE = (kGemmBK / 8) * A_LBO;
-  constexpr int B_STAGE = (kGemmBK / 8) * B_LBO;
-  uint8_t* a_s = smem;
-  uint8_t* b_s = smem + kGemmStages * A_STAGE;
-  const int m0 = tile_m * 128, n0 = tile_n * BN;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t NCOLS = BN < 32 ? 32 : BN;
-  if (tid == 0) {
-    for (int s = 0; s < kGemmStages; ++s) mbar_init(smem_u32(&mma_done[s]), 1);
-    mbar_init(smem_u32(&acc_done), 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), NCOLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-  const int nkb = (g.K + kGemmBK - 1) / kGemmBK;
-
-  auto load_stage = [&](int kb, int s) {
-    const int k0 = kb * kGemmBK;
-    // 8 consecutive threads fetch the 8 chunks (one contiguous 128-byte line) of one row
-    const int kc = tid & 7;
-    const bool kv = (k0 + kc * 8) < g.K;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = (tid >> 3) + 16 * i;
-      const bool rv = (m0 + r) < g.M;
-      cp_async16(smem_u32(a_s + s * A_STAGE + kc * A_LBO + r * 16), g.A + (size_t)(rv ? (m0 + r) : 0) * g.lda + k0 + kc * 8, rv && kv);
-    }
-#pragma unroll
-    for (int i = 0; i < BN / 16; ++i) {
-      const int r = (tid >> 3) + 16 * i;
-      const bool rv = (n0 + r) < g.N;
-      cp_async16(smem_u32(b_s + s * B_STAGE + kc * B_LBO + r * 16), g.B + (size_t)(rv ? (n0 + r) : 0) * g.ldb + k0 + kc * 8, rv && kv);
-    }
-    cp_async_commit();
-  };
-
-  // prologue
-  for (int p = 0; p < kGemmStages - 1; ++p) { if (p < nkb) load_stage(p, p); else cp_async_commit(); }
-  uint32_t done_phase_bits = 0;   // bit s = parity to wait for on mma_done[s]
-  const uint32_t idesc = idesc_bf16(128, BN);
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb % kGemmStages;
-    // issue the load for k-block kb + stages - 1 into the stage that k-block kb-1 used
-    {
-      const int nk = kb + kGemmStages - 1, ns = nk % kGemmStages;
-      if (nk < nkb) {
-        if (kb >= 1) { mbar_wait(smem_u32(&mma_done[ns]), (done_phase_bits >> ns) & 1u); done_phase_bits ^= 1u << ns; }
-        load_stage(nk, ns);
-      } else {
-        cp_async_commit();
-      }
-    }
-    cp_async_wait<kGemmStages - 1>();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int k16 = 0; k16 < kGemmBK / 16; ++k16) {
-        uint64_t ad = smem_desc(smem_u32(a_s + s * A_STAGE) + 2 * k16 * A_LBO, A_LBO, 128);
-        uint64_t bd = smem_desc(smem_u32(b_s + s * B_STAGE) + 2 * k16 * B_LBO, B_LBO, 128);
-        tc_mma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
-      }
-      tc_commit(smem_u32(&mma_done[s]));
-      if (kb == nkb - 1) tc_commit(smem_u32(&acc_done));
-    }
-  }
-  mbar_wait(smem_u32(&acc_done), 0);
-  tc_fence_after();
-  const int row = m0 + warp * 32 + lane;
-  for (int c = 0; c < BN; c += 16) {
-    uint32_t r[16];
-    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, r);
-    tc_wait_ld();
-    if (row < g.M) {
-      float out[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float v = __uint_as_float(r[j]);
-        if (g.bias) v += g.bias[n0 + c + j];
-        if (g.relu) v = fmaxf(v, 0.0f);
-        out[j] = v;
-      }
-      float4* dst = reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n0 + c);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, NCOLS);
-}
-
-template <int BN>
-static int launch_gemm(const GemmArgs& g, cudaStream_t s) {
-  constexpr int smem = kGemmStages * (kGemmBK / 8) * ((128 + 1) * 16 + (BN + 1) * 16);
-  static bool attr_done = false;
-  if (!attr_done) {
-    YY_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
-  dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)(g.N / BN));
-  gemm_bf16_tn_kernel<BN><<<grid, 128, smem, s>>>(g);
-  YY_LAUNCH_CHECK();
-  return YY_OK;
-}
-
-int gemm_bf16_tn_pair(const GemmArgs& p0, const GemmArgs& p1, cudaStream_t s) {
-  if (p0.M <= 0) return YY_OK;
-  if (p0.M != p1.M || p0.N % 64 || p1.N % 64 || p0.K % 8 || p1.K % 8 || p0.lda % 8 || p1.lda % 8 || p0.ldb % 8 || p1.ldb % 8)
-    return set_error(YY_ERR_INVALID, "gemm pair: equal M, N multiples of 64, K/lda/ldb multiples of 8 required");
-  constexpr int BN = 64;
-  constexpr int smem = kGemmStages * (kGemmBK / 8) * ((128 + 1) * 16 + (BN + 1) * 16);
-  static bool attr_done = false;
-  if (!attr_done) {
-    YY_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
-  GemmPair gp; gp.p[0] = p0; gp.p[1] = p1; gp.ytiles0 = p0.N / BN;
-  dim3 grid((unsigned)((p0.M + 127) / 128), (unsigned)(p0.N / BN + p1.N / BN));
-  gemm_bf16_tn_pair_kernel<BN><<<grid, 128, smem, s>>>(gp);
-  YY_LAUNCH_CHECK();
-  return YY_OK;
-}
-
-int gemm_bf16_tn(const GemmArgs& g, cudaStream_t s) {
-  if (g.M <= 0) return YY_OK;
-  if (g.K % 8 || g.lda % 8 || g.ldb % 8 || g.ldc % 4) return set_error(YY_ERR_INVALID, "gemm: K, lda, ldb must be multiples of 8, ldc of 4");
-  if (g.N % 64 == 0) return launch_gemm<64>(g, s);
-  if (g.N % 32 == 0) return launch_gemm<32>(g, s);
-  if (g.N % 16 == 0) return launch_gemm<16>(g, s);
-  return set_error(YY_ERR_INVALID, "gemm: N must be a multiple of 16 (got %d)", g.N);
 }
 
 }  // namespace yy

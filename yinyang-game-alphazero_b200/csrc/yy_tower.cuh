@@ -1,5 +1,17 @@
-// yy_tower.cuh -- geometry, weight-stream layout and shared-memory map of the tcgen05 residual-tower kernels
-// (shared by yy_nn.cu and the persistent search kernel in yy_fused.cu).  Layout rationale: yy_nn.cu header.
+// yy_tower.cuh -- geometry, weight-stream layout and shared-memory map of the tcgen05 residual tower
+// (host side: yy_nn.cu; device side: the persistent search kernel in yy_fused.cu).
+//
+// A CTA walks "groups" of boards.  A group is a flat list of up to 512 padded positions: each board contributes
+// (n+1) x (m+1) positions -- its n x m cells plus one zero column on the right and one zero row below -- so that the
+// 3x3 tap (dy,dx) of EVERY position is the position dy*(m+1)+dx further along the list and zero padding comes for free.
+// The whole residual tower runs with the group's activations resident in shared memory ([C/8 chunks][616 rows][8 ch]
+// bf16 = no-swizzle K-major UMMA core matrices, so a tap shift is just a +16 B/row move of the descriptor start
+// address); only the weights stream in (K = 64 stages by cp.async.bulk into a 4-deep mbarrier ring, shared by the
+// group's 4 M=128 tiles).  For 8-wide boards the MMA's 8-row groups are the board rows themselves (descriptor SBO =
+// 9*16 B skips the zero column): 7 boards per group, 87.5 % of the MMA rows are real cells.  Accumulators live in TMEM
+// (4 tiles x 128 fp32 columns = all 512 columns).  The skip connection never touches shared memory: conv1's epilogue
+// re-loads the block input into the TMEM accumulator (tcgen05.st) before overwriting it in place, and conv2
+// accumulates on top of it.  Algorithmic FLOPs per board: 2*A*(9*5*C + blocks*2*9*C*C + C*64) + FC heads.
 #pragma once
 #include <cuda_bf16.h>
 

@@ -297,10 +297,9 @@ int launch_step(yy_engine* e, cudaStream_t s) {
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
-// network forward: the persistent kernel with one iteration and no tree step, or the per-layer-group legacy kernels
+// network forward = the persistent kernel with one iteration and no tree step
 int engine_forward(yy_engine* e, const uint64_t* black, const uint64_t* white, int64_t count, float* policy, float* value,
                    float* logits, cudaStream_t s) {
-  if (e->cfg.mode_flags & YY_MODE_STEP_KERNELS) return nn_forward(e->nn, black, white, count, policy, value, logits, s);
   for (int64_t done = 0; done < count; done += e->nn.max_boards) {
     const int64_t n = (count - done) < e->nn.max_boards ? (count - done) : e->nn.max_boards;
     int rc = nn_fused_run(e->nn, nullptr, e->cfg.rule_flags, black + done * e->dev.W, white + done * e->dev.W, n, policy + done * e->dev.A,
