@@ -218,7 +218,9 @@ def run_b200(args):
     for _ in range(e2e_steps):
         counts, _ = eng.search_host(boards, players_s)
         tot = counts.sum(axis=1)
-        acts = np.array([rng.choice(A, p=c / t) if t > 0 else -1 for c, t in zip(counts, tot)], dtype=np.int32)
+        # temperature-1 sampling proportional to the visit counts (self_play.py:145-152), vectorised over the games
+        cdf = np.cumsum(counts, axis=1)
+        acts = np.where(tot > 0, (cdf > (rng.random(len(tot)) * tot)[:, None]).argmax(axis=1), -1).astype(np.int32)
         boards, players = engine.next_state_host(boards, players, acts, ROWS, COLS)
     barrier()
     e2e_s = time.perf_counter() - t0

@@ -127,10 +127,11 @@ _lib = None
 
 
 def lib() -> ctypes.CDLL:
-    """Load (building first if stale) the shared library and attach signatures."""
+    """Load (building first if stale) the shared library and attach signatures.  YY_LIB_PATH (developer switch) loads
+    a prebuilt library instead, e.g. to A/B two kernel variants in one GPU session."""
     global _lib
     if _lib is None:
-        path = build()
+        path = os.environ.get("YY_LIB_PATH") or build()
         L = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
