@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     uint8_t* act = smem + SM_ACT;
     float* sc_logit = reinterpret_cast<float*>(act);                 // [FC_N][256] heads scratch (act region is free then)
     float* sc_hidden = reinterpret_cast<float*>(act) + FC_N * 256;   // [FC_N][256] relu(fc1) * w2
+    float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS);
     long long ph_t = clock64(), ph_acc[5] = {0, 0, 0, 0, 0};             // developer stamps: tower / FC / heads+tree / barrier / zero
     auto phase = [&](int k) { if (a.dbg) { const long long now = clock64(); ph_acc[k] += now - ph_t; ph_t = now; } };
     const uint32_t act_ready_leader = CG == 2 ? mapa_u32(act_ready, 0) : act_ready;
@@ -320,13 +321,17 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
             tc_fence_before();
             fence_proxy_async_smem();
             arrive_act();
+            if (etid < TW_C) bias_s[etid] = __ldg(a.conv_bias + etid);     // stem biases (buffer 0)
 
             for (int l = 0; l < L; ++l) {
               const bool is_head = (l == L - 1);
               const bool is_conv1 = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 1);
-              const float* bias = a.conv_bias + (size_t)l * TW_C;
+              // this layer's biases were staged in shared memory while its MMAs ran (an LDG per chunk sat on the
+              // epilogue's critical path: 40 % of its stall samples); double buffered by layer parity
+              const float* bias = bias_s + (l & 1) * TW_C;
               mbar_wait(acc_full, acc_phase); acc_phase ^= 1;
               tc_fence_after();
+              epi_sync();
               for (int t = tile0; t < T; t += kTileStride) {
                 const int mi = t * 128 + quarter * 32 + lane;
                 const int p = pos_p[mi];
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                     float v[16];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                      const float4 bq = __ldg(b4 + q);
+                      const float4 bq = b4[q];
                       v[4 * q + 0] = fmaxf(__uint_as_float(r[4 * q + 0]) + bq.x, 0.0f);
                       v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + bq.y, 0.0f);
                       v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + bq.z, 0.0f);
@@ -388,13 +393,17 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                     if (real) {
 #pragma unroll
                       for (int j = 0; j < 16; ++j)
-                        dst[(size_t)(cc * 16 + j) * g.A] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + __ldg(bias + cc * 16 + j), 0.0f));
+                        dst[(size_t)(cc * 16 + j) * g.A] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + bias[cc * 16 + j], 0.0f));
                     }
                   }
                 }
               }
               tc_fence_before();
-              if (!is_head) { fence_proxy_async_smem(); arrive_act(); }
+              if (!is_head) {
+                fence_proxy_async_smem();
+                arrive_act();
+                if (etid < TW_C) bias_s[((l + 1) & 1) * TW_C + etid] = __ldg(a.conv_bias + (size_t)(l + 1) * TW_C + etid);
+              }
             }
           }
 

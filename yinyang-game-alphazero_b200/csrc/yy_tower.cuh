@@ -38,7 +38,8 @@ constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 157696
 constexpr int SM_POS = SM_RING + TW_STAGES * TW_STAGE_BYTES;          // position tables: padded position + (board, cell)
 constexpr int SM_BAR = SM_POS + 2 * 128 * TW_MAXT * 2;
 constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_STAGES + 2);   // full, empty, peer-full rings + acc_full, act_ready
-constexpr int SM_TOTAL = SM_TMEM + 16;
+constexpr int SM_BIAS = SM_TMEM + 16;                                 // current / next layer's 128 fp32 biases (double buffer)
+constexpr int SM_TOTAL = SM_BIAS + 2 * TW_C * 4;
 
 struct TowerGeo {
   int n, m, A, W, pitch, PB;  // PB = padded positions per board
