@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   for (int i = tid; i < (SM_POS - SM_ACT) / 4; i += TW_THREADS) reinterpret_cast<uint32_t*>(smem + SM_ACT)[i] = 0u;   // act + ring
   for (int i = tid; i < 128 * TW_MAXT; i += TW_THREADS) {
     int v = -1, p, b, y, x;
-    if (g.row_aligned) {
+    if (g.row_aligned == 2) {
+      const int t = i >> 7, r = i & 127;
+      b = t >> 1; y = r >> 3; x = 8 * (t & 1) + (r & 7); p = b * g.PB + y * g.pitch + x;
+    } else if (g.row_aligned) {
       const int R = (i >> 7) * 16 + ((i & 127) >> 3);
       x = i & 7; p = R * g.pitch + x; b = R / g.rows_per_board; y = R % g.rows_per_board;
     } else {
@@ -108,7 +111,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   // (+pitch+1: the taps of the last real position read that far; rows beyond the group's tiles may be stale)
   auto tiles_for = [&](long long b0, long long lim) {
     long long nb = lim - b0; if (nb > g.Gb) nb = g.Gb;
-    int t = g.row_aligned ? (int)((nb * g.rows_per_board + 15) >> 4) : (int)((nb * g.PB + g.pitch + 1 + 127) >> 7);
+    int t = g.row_aligned == 2 ? (int)(2 * nb)
+          : g.row_aligned ? (int)((nb * g.rows_per_board + 15) >> 4) : (int)((nb * g.PB + g.pitch + 1 + 127) >> 7);
     return t < g.T ? t : g.T;
   };
   auto batch_end = [&](long long bb0) { return (bb0 + a.batch_boards < run_end) ? bb0 + a.batch_boards : run_end; };   // structural
@@ -189,7 +193,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         if (CG == 2) tc_mma_bf16_2(d, ad, bd, idesc, acc); else tc_mma_bf16(d, ad, bd, idesc, acc);
       };
       auto commit = [&](uint32_t bar) { if (CG == 2) tc_commit2(bar); else tc_commit(bar); };
-      const uint64_t kTileDelta = (uint64_t)g.tile_adv;            // next M=128 tile, in 16-byte rows
+      uint64_t tile_delta[TW_MAXT];                                // start of M=128 tile t, in 16-byte rows
+#pragma unroll
+      for (int t = 0; t < TW_MAXT; ++t)
+        tile_delta[t] = g.row_aligned == 2 ? (uint64_t)((t >> 1) * g.PB + (t & 1) * 8) : (uint64_t)(t * g.tile_adv);
       constexpr uint64_t kK16DeltaA = (2u * TW_ROWS * 16u) >> 4;   // next K=16 slice: +2 channel chunks
       constexpr uint64_t kK16DeltaF = (2u * FC_LBO) >> 4;          // same for the FC feature panel
       for (int iter = 0; iter < a.iterations; ++iter) {
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
 #pragma unroll
                       for (int k = 0; k < 4; ++k) {
                         if (k < li.nk16)
-                          mma(tmem_base + (uint32_t)(t * 128), ad0 + (uint64_t)t * kTileDelta + (uint64_t)k * kK16DeltaA,
+                          mma(tmem_base + (uint32_t)(t * 128), ad0 + tile_delta[t] + (uint64_t)k * kK16DeltaA,
                               bd0 + (uint64_t)k * k16_delta_b, idesc, k > 0 ? 1u : acc0);
                       }
                     }

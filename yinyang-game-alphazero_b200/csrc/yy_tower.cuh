@@ -26,7 +26,7 @@ constexpr int TW_HEADC = 64;           // policy 32 + value 32 head-conv channel
 constexpr int TW_INC = 16;             // stem input channels after padding (K = 16 per tap)
 constexpr int TW_MAXT = 4;             // tiles (of 128 positions) per group
 constexpr int TW_PAD = 24;             // zero rows before/after the group's positions (>= m+2)
-constexpr int TW_ROWS = 616;            // activation rows: flat layout needs 512+2*24, row-aligned 24+64*9+10
+constexpr int TW_ROWS = 624;            // activation rows: flat layout 512+2*24, row-aligned 24+64*9+10, half-board tiles 24+2*289+18
 constexpr int TW_STAGES = 4;
 constexpr int TW_STAGE_BYTES = 16384;
 constexpr int TW_EPI_WARPS = 16;           // one (tile, TMEM-lane-quarter) pair per warp
@@ -49,18 +49,10 @@ struct TowerGeo {
   //  flat        : M row r of tile t is padded position t*128 + r            (SBO 128 B, any board width)
   //  row-aligned : (cols == 8) an 8-row MMA group is exactly one board row: M row r of tile t is padded position
   //                (16t + r/8)*pitch + r%8, SBO = pitch*16 B -- the zero column is skipped, 7 boards per 4 tiles
+  //  half-board  : (16 x 16, row_aligned == 2) tile t = columns [8(t%2), +8) of board t/2: M row r is padded position
+  //                (t/2)*PB + (r/8)*pitch + 8(t%2) + r%8, SBO = pitch*16 B -- neither the zero column nor the zero row
+  //                is an MMA row: 2 boards per 4 tiles, 100 % of the MMA rows are real cells
   int row_aligned, sbo_bytes, tile_adv, rows_per_board;
-};
-
-struct TowerArgs {
-  TowerGeo g;
-  const uint8_t* conv_stream;  // stage-ordered bf16 weight blocks
-  const float* conv_bias;      // [1 + 2*blocks][128] then head [64]
-  const uint64_t* black; const uint64_t* white;
-  long long count;
-  int boards_per_cta;          // boards are dealt to CTAs in contiguous runs; the last group of a run may be short
-  __nv_bfloat16* headfeat;     // [count][64*A], index c*A + cell (matches .view(-1, 32*n*m), neural_network.py:112,117)
-  long long* dbg;              // optional per-layer clock64 stamps of CTA 0's first group (developer tool), else nullptr
 };
 
 // ---- weight-stream geometry shared by producer and MMA issuer ----
@@ -152,6 +144,11 @@ inline TowerGeo make_tower_geo(int rows, int cols, int blocks) {
   g.n = rows; g.m = cols; g.A = rows * cols; g.W = words_for_cells(g.A); g.pitch = cols + 1; g.PB = (rows + 1) * (cols + 1);
   g.blocks = blocks;
   g.row_aligned = 0; g.sbo_bytes = 128; g.tile_adv = 128; g.rows_per_board = rows + 1;
+  if (cols == 16 && rows == 16) {                // half-board tiles: one M=128 tile = 16 board rows x 8 cells, every MMA row is
+    g.row_aligned = 2; g.sbo_bytes = g.pitch * 16; g.tile_adv = 0;   // a real cell; tile t starts at (t/2)*PB + (t%2)*8
+    g.T = TW_MAXT; g.Gb = TW_MAXT / 2;
+    return g;
+  }
   if (cols == 8 && rows + 1 <= 16 * TW_MAXT) {   // one board row == one 8-row MMA group
     g.row_aligned = 1; g.sbo_bytes = g.pitch * 16; g.tile_adv = 16 * g.pitch;
     g.T = TW_MAXT; g.Gb = (16 * TW_MAXT) / (rows + 1);
