@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   for (int i = tid; i < (SM_POS - SM_ACT) / 4; i += TW_THREADS) reinterpret_cast<uint32_t*>(smem + SM_ACT)[i] = 0u;   // act + ring
   for (int i = tid; i < 128 * TW_MAXT; i += TW_THREADS) {
     int v = -1, p, b, y, x;
-    if (g.row_aligned == 2) {
+    if (g.row_aligned == 3) {
+      const int t = i >> 7, j = (i & 127) >> 3;
+      x = i & 7; b = 2 * t + (j & 1); y = j >> 1; p = t * g.tile_adv + j * g.pitch + x;
+    } else if (g.row_aligned == 2) {
       const int t = i >> 7, r = i & 127;
       b = t >> 1; y = r >> 3; x = 8 * (t & 1) + (r & 7); p = b * g.PB + y * g.pitch + x;
     } else if (g.row_aligned) {
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   // (+pitch+1: the taps of the last real position read that far; rows beyond the group's tiles may be stale)
   auto tiles_for = [&](long long b0, long long lim) {
     long long nb = lim - b0; if (nb > g.Gb) nb = g.Gb;
-    int t = g.row_aligned == 2 ? (int)(2 * nb)
+    int t = g.row_aligned == 3 ? (int)((nb + 1) >> 1) : g.row_aligned == 2 ? (int)(2 * nb)
           : g.row_aligned ? (int)((nb * g.rows_per_board + 15) >> 4) : (int)((nb * g.PB + g.pitch + 1 + 127) >> 7);
     return t < g.T ? t : g.T;
   };
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           const long long slim = batch_end(bb0);
           for (long long b0 = bb0; b0 < slim; b0 += g.Gb) {
             for (int l = 0; l < L; ++l) {
-              const LayerInfo li = layer_info(l, g.blocks);
+              const LayerInfo li = layer_info(l, g.blocks, CG);
               const uint32_t bytes = (uint32_t)li.stage_bytes / CG;     // pair: my half of the stage's output channels
               const uint8_t* src = a.conv_stream + li.stream_off + (long long)rank * bytes;
               for (int j = 0; j < li.n_stages; ++j) push(src + (long long)j * li.stage_bytes, bytes);
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
           const long long slim = batch_end(bb0);
           for (long long b0 = bb0; b0 < slim; b0 += g.Gb)
-            for (int l = 0; l < L; ++l) { const int ns = layer_info(l, g.blocks).n_stages; for (int j = 0; j < ns; ++j) relay(); }
+            for (int l = 0; l < L; ++l) { const int ns = layer_info(l, g.blocks, CG).n_stages; for (int j = 0; j < ns; ++j) relay(); }
           for (int h = 0; h < 2; ++h)
             for (int p = 0; p < fc.n_panels; ++p) { const int ns = panel_stages(p) * fc_tiles(h); for (int j = 0; j < ns; ++j) relay(); }
         }
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           for (long long b0 = bb0; b0 < slim; b0 += g.Gb) {
             const int T = tiles_for(b0, slim);
             for (int l = 0; l < L; ++l) {
-              const LayerInfo li = layer_info(l, g.blocks);
+              const LayerInfo li = layer_info(l, g.blocks, CG);
               const bool preloaded = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 0);  // conv2: accumulator holds the skip input
               const uint32_t idesc = idesc_bf16(128 * CG, li.N);
               const uint32_t nrows_b = (uint32_t)li.N / CG;                          // weight rows staged per CTA
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
               for (int j = 0; j < li.n_stages; ++j, ++it) {
                 const uint32_t slot = it % TW_STAGES;
                 int tapshift, chunk0;
-                stage_info(l, j, g.blocks, g.pitch, tapshift, chunk0);
+                stage_info(l, j, g.blocks, g.pitch, g.dy_rows, CG, tapshift, chunk0);
                 wait_stage(slot, (it / TW_STAGES) & 1);
                 tc_fence_after();
                 const uint64_t ad0 = smem_desc(act_base + (uint32_t)((chunk0 * TW_ROWS + TW_PAD + tapshift) * 16), TW_ROWS * 16, (uint32_t)g.sbo_bytes);
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                   for (int t = 0; t < TW_MAXT; ++t) {
                     if (t < T) {
 #pragma unroll
-                      for (int k = 0; k < 4; ++k) {
+                      for (int k = 0; k < 4 * CG; ++k) {
                         if (k < li.nk16)
                           mma(tmem_base + (uint32_t)(t * 128), ad0 + tile_delta[t] + (uint64_t)k * kK16DeltaA,
                               bd0 + (uint64_t)k * k16_delta_b, idesc, k > 0 ? 1u : acc0);

@@ -26,8 +26,8 @@ constexpr int TW_HEADC = 64;           // policy 32 + value 32 head-conv channel
 constexpr int TW_INC = 16;             // stem input channels after padding (K = 16 per tap)
 constexpr int TW_MAXT = 4;             // tiles (of 128 positions) per group
 constexpr int TW_PAD = 24;             // zero rows before/after the group's positions (>= m+2)
-constexpr int TW_ROWS = 624;            // activation rows: flat layout 512+2*24, row-aligned 24+64*9+10, half-board tiles 24+2*289+18
-constexpr int TW_STAGES = 4;
+constexpr int TW_ROWS = 680;            // activation rows: flat 512+2*24, row-aligned 24+64*9+10, half-board 24+2*289+18, interleaved 24+4*162+8
+constexpr int TW_STAGES = 3;
 constexpr int TW_STAGE_BYTES = 16384;
 constexpr int TW_EPI_WARPS = 16;           // one (tile, TMEM-lane-quarter) pair per warp
 constexpr int TW_THREADS = 64 + 32 * TW_EPI_WARPS;
@@ -38,8 +38,9 @@ constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 157696
 constexpr int SM_POS = SM_RING + TW_STAGES * TW_STAGE_BYTES;          // position tables: padded position + (board, cell)
 constexpr int SM_BAR = SM_POS + 2 * 128 * TW_MAXT * 2;
 constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_STAGES + 2);   // full, empty, peer-full rings + acc_full, act_ready
-constexpr int SM_BIAS = SM_TMEM + 16;                                 // current / next layer's 128 fp32 biases (double buffer)
+constexpr int SM_BIAS = (SM_TMEM + 16 + 15) & ~15;                                 // current / next layer's 128 fp32 biases (double buffer)
 constexpr int SM_TOTAL = SM_BIAS + 2 * TW_C * 4;
+static_assert(SM_TOTAL <= 232448, "persistent kernel exceeds the 227 KB opt-in shared memory of sm_100");
 
 struct TowerGeo {
   int n, m, A, W, pitch, PB;  // PB = padded positions per board
@@ -52,17 +53,33 @@ struct TowerGeo {
   //  half-board  : (16 x 16, row_aligned == 2) tile t = columns [8(t%2), +8) of board t/2: M row r is padded position
   //                (t/2)*PB + (r/8)*pitch + 8(t%2) + r%8, SBO = pitch*16 B -- neither the zero column nor the zero row
   //                is an MMA row: 2 boards per 4 tiles, 100 % of the MMA rows are real cells
+  //  interleaved : (8 x 8, row_aligned == 3) the rows of two boards alternate: row group j of tile t is row j/2 of
+  //                board 2t + j%2, at padded position 162t + 9j; two zero row groups separate consecutive pairs and a
+  //                vertical tap moves TWO row groups (dy_rows = 18).  No zero row is an MMA row: 8 boards per 4 tiles,
+  //                100 % of the MMA rows are real cells (row-aligned: 7 boards, 87.5 %)
   int row_aligned, sbo_bytes, tile_adv, rows_per_board;
+  int dy_rows;                // padded positions between vertically adjacent cells (pitch, or 2*pitch when interleaved)
 };
 
 // ---- weight-stream geometry shared by producer and MMA issuer ----
 struct LayerInfo { int n_stages, stage_bytes, nk16, N; long long stream_off; };
-__host__ __device__ inline LayerInfo layer_info(int l, int blocks) {
+// `stage_bytes` is what the stream holds per stage; a CTA of a pair (cg = 2) stages half of it (its half of the output
+// channels).  Single CTA: a stage is one 64-channel slab of one tap (16 KB).  Pair: a stage is one whole tap (K = 128,
+// 2 x 16 KB), so a ring slot still carries 16 KB per CTA and feeds 32 MMAs.
+__host__ __device__ inline LayerInfo layer_info(int l, int blocks, int cg = 1) {
   LayerInfo li;
   const long long stem = 9ll * (2 * 128 * 16);
+  const long long conv = 18ll * TW_STAGE_BYTES;    // bytes of one 3x3 conv layer, either way
   if (l == 0) { li.n_stages = 9; li.stage_bytes = 2 * 128 * 16; li.nk16 = 1; li.N = 128; li.stream_off = 0; }
-  else if (l <= 2 * blocks) { li.n_stages = 18; li.stage_bytes = TW_STAGE_BYTES; li.nk16 = 4; li.N = 128; li.stream_off = stem + (long long)(l - 1) * 18 * TW_STAGE_BYTES; }
-  else { li.n_stages = 2; li.stage_bytes = 8 * TW_HEADC * 16; li.nk16 = 4; li.N = TW_HEADC; li.stream_off = stem + (long long)(2 * blocks) * 18 * TW_STAGE_BYTES; }
+  else if (l <= 2 * blocks) {
+    li.N = 128; li.stream_off = stem + (long long)(l - 1) * conv;
+    if (cg == 2) { li.n_stages = 9; li.stage_bytes = 2 * TW_STAGE_BYTES; li.nk16 = 8; }
+    else { li.n_stages = 18; li.stage_bytes = TW_STAGE_BYTES; li.nk16 = 4; }
+  } else {
+    li.N = TW_HEADC; li.stream_off = stem + (long long)(2 * blocks) * conv;
+    if (cg == 2) { li.n_stages = 1; li.stage_bytes = 16 * TW_HEADC * 16; li.nk16 = 8; }
+    else { li.n_stages = 2; li.stage_bytes = 8 * TW_HEADC * 16; li.nk16 = 4; }
+  }
   return li;
 }
 __host__ __device__ inline long long conv_stream_bytes(int blocks) {
@@ -70,12 +87,12 @@ __host__ __device__ inline long long conv_stream_bytes(int blocks) {
   return li.stream_off + (long long)li.n_stages * li.stage_bytes;
 }
 // stage j of layer l: which 3x3 tap and which first activation chunk it covers
-__device__ __forceinline__ void stage_info(int l, int j, int blocks, int pitch, int& tapshift, int& chunk0) {
+__device__ __forceinline__ void stage_info(int l, int j, int blocks, int pitch, int dy_rows, int cg, int& tapshift, int& chunk0) {
   int tap, slab;
   if (l == 0) { tap = j; slab = 0; }
-  else if (l <= 2 * blocks) { tap = j >> 1; slab = j & 1; }
-  else { tap = 4; slab = j; }
-  tapshift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
+  else if (l <= 2 * blocks) { if (cg == 2) { tap = j; slab = 0; } else { tap = j >> 1; slab = j & 1; } }
+  else { tap = 4; slab = cg == 2 ? 0 : j; }
+  tapshift = (tap / 3 - 1) * dy_rows + (tap % 3 - 1);
   chunk0 = slab * 8;
 }
 
@@ -143,7 +160,12 @@ inline TowerGeo make_tower_geo(int rows, int cols, int blocks) {
   TowerGeo g;
   g.n = rows; g.m = cols; g.A = rows * cols; g.W = words_for_cells(g.A); g.pitch = cols + 1; g.PB = (rows + 1) * (cols + 1);
   g.blocks = blocks;
-  g.row_aligned = 0; g.sbo_bytes = 128; g.tile_adv = 128; g.rows_per_board = rows + 1;
+  g.row_aligned = 0; g.sbo_bytes = 128; g.tile_adv = 128; g.rows_per_board = rows + 1; g.dy_rows = g.pitch;
+  if (cols == 8 && rows == 8) {                  // interleaved board pairs: one M=128 tile = 2 boards, every MMA row a real cell
+    g.row_aligned = 3; g.sbo_bytes = g.pitch * 16; g.tile_adv = 18 * g.pitch; g.dy_rows = 2 * g.pitch;
+    g.T = TW_MAXT; g.Gb = 2 * TW_MAXT;
+    return g;
+  }
   if (cols == 16 && rows == 16) {                // half-board tiles: one M=128 tile = 16 board rows x 8 cells, every MMA row is
     g.row_aligned = 2; g.sbo_bytes = g.pitch * 16; g.tile_adv = 0;   // a real cell; tile t starts at (t/2)*PB + (t%2)*8
     g.T = TW_MAXT; g.Gb = TW_MAXT / 2;

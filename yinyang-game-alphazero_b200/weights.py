@@ -140,13 +140,13 @@ def pack_state_dict(state_dict, rows: int, cols: int) -> np.ndarray:
     s = np.concatenate(stream).view(np.uint8)
     assert s.size <= lay["conv_bias"] - lay["conv_stream"], (s.size, lay)
     img[lay["conv_stream"]: lay["conv_stream"] + s.size] = s
-    # CTA-pair kernel: every stage block [kc][oc][8] becomes [half][kc][oc/2][8] (each CTA stages its half of the output channels)
+    # CTA-pair kernel: a stage is one whole tap (or the whole 1x1 head conv), [kc][oc][8] over ALL its K chunks, split
+    # into the two CTAs' halves of the output channels: [half][kc][oc/2][8]  (csrc/yy_tower.cuh layer_info, cg = 2)
     halves = []
     for i, blk in enumerate(stream):
         oc = HEAD_C if i == len(stream) - 1 else TOWER_C
-        kc = 2 if i < 9 else 8                               # K chunks per stage: stem taps have K = 16, the rest K = 64
-        b4 = blk.reshape(-1, kc, oc, 8)                      # [stage][kc][oc][8]
-        halves.append(np.ascontiguousarray(np.stack([b4[:, :, : oc // 2], b4[:, :, oc // 2:]], axis=1)).reshape(-1))
+        b3 = blk.reshape(-1, oc, 8)                          # slabs of a tap are consecutive K chunks -> [kc_total][oc][8]
+        halves.append(np.ascontiguousarray(np.stack([b3[:, : oc // 2], b3[:, oc // 2:]], axis=0)).reshape(-1))
     s2 = np.concatenate(halves).view(np.uint8)
     assert s2.size == s.size
     img[lay["conv_stream_pair"]: lay["conv_stream_pair"] + s2.size] = s2
