@@ -3,7 +3,8 @@
 // over YinYangLogic (src/yin_yang/yin_yang_logic.py:24-134).
 //
 // Roofline: HBM.  Algorithmic bytes per env step = 6*ceil(A/8)+4 (52 B at 8x8); the kernels are
-// a few hundred integer ops per board, so at 65,536 boards they are launch/latency bound, not bandwidth bound.
+// ~2,600 dependent integer instructions per warp (flood fills), so at 65,536 boards (14 warps per SM) they are
+// latency bound -- 15 us, of which the SMs are busy 10 -- and at 1 M boards integer-issue bound (10.8 G steps/s).
 #include "yy_common.cuh"
 
 namespace yy {
@@ -52,12 +53,40 @@ ended_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint64_
   out[i] = (int8_t)ended_code(g, b, w, players[i] == 1 ? 1 : -1);
 }
 
+// Fused getValidMoves + getNextState + getGameEnded.  The flood fills make the work per board data dependent (it
+// grows with the number of stones), and a batch usually mixes game stages: with one thread per board in input order
+// only 9 of 32 lanes were active per issued instruction (ncu, BASELINE configs[1]).  Each block therefore first
+// counting-sorts its boards by stone count in shared memory and hands them to the threads in that order, so the
+// lanes of a warp get boards of similar cost; results go back to the boards' own slots.
+constexpr int kEnvBlock = 256;              // (one 448-thread block per SM, a single balanced wave, was no faster at 65,536
+constexpr int kEnvBins = 64;                //  boards and slower at 1 M: the longest warp, not the tail, sets the latency)
+
 template <int NW>
-__global__ void __launch_bounds__(kRulesBlock)
+__global__ void __launch_bounds__(kEnvBlock)
 env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __restrict__ white,
                 int8_t* __restrict__ players, const int32_t* __restrict__ actions, uint64_t* __restrict__ out_mask,
                 int8_t* __restrict__ out_result, long long count) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_hist[kEnvBins + 1];
+  __shared__ int s_off[kEnvBins + 1];
+  __shared__ uint16_t s_order[kEnvBlock];     // sorted position -> thread whose board it is
+  const int tid = threadIdx.x;
+  const long long base = (long long)blockIdx.x * blockDim.x;
+  const long long mine = base + tid;
+  if (tid <= kEnvBins) s_hist[tid] = 0;
+  __syncthreads();
+  int key = kEnvBins;                         // threads past the end sort last
+  if (mine < count) {
+    int stones = 0;
+    for (int k = 0; k < W; ++k) stones += popc64(black[mine * W + k] | white[mine * W + k]);
+    key = stones * kEnvBins / (g.cells + 1);
+  }
+  const int rank = atomicAdd(&s_hist[key], 1);
+  __syncthreads();
+  if (tid == 0) { int acc = 0; for (int k = 0; k <= kEnvBins; ++k) { s_off[k] = acc; acc += s_hist[k]; } }
+  __syncthreads();
+  s_order[s_off[key] + rank] = (uint16_t)tid;
+  __syncthreads();
+  const long long i = base + s_order[tid];
   if (i >= count) return;
   BB<NW> b = load_bb<NW>(black, i, W) & g.full, w = load_bb<NW>(white, i, W) & g.full;
   int p = players[i] == 1 ? 1 : -1;
@@ -159,8 +188,8 @@ int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64
   int rc = check_rules_args(rows, cols, count); if (rc) return rc;
   if (count == 0) return YY_OK;
   int cells = rows * cols, W = words_for_cells(cells);
-  unsigned grid = (unsigned)((count + kRulesBlock - 1) / kRulesBlock);
-  YY_DISPATCH_NW(cells, env_step_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
+  unsigned grid = (unsigned)((count + kEnvBlock - 1) / kEnvBlock);
+  YY_DISPATCH_NW(cells, env_step_kernel<NW><<<grid, kEnvBlock, 0, (cudaStream_t)stream>>>(
       make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count));
   YY_LAUNCH_CHECK();
   return YY_OK;
