@@ -232,6 +232,21 @@ const uint64_t *yy_engine_game_black(yy_engine *e);
 const uint64_t *yy_engine_game_white(yy_engine *e);
 const int8_t *yy_engine_game_player(yy_engine *e);
 
+/* ---------------------------------------------------------------------------------------------
+ * Replay records -> training tensors.  Replaces create_dataset_from_games /
+ * DataProcessor.preprocess_sample / augment_sample (src/yin_yang/ai/data_utils.py:16-215) over
+ * board_to_input (neural_network.py:156-196) for a whole replay buffer at once.  Per record r the 8 forms of
+ * augment_sample, in its order (identity, rot90 x1/x2/x3, flip left-right, flip up-down, transpose,
+ * anti-transpose), sample index 8r + form:
+ *   out_planes float32[8*count][5][n][m], out_policy float32[8*count][A], out_values float32[8*count] (optional).
+ * Policy source: counts uint16[count][A] (visit counts: policy = counts / sum in float64, uniform when the sum
+ * is 0 -- Node.get_children_distribution at temperature 1, mcts.py:183-215 -- rounded to float32 like
+ * torch.FloatTensor(policy), data_utils.py:34) or, when counts is NULL, policy float32[count][A] as is.
+ * Square boards only (the reference rotates by 90 degrees).  Bit-exact against the reference. */
+int yy_augment_samples(int rows, int cols, const uint64_t *black_dev, const uint64_t *white_dev,
+                       const uint16_t *counts_dev, const float *policy_dev, const float *values_dev, int64_t count,
+                       float *out_planes_dev, float *out_policy_dev, float *out_values_dev, void *stream);
+
 /* tcgen05 self-test used by tests/ (C = A[M,K] * B[N,K]^T, bf16 in / fp32 out, operands in the
  * same no-swizzle K-major core-matrix layout the tower kernel uses).  Layout: csrc/yy_probe.cu. */
 int yy_probe_umma(const void *a_dev, const void *b_dev, float *c_dev, int M, int N, int K, int a_row_offset,

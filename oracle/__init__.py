@@ -155,3 +155,44 @@ def mcts_search(board, player, n, m, num_sims, cpuct=1.0, rule_flags=0, noise=No
                               _p(counts, ctypes.c_int32), _p(cw, ctypes.c_float), _p(stats, ctypes.c_int32))
     return {"counts": counts, "child_w": cw, "n_evals": int(ne),
             "n_nodes": int(stats[0]), "max_depth": int(stats[1]), "root_visits": int(stats[2])}
+
+
+# ---------------------------------------------------------------------------------------- dataset / augmentation
+def input_planes(boards, n, m) -> np.ndarray:
+    """board_to_input (src/yin_yang/ai/neural_network.py:156-196) for int8[N,n,m] boards -> float32[N,5,n,m]."""
+    b = _boards(boards, n, m).reshape(-1, n, m)
+    occ = b != 0
+    x = np.zeros((b.shape[0], 5, n, m), dtype=np.float32)
+    x[:, 0] = b == 0
+    x[:, 1] = b == 1
+    x[:, 2] = b == -1
+    x[:, 3] = (occ.sum(axis=2) / m)[:, :, None]        # python float (float64) stored into a float32 tensor
+    x[:, 4] = (occ.sum(axis=1) / n)[:, None, :]
+    return x
+
+
+def _symmetries(g: np.ndarray):
+    """The 8 forms in the order of DataProcessor.augment_sample (data_utils.py:39-134) of an array [..., n, m]."""
+    t = np.swapaxes(g, -1, -2)
+    return [g, np.rot90(g, 1, axes=(-2, -1)), np.rot90(g, 2, axes=(-2, -1)), np.rot90(g, 3, axes=(-2, -1)),
+            np.flip(g, -1), np.flip(g, -2), t, np.flip(t, (-2, -1))]
+
+
+def augment_dataset(boards, counts, values, n, m):
+    """create_dataset_from_games(..., augment=True) (data_utils.py:182-215) for visit-count policies:
+    policy = counts / sum in float64 (uniform 1/A when the sum is 0: mcts.py:209-213), torch.FloatTensor'ed to
+    float32 (data_utils.py:34), then for every record the 8 symmetric copies of planes and policy, the value
+    replicated.  Returns (planes f32[8N,5,n,m], policies f32[8N,A], values f32[8N]); sample index = 8*record + form."""
+    if n != m:
+        raise ValueError("the reference's augmentation rotates by 90 degrees: square boards only")
+    A = n * m
+    c = np.asarray(counts, dtype=np.float64).reshape(-1, A)
+    tot = c.sum(axis=1, keepdims=True)
+    pi = np.where(tot > 0, c / np.maximum(tot, 1.0), 1.0 / A).astype(np.float32)
+    x = input_planes(boards, n, m)
+    N = x.shape[0]
+    grid = pi.reshape(N, n, m)
+    planes = np.stack(_symmetries(x), axis=1).reshape(N * 8, 5, n, m)
+    policies = np.stack(_symmetries(grid), axis=1).reshape(N * 8, A)
+    vals = np.repeat(np.asarray(values, dtype=np.float64).astype(np.float32), 8)
+    return np.ascontiguousarray(planes, dtype=np.float32), np.ascontiguousarray(policies, dtype=np.float32), vals

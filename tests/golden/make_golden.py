@@ -14,6 +14,9 @@ What is pinned
                      src/yin_yang/ai/mcts.py driven through a value-semantics Game adapter
                      (getNextState deep-copies) with the deterministic hash-stub
                      evaluator (dyadic priors / values)
+  augment_*.npz      data_utils.create_dataset_from_games (preprocess_sample + augment_sample: the 8 symmetric
+                     copies of the input planes and of the policy, and the replicated value) on random-play
+                     boards with visit-count policies   (data_utils.py:16-215)
   net_*.npz          a small YinYangNeuralNetwork (random weights AND random BN statistics):
                      state_dict, board_to_input planes, forward logits/value, predict()
 The reference modules open *.log files in the CWD on import -> run from a scratch dir.
@@ -216,8 +219,37 @@ def make_net(name, n, m, channels, blocks, seed):
     print(f"net {name}: params={sum(v.size for v in sd.values())}")
 
 
+def make_augment(name, n, m, count, seed):
+    from src.yin_yang.ai.data_utils import create_dataset_from_games
+    rng = np.random.default_rng(seed)
+    game = YinYangGame(n, m)
+    boards, counts, values, data = [], [], [], []
+    for i in range(count):
+        b, player = random_play_board(game, rng, int(rng.integers(0, n * m)))
+        mask = game.getValidMoves(b, player)
+        c = (rng.integers(0, 200, size=n * m) * (rng.random(n * m) < 0.6) * (mask > 0)).astype(np.uint16)
+        if i % 7 == 3:
+            c[:] = 0                                              # no visits at all: uniform fallback (mcts.py:211-213)
+        tot = float(c.sum())
+        pi = c.astype(np.float64) / tot if tot > 0 else np.ones(n * m) / (n * m)   # get_children_distribution, temperature 1
+        z = float(rng.choice([1.0, -1.0, 0.0001, -0.0001]))
+        boards.append(b.get_board().copy()); counts.append(c); values.append(z)
+        data.append((b, pi, z))
+    bt, pt, vt = create_dataset_from_games(data, game, augment=True)
+    np.savez_compressed(os.path.join(OUT, f"augment_{name}.npz"), n=n, m=m, boards=np.array(boards, dtype=np.int8),
+                        counts=np.array(counts, dtype=np.uint16), values=np.array(values, dtype=np.float64),
+                        planes=np.stack([t.numpy() for t in bt]).astype(np.float32),
+                        policies=np.stack([t.numpy() for t in pt]).astype(np.float32),
+                        out_values=np.stack([t.numpy() for t in vt]).astype(np.float32)[:, 0])
+    print(f"augment {name}: {count} records -> {len(bt)} samples")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rules", "mcts", "net"]
+    which = sys.argv[1:] or ["rules", "mcts", "net", "augment"]
+    if "augment" in which:
+        make_augment("6x6", 6, 6, 24, 21)
+        make_augment("8x8", 8, 8, 40, 22)
+        make_augment("16x16", 16, 16, 6, 23)
     if "rules" in which:
         make_rules(4, 4, 120, 120, 1)
         make_rules(6, 6, 200, 150, 2)

@@ -111,3 +111,32 @@ def test_generate_self_play_data_and_cli(pkg, tmp_path):
                                  "--model-dir", str(model_dir), "--data-dir", str(data_dir)]) == 0
     assert train_alphazero.main(["--mode", "self-play", "--model-dir", str(tmp_path / "none"), "--data-dir", str(data_dir)]) == 1
     assert len([f for f in os.listdir(data_dir) if f.endswith(".npz")]) >= 1
+
+
+def test_data_utils_facade_matches_reference_golden(pkg):
+    """create_dataset_from_games / DataProcessor with the reference's signatures (data_utils.py:7-215)."""
+    import torch
+    from conftest import load_golden
+    from yinyang_game_alphazero_b200 import data_utils
+    g = load_golden("augment_6x6.npz")
+    n, m = int(g["n"]), int(g["m"])
+    game = pkg["game"].YinYangGame(n, m)
+    data = []
+    for b, c, z in zip(g["boards"], g["counts"], g["values"]):
+        tot = float(c.sum())
+        pi = c.astype(np.float64) / tot if tot > 0 else np.ones(n * m) / (n * m)
+        board = game.getInitBoard()
+        board.board[:] = b
+        data.append((board, pi, float(z)))
+    bt, pt, vt = data_utils.create_dataset_from_games(data, game, augment=True)
+    assert len(bt) == len(pt) == len(vt) == 8 * len(data)
+    assert bt[0].shape == (5, n, m) and pt[0].shape == (n * m,) and vt[0].shape == (1,)
+    assert np.array_equal(torch.stack(bt).numpy(), g["planes"])
+    assert np.array_equal(torch.stack(pt).numpy(), g["policies"])
+    assert np.array_equal(torch.cat(vt).numpy(), g["out_values"])
+    bt1, pt1, vt1 = data_utils.create_dataset_from_games(data, game, augment=False)
+    assert len(bt1) == len(data) and np.array_equal(torch.stack(bt1).numpy(), g["planes"][0::8])
+    proc = data_utils.DataProcessor(game)
+    x, p = proc.preprocess_sample(data[0][0], data[0][1], 1)
+    forms = proc.augment_sample(x, p)                       # the reference passes the plane tensor here
+    assert len(forms) == 8 and np.array_equal(forms[3][0].numpy(), g["planes"][3]) and np.array_equal(forms[3][1].numpy(), g["policies"][3])

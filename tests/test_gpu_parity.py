@@ -297,6 +297,44 @@ def test_network_search_persistent_vs_step_kernels(eng, oracle_mod):
     assert np.array_equal(c0, c1) and np.array_equal(w0, w1)
 
 
+# ------------------------------------------------------------------------------------------------ dataset / augmentation
+@pytest.mark.parametrize("name", golden_files("augment_"))
+def test_augmentation_matches_reference_golden(eng, name):
+    """yy_augment_samples vs create_dataset_from_games of the unmodified reference (data_utils.py:182-215): float32
+    planes, policies and values of all 8 forms, bit for bit; both policy sources (visit counts / float32 policy)."""
+    g = load_golden(name)
+    n, m = int(g["n"]), int(g["m"])
+    planes, pol, vals = eng.augment_samples_host(g["boards"], n, m, counts=g["counts"], values=g["values"])
+    assert np.array_equal(planes, g["planes"]) and np.array_equal(pol, g["policies"]) and np.array_equal(vals, g["out_values"])
+    planes2, pol2, _ = eng.augment_samples_host(g["boards"], n, m, policy=g["policies"][0::8])
+    assert np.array_equal(planes2, g["planes"]) and np.array_equal(pol2, g["policies"])
+
+
+@pytest.mark.parametrize("shape,count", [((8, 8), 5000), ((6, 6), 777), ((16, 16), 300), ((3, 3), 33), ((8, 8), 0)])
+def test_augmentation_matches_oracle(eng, oracle_mod, shape, count):
+    n, m = shape
+    rng = np.random.default_rng(n * 100 + count)
+    boards = rng.integers(-1, 2, size=(count, n, m)).astype(np.int8)
+    counts = (rng.integers(0, 65535, size=(count, n * m)) * (rng.random((count, n * m)) < 0.5)).astype(np.uint16)
+    if count:
+        counts[::11] = 0
+    values = rng.choice([1.0, -1.0, 0.0001], size=count)
+    planes, pol, vals = eng.augment_samples_host(boards, n, m, counts=counts, values=values)
+    rp, rq, rv = oracle_mod.augment_dataset(boards, counts, values, n, m)
+    assert planes.shape == rp.shape and np.array_equal(planes, rp)
+    assert np.array_equal(pol, rq) and np.array_equal(vals, rv)
+    # size-independent properties: every form is a permutation of the identity form; policies still sum to one
+    if count:
+        assert np.array_equal(np.sort(pol.reshape(count, 8, -1), axis=2), np.sort(pol.reshape(count, 8, -1)[:, :1], axis=2).repeat(8, 1))
+        np.testing.assert_allclose(pol.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_augmentation_rejects_non_square(eng):
+    from yinyang_game_alphazero_b200 import YinYangError
+    with pytest.raises(YinYangError):
+        eng.augment_samples_host(np.zeros((2, 5, 7), np.int8), 5, 7, counts=np.ones((2, 35), np.uint16))
+
+
 # ------------------------------------------------------------------------------------------------ self-play driver
 def test_selfplay_records_match_oracle_search(eng, oracle_mod):
     """Every replay record's visit counts must equal the oracle's search from that record's board (noise off,

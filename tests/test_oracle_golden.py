@@ -82,3 +82,15 @@ def test_stub_evaluator_spec(oracle_mod):
     assert pol.dtype == np.float32 and np.all(pol > 0) and np.all(pol <= 4096 / 65536)
     assert np.all(pol * 65536 == np.round(pol * 65536))        # dyadic
     assert -1.0 <= float(val) < 1.0 and float(val) * 65536 == round(float(val) * 65536)
+
+
+@pytest.mark.parametrize("name", golden_files("augment_"))
+def test_oracle_augmentation_matches_reference(oracle_mod, name):
+    """create_dataset_from_games / DataProcessor.augment_sample (data_utils.py:39-215): bit-exact float32 planes,
+    policies and values for all 8 symmetric forms."""
+    g = load_golden(name)
+    n, m = int(g["n"]), int(g["m"])
+    planes, policies, values = oracle_mod.augment_dataset(g["boards"], g["counts"], g["values"], n, m)
+    assert np.array_equal(planes, g["planes"])
+    assert np.array_equal(policies, g["policies"])
+    assert np.array_equal(values, g["out_values"])

@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libyinyang_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "yinyang_b200.h")
-SOURCES = ["yy_rules_kernels.cu", "yy_tree.cu", "yy_probe.cu", "yy_nn.cu", "yy_fused.cu"]
+SOURCES = ["yy_rules_kernels.cu", "yy_tree.cu", "yy_probe.cu", "yy_nn.cu", "yy_fused.cu", "yy_dataset.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
@@ -120,6 +120,7 @@ SIGNATURES = {
     "yy_engine_game_black": (_P, [_P]),
     "yy_engine_game_white": (_P, [_P]),
     "yy_engine_game_player": (_P, [_P]),
+    "yy_augment_samples": (_I, [_I, _I, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "yy_probe_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 

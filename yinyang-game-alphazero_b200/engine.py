@@ -94,6 +94,44 @@ def env_step(black, white, players, actions, rows, cols, rule_flags=0, out_mask=
     return out_mask, out_result
 
 
+def augment_samples(black, white, rows, cols, counts=None, policy=None, values=None):
+    """Replay records -> training tensors with the reference's 8-fold augmentation (yy_augment_samples; replaces
+    data_utils.create_dataset_from_games).  Device tensors in: black/white int64[N,W], counts int16/uint16[N,A] (visit
+    counts) or policy float32[N,A], values float32[N] (optional).  Returns device tensors
+    (planes float32[8N,5,n,m], policy float32[8N,A], values float32[8N] or None); sample 8r+f = form f of record r."""
+    _require_cuda()
+    if (counts is None) == (policy is None):
+        raise ValueError("give exactly one of counts / policy")
+    n = black.shape[0]
+    A = rows * cols
+    dev = black.device
+    planes = torch.empty((8 * n, 5, rows, cols), dtype=torch.float32, device=dev)
+    pol = torch.empty((8 * n, A), dtype=torch.float32, device=dev)
+    vals = torch.empty(8 * n, dtype=torch.float32, device=dev) if values is not None else None
+    if counts is not None:
+        counts = counts.contiguous()
+        assert counts.element_size() == 2 and counts.numel() == n * A
+    if policy is not None:
+        policy = policy.to(torch.float32).contiguous()
+        assert policy.numel() == n * A
+    if values is not None:
+        values = values.to(torch.float32).contiguous()
+    _lib.check(_lib.lib().yy_augment_samples(rows, cols, _ptr(black), _ptr(white), _ptr(counts), _ptr(policy), _ptr(values),
+                                             n, _ptr(planes), _ptr(pol), _ptr(vals), _stream()))
+    return planes, pol, vals
+
+
+def augment_samples_host(boards, rows, cols, counts=None, policy=None, values=None):
+    """numpy in / numpy out variant of augment_samples (H2D + kernel + D2H)."""
+    _require_cuda()
+    b, w = bitboard.pack_boards(boards, rows, cols)
+    c = _to_dev(np.ascontiguousarray(counts, dtype=np.uint16).view(np.int16), torch.int16) if counts is not None else None
+    p = _to_dev(np.ascontiguousarray(policy, dtype=np.float32), torch.float32) if policy is not None else None
+    v = _to_dev(np.ascontiguousarray(values, dtype=np.float64).astype(np.float32), torch.float32) if values is not None else None
+    planes, pol, vals = augment_samples(_to_dev(b, torch.int64), _to_dev(w, torch.int64), rows, cols, counts=c, policy=p, values=v)
+    return planes.cpu().numpy(), pol.cpu().numpy(), (vals.cpu().numpy() if vals is not None else None)
+
+
 def random_playout(count, plies, rows, cols, seed=0xC0FFEE, rule_flags=0, device="cuda"):
     """Synthetic boards: board i = empty board advanced by plies[i] uniformly random legal plies."""
     _require_cuda()
