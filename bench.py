@@ -232,6 +232,7 @@ def run_b200(args):
 
     # ---- env steps/s (BASELINE.json configs[1]): 65,536 synthetic random-play boards on this GPU
     env = bench_env(engine, torch, peaks) if rank == 0 else None
+    dataset = bench_dataset(engine, torch, peaks) if rank == 0 else None
 
     if rank == 0:
         tower_s = prof["ms"] * 1e-3 / max(1, prof["launches"])
@@ -260,7 +261,7 @@ def run_b200(args):
                 "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "api": "Engine.search_host + next_state_host (numpy in/out)"},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "env": env,
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "env": env, "dataset": dataset,
                 "moves_per_s_roofline": peaks["bf16_tflops_sustained"] * 1e12 / ((SIMS + 1) * FLOPS_PER_LEAF) * world,
                 "leaf_evals_per_s": (SIMS + 1) * value,
                 "nccl": {"weight_broadcast_s": t_bcast, "replay_gather_s": t_gather, "replay_records_gathered": int(n_records)},
@@ -346,6 +347,33 @@ def emit(line):
         sys.stdout.write(data.decode()); sys.stdout.flush()
     else:
         os.write(_JSON_FD, data)
+
+
+def bench_dataset(engine, torch, peaks):
+    """replay records -> training tensors with the 8-fold augmentation (yy_augment_samples), HBM bound."""
+    n_rec = 262144                                           # 3.2 GB of output per launch: far larger than L2
+    plies = torch.arange(n_rec, dtype=torch.int32) % 52
+    black, white, _ = engine.random_playout(n_rec, plies, ROWS, COLS, seed=0xDA7A)
+    counts = torch.randint(0, 800, (n_rec, A), dtype=torch.int16, device="cuda")
+    values = torch.ones(n_rec, dtype=torch.float32, device="cuda")
+    out = engine.augment_samples(black, white, ROWS, COLS, counts=counts, values=values)
+    del out
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    ev0.record()
+    for _ in range(reps):
+        out = engine.augment_samples(black, white, ROWS, COLS, counts=counts, values=values)
+        del out
+    ev1.record(); torch.cuda.synchronize()
+    sec = ev0.elapsed_time(ev1) * 1e-3 / reps
+    bytes_per_record = 16 + 2 * A + 4 + 8 * (6 * A + 1) * 4
+    gbs = bytes_per_record * n_rec / sec / 1e9
+    return {"metric": "augmented training samples/sec (8x8, 8 forms per replay record)", "value": 8 * n_rec / sec, "unit": "samples/s",
+            "records": n_rec, "ms_per_launch": sec * 1e3,
+            "roofline": {"bound": "hbm", "kernel": "augment_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_record": bytes_per_record},
+            "l2_policy": "outputs (3.2 GB per launch) larger than L2; the timing includes torch's allocation of the outputs"}
 
 
 def main():

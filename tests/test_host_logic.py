@@ -152,3 +152,43 @@ def test_bf16_rounding_helper(yy):
     x = np.random.default_rng(0).standard_normal(4096).astype(np.float32)
     ref = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
     assert np.array_equal(weights.to_bf16_bits(x), ref)
+
+
+def test_reference_wire_format_loads_in_the_reference(yy, tmp_path):
+    """wire="reference": the .npz written by the facade must load in the UNMODIFIED reference's TrainingDataQueue
+    (training_pipeline.py:55-73) in a process that cannot import this package; boards come back as the reference's
+    own YinYangLogic.  Needs /root/reference (build container only)."""
+    import subprocess
+    import sys
+    ref = os.environ.get("YY_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src", "yin_yang")):
+        pytest.skip("reference tree not present")
+    from yinyang_game_alphazero_b200 import game as game_mod, self_play
+    rng = np.random.default_rng(0)
+    examples = []
+    for i in range(5):
+        b = game_mod.YinYangLogic(6, 6)
+        b.board = rng.integers(-1, 2, size=(6, 6)).astype(np.int8)
+        pi = rng.random(36); pi /= pi.sum()
+        examples.append((b, pi, [1, -1, 0.0001][i % 3]))
+    path = str(tmp_path / "self_play_data_1.npz")
+    self_play.save_examples(path, examples, 36, wire="reference")
+    assert "src.yin_yang.yin_yang_logic" not in sys.modules or hasattr(sys.modules["src.yin_yang.yin_yang_logic"], "__file__")
+    code = (
+        "import sys, logging, numpy as np; logging.disable(logging.CRITICAL); sys.path.insert(0, %r)\n"
+        "from src.yin_yang.ai.training_pipeline import TrainingDataQueue\n"
+        "from src.yin_yang.yin_yang_logic import YinYangLogic\n"
+        "q = TrainingDataQueue(100, 10); q.push_file(%r)\n"
+        "assert len(q) == 5\n"
+        "b, pi, v = q.queue[1]\n"
+        "assert type(b) is YinYangLogic and b.n == 6 and b.get_board().shape == (6, 6) and pi.shape == (36,)\n"
+        "assert 'yy_b200' not in sys.modules\n"
+        "print('ok', int(b.get_board().sum()), float(v))\n" % (ref, path))
+    r = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True,
+                       env={**os.environ, "PYTHONDONTWRITEBYTECODE": "1", "PYTHONPATH": ""})
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.split()[0] == "ok" and int(r.stdout.split()[1]) == int(examples[1][0].board.sum())
+    # native wire: this package's class
+    self_play.save_examples(path, examples, 36, wire="native")
+    d = np.load(path, allow_pickle=True)
+    assert type(d["boards"][0]).__module__.startswith("yinyang_game_alphazero_b200")

@@ -40,6 +40,9 @@ def parse_args(argv=None):
     p.add_argument("--rules-rowcol", action="store_true", help="also apply the browser game's row/column rule")
     p.add_argument("--init-model", action="store_true", help="create a randomly initialised model file if missing")
     p.add_argument("--eval-games", type=int, default=10)
+    p.add_argument("--replay-wire", choices=["native", "reference"], default="native",
+                   help="'reference': pickle replay boards as src.yin_yang.yin_yang_logic.YinYangLogic so that the "
+                        "reference's own trainer loads the .npz without this package")
     return p.parse_args(argv)
 
 
@@ -70,7 +73,7 @@ def main(argv=None):
         logger.info(f"Generating self-play data using model: {model_path}")
         data_file = generate_self_play_data(game=game, model_path=model_path, output_dir=args.data_dir,
                                             num_games=args.episodes, num_workers=args.workers,
-                                            num_simulations=args.simulations)
+                                            num_simulations=args.simulations, wire=args.replay_wire)
         logger.info(f"Self-play data generation completed. Data saved to {data_file}")
         return 0
     # evaluate: AlphaZero vs random, colours alternate (train_alphazero.py:165-243)

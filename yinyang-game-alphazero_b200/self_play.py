@@ -133,8 +133,61 @@ class SelfPlayManager:
         return examples
 
 
-def generate_self_play_data(game, model_path, output_dir, num_games=100, num_workers=1, num_simulations=800):
-    """self_play.py:337-387.  Returns the path of the written .npz."""
+def save_examples(filename, examples, action_size, wire="native"):
+    """np.savez(boards=<object array>, policies=float64[N,A], values=float64[N]) (self_play.py:373-384).
+
+    wire="native"    : boards are this package's ``YinYangLogic`` (unpickling needs ``yy_b200`` importable);
+    wire="reference" : boards are pickled as ``src.yin_yang.yin_yang_logic.YinYangLogic`` (attributes n, m, board:
+                       yin_yang_logic.py:14-22), so the reference's own trainer (``TrainingDataQueue.push_file``,
+                       training_pipeline.py:55-73) loads the file without this package installed."""
+    boards = np.empty(len(examples), dtype=object)
+    undo = None
+    if wire == "reference":
+        cls, undo = _reference_board_class()
+        for i, ex in enumerate(examples):
+            o = cls.__new__(cls)
+            o.n, o.m = int(ex[0].n), int(ex[0].m)
+            o.board = np.array(ex[0].get_board() if hasattr(ex[0], "get_board") else ex[0].board, dtype=np.int8)
+            boards[i] = o
+    elif wire == "native":
+        for i, ex in enumerate(examples):
+            boards[i] = ex[0]
+    else:
+        raise ValueError("wire must be 'native' or 'reference'")
+    policies = np.array([ex[1] for ex in examples], dtype=np.float64).reshape(len(examples), action_size)
+    values = np.array([ex[2] for ex in examples], dtype=np.float64)
+    try:
+        np.savez(filename, boards=boards, policies=policies, values=values)
+    finally:
+        if undo:
+            import sys
+            for name in undo:
+                sys.modules.pop(name, None)
+    return filename
+
+
+def _reference_board_class():
+    """(class, fake module names to remove afterwards).  pickle stores a class by module path + name and checks that the
+    path resolves to the very object being pickled: use the reference's class when it is importable, otherwise register
+    a stand-in under the reference's module path for the duration of the save."""
+    import sys
+    import types
+    try:
+        from src.yin_yang.yin_yang_logic import YinYangLogic as Ref   # running inside the reference tree
+        return Ref, None
+    except Exception:
+        created = []
+        for name in ("src", "src.yin_yang", "src.yin_yang.yin_yang_logic"):
+            if name not in sys.modules:
+                sys.modules[name] = types.ModuleType(name)
+                created.append(name)
+        cls = type("YinYangLogic", (), {"__module__": "src.yin_yang.yin_yang_logic"})
+        sys.modules["src.yin_yang.yin_yang_logic"].YinYangLogic = cls
+        return cls, created
+
+
+def generate_self_play_data(game, model_path, output_dir, num_games=100, num_workers=1, num_simulations=800, wire="native"):
+    """self_play.py:337-387.  Returns the path of the written .npz (``wire``: see save_examples)."""
     if not os.path.exists(output_dir):
         os.makedirs(output_dir)
     games_per_worker = max(1, num_games // num_workers)          # self_play.py:355
@@ -142,11 +195,6 @@ def generate_self_play_data(game, model_path, output_dir, num_games=100, num_wor
                               num_simulations=num_simulations)
     examples = manager.generate_games_parallel()
     filename = os.path.join(output_dir, f"self_play_data_{int(time.time())}.npz")
-    boards = np.empty(len(examples), dtype=object)
-    for i, ex in enumerate(examples):
-        boards[i] = ex[0]
-    policies = np.array([ex[1] for ex in examples], dtype=np.float64).reshape(len(examples), game.getActionSize())
-    values = np.array([ex[2] for ex in examples], dtype=np.float64)
-    np.savez(filename, boards=boards, policies=policies, values=values)
+    save_examples(filename, examples, game.getActionSize(), wire)
     logger.info(f"Saved {len(examples)} examples to {filename}")
     return filename
