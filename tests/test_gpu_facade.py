@@ -140,3 +140,39 @@ def test_data_utils_facade_matches_reference_golden(pkg):
     x, p = proc.preprocess_sample(data[0][0], data[0][1], 1)
     forms = proc.augment_sample(x, p)                       # the reference passes the plane tensor here
     assert len(forms) == 8 and np.array_equal(forms[3][0].numpy(), g["planes"][3]) and np.array_equal(forms[3][1].numpy(), g["policies"][3])
+
+
+def test_arena_matches_sequential_reference_loop(pkg):
+    """arena.play_match (all games in lock-step, two batched searches per ply) against the reference's own loop
+    (alphazero.py:176-219) written with the facade's MCTS.select_action / game.getNextState / getGameEnded, which are
+    pinned against the reference goldens.  Deterministic evaluators; the two 'models' differ in c_puct."""
+    from yinyang_game_alphazero_b200 import arena
+    n = m = 5
+    game = pkg["game"].YinYangGame(n, m)
+    stub = pkg["network"].HashStubEvaluator(game)
+    cur = pkg["mcts"].MCTS(game, stub, num_simulations=40, cpuct=1.0, dirichlet_noise=False, verbose=0)
+    best = pkg["mcts"].MCTS(game, stub, num_simulations=40, cpuct=3.0, dirichlet_noise=False, verbose=0)
+    G = 6
+    out = arena.play_match(game, cur, best, G)
+    cw = bw = dr = 0
+    results = []
+    for i in range(G):
+        first, second, first_is_current = (cur, best, True) if i % 2 == 0 else (best, cur, False)
+        board, player = game.getInitBoard(), 1
+        for _ in range(4 * n * m + 8):
+            action = (first if player == 1 else second).select_action(board, player, temperature=0)
+            board, player = game.getNextState(board, player, action)
+            r = game.getGameEnded(board, player)
+            if r != 0:
+                break
+        results.append(r)
+        if r == 1:
+            cw, bw = (cw + 1, bw) if first_is_current else (cw, bw + 1)
+        elif r == -1:
+            cw, bw = (cw, bw + 1) if first_is_current else (cw + 1, bw)
+        else:
+            dr += 1
+    assert [float(x) for x in out["results"]] == [float(x) for x in results]
+    assert (out["current_wins"], out["best_wins"], out["draws"]) == (cw, bw, dr)
+    assert out["win_ratio"] == cw / G and arena.should_promote(0.6) and not arena.should_promote(0.59)
+    cur.close(); best.close()
