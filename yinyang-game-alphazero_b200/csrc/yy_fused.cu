@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   int16_t* pos_tab = reinterpret_cast<int16_t*>(smem + SM_POS + 128 * TW_MAXT * 2);    // M row -> board*256 + cell, or -1
   const uint32_t bar0 = smem_u32(smem + SM_BAR);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (TW_STAGES + s); };
-  auto peer_full_bar = [&](int s) { return bar0 + 8u * (2 * TW_STAGES + 2 + s); };   // leader: the follower's stage s landed
-  const uint32_t acc_full = bar0 + 8u * (2 * TW_STAGES), act_ready = bar0 + 8u * (2 * TW_STAGES + 1);
+  auto empty_bar = [&](int s) { return bar0 + 8u * (TW_FC_SLOTS + s); };
+  auto peer_full_bar = [&](int s) { return bar0 + 8u * (2 * TW_FC_SLOTS + s); };   // leader: the follower's stage s landed
+  const uint32_t acc_full = bar0 + 8u * (3 * TW_FC_SLOTS), act_ready = bar0 + 8u * (3 * TW_FC_SLOTS + 1);
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
 
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     pos_tab[i] = (int16_t)v;
   }
   if (tid == 0) {
-    for (int s = 0; s < TW_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(peer_full_bar(s), 1); }
+    for (int s = 0; s < TW_FC_SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(peer_full_bar(s), 1); }
     mbar_init(acc_full, 1);
     mbar_init(act_ready, CG * TW_EPI_THREADS);   // pair: the leader's barrier also collects the follower's epilogue threads
     fence_barrier_init();
@@ -124,40 +124,56 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   auto fc_tiles = [&](int h) { return h ? 2 : fc.Tp; };
   auto fc_rows = [&](int h, int t) { return (h || t < fc.Tp - 1) ? 128 : fc.Rp_last; };
   auto panel_stages = [&](int p) { const int r = fc.KS - p * FC_PANEL_STAGES; return r < FC_PANEL_STAGES ? r : FC_PANEL_STAGES; };
+  // Weight slots: the conv stream cycles through the TW_STAGES ring slots; the FC stream of a batch cycles through
+  // TW_FC_SLOTS slots -- the ring plus two more in the tail of the activation region, which is free while the heads run
+  // (the FC phase is bound by the bytes in flight: 16 KB per slot against ~1 us of L2 latency).  Every role tracks one
+  // phase bit per slot, so the two cycles can share the ring.  A policy tile of <= 64 rows packs two K = 64 stages per slot.
+  auto slot_addr = [&](uint32_t s) {
+    return s < (uint32_t)TW_STAGES ? ring_base + s * TW_STAGE_BYTES : act_base + (uint32_t)TW_FC_EXTRA_OFF + (s - TW_STAGES) * TW_STAGE_BYTES;
+  };
+  auto fc_merge = [&](int h, int t) { return fc_rows(h, t) <= 64 ? 2 : 1; };
 
   if (warp == 0) {
     // =========================================================== weight producer (whole warp walks the loop with
     // warp-uniform state; one elected lane issues the bulk copies -- keeps everything on the uniform datapath)
     if (a.use_nn) {
-      uint32_t it = 0;
-      auto push = [&](const uint8_t* src, uint32_t bytes) {
-        const uint32_t slot = it % TW_STAGES;
-        if (it >= TW_STAGES) mbar_wait(empty_bar(slot), ((it / TW_STAGES) - 1) & 1);
+      uint32_t ci = 0, used = 0, ephase = 0, acc_n = 0;     // conv stage counter, slots used so far, empty-phase bits, commits so far
+      auto push = [&](uint32_t slot, const uint8_t* src, uint32_t bytes) {
+        if ((used >> slot) & 1u) { mbar_wait(empty_bar(slot), (ephase >> slot) & 1u); ephase ^= 1u << slot; }
+        used |= 1u << slot;
         if (elect_one()) {
           mbar_arrive_expect_tx(full_bar(slot), bytes);
-          bulk_g2s(ring_base + slot * TW_STAGE_BYTES, src, bytes, full_bar(slot));
+          bulk_g2s(slot_addr(slot), src, bytes, full_bar(slot));
         }
         __syncwarp();
-        ++it;
       };
       for (int iter = 0; iter < a.iterations; ++iter) {
         for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
           const long long slim = batch_end(bb0);
           for (long long b0 = bb0; b0 < slim; b0 += g.Gb) {
-            for (int l = 0; l < L; ++l) {
+            for (int l = 0; l < L; ++l, ++acc_n) {
               const LayerInfo li = layer_info(l, g.blocks, CG);
               const uint32_t bytes = (uint32_t)li.stage_bytes / CG;     // pair: my half of the stage's output channels
               const uint8_t* src = a.conv_stream + li.stream_off + (long long)rank * bytes;
-              for (int j = 0; j < li.n_stages; ++j) push(src + (long long)j * li.stage_bytes, bytes);
+              for (int j = 0; j < li.n_stages; ++j, ++ci) push(ci % TW_STAGES, src + (long long)j * li.stage_bytes, bytes);
             }
           }
+          // the extra FC slots overlay activation rows: wait until the last head conv of the batch has been computed
+          // (commit number acc_n - 1 of acc_full; it cannot be overtaken -- the next commit needs FC stages from me)
+          mbar_wait(acc_full, (acc_n - 1) & 1u);
           const uint8_t* src = a.fc_stream;
+          uint32_t fi = 0;
           for (int h = 0; h < 2; ++h)
-            for (int p = 0; p < fc.n_panels; ++p) {
+            for (int p = 0; p < fc.n_panels; ++p, ++acc_n) {
               const int ns = panel_stages(p);
               for (int t = 0; t < fc_tiles(h); ++t) {
                 const uint32_t bytes = 128u * (uint32_t)fc_rows(h, t);
-                for (int s = 0; s < ns; ++s) { push(src, bytes); src += bytes; }
+                const int mg = fc_merge(h, t);
+                for (int s0 = 0; s0 < ns; s0 += mg, ++fi) {
+                  const uint32_t k = (uint32_t)(ns - s0 < mg ? ns - s0 : mg);
+                  push(fi % TW_FC_SLOTS, src, k * bytes);
+                  src += k * bytes;
+                }
               }
             }
         }
@@ -168,26 +184,31 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     // tcgen05.mma / commit instructions are issued by one elected lane; descriptors are base + constant deltas)
     if (a.use_nn && rank != 0) {
       // follower of a pair: no MMAs to issue -- relay "my half of stage s has landed" to the leader's peer-full ring
-      uint32_t it = 0;
-      auto relay = [&]() {
-        const uint32_t slot = it % TW_STAGES;
-        mbar_wait(full_bar(slot), (it / TW_STAGES) & 1);
+      uint32_t ci = 0, fphase = 0;
+      auto relay = [&](uint32_t slot) {
+        mbar_wait(full_bar(slot), (fphase >> slot) & 1u); fphase ^= 1u << slot;
         if (elect_one()) mbar_arrive_cluster(mapa_u32(peer_full_bar(slot), 0));
         __syncwarp();
-        ++it;
       };
       for (int iter = 0; iter < a.iterations; ++iter) {
         for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
           const long long slim = batch_end(bb0);
           for (long long b0 = bb0; b0 < slim; b0 += g.Gb)
-            for (int l = 0; l < L; ++l) { const int ns = layer_info(l, g.blocks, CG).n_stages; for (int j = 0; j < ns; ++j) relay(); }
+            for (int l = 0; l < L; ++l) { const int ns = layer_info(l, g.blocks, CG).n_stages; for (int j = 0; j < ns; ++j, ++ci) relay(ci % TW_STAGES); }
+          uint32_t fi = 0;
           for (int h = 0; h < 2; ++h)
-            for (int p = 0; p < fc.n_panels; ++p) { const int ns = panel_stages(p) * fc_tiles(h); for (int j = 0; j < ns; ++j) relay(); }
+            for (int p = 0; p < fc.n_panels; ++p)
+              for (int t = 0; t < fc_tiles(h); ++t) {
+                const int ns = (panel_stages(p) + fc_merge(h, t) - 1) / fc_merge(h, t);
+                for (int j = 0; j < ns; ++j, ++fi) relay(fi % TW_FC_SLOTS);
+              }
         }
       }
     } else if (a.use_nn) {
-      uint32_t it = 0, act_phase = 0;
-      auto wait_stage = [&](uint32_t slot, uint32_t parity) {
+      uint32_t ci = 0, fphase = 0, act_phase = 0;
+      auto wait_stage = [&](uint32_t slot) {
+        const uint32_t parity = (fphase >> slot) & 1u;
+        fphase ^= 1u << slot;
         mbar_wait(full_bar(slot), parity);
         if (CG == 2) mbar_wait_cluster(peer_full_bar(slot), parity);
       };
@@ -215,14 +236,14 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
               const uint64_t k16_delta_b = (uint64_t)((2u * nrows_b * 16u) >> 4);
               wait_act(act_phase); act_phase ^= 1;
               tc_fence_after();
-              for (int j = 0; j < li.n_stages; ++j, ++it) {
-                const uint32_t slot = it % TW_STAGES;
+              for (int j = 0; j < li.n_stages; ++j, ++ci) {
+                const uint32_t slot = ci % TW_STAGES;
                 int tapshift, chunk0;
                 stage_info(l, j, g.blocks, g.pitch, g.dy_rows, CG, tapshift, chunk0);
-                wait_stage(slot, (it / TW_STAGES) & 1);
+                wait_stage(slot);
                 tc_fence_after();
                 const uint64_t ad0 = smem_desc(act_base + (uint32_t)((chunk0 * TW_ROWS + TW_PAD + tapshift) * 16), TW_ROWS * 16, (uint32_t)g.sbo_bytes);
-                const uint64_t bd0 = smem_desc(ring_base + slot * TW_STAGE_BYTES, nrows_b * 16, 128);
+                const uint64_t bd0 = smem_desc(slot_addr(slot), nrows_b * 16, 128);
                 const uint32_t acc0 = (preloaded || j > 0) ? 1u : 0u;
                 if (elect_one()) {
 #pragma unroll
@@ -247,6 +268,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           // ---- FC heads: D[o][board] (+)= Wfc[o][k] * feat[board][k]; A = weight stage in the ring, B = feature panel
           // (pair: both CTAs stage the same weight tile, so both get D for all 2 x FC_N boards; column block `rank` is mine)
           const uint32_t idesc_fc = idesc_bf16(128 * CG, FC_N * CG);
+          uint32_t fi = 0;
           for (int h = 0; h < 2; ++h)
             for (int p = 0; p < fc.n_panels; ++p) {
               const int ns = panel_stages(p);
@@ -256,17 +278,20 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                 const uint32_t R = (uint32_t)fc_rows(h, t);
                 const uint32_t dcol = (uint32_t)((h ? fc.Tp + t : t) * FC_N * CG);
                 const uint64_t k16_delta_w = (uint64_t)((2u * R * 16u) >> 4);
-                for (int s = 0; s < ns; ++s, ++it) {
-                  const uint32_t slot = it % TW_STAGES;
-                  wait_stage(slot, (it / TW_STAGES) & 1);
+                const int mg = fc_merge(h, t);
+                for (int s0 = 0; s0 < ns; s0 += mg, ++fi) {
+                  const uint32_t slot = fi % TW_FC_SLOTS;
+                  const int nk = 4 * (ns - s0 < mg ? ns - s0 : mg);      // K = 16 slices in this slot
+                  wait_stage(slot);
                   tc_fence_after();
-                  const uint64_t wd0 = smem_desc(ring_base + slot * TW_STAGE_BYTES, R * 16, 128);
-                  const uint64_t fd0 = smem_desc(act_base + (uint32_t)(s * 8 * FC_LBO), FC_LBO, 128);
-                  const uint32_t acc0 = (p > 0 || s > 0) ? 1u : 0u;
+                  const uint64_t wd0 = smem_desc(slot_addr(slot), R * 16, 128);
+                  const uint64_t fd0 = smem_desc(act_base + (uint32_t)(s0 * 8 * FC_LBO), FC_LBO, 128);
+                  const uint32_t acc0 = (p > 0 || s0 > 0) ? 1u : 0u;
                   if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                      mma(tmem_base + dcol, wd0 + (uint64_t)k * k16_delta_w, fd0 + (uint64_t)k * kK16DeltaF, idesc_fc, k > 0 ? 1u : acc0);
+                    for (int k = 0; k < 8; ++k)
+                      if (k < nk)
+                        mma(tmem_base + dcol, wd0 + (uint64_t)k * k16_delta_w, fd0 + (uint64_t)k * kK16DeltaF, idesc_fc, k > 0 ? 1u : acc0);
                     commit(empty_bar(slot));
                   }
                   __syncwarp();

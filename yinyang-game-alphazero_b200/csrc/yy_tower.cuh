@@ -37,10 +37,13 @@ constexpr int SM_ACT = 0;
 constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 157696
 constexpr int SM_POS = SM_RING + TW_STAGES * TW_STAGE_BYTES;          // position tables: padded position + (board, cell)
 constexpr int SM_BAR = SM_POS + 2 * 128 * TW_MAXT * 2;
-constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_STAGES + 2);   // full, empty, peer-full rings + acc_full, act_ready
+constexpr int TW_FC_SLOTS = 5;          // weight slots during the FC heads: the ring + 2 in the free tail of the activation region
+constexpr int TW_FC_EXTRA_OFF = 136 * 1024;   // (the FC feature panel ends at 135,168 B)
+constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_FC_SLOTS + 2);   // full, empty, peer-full per slot + acc_full, act_ready
 constexpr int SM_BIAS = (SM_TMEM + 16 + 15) & ~15;                                 // current / next layer's 128 fp32 biases (double buffer)
 constexpr int SM_TOTAL = SM_BIAS + 2 * TW_C * 4;
 static_assert(SM_TOTAL <= 232448, "persistent kernel exceeds the 227 KB opt-in shared memory of sm_100");
+static_assert(TW_FC_EXTRA_OFF + (TW_FC_SLOTS - TW_STAGES) * TW_STAGE_BYTES <= TW_CHUNKS * TW_ROWS * 16, "FC slots exceed the activation region");
 
 struct TowerGeo {
   int n, m, A, W, pitch, PB;  // PB = padded positions per board
