@@ -188,7 +188,7 @@ int yy_engine_set_profiling(yy_engine *e, int enable);
 int yy_engine_get_profile(yy_engine *e, int64_t *tower_launches, double *tower_ms, int64_t *tower_boards);
 /* Developer tool: while dbg_dev != NULL (>= 1024 int64) the persistent kernel records per-CTA start / end
  * %globaltimer stamps at dbg_dev[128 + 2*cta ..] and, for CTAs 0 and 100, the cycles its epilogue warps spent in
- * each phase (tower, FC heads, softmax + tree step, barrier, re-zero) at dbg_dev[600 ..] / [700 ..]. */
+ * each phase (tower, FC heads, softmax + tree step, barrier, re-zero, ...) at dbg_dev[600 ..] / [760 ..]. */
 int yy_engine_set_debug_stamps(yy_engine *e, long long *dbg_dev);
 
 /* Self-play driver (SelfPlayWorker.play_game, self_play.py:72-192, for n_games games in

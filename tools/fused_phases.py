@@ -27,9 +27,9 @@ print(f"move step {ms:.2f} ms = {ms / (sims + 1) * 1e3:.1f} us per simulation; s
 gt = raw[128:128 + 2 * 148].reshape(-1, 2)
 busy = gt[:, 0] > 0
 print("CTA duration ms:", np.percentile((gt[busy, 1] - gt[busy, 0]) / 1e6, [0, 50, 100]), "busy CTAs", busy.sum())
-for name, off in (("cta0", 600), ("cta100", 700)):
-    ph = raw[off:off + 80].reshape(16, 5)
-    tot = ph.sum(axis=1)
-    print(name, "per-iteration cycles by phase (warp 0 / warp 15): tower, fc, heads+tree, barrier, zero")
+for name, off in (("cta0", 600), ("cta100", 760)):
+    ph = raw[off:off + 128].reshape(16, 8)
+    tot = ph[:, :5].sum(axis=1)
+    print(name, "per-iteration cycles by phase (warp 0 / warp 15): tower, fc, heads+tree, barrier, zero | inside fc: panel loads, MMA waits, scatter")
     for w in (0, 15):
         print("   ", (ph[w] / (sims + 1)).round(0), "total", round(tot[w] / (sims + 1)))

@@ -147,6 +147,19 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         }
         __syncwarp();
       };
+      // pair, FC stages: both CTAs need the SAME weight tile, so the two producers take turns fetching a stage and the
+      // copy is multicast into both CTAs' slots (each CTA arms its own barrier) -- halves the L2 reads of the FC phase,
+      // which is bound by the aggregate L2 bandwidth (all SMs stream the 1.25 MB at the same time).  A slot is free in
+      // both CTAs at once: its empty barrier is armed by the leader's multicast commit.
+      auto push_shared = [&](uint32_t slot, const uint8_t* src, uint32_t bytes, bool mine) {
+        if ((used >> slot) & 1u) { mbar_wait(empty_bar(slot), (ephase >> slot) & 1u); ephase ^= 1u << slot; }
+        used |= 1u << slot;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(slot), bytes);
+          if (mine) bulk_g2s_multicast(slot_addr(slot), src, bytes, full_bar(slot), (uint16_t)3);
+        }
+        __syncwarp();
+      };
       for (int iter = 0; iter < a.iterations; ++iter) {
         for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
           const long long slim = batch_end(bb0);
@@ -171,7 +184,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                 const int mg = fc_merge(h, t);
                 for (int s0 = 0; s0 < ns; s0 += mg, ++fi) {
                   const uint32_t k = (uint32_t)(ns - s0 < mg ? ns - s0 : mg);
-                  push(fi % TW_FC_SLOTS, src, k * bytes);
+                  if (CG == 2) push_shared(fi % TW_FC_SLOTS, src, k * bytes, (fi & 1u) == (uint32_t)rank);
+                  else push(fi % TW_FC_SLOTS, src, k * bytes);
                   src += k * bytes;
                 }
               }
@@ -315,8 +329,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     float* sc_logit = reinterpret_cast<float*>(act);                 // [FC_N][256] heads scratch (act region is free then)
     float* sc_hidden = reinterpret_cast<float*>(act) + FC_N * 256;   // [FC_N][256] relu(fc1) * w2
     float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS);
-    long long ph_t = clock64(), ph_acc[5] = {0, 0, 0, 0, 0};             // developer stamps: tower / FC / heads+tree / barrier / zero
-    auto phase = [&](int k) { if (a.dbg) { const long long now = clock64(); ph_acc[k] += now - ph_t; ph_t = now; } };
+    // developer stamps: tower / FC / heads+tree / barrier / zero, and inside FC: feature-panel loads / MMA waits / scatter
+    long long ph_t = clock64(), ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sub_t = 0;
+    auto phase = [&](int k) { if (a.dbg) { const long long now = clock64(); ph_acc[k] += now - ph_t; ph_t = now; sub_t = now; } };
+    auto sub = [&](int k) { if (a.dbg) { const long long now = clock64(); ph_acc[k] += now - sub_t; sub_t = now; } };
     const uint32_t act_ready_leader = CG == 2 ? mapa_u32(act_ready, 0) : act_ready;
     // Accumulators complete: ONE warp polls the mbarrier, the other 15 block on the hardware named barrier.  (With all
     // 16 warps spinning on try_wait for the 80 % of a layer that the MMAs take, the poll loop was 70 % of all executed
@@ -454,7 +470,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           phase(0);
           for (int q = 0; q < 2 * fc.n_panels; ++q) {
             const int h = q / fc.n_panels, p = q % fc.n_panels;
-            if (q > 0) wait_acc();   // previous panel consumed
+            if (q > 0) { wait_acc(); sub(6); }   // previous panel consumed
             const int nchunks = panel_stages(p) * 8;
             const int kbase = p * FC_PANEL_STAGES * 64;
             const __nv_bfloat16* src0 = a.headfeat + (size_t)bb0 * (TW_HEADC * g.A) + (size_t)h * fc.Kh + kbase;
@@ -468,8 +484,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
             tc_fence_before();
             fence_proxy_async_smem();
             arrive_act();
+            sub(5);
           }
           wait_acc();
+          sub(6);
           // D tiles -> scratch: policy logits (+bias), value hidden units relu(.+b1) * w2   (lane = output unit)
           if (tile0 < fc.Tp + 2) {
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile0 * FC_N * CG + rank * FC_N);
@@ -497,6 +515,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           }
           tc_fence_before();
           epi_sync();
+          sub(7);
           phase(1);
         }
 
@@ -534,7 +553,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
       }
     }
     if (a.dbg && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 100))
-      for (int k = 0; k < 5; ++k) a.dbg[600 + (blockIdx.x ? 100 : 0) + ew * 5 + k] = ph_acc[k];
+      for (int k = 0; k < 8; ++k) a.dbg[600 + (blockIdx.x ? 160 : 0) + ew * 8 + k] = ph_acc[k];
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();

@@ -41,6 +41,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
                ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
 }
 
+// same copy delivered to the same shared-memory offset of every CTA in `cta_mask` of the cluster; each destination
+// CTA's barrier (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
+}
+
 // ---------------------------------------------------------------- cp.async (LDGSTS), 16 bytes
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gmem, bool valid) {
   uint32_t sz = valid ? 16u : 0u;  // src-size 0 => zero fill
