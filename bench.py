@@ -299,6 +299,22 @@ def bench_env(engine, torch, peaks):
             engine.env_step(b, w, p, acts, ROWS, COLS, out_mask=out_mask, out_result=out_res)
         ev1.record(); torch.cuda.synchronize()
         total_ms += ev0.elapsed_time(ev1)
+    api_launch_s = total_ms * 1e-3 / (reps * inner)      # one Python/ctypes call per launch: bound by the host's issue rate
+    # the same 8 launches replayed from a CUDA graph (fresh boards restored and L2 flushed before every replay): device time
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for b, w, p in bufs:
+            engine.env_step(b, w, p, acts, ROWS, COLS, out_mask=out_mask, out_result=out_res)
+    total_ms = 0.0
+    for r in range(reps):
+        for b, w, p in bufs:
+            b.copy_(black0); w.copy_(white0); p.copy_(players0)
+        flush.fill_(r)
+        torch.cuda.synchronize()
+        ev0.record()
+        graph.replay()
+        ev1.record(); torch.cuda.synchronize()
+        total_ms += ev0.elapsed_time(ev1)
     per_launch_s = total_ms * 1e-3 / (reps * inner)
     steps_s = ENV_BOARDS / per_launch_s
     # e2e: host buffers
@@ -326,14 +342,17 @@ def bench_env(engine, torch, peaks):
     big_s = ev0.elapsed_time(ev1) * 1e-3 / 3
     return {"metric": "env steps/sec (8x8)", "workload": "BASELINE.json configs[1]: 65,536 synthetic random-play boards, fused mask+step+ended",
             "value": steps_s, "unit": "steps/s", "us_per_launch": per_launch_s * 1e6,
+            "timing": "8 launches replayed from a CUDA graph, CUDA events around the replay",
+            "per_call": {"value": ENV_BOARDS / api_launch_s, "unit": "steps/s", "us_per_launch": api_launch_s * 1e6,
+                         "note": "one engine.env_step() Python/ctypes call per launch, device-resident tensors"},
             "e2e": {"value": e2e, "unit": "steps/s", "api": "env_step_host (int8 numpy boards in/out, pack/unpack on host)"},
             "roofline": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs / peaks["hbm_gbs"], "traffic": None,
-                         "note": "3.4 MB of algorithmic traffic per launch: latency bound at this batch size (14 warps per SM, "
-                                 "~2,600 dependent integer instructions per warp); integer-issue bound when the machine is full"},
+                         "note": "3.4 MB of algorithmic traffic per launch: latency bound at this batch size (two lanes per board, "
+                                 "28 warps per SM, one flood fill per lane); integer-issue bound when the machine is full"},
             "saturated": {"boards": big, "value": big / big_s, "unit": "steps/s", "us_per_launch": big_s * 1e6,
                           "achieved_GBps": ENV_BYTES_PER_STEP * big / big_s / 1e9},
-            "l2_policy": "L2 flushed (256 MB write) before each timed group of 8 launches on fresh copies"}
+            "l2_policy": "L2 flushed (256 MB write) before each timed group of 8 launches on fresh boards"}
 
 
 _JSON_FD = None

@@ -140,13 +140,15 @@ template <int NW> YY_HD BB<NW> completes_2x2(const Geo<NW>& g, BB<NW> x) {
   return (e & s & se) | (w & s & sw) | (e & n & ne) | (w & n & nw);
 }
 
-// 4-connected component of `seed` inside `x` (_check_connectivity BFS, yin_yang_logic.py:58-94)
+// 4-connected component of `seed` inside `x` (_check_connectivity BFS, yin_yang_logic.py:58-94).
+// Two dilation steps per convergence test (the fixed point is unchanged; at most one step is wasted).
 template <int NW> YY_HD BB<NW> flood(const Geo<NW>& g, BB<NW> seed, BB<NW> x) {
   BB<NW> f = seed;
   for (;;) {
-    BB<NW> nx = f | (dilate4(g, f) & x);
-    if (same(nx, f)) return f;
-    f = nx;
+    BB<NW> n1 = f | (dilate4(g, f) & x);
+    BB<NW> n2 = n1 | (dilate4(g, n1) & x);
+    if (same(n2, f)) return f;
+    f = n2;
   }
 }
 
@@ -194,15 +196,21 @@ template <int NW> YY_HD BB<NW> completes_rowcol(const Geo<NW>& g, BB<NW> p, BB<N
   return bad;
 }
 
-// get_valid_moves (yin_yang_logic.py:111-120): legal placements for the colour whose stones are `p`
-// (opponent stones `o`).
-template <int NW> YY_HD BB<NW> legal_moves(const Geo<NW>& g, BB<NW> p, BB<NW> o) {
+// get_valid_moves (yin_yang_logic.py:111-120) without the connectivity test: empty cells that pass the 2x2 rule
+// (and the optional row/column rule) for the colour whose stones are `p` (opponent stones `o`).
+template <int NW> YY_HD BB<NW> legal_candidates(const Geo<NW>& g, BB<NW> p, BB<NW> o) {
   if (has_2x2(g, p) || has_2x2(g, o)) return bb_zero<NW>();
   BB<NW> cand = andnot(andnot(g.full, p | o), completes_2x2(g, p));
   if (g.rule_flags & YY_RULE_ROWCOL_BIT) {
     if (rowcol_violated(g, p, o)) return bb_zero<NW>();
     cand = andnot(cand, completes_rowcol(g, p, o));
   }
+  return cand;
+}
+
+// get_valid_moves: legal placements for the colour whose stones are `p` (opponent stones `o`).
+template <int NW> YY_HD BB<NW> legal_moves(const Geo<NW>& g, BB<NW> p, BB<NW> o) {
+  BB<NW> cand = legal_candidates(g, p, o);
   if (!any(cand)) return cand;
   return cand & touches_all_components(g, p);
 }

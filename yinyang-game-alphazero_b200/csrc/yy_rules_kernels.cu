@@ -6,6 +6,7 @@
 // ~2,600 dependent integer instructions per warp (flood fills), so at 65,536 boards (14 warps per SM) they are
 // latency bound -- 15 us, of which the SMs are busy 10 -- and at 1 M boards integer-issue bound (10.8 G steps/s).
 #include "yy_common.cuh"
+#include <stdlib.h>
 
 namespace yy {
 
@@ -53,52 +54,99 @@ ended_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint64_
   out[i] = (int8_t)ended_code(g, b, w, players[i] == 1 ? 1 : -1);
 }
 
-// Fused getValidMoves + getNextState + getGameEnded.  The flood fills make the work per board data dependent (it
-// grows with the number of stones), and a batch usually mixes game stages: with one thread per board in input order
-// only 9 of 32 lanes were active per issued instruction (ncu, BASELINE configs[1]).  Each block therefore first
-// counting-sorts its boards by stone count in shared memory and hands them to the threads in that order, so the
-// lanes of a warp get boards of similar cost; results go back to the boards' own slots.
-constexpr int kEnvBlock = 256;              // (one 448-thread block per SM, a single balanced wave, was no faster at 65,536
-constexpr int kEnvBins = 64;                //  boards and slower at 1 M: the longest warp, not the tail, sets the latency)
+// Fused getValidMoves + getNextState + getGameEnded.
+// Two lanes per board: lane 2k analyses the mover's colour, lane 2k+1 the other colour, so the two flood fills of a
+// step (the only long dependent chains) run side by side and the chain per lane halves.  What a step needs is then
+// exactly one component analysis per colour: the successor's masks follow without further fills, because the
+// opponent's stones do not change and a legal placement leaves the mover's stones one component (its dilation is
+// the new "touches every component" set).  The fills make the work per board data dependent (it grows with the
+// number of stones) and a batch usually mixes game stages: in input order only 9 of 32 lanes were active per issued
+// instruction (ncu, BASELINE configs[1]).  Each block therefore first counting-sorts its boards by stone count in
+// shared memory, so the lanes of a warp get boards of similar cost; results go back to the boards' own slots.
+constexpr int kEnvBins = 64;
 
-template <int NW>
-__global__ void __launch_bounds__(kEnvBlock)
+template <int NW, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
 env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __restrict__ white,
                 int8_t* __restrict__ players, const int32_t* __restrict__ actions, uint64_t* __restrict__ out_mask,
                 int8_t* __restrict__ out_result, long long count) {
+  constexpr int BOARDS = BLOCK / 2;
+  static_assert(BOARDS > kEnvBins, "one thread per histogram bin");
   __shared__ int s_hist[kEnvBins + 1];
   __shared__ int s_off[kEnvBins + 1];
-  __shared__ uint16_t s_order[kEnvBlock];     // sorted position -> thread whose board it is
+  __shared__ uint16_t s_order[BOARDS];        // sorted position -> board of this block
   const int tid = threadIdx.x;
-  const long long base = (long long)blockIdx.x * blockDim.x;
-  const long long mine = base + tid;
+  const long long base = (long long)blockIdx.x * BOARDS;
   if (tid <= kEnvBins) s_hist[tid] = 0;
   __syncthreads();
-  int key = kEnvBins;                         // threads past the end sort last
-  if (mine < count) {
-    int stones = 0;
-    for (int k = 0; k < W; ++k) stones += popc64(black[mine * W + k] | white[mine * W + k]);
-    key = stones * kEnvBins / (g.cells + 1);
+  int key = kEnvBins, rank = 0;               // boards past the end sort last
+  if (tid < BOARDS) {
+    const long long mine = base + tid;
+    if (mine < count) {
+      int stones = 0;
+      for (int k = 0; k < W; ++k) stones += popc64(black[mine * W + k] | white[mine * W + k]);
+      key = stones * kEnvBins / (g.cells + 1);
+    }
+    rank = atomicAdd(&s_hist[key], 1);
   }
-  const int rank = atomicAdd(&s_hist[key], 1);
   __syncthreads();
-  if (tid == 0) { int acc = 0; for (int k = 0; k <= kEnvBins; ++k) { s_off[k] = acc; acc += s_hist[k]; } }
-  __syncthreads();
-  s_order[s_off[key] + rank] = (uint16_t)tid;
-  __syncthreads();
-  const long long i = base + s_order[tid];
-  if (i >= count) return;
-  BB<NW> b = load_bb<NW>(black, i, W) & g.full, w = load_bb<NW>(white, i, W) & g.full;
-  int p = players[i] == 1 ? 1 : -1;
-  BB<NW> lm = legal_for(g, b, w, p);
-  store_bb<NW>(out_mask, i, W, lm);
-  int a = actions[i];
-  if (a >= 0 && a < g.cells && test(lm, a)) {
-    if (p == 1) { setbit(b, a); store_bb<NW>(black, i, W, b); }
-    else        { setbit(w, a); store_bb<NW>(white, i, W, w); }
+  if (tid < 32) {                             // exclusive scan of the 65 bins by one warp
+    int v0 = s_hist[tid], v1 = s_hist[tid + 32], v2 = tid == 0 ? s_hist[64] : 0;
+    int i0 = v0, i1 = v1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t0 = __shfl_up_sync(0xffffffffu, i0, d), t1 = __shfl_up_sync(0xffffffffu, i1, d);
+      if (tid >= d) { i0 += t0; i1 += t1; }
+    }
+    int tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+    s_off[tid] = i0 - v0; s_off[tid + 32] = tot0 + i1 - v1;
+    if (tid == 0) { s_off[64] = tot0 + tot1; (void)v2; }
   }
-  players[i] = (int8_t)(-players[i]);
-  out_result[i] = (int8_t)ended_code(g, b, w, -p);
+  __syncthreads();
+  if (tid < BOARDS) s_order[s_off[key] + rank] = (uint16_t)tid;
+  __syncthreads();
+
+  const int side = tid & 1;                   // 0: the mover's colour, 1: the other colour
+  const long long i = base + s_order[tid >> 1];
+  const bool live = i < count;                // both lanes of a pair agree; nobody leaves before the shuffles
+  BB<NW> b = bb_zero<NW>(), w = bb_zero<NW>();
+  int praw = 1, a = -1;
+  if (live) {
+    b = load_bb<NW>(black, i, W) & g.full; w = load_bb<NW>(white, i, W) & g.full;
+    praw = players[i]; a = actions[i];
+  }
+  const int p = praw == 1 ? 1 : -1;
+  const bool mine_black = (p == 1) == (side == 0);
+  BB<NW> x = mine_black ? b : w, y = mine_black ? w : b;   // x: the colour this lane analyses
+  const bool rowcol = (g.rule_flags & YY_RULE_ROWCOL_BIT) != 0;
+
+  BB<NW> cand = legal_candidates(g, x, y);
+  BB<NW> acc = g.full;                        // cells touching every component of x
+  if (any(cand) || rowcol) acc = touches_all_components(g, x);
+  BB<NW> lm = cand & acc;
+  int placed = side == 0 && a >= 0 && a < g.cells && test(lm, a);
+  placed = __shfl_sync(0xffffffffu, placed, (tid & 31) & ~1);
+  if (live && side == 0) store_bb<NW>(out_mask, i, W, lm);
+  if (placed) {                               // the pair takes this branch together
+    if (side == 0) {
+      setbit(x, a); acc = dilate4(g, x);
+      store_bb<NW>(p == 1 ? black : white, i, W, x);
+    } else {
+      setbit(y, a);
+    }
+    lm = legal_candidates(g, x, y) & acc;     // masks of the successor
+  }
+  const int mine_any = any(lm);
+  const int peer_any = __shfl_xor_sync(0xffffffffu, mine_any, 1);
+  if (live && side == 0) {
+    int code = 0;                             // getGameEnded(successor, -p)
+    if (!mine_any && !peer_any) {
+      int bc = popcount(p == 1 ? x : y), wc = popcount(p == 1 ? y : x);
+      code = bc > wc ? (p == 1 ? -1 : 1) : (wc > bc ? (p == 1 ? 1 : -1) : 2);
+    }
+    out_result[i] = (int8_t)code;
+    players[i] = (int8_t)(-praw);             // yin_yang_game.py:58 returns -player whatever it was
+  }
 }
 
 template <int NW>
@@ -188,9 +236,16 @@ int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64
   int rc = check_rules_args(rows, cols, count); if (rc) return rc;
   if (count == 0) return YY_OK;
   int cells = rows * cols, W = words_for_cells(cells);
-  unsigned grid = (unsigned)((count + kEnvBlock - 1) / kEnvBlock);
-  YY_DISPATCH_NW(cells, env_step_kernel<NW><<<grid, kEnvBlock, 0, (cudaStream_t)stream>>>(
-      make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count));
+  static const int block = [] { const char* e = getenv("YY_ENV_BLOCK"); return e ? atoi(e) : 256; }();  // developer A/B switch
+  if (block == 512) {
+    unsigned grid = (unsigned)((count + 255) / 256);
+    YY_DISPATCH_NW(cells, env_step_kernel<NW, 512><<<grid, 512, 0, (cudaStream_t)stream>>>(
+        make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count));
+  } else {
+    unsigned grid = (unsigned)((count + 127) / 128);
+    YY_DISPATCH_NW(cells, env_step_kernel<NW, 256><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count));
+  }
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
