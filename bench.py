@@ -233,6 +233,7 @@ def run_b200(args):
     # ---- env steps/s (BASELINE.json configs[1]): 65,536 synthetic random-play boards on this GPU
     env = bench_env(engine, torch, peaks) if rank == 0 else None
     dataset = bench_dataset(engine, torch, peaks) if rank == 0 else None
+    learner_leg = bench_learner(engine, torch, peaks) if rank == 0 else None
 
     if rank == 0:
         tower_s = prof["ms"] * 1e-3 / max(1, prof["launches"])
@@ -261,7 +262,7 @@ def run_b200(args):
                 "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "api": "Engine.search_host + next_state_host (numpy in/out)"},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "env": env, "dataset": dataset,
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "env": env, "dataset": dataset, "learner": learner_leg,
                 "moves_per_s_roofline": peaks["bf16_tflops_sustained"] * 1e12 / ((SIMS + 1) * FLOPS_PER_LEAF) * world,
                 "leaf_evals_per_s": (SIMS + 1) * value,
                 "nccl": {"weight_broadcast_s": t_bcast, "replay_gather_s": t_gather, "replay_records_gathered": int(n_records)},
@@ -393,6 +394,54 @@ def bench_dataset(engine, torch, peaks):
             "roofline": {"bound": "hbm", "kernel": "augment_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_record": bytes_per_record},
             "l2_policy": "outputs (3.2 GB per launch) larger than L2; the timing includes torch's allocation of the outputs"}
+
+
+def bench_learner(engine, torch, peaks):
+    """optimisation steps of the reference trainer (trainer.py:120-137; batch 64, Adam) on the 128x10 network,
+    8x8 boards: one CUDA-graph replay of the yy_lrn_* kernels per step.  Tensor bound on paper, latency bound in fact."""
+    import numpy as np
+    from yinyang_game_alphazero_b200 import learner as lrn, _lib
+    from oracle import port
+    B = 64
+    torch.manual_seed(0)
+    net = port.build_net(ROWS, COLS, 128, 10)                  # reference initialisation only
+    n_rec = 256
+    plies = torch.arange(n_rec, dtype=torch.int32) % 52
+    black, white, _ = engine.random_playout(n_rec, plies, ROWS, COLS, seed=0x1EA2)
+    counts = torch.randint(0, 800, (n_rec, A), dtype=torch.int16, device="cuda")
+    values = (torch.randint(0, 2, (n_rec,), device="cuda").float() * 2 - 1)
+    planes, pol, val = engine.augment_samples(black, white, ROWS, COLS, counts=counts, values=values)   # 2,048 samples
+    out = {}
+    for precision in ("3xtf32", "tf32"):
+        L = lrn.Learner(ROWS, COLS, 128, 10, batch_size=B, state_dict=net.state_dict(), precision=precision)
+        l0 = _lib.lib().yy_launch_count()
+        first = L.step(planes[:B], pol[:B], val[:B]).clone()
+        kernels = (_lib.lib().yy_launch_count() - l0) // 2     # the eager step + its capture pass both count
+        for i in range(1, 4):
+            L.step(planes[i * B:(i + 1) * B], pol[i * B:(i + 1) * B], val[i * B:(i + 1) * B])
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 64
+        ev0.record()
+        for i in range(steps):
+            j = (i % 32) * B
+            last = L.step(planes[j:j + B], pol[j:j + B], val[j:j + B])
+        ev1.record(); torch.cuda.synchronize()
+        sec = ev0.elapsed_time(ev1) * 1e-3 / steps
+        flops = 3 * B * FLOPS_PER_LEAF                           # forward + backward-data + backward-weights (algorithmic)
+        tf = flops / sec / 1e12
+        peak = peaks["bf16_tflops_sustained"] / 2                # TF32 runs at half the bf16 rate; no measured TF32 peak on file
+        out[precision] = {"value": B / sec, "unit": "samples/s", "ms_per_step": sec * 1e3, "kernels_per_step": int(kernels),
+                          "losses_first": [float(x) for x in first.tolist()], "losses_last": [float(x) for x in last.tolist()],
+                          "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                                       "peak_source": "half of the measured sustained bf16 rate (TF32 = half rate)",
+                                       "algorithmic_flops_per_step": flops,
+                                       "note": "4,096 positions per step: every kernel is microseconds long, the step is launch/latency bound"}}
+    res = out["3xtf32"]
+    res["metric"] = "training samples/sec (8x8, 128x10 network, batch 64, Adam; one CUDA-graph replay per step)"
+    res["single_pass_tf32"] = out["tf32"]
+    res["l2_policy"] = "a step touches ~190 MB of activations, im2col scratch, weights and Adam state (> L2); 32 distinct batches rotate"
+    return res
 
 
 def main():

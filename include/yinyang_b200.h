@@ -247,6 +247,61 @@ int yy_augment_samples(int rows, int cols, const uint64_t *black_dev, const uint
                        const uint16_t *counts_dev, const float *policy_dev, const float *values_dev, int64_t count,
                        float *out_planes_dev, float *out_policy_dev, float *out_values_dev, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Learner-step primitives.  Together they replace one optimisation step of
+ * AlphaZeroTrainer.train (src/yin_yang/ai/trainer.py:67-161): YinYangNeuralNetwork.forward in training mode
+ * (neural_network.py:94-123; nn.BatchNorm2d batch statistics), CrossEntropyLoss(soft targets) + MSELoss
+ * (trainer.py:60-61,131-133), backward, and torch.optim.Adam(lr, weight_decay) (trainer.py:52-56,136-137).
+ * The host side (yinyang-game-alphazero_b200/learner.py) strings them into the layer sequence and captures the
+ * step in one CUDA graph.  Activations are float32 [positions][channels] (positions = batch x cells, NHWC);
+ * every matrix is row-major with a leading dimension in floats; all pointers are device pointers. */
+
+/* C[M,N] = A[M,K] * B[N,K]^T (+ bias[n]) (ReLU) on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulate) --
+ * nn.Conv2d / nn.Linear forward (F.conv2d via im2col, F.linear) and both of their gradients.  precision:
+ * YY_GEMM_3XTF32 splits every operand into the 19 bits a TF32 multiplier reads and the remainder and runs three MMAs
+ * per K-slice (lo*hi + hi*lo + hi*hi): fp32-level results, what the fp32 reference computes; YY_GEMM_TF32 is the
+ * single-pass variant (torch's default for fp32 convolutions on a GPU).  atomic != 0: C += ... with float atomics onto
+ * a C the caller initialised (split-K partial sums, gradient accumulation onto a skip connection's share).
+ * tile_n: output columns per CTA (16..256, multiple of 16; <= 128 for 3xTF32); split_k >= 1 slices K over gridDim.z
+ * (needs atomic).  lda/ldb/ldc/K multiples of 4, pointers 16-byte aligned. */
+#define YY_GEMM_TF32 0
+#define YY_GEMM_3XTF32 1
+int yy_lrn_gemm(const float *A, int lda, const float *B, int ldb, float *C, int ldc, int M, int N, int K,
+                const float *bias, int relu, int atomic, int tile_n, int split_k, int precision, void *stream);
+/* out[p][t*C + c] = X[p + d(t)][c], zero outside the board; t = kh*3 + kw of nn.Conv2d(kernel_size=3, padding=1)
+ * (neural_network.py:21-23,43); flip != 0 mirrors the taps (the gather of the backward-data pass). */
+int yy_lrn_im2col3x3(const float *X, int ldx, float *out, int ldo, int64_t positions, int rows, int cols, int C,
+                     int flip, void *stream);
+/* out[c][r] = in[r][c] */
+int yy_lrn_transpose(const float *in, int ldi, float *out, int ldo, int R, int C, void *stream);
+/* Wt[ci][t*Cout + co] = W[co][t*Cin + ci]: the B operand of the backward-data GEMM of a 3x3 convolution. */
+int yy_lrn_conv_weight_t(const float *W, float *Wt, int Cout, int Cin, void *stream);
+/* planes float32 [boards][5][cells] (board_to_input, neural_network.py:156-196) -> X0 float32 [boards*cells][8]. */
+int yy_lrn_planes_nhwc(const float *planes, float *X0, int64_t boards, int cells, void *stream);
+/* out[c] = sum_r X[r][c] (bias gradients), float64 accumulation. */
+int yy_lrn_colsum(const float *X, int ld, int R, int C, float *out, void *stream);
+/* nn.BatchNorm2d in train() (neural_network.py:22-25,44): out = [relu](gamma*(Y-mean)*invstd + beta [+ residual]) with
+ * the batch's own mean / biased variance over the P positions; writes mean_invstd float[2C] for the backward pass and
+ * updates running_mean / running_var (unbiased variance, `momentum`) in place when not NULL.  sums_ws: float64[2C]. */
+int yy_lrn_bn_forward(const float *Y, int ld, int P, int C, const float *gamma, const float *beta,
+                      const float *residual, int ldr, float *out, int ldo, int relu, float eps, float momentum,
+                      double *sums_ws, float *mean_invstd, float *running_mean, float *running_var, void *stream);
+/* Backward of the above (and of the ReLU after it when Out != NULL: dZ = dOut*[Out > 0]):
+ * dY = gamma*invstd*(dZ - mean(dZ) - xhat*mean(dZ*xhat)); dRes (optional) = dZ; dgamma = sum dZ*xhat; dbeta = sum dZ. */
+int yy_lrn_bn_backward(const float *dOut, int ldd, const float *Out, int ldo, const float *Y, int ldy, int P, int C,
+                       const float *mean_invstd, const float *gamma, double *sums_ws, float *dY, int lddy,
+                       float *dRes, int lddr, float *dgamma, float *dbeta, void *stream);
+/* Both losses and their gradients at the heads (trainer.py:131-133; value head tail neural_network.py:119-121):
+ * losses[0] = CrossEntropyLoss(logits, pi) with probability targets, losses[1] = MSELoss(tanh(h.w2 + b2), z);
+ * dlogits, dh (through the ReLU that produced h), dpre[B], v_out[B], dw2[H], db2[1]. */
+int yy_lrn_heads_loss(const float *logits, int ldl, const float *pi, int A, const float *h, int ldh, int H,
+                      const float *w2, const float *b2, const float *z, int B, float *dlogits, int lddl, float *dh,
+                      int lddh, float *dpre, float *v_out, float *dw2, float *db2, float *losses, void *stream);
+/* torch.optim.Adam step (L2 weight decay folded into the gradient) over one flat parameter buffer;
+ * *step_dev is incremented first (bias correction). */
+int yy_lrn_adam(float *params, const float *grads, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, int *step_dev, void *stream);
+
 /* tcgen05 self-test used by tests/ (C = A[M,K] * B[N,K]^T, bf16 in / fp32 out, operands in the
  * same no-swizzle K-major core-matrix layout the tower kernel uses).  Layout: csrc/yy_probe.cu. */
 int yy_probe_umma(const void *a_dev, const void *b_dev, float *c_dev, int M, int N, int K, int a_row_offset,

@@ -81,7 +81,7 @@ def test_network_predict_contract(pkg):
     import torch
     game = pkg["game"].YinYangGame(6, 6)
     torch.manual_seed(0)
-    net = pkg["network"].YinYangNeuralNetwork(game, num_channels=32, num_res_blocks=2)
+    net = pkg["network"].YinYangNeuralNetwork(game, num_channels=128, num_res_blocks=2)
     p, v = net.predict(game.getInitBoard())
     assert p.shape == (36,) and p.dtype == np.float32 and abs(p.sum() - 1) < 1e-5 and -1 <= float(v) <= 1
     assert isinstance(v, np.float32)
@@ -176,3 +176,38 @@ def test_arena_matches_sequential_reference_loop(pkg):
     assert (out["current_wins"], out["best_wins"], out["draws"]) == (cw, bw, dr)
     assert out["win_ratio"] == cw / G and arena.should_promote(0.6) and not arena.should_promote(0.59)
     cur.close(); best.close()
+
+
+def test_trainer_facade_trains_and_checkpoints(pkg, tmp_path):
+    """AlphaZeroTrainer (src/yin_yang/ai/trainer.py) surface: train(examples, epochs, augment) -> metrics, checkpoints in the
+    reference's format, and the trained weights reach the self-play evaluator."""
+    import torch
+    from yinyang_game_alphazero_b200 import trainer
+    game = pkg["game"].YinYangGame(6, 6)
+    rng = np.random.default_rng(0)
+    examples = []
+    for i in range(24):
+        b = game.getInitBoard()
+        b.board = rng.integers(-1, 2, (6, 6)).astype(np.int8)
+        pi = rng.random(36); pi /= pi.sum()
+        examples.append((b, pi, float(rng.choice([-1.0, 1.0]))))
+    torch.manual_seed(0)
+    tr = trainer.AlphaZeroTrainer(game, model_dir=str(tmp_path), batch_size=64, num_channels=128, num_res_blocks=2)
+    before = {k: v.clone() for k, v in tr.nnet.state_dict().items()}
+    m = tr.train(examples, epochs=6, augment=True)            # 192 samples -> 3 full batches per epoch
+    assert set(m) == {"policy_loss", "value_loss", "total_loss"} and all(len(v) == 6 for v in m.values())
+    assert all(np.isfinite(m["total_loss"])) and m["total_loss"][-1] < m["total_loss"][0]
+    m2 = tr.train(examples[:5], epochs=1, augment=False)      # 5 samples: one remainder-sized batch
+    assert np.isfinite(m2["total_loss"][0])
+    after = tr.nnet.state_dict()
+    assert any(not torch.equal(before[k], after[k]) for k in before)
+    tr.save_checkpoint(iteration=3)
+    path = os.path.join(str(tmp_path), "checkpoint_3.pth.tar")
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"state_dict", "board_size", "action_size"} and set(ck["state_dict"]) == set(before)
+    tr2 = trainer.AlphaZeroTrainer(game, model_dir=str(tmp_path), batch_size=64, num_channels=128, num_res_blocks=2)
+    tr2.load_checkpoint(iteration=3)
+    for k, v in tr2.learner.state_dict().items():
+        assert torch.equal(v.float(), after[k].float()), k
+    p, v = tr.nnet.predict(examples[0][0])                     # the self-play evaluator sees the trained weights
+    assert p.shape == (36,) and abs(p.sum() - 1) < 1e-3 and -1 <= v <= 1

@@ -1,0 +1,287 @@
+"""Learner step.
+
+CPU part: the layer sequence / parameter layouts / backward formulas of learner.Learner against torch autograd, with the
+kernels replaced by their torch emulation (tests/emu_learner_ops.py) through the `_ops` test seam.
+GPU part (-m gpu): every yy_lrn_* kernel against that emulation on the same inputs, and the whole CUDA step against the
+fp32 torch restatement of the reference's training step (oracle/port.py build_net + torch.optim.Adam).
+
+Tolerances.  GEMM (tensor cores, fp32 accumulation), elementwise against a float64 product: 3xTF32 (the learner's
+default) |err| <= 3e-6 * (|A| @ |B|^T); single-pass TF32 <= 1.5e-3 * (|A| @ |B|^T) (two operand truncations of 2^-10).
+Full step of the 128x10 network at batch 64 against the fp32 torch step (everything else is fp32 with float64 batch-norm
+sums): see test_cuda_step_matches_torch_fp32_training_step (the convolutions' own biases are excluded: their true
+gradient is zero under a following batch norm and both sides hold rounding noise).
+"""
+import numpy as np
+import pytest
+import torch
+
+from emu_learner_ops import TorchEmuOps
+
+
+def _reference_net(n, m, C, nb, seed):
+    from oracle import port
+    torch.manual_seed(seed)
+    net = port.build_net(n, m, C, nb)
+    with torch.no_grad():                      # move batch-norm affine parameters and biases off their trivial init
+        for k, p in net.named_parameters():
+            if "bn" in k or k.endswith("bias"):
+                p.add_(torch.randn_like(p) * 0.2)
+    return net
+
+
+def _batch(net, n, m, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    grids = torch.randint(-1, 2, (B, n, m), generator=g).numpy().astype(np.int8)
+    planes = torch.as_tensor(net.planes(grids))
+    pi = torch.softmax(torch.randn(B, n * m, generator=g) * 2, 1)
+    z = torch.rand(B, generator=g) * 2 - 1
+    return planes, pi, z
+
+
+def _torch_step(net, opt, planes, pi, z):
+    net.train()
+    opt.zero_grad()
+    lg, v = net(planes)
+    lp = torch.nn.CrossEntropyLoss()(lg, pi)               # trainer.py:61,131
+    lv = torch.nn.MSELoss()(v.view(-1), z)                 # trainer.py:60,132
+    (lp + lv).backward()
+    grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    opt.step()
+    return lp.item(), lv.item(), grads
+
+
+def _is_conv_bias(k):
+    return k.endswith("bias") and "conv" in k
+
+
+def test_layer_sequence_matches_autograd_with_emulated_kernels(yy):
+    from yinyang_game_alphazero_b200 import learner
+    n = m = 4
+    net = _reference_net(n, m, 8, 2, seed=1)
+    L = learner.Learner(n, m, 8, 2, batch_size=8, state_dict=net.state_dict(), _ops=TorchEmuOps())
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
+    planes, pi, z = _batch(net, n, m, 8, seed=2)
+    for b in (8, 8, 5, 3):                                 # full batches, then DataLoader-style remainders (odd sizes)
+        lp, lv, ref = _torch_step(net, opt, planes[:b], pi[:b], z[:b])
+        losses = L.step(planes[:b], pi[:b], z[:b])
+        assert abs(losses[0].item() - lp) < 1e-5 and abs(losses[1].item() - lv) < 1e-5
+        got = L.grad_dict()
+        for k, g in ref.items():
+            if not _is_conv_bias(k):
+                assert (got[k] - g).abs().max() <= 1e-4 * g.abs().max() + 1e-7, k
+    sd, rs = L.state_dict(), net.state_dict()
+    assert set(sd) == set(rs)
+    for k in rs:
+        assert sd[k].shape == rs[k].shape, k
+        if not _is_conv_bias(k):
+            assert (sd[k].float() - rs[k].float()).abs().max() < 2e-4, k
+    assert int(sd["bn1.num_batches_tracked"]) == 4
+
+
+def test_state_dict_round_trip(yy):
+    from yinyang_game_alphazero_b200 import learner
+    net = _reference_net(6, 6, 16, 1, seed=3)
+    L = learner.Learner(6, 6, 16, 1, batch_size=4, state_dict=net.state_dict(), _ops=TorchEmuOps())
+    sd = L.state_dict()
+    for k, v in net.state_dict().items():
+        assert torch.equal(sd[k].float(), v.float()), k
+
+
+def test_learner_needs_cuda(yy):
+    from yinyang_game_alphazero_b200 import learner, YinYangError
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(YinYangError):
+        learner.Learner(4, 4, 8, 1, batch_size=4)
+
+
+# ------------------------------------------------------------------------------------------------------- GPU
+def _cuda_ops(precision="3xtf32"):
+    from yinyang_game_alphazero_b200 import learner
+    return learner.CudaOps(precision)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+@pytest.mark.parametrize("M,N,K,bias,relu,mode", [
+    (4096, 128, 1152, True, False, "store"),      # 3x3 convolution forward at batch 64, 8x8
+    (4096, 128, 72, True, False, "store"),        # stem (K tail zero-filled)
+    (4096, 32, 128, True, False, "store"),        # 1x1 head convolution
+    (64, 64, 2048, True, False, "store"),         # policy_fc (M < 128)
+    (64, 256, 2048, True, True, "store"),         # value_fc1 + ReLU
+    (128, 1152, 4096, False, False, "split"),     # weight gradient, split-K
+    (32, 128, 4096, False, False, "split"),       # head convolution weight gradient
+    (4096, 128, 1152, False, False, "acc"),       # backward data accumulated onto the skip share
+    (2304, 128, 1152, True, False, "store"),      # 6x6 boards
+    (200, 36, 1152, True, False, "store"),        # ragged M and N
+    (20, 2048, 20, False, False, "store"),        # tiny K
+])
+def test_gemm_tf32(yy, M, N, K, bias, relu, mode, precision):
+    ops = _cuda_ops(precision)
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    bv = torch.randn(N, generator=g) if bias else None
+    C0 = torch.randn(M, N, generator=g) if mode == "acc" else torch.zeros(M, N)
+    ref = A.double() @ B.double().t() + (bv.double() if bias else 0.0)
+    if relu:
+        ref = ref.clamp_min(0)
+    ref = ref + C0.double()
+    Cd = C0.cuda()
+    ops.gemm(A.cuda(), B.cuda(), Cd, bias=bv.cuda() if bias else None, relu=relu, accumulate=mode == "acc", split_ok=mode == "split")
+    bound = (3e-6 if precision == "3xtf32" else 1.5e-3) * (A.abs().double() @ B.abs().double().t()) + 1e-6
+    err = (Cd.cpu().double() - ref).abs()
+    assert bool((err <= bound).all()), f"max err {err.max().item():.3e} (bound {bound.max().item():.3e})"
+
+
+@pytest.mark.gpu
+def test_gemm_strided_views(yy):
+    ops = _cuda_ops()
+    A, B = torch.randn(300, 96), torch.randn(80, 96)
+    Ad, Bd = torch.zeros(300, 128).cuda(), torch.zeros(80, 100).cuda()
+    Ad[:, :96] = A.cuda(); Bd[:, :96] = B.cuda()
+    Cd = torch.full((300, 96), 7.0).cuda()
+    ops.gemm(Ad[:, :96], Bd[:, :96], Cd[:, :80])
+    ref = A.double() @ B.double().t()
+    assert (Cd[:, :80].cpu().double() - ref).abs().max() < 0.05
+    assert bool((Cd[:, 80:] == 7.0).all())            # columns past N untouched
+
+
+@pytest.mark.gpu
+def test_kernels_match_their_emulation(yy):
+    ops, emu = _cuda_ops(), TorchEmuOps()
+    g = torch.Generator().manual_seed(5)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    cu = lambda t: t.cuda() if t is not None else None
+    for rows, cols, C, Bt in ((8, 8, 128, 16), (6, 6, 32, 5), (4, 4, 8, 3)):
+        P = Bt * rows * cols
+        X = rn(P, C)
+        for flip in (False, True):
+            o_ref, o = torch.zeros(P, 9 * C), torch.zeros(P, 9 * C).cuda()
+            emu.im2col(X, o_ref, rows, cols, flip); ops.im2col(cu(X), o, rows, cols, flip)
+            assert torch.equal(o.cpu(), o_ref)
+        t_ref, t = torch.zeros(C, P), torch.zeros(C, P).cuda()
+        emu.transpose(X, t_ref); ops.transpose(cu(X), t)
+        assert torch.equal(t.cpu(), t_ref)
+        W = rn(C, 9 * 8)
+        wt_ref, wt = torch.zeros(8, 9 * C), torch.zeros(8, 9 * C).cuda()
+        emu.conv_weight_t(W, wt_ref, C, 8); ops.conv_weight_t(cu(W), wt, C, 8)
+        assert torch.equal(wt.cpu(), wt_ref)
+        cs_ref, cs = torch.zeros(C), torch.zeros(C).cuda()
+        emu.colsum(X, cs_ref); ops.colsum(cu(X), cs)
+        assert torch.allclose(cs.cpu(), cs_ref, rtol=1e-6, atol=1e-6)
+        planes = rn(Bt, 5, rows, cols)
+        x0_ref, x0 = torch.zeros(P, 8), torch.zeros(P, 8).cuda()
+        emu.planes_nhwc(planes, x0_ref); ops.planes_nhwc(cu(planes), x0)
+        assert torch.equal(x0.cpu(), x0_ref)
+        # batch norm forward / backward (with and without skip connection / ReLU)
+        Y = rn(P, C) * 2 + 0.5
+        gamma, beta, res = rn(C) + 1, rn(C), rn(P, C)
+        for residual, relu in ((None, True), (res, True), (None, False)):
+            out_ref, mi_ref, rm_ref, rv_ref = torch.zeros(P, C), torch.zeros(2 * C), torch.zeros(C), torch.ones(C)
+            out, mi, rm, rv = (t.clone().cuda() for t in (out_ref, mi_ref, rm_ref, rv_ref))
+            ws = torch.zeros(256, dtype=torch.float64).cuda()
+            emu.bn_forward(Y, gamma, beta, residual, out_ref, relu, 1e-5, 0.1, None, mi_ref, rm_ref, rv_ref)
+            ops.bn_forward(cu(Y), cu(gamma), cu(beta), cu(residual), out, relu, 1e-5, 0.1, ws, mi, rm, rv)
+            assert torch.allclose(out.cpu(), out_ref, rtol=1e-5, atol=1e-5)
+            assert torch.allclose(mi.cpu(), mi_ref, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(rm.cpu(), rm_ref, rtol=1e-5, atol=1e-6) and torch.allclose(rv.cpu(), rv_ref, rtol=1e-5, atol=1e-6)
+            dOut = rn(P, C)
+            for want_res in (False, True):
+                dy_ref, dr_ref, dg_ref, db_ref = torch.zeros(P, C), torch.zeros(P, C), torch.zeros(C), torch.zeros(C)
+                dy, dr, dg, db = (t.clone().cuda() for t in (dy_ref, dr_ref, dg_ref, db_ref))
+                emu.bn_backward(dOut, out_ref if relu else None, Y, mi_ref, gamma, None, dy_ref, dr_ref if want_res else None, dg_ref, db_ref)
+                ops.bn_backward(cu(dOut), out if relu else None, cu(Y), mi, cu(gamma), ws, dy, dr if want_res else None, dg, db)
+                assert torch.allclose(dy.cpu(), dy_ref, rtol=1e-4, atol=1e-5)
+                assert torch.allclose(dg.cpu(), dg_ref, rtol=1e-4, atol=1e-4) and torch.allclose(db.cpu(), db_ref, rtol=1e-4, atol=1e-4)
+                if want_res:
+                    assert torch.equal(dr.cpu(), dr_ref)
+    # heads
+    for B, A, H in ((64, 64, 256), (5, 36, 256), (3, 16, 64)):
+        logits, pi = rn(B, A) * 3, torch.softmax(rn(B, A), 1)
+        h, w2, b2, z = rn(B, H).clamp_min(0), rn(H) * 0.1, rn(1), torch.rand(B, generator=g) * 2 - 1
+        outs_ref = [torch.zeros(B, A), torch.zeros(B, H), torch.zeros(B), torch.zeros(B), torch.zeros(H), torch.zeros(1), torch.zeros(2)]
+        outs = [t.clone().cuda() for t in outs_ref]
+        emu.heads_loss(logits, pi, h, w2, b2, z, *outs_ref)
+        ops.heads_loss(cu(logits), cu(pi), cu(h), cu(w2), cu(b2), cu(z), *outs)
+        for a, b_ in zip(outs, outs_ref):
+            assert torch.allclose(a.cpu(), b_, rtol=2e-4, atol=2e-6)
+    # Adam, three steps
+    n = 10_001
+    p_ref, gr, m_ref, v_ref, st_ref = rn(n), rn(n) * 0.01, torch.zeros(n), torch.zeros(n), torch.zeros(1, dtype=torch.int32)
+    p, m_, v_, st = p_ref.clone().cuda(), m_ref.clone().cuda(), v_ref.clone().cuda(), st_ref.clone().cuda()
+    for _ in range(3):
+        emu.adam(p_ref, gr, m_ref, v_ref, 1e-3, 0.9, 0.999, 1e-8, 1e-4, st_ref)
+        ops.adam(p, cu(gr), m_, v_, 1e-3, 0.9, 0.999, 1e-8, 1e-4, st)
+    assert int(st.item()) == 3
+    assert torch.allclose(p.cpu(), p_ref, rtol=1e-5, atol=1e-6) and torch.allclose(v_.cpu(), v_ref, rtol=1e-4, atol=1e-12)
+
+
+HEAD_KEYS = ("policy_fc", "value_fc1", "value_fc2", "policy_bn", "value_bn")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,C,nb,B,precision", [(8, 128, 10, 64, "3xtf32"), (6, 32, 2, 20, "3xtf32"), (8, 128, 10, 64, "tf32")])
+def test_cuda_step_matches_torch_fp32_training_step(yy, n, C, nb, B, precision):
+    """Four optimisation steps (eager, two CUDA-graph replays, a remainder batch).  Before every step the torch fp32 net
+    takes the learner's current weights, so losses and gradients are compared at identical weights (Adam's first steps
+    move every weight by ~lr * sign(gradient): trajectories from *independently* rounded gradients separate quickly,
+    which says nothing about either side); the torch Adam then steps with the LEARNER's gradients and must land on the
+    learner's new weights, which checks the fused Adam kernel along a 4-step trajectory.
+    3xTF32 (default): losses within 1e-4 relative; gradient tensors of the heads within 5e-3 (relative L2; the linear
+    layers measure 2e-5, the head batch norms 1e-3); trunk
+    tensors within 3e-2 relative L2 and cosine >= 0.9995 -- what is left there are a handful of ReLU masks (1-6 of
+    524,288 per layer, measured) whose pre-activation lies within ~1e-5 of zero and flips under a different summation
+    order.  Single-pass TF32 flips ~200 masks per layer: losses 5e-3, gradients 0.2 relative L2 / cosine 0.98
+    (measured 0.09 / 0.996)."""
+    from yinyang_game_alphazero_b200 import learner
+    tight = precision == "3xtf32"
+    net = _reference_net(n, n, C, nb, seed=7)
+    L = learner.Learner(n, n, C, nb, batch_size=B, state_dict=net.state_dict(), precision=precision)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
+    planes, pi, z = _batch(net, n, n, B, seed=8)
+    ltol = 1e-4 if tight else 5e-3
+    worst_l2, worst_cos = 0.0, 1.0
+    for it, b in enumerate((B, B, B, B - 3)):
+        net.load_state_dict(L.state_dict())
+        net.train(); opt.zero_grad()
+        lg, v = net(planes[:b])
+        lp = torch.nn.CrossEntropyLoss()(lg, pi[:b]); lv = torch.nn.MSELoss()(v.view(-1), z[:b])
+        (lp + lv).backward()
+        losses = L.step(planes[:b].cuda(), pi[:b].cuda(), z[:b].cuda()).cpu()
+        assert abs(losses[0].item() - lp.item()) <= ltol * abs(lp.item()) + 1e-5, (it, losses.tolist(), lp.item(), lv.item())
+        assert abs(losses[1].item() - lv.item()) <= ltol * abs(lv.item()) + 1e-5, (it, losses.tolist(), lp.item(), lv.item())
+        got = L.grad_dict()
+        for k, p in net.named_parameters():
+            gr = p.grad
+            if not _is_conv_bias(k):
+                l2 = ((got[k] - gr).norm() / (gr.norm() + 1e-20)).item()
+                cos = torch.nn.functional.cosine_similarity(got[k].flatten().double(), gr.flatten().double(), dim=0).item()
+                worst_l2, worst_cos = max(worst_l2, l2), min(worst_cos, cos)
+                if tight:
+                    assert l2 <= (5e-3 if k.startswith(HEAD_KEYS) else 3e-2) and cos >= 0.9995, (it, k, l2, cos)
+                else:
+                    assert l2 <= 0.2 and cos >= 0.98, (it, k, l2, cos)
+            p.grad = got[k].clone()
+        opt.step()                                            # torch Adam on the learner's own gradients
+        sd = L.state_dict()
+        for k, p in net.named_parameters():
+            assert torch.allclose(sd[k], p.detach(), rtol=1e-5, atol=2e-7), (it, k, (sd[k] - p.detach()).abs().max().item())
+        for k, buf in net.named_buffers():
+            if "running" in k:
+                assert torch.allclose(sd[k], buf, rtol=2e-3 if tight else 2e-2, atol=2e-4 if tight else 2e-3), (it, k)
+    print(f"[{precision} {n}x{n} {C}x{nb}] worst gradient-tensor relative L2 error {worst_l2:.2e}, worst cosine {worst_cos:.6f}")
+    assert int(L.state_dict()["bn1.num_batches_tracked"]) == 4
+
+
+@pytest.mark.gpu
+def test_training_on_a_fixed_batch_reduces_the_loss(yy):
+    from yinyang_game_alphazero_b200 import learner
+    net = _reference_net(8, 8, 128, 10, seed=11)
+    L = learner.Learner(8, 8, 128, 10, batch_size=64, state_dict=net.state_dict())
+    planes, pi, z = (t.cuda() for t in _batch(net, 8, 8, 64, seed=12))
+    first = L.step(planes, pi, z).cpu().clone()
+    for _ in range(60):
+        last = L.step(planes, pi, z)
+    last = last.cpu()
+    assert torch.isfinite(last).all()
+    assert last.sum() < 0.7 * first.sum(), (first.tolist(), last.tolist())

@@ -13,7 +13,8 @@ Layout
   _lib.py      nvcc build + ctypes binding
   engine.py    device/host buffer API over the C ABI
   weights.py   reference checkpoint -> packed bf16 weight image (BN folded)
-  game.py, network.py, mcts.py, self_play.py, players.py, data_utils.py   host-side mirror of the reference's Python interface
+  game.py, network.py, mcts.py, self_play.py, players.py, data_utils.py, trainer.py   host-side mirror of the reference's Python interface
+  learner.py   one optimisation step of the reference trainer as a CUDA graph over the yy_lrn_* kernels (csrc/yy_learn.cu)
 """
 from . import _lib, bitboard  # noqa: F401
 from ._lib import YinYangError, build  # noqa: F401
@@ -24,7 +25,7 @@ __all__ = ["build", "YinYangError", "bitboard"]
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `build()` works in a bare interpreter
     import importlib
-    for mod in ("engine", "game", "network", "mcts", "self_play", "players", "weights", "distributed", "data_utils", "arena"):
+    for mod in ("engine", "game", "network", "mcts", "self_play", "players", "weights", "distributed", "data_utils", "arena", "learner", "trainer"):
         try:
             m = importlib.import_module(f"{__name__}.{mod}")
         except ModuleNotFoundError as e:

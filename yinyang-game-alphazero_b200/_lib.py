@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libyinyang_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "yinyang_b200.h")
-SOURCES = ["yy_rules_kernels.cu", "yy_tree.cu", "yy_probe.cu", "yy_nn.cu", "yy_fused.cu", "yy_dataset.cu"]
+SOURCES = ["yy_rules_kernels.cu", "yy_tree.cu", "yy_probe.cu", "yy_nn.cu", "yy_fused.cu", "yy_dataset.cu", "yy_learn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
@@ -84,6 +84,7 @@ _P = ctypes.c_void_p
 _I = ctypes.c_int
 _I64 = ctypes.c_int64
 _U32 = ctypes.c_uint32
+_F = ctypes.c_float
 
 # name -> (restype, argtypes); every symbol include/yinyang_b200.h declares
 SIGNATURES = {
@@ -121,6 +122,16 @@ SIGNATURES = {
     "yy_engine_game_white": (_P, [_P]),
     "yy_engine_game_player": (_P, [_P]),
     "yy_augment_samples": (_I, [_I, _I, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "yy_lrn_gemm": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "yy_lrn_im2col3x3": (_I, [_P, _I, _P, _I, _I64, _I, _I, _I, _I, _P]),
+    "yy_lrn_transpose": (_I, [_P, _I, _P, _I, _I, _I, _P]),
+    "yy_lrn_conv_weight_t": (_I, [_P, _P, _I, _I, _P]),
+    "yy_lrn_planes_nhwc": (_I, [_P, _P, _I64, _I, _P]),
+    "yy_lrn_colsum": (_I, [_P, _I, _I, _I, _P, _P]),
+    "yy_lrn_bn_forward": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
+    "yy_lrn_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P]),
+    "yy_lrn_heads_loss": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "yy_lrn_adam": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _P, _P]),
     "yy_probe_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 

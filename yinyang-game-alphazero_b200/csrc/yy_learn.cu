@@ -1,0 +1,596 @@
+// yy_learn.cu -- learner-step primitives: the kernels behind one optimisation step of
+//   AlphaZeroTrainer.train            src/yin_yang/ai/trainer.py:67-161  (Adam lr 1e-3, weight_decay 1e-4,
+//                                     CrossEntropyLoss(soft targets) + MSELoss, batch 64, nnet.train())
+//   YinYangNeuralNetwork.forward      src/yin_yang/ai/neural_network.py:94-123 in TRAINING mode (batch-norm batch statistics)
+// Activations live in HBM as fp32 [positions][channels] (positions = batch x cells, channel contiguous); every
+// convolution / linear layer and both of its gradients are ONE shape of GEMM, C[M,N] = A[M,K] * B[N,K]^T, run on the
+// 5th-gen tensor cores as tcgen05.mma kind::tf32 (fp32 operands read as TF32, fp32 accumulation in TMEM) -- the
+// precision torch itself uses for fp32 convolutions on a GPU.  3x3 convolutions reach that shape through an explicit
+// im2col (a batch of 64 boards is 4,096 positions: the whole step is a few hundred microsecond-sized kernels, captured
+// in one CUDA graph by the host side, learner.py).  Batch-norm statistics are accumulated in float64.
+#include "yy_common.cuh"
+#include "yy_ptx.cuh"
+
+namespace yy {
+using namespace ptx;
+
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 x tf32 -> fp32 (K = 8 per instruction), issued by ONE thread
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Instruction descriptor for kind::tf32: D fp32, A/B tf32 (format 2), both K-major, dense, MxN tile.
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM
+// C[M,N] (ldc) = A[M,K] (lda) * B[N,K]^T (ldb) [+ bias[n]] [ReLU], or C += ... (atomic) for split-K / accumulation onto
+// an initialised C.  One CTA per (128-row, tile_n-column, K-slice) tile.  Operands go global -> shared with 16-byte
+// cp.async straight into the no-swizzle K-major core-matrix layout ([K/4 chunk planes][row][16 B], plane pitch
+// rows*16+16 B so that the scatter is bank-conflict free; rows/columns/K past the end are zero-filled), stages of
+// 32 K-values; one elected thread issues the MMAs of a stage and commits the stage's "free" mbarrier.
+// X3 (default precision of the learner): every operand chunk is split in shared memory, by the thread that loaded it,
+// into hi = the 19 bits a TF32 multiplier sees and lo = x - hi, and each K-slice runs three MMAs (lo*hi + hi*lo + hi*hi)
+// -- "3xTF32": products carry ~21 mantissa bits, i.e. fp32-level results (the reference trains in fp32; with plain TF32
+// ~4e-4 of the ReLU masks flip and the gradients differ from fp32 by 5-9 % in L2).
+constexpr int kGemmKStage = 32;   // floats of K per stage = 8 16-byte chunks = 4 K-slices of 8
+constexpr int kGemmPlaneA = 128 * 16 + 16;
+
+struct GemmArgs {
+  const float* A; const float* B; float* C; const float* bias;
+  int lda, ldb, ldc, M, N, K, tile_n, k_per_split, relu, atomic;
+};
+
+__device__ __forceinline__ void split_chunk(uint8_t* hi_ptr, uint8_t* lo_ptr) {
+  float4 v = *reinterpret_cast<float4*>(hi_ptr);
+  float4 h = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                         __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+  *reinterpret_cast<float4*>(hi_ptr) = h;
+  *reinterpret_cast<float4*>(lo_ptr) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
+template <int S, bool X3>
+__global__ void __launch_bounds__(128) gemm_tf32_kernel(GemmArgs g) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t free_bar[S];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * g.tile_n;
+  const int k_begin = blockIdx.z * g.k_per_split;
+  const int k_end = min(g.K, k_begin + g.k_per_split);
+  const int KT = (k_end - k_begin + kGemmKStage - 1) / kGemmKStage;
+  const int planeB = g.tile_n * 16 + 16;
+  const int half_bytes = 8 * (kGemmPlaneA + planeB);          // one copy (hi) of a stage's A and B tiles
+  const int stage_bytes = X3 ? 2 * half_bytes : half_bytes;
+  uint32_t ncols = 32; while ((int)ncols < g.tile_n) ncols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(smem_u32(&free_bar[s]), 1);
+    mbar_init(smem_u32(&done_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t smem0 = smem_u32(smem);
+  const int chunk = tid & 7;
+
+  auto load_stage = [&](int s, int kt) {
+    const int kbase = k_begin + kt * kGemmKStage;
+    const uint32_t sA = smem0 + (uint32_t)(s * stage_bytes), sB = sA + 8u * kGemmPlaneA;
+    const int k = kbase + chunk * 4;
+    const bool kok = k < k_end;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = (tid >> 3) + 16 * i;
+      const bool ok = kok && (m0 + row) < g.M;
+      cp_async16(sA + (uint32_t)(chunk * kGemmPlaneA + row * 16), ok ? g.A + (size_t)(m0 + row) * g.lda + k : g.A, ok);
+    }
+    for (int row = tid >> 3; row < g.tile_n; row += 16) {
+      const bool ok = kok && (n0 + row) < g.N;
+      cp_async16(sB + (uint32_t)(chunk * planeB + row * 16), ok ? g.B + (size_t)(n0 + row) * g.ldb + k : g.B, ok);
+    }
+  };
+  auto split_stage = [&](int s) {   // every thread splits exactly the chunks it copied (visible to it after wait_group)
+    uint8_t* a = smem + (size_t)s * stage_bytes;
+    uint8_t* b = a + 8 * kGemmPlaneA;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint8_t* p = a + chunk * kGemmPlaneA + ((tid >> 3) + 16 * i) * 16;
+      split_chunk(p, p + half_bytes);
+    }
+    for (int row = tid >> 3; row < g.tile_n; row += 16) {
+      uint8_t* p = b + chunk * planeB + row * 16;
+      split_chunk(p, p + half_bytes);
+    }
+  };
+
+  for (int s = 0; s < S - 1; ++s) {
+    if (s < KT) load_stage(s, s);
+    cp_async_commit();
+  }
+  const uint32_t idesc = idesc_tf32(128, g.tile_n);
+  for (int kt = 0; kt < KT; ++kt) {
+    const int s = kt % S;
+    cp_async_wait<S - 2>();
+    if (X3) split_stage(s);
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        const uint32_t sA = smem0 + (uint32_t)(s * stage_bytes), sB = sA + 8u * kGemmPlaneA;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t ad = smem_desc(sA + (uint32_t)(2 * j * kGemmPlaneA), kGemmPlaneA, 128);
+          const uint64_t bd = smem_desc(sB + (uint32_t)(2 * j * planeB), planeB, 128);
+          const uint32_t first = (kt > 0 || j > 0) ? 1u : 0u;
+          if (X3) {
+            const uint64_t adl = smem_desc(sA + (uint32_t)(half_bytes + 2 * j * kGemmPlaneA), kGemmPlaneA, 128);
+            const uint64_t bdl = smem_desc(sB + (uint32_t)(half_bytes + 2 * j * planeB), planeB, 128);
+            tc_mma_tf32(tmem_base, adl, bd, idesc, first);
+            tc_mma_tf32(tmem_base, ad, bdl, idesc, 1u);
+            tc_mma_tf32(tmem_base, ad, bd, idesc, 1u);
+          } else {
+            tc_mma_tf32(tmem_base, ad, bd, idesc, first);
+          }
+        }
+        tc_commit(smem_u32(&free_bar[s]));
+      }
+      __syncwarp();
+    }
+    const int nxt = kt + S - 1;
+    if (nxt < KT) {
+      if (kt >= 1) mbar_wait(smem_u32(&free_bar[(kt - 1) % S]), (uint32_t)(((kt - 1) / S) & 1));
+      load_stage(nxt % S, nxt);
+    }
+    cp_async_commit();
+  }
+  if (warp == 0) {
+    if (elect_one()) tc_commit(smem_u32(&done_bar));
+    __syncwarp();
+  }
+  mbar_wait(smem_u32(&done_bar), 0);
+  tc_fence_after();
+
+  // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane
+  const int row = m0 + warp * 32 + lane;
+  const bool add_bias = g.bias != nullptr && blockIdx.z == 0;
+  for (int c = 0; c < g.tile_n; c += 16) {
+    uint32_t r[16];
+    if (KT > 0) {
+      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, r);
+      tc_wait_ld();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = 0u;
+    }
+    if (row < g.M) {
+      float* crow = g.C + (size_t)row * g.ldc;
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        const int n = n0 + c + j4;
+        if (n + 3 < g.N) {
+          float4 v = make_float4(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]));
+          if (add_bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
+          if (g.atomic) {
+            atomicAdd(crow + n, v.x); atomicAdd(crow + n + 1, v.y); atomicAdd(crow + n + 2, v.z); atomicAdd(crow + n + 3, v.w);
+          } else {
+            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *reinterpret_cast<float4*>(crow + n) = v;
+          }
+        } else {
+          for (int j = j4; j < j4 + 4; ++j) {
+            const int nn = n0 + c + j;
+            if (nn < g.N) {
+              float v = __uint_as_float(r[j]);
+              if (add_bias) v += g.bias[nn];
+              if (g.atomic) atomicAdd(crow + nn, v);
+              else crow[nn] = g.relu ? fmaxf(v, 0.f) : v;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------ im2col / layout kernels
+// out[p][t*C + c] = X[p + d(t)][c] (zero outside the board), t = (dx+1)*3 + (dy+1), d(t) = dx*cols + dy;
+// flip != 0 negates (dx, dy): the gather a transposed convolution (backward-data) needs.
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out, int ldo,
+                                                       long long P, int rows, int cols, int C4, int flip) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = P * 9 * C4;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  const int t = (int)((idx / C4) % 9);
+  const long long p = idx / (9 * C4);
+  const int cell = (int)(p % (rows * cols)), x = cell / cols, y = cell % cols;
+  int dx = t / 3 - 1, dy = t % 3 - 1;
+  if (flip) { dx = -dx; dy = -dy; }
+  const int xx = x + dx, yy = y + dy;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (xx >= 0 && xx < rows && yy >= 0 && yy < cols)
+    v = *reinterpret_cast<const float4*>(X + (size_t)(p + dx * cols + dy) * ldx + c4 * 4);
+  *reinterpret_cast<float4*>(out + (size_t)p * ldo + t * (C4 * 4) + c4 * 4) = v;
+}
+
+// out[c][r] = in[r][c]
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < R && c < C) ? in[(size_t)r * ldi + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (c < C && r < R) out[(size_t)c * ldo + r] = tile[tx][j];
+  }
+}
+
+// Wt[ci][t*Cout + co] = W[co][t*Cin + ci]  (operand of the backward-data GEMM; the tap flip lives in im2col)
+__global__ void __launch_bounds__(256) conv_weight_t_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Cout, int Cin) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * 9 * Cin) return;
+  const int co = idx % Cout, t = (idx / Cout) % 9, ci = idx / (9 * Cout);
+  Wt[idx] = W[(size_t)co * 9 * Cin + t * Cin + ci];
+}
+
+// planes float32 [B][5][cells] (board_to_input, neural_network.py:156-196) -> X0 [B*cells][8] (channels 5..7 zero)
+__global__ void __launch_bounds__(256) planes_nhwc_kernel(const float* __restrict__ planes, float* __restrict__ X0, long long P, int cells) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const long long b = p / cells; const int cell = (int)(p % cells);
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = c < 5 ? planes[(size_t)(b * 5 + c) * cells + cell] : 0.f;
+  float4* o = reinterpret_cast<float4*>(X0 + (size_t)p * 8);
+  o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// out[c] = sum_r X[r][c] (bias gradients); float64 accumulation, deterministic
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ld, int R, int C, float* __restrict__ out) {
+  __shared__ double part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  double s = 0.0;
+  if (c < C) for (int r = ty; r < R; r += 8) s += (double)X[(size_t)r * ld + c];
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) s += part[j][tx];
+    out[c] = (float)s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ batch norm (training mode)
+// nn.BatchNorm2d forward in train(): statistics over all P positions of the batch (biased variance for the
+// normalisation, unbiased for running_var, momentum 0.1, eps 1e-5).  sums = float64 [2C]: sum, sum of squares.
+__global__ void __launch_bounds__(128) bn_stats_kernel(const float* __restrict__ Y, int ld, int P, int C, double* __restrict__ sums, int rows_per_block) {
+  const int c = threadIdx.x % C, rl = threadIdx.x / C, lanes = blockDim.x / C;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(P, r0 + rows_per_block);
+  float s = 0.f, q = 0.f;
+  if (rl < lanes)
+    for (int r = r0 + rl; r < r1; r += lanes) { const float v = Y[(size_t)r * ld + c]; s += v; q += v * v; }
+  if (rl < lanes) { atomicAdd(&sums[c], (double)s); atomicAdd(&sums[C + c], (double)q); }
+}
+// mean_invstd float [2C]; running_mean / running_var updated in place (may be NULL)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int P, int C, float eps, float momentum, float* __restrict__ mean_invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / P;
+  double var = sums[C + c] / P - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_invstd[c] = (float)mean;
+  mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(P > 1 ? var * P / (P - 1) : var);
+}
+// out = [relu]( gamma * (Y - mean) * invstd + beta [+ residual] )
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ Y, int ld, long long P, int C4, const float* __restrict__ mean_invstd,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ residual,
+                                                      int ldr, float* __restrict__ out, int ldo, int relu) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * C4) return;
+  const int c = (int)(idx % C4) * 4; const long long p = idx / C4; const int C = C4 * 4;
+  const float4 y = *reinterpret_cast<const float4*>(Y + (size_t)p * ld + c);
+  const float4 mu = *reinterpret_cast<const float4*>(mean_invstd + c), is = *reinterpret_cast<const float4*>(mean_invstd + C + c);
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+  float4 o = make_float4((y.x - mu.x) * is.x * ga.x + be.x, (y.y - mu.y) * is.y * ga.y + be.y, (y.z - mu.z) * is.z * ga.z + be.z,
+                         (y.w - mu.w) * is.w * ga.w + be.w);
+  if (residual) {
+    const float4 r = *reinterpret_cast<const float4*>(residual + (size_t)p * ldr + c);
+    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+  }
+  if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+  *reinterpret_cast<float4*>(out + (size_t)p * ldo + c) = o;
+}
+// backward, pass 1: sums[c] += sum_p dZ*xhat (= d gamma), sums[C+c] += sum_p dZ (= d beta), dZ = dOut * [Out > 0]
+__global__ void __launch_bounds__(128) bn_bwd_reduce_kernel(const float* __restrict__ dOut, int ldd, const float* __restrict__ Out, int ldo,
+                                                           const float* __restrict__ Y, int ldy, const float* __restrict__ mean_invstd, int P, int C,
+                                                           double* __restrict__ sums, int rows_per_block) {
+  const int c = threadIdx.x % C, rl = threadIdx.x / C, lanes = blockDim.x / C;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(P, r0 + rows_per_block);
+  const float mu = mean_invstd[c], is = mean_invstd[C + c];
+  float sg = 0.f, sb = 0.f;
+  if (rl < lanes)
+    for (int r = r0 + rl; r < r1; r += lanes) {
+      float dz = dOut[(size_t)r * ldd + c];
+      if (Out && !(Out[(size_t)r * ldo + c] > 0.f)) dz = 0.f;
+      sg += dz * ((Y[(size_t)r * ldy + c] - mu) * is); sb += dz;
+    }
+  if (rl < lanes) { atomicAdd(&sums[c], (double)sg); atomicAdd(&sums[C + c], (double)sb); }
+}
+// backward, pass 2: dY = gamma*invstd*(dZ - dbeta/P - xhat*dgamma/P); optional dRes = dZ (the skip connection's share);
+// block 0 also writes d gamma / d beta into the gradient buffer.
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dOut, int ldd, const float* __restrict__ Out, int ldo,
+                                                          const float* __restrict__ Y, int ldy, const float* __restrict__ mean_invstd,
+                                                          const float* __restrict__ gamma, const double* __restrict__ sums, long long P, int C4,
+                                                          float* __restrict__ dY, int lddy, float* __restrict__ dRes, int lddr,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = C4 * 4;
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = (float)sums[c]; dbeta[c] = (float)sums[C + c]; }
+  if (idx >= P * C4) return;
+  const int c = (int)(idx % C4) * 4; const long long p = idx / C4;
+  const float invP = 1.f / (float)P;
+  float dz[4], y[4], o[4];
+  *reinterpret_cast<float4*>(dz) = *reinterpret_cast<const float4*>(dOut + (size_t)p * ldd + c);
+  *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Y + (size_t)p * ldy + c);
+  if (Out) {
+    *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(Out + (size_t)p * ldo + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (!(o[j] > 0.f)) dz[j] = 0.f;
+  }
+  float r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float mu = mean_invstd[c + j], is = mean_invstd[C + c + j];
+    const float xhat = (y[j] - mu) * is;
+    r[j] = gamma[c + j] * is * (dz[j] - (float)sums[C + c + j] * invP - xhat * (float)sums[c + j] * invP);
+  }
+  *reinterpret_cast<float4*>(dY + (size_t)p * lddy + c) = *reinterpret_cast<float4*>(r);
+  if (dRes) *reinterpret_cast<float4*>(dRes + (size_t)p * lddr + c) = *reinterpret_cast<float4*>(dz);
+}
+
+// ------------------------------------------------------------------------------------------------ heads: losses and their gradients
+// One warp per sample.  Policy: nn.CrossEntropyLoss with probability targets (trainer.py:61,131): loss_p = mean_b( -sum_a pi*log_softmax ),
+// dlogits = (softmax * sum(pi) - pi) / B.  Value: v = tanh(h . w2 + b2) (neural_network.py:119-121), nn.MSELoss (trainer.py:60,132):
+// loss_v = mean_b (v - z)^2; dpre = 2 (v - z)/B * (1 - v^2); dh = dpre * w2 * [h > 0] (h is stored after its ReLU).
+// losses[0] += policy loss, losses[1] += value loss (zeroed by the caller).
+__global__ void __launch_bounds__(128) heads_loss_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ pi, int A,
+                                                        const float* __restrict__ h, int ldh, int H, const float* __restrict__ w2,
+                                                        const float* __restrict__ b2, const float* __restrict__ z, int B,
+                                                        float* __restrict__ dlogits, int lddl, float* __restrict__ dh, int lddh,
+                                                        float* __restrict__ dpre_out, float* __restrict__ v_out, float* __restrict__ losses) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* lg = logits + (size_t)b * ldl;
+  const float* pb = pi + (size_t)b * A;
+  float mx = -INFINITY;
+  for (int a = lane; a < A; a += 32) mx = fmaxf(mx, lg[a]);
+  for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  float se = 0.f, sp = 0.f, spl = 0.f;
+  for (int a = lane; a < A; a += 32) { se += expf(lg[a] - mx); sp += pb[a]; spl += pb[a] * (lg[a] - mx); }
+  for (int d = 16; d; d >>= 1) {
+    se += __shfl_xor_sync(0xffffffffu, se, d); sp += __shfl_xor_sync(0xffffffffu, sp, d); spl += __shfl_xor_sync(0xffffffffu, spl, d);
+  }
+  const float lse = logf(se);
+  const float invB = 1.f / (float)B;
+  for (int a = lane; a < A; a += 32) dlogits[(size_t)b * lddl + a] = (expf(lg[a] - mx - lse) * sp - pb[a]) * invB;
+  const float* hb = h + (size_t)b * ldh;
+  float dot = 0.f;
+  for (int j = lane; j < H; j += 32) dot += hb[j] * w2[j];
+  for (int d = 16; d; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
+  const float v = tanhf(dot + b2[0]);
+  const float err = v - z[b];
+  const float dpre = 2.f * err * invB * (1.f - v * v);
+  for (int j = lane; j < H; j += 32) dh[(size_t)b * lddh + j] = hb[j] > 0.f ? dpre * w2[j] : 0.f;
+  if (lane == 0) {
+    dpre_out[b] = dpre; v_out[b] = v;
+    atomicAdd(&losses[0], (lse * sp - spl) * invB);
+    atomicAdd(&losses[1], err * err * invB);
+  }
+}
+// dw2[j] = sum_b dpre[b]*h[b][j]; db2 = sum_b dpre[b]
+__global__ void value_fc2_grad_kernel(const float* __restrict__ dpre, const float* __restrict__ h, int ldh, int H, int B,
+                                      float* __restrict__ dw2, float* __restrict__ db2) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < H) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dpre[b] * h[(size_t)b * ldh + j];
+    dw2[j] = s;
+  }
+  if (j == 0) { float s = 0.f; for (int b = 0; b < B; ++b) s += dpre[b]; db2[0] = s; }
+}
+
+// ------------------------------------------------------------------------------------------------ Adam (torch.optim.Adam, trainer.py:52-56)
+__global__ void adam_tick_kernel(int* step) { *step += 1; }
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                  long long n, float lr, float b1, float b2, float eps, float wd, const int* __restrict__ step) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = *step;
+  const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+  const float step_size = (float)((double)lr / bc1), bc2s = (float)sqrt(bc2);
+  const float pi = p[i];
+  const float gi = g[i] + wd * pi;                          // L2 weight decay folded into the gradient
+  const float mi = m[i] + (gi - m[i]) * (1.f - b1);         // exp_avg.lerp_(grad, 1 - beta1)
+  const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2s + eps));
+}
+
+static int need_device() {
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) { cudaGetLastError(); return set_error(YY_ERR_NO_DEVICE, "no CUDA device: the learner has no CPU fallback"); }
+  return YY_OK;
+}
+
+}  // namespace yy
+
+using namespace yy;
+
+extern "C" {
+
+int yy_lrn_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const float* bias,
+                int relu, int atomic, int tile_n, int split_k, int precision, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(YY_ERR_INVALID, "gemm: empty problem");
+  if ((lda | ldb | ldc | K) & 3) return set_error(YY_ERR_INVALID, "gemm: lda, ldb, ldc and K must be multiples of 4 floats");
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return set_error(YY_ERR_INVALID, "gemm: operands must be 16-byte aligned");
+  if (precision != YY_GEMM_TF32 && precision != YY_GEMM_3XTF32) return set_error(YY_ERR_INVALID, "gemm: precision must be YY_GEMM_TF32 or YY_GEMM_3XTF32");
+  const int max_tile = precision == YY_GEMM_3XTF32 ? 128 : 256;
+  if (tile_n < 16 || tile_n > max_tile || tile_n % 16) return set_error(YY_ERR_INVALID, "gemm: tile_n in [16,%d] step 16", max_tile);
+  if (split_k < 1) return set_error(YY_ERR_INVALID, "gemm: split_k >= 1");
+  if (split_k > 1 && !atomic) return set_error(YY_ERR_INVALID, "gemm: split-K needs the atomic epilogue (C initialised by the caller)");
+  if (atomic && relu) return set_error(YY_ERR_INVALID, "gemm: ReLU cannot follow an atomic accumulation");
+  int kps = (K + split_k - 1) / split_k;
+  kps = (kps + kGemmKStage - 1) / kGemmKStage * kGemmKStage;
+  const int zs = (K + kps - 1) / kps;
+  GemmArgs g{A, B, C, bias, lda, ldb, ldc, M, N, K, tile_n, kps, relu, atomic};
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + tile_n - 1) / tile_n), (unsigned)zs);
+  const int half = 8 * (kGemmPlaneA + tile_n * 16 + 16);
+  if (precision == YY_GEMM_3XTF32) {
+    const int smem = 3 * 2 * half;
+    static int max_set = 0;
+    if (smem > max_set) {
+      YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      max_set = smem;
+    }
+    gemm_tf32_kernel<3, true><<<grid, 128, smem, (cudaStream_t)stream>>>(g);
+  } else {
+    const int smem = 4 * half;
+    static int max_set = 0;
+    if (smem > max_set) {
+      YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      max_set = smem;
+    }
+    gemm_tf32_kernel<4, false><<<grid, 128, smem, (cudaStream_t)stream>>>(g);
+  }
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_lrn_im2col3x3(const float* X, int ldx, float* out, int ldo, int64_t positions, int rows, int cols, int C, int flip, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  if (C % 4 || ldx % 4 || ldo % 4 || ldo < 9 * C) return set_error(YY_ERR_INVALID, "im2col: C, ldx, ldo multiples of 4, ldo >= 9*C");
+  if (positions % (rows * cols)) return set_error(YY_ERR_INVALID, "im2col: positions must be whole boards");
+  const long long total = positions * 9 * (C / 4);
+  if (total == 0) return YY_OK;
+  im2col3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, out, ldo, positions, rows, cols, C / 4, flip);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_lrn_transpose(const float* in, int ldi, float* out, int ldo, int R, int C, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  if (R <= 0 || C <= 0) return YY_OK;
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32));
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ldi, out, ldo, R, C);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_lrn_conv_weight_t(const float* W, float* Wt, int Cout, int Cin, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  const int total = Cout * 9 * Cin;
+  conv_weight_t_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, Wt, Cout, Cin);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_lrn_planes_nhwc(const float* planes, float* X0, int64_t boards, int cells, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  const long long P = boards * cells;
+  if (P == 0) return YY_OK;
+  planes_nhwc_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, X0, P, cells);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_lrn_colsum(const float* X, int ld, int R, int C, float* out, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  colsum_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(X, ld, R, C, out);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+static int bn_shape_ok(int C) { return C >= 4 && C <= 128 && 128 % C == 0; }
+
+int yy_lrn_bn_forward(const float* Y, int ld, int P, int C, const float* gamma, const float* beta, const float* residual, int ldr,
+                      float* out, int ldo, int relu, float eps, float momentum, double* sums_ws, float* mean_invstd,
+                      float* running_mean, float* running_var, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
+  cudaStream_t st = (cudaStream_t)stream;
+  YY_CUDA_OK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * 2 * C, st));
+  const int rpb = 32;
+  bn_stats_kernel<<<(P + rpb - 1) / rpb, 128, 0, st>>>(Y, ld, P, C, sums_ws, rpb);
+  YY_LAUNCH_CHECK();
+  bn_finalize_kernel<<<1, 128, 0, st>>>(sums_ws, P, C, eps, momentum, mean_invstd, running_mean, running_var);
+  YY_LAUNCH_CHECK();
+  const long long total = (long long)P * (C / 4);
+  bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Y, ld, P, C / 4, mean_invstd, gamma, beta, residual, ldr, out, ldo, relu);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_lrn_bn_backward(const float* dOut, int ldd, const float* Out, int ldo, const float* Y, int ldy, int P, int C,
+                       const float* mean_invstd, const float* gamma, double* sums_ws, float* dY, int lddy, float* dRes, int lddr,
+                       float* dgamma, float* dbeta, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
+  cudaStream_t st = (cudaStream_t)stream;
+  YY_CUDA_OK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * 2 * C, st));
+  const int rpb = 32;
+  bn_bwd_reduce_kernel<<<(P + rpb - 1) / rpb, 128, 0, st>>>(dOut, ldd, Out, ldo, Y, ldy, mean_invstd, P, C, sums_ws, rpb);
+  YY_LAUNCH_CHECK();
+  const long long total = (long long)P * (C / 4);
+  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dOut, ldd, Out, ldo, Y, ldy, mean_invstd, gamma, sums_ws, P, C / 4,
+                                                                      dY, lddy, dRes, lddr, dgamma, dbeta);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_lrn_heads_loss(const float* logits, int ldl, const float* pi, int A, const float* h, int ldh, int H, const float* w2,
+                      const float* b2, const float* z, int B, float* dlogits, int lddl, float* dh, int lddh, float* dpre,
+                      float* v_out, float* dw2, float* db2, float* losses, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  if (B <= 0) return set_error(YY_ERR_INVALID, "heads: empty batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  YY_CUDA_OK(cudaMemsetAsync(losses, 0, 2 * sizeof(float), st));
+  heads_loss_kernel<<<(B + 3) / 4, 128, 0, st>>>(logits, ldl, pi, A, h, ldh, H, w2, b2, z, B, dlogits, lddl, dh, lddh, dpre, v_out, losses);
+  YY_LAUNCH_CHECK();
+  value_fc2_grad_kernel<<<(H + 127) / 128, 128, 0, st>>>(dpre, h, ldh, H, B, dw2, db2);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_lrn_adam(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                float weight_decay, int* step_dev, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_tick_kernel<<<1, 1, 0, st>>>(step_dev);
+  YY_LAUNCH_CHECK();
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+}  // extern "C"
