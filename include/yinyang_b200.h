@@ -256,29 +256,42 @@ int yy_augment_samples(int rows, int cols, const uint64_t *black_dev, const uint
  * step in one CUDA graph.  Activations are float32 [positions][channels] (positions = batch x cells, NHWC);
  * every matrix is row-major with a leading dimension in floats; all pointers are device pointers. */
 
-/* C[M,N] = A[M,K] * B[N,K]^T (+ bias[n]) (ReLU) on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulate) --
- * nn.Conv2d / nn.Linear forward (F.conv2d via im2col, F.linear) and both of their gradients.  precision:
- * YY_GEMM_3XTF32 splits every operand into the 19 bits a TF32 multiplier reads and the remainder and runs three MMAs
- * per K-slice (lo*hi + hi*lo + hi*hi): fp32-level results, what the fp32 reference computes; YY_GEMM_TF32 is the
- * single-pass variant (torch's default for fp32 convolutions on a GPU).  atomic != 0: C += ... with float atomics onto
- * a C the caller initialised (split-K partial sums, gradient accumulation onto a skip connection's share).
- * tile_n: output columns per CTA (16..256, multiple of 16; <= 128 for 3xTF32); split_k >= 1 slices K over gridDim.z
- * (needs atomic).  lda/ldb/ldc/K multiples of 4, pointers 16-byte aligned. */
+/* C[M,N] = [C +] A[M,K] * B[N,K]^T (+ bias[n]) (ReLU) on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulate in
+ * TMEM) -- nn.Conv2d / nn.Linear forward (neural_network.py:94-123) and both of their gradients.
+ *   a_mode YY_OP_K        A is [M][K] row-major (lda)
+ *          YY_OP_K_CONV   implicit im2col: A[p][t*cin + ci] = X[p + d(t)][ci], X = [positions][cin] (lda), zero outside
+ *                         the board; t = kh*3 + kw of nn.Conv2d(kernel_size=3, padding=1); conv->flip mirrors the taps
+ *                         (the gather of the backward-data pass)
+ *   B is [N][K] row-major (ldb).
+ * precision: YY_GEMM_3XTF32 splits every operand into the 19 bits a TF32 multiplier reads and the remainder and runs
+ * three MMAs per K-slice (lo*hi + hi*lo + hi*hi): fp32-level results, what the fp32 reference computes; YY_GEMM_TF32 is
+ * the single-pass variant (torch's default for fp32 convolutions on a GPU).  accumulate != 0: the product is added to C
+ * (a skip connection's share of a gradient).  tile_n: output columns per CTA (16..128, multiple of 16); split_k >= 1
+ * slices K over gridDim.z: partial tiles go to ws (>= split*M*N floats) and a reducer adds them in slice order, so
+ * results are bit-reproducible.  lda/ldb/ldc/N/K multiples of 4, pointers 16-byte aligned. */
 #define YY_GEMM_TF32 0
 #define YY_GEMM_3XTF32 1
-int yy_lrn_gemm(const float *A, int lda, const float *B, int ldb, float *C, int ldc, int M, int N, int K,
-                const float *bias, int relu, int atomic, int tile_n, int split_k, int precision, void *stream);
-/* out[p][t*C + c] = X[p + d(t)][c], zero outside the board; t = kh*3 + kw of nn.Conv2d(kernel_size=3, padding=1)
- * (neural_network.py:21-23,43); flip != 0 mirrors the taps (the gather of the backward-data pass). */
-int yy_lrn_im2col3x3(const float *X, int ldx, float *out, int ldo, int64_t positions, int rows, int cols, int C,
-                     int flip, void *stream);
+#define YY_OP_K 0
+#define YY_OP_K_CONV 1
+typedef struct {
+  int32_t rows, cols; /* board */
+  int32_t cin;        /* channels of the gathered activation tensor (multiple of 4) */
+  int32_t flip;       /* mirror the taps                                            */
+} yy_conv_geom;
+int yy_lrn_gemm(const float *A, int lda, int a_mode, const float *B, int ldb, float *C, int ldc, int M, int N, int K,
+                const float *bias, int relu, int accumulate, int tile_n, int split_k, float *ws, int64_t ws_floats,
+                int precision, const yy_conv_geom *conv, void *stream);
 /* out[c][r] = in[r][c] */
 int yy_lrn_transpose(const float *in, int ldi, float *out, int ldo, int R, int C, void *stream);
+/* colT[t*C + c][p] = X[p + d(t)][c], zero outside the board: the transposed im2col the weight gradient of a 3x3
+ * convolution reads (dW = dY^T * colT^T; the reduction index is the position). */
+int yy_lrn_im2col_t(const float *X, int ldx, float *colT, int ldo, int64_t positions, int rows, int cols, int C,
+                    void *stream);
 /* Wt[ci][t*Cout + co] = W[co][t*Cin + ci]: the B operand of the backward-data GEMM of a 3x3 convolution. */
 int yy_lrn_conv_weight_t(const float *W, float *Wt, int Cout, int Cin, void *stream);
 /* planes float32 [boards][5][cells] (board_to_input, neural_network.py:156-196) -> X0 float32 [boards*cells][8]. */
 int yy_lrn_planes_nhwc(const float *planes, float *X0, int64_t boards, int cells, void *stream);
-/* out[c] = sum_r X[r][c] (bias gradients), float64 accumulation. */
+/* out[c] = sum_r X[r][c] (bias gradients). */
 int yy_lrn_colsum(const float *X, int ld, int R, int C, float *out, void *stream);
 /* nn.BatchNorm2d in train() (neural_network.py:22-25,44): out = [relu](gamma*(Y-mean)*invstd + beta [+ residual]) with
  * the batch's own mean / biased variance over the P positions; writes mean_invstd float[2C] for the backward pass and
@@ -292,15 +305,15 @@ int yy_lrn_bn_backward(const float *dOut, int ldd, const float *Out, int ldo, co
                        const float *mean_invstd, const float *gamma, double *sums_ws, float *dY, int lddy,
                        float *dRes, int lddr, float *dgamma, float *dbeta, void *stream);
 /* Both losses and their gradients at the heads (trainer.py:131-133; value head tail neural_network.py:119-121):
- * losses[0] = CrossEntropyLoss(logits, pi) with probability targets, losses[1] = MSELoss(tanh(h.w2 + b2), z);
- * dlogits, dh (through the ReLU that produced h), dpre[B], v_out[B], dw2[H], db2[1]. */
+ * losses[0] = CrossEntropyLoss(logits, pi) with probability targets, losses[1] = MSELoss(tanh(relu(h).w2 + b2), z),
+ * h = value_fc1's output before its ReLU; dlogits, dh (through that ReLU), dpre[B], v_out[B], dw2[H], db2[1]. */
 int yy_lrn_heads_loss(const float *logits, int ldl, const float *pi, int A, const float *h, int ldh, int H,
                       const float *w2, const float *b2, const float *z, int B, float *dlogits, int lddl, float *dh,
                       int lddh, float *dpre, float *v_out, float *dw2, float *db2, float *losses, void *stream);
-/* torch.optim.Adam step (L2 weight decay folded into the gradient) over one flat parameter buffer;
- * *step_dev is incremented first (bias correction). */
+/* torch.optim.Adam step (L2 weight decay folded into the gradient) over one flat parameter buffer (n a multiple of 4).
+ * step_state: 4 x int32 on the device; [0] = step counter (incremented first), [2..3] scratch for the bias corrections. */
 int yy_lrn_adam(float *params, const float *grads, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
-                float eps, float weight_decay, int *step_dev, void *stream);
+                float eps, float weight_decay, int *step_state, void *stream);
 
 /* tcgen05 self-test used by tests/ (C = A[M,K] * B[N,K]^T, bf16 in / fp32 out, operands in the
  * same no-swizzle K-major core-matrix layout the tower kernel uses).  Layout: csrc/yy_probe.cu. */

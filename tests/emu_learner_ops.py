@@ -6,21 +6,13 @@ import torch
 
 
 class TorchEmuOps:
-    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, split_ok=False):
-        r = A.double() @ B.double().t()
-        if bias is not None:
-            r = r + bias.double()
-        if accumulate or split_ok:
-            C.add_(r.float())
-        else:
-            C.copy_((r.clamp_min(0) if relu else r).float())
-
-    def im2col(self, X, out, rows, cols, flip=False):
+    @staticmethod
+    def _im2col(X, rows, cols, flip):
+        """[P, C] -> [P, 9*C], column t*C + c = X[p + d(t)][c] (zero outside the board), t = kh*3 + kw."""
         P, C = X.shape
         B = P // (rows * cols)
-        x = X.view(B, rows, cols, C)
-        o = out.view(B, rows, cols, 9, C)
-        o.zero_()
+        x = X.reshape(B, rows, cols, C)
+        o = X.new_zeros(B, rows, cols, 9, C)
         for t in range(9):
             dx, dy = t // 3 - 1, t % 3 - 1
             if flip:
@@ -28,9 +20,22 @@ class TorchEmuOps:
             xs, xe = max(0, -dx), min(rows, rows - dx)
             ys, ye = max(0, -dy), min(cols, cols - dy)
             o[:, xs:xe, ys:ye, t, :] = x[:, xs + dx:xe + dx, ys + dy:ye + dy, :]
+        return o.reshape(P, 9 * C)
+
+    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None):
+        Ae = A if conv is None else self._im2col(A, conv[0], conv[1], conv[3])
+        r = Ae.double() @ B.double().t()
+        if bias is not None:
+            r = r + bias.double()
+        if accumulate:
+            r = r + C.double()
+        C.copy_((r.clamp_min(0) if relu else r).float())
 
     def transpose(self, inp, out):
         out.copy_(inp.t())
+
+    def im2col_t(self, X, colT, rows, cols):
+        colT.copy_(self._im2col(X, rows, cols, False).t())
 
     def conv_weight_t(self, W, Wt, cout, cin):
         Wt.view(cin, 9, cout).copy_(W.view(cout, 9, cin).permute(2, 1, 0))
@@ -71,16 +76,16 @@ class TorchEmuOps:
         lsm = torch.log_softmax(logits, dim=1)
         losses[0] = -(pi * lsm).sum(1).mean()
         dlogits.copy_((lsm.exp() * pi.sum(1, keepdim=True) - pi) / B)
-        val = torch.tanh(h @ w2 + b2)
+        val = torch.tanh(h.clamp_min(0) @ w2 + b2)
         losses[1] = ((val - z) ** 2).mean()
         dp = 2 * (val - z) / B * (1 - val * val)
         dpre.copy_(dp); v.copy_(val)
         dh.copy_(dp[:, None] * w2[None, :] * (h > 0))
-        dw2.copy_(dp @ h); db2.copy_(dp.sum().reshape(1))
+        dw2.copy_(dp @ h.clamp_min(0)); db2.copy_(dp.sum().reshape(1))
 
     def adam(self, params, grads, m, v, lr, beta1, beta2, eps, wd, step):
-        step += 1
-        t = int(step.item())
+        step[0] += 1
+        t = int(step[0].item())
         g = grads + wd * params
         m.lerp_(g, 1 - beta1)
         v.mul_(beta2).addcmul_(g, g, value=1 - beta2)

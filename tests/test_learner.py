@@ -76,6 +76,7 @@ def test_layer_sequence_matches_autograd_with_emulated_kernels(yy):
         if not _is_conv_bias(k):
             assert (sd[k].float() - rs[k].float()).abs().max() < 2e-4, k
     assert int(sd["bn1.num_batches_tracked"]) == 4
+    assert int(L.step_count[0]) == 4
 
 
 def test_state_dict_round_trip(yy):
@@ -103,34 +104,76 @@ def _cuda_ops(precision="3xtf32"):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
-@pytest.mark.parametrize("M,N,K,bias,relu,mode", [
-    (4096, 128, 1152, True, False, "store"),      # 3x3 convolution forward at batch 64, 8x8
-    (4096, 128, 72, True, False, "store"),        # stem (K tail zero-filled)
-    (4096, 32, 128, True, False, "store"),        # 1x1 head convolution
-    (64, 64, 2048, True, False, "store"),         # policy_fc (M < 128)
-    (64, 256, 2048, True, True, "store"),         # value_fc1 + ReLU
-    (128, 1152, 4096, False, False, "split"),     # weight gradient, split-K
-    (32, 128, 4096, False, False, "split"),       # head convolution weight gradient
-    (4096, 128, 1152, False, False, "acc"),       # backward data accumulated onto the skip share
-    (2304, 128, 1152, True, False, "store"),      # 6x6 boards
-    (200, 36, 1152, True, False, "store"),        # ragged M and N
-    (20, 2048, 20, False, False, "store"),        # tiny K
+@pytest.mark.parametrize("M,N,K,bias,relu,acc", [
+    (4096, 128, 1152, True, False, False),     # K-major operands, split-K 4
+    (4096, 32, 128, True, False, False),       # 1x1 head convolution
+    (64, 64, 2048, True, False, False),        # policy_fc (M < 128), split-K
+    (64, 256, 2048, True, True, False),        # bias + ReLU through the split-K reducer
+    (4096, 128, 1152, False, False, True),     # accumulate onto C through the reducer
+    (256, 128, 96, True, True, True),          # no split: bias + skip share + ReLU in the epilogue
+    (200, 36, 1152, True, False, False),       # ragged M and N
+    (20, 2048, 20, False, False, False),       # tiny K
 ])
-def test_gemm_tf32(yy, M, N, K, bias, relu, mode, precision):
+def test_gemm_tf32(yy, M, N, K, bias, relu, acc, precision):
     ops = _cuda_ops(precision)
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
     bv = torch.randn(N, generator=g) if bias else None
-    C0 = torch.randn(M, N, generator=g) if mode == "acc" else torch.zeros(M, N)
-    ref = A.double() @ B.double().t() + (bv.double() if bias else 0.0)
+    C0 = torch.randn(M, N, generator=g) if acc else torch.zeros(M, N)
+    ref = A.double() @ B.double().t() + (bv.double() if bias else 0.0) + C0.double()
     if relu:
         ref = ref.clamp_min(0)
-    ref = ref + C0.double()
     Cd = C0.cuda()
-    ops.gemm(A.cuda(), B.cuda(), Cd, bias=bv.cuda() if bias else None, relu=relu, accumulate=mode == "acc", split_ok=mode == "split")
+    ops.gemm(A.cuda(), B.cuda(), Cd, bias=bv.cuda() if bias else None, relu=relu, accumulate=acc)
     bound = (3e-6 if precision == "3xtf32" else 1.5e-3) * (A.abs().double() @ B.abs().double().t()) + 1e-6
     err = (Cd.cpu().double() - ref).abs()
     assert bool((err <= bound).all()), f"max err {err.max().item():.3e} (bound {bound.max().item():.3e})"
+    Cd2 = C0.cuda()
+    ops.gemm(A.cuda(), B.cuda(), Cd2, bias=bv.cuda() if bias else None, relu=relu, accumulate=acc)
+    assert torch.equal(Cd, Cd2)                # split-K included, results are bit-reproducible
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,cin,cout,boards", [(8, 8, 128, 128, 64), (8, 8, 8, 128, 64), (6, 6, 32, 32, 5), (4, 4, 8, 16, 3), (5, 8, 16, 32, 7)])
+def test_convolution_passes_match_their_definition(yy, rows, cols, cin, cout, boards):
+    """The three GEMMs of a 3x3 convolution (forward with the implicit im2col, weight gradient from the transposed
+    copies, backward data with the mirrored gather) against the emulation that materialises the operands, and that
+    emulation against autograd of F.conv2d."""
+    ops, emu = _cuda_ops("3xtf32"), TorchEmuOps()
+    g = torch.Generator().manual_seed(rows * 100 + cin)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    P = boards * rows * cols
+    X, W, dY, bias = rn(P, cin), rn(cout, 9 * cin), rn(P, cout), rn(cout)
+
+    def close(c, c_ref, what):
+        assert (c.cpu() - c_ref).abs().max().item() <= 2e-5 * c_ref.abs().max().item() + 1e-6, what
+
+    y_ref, y = torch.zeros(P, cout), torch.zeros(P, cout).cuda()
+    emu.gemm(X, W, y_ref, bias=bias, conv=(rows, cols, cin, 0)); ops.gemm(X.cuda(), W.cuda(), y, bias=bias.cuda(), conv=(rows, cols, cin, 0))
+    close(y, y_ref, "forward")
+    colT_ref, colT = torch.zeros(9 * cin, P), torch.zeros(9 * cin, P).cuda()
+    emu.im2col_t(X, colT_ref, rows, cols); ops.im2col_t(X.cuda(), colT, rows, cols)
+    assert torch.equal(colT.cpu(), colT_ref)
+    dYT = torch.zeros(cout, P).cuda()
+    ops.transpose(dY.cuda(), dYT)
+    assert torch.equal(dYT.cpu(), dY.t())
+    dw_ref, dw = torch.zeros(cout, 9 * cin), torch.zeros(cout, 9 * cin).cuda()
+    emu.gemm(dY.t().contiguous(), colT_ref, dw_ref); ops.gemm(dYT, colT, dw)
+    close(dw, dw_ref, "weight gradient")
+    wt_ref, wt = torch.zeros(cin, 9 * cout), torch.zeros(cin, 9 * cout).cuda()
+    emu.conv_weight_t(W, wt_ref, cout, cin); ops.conv_weight_t(W.cuda(), wt, cout, cin)
+    assert torch.equal(wt.cpu(), wt_ref)
+    skip = rn(P, cin)
+    dx_ref, dx = skip.clone(), skip.clone().cuda()
+    emu.gemm(dY, wt_ref, dx_ref, accumulate=True, conv=(rows, cols, cout, 1)); ops.gemm(dY.cuda(), wt, dx, accumulate=True, conv=(rows, cols, cout, 1))
+    close(dx, dx_ref, "backward data")
+    xt = X.view(boards, rows, cols, cin).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wt4 = W.view(cout, 3, 3, cin).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yt = torch.nn.functional.conv2d(xt, wt4, bias, padding=1)
+    assert torch.allclose(yt.permute(0, 2, 3, 1).reshape(P, cout), y_ref, rtol=1e-4, atol=1e-4)
+    yt.backward(dY.view(boards, rows, cols, cout).permute(0, 3, 1, 2))
+    assert torch.allclose(wt4.grad.permute(0, 2, 3, 1).reshape(cout, 9 * cin), dw_ref, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(xt.grad.permute(0, 2, 3, 1).reshape(P, cin) + skip, dx_ref, rtol=1e-4, atol=1e-3)
 
 
 @pytest.mark.gpu
@@ -142,7 +185,7 @@ def test_gemm_strided_views(yy):
     Cd = torch.full((300, 96), 7.0).cuda()
     ops.gemm(Ad[:, :96], Bd[:, :96], Cd[:, :80])
     ref = A.double() @ B.double().t()
-    assert (Cd[:, :80].cpu().double() - ref).abs().max() < 0.05
+    assert (Cd[:, :80].cpu().double() - ref).abs().max() < 1e-3
     assert bool((Cd[:, 80:] == 7.0).all())            # columns past N untouched
 
 
@@ -155,20 +198,9 @@ def test_kernels_match_their_emulation(yy):
     for rows, cols, C, Bt in ((8, 8, 128, 16), (6, 6, 32, 5), (4, 4, 8, 3)):
         P = Bt * rows * cols
         X = rn(P, C)
-        for flip in (False, True):
-            o_ref, o = torch.zeros(P, 9 * C), torch.zeros(P, 9 * C).cuda()
-            emu.im2col(X, o_ref, rows, cols, flip); ops.im2col(cu(X), o, rows, cols, flip)
-            assert torch.equal(o.cpu(), o_ref)
-        t_ref, t = torch.zeros(C, P), torch.zeros(C, P).cuda()
-        emu.transpose(X, t_ref); ops.transpose(cu(X), t)
-        assert torch.equal(t.cpu(), t_ref)
-        W = rn(C, 9 * 8)
-        wt_ref, wt = torch.zeros(8, 9 * C), torch.zeros(8, 9 * C).cuda()
-        emu.conv_weight_t(W, wt_ref, C, 8); ops.conv_weight_t(cu(W), wt, C, 8)
-        assert torch.equal(wt.cpu(), wt_ref)
         cs_ref, cs = torch.zeros(C), torch.zeros(C).cuda()
         emu.colsum(X, cs_ref); ops.colsum(cu(X), cs)
-        assert torch.allclose(cs.cpu(), cs_ref, rtol=1e-6, atol=1e-6)
+        assert torch.allclose(cs.cpu(), cs_ref, rtol=1e-5, atol=1e-4)
         planes = rn(Bt, 5, rows, cols)
         x0_ref, x0 = torch.zeros(P, 8), torch.zeros(P, 8).cuda()
         emu.planes_nhwc(planes, x0_ref); ops.planes_nhwc(cu(planes), x0)
@@ -198,7 +230,7 @@ def test_kernels_match_their_emulation(yy):
     # heads
     for B, A, H in ((64, 64, 256), (5, 36, 256), (3, 16, 64)):
         logits, pi = rn(B, A) * 3, torch.softmax(rn(B, A), 1)
-        h, w2, b2, z = rn(B, H).clamp_min(0), rn(H) * 0.1, rn(1), torch.rand(B, generator=g) * 2 - 1
+        h, w2, b2, z = rn(B, H), rn(H) * 0.1, rn(1), torch.rand(B, generator=g) * 2 - 1
         outs_ref = [torch.zeros(B, A), torch.zeros(B, H), torch.zeros(B), torch.zeros(B), torch.zeros(H), torch.zeros(1), torch.zeros(2)]
         outs = [t.clone().cuda() for t in outs_ref]
         emu.heads_loss(logits, pi, h, w2, b2, z, *outs_ref)
@@ -206,13 +238,13 @@ def test_kernels_match_their_emulation(yy):
         for a, b_ in zip(outs, outs_ref):
             assert torch.allclose(a.cpu(), b_, rtol=2e-4, atol=2e-6)
     # Adam, three steps
-    n = 10_001
-    p_ref, gr, m_ref, v_ref, st_ref = rn(n), rn(n) * 0.01, torch.zeros(n), torch.zeros(n), torch.zeros(1, dtype=torch.int32)
+    n = 10_004
+    p_ref, gr, m_ref, v_ref, st_ref = rn(n), rn(n) * 0.01, torch.zeros(n), torch.zeros(n), torch.zeros(4, dtype=torch.int32)
     p, m_, v_, st = p_ref.clone().cuda(), m_ref.clone().cuda(), v_ref.clone().cuda(), st_ref.clone().cuda()
     for _ in range(3):
         emu.adam(p_ref, gr, m_ref, v_ref, 1e-3, 0.9, 0.999, 1e-8, 1e-4, st_ref)
         ops.adam(p, cu(gr), m_, v_, 1e-3, 0.9, 0.999, 1e-8, 1e-4, st)
-    assert int(st.item()) == 3
+    assert int(st[0].item()) == 3
     assert torch.allclose(p.cpu(), p_ref, rtol=1e-5, atol=1e-6) and torch.allclose(v_.cpu(), v_ref, rtol=1e-4, atol=1e-12)
 
 

@@ -74,6 +74,11 @@ class SelfPlayStats(ctypes.Structure):
                 ("max_depth", ctypes.c_int32)]
 
 
+class ConvGeom(ctypes.Structure):
+    """yy_conv_geom (include/yinyang_b200.h)."""
+    _fields_ = [("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("cin", ctypes.c_int32), ("flip", ctypes.c_int32)]
+
+
 class ReplayView(ctypes.Structure):
     _fields_ = [("black", ctypes.c_void_p), ("white", ctypes.c_void_p), ("counts", ctypes.c_void_p),
                 ("game_serial", ctypes.c_void_p), ("ply", ctypes.c_void_p), ("player", ctypes.c_void_p),
@@ -122,9 +127,9 @@ SIGNATURES = {
     "yy_engine_game_white": (_P, [_P]),
     "yy_engine_game_player": (_P, [_P]),
     "yy_augment_samples": (_I, [_I, _I, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
-    "yy_lrn_gemm": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
-    "yy_lrn_im2col3x3": (_I, [_P, _I, _P, _I, _I64, _I, _I, _I, _I, _P]),
+    "yy_lrn_gemm": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I64, _I, _P, _P]),
     "yy_lrn_transpose": (_I, [_P, _I, _P, _I, _I, _I, _P]),
+    "yy_lrn_im2col_t": (_I, [_P, _I, _P, _I, _I64, _I, _I, _I, _P]),
     "yy_lrn_conv_weight_t": (_I, [_P, _P, _I, _I, _P]),
     "yy_lrn_planes_nhwc": (_I, [_P, _P, _I64, _I, _P]),
     "yy_lrn_colsum": (_I, [_P, _I, _I, _I, _P, _P]),

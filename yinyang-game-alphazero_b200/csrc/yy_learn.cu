@@ -2,12 +2,17 @@
 //   AlphaZeroTrainer.train            src/yin_yang/ai/trainer.py:67-161  (Adam lr 1e-3, weight_decay 1e-4,
 //                                     CrossEntropyLoss(soft targets) + MSELoss, batch 64, nnet.train())
 //   YinYangNeuralNetwork.forward      src/yin_yang/ai/neural_network.py:94-123 in TRAINING mode (batch-norm batch statistics)
-// Activations live in HBM as fp32 [positions][channels] (positions = batch x cells, channel contiguous); every
-// convolution / linear layer and both of its gradients are ONE shape of GEMM, C[M,N] = A[M,K] * B[N,K]^T, run on the
-// 5th-gen tensor cores as tcgen05.mma kind::tf32 (fp32 operands read as TF32, fp32 accumulation in TMEM) -- the
-// precision torch itself uses for fp32 convolutions on a GPU.  3x3 convolutions reach that shape through an explicit
-// im2col (a batch of 64 boards is 4,096 positions: the whole step is a few hundred microsecond-sized kernels, captured
-// in one CUDA graph by the host side, learner.py).  Batch-norm statistics are accumulated in float64.
+// Activations live in HBM as fp32 [positions][channels] (positions = batch x cells, channel contiguous).  Every
+// convolution / linear layer and both of its gradients are ONE GEMM kernel, C[M,N] = A[M,K] * B[N,K]^T on the 5th-gen
+// tensor cores (tcgen05.mma kind::tf32, fp32 accumulation in TMEM; 3xTF32 by default = fp32-level results).  The im2col
+// of a 3x3 convolution is implicit in the A-operand loader of the forward and backward-data passes (a tap is a row
+// offset, borders are zero-filled by cp.async); the weight gradient, whose reduction index is the position, reads
+// transposed copies ([channels][positions]) written by two small kernels.  (tcgen05 can read a transposed, "MN-major",
+// operand itself, but with kind::tf32 and the no-swizzle layout the MMA returned zeros in every descriptor variant
+// tried here; the 32-bit case seems to need the 128B/32B-atom swizzle mode.)  Split-K partial tiles go to a workspace
+// and a reducer adds them in a fixed order (bias, skip share, ReLU fused there): every result is bit-reproducible.
+// Batch-norm statistics are float64.  A batch of 64 boards is 4,096 positions: the step is a few hundred
+// microsecond-sized kernels in one CUDA graph (learner.py).
 #include "yy_common.cuh"
 #include "yy_ptx.cuh"
 
@@ -26,21 +31,23 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM
-// C[M,N] (ldc) = A[M,K] (lda) * B[N,K]^T (ldb) [+ bias[n]] [ReLU], or C += ... (atomic) for split-K / accumulation onto
-// an initialised C.  One CTA per (128-row, tile_n-column, K-slice) tile.  Operands go global -> shared with 16-byte
-// cp.async straight into the no-swizzle K-major core-matrix layout ([K/4 chunk planes][row][16 B], plane pitch
-// rows*16+16 B so that the scatter is bank-conflict free; rows/columns/K past the end are zero-filled), stages of
-// 32 K-values; one elected thread issues the MMAs of a stage and commits the stage's "free" mbarrier.
+// One CTA per (128-row, tile_n-column, K-slice) tile; stages of 32 K-values; operands go global -> shared with 16-byte
+// cp.async (zero-fill past the edges) straight into UMMA's no-swizzle K-major core-matrix layout: [k/4 planes][row][16 B],
+// plane pitch rows*16+16 B (LBO = pitch, SBO = 128; the 16 B of padding make the scatter bank-conflict free).  One
+// elected thread issues the MMAs of a stage and commits the stage's "free" mbarrier.
 // X3 (default precision of the learner): every operand chunk is split in shared memory, by the thread that loaded it,
 // into hi = the 19 bits a TF32 multiplier sees and lo = x - hi, and each K-slice runs three MMAs (lo*hi + hi*lo + hi*hi)
 // -- "3xTF32": products carry ~21 mantissa bits, i.e. fp32-level results (the reference trains in fp32; with plain TF32
 // ~4e-4 of the ReLU masks flip and the gradients differ from fp32 by 5-9 % in L2).
-constexpr int kGemmKStage = 32;   // floats of K per stage = 8 16-byte chunks = 4 K-slices of 8
-constexpr int kGemmPlaneA = 128 * 16 + 16;
+constexpr int kGemmKStage = 32;                     // K-values per stage = 4 K-slices of 8
+constexpr int kPlaneA = 128 * 16 + 16;
+constexpr int kRegionA = 8 * kPlaneA;               // bytes of a stage's A tile
+enum { OP_K = YY_OP_K, OP_K_CONV = YY_OP_K_CONV };
 
 struct GemmArgs {
-  const float* A; const float* B; float* C; const float* bias;
-  int lda, ldb, ldc, M, N, K, tile_n, k_per_split, relu, atomic;
+  const float* A; const float* B; float* C; const float* bias; float* ws;
+  int lda, ldb, ldc, M, N, K, tile_n, k_per_split, relu, accumulate, a_mode;
+  int rows, cols, cin, flip;                        // convolution geometry of the implicit A operand (cin: gathered channels)
 };
 
 __device__ __forceinline__ void split_chunk(uint8_t* hi_ptr, uint8_t* lo_ptr) {
@@ -49,6 +56,14 @@ __device__ __forceinline__ void split_chunk(uint8_t* hi_ptr, uint8_t* lo_ptr) {
                          __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
   *reinterpret_cast<float4*>(hi_ptr) = h;
   *reinterpret_cast<float4*>(lo_ptr) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+// is the (dx,dy) neighbour of the cell of position p on the board?  offset = dx*cols + dy
+__device__ __forceinline__ bool tap_ok(int p, int tap, int rows, int cols, int flip, int* offset) {
+  const int cell = p % (rows * cols), x = cell / cols, y = cell - x * cols;
+  int dx = tap / 3 - 1, dy = tap - (tap / 3) * 3 - 1;
+  if (flip) { dx = -dx; dy = -dy; }
+  *offset = dx * cols + dy;
+  return (unsigned)(x + dx) < (unsigned)rows && (unsigned)(y + dy) < (unsigned)cols;
 }
 
 template <int S, bool X3>
@@ -62,8 +77,8 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(GemmArgs g) {
   const int k_begin = blockIdx.z * g.k_per_split;
   const int k_end = min(g.K, k_begin + g.k_per_split);
   const int KT = (k_end - k_begin + kGemmKStage - 1) / kGemmKStage;
-  const int planeB = g.tile_n * 16 + 16;
-  const int half_bytes = 8 * (kGemmPlaneA + planeB);          // one copy (hi) of a stage's A and B tiles
+  const int planeA = kPlaneA, planeB = g.tile_n * 16 + 16;
+  const int half_bytes = kRegionA + 8 * planeB;               // one copy (hi) of a stage's A and B tiles
   const int stage_bytes = X3 ? 2 * half_bytes : half_bytes;
   uint32_t ncols = 32; while ((int)ncols < g.tile_n) ncols <<= 1;
 
@@ -78,36 +93,43 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(GemmArgs g) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t smem0 = smem_u32(smem);
-  const int chunk = tid & 7;
 
-  auto load_stage = [&](int s, int kt) {
-    const int kbase = k_begin + kt * kGemmKStage;
-    const uint32_t sA = smem0 + (uint32_t)(s * stage_bytes), sB = sA + 8u * kGemmPlaneA;
-    const int k = kbase + chunk * 4;
-    const bool kok = k < k_end;
+  // Visits every 16-byte chunk this thread owns in a stage: f(byte offset inside the stage's hi copy, source, valid).
+  // The same walk (with kt = -1: offsets only) drives the hi/lo split, so a thread splits exactly what it copied.
+  auto walk = [&](int kt, auto&& f) {
+    const int kbase = k_begin + max(kt, 0) * kGemmKStage;
+    const bool addr = kt >= 0;
+    const int chunk = tid & 7, k = kbase + chunk * 4;       // chunk = 4 consecutive k of one row
+    const bool kok = addr && k < k_end;
+    int tap = 0, ci = k;
+    if (g.a_mode == OP_K_CONV) { tap = k / g.cin; ci = k - tap * g.cin; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int row = (tid >> 3) + 16 * i;
-      const bool ok = kok && (m0 + row) < g.M;
-      cp_async16(sA + (uint32_t)(chunk * kGemmPlaneA + row * 16), ok ? g.A + (size_t)(m0 + row) * g.lda + k : g.A, ok);
+      const int row = (tid >> 3) + 16 * i, p = m0 + row;
+      bool ok = kok && p < g.M;
+      const float* src = g.A;
+      if (ok) {
+        if (g.a_mode == OP_K_CONV) {
+          int off; ok = tap_ok(p, tap, g.rows, g.cols, g.flip, &off);
+          src = g.A + (size_t)(p + off) * g.lda + ci;
+        } else {
+          src = g.A + (size_t)p * g.lda + k;
+        }
+      }
+      f(chunk * planeA + row * 16, src, ok);
     }
     for (int row = tid >> 3; row < g.tile_n; row += 16) {
       const bool ok = kok && (n0 + row) < g.N;
-      cp_async16(sB + (uint32_t)(chunk * planeB + row * 16), ok ? g.B + (size_t)(n0 + row) * g.ldb + k : g.B, ok);
+      f(kRegionA + chunk * planeB + row * 16, ok ? g.B + (size_t)(n0 + row) * g.ldb + k : g.B, ok);
     }
   };
-  auto split_stage = [&](int s) {   // every thread splits exactly the chunks it copied (visible to it after wait_group)
-    uint8_t* a = smem + (size_t)s * stage_bytes;
-    uint8_t* b = a + 8 * kGemmPlaneA;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      uint8_t* p = a + chunk * kGemmPlaneA + ((tid >> 3) + 16 * i) * 16;
-      split_chunk(p, p + half_bytes);
-    }
-    for (int row = tid >> 3; row < g.tile_n; row += 16) {
-      uint8_t* p = b + chunk * planeB + row * 16;
-      split_chunk(p, p + half_bytes);
-    }
+  auto load_stage = [&](int s, int kt) {
+    const uint32_t base = smem0 + (uint32_t)(s * stage_bytes);
+    walk(kt, [&](int off, const float* src, bool ok) { cp_async16(base + (uint32_t)off, src, ok); });
+  };
+  auto split_stage = [&](int s) {
+    uint8_t* base = smem + (size_t)s * stage_bytes;
+    walk(-1, [&](int off, const float*, bool) { split_chunk(base + off, base + off + half_bytes); });
   };
 
   for (int s = 0; s < S - 1; ++s) {
@@ -125,15 +147,14 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(GemmArgs g) {
     if (warp == 0) {
       if (elect_one()) {
         tc_fence_after();
-        const uint32_t sA = smem0 + (uint32_t)(s * stage_bytes), sB = sA + 8u * kGemmPlaneA;
+        const uint32_t sA = smem0 + (uint32_t)(s * stage_bytes), sB = sA + kRegionA;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint64_t ad = smem_desc(sA + (uint32_t)(2 * j * kGemmPlaneA), kGemmPlaneA, 128);
-          const uint64_t bd = smem_desc(sB + (uint32_t)(2 * j * planeB), planeB, 128);
+          const uint32_t aoff = 2 * j * planeA, boff = 2 * j * planeB;
+          const uint64_t ad = smem_desc(sA + aoff, planeA, 128), bd = smem_desc(sB + boff, planeB, 128);
           const uint32_t first = (kt > 0 || j > 0) ? 1u : 0u;
           if (X3) {
-            const uint64_t adl = smem_desc(sA + (uint32_t)(half_bytes + 2 * j * kGemmPlaneA), kGemmPlaneA, 128);
-            const uint64_t bdl = smem_desc(sB + (uint32_t)(half_bytes + 2 * j * planeB), planeB, 128);
+            const uint64_t adl = smem_desc(sA + half_bytes + aoff, planeA, 128), bdl = smem_desc(sB + half_bytes + boff, planeB, 128);
             tc_mma_tf32(tmem_base, adl, bd, idesc, first);
             tc_mma_tf32(tmem_base, ad, bdl, idesc, 1u);
             tc_mma_tf32(tmem_base, ad, bd, idesc, 1u);
@@ -159,9 +180,11 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(GemmArgs g) {
   mbar_wait(smem_u32(&done_bar), 0);
   tc_fence_after();
 
-  // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane
+  // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane.  With split-K the tile goes to the workspace
+  // ([slice][M][N]) and gemm_reduce_kernel finishes it; otherwise bias / skip share / ReLU are applied here.
   const int row = m0 + warp * 32 + lane;
-  const bool add_bias = g.bias != nullptr && blockIdx.z == 0;
+  const bool partial = gridDim.z > 1;
+  float* crow = partial ? g.ws + ((size_t)blockIdx.z * g.M + row) * g.N : g.C + (size_t)row * g.ldc;
   for (int c = 0; c < g.tile_n; c += 16) {
     uint32_t r[16];
     if (KT > 0) {
@@ -172,29 +195,17 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(GemmArgs g) {
       for (int j = 0; j < 16; ++j) r[j] = 0u;
     }
     if (row < g.M) {
-      float* crow = g.C + (size_t)row * g.ldc;
 #pragma unroll
       for (int j4 = 0; j4 < 16; j4 += 4) {
         const int n = n0 + c + j4;
-        if (n + 3 < g.N) {
+        if (n < g.N) {                               // N is a multiple of 4
           float4 v = make_float4(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]));
-          if (add_bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
-          if (g.atomic) {
-            atomicAdd(crow + n, v.x); atomicAdd(crow + n + 1, v.y); atomicAdd(crow + n + 2, v.z); atomicAdd(crow + n + 3, v.w);
-          } else {
+          if (!partial) {
+            if (g.bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
+            if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(crow + n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
             if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            *reinterpret_cast<float4*>(crow + n) = v;
           }
-        } else {
-          for (int j = j4; j < j4 + 4; ++j) {
-            const int nn = n0 + c + j;
-            if (nn < g.N) {
-              float v = __uint_as_float(r[j]);
-              if (add_bias) v += g.bias[nn];
-              if (g.atomic) atomicAdd(crow + nn, v);
-              else crow[nn] = g.relu ? fmaxf(v, 0.f) : v;
-            }
-          }
+          *reinterpret_cast<float4*>(crow + n) = v;
         }
       }
     }
@@ -204,27 +215,26 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(GemmArgs g) {
   if (warp == 0) tmem_dealloc(tmem_base, ncols);
 }
 
-// ------------------------------------------------------------------------------------------------ im2col / layout kernels
-// out[p][t*C + c] = X[p + d(t)][c] (zero outside the board), t = (dx+1)*3 + (dy+1), d(t) = dx*cols + dy;
-// flip != 0 negates (dx, dy): the gather a transposed convolution (backward-data) needs.
-__global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out, int ldo,
-                                                       long long P, int rows, int cols, int C4, int flip) {
+// C = [C +] bias + sum_z ws[z] [ReLU], slices added in index order (deterministic)
+__global__ void __launch_bounds__(256) gemm_reduce_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, int ldc, int M, int N4,
+                                                         const float* __restrict__ bias, int relu, int accumulate) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = P * 9 * C4;
-  if (idx >= total) return;
-  const int c4 = (int)(idx % C4);
-  const int t = (int)((idx / C4) % 9);
-  const long long p = idx / (9 * C4);
-  const int cell = (int)(p % (rows * cols)), x = cell / cols, y = cell % cols;
-  int dx = t / 3 - 1, dy = t % 3 - 1;
-  if (flip) { dx = -dx; dy = -dy; }
-  const int xx = x + dx, yy = y + dy;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (xx >= 0 && xx < rows && yy >= 0 && yy < cols)
-    v = *reinterpret_cast<const float4*>(X + (size_t)(p + dx * cols + dy) * ldx + c4 * 4);
-  *reinterpret_cast<float4*>(out + (size_t)p * ldo + t * (C4 * 4) + c4 * 4) = v;
+  if (idx >= (long long)M * N4) return;
+  const int m = (int)(idx / N4), n = (int)(idx % N4) * 4;
+  const size_t slice = (size_t)M * N4 * 4;
+  float4 a = *reinterpret_cast<const float4*>(ws + (size_t)m * N4 * 4 + n);
+  for (int z = 1; z < splits; ++z) {
+    const float4 b = *reinterpret_cast<const float4*>(ws + z * slice + (size_t)m * N4 * 4 + n);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  if (bias) { a.x += bias[n]; a.y += bias[n + 1]; a.z += bias[n + 2]; a.w += bias[n + 3]; }
+  float* c = C + (size_t)m * ldc + n;
+  if (accumulate) { const float4 o = *reinterpret_cast<const float4*>(c); a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+  if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+  *reinterpret_cast<float4*>(c) = a;
 }
 
+// ------------------------------------------------------------------------------------------------ layout / reduction kernels
 // out[c][r] = in[r][c]
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, int R, int C) {
   __shared__ float tile[32][33];
@@ -240,15 +250,35 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     if (c < C && r < R) out[(size_t)c * ldo + r] = tile[tx][j];
   }
 }
-
-// Wt[ci][t*Cout + co] = W[co][t*Cin + ci]  (operand of the backward-data GEMM; the tap flip lives in im2col)
+// colT[t*C + c][p] = X[p + d(t)][c] (zero outside the board): the transposed im2col the weight-gradient GEMM reads
+// (its reduction index is the position).  One block per (32 positions, 32 channels, tap).
+__global__ void __launch_bounds__(256) im2col_t_kernel(const float* __restrict__ X, int ldx, float* __restrict__ colT, int ldo, int P, int rows,
+                                                      int cols, int C) {
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tap = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int p = p0 + j, c = c0 + tx;
+    float v = 0.f;
+    if (p < P && c < C) {
+      int off;
+      if (tap_ok(p, tap, rows, cols, 0, &off)) v = X[(size_t)(p + off) * ldx + c];
+    }
+    tile[j][tx] = v;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, p = p0 + tx;
+    if (c < C && p < P) colT[(size_t)(tap * C + c) * ldo + p] = tile[tx][j];
+  }
+}
+// Wt[ci][t*Cout + co] = W[co][t*Cin + ci]  (B operand of the backward-data GEMM; the tap flip lives in the A gather)
 __global__ void __launch_bounds__(256) conv_weight_t_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Cout, int Cin) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * 9 * Cin) return;
   const int co = idx % Cout, t = (idx / Cout) % 9, ci = idx / (9 * Cout);
   Wt[idx] = W[(size_t)co * 9 * Cin + t * Cin + ci];
 }
-
 // planes float32 [B][5][cells] (board_to_input, neural_network.py:156-196) -> X0 [B*cells][8] (channels 5..7 zero)
 __global__ void __launch_bounds__(256) planes_nhwc_kernel(const float* __restrict__ planes, float* __restrict__ X0, long long P, int cells) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,31 +291,70 @@ __global__ void __launch_bounds__(256) planes_nhwc_kernel(const float* __restric
   o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
-// out[c] = sum_r X[r][c] (bias gradients); float64 accumulation, deterministic
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ld, int R, int C, float* __restrict__ out) {
-  __shared__ double part[8][33];
+// out[c] (+)= sum_r X[r][c] (bias gradients).  One block per 32 columns x 256 rows; with more than one row chunk the
+// chunk sums are added to the (zeroed) output with float atomics.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ld, int R, int C, float* __restrict__ out, int atomic) {
+  __shared__ float part[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
-  double s = 0.0;
-  if (c < C) for (int r = ty; r < R; r += 8) s += (double)X[(size_t)r * ld + c];
+  const int r0 = blockIdx.y * 256, r1 = min(R, r0 + 256);
+  float s = 0.f;
+  if (c < C) for (int r = r0 + ty; r < r1; r += 8) s += X[(size_t)r * ld + c];
   part[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && c < C) {
     for (int j = 1; j < 8; ++j) s += part[j][tx];
-    out[c] = (float)s;
+    if (atomic) atomicAdd(out + c, s); else out[c] = s;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ batch norm (training mode)
 // nn.BatchNorm2d forward in train(): statistics over all P positions of the batch (biased variance for the
-// normalisation, unbiased for running_var, momentum 0.1, eps 1e-5).  sums = float64 [2C]: sum, sum of squares.
-__global__ void __launch_bounds__(128) bn_stats_kernel(const float* __restrict__ Y, int ld, int P, int C, double* __restrict__ sums, int rows_per_block) {
-  const int c = threadIdx.x % C, rl = threadIdx.x / C, lanes = blockDim.x / C;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(P, r0 + rows_per_block);
-  float s = 0.f, q = 0.f;
-  if (rl < lanes)
-    for (int r = r0 + rl; r < r1; r += lanes) { const float v = Y[(size_t)r * ld + c]; s += v; q += v * v; }
-  if (rl < lanes) { atomicAdd(&sums[c], (double)s); atomicAdd(&sums[C + c], (double)q); }
+// normalisation, unbiased for running_var, momentum 0.1, eps 1e-5).  sums = float64 [2C]: forward sum / sum of squares;
+// backward sum dZ*xhat (= d gamma) / sum dZ (= d beta), dZ = dOut * [Out > 0].
+// 256 threads = (C/4 float4 column groups) x (1024/C row lanes); 32 rows per block
+template <bool BWD>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ Y, int ldy, const float* __restrict__ dOut, int ldd,
+                                                       const float* __restrict__ Out, int ldo, const float* __restrict__ mean_invstd,
+                                                       int P, int C, double* __restrict__ sums) {
+  __shared__ float red[2][256][4];
+  const int C4 = C >> 2, cg = threadIdx.x % C4, rl = threadIdx.x / C4, lanes = 256 / C4, c = cg * 4;
+  const int r0 = blockIdx.x * 32, r1 = min(P, r0 + 32);
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  float mu[4] = {0.f, 0.f, 0.f, 0.f}, is[4] = {0.f, 0.f, 0.f, 0.f};
+  if (BWD) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mu[j] = mean_invstd[c + j]; is[j] = mean_invstd[C + c + j]; }
+  }
+  for (int r = r0 + rl; r < r1; r += lanes) {
+    float y[4];
+    *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Y + (size_t)r * ldy + c);
+    if (!BWD) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j] += y[j]; b[j] += y[j] * y[j]; }
+    } else {
+      float dz[4];
+      *reinterpret_cast<float4*>(dz) = *reinterpret_cast<const float4*>(dOut + (size_t)r * ldd + c);
+      if (Out) {
+        float o[4];
+        *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(Out + (size_t)r * ldo + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (!(o[j] > 0.f)) dz[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j] += dz[j] * ((y[j] - mu[j]) * is[j]); b[j] += dz[j]; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[0][threadIdx.x][j] = a[j]; red[1][threadIdx.x][j] = b[j]; }
+  __syncthreads();
+  if (rl == 0) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j] += red[0][l * C4 + cg][j]; b[j] += red[1][l * C4 + cg][j]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { atomicAdd(&sums[c + j], (double)a[j]); atomicAdd(&sums[C + c + j], (double)b[j]); }
+  }
 }
 // mean_invstd float [2C]; running_mean / running_var updated in place (may be NULL)
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int P, int C, float eps, float momentum, float* __restrict__ mean_invstd,
@@ -318,22 +387,6 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
   }
   if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
   *reinterpret_cast<float4*>(out + (size_t)p * ldo + c) = o;
-}
-// backward, pass 1: sums[c] += sum_p dZ*xhat (= d gamma), sums[C+c] += sum_p dZ (= d beta), dZ = dOut * [Out > 0]
-__global__ void __launch_bounds__(128) bn_bwd_reduce_kernel(const float* __restrict__ dOut, int ldd, const float* __restrict__ Out, int ldo,
-                                                           const float* __restrict__ Y, int ldy, const float* __restrict__ mean_invstd, int P, int C,
-                                                           double* __restrict__ sums, int rows_per_block) {
-  const int c = threadIdx.x % C, rl = threadIdx.x / C, lanes = blockDim.x / C;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(P, r0 + rows_per_block);
-  const float mu = mean_invstd[c], is = mean_invstd[C + c];
-  float sg = 0.f, sb = 0.f;
-  if (rl < lanes)
-    for (int r = r0 + rl; r < r1; r += lanes) {
-      float dz = dOut[(size_t)r * ldd + c];
-      if (Out && !(Out[(size_t)r * ldo + c] > 0.f)) dz = 0.f;
-      sg += dz * ((Y[(size_t)r * ldy + c] - mu) * is); sb += dz;
-    }
-  if (rl < lanes) { atomicAdd(&sums[c], (double)sg); atomicAdd(&sums[C + c], (double)sb); }
 }
 // backward, pass 2: dY = gamma*invstd*(dZ - dbeta/P - xhat*dgamma/P); optional dRes = dZ (the skip connection's share);
 // block 0 also writes d gamma / d beta into the gradient buffer.
@@ -370,8 +423,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 
 // ------------------------------------------------------------------------------------------------ heads: losses and their gradients
 // One warp per sample.  Policy: nn.CrossEntropyLoss with probability targets (trainer.py:61,131): loss_p = mean_b( -sum_a pi*log_softmax ),
-// dlogits = (softmax * sum(pi) - pi) / B.  Value: v = tanh(h . w2 + b2) (neural_network.py:119-121), nn.MSELoss (trainer.py:60,132):
-// loss_v = mean_b (v - z)^2; dpre = 2 (v - z)/B * (1 - v^2); dh = dpre * w2 * [h > 0] (h is stored after its ReLU).
+// dlogits = (softmax * sum(pi) - pi) / B.  Value: v = tanh(relu(h) . w2 + b2) (neural_network.py:119-121), nn.MSELoss (trainer.py:60,132):
+// loss_v = mean_b (v - z)^2; dpre = 2 (v - z)/B * (1 - v^2); dh = dpre * w2 * [h > 0] (h = value_fc1's output before its ReLU).
 // losses[0] += policy loss, losses[1] += value loss (zeroed by the caller).
 __global__ void __launch_bounds__(128) heads_loss_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ pi, int A,
                                                         const float* __restrict__ h, int ldh, int H, const float* __restrict__ w2,
@@ -395,7 +448,7 @@ __global__ void __launch_bounds__(128) heads_loss_kernel(const float* __restrict
   for (int a = lane; a < A; a += 32) dlogits[(size_t)b * lddl + a] = (expf(lg[a] - mx - lse) * sp - pb[a]) * invB;
   const float* hb = h + (size_t)b * ldh;
   float dot = 0.f;
-  for (int j = lane; j < H; j += 32) dot += hb[j] * w2[j];
+  for (int j = lane; j < H; j += 32) dot += fmaxf(hb[j], 0.f) * w2[j];
   for (int d = 16; d; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
   const float v = tanhf(dot + b2[0]);
   const float err = v - z[b];
@@ -413,27 +466,37 @@ __global__ void value_fc2_grad_kernel(const float* __restrict__ dpre, const floa
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < H) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dpre[b] * h[(size_t)b * ldh + j];
+    for (int b = 0; b < B; ++b) s += dpre[b] * fmaxf(h[(size_t)b * ldh + j], 0.f);
     dw2[j] = s;
   }
   if (j == 0) { float s = 0.f; for (int b = 0; b < B; ++b) s += dpre[b]; db2[0] = s; }
 }
 
 // ------------------------------------------------------------------------------------------------ Adam (torch.optim.Adam, trainer.py:52-56)
-__global__ void adam_tick_kernel(int* step) { *step += 1; }
+// step_state: int step counter followed (at float index 2, 3) by lr/(1-beta1^t) and sqrt(1-beta2^t) of the current step
+__global__ void adam_tick_kernel(int* step_state, float lr, float b1, float b2) {
+  const int t = ++step_state[0];
+  float* f = reinterpret_cast<float*>(step_state);
+  f[2] = (float)((double)lr / (1.0 - pow((double)b1, (double)t)));
+  f[3] = (float)sqrt(1.0 - pow((double)b2, (double)t));
+}
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                                  long long n, float lr, float b1, float b2, float eps, float wd, const int* __restrict__ step) {
+                                                  long long n4, float b1, float b2, float eps, float wd, const int* __restrict__ step_state) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int t = *step;
-  const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
-  const float step_size = (float)((double)lr / bc1), bc2s = (float)sqrt(bc2);
-  const float pi = p[i];
-  const float gi = g[i] + wd * pi;                          // L2 weight decay folded into the gradient
-  const float mi = m[i] + (gi - m[i]) * (1.f - b1);         // exp_avg.lerp_(grad, 1 - beta1)
-  const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
-  m[i] = mi; v[i] = vi;
-  p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2s + eps));
+  if (i >= n4) return;
+  const float step_size = reinterpret_cast<const float*>(step_state)[2], bc2s = reinterpret_cast<const float*>(step_state)[3];
+  float pi[4], gi[4], mi[4], vi[4];
+  *reinterpret_cast<float4*>(pi) = reinterpret_cast<const float4*>(p)[i]; *reinterpret_cast<float4*>(gi) = reinterpret_cast<const float4*>(g)[i];
+  *reinterpret_cast<float4*>(mi) = reinterpret_cast<const float4*>(m)[i]; *reinterpret_cast<float4*>(vi) = reinterpret_cast<const float4*>(v)[i];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float gg = gi[j] + wd * pi[j];                      // L2 weight decay folded into the gradient
+    mi[j] = mi[j] + (gg - mi[j]) * (1.f - b1);                // exp_avg.lerp_(grad, 1 - beta1)
+    vi[j] = vi[j] * b2 + (1.f - b2) * gg * gg;
+    pi[j] = pi[j] - step_size * (mi[j] / (sqrtf(vi[j]) / bc2s + eps));
+  }
+  reinterpret_cast<float4*>(p)[i] = *reinterpret_cast<float4*>(pi);
+  reinterpret_cast<float4*>(m)[i] = *reinterpret_cast<float4*>(mi); reinterpret_cast<float4*>(v)[i] = *reinterpret_cast<float4*>(vi);
 }
 
 static int need_device() {
@@ -448,24 +511,31 @@ using namespace yy;
 
 extern "C" {
 
-int yy_lrn_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const float* bias,
-                int relu, int atomic, int tile_n, int split_k, int precision, void* stream) {
+int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                const float* bias, int relu, int accumulate, int tile_n, int split_k, float* ws, int64_t ws_floats, int precision,
+                const yy_conv_geom* conv, void* stream) {
   int rc = need_device(); if (rc) return rc;
   if (M <= 0 || N <= 0 || K <= 0) return set_error(YY_ERR_INVALID, "gemm: empty problem");
-  if ((lda | ldb | ldc | K) & 3) return set_error(YY_ERR_INVALID, "gemm: lda, ldb, ldc and K must be multiples of 4 floats");
-  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return set_error(YY_ERR_INVALID, "gemm: operands must be 16-byte aligned");
+  if ((lda | ldb | ldc | N | K) & 3) return set_error(YY_ERR_INVALID, "gemm: lda, ldb, ldc, N and K must be multiples of 4 floats");
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C | (uintptr_t)ws) & 15) return set_error(YY_ERR_INVALID, "gemm: operands must be 16-byte aligned");
+  if (a_mode != YY_OP_K && a_mode != YY_OP_K_CONV) return set_error(YY_ERR_INVALID, "gemm: bad a_mode");
+  if (a_mode == YY_OP_K_CONV) {
+    if (!conv || conv->rows < 1 || conv->cols < 1 || conv->cin < 4 || (conv->cin & 3))
+      return set_error(YY_ERR_INVALID, "gemm: the implicit convolution operand needs a geometry with cin a multiple of 4");
+    if (K != 9 * conv->cin || M % (conv->rows * conv->cols)) return set_error(YY_ERR_INVALID, "gemm: conv A needs K = 9*cin and whole boards");
+  }
   if (precision != YY_GEMM_TF32 && precision != YY_GEMM_3XTF32) return set_error(YY_ERR_INVALID, "gemm: precision must be YY_GEMM_TF32 or YY_GEMM_3XTF32");
-  const int max_tile = precision == YY_GEMM_3XTF32 ? 128 : 256;
-  if (tile_n < 16 || tile_n > max_tile || tile_n % 16) return set_error(YY_ERR_INVALID, "gemm: tile_n in [16,%d] step 16", max_tile);
+  if (tile_n < 16 || tile_n > 128 || tile_n % 16) return set_error(YY_ERR_INVALID, "gemm: tile_n in [16,128] step 16");
   if (split_k < 1) return set_error(YY_ERR_INVALID, "gemm: split_k >= 1");
-  if (split_k > 1 && !atomic) return set_error(YY_ERR_INVALID, "gemm: split-K needs the atomic epilogue (C initialised by the caller)");
-  if (atomic && relu) return set_error(YY_ERR_INVALID, "gemm: ReLU cannot follow an atomic accumulation");
   int kps = (K + split_k - 1) / split_k;
   kps = (kps + kGemmKStage - 1) / kGemmKStage * kGemmKStage;
   const int zs = (K + kps - 1) / kps;
-  GemmArgs g{A, B, C, bias, lda, ldb, ldc, M, N, K, tile_n, kps, relu, atomic};
+  if (zs > 1 && (!ws || ws_floats < (int64_t)zs * M * N)) return set_error(YY_ERR_INVALID, "gemm: split-K needs a workspace of split*M*N floats");
+  GemmArgs g{A, B, C, bias, ws, lda, ldb, ldc, M, N, K, tile_n, kps, relu, accumulate, a_mode,
+             conv ? conv->rows : 1, conv ? conv->cols : 1, conv ? conv->cin : 4, conv ? conv->flip : 0};
   dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + tile_n - 1) / tile_n), (unsigned)zs);
-  const int half = 8 * (kGemmPlaneA + tile_n * 16 + 16);
+  const int half = kRegionA + 8 * (tile_n * 16 + 16);
+  cudaStream_t st = (cudaStream_t)stream;
   if (precision == YY_GEMM_3XTF32) {
     const int smem = 3 * 2 * half;
     static int max_set = 0;
@@ -473,7 +543,7 @@ int yy_lrn_gemm(const float* A, int lda, const float* B, int ldb, float* C, int 
       YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       max_set = smem;
     }
-    gemm_tf32_kernel<3, true><<<grid, 128, smem, (cudaStream_t)stream>>>(g);
+    gemm_tf32_kernel<3, true><<<grid, 128, smem, st>>>(g);
   } else {
     const int smem = 4 * half;
     static int max_set = 0;
@@ -481,20 +551,14 @@ int yy_lrn_gemm(const float* A, int lda, const float* B, int ldb, float* C, int 
       YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       max_set = smem;
     }
-    gemm_tf32_kernel<4, false><<<grid, 128, smem, (cudaStream_t)stream>>>(g);
+    gemm_tf32_kernel<4, false><<<grid, 128, smem, st>>>(g);
   }
   YY_LAUNCH_CHECK();
-  return YY_OK;
-}
-
-int yy_lrn_im2col3x3(const float* X, int ldx, float* out, int ldo, int64_t positions, int rows, int cols, int C, int flip, void* stream) {
-  int rc = need_device(); if (rc) return rc;
-  if (C % 4 || ldx % 4 || ldo % 4 || ldo < 9 * C) return set_error(YY_ERR_INVALID, "im2col: C, ldx, ldo multiples of 4, ldo >= 9*C");
-  if (positions % (rows * cols)) return set_error(YY_ERR_INVALID, "im2col: positions must be whole boards");
-  const long long total = positions * 9 * (C / 4);
-  if (total == 0) return YY_OK;
-  im2col3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, out, ldo, positions, rows, cols, C / 4, flip);
-  YY_LAUNCH_CHECK();
+  if (zs > 1) {
+    const long long total = (long long)M * (N / 4);
+    gemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, zs, C, ldc, M, N / 4, bias, relu, accumulate);
+    YY_LAUNCH_CHECK();
+  }
   return YY_OK;
 }
 
@@ -503,6 +567,16 @@ int yy_lrn_transpose(const float* in, int ldi, float* out, int ldo, int R, int C
   if (R <= 0 || C <= 0) return YY_OK;
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32));
   transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ldi, out, ldo, R, C);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_lrn_im2col_t(const float* X, int ldx, float* colT, int ldo, int64_t positions, int rows, int cols, int C, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  if (positions % (rows * cols)) return set_error(YY_ERR_INVALID, "im2col_t: positions must be whole boards");
+  if (positions == 0) return YY_OK;
+  dim3 grid((unsigned)((positions + 31) / 32), (unsigned)((C + 31) / 32), 9);
+  im2col_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, colT, ldo, (int)positions, rows, cols, C);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -526,7 +600,11 @@ int yy_lrn_planes_nhwc(const float* planes, float* X0, int64_t boards, int cells
 
 int yy_lrn_colsum(const float* X, int ld, int R, int C, float* out, void* stream) {
   int rc = need_device(); if (rc) return rc;
-  colsum_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(X, ld, R, C, out);
+  if (R <= 0 || C <= 0) return YY_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = (R + 255) / 256;
+  if (chunks > 1) YY_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+  colsum_kernel<<<dim3((unsigned)((C + 31) / 32), (unsigned)chunks), 256, 0, st>>>(X, ld, R, C, out, chunks > 1);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -540,8 +618,7 @@ int yy_lrn_bn_forward(const float* Y, int ld, int P, int C, const float* gamma, 
   if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
   cudaStream_t st = (cudaStream_t)stream;
   YY_CUDA_OK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * 2 * C, st));
-  const int rpb = 32;
-  bn_stats_kernel<<<(P + rpb - 1) / rpb, 128, 0, st>>>(Y, ld, P, C, sums_ws, rpb);
+  bn_reduce_kernel<false><<<(P + 31) / 32, 256, 0, st>>>(Y, ld, nullptr, 0, nullptr, 0, nullptr, P, C, sums_ws);
   YY_LAUNCH_CHECK();
   bn_finalize_kernel<<<1, 128, 0, st>>>(sums_ws, P, C, eps, momentum, mean_invstd, running_mean, running_var);
   YY_LAUNCH_CHECK();
@@ -558,8 +635,7 @@ int yy_lrn_bn_backward(const float* dOut, int ldd, const float* Out, int ldo, co
   if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
   cudaStream_t st = (cudaStream_t)stream;
   YY_CUDA_OK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * 2 * C, st));
-  const int rpb = 32;
-  bn_bwd_reduce_kernel<<<(P + rpb - 1) / rpb, 128, 0, st>>>(dOut, ldd, Out, ldo, Y, ldy, mean_invstd, P, C, sums_ws, rpb);
+  bn_reduce_kernel<true><<<(P + 31) / 32, 256, 0, st>>>(Y, ldy, dOut, ldd, Out, ldo, mean_invstd, P, C, sums_ws);
   YY_LAUNCH_CHECK();
   const long long total = (long long)P * (C / 4);
   bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dOut, ldd, Out, ldo, Y, ldy, mean_invstd, gamma, sums_ws, P, C / 4,
@@ -583,12 +659,13 @@ int yy_lrn_heads_loss(const float* logits, int ldl, const float* pi, int A, cons
 }
 
 int yy_lrn_adam(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                float weight_decay, int* step_dev, void* stream) {
+                float weight_decay, int* step_state, void* stream) {
   int rc = need_device(); if (rc) return rc;
+  if (n & 3) return set_error(YY_ERR_INVALID, "adam: the flat buffers must hold a multiple of 4 floats");
   cudaStream_t st = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, st>>>(step_dev);
+  adam_tick_kernel<<<1, 1, 0, st>>>(step_state, lr, beta1, beta2);
   YY_LAUNCH_CHECK();
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev);
+  adam_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(params, grads, m, v, n / 4, beta1, beta2, eps, weight_decay, step_state);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }

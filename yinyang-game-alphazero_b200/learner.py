@@ -24,6 +24,7 @@ from . import _lib
 HEAD_CH = 32      # policy_conv / value_conv output channels (neural_network.py:58,63)
 VALUE_HID = 256   # value_fc1 width (:65)
 STEM_CIN = 8      # the 5 input planes padded to 8 channels (16-byte rows)
+OP_K, OP_K_CONV = 0, 1   # YY_OP_* A-operand modes of yy_lrn_gemm
 
 
 # --------------------------------------------------------------------------------------------- device ops
@@ -44,42 +45,41 @@ class CudaOps:
             raise _lib.YinYangError("the learner needs a CUDA device: there is no CPU fallback")
         self.L = _lib.lib()
         self.precision = {"tf32": 0, "3xtf32": 1}[precision]     # YY_GEMM_TF32 / YY_GEMM_3XTF32
+        self.ws = torch.empty(6 << 20, dtype=torch.float32, device="cuda")   # split-K partial tiles (24 MB)
         self.sm_count = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
 
     @staticmethod
     def _stream():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, split_ok=False):
-        """C[M,N] = A[M,K] @ B[N,K]^T (+bias) (relu); accumulate: C += (atomics).  split_ok: C is zero / initialised
-        and may receive split-K partial sums."""
-        M, K = A.shape
-        N = B.shape[0]
-        assert B.shape[1] == K and tuple(C.shape) == (M, N)
+    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None):
+        """C[M,N] = [C +] A @ B^T (+bias) (relu), B = [N,K].  conv = (rows, cols, cin, flip): A is the activation tensor
+        [positions, cin] and the product runs over its implicit im2col (YY_OP_K_CONV)."""
+        M, N = C.shape
+        K = B.shape[1]
+        assert B.shape[0] == N and (conv is not None or A.shape == (M, K))
         tiles_m = (M + 127) // 128
-        n16 = (N + 15) // 16 * 16
-        cands = [c for c in (128, 64, 32) if c <= max(32, n16)]
-        tile_n = next((c for c in cands if tiles_m * ((N + c - 1) // c) >= 96), None)
-        if tile_n is None:       # too few tiles to fill the machine: big tiles + split-K when allowed, else small tiles
-            tile_n = cands[0] if (accumulate or split_ok) else cands[-1]
-        tile_n = min(tile_n, max(16, n16))
+        tile_n = min(128, (N + 15) // 16 * 16)
         ctas = tiles_m * ((N + tile_n - 1) // tile_n)
         split = 1
-        if (accumulate or split_ok) and ctas < 96:
-            split = max(1, min(self.sm_count // ctas, K // 128))
-        atomic = accumulate or split > 1
-        _lib.check(self.L.yy_lrn_gemm(_p(A), _ld(A), _p(B), _ld(B), _p(C), _ld(C), M, N, K, _p(bias), int(relu), int(atomic),
-                                      tile_n, split, self.precision, self._stream()))
-
-    def im2col(self, X, out, rows, cols, flip=False):
-        P, C = X.shape
-        assert out.shape[0] == P and out.shape[1] == 9 * C
-        _lib.check(self.L.yy_lrn_im2col3x3(_p(X), _ld(X), _p(out), _ld(out), P, rows, cols, C, int(flip), self._stream()))
+        if ctas < 100:                 # too few tiles to fill 148 SMs: slice K (>= 256 per slice), partial tiles -> workspace
+            split = max(1, min(self.sm_count // ctas, K // 256))
+        if split > 1 and split * M * N > self.ws.numel():
+            split = max(1, self.ws.numel() // (M * N))
+        geom = ctypes.byref(_lib.ConvGeom(*conv)) if conv is not None else None
+        _lib.check(self.L.yy_lrn_gemm(_p(A), _ld(A), OP_K_CONV if conv is not None else OP_K, _p(B), _ld(B), _p(C), _ld(C), M, N, K,
+                                      _p(bias), int(relu), int(accumulate), tile_n, split, _p(self.ws), self.ws.numel(), self.precision,
+                                      geom, self._stream()))
 
     def transpose(self, inp, out):
         R, C = inp.shape
         assert tuple(out.shape) == (C, R)
         _lib.check(self.L.yy_lrn_transpose(_p(inp), _ld(inp), _p(out), _ld(out), R, C, self._stream()))
+
+    def im2col_t(self, X, colT, rows, cols):
+        P, C = X.shape
+        assert tuple(colT.shape) == (9 * C, P)
+        _lib.check(self.L.yy_lrn_im2col_t(_p(X), _ld(X), _p(colT), _ld(colT), P, rows, cols, C, self._stream()))
 
     def conv_weight_t(self, W, Wt, cout, cin):
         _lib.check(self.L.yy_lrn_conv_weight_t(_p(W), _p(Wt), cout, cin, self._stream()))
@@ -201,14 +201,14 @@ class Learner:
         self.bn_eps, self.bn_momentum = 1e-5, 0.1
         if channels % 4 or 128 % channels:
             raise ValueError("channels must divide 128 and be a multiple of 4")
-        if self.A % 4 or batch_size % 4:
-            raise ValueError("rows*cols and batch_size must be multiples of 4 (16-byte rows for the tensor-core GEMMs)")
+        if self.A % 4:
+            raise ValueError("rows*cols must be a multiple of 4 (16-byte rows for the tensor-core GEMMs)")
         self.layout = _Layout(rows, cols, channels, blocks)
         f32 = dict(dtype=torch.float32, device=self.dev)
         n = self.layout.total
         self.params, self.grads = torch.zeros(n, **f32), torch.zeros(n, **f32)
         self.m, self.v = torch.zeros(n, **f32), torch.zeros(n, **f32)
-        self.step_count = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.step_count = torch.zeros(4, dtype=torch.int32, device=self.dev)   # [0] = Adam step; [2..3] kernel scratch
         self._bn = self.layout.bn_prefixes(blocks)
         self.running = {}
         for pre in self._bn:
@@ -242,25 +242,23 @@ class Learner:
         z = lambda *s: torch.zeros(*s, **f32)
         self.planes_in, self.pi_in, self.z_in = z(B, 5, self.rows, self.cols), z(B, A), z(B)
         self.X0 = z(P, STEM_CIN)
-        self.col, self.colT = z(P * 9 * C), z(9 * C * P)
-        self.Y = [z(P, C) for _ in range(n_conv)]
-        self.act = [z(P, C) for _ in range(n_conv)]
+        self.Y = [z(P, C) for _ in range(n_conv)]            # convolution outputs (batch-norm inputs), kept for backward
+        self.act = [z(P, C) for _ in range(n_conv)]          # layer outputs
         self.mi = {pre: z(2 * (HEAD_CH if pre in ("policy_bn", "value_bn") else C)) for pre in self._bn}
         self.Yh = {h: z(P, HEAD_CH) for h in ("policy", "value")}
         self.acth = {h: z(P, HEAD_CH) for h in ("policy", "value")}
-        self.logits, self.hid = z(B, A), z(B, VALUE_HID)
+        self.logits, self.hid = z(B, A), z(B, VALUE_HID)     # hid: value_fc1 output BEFORE its ReLU
         self.dlogits, self.dhid, self.dpre, self.v_out = z(B, A), z(B, VALUE_HID), z(B), z(B)
         self.losses = z(2)
         self.ws = torch.zeros(2 * 128, dtype=torch.float64, device=self.dev)
-        # backward scratch
-        self.G = [z(P, C) for _ in range(3)]
-        self.dY, self.dYT = z(P, C), z(max(C, HEAD_CH) * P)
+        self.G = [z(P, C) for _ in range(3)]                 # gradients w.r.t. layer outputs (rotating)
+        self.dY = z(P, C)
         self.dacth, self.dYh = z(P, HEAD_CH), z(P, HEAD_CH)
-        self.trunkT = z(C, P)
+        # transposed copies ([channels][positions]) for the weight-gradient GEMMs, whose reduction index is the position
+        self.dYT, self.colT, self.trunkT = z(max(C, HEAD_CH) * P), z(9 * C * P), z(C * P)
         self.Wt = z(C * max(9 * C, HEAD_CH))
-        self.fcT = z(HEAD_CH * A * max(VALUE_HID, A))
-        self.smallT = z(max(VALUE_HID, A) * ((B + 3) // 4 * 4))
-        self.featT = z(HEAD_CH * A, (B + 3) // 4 * 4)
+        kp = (B + 3) // 4 * 4
+        self.fcT, self.smallT, self.featT = z(HEAD_CH * A * max(VALUE_HID, A)), z(max(VALUE_HID, A) * kp), z(HEAD_CH * A * kp)
 
     # -- checkpoints (neural_network.py:198-237 state_dict keys)
     def load_state_dict(self, sd):
@@ -290,12 +288,12 @@ class Learner:
         return self._export(self.grads)
 
     # -- one conv + batch norm (+ skip) + ReLU
+    def _geom(self, cin, flip=False):
+        return (self.rows, self.cols, cin, int(flip))      # yy_conv_geom: cin = channels of the gathered tensor
+
     def _conv3_forward(self, x, wkey, bkey, bnpre, li, residual=None):
         ops, P = self.ops, self.p
-        cin = x.shape[1]
-        col = self.col[:P * 9 * cin].view(P, 9 * cin)
-        ops.im2col(x, col, self.rows, self.cols, False)
-        ops.gemm(col, self.w(wkey), self.Y[li][:P], bias=self.w(bkey))
+        ops.gemm(x, self.w(wkey), self.Y[li][:P], bias=self.w(bkey), conv=self._geom(x.shape[1]))
         ops.bn_forward(self.Y[li][:P], self.w(bnpre + ".weight"), self.w(bnpre + ".bias"), residual, self.act[li][:P], True, self.bn_eps,
                        self.bn_momentum, self.ws, self.mi[bnpre], self.running[bnpre][0], self.running[bnpre][1])
 
@@ -308,19 +306,16 @@ class Learner:
         ops.bn_backward(dOut, self.act[li][:P], self.Y[li][:P], self.mi[bnpre], self.w(bnpre + ".weight"), self.ws, dY, dRes,
                         self.g(bnpre + ".weight"), self.g(bnpre + ".bias"))
         ops.colsum(dY, self.g(bkey))
-        dYT = self.dYT[:C * P].view(C, P)
+        # dW[co][t*cin+ci] = sum_p dY[p][co] * x_in[p + d(t)][ci]: K = positions, both operands from transposed copies
+        dYT, colT = self.dYT[:C * P].view(C, P), self.colT[:9 * cin * P].view(9 * cin, P)
         ops.transpose(dY, dYT)
-        col = self.col[:P * 9 * cin].view(P, 9 * cin)
-        colT = self.colT[:P * 9 * cin].view(9 * cin, P)
-        ops.im2col(x_in, col, self.rows, self.cols, False)
-        ops.transpose(col, colT)
-        ops.gemm(dYT, colT, self.g(wkey), split_ok=True)                       # dW[co][t*cin+ci] (gradients were zeroed)
+        ops.im2col_t(x_in, colT, self.rows, self.cols)
+        ops.gemm(dYT, colT, self.g(wkey))
         if dPrev is not None:
+            # dX[p][ci] = sum_{t,co} dY[p - d(t)][co] * W[co][t*cin+ci]: implicit (mirrored) im2col of dY times Wt
             Wt = self.Wt[:cin * 9 * C].view(cin, 9 * C)
             ops.conv_weight_t(self.w(wkey), Wt, C, cin)
-            colg = self.col[:P * 9 * C].view(P, 9 * C)
-            ops.im2col(dY, colg, self.rows, self.cols, True)
-            ops.gemm(colg, Wt, dPrev, accumulate=accumulate)
+            ops.gemm(dY, Wt, dPrev, accumulate=accumulate, conv=self._geom(C, flip=True))
 
     def _head_forward(self, head, trunk):
         ops, P = self.ops, self.p
@@ -333,24 +328,20 @@ class Learner:
     def _kpad(self):
         return (self.b + 3) // 4 * 4                         # the batch as a GEMM K dimension: whole 16-byte chunks
 
-    def _feat_t(self, feat):
-        """feat [b,F] -> [F, kpad] (columns past b zero) for the weight-gradient GEMMs of the linear layers."""
+    def _t_batch(self, x, buf):
+        """x [b,F] -> [F, kpad] (columns past b zero): operand of a linear layer's weight-gradient GEMM (K = batch)."""
         kp = self._kpad()
-        T = self.featT.view(-1)[:feat.shape[1] * kp].view(feat.shape[1], kp)
+        T = buf[:x.shape[1] * kp].view(x.shape[1], kp)
         if kp != self.b:
             T[:, self.b:].zero_()
-        self.ops.transpose(feat, T[:, :self.b])
+        self.ops.transpose(x, T[:, :self.b])
         return T
 
-    def _fc_backward(self, dout, feat_T, wkey, bkey, dfeat):
-        """dout [b,N]: gradient at an nn.Linear's output; feat_T [F,kpad]; writes dW, db and dfeat [b,F] = dout @ W."""
-        ops, kp = self.ops, self._kpad()
-        N, F = dout.shape[1], feat_T.shape[0]
-        doutT = self.smallT[:N * kp].view(N, kp)
-        if kp != self.b:
-            doutT[:, self.b:].zero_()
-        ops.transpose(dout, doutT[:, :self.b])
-        ops.gemm(doutT, feat_T, self.g(wkey), split_ok=True)
+    def _fc_backward(self, dout, feat, wkey, bkey, dfeat):
+        """dout [b,N]: gradient at an nn.Linear's output; feat [b,F] its input; writes dW, db and dfeat [b,F] = dout @ W."""
+        ops = self.ops
+        N, F = dout.shape[1], feat.shape[1]
+        ops.gemm(self._t_batch(dout, self.smallT), self._t_batch(feat, self.featT), self.g(wkey))     # dW = dout^T @ feat
         ops.colsum(dout, self.g(bkey))
         WT = self.fcT[:F * N].view(F, N)
         ops.transpose(self.w(wkey), WT)
@@ -365,7 +356,7 @@ class Learner:
         ops.colsum(dYh, self.g(f"{head}_conv.bias"))
         dYhT = self.dYT[:HEAD_CH * P].view(HEAD_CH, P)
         ops.transpose(dYh, dYhT)
-        ops.gemm(dYhT, self.trunkT.view(-1)[:C * P].view(C, P), self.g(f"{head}_conv.weight"), split_ok=True)
+        ops.gemm(dYhT, self.trunkT[:C * P].view(C, P), self.g(f"{head}_conv.weight"))
         WT = self.Wt[:C * HEAD_CH].view(C, HEAD_CH)
         ops.transpose(self.w(f"{head}_conv.weight"), WT)
         ops.gemm(dYh, WT, dTrunk, accumulate=accumulate)
@@ -387,18 +378,18 @@ class Learner:
         fv = self._head_forward("value", trunk)
         logits, hid = self.logits[:b], self.hid[:b]
         ops.gemm(fp, self.w("policy_fc.weight"), logits, bias=self.w("policy_fc.bias"))
-        ops.gemm(fv, self.w("value_fc1.weight"), hid, bias=self.w("value_fc1.bias"), relu=True)
+        ops.gemm(fv, self.w("value_fc1.weight"), hid, bias=self.w("value_fc1.bias"))       # its ReLU is applied by the head kernels
         # ---- losses + head gradients (trainer.py:131-133)
         dlogits, dhid = self.dlogits[:b], self.dhid[:b]
         ops.heads_loss(logits, self.pi_in[:b], hid, self.w("value_fc2.weight"), self.w("value_fc2.bias"), self.z_in[:b],
                        dlogits, dhid, self.dpre[:b], self.v_out[:b], self.g("value_fc2.weight"), self.g("value_fc2.bias"), self.losses)
         # ---- backward
-        ops.transpose(trunk, self.trunkT.view(-1)[:C * P].view(C, P))
+        ops.transpose(trunk, self.trunkT[:C * P].view(C, P))
         dfeat = self.dacth[:P].view(b, self.A * HEAD_CH)
         G = [g[:P] for g in self.G]
-        self._fc_backward(dlogits, self._feat_t(fp), "policy_fc.weight", "policy_fc.bias", dfeat)
+        self._fc_backward(dlogits, fp, "policy_fc.weight", "policy_fc.bias", dfeat)
         self._head_backward("policy", dfeat, trunk, G[0], accumulate=False)
-        self._fc_backward(dhid, self._feat_t(fv), "value_fc1.weight", "value_fc1.bias", dfeat)
+        self._fc_backward(dhid, fv, "value_fc1.weight", "value_fc1.bias", dfeat)
         self._head_backward("value", dfeat, trunk, G[0], accumulate=True)
         gi = 0                                               # G[gi]: gradient w.r.t. the current block's output
         for k in reversed(range(nb)):
