@@ -281,6 +281,10 @@ typedef struct {
 int yy_lrn_gemm(const float *A, int lda, int a_mode, const float *B, int ldb, float *C, int ldc, int M, int N, int K,
                 const float *bias, int relu, int accumulate, int tile_n, int split_k, float *ws, int64_t ws_floats,
                 int precision, const yy_conv_geom *conv, void *stream);
+/* Developer tool: while dbg_dev != NULL (>= 128 int64) CTA (0,0,0) of every yy_lrn_gemm launch records clock64 stamps:
+ * [0] start, [1] after setup, [4+6k .. 8+6k] producer phases of K-iteration k (start, slot free, copies issued, copies of
+ * iteration k-1 landed, iteration k-1 split + published), [2] loop end, [119] accumulator complete, [3] epilogue end. */
+int yy_lrn_gemm_debug_stamps(long long *dbg_dev);
 /* out[c][r] = in[r][c] */
 int yy_lrn_transpose(const float *in, int ldi, float *out, int ldo, int R, int C, void *stream);
 /* colT[t*C + c][p] = X[p + d(t)][c], zero outside the board: the transposed im2col the weight gradient of a 3x3

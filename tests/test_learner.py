@@ -248,7 +248,7 @@ def test_kernels_match_their_emulation(yy):
     assert torch.allclose(p.cpu(), p_ref, rtol=1e-5, atol=1e-6) and torch.allclose(v_.cpu(), v_ref, rtol=1e-4, atol=1e-12)
 
 
-HEAD_KEYS = ("policy_fc", "value_fc1", "value_fc2", "policy_bn", "value_bn")
+HEAD_KEYS = ("policy_fc", "value_fc1", "value_fc2")    # linear layers: no ReLU mask between them and the loss
 
 
 @pytest.mark.gpu
@@ -259,8 +259,8 @@ def test_cuda_step_matches_torch_fp32_training_step(yy, n, C, nb, B, precision):
     move every weight by ~lr * sign(gradient): trajectories from *independently* rounded gradients separate quickly,
     which says nothing about either side); the torch Adam then steps with the LEARNER's gradients and must land on the
     learner's new weights, which checks the fused Adam kernel along a 4-step trajectory.
-    3xTF32 (default): losses within 1e-4 relative; gradient tensors of the heads within 5e-3 (relative L2; the linear
-    layers measure 2e-5, the head batch norms 1e-3); trunk
+    3xTF32 (default): losses within 1e-4 relative; gradient tensors of the linear layers within 1e-3 (relative L2;
+    measured 2e-5); convolution / batch-norm
     tensors within 3e-2 relative L2 and cosine >= 0.9995 -- what is left there are a handful of ReLU masks (1-6 of
     524,288 per layer, measured) whose pre-activation lies within ~1e-5 of zero and flips under a different summation
     order.  Single-pass TF32 flips ~200 masks per layer: losses 5e-3, gradients 0.2 relative L2 / cosine 0.98
@@ -290,7 +290,7 @@ def test_cuda_step_matches_torch_fp32_training_step(yy, n, C, nb, B, precision):
                 cos = torch.nn.functional.cosine_similarity(got[k].flatten().double(), gr.flatten().double(), dim=0).item()
                 worst_l2, worst_cos = max(worst_l2, l2), min(worst_cos, cos)
                 if tight:
-                    assert l2 <= (5e-3 if k.startswith(HEAD_KEYS) else 3e-2) and cos >= 0.9995, (it, k, l2, cos)
+                    assert l2 <= (1e-3 if k.startswith(HEAD_KEYS) else 3e-2) and cos >= 0.9995, (it, k, l2, cos)
                 else:
                     assert l2 <= 0.2 and cos >= 0.98, (it, k, l2, cos)
             p.grad = got[k].clone()

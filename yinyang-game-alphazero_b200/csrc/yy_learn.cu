@@ -33,8 +33,7 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 // ------------------------------------------------------------------------------------------------ GEMM
 // One CTA per (128-row, tile_n-column, K-slice) tile; stages of 32 K-values; operands go global -> shared with 16-byte
 // cp.async (zero-fill past the edges) straight into UMMA's no-swizzle K-major core-matrix layout: [k/4 planes][row][16 B],
-// plane pitch rows*16+16 B (LBO = pitch, SBO = 128; the 16 B of padding make the scatter bank-conflict free).  One
-// elected thread issues the MMAs of a stage and commits the stage's "free" mbarrier.
+// plane pitch rows*16+16 B (LBO = pitch, SBO = 128; the 16 B of padding make the scatter bank-conflict free).
 // X3 (default precision of the learner): every operand chunk is split in shared memory, by the thread that loaded it,
 // into hi = the 19 bits a TF32 multiplier sees and lo = x - hi, and each K-slice runs three MMAs (lo*hi + hi*lo + hi*hi)
 // -- "3xTF32": products carry ~21 mantissa bits, i.e. fp32-level results (the reference trains in fp32; with plain TF32
@@ -48,6 +47,7 @@ struct GemmArgs {
   const float* A; const float* B; float* C; const float* bias; float* ws;
   int lda, ldb, ldc, M, N, K, tile_n, k_per_split, relu, accumulate, a_mode;
   int rows, cols, cin, flip;                        // convolution geometry of the implicit A operand (cin: gathered channels)
+  long long* dbg;                                   // developer tool: clock64 stamps of CTA 0 (yy_lrn_gemm_debug_stamps)
 };
 
 __device__ __forceinline__ void split_chunk(uint8_t* hi_ptr, uint8_t* lo_ptr) {
@@ -66,12 +66,21 @@ __device__ __forceinline__ bool tap_ok(int p, int tap, int rows, int cols, int f
   return (unsigned)(x + dx) < (unsigned)rows && (unsigned)(y + dy) < (unsigned)cols;
 }
 
+#define YY_STAMP(i) do { if (stamp && (i) < 120) g.dbg[(i)] = clock64(); } while (0)
+// Warp roles: warps 0-3 = producers (cp.async + hi/lo split of the chunks they copied) and, at the end, the epilogue
+// (warp w reads TMEM lanes 32w..32w+31); warp 4 = MMA issuer.  full[s] (128 arrivals: every producer thread after its
+// chunks of stage s are in place and fenced for the async proxy), free[s] (tcgen05.commit: the MMAs that read stage s
+// have completed), done (accumulator complete).  Producers keep the copies of stage kt in flight while they split
+// stage kt-1; all per-row address arithmetic (board coordinates of the implicit im2col included) is done once per CTA.
 template <int S, bool X3>
-__global__ void __launch_bounds__(128) gemm_tf32_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(160) gemm_tf32_kernel(GemmArgs g) {
   extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ __align__(8) uint64_t free_bar[S];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_base_s;
+  const bool stamp = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+  YY_STAMP(0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * g.tile_n;
   const int k_begin = blockIdx.z * g.k_per_split;
@@ -83,80 +92,36 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(GemmArgs g) {
   uint32_t ncols = 32; while ((int)ncols < g.tile_n) ncols <<= 1;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(smem_u32(&free_bar[s]), 1);
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&full_bar[s]), 128); mbar_init(smem_u32(&free_bar[s]), 1); }
     mbar_init(smem_u32(&done_bar), 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), ncols);
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), ncols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t smem0 = smem_u32(smem);
+  YY_STAMP(1);
 
-  // Visits every 16-byte chunk this thread owns in a stage: f(byte offset inside the stage's hi copy, source, valid).
-  // The same walk (with kt = -1: offsets only) drives the hi/lo split, so a thread splits exactly what it copied.
-  auto walk = [&](int kt, auto&& f) {
-    const int kbase = k_begin + max(kt, 0) * kGemmKStage;
-    const bool addr = kt >= 0;
-    const int chunk = tid & 7, k = kbase + chunk * 4;       // chunk = 4 consecutive k of one row
-    const bool kok = addr && k < k_end;
-    int tap = 0, ci = k;
-    if (g.a_mode == OP_K_CONV) { tap = k / g.cin; ci = k - tap * g.cin; }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = (tid >> 3) + 16 * i, p = m0 + row;
-      bool ok = kok && p < g.M;
-      const float* src = g.A;
-      if (ok) {
-        if (g.a_mode == OP_K_CONV) {
-          int off; ok = tap_ok(p, tap, g.rows, g.cols, g.flip, &off);
-          src = g.A + (size_t)(p + off) * g.lda + ci;
-        } else {
-          src = g.A + (size_t)p * g.lda + k;
-        }
-      }
-      f(chunk * planeA + row * 16, src, ok);
-    }
-    for (int row = tid >> 3; row < g.tile_n; row += 16) {
-      const bool ok = kok && (n0 + row) < g.N;
-      f(kRegionA + chunk * planeB + row * 16, ok ? g.B + (size_t)(n0 + row) * g.ldb + k : g.B, ok);
-    }
-  };
-  auto load_stage = [&](int s, int kt) {
-    const uint32_t base = smem0 + (uint32_t)(s * stage_bytes);
-    walk(kt, [&](int off, const float* src, bool ok) { cp_async16(base + (uint32_t)off, src, ok); });
-  };
-  auto split_stage = [&](int s) {
-    uint8_t* base = smem + (size_t)s * stage_bytes;
-    walk(-1, [&](int off, const float*, bool) { split_chunk(base + off, base + off + half_bytes); });
-  };
-
-  for (int s = 0; s < S - 1; ++s) {
-    if (s < KT) load_stage(s, s);
-    cp_async_commit();
-  }
-  const uint32_t idesc = idesc_tf32(128, g.tile_n);
-  for (int kt = 0; kt < KT; ++kt) {
-    const int s = kt % S;
-    cp_async_wait<S - 2>();
-    if (X3) split_stage(s);
-    tc_fence_before();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (warp == 0) {
+  if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = idesc_tf32(128, g.tile_n);
+    const uint64_t a0 = smem_desc(smem0, planeA, 128), b0 = smem_desc(smem0 + kRegionA, planeB, 128);
+    const uint64_t a_step = (uint64_t)((2 * planeA) >> 4), b_step = (uint64_t)((2 * planeB) >> 4), lo = (uint64_t)(half_bytes >> 4);
+    for (int kt = 0; kt < KT; ++kt) {
+      const int s = kt % S;
+      mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((kt / S) & 1));
+      tc_fence_after();
       if (elect_one()) {
-        tc_fence_after();
-        const uint32_t sA = smem0 + (uint32_t)(s * stage_bytes), sB = sA + kRegionA;
+        const uint64_t st = (uint64_t)((s * stage_bytes) >> 4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t aoff = 2 * j * planeA, boff = 2 * j * planeB;
-          const uint64_t ad = smem_desc(sA + aoff, planeA, 128), bd = smem_desc(sB + boff, planeB, 128);
+          const uint64_t ad = a0 + st + j * a_step, bd = b0 + st + j * b_step;
           const uint32_t first = (kt > 0 || j > 0) ? 1u : 0u;
           if (X3) {
-            const uint64_t adl = smem_desc(sA + half_bytes + aoff, planeA, 128), bdl = smem_desc(sB + half_bytes + boff, planeB, 128);
-            tc_mma_tf32(tmem_base, adl, bd, idesc, first);
-            tc_mma_tf32(tmem_base, ad, bdl, idesc, 1u);
+            tc_mma_tf32(tmem_base, ad + lo, bd, idesc, first);
+            tc_mma_tf32(tmem_base, ad, bd + lo, idesc, 1u);
             tc_mma_tf32(tmem_base, ad, bd, idesc, 1u);
           } else {
             tc_mma_tf32(tmem_base, ad, bd, idesc, first);
@@ -166,53 +131,139 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(GemmArgs g) {
       }
       __syncwarp();
     }
-    const int nxt = kt + S - 1;
-    if (nxt < KT) {
-      if (kt >= 1) mbar_wait(smem_u32(&free_bar[(kt - 1) % S]), (uint32_t)(((kt - 1) / S) & 1));
-      load_stage(nxt % S, nxt);
-    }
-    cp_async_commit();
-  }
-  if (warp == 0) {
     if (elect_one()) tc_commit(smem_u32(&done_bar));
     __syncwarp();
-  }
-  mbar_wait(smem_u32(&done_bar), 0);
-  tc_fence_after();
-
-  // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane.  With split-K the tile goes to the workspace
-  // ([slice][M][N]) and gemm_reduce_kernel finishes it; otherwise bias / skip share / ReLU are applied here.
-  const int row = m0 + warp * 32 + lane;
-  const bool partial = gridDim.z > 1;
-  float* crow = partial ? g.ws + ((size_t)blockIdx.z * g.M + row) * g.N : g.C + (size_t)row * g.ldc;
-  for (int c = 0; c < g.tile_n; c += 16) {
-    uint32_t r[16];
-    if (KT > 0) {
-      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, r);
-      tc_wait_ld();
-    } else {
+  } else {
+    // ------------------------------------------------------------------ producers
+    // Chunk ownership: lane = (row within an 8-row group) + 8 * (k-chunk within a half stage); one cp.async of a warp
+    // fills 4 whole 128-byte lines of the core-matrix layout and reads 64 contiguous bytes of 8 rows.  A thread owns 8
+    // chunks of A (4 row groups x 2 half stages) and tile_n/16 of B.
+    const int r8 = lane & 7, c4 = lane >> 3;
+    const int nB = g.tile_n >> 4;
+    const bool convA = g.a_mode == OP_K_CONV;
+    const float* arow0 = g.A + (size_t)(m0 + 32 * warp + r8) * g.lda;     // row group gi adds 8*gi rows
+    const float* brow0 = g.B + (size_t)(n0 + r8) * g.ldb;
+    // per owned A row (gi = 0..3): bit 4gi+0/1/2/3 = the neighbour above / below / left / right of its cell is on the board
+    uint32_t edge = 0, rowok = 0;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) r[j] = 0u;
-    }
-    if (row < g.M) {
-#pragma unroll
-      for (int j4 = 0; j4 < 16; j4 += 4) {
-        const int n = n0 + c + j4;
-        if (n < g.N) {                               // N is a multiple of 4
-          float4 v = make_float4(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]));
-          if (!partial) {
-            if (g.bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
-            if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(crow + n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          }
-          *reinterpret_cast<float4*>(crow + n) = v;
+    for (int gi = 0; gi < 4; ++gi) {
+      const int p = m0 + 32 * warp + 8 * gi + r8;
+      if (p < g.M) {
+        rowok |= 1u << gi;
+        if (convA) {
+          const int cell = p % (g.rows * g.cols), x = cell / g.cols, y = cell - x * g.cols;
+          edge |= ((x > 0 ? 1u : 0u) | (x < g.rows - 1 ? 2u : 0u) | (y > 0 ? 4u : 0u) | (y < g.cols - 1 ? 8u : 0u)) << (4 * gi);
         }
       }
     }
+    auto load_stage = [&](int s, int kt) {
+      const uint32_t st = smem0 + (uint32_t)(s * stage_bytes);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int chunk = c4 + 4 * h, k = k_begin + kt * kGemmKStage + chunk * 4;
+        const bool kok = k < k_end;
+        long long aoff = k;                                   // element offset added to a row's base
+        uint32_t need = 0;                                    // edge bits this tap needs
+        if (convA) {
+          const int tap = k / g.cin, ci = k - tap * g.cin;
+          int dx = tap / 3 - 1, dy = tap - (tap / 3) * 3 - 1;
+          if (g.flip) { dx = -dx; dy = -dy; }
+          need = (dx < 0 ? 1u : 0u) | (dx > 0 ? 2u : 0u) | (dy < 0 ? 4u : 0u) | (dy > 0 ? 8u : 0u);
+          aoff = (long long)(dx * g.cols + dy) * g.lda + ci;
+        }
+        const uint32_t sA = st + (uint32_t)(chunk * planeA + (32 * warp + r8) * 16);
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          const bool ok = kok && ((rowok >> gi) & 1u) && ((need & ~(edge >> (4 * gi))) & 15u) == 0;
+          cp_async16(sA + (uint32_t)(gi * 128), ok ? arow0 + (size_t)(8 * gi) * g.lda + aoff : g.A, ok);
+        }
+      }
+      for (int q = warp; q < 2 * (g.tile_n >> 3); q += 4) {   // (row group, half stage) pairs of B
+        const int gB = q >> 1, chunk = c4 + 4 * (q & 1), k = k_begin + kt * kGemmKStage + chunk * 4;
+        const int n = n0 + 8 * gB + r8;
+        const bool ok = k < k_end && n < g.N;
+        cp_async16(st + (uint32_t)(kRegionA + chunk * planeB + (8 * gB + r8) * 16), ok ? brow0 + (size_t)(8 * gB) * g.ldb + k : g.B, ok);
+      }
+    };
+    auto finish_stage = [&](int s) {                          // the copies of stage s have landed (for this thread)
+      if (X3) {
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint8_t* a = st + (c4 + 4 * h) * planeA + (32 * warp + r8) * 16;
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) split_chunk(a + gi * 128, a + gi * 128 + half_bytes);
+        }
+        for (int q = warp; q < 2 * (g.tile_n >> 3); q += 4) {
+          uint8_t* b = st + kRegionA + (c4 + 4 * (q & 1)) * planeB + (8 * (q >> 1) + r8) * 16;
+          split_chunk(b, b + half_bytes);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&full_bar[s]));
+    };
+    (void)nB;
+    for (int kt = 0; kt < KT; ++kt) {
+      const int s = kt % S;
+      YY_STAMP(4 + 6 * kt);
+      if (kt >= S) {                                          // the MMAs that read this slot S iterations ago
+        if (lane == 0) mbar_wait(smem_u32(&free_bar[s]), (uint32_t)(((kt / S) - 1) & 1));
+        __syncwarp();
+      }
+      YY_STAMP(5 + 6 * kt);
+      load_stage(s, kt);
+      cp_async_commit();
+      YY_STAMP(6 + 6 * kt);
+      if (kt >= 1) {
+        cp_async_wait<1>();
+        YY_STAMP(7 + 6 * kt);
+        finish_stage((kt - 1) % S);
+        YY_STAMP(8 + 6 * kt);
+      }
+    }
+    cp_async_wait<0>();
+    if (KT > 0) finish_stage((KT - 1) % S);
+    YY_STAMP(2);
+    if (lane == 0) mbar_wait(smem_u32(&done_bar), 0);
+    __syncwarp();
+    tc_fence_after();
+    YY_STAMP(119);
+
+    // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane.  With split-K the tile goes to the workspace
+    // ([slice][M][N]) and gemm_reduce_kernel finishes it; otherwise bias / skip share / ReLU are applied here.
+    const int row = m0 + warp * 32 + lane;
+    const bool partial = gridDim.z > 1;
+    float* crow = partial ? g.ws + ((size_t)blockIdx.z * g.M + row) * g.N : g.C + (size_t)row * g.ldc;
+    for (int c = 0; c < g.tile_n; c += 16) {
+      uint32_t r[16];
+      if (KT > 0) {
+        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, r);
+        tc_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;
+      }
+      if (row < g.M) {
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const int n = n0 + c + j4;
+          if (n < g.N) {                               // N is a multiple of 4
+            float4 v = make_float4(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]));
+            if (!partial) {
+              if (g.bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
+              if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(crow + n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+              if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            }
+            *reinterpret_cast<float4*>(crow + n) = v;
+          }
+        }
+      }
+    }
+    YY_STAMP(3);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+  if (warp == 4) tmem_dealloc(tmem_base, ncols);
 }
 
 // C = [C +] bias + sum_z ws[z] [ReLU], slices added in index order (deterministic)
@@ -499,6 +550,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   reinterpret_cast<float4*>(m)[i] = *reinterpret_cast<float4*>(mi); reinterpret_cast<float4*>(v)[i] = *reinterpret_cast<float4*>(vi);
 }
 
+static long long* g_gemm_dbg = nullptr;
+
 static int need_device() {
   int nd = 0;
   if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) { cudaGetLastError(); return set_error(YY_ERR_NO_DEVICE, "no CUDA device: the learner has no CPU fallback"); }
@@ -532,7 +585,7 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
   const int zs = (K + kps - 1) / kps;
   if (zs > 1 && (!ws || ws_floats < (int64_t)zs * M * N)) return set_error(YY_ERR_INVALID, "gemm: split-K needs a workspace of split*M*N floats");
   GemmArgs g{A, B, C, bias, ws, lda, ldb, ldc, M, N, K, tile_n, kps, relu, accumulate, a_mode,
-             conv ? conv->rows : 1, conv ? conv->cols : 1, conv ? conv->cin : 4, conv ? conv->flip : 0};
+             conv ? conv->rows : 1, conv ? conv->cols : 1, conv ? conv->cin : 4, conv ? conv->flip : 0, g_gemm_dbg};
   dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + tile_n - 1) / tile_n), (unsigned)zs);
   const int half = kRegionA + 8 * (tile_n * 16 + 16);
   cudaStream_t st = (cudaStream_t)stream;
@@ -543,7 +596,7 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
       YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       max_set = smem;
     }
-    gemm_tf32_kernel<3, true><<<grid, 128, smem, st>>>(g);
+    gemm_tf32_kernel<3, true><<<grid, 160, smem, st>>>(g);
   } else {
     const int smem = 4 * half;
     static int max_set = 0;
@@ -551,7 +604,7 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
       YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       max_set = smem;
     }
-    gemm_tf32_kernel<4, false><<<grid, 128, smem, st>>>(g);
+    gemm_tf32_kernel<4, false><<<grid, 160, smem, st>>>(g);
   }
   YY_LAUNCH_CHECK();
   if (zs > 1) {
@@ -561,6 +614,8 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
   }
   return YY_OK;
 }
+
+int yy_lrn_gemm_debug_stamps(long long* dbg_dev) { g_gemm_dbg = dbg_dev; return YY_OK; }
 
 int yy_lrn_transpose(const float* in, int ldi, float* out, int ldo, int R, int C, void* stream) {
   int rc = need_device(); if (rc) return rc;
