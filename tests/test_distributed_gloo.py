@@ -70,3 +70,65 @@ def test_shard_games_properties():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _learner_worker(rank, world, port, q):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here)); sys.path.insert(0, here)
+    import yy_b200  # noqa: F401
+    from yinyang_game_alphazero_b200 import learner
+    from emu_learner_ops import TorchEmuOps
+    from test_learner import _reference_net, _batch
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        net = _reference_net(4, 4, 8, 1, seed=5)
+        L = learner.Learner(4, 4, 8, 1, batch_size=4, state_dict=net.state_dict(), _ops=TorchEmuOps())
+        planes, pi, z = _batch(net, 4, 4, 8, seed=6)
+        sl = slice(4 * rank, 4 * rank + 4)                  # every rank trains on its own half of the global batch
+        for _ in range(2):
+            L.step(planes[sl], pi[sl], z[sl])
+        q.put((rank, {k: v.numpy().copy() for k, v in L.state_dict().items() if "running" not in k and "tracked" not in k}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_learner_world2():
+    """Two ranks, one half batch each: identical weights on both ranks after every step, equal to a single process that
+    averages the two half-batch gradients before Adam (DistributedDataParallel semantics)."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here)); sys.path.insert(0, here)
+    import yy_b200  # noqa: F401
+    from yinyang_game_alphazero_b200 import learner
+    from emu_learner_ops import TorchEmuOps
+    from test_learner import _reference_net, _batch
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_learner_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
+    # single-process restatement: two learners sharing weights, gradients averaged by hand
+    net = _reference_net(4, 4, 8, 1, seed=5)
+    planes, pi, z = _batch(net, 4, 4, 8, seed=6)
+    A = learner.Learner(4, 4, 8, 1, batch_size=4, state_dict=net.state_dict(), _ops=TorchEmuOps())
+    B = learner.Learner(4, 4, 8, 1, batch_size=4, state_dict=net.state_dict(), _ops=TorchEmuOps())
+    for _ in range(2):
+        for L, sl in ((A, slice(0, 4)), (B, slice(4, 8))):
+            L.b, L.p = 4, 4 * L.A
+            L.planes_in.copy_(planes[sl]); L.pi_in.copy_(pi[sl]); L.z_in.copy_(z[sl])
+            L._run()
+        mean = (A.grads + B.grads) / 2
+        A.grads.copy_(mean); B.grads.copy_(mean)
+        A._run_adam(); B._run_adam()
+    ref = A.state_dict()
+    for k in res[0]:
+        assert np.allclose(res[0][k], ref[k].numpy(), rtol=1e-6, atol=1e-7), k

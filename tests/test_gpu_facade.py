@@ -211,3 +211,22 @@ def test_trainer_facade_trains_and_checkpoints(pkg, tmp_path):
         assert torch.equal(v.float(), after[k].float()), k
     p, v = tr.nnet.predict(examples[0][0])                     # the self-play evaluator sees the trained weights
     assert p.shape == (36,) and abs(p.sum() - 1) < 1e-3 and -1 <= v <= 1
+
+
+def test_cli_train_mode_runs_the_whole_loop(pkg, tmp_path):
+    """train_alphazero.py --mode train (AlphaZero.run, alphazero.py:248-270): self-play -> learner -> arena -> promotion."""
+    import subprocess, sys, glob
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md, dd = str(tmp_path / "models"), str(tmp_path / "data")
+    r = subprocess.run([sys.executable, os.path.join(root, "train_alphazero.py"), "--mode", "train", "--rows", "6", "--cols", "6",
+                        "--iterations", "1", "--episodes", "8", "--simulations", "16", "--epochs", "1", "--arena-games", "4",
+                        "--model-dir", md, "--data-dir", dd], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(glob.glob(os.path.join(dd, "self_play_data_*.npz"))) == 1
+    for name in ("current_model.pth.tar", "best_model.pth.tar", "checkpoint_1.pth.tar"):
+        assert os.path.exists(os.path.join(md, name)), name
+    cur = torch.load(os.path.join(md, "current_model.pth.tar"), map_location="cpu", weights_only=False)["state_dict"]
+    ck = torch.load(os.path.join(md, "checkpoint_1.pth.tar"), map_location="cpu", weights_only=False)["state_dict"]
+    assert all(torch.equal(cur[k], ck[k]) for k in ck)                       # the trained checkpoint became the current model
+    assert int(ck["bn1.num_batches_tracked"]) > 0                             # the learner actually stepped

@@ -1,13 +1,14 @@
 #!/usr/bin/env python
-"""CLI with the reference's flags (train_alphazero.py:30-61) for the modes on the accelerated path:
+"""CLI with the reference's flags (train_alphazero.py:30-61) for all three modes:
 
     python train_alphazero.py --mode self-play --rows 8 --cols 8 --simulations 800 --episodes 4096
     python train_alphazero.py --mode evaluate  --simulations 100
 
 ``--mode self-play`` -> generate_self_play_data (train_alphazero.py:103-122); ``--mode evaluate`` -> 10 games
-AlphaZeroPlayer vs RandomPlayer with alternating colours (:124-243).  ``--mode train`` (the learner) is outside
-this engine's scope: use the reference trainer on the generated .npz files.  Extra flags: ``--rules-rowcol``
-(browser-game row/column rule), ``--init-model`` (write a randomly initialised checkpoint if none exists).
+AlphaZeroPlayer vs RandomPlayer with alternating colours (:124-243); ``--mode train`` -> AlphaZero.run (:86-101): per
+iteration self-play with the best model, the CUDA learner on the data directory, current-vs-best arena, promotion at a
+win ratio >= 0.6 -- every stage on the GPU.  Extra flags: ``--rules-rowcol`` (browser-game row/column rule),
+``--init-model`` (write a randomly initialised checkpoint if none exists), ``--arena-games`` (default 40).
 """
 import argparse
 import logging
@@ -40,6 +41,7 @@ def parse_args(argv=None):
     p.add_argument("--rules-rowcol", action="store_true", help="also apply the browser game's row/column rule")
     p.add_argument("--init-model", action="store_true", help="create a randomly initialised model file if missing")
     p.add_argument("--eval-games", type=int, default=10)
+    p.add_argument("--arena-games", type=int, default=40, help="--mode train: games of current vs best per iteration (alphazero.py:136)")
     p.add_argument("--replay-wire", choices=["native", "reference"], default="native",
                    help="'reference': pickle replay boards as src.yin_yang.yin_yang_logic.YinYangLogic so that the "
                         "reference's own trainer loads the .npz without this package")
@@ -58,10 +60,14 @@ def main(argv=None):
     for d in (args.model_dir, args.data_dir):
         os.makedirs(d, exist_ok=True)
     model_path = os.path.join(args.model_dir, args.output_model)
-    if args.mode == "train":
-        logger.error("--mode train (the learner) is not part of the B200 self-play engine; run the reference trainer "
-                     "on the .npz files written by --mode self-play")
-        return 2
+    if args.mode == "train":                                             # train_alphazero.py:86-101
+        from yinyang_game_alphazero_b200.alphazero import AlphaZero
+        AlphaZero(game=game, model_dir=args.model_dir, data_dir=args.data_dir, num_iterations=args.iterations,
+                  num_episodes=args.episodes, num_simulations=args.simulations, num_epochs=args.epochs,
+                  num_workers=args.workers, mcts_threads=args.mcts_threads, eval_games=args.arena_games,
+                  batch_size=args.batch_size, lr=args.lr).run()
+        logger.info("Training completed!")
+        return 0
     if not os.path.exists(model_path):
         if args.init_model:
             YinYangNeuralNetwork(game).save_model(model_path)

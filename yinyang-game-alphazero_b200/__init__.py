@@ -25,7 +25,7 @@ __all__ = ["build", "YinYangError", "bitboard"]
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `build()` works in a bare interpreter
     import importlib
-    for mod in ("engine", "game", "network", "mcts", "self_play", "players", "weights", "distributed", "data_utils", "arena", "learner", "trainer"):
+    for mod in ("engine", "game", "network", "mcts", "self_play", "players", "weights", "distributed", "data_utils", "arena", "learner", "trainer", "training_pipeline", "alphazero"):
         try:
             m = importlib.import_module(f"{__name__}.{mod}")
         except ModuleNotFoundError as e:

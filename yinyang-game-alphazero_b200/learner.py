@@ -184,10 +184,12 @@ class _Layout:
 # --------------------------------------------------------------------------------------------- the learner
 class Learner:
     """One Adam step per ``step()`` call on a batch of up to ``batch_size`` samples (the DataLoader's last batch of an
-    epoch is smaller, trainer.py:96-100; each batch size gets its own CUDA graph)."""
+    epoch is smaller, trainer.py:96-100; each batch size gets its own pair of CUDA graphs: forward + backward, Adam).
+    With an initialised ``torch.distributed`` process group (and ``data_parallel``) every rank steps on its own batch and
+    the gradients are averaged with one all-reduce of the flat buffer between the two graphs."""
 
     def __init__(self, rows, cols, channels=128, blocks=10, batch_size=64, lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999),
-                 eps=1e-8, state_dict=None, device=None, use_graph=True, precision="3xtf32", _ops=None):
+                 eps=1e-8, state_dict=None, device=None, use_graph=True, precision="3xtf32", data_parallel=True, _ops=None):
         # _ops: test seam (tests/ inject a torch emulation of the kernels to check the layer sequence against autograd
         # on a CPU box); the product always runs CudaOps and fails without a CUDA device.
         # precision: "3xtf32" (default; fp32-level GEMMs, what the fp32 reference computes) or "tf32" (single pass)
@@ -217,6 +219,11 @@ class Learner:
         self.batches_tracked = 0
         self._alloc_buffers()
         self._graphs = {}
+        self.world = 1
+        if data_parallel:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.world = dist.get_world_size()
         self._use_graph = use_graph and _ops is None
         if state_dict is not None:
             self.load_state_dict(state_dict)
@@ -400,8 +407,16 @@ class Learner:
             self._conv3_backward(G[h], self.act[l1 - 1][:P], pre + ".conv1.weight", pre + ".conv1.bias", pre + ".bn1", l1, dRes=None, dPrev=G[r], accumulate=True)
             gi = r
         self._conv3_backward(G[gi], X0, "conv1.weight", "conv1.bias", "bn1", 0, dRes=None, dPrev=None, accumulate=False)
-        # ---- Adam (trainer.py:52-56)
-        ops.adam(self.params, self.grads, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count)
+
+    def _run_adam(self):  # trainer.py:52-56
+        self.ops.adam(self.params, self.grads, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count)
+
+    def _allreduce_grads(self):
+        """Data parallel: one all-reduce (NCCL over NVLink on the GPU box) of the flat gradient buffer, mean over
+        ranks -- what DistributedDataParallel does bucket by bucket; batch-norm statistics stay per rank, as in DDP."""
+        import torch.distributed as dist
+        dist.all_reduce(self.grads)
+        self.grads.mul_(1.0 / self.world)
 
     def step(self, planes, policies, values):
         """planes float32[b,5,n,m], policies float32[b,A], values float32[b] (device tensors, 1 <= b <= batch_size).
@@ -411,16 +426,24 @@ class Learner:
             raise ValueError(f"the learner was built for batches of up to {self.B}, got {b}")
         self.b, self.p = b, b * self.A
         self.planes_in[:b].copy_(planes.reshape(b, 5, self.rows, self.cols)); self.pi_in[:b].copy_(policies); self.z_in[:b].copy_(values.reshape(-1))
-        graph = self._graphs.get(b)
-        if graph is not None:
-            graph.replay()
+        graphs = self._graphs.get(b)
+        if graphs is not None:
+            graphs[0].replay()
+            if self.world > 1:
+                self._allreduce_grads()
+            graphs[1].replay()
         else:
             self._run()                                      # the first step of a batch size runs eagerly ...
+            if self.world > 1:
+                self._allreduce_grads()
+            self._run_adam()
             if self._use_graph:                              # ... and is then captured (capture does not execute)
                 torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                g_bwd, g_adam = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_bwd):
                     self._run()
-                self._graphs[b] = graph
+                with torch.cuda.graph(g_adam):
+                    self._run_adam()
+                self._graphs[b] = (g_bwd, g_adam)
         self.batches_tracked += 1
         return self.losses
