@@ -192,3 +192,13 @@ def test_reference_wire_format_loads_in_the_reference(yy, tmp_path):
     self_play.save_examples(path, examples, 36, wire="native")
     d = np.load(path, allow_pickle=True)
     assert type(d["boards"][0]).__module__.startswith("yinyang_game_alphazero_b200")
+
+
+def test_cli_imports_in_a_fresh_process(tmp_path):
+    """The package's lazy attribute hook must not import modules in a cycle: run the CLI in a new interpreter up to the
+    reference's "model file not found" exit (train_alphazero.py:107-109)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "train_alphazero.py"), "--mode", "self-play", "--model-dir", str(tmp_path / "m"),
+                        "--data-dir", str(tmp_path / "d")], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 1 and "ImportError" not in r.stderr, r.stderr[-1500:]

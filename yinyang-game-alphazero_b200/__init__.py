@@ -22,18 +22,19 @@ from ._lib import YinYangError, build  # noqa: F401
 __all__ = ["build", "YinYangError", "bitboard"]
 
 
+_MODULES = ("engine", "game", "network", "mcts", "self_play", "players", "weights", "distributed", "data_utils", "arena",
+            "learner", "trainer", "training_pipeline", "alphazero")
+
+
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `build()` works in a bare interpreter
     import importlib
-    for mod in ("engine", "game", "network", "mcts", "self_play", "players", "weights", "distributed", "data_utils", "arena", "learner", "trainer", "training_pipeline", "alphazero"):
-        try:
-            m = importlib.import_module(f"{__name__}.{mod}")
-        except ModuleNotFoundError as e:
-            if e.name and e.name.endswith(mod):
-                continue
-            raise
-        if name == mod:
-            return m
+    if name in _MODULES:                       # `from . import engine` inside the package: import just that module
+        return importlib.import_module(f"{__name__}.{name}")
+    if name.startswith("__"):
+        raise AttributeError(name)
+    for mod in _MODULES:                       # `from yinyang_game_alphazero_b200 import Engine, YinYangGame, MCTS`
+        m = importlib.import_module(f"{__name__}.{mod}")
         if hasattr(m, name):
             return getattr(m, name)
     raise AttributeError(name)
