@@ -291,23 +291,28 @@ int yy_lrn_transpose(const float *in, int ldi, float *out, int ldo, int R, int C
  * convolution reads (dW = dY^T * colT^T; the reduction index is the position). */
 int yy_lrn_im2col_t(const float *X, int ldx, float *colT, int ldo, int64_t positions, int rows, int cols, int C,
                     void *stream);
-/* Wt[ci][t*Cout + co] = W[co][t*Cin + ci]: the B operand of the backward-data GEMM of a 3x3 convolution. */
-int yy_lrn_conv_weight_t(const float *W, float *Wt, int Cout, int Cin, void *stream);
+/* Wt[l][ci][t*Cout + co] = W_l[co][t*Cin + ci], W_l = params + offsets_dev[l] (offsets NULL: one layer at params): the B
+ * operands of the backward-data GEMMs of `layers` 3x3 convolutions of the same shape, in one launch. */
+int yy_lrn_conv_weight_t(const float *params, const long long *offsets_dev, int layers, float *Wt, int Cout, int Cin,
+                         void *stream);
 /* planes float32 [boards][5][cells] (board_to_input, neural_network.py:156-196) -> X0 float32 [boards*cells][8]. */
 int yy_lrn_planes_nhwc(const float *planes, float *X0, int64_t boards, int cells, void *stream);
 /* out[c] = sum_r X[r][c] (bias gradients). */
 int yy_lrn_colsum(const float *X, int ld, int R, int C, float *out, void *stream);
 /* nn.BatchNorm2d in train() (neural_network.py:22-25,44): out = [relu](gamma*(Y-mean)*invstd + beta [+ residual]) with
  * the batch's own mean / biased variance over the P positions; writes mean_invstd float[2C] for the backward pass and
- * updates running_mean / running_var (unbiased variance, `momentum`) in place when not NULL.  sums_ws: float64[2C]. */
+ * updates running_mean / running_var (unbiased variance, `momentum`) in place when not NULL.  sums_ws: float64[2C], ZERO
+ * on entry (the host side zeroes one slot per layer and pass with a single memset per step). */
 int yy_lrn_bn_forward(const float *Y, int ld, int P, int C, const float *gamma, const float *beta,
                       const float *residual, int ldr, float *out, int ldo, int relu, float eps, float momentum,
                       double *sums_ws, float *mean_invstd, float *running_mean, float *running_var, void *stream);
 /* Backward of the above (and of the ReLU after it when Out != NULL: dZ = dOut*[Out > 0]):
- * dY = gamma*invstd*(dZ - mean(dZ) - xhat*mean(dZ*xhat)); dRes (optional) = dZ; dgamma = sum dZ*xhat; dbeta = sum dZ. */
+ * dY = gamma*invstd*(dZ - mean(dZ) - xhat*mean(dZ*xhat)); dRes (optional) = dZ; dgamma = sum dZ*xhat; dbeta = sum dZ;
+ * dbias (optional, zero on entry) += column sums of dY = the bias gradient of the convolution feeding this batch norm.
+ * sums_ws: float64[2C], zero on entry. */
 int yy_lrn_bn_backward(const float *dOut, int ldd, const float *Out, int ldo, const float *Y, int ldy, int P, int C,
                        const float *mean_invstd, const float *gamma, double *sums_ws, float *dY, int lddy,
-                       float *dRes, int lddr, float *dgamma, float *dbeta, void *stream);
+                       float *dRes, int lddr, float *dgamma, float *dbeta, float *dbias, void *stream);
 /* Both losses and their gradients at the heads (trainer.py:131-133; value head tail neural_network.py:119-121):
  * losses[0] = CrossEntropyLoss(logits, pi) with probability targets, losses[1] = MSELoss(tanh(relu(h).w2 + b2), z),
  * h = value_fc1's output before its ReLU; dlogits, dh (through that ReLU), dpre[B], v_out[B], dw2[H], db2[1]. */

@@ -37,8 +37,10 @@ class TorchEmuOps:
     def im2col_t(self, X, colT, rows, cols):
         colT.copy_(self._im2col(X, rows, cols, False).t())
 
-    def conv_weight_t(self, W, Wt, cout, cin):
-        Wt.view(cin, 9, cout).copy_(W.view(cout, 9, cin).permute(2, 1, 0))
+    def conv_weight_t(self, params, offsets, Wt, cout, cin):
+        for l, off in enumerate(offsets.tolist()):
+            W = params[off:off + cout * 9 * cin]
+            Wt[l].view(cin, 9, cout).copy_(W.view(cout, 9, cin).permute(2, 1, 0))
 
     def planes_nhwc(self, planes, X0):
         B = planes.shape[0]
@@ -61,7 +63,7 @@ class TorchEmuOps:
             o = o + residual
         out.copy_(o.clamp_min(0) if relu else o)
 
-    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta):
+    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias=None):
         P, C = Y.shape
         dz = dOut * (Out > 0) if Out is not None else dOut.clone()
         xhat = (Y - mean_invstd[:C]) * mean_invstd[C:]
@@ -70,6 +72,8 @@ class TorchEmuOps:
         dY.copy_(gamma * mean_invstd[C:] * (dz - db.float() / P - xhat * dg.float() / P))
         if dRes is not None:
             dRes.copy_(dz)
+        if dbias is not None:
+            dbias.add_(dY.double().sum(0).float())
 
     def heads_loss(self, logits, pi, h, w2, b2, z, dlogits, dh, dpre, v, dw2, db2, losses):
         B = logits.shape[0]

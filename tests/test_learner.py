@@ -160,9 +160,13 @@ def test_convolution_passes_match_their_definition(yy, rows, cols, cin, cout, bo
     dw_ref, dw = torch.zeros(cout, 9 * cin), torch.zeros(cout, 9 * cin).cuda()
     emu.gemm(dY.t().contiguous(), colT_ref, dw_ref); ops.gemm(dYT, colT, dw)
     close(dw, dw_ref, "weight gradient")
-    wt_ref, wt = torch.zeros(cin, 9 * cout), torch.zeros(cin, 9 * cout).cuda()
-    emu.conv_weight_t(W, wt_ref, cout, cin); ops.conv_weight_t(W.cuda(), wt, cout, cin)
-    assert torch.equal(wt.cpu(), wt_ref)
+    # two layers' weights inside one flat buffer -> both transposed views in one launch
+    flat = torch.cat([rn(12), W.flatten(), rn(8), (W * 2).flatten()])
+    offs = torch.tensor([12, 12 + W.numel() + 8], dtype=torch.int64)
+    wts_ref, wts = torch.zeros(2, cin, 9 * cout), torch.zeros(2, cin, 9 * cout).cuda()
+    emu.conv_weight_t(flat, offs, wts_ref, cout, cin); ops.conv_weight_t(flat.cuda(), offs.cuda(), wts, cout, cin)
+    assert torch.equal(wts.cpu(), wts_ref) and torch.equal(wts_ref[1], wts_ref[0] * 2)
+    wt_ref, wt = wts_ref[0], wts[0]
     skip = rn(P, cin)
     dx_ref, dx = skip.clone(), skip.clone().cuda()
     emu.gemm(dY, wt_ref, dx_ref, accumulate=True, conv=(rows, cols, cout, 1)); ops.gemm(dY.cuda(), wt, dx, accumulate=True, conv=(rows, cols, cout, 1))
@@ -211,7 +215,7 @@ def test_kernels_match_their_emulation(yy):
         for residual, relu in ((None, True), (res, True), (None, False)):
             out_ref, mi_ref, rm_ref, rv_ref = torch.zeros(P, C), torch.zeros(2 * C), torch.zeros(C), torch.ones(C)
             out, mi, rm, rv = (t.clone().cuda() for t in (out_ref, mi_ref, rm_ref, rv_ref))
-            ws = torch.zeros(256, dtype=torch.float64).cuda()
+            ws = torch.zeros(256, dtype=torch.float64).cuda()       # zero on entry (one slot per layer and pass in the learner)
             emu.bn_forward(Y, gamma, beta, residual, out_ref, relu, 1e-5, 0.1, None, mi_ref, rm_ref, rv_ref)
             ops.bn_forward(cu(Y), cu(gamma), cu(beta), cu(residual), out, relu, 1e-5, 0.1, ws, mi, rm, rv)
             assert torch.allclose(out.cpu(), out_ref, rtol=1e-5, atol=1e-5)
@@ -219,11 +223,12 @@ def test_kernels_match_their_emulation(yy):
             assert torch.allclose(rm.cpu(), rm_ref, rtol=1e-5, atol=1e-6) and torch.allclose(rv.cpu(), rv_ref, rtol=1e-5, atol=1e-6)
             dOut = rn(P, C)
             for want_res in (False, True):
-                dy_ref, dr_ref, dg_ref, db_ref = torch.zeros(P, C), torch.zeros(P, C), torch.zeros(C), torch.zeros(C)
-                dy, dr, dg, db = (t.clone().cuda() for t in (dy_ref, dr_ref, dg_ref, db_ref))
-                emu.bn_backward(dOut, out_ref if relu else None, Y, mi_ref, gamma, None, dy_ref, dr_ref if want_res else None, dg_ref, db_ref)
-                ops.bn_backward(cu(dOut), out if relu else None, cu(Y), mi, cu(gamma), ws, dy, dr if want_res else None, dg, db)
+                dy_ref, dr_ref, dg_ref, db_ref, dbi_ref = torch.zeros(P, C), torch.zeros(P, C), torch.zeros(C), torch.zeros(C), torch.zeros(C)
+                dy, dr, dg, db, dbi = (t.clone().cuda() for t in (dy_ref, dr_ref, dg_ref, db_ref, dbi_ref))
+                emu.bn_backward(dOut, out_ref if relu else None, Y, mi_ref, gamma, None, dy_ref, dr_ref if want_res else None, dg_ref, db_ref, dbi_ref)
+                ops.bn_backward(cu(dOut), out if relu else None, cu(Y), mi, cu(gamma), ws.zero_(), dy, dr if want_res else None, dg, db, dbi)
                 assert torch.allclose(dy.cpu(), dy_ref, rtol=1e-4, atol=1e-5)
+                assert torch.allclose(dbi.cpu(), dy_ref.double().sum(0).float(), atol=1e-4 * dy_ref.abs().sum(0).max().item())
                 assert torch.allclose(dg.cpu(), dg_ref, rtol=1e-4, atol=1e-4) and torch.allclose(db.cpu(), db_ref, rtol=1e-4, atol=1e-4)
                 if want_res:
                     assert torch.equal(dr.cpu(), dr_ref)

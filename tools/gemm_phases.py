@@ -17,7 +17,7 @@ _lib.lib().yy_lrn_gemm_debug_stamps(None)
 d = dbg.cpu().tolist()
 t0 = d[0]
 print(prec, "setup", d[1] - t0, "loop end", d[2] - t0, "acc complete", d[119] - t0, "epilogue end", d[3] - t0)
-names = ["iter start", "slot free", "copies issued", "prev landed", "prev published", "-"]
+names = ["iter start", "next loads issued", "slot free", "stored + published", "-", "-"]
 for k in range(9):
     row = [d[4 + 6 * k + j] - t0 if d[4 + 6 * k + j] else None for j in range(6)]
     print(k, dict(zip(names, row)))

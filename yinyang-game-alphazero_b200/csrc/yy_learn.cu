@@ -32,9 +32,10 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 
 // ------------------------------------------------------------------------------------------------ GEMM
 // One CTA per (128-row, tile_n-column, K-slice) tile; stages of 32 K-values; operands go global -> shared with 16-byte
-// cp.async (zero-fill past the edges) straight into UMMA's no-swizzle K-major core-matrix layout: [k/4 planes][row][16 B],
-// plane pitch rows*16+16 B (LBO = pitch, SBO = 128; the 16 B of padding make the scatter bank-conflict free).
-// X3 (default precision of the learner): every operand chunk is split in shared memory, by the thread that loaded it,
+// loads through registers (LDG.128 -> hi/lo split -> STS.128; the 16-byte cp.async scatter measured one chunk per cycle per
+// SM and bounded the kernel) into UMMA's no-swizzle K-major core-matrix layout: [k/4 planes][row][16 B], plane pitch
+// rows*16+16 B (LBO = pitch, SBO = 128; the 16 B of padding keep the stores bank-conflict free); zeros past the edges.
+// X3 (default precision of the learner): every operand chunk is split in registers on its way to shared memory
 // into hi = the 19 bits a TF32 multiplier sees and lo = x - hi, and each K-slice runs three MMAs (lo*hi + hi*lo + hi*hi)
 // -- "3xTF32": products carry ~21 mantissa bits, i.e. fp32-level results (the reference trains in fp32; with plain TF32
 // ~4e-4 of the ReLU masks flip and the gradients differ from fp32 by 5-9 % in L2).
@@ -50,13 +51,6 @@ struct GemmArgs {
   long long* dbg;                                   // developer tool: clock64 stamps of CTA 0 (yy_lrn_gemm_debug_stamps)
 };
 
-__device__ __forceinline__ void split_chunk(uint8_t* hi_ptr, uint8_t* lo_ptr) {
-  float4 v = *reinterpret_cast<float4*>(hi_ptr);
-  float4 h = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
-                         __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-  *reinterpret_cast<float4*>(hi_ptr) = h;
-  *reinterpret_cast<float4*>(lo_ptr) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-}
 // is the (dx,dy) neighbour of the cell of position p on the board?  offset = dx*cols + dy
 __device__ __forceinline__ bool tap_ok(int p, int tap, int rows, int cols, int flip, int* offset) {
   const int cell = p % (rows * cols), x = cell / cols, y = cell - x * cols;
@@ -67,13 +61,14 @@ __device__ __forceinline__ bool tap_ok(int p, int tap, int rows, int cols, int f
 }
 
 #define YY_STAMP(i) do { if (stamp && (i) < 120) g.dbg[(i)] = clock64(); } while (0)
-// Warp roles: warps 0-3 = producers (cp.async + hi/lo split of the chunks they copied) and, at the end, the epilogue
-// (warp w reads TMEM lanes 32w..32w+31); warp 4 = MMA issuer.  full[s] (128 arrivals: every producer thread after its
+// Warp roles: warps 0-7 = producers (two warps per scheduler; the loads of stage kt+1 are in flight while stage kt is
+// split and stored) and, at the end, the epilogue (warps w and w+4 share TMEM lanes
+// 32(w&3).. and alternate 16-column chunks); warp 8 = MMA issuer.  full[s] (256 arrivals: every producer thread after its
 // chunks of stage s are in place and fenced for the async proxy), free[s] (tcgen05.commit: the MMAs that read stage s
-// have completed), done (accumulator complete).  Producers keep the copies of stage kt in flight while they split
-// stage kt-1; all per-row address arithmetic (board coordinates of the implicit im2col included) is done once per CTA.
+// have completed), done (accumulator complete).  All per-row address arithmetic (board coordinates of the implicit
+// im2col included) is done once per CTA.
 template <int S, bool X3>
-__global__ void __launch_bounds__(160) gemm_tf32_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ __align__(8) uint64_t free_bar[S];
@@ -92,11 +87,11 @@ __global__ void __launch_bounds__(160) gemm_tf32_kernel(GemmArgs g) {
   uint32_t ncols = 32; while ((int)ncols < g.tile_n) ncols <<= 1;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&full_bar[s]), 128); mbar_init(smem_u32(&free_bar[s]), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&full_bar[s]), 256); mbar_init(smem_u32(&free_bar[s]), 1); }
     mbar_init(smem_u32(&done_bar), 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), ncols);
+  if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), ncols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -104,7 +99,7 @@ __global__ void __launch_bounds__(160) gemm_tf32_kernel(GemmArgs g) {
   const uint32_t smem0 = smem_u32(smem);
   YY_STAMP(1);
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = idesc_tf32(128, g.tile_n);
     const uint64_t a0 = smem_desc(smem0, planeA, 128), b0 = smem_desc(smem0 + kRegionA, planeB, 128);
@@ -136,18 +131,18 @@ __global__ void __launch_bounds__(160) gemm_tf32_kernel(GemmArgs g) {
   } else {
     // ------------------------------------------------------------------ producers
     // Chunk ownership: lane = (row within an 8-row group) + 8 * (k-chunk within a half stage); one cp.async of a warp
-    // fills 4 whole 128-byte lines of the core-matrix layout and reads 64 contiguous bytes of 8 rows.  A thread owns 8
-    // chunks of A (4 row groups x 2 half stages) and tile_n/16 of B.
-    const int r8 = lane & 7, c4 = lane >> 3;
+    // fills 4 whole 128-byte lines of the core-matrix layout and reads 64 contiguous bytes of 8 rows.  A thread owns 4
+    // chunks of A (4 row groups of one half stage) and tile_n/32 of B.
+    const int r8 = lane & 7, c4 = lane >> 3, wq = warp & 3, wh = warp >> 2;
     const int nB = g.tile_n >> 4;
     const bool convA = g.a_mode == OP_K_CONV;
-    const float* arow0 = g.A + (size_t)(m0 + 32 * warp + r8) * g.lda;     // row group gi adds 8*gi rows
+    const float* arow0 = g.A + (size_t)(m0 + 32 * wq + r8) * g.lda;     // row group gi adds 8*gi rows
     const float* brow0 = g.B + (size_t)(n0 + r8) * g.ldb;
     // per owned A row (gi = 0..3): bit 4gi+0/1/2/3 = the neighbour above / below / left / right of its cell is on the board
     uint32_t edge = 0, rowok = 0;
 #pragma unroll
     for (int gi = 0; gi < 4; ++gi) {
-      const int p = m0 + 32 * warp + 8 * gi + r8;
+      const int p = m0 + 32 * wq + 8 * gi + r8;
       if (p < g.M) {
         rowok |= 1u << gi;
         if (convA) {
@@ -156,11 +151,13 @@ __global__ void __launch_bounds__(160) gemm_tf32_kernel(GemmArgs g) {
         }
       }
     }
-    auto load_stage = [&](int s, int kt) {
-      const uint32_t st = smem0 + (uint32_t)(s * stage_bytes);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int chunk = c4 + 4 * h, k = k_begin + kt * kGemmKStage + chunk * 4;
+    const int npairs = g.tile_n >> 2;                         // (row group, half stage) pairs of B; this warp owns q = warp + 8j
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // global -> registers (read-only path), zeros past the edges / outside the board
+    auto load_regs = [&](float4 (&ra)[4], float4 (&rb)[4], int kt) {
+      const int kc = k_begin + kt * kGemmKStage;
+      {
+        const int k = kc + (c4 + 4 * wh) * 4;
         const bool kok = k < k_end;
         long long aoff = k;                                   // element offset added to a row's base
         uint32_t need = 0;                                    // edge bits this tap needs
@@ -171,58 +168,60 @@ __global__ void __launch_bounds__(160) gemm_tf32_kernel(GemmArgs g) {
           need = (dx < 0 ? 1u : 0u) | (dx > 0 ? 2u : 0u) | (dy < 0 ? 4u : 0u) | (dy > 0 ? 8u : 0u);
           aoff = (long long)(dx * g.cols + dy) * g.lda + ci;
         }
-        const uint32_t sA = st + (uint32_t)(chunk * planeA + (32 * warp + r8) * 16);
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
           const bool ok = kok && ((rowok >> gi) & 1u) && ((need & ~(edge >> (4 * gi))) & 15u) == 0;
-          cp_async16(sA + (uint32_t)(gi * 128), ok ? arow0 + (size_t)(8 * gi) * g.lda + aoff : g.A, ok);
+          ra[gi] = ok ? __ldg(reinterpret_cast<const float4*>(arow0 + (size_t)(8 * gi) * g.lda + aoff)) : zero4;
         }
       }
-      for (int q = warp; q < 2 * (g.tile_n >> 3); q += 4) {   // (row group, half stage) pairs of B
-        const int gB = q >> 1, chunk = c4 + 4 * (q & 1), k = k_begin + kt * kGemmKStage + chunk * 4;
-        const int n = n0 + 8 * gB + r8;
-        const bool ok = k < k_end && n < g.N;
-        cp_async16(st + (uint32_t)(kRegionA + chunk * planeB + (8 * gB + r8) * 16), ok ? brow0 + (size_t)(8 * gB) * g.ldb + k : g.B, ok);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = warp + 8 * j, gB = q >> 1, k = kc + (c4 + 4 * (q & 1)) * 4;
+        const bool ok = q < npairs && k < k_end && (n0 + 8 * gB + r8) < g.N;
+        rb[j] = ok ? __ldg(reinterpret_cast<const float4*>(brow0 + (size_t)(8 * gB) * g.ldb + k)) : zero4;
       }
     };
-    auto finish_stage = [&](int s) {                          // the copies of stage s have landed (for this thread)
+    // registers -> the stage's core-matrix layout (hi / lo copies for 3xTF32), then publish the stage
+    auto put = [&](uint8_t* dst, const float4& v) {
       if (X3) {
-        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const float4 h = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                                     __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+        *reinterpret_cast<float4*>(dst) = h;
+        *reinterpret_cast<float4*>(dst + half_bytes) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      } else {
+        *reinterpret_cast<float4*>(dst) = v;
+      }
+    };
+    auto store_stage = [&](const float4 (&ra)[4], const float4 (&rb)[4], int s) {
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      uint8_t* a = st + (c4 + 4 * wh) * planeA + (32 * wq + r8) * 16;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint8_t* a = st + (c4 + 4 * h) * planeA + (32 * warp + r8) * 16;
+      for (int gi = 0; gi < 4; ++gi) put(a + gi * 128, ra[gi]);
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi) split_chunk(a + gi * 128, a + gi * 128 + half_bytes);
-        }
-        for (int q = warp; q < 2 * (g.tile_n >> 3); q += 4) {
-          uint8_t* b = st + kRegionA + (c4 + 4 * (q & 1)) * planeB + (8 * (q >> 1) + r8) * 16;
-          split_chunk(b, b + half_bytes);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int q = warp + 8 * j;
+        if (q < npairs) put(st + kRegionA + (c4 + 4 * (q & 1)) * planeB + (8 * (q >> 1) + r8) * 16, rb[j]);
       }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&full_bar[s]));
     };
-    (void)nB;
+    float4 ra[4], rb[4], na[4], nb[4];
+    if (KT > 0) load_regs(ra, rb, 0);
     for (int kt = 0; kt < KT; ++kt) {
       const int s = kt % S;
       YY_STAMP(4 + 6 * kt);
+      if (kt + 1 < KT) load_regs(na, nb, kt + 1);             // next stage's loads in flight while this one is stored
+      YY_STAMP(5 + 6 * kt);
       if (kt >= S) {                                          // the MMAs that read this slot S iterations ago
         if (lane == 0) mbar_wait(smem_u32(&free_bar[s]), (uint32_t)(((kt / S) - 1) & 1));
         __syncwarp();
       }
-      YY_STAMP(5 + 6 * kt);
-      load_stage(s, kt);
-      cp_async_commit();
       YY_STAMP(6 + 6 * kt);
-      if (kt >= 1) {
-        cp_async_wait<1>();
-        YY_STAMP(7 + 6 * kt);
-        finish_stage((kt - 1) % S);
-        YY_STAMP(8 + 6 * kt);
-      }
+      store_stage(ra, rb, s);
+      YY_STAMP(7 + 6 * kt);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { ra[i] = na[i]; rb[i] = nb[i]; }
     }
-    cp_async_wait<0>();
-    if (KT > 0) finish_stage((KT - 1) % S);
     YY_STAMP(2);
     if (lane == 0) mbar_wait(smem_u32(&done_bar), 0);
     __syncwarp();
@@ -231,13 +230,13 @@ __global__ void __launch_bounds__(160) gemm_tf32_kernel(GemmArgs g) {
 
     // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane.  With split-K the tile goes to the workspace
     // ([slice][M][N]) and gemm_reduce_kernel finishes it; otherwise bias / skip share / ReLU are applied here.
-    const int row = m0 + warp * 32 + lane;
+    const int row = m0 + wq * 32 + lane;
     const bool partial = gridDim.z > 1;
     float* crow = partial ? g.ws + ((size_t)blockIdx.z * g.M + row) * g.N : g.C + (size_t)row * g.ldc;
-    for (int c = 0; c < g.tile_n; c += 16) {
+    for (int c = 16 * wh; c < g.tile_n; c += 32) {
       uint32_t r[16];
       if (KT > 0) {
-        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, r);
+        tc_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, r);
         tc_wait_ld();
       } else {
 #pragma unroll
@@ -263,7 +262,7 @@ __global__ void __launch_bounds__(160) gemm_tf32_kernel(GemmArgs g) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, ncols);
+  if (warp == 8) tmem_dealloc(tmem_base, ncols);
 }
 
 // C = [C +] bias + sum_z ws[z] [ReLU], slices added in index order (deterministic)
@@ -302,33 +301,47 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 // colT[t*C + c][p] = X[p + d(t)][c] (zero outside the board): the transposed im2col the weight-gradient GEMM reads
-// (its reduction index is the position).  One block per (32 positions, 32 channels, tap).
+// (its reduction index is the position).  One block per (128 positions, 32 channels, tap): all loads first, then the
+// transposed stores (128 consecutive positions of one channel row per warp pass).
 __global__ void __launch_bounds__(256) im2col_t_kernel(const float* __restrict__ X, int ldx, float* __restrict__ colT, int ldo, int P, int rows,
                                                       int cols, int C) {
-  __shared__ float tile[32][33];
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tap = blockIdx.z;
+  __shared__ float tile[128][33];
+  const int p0 = blockIdx.x * 128, c0 = blockIdx.y * 32, tap = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int j = ty; j < 32; j += 8) {
-    const int p = p0 + j, c = c0 + tx;
-    float v = 0.f;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int p = p0 + ty + 8 * i, c = c0 + tx;
+    v[i] = 0.f;
     if (p < P && c < C) {
       int off;
-      if (tap_ok(p, tap, rows, cols, 0, &off)) v = X[(size_t)(p + off) * ldx + c];
+      if (tap_ok(p, tap, rows, cols, 0, &off)) v[i] = X[(size_t)(p + off) * ldx + c];
     }
-    tile[j][tx] = v;
   }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tile[ty + 8 * i][tx] = v[i];
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
-    const int c = c0 + j, p = p0 + tx;
-    if (c < C && p < P) colT[(size_t)(tap * C + c) * ldo + p] = tile[tx][j];
+    const int c = c0 + j;
+    if (c < C) {
+      float* dst = colT + (size_t)(tap * C + c) * ldo + p0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pp = tx + 32 * i;
+        if (p0 + pp < P) dst[pp] = tile[pp][j];
+      }
+    }
   }
 }
 // Wt[ci][t*Cout + co] = W[co][t*Cin + ci]  (B operand of the backward-data GEMM; the tap flip lives in the A gather)
-__global__ void __launch_bounds__(256) conv_weight_t_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Cout, int Cin) {
+// Layer l = blockIdx.y: W = params + offsets[l] -> Wt + l*Cout*9*Cin (all layers of the tower in one launch).
+__global__ void __launch_bounds__(256) conv_weight_t_kernel(const float* __restrict__ params, const long long* __restrict__ offsets,
+                                                           float* __restrict__ Wt, int Cout, int Cin) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * 9 * Cin) return;
+  const float* W = params + (offsets ? offsets[blockIdx.y] : 0);
   const int co = idx % Cout, t = (idx / Cout) % 9, ci = idx / (9 * Cout);
-  Wt[idx] = W[(size_t)co * 9 * Cin + t * Cin + ci];
+  Wt[(size_t)blockIdx.y * Cout * 9 * Cin + idx] = W[(size_t)co * 9 * Cin + t * Cin + ci];
 }
 // planes float32 [B][5][cells] (board_to_input, neural_network.py:156-196) -> X0 [B*cells][8] (channels 5..7 zero)
 __global__ void __launch_bounds__(256) planes_nhwc_kernel(const float* __restrict__ planes, float* __restrict__ X0, long long P, int cells) {
@@ -407,69 +420,94 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
     for (int j = 0; j < 4; ++j) { atomicAdd(&sums[c + j], (double)a[j]); atomicAdd(&sums[C + c + j], (double)b[j]); }
   }
 }
-// mean_invstd float [2C]; running_mean / running_var updated in place (may be NULL)
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int P, int C, float eps, float momentum, float* __restrict__ mean_invstd,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double mean = sums[c] / P;
-  double var = sums[C + c] / P - mean * mean;
-  if (var < 0.0) var = 0.0;
-  mean_invstd[c] = (float)mean;
-  mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-  if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(P > 1 ? var * P / (P - 1) : var);
-}
-// out = [relu]( gamma * (Y - mean) * invstd + beta [+ residual] )
-__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ Y, int ld, long long P, int C4, const float* __restrict__ mean_invstd,
-                                                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ residual,
-                                                      int ldr, float* __restrict__ out, int ldo, int relu) {
+// out = [relu]( gamma * (Y - mean) * invstd + beta [+ residual] ), mean / invstd from the float64 sums; block 0 also writes
+// mean_invstd float [2C] for the backward pass and updates running_mean / running_var in place (may be NULL).
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ Y, int ld, long long P, int C4, const double* __restrict__ sums,
+                                                      float eps, float momentum, float* __restrict__ mean_invstd, float* __restrict__ running_mean,
+                                                      float* __restrict__ running_var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ residual, int ldr, float* __restrict__ out, int ldo, int relu) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = C4 * 4;
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double mean = sums[c] / P;
+      double var = sums[C + c] / P - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mean_invstd[c] = (float)mean;
+      mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(P > 1 ? var * P / (P - 1) : var);
+    }
   if (idx >= P * C4) return;
-  const int c = (int)(idx % C4) * 4; const long long p = idx / C4; const int C = C4 * 4;
-  const float4 y = *reinterpret_cast<const float4*>(Y + (size_t)p * ld + c);
-  const float4 mu = *reinterpret_cast<const float4*>(mean_invstd + c), is = *reinterpret_cast<const float4*>(mean_invstd + C + c);
-  const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-  float4 o = make_float4((y.x - mu.x) * is.x * ga.x + be.x, (y.y - mu.y) * is.y * ga.y + be.y, (y.z - mu.z) * is.z * ga.z + be.z,
-                         (y.w - mu.w) * is.w * ga.w + be.w);
+  const int c = (int)(idx % C4) * 4; const long long p = idx / C4;
+  float y[4], o[4];
+  *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Y + (size_t)p * ld + c);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double mean = sums[c + j] / P;
+    double var = sums[C + c + j] / P - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)mean, is = (float)(1.0 / sqrt(var + (double)eps));
+    o[j] = (y[j] - mu) * is * gamma[c + j] + beta[c + j];
+  }
   if (residual) {
     const float4 r = *reinterpret_cast<const float4*>(residual + (size_t)p * ldr + c);
-    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
   }
-  if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-  *reinterpret_cast<float4*>(out + (size_t)p * ldo + c) = o;
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+  }
+  *reinterpret_cast<float4*>(out + (size_t)p * ldo + c) = *reinterpret_cast<float4*>(o);
 }
 // backward, pass 2: dY = gamma*invstd*(dZ - dbeta/P - xhat*dgamma/P); optional dRes = dZ (the skip connection's share);
-// block 0 also writes d gamma / d beta into the gradient buffer.
+// block 0 also writes d gamma / d beta into the gradient buffer; dbias (optional, zero on entry) += column sums of dY --
+// the gradient of the bias of the convolution in front of this batch norm (float atomics: its true value is zero, both
+// this and the reference hold rounding noise there).
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dOut, int ldd, const float* __restrict__ Out, int ldo,
                                                           const float* __restrict__ Y, int ldy, const float* __restrict__ mean_invstd,
                                                           const float* __restrict__ gamma, const double* __restrict__ sums, long long P, int C4,
                                                           float* __restrict__ dY, int lddy, float* __restrict__ dRes, int lddr,
-                                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+  __shared__ float red[256][4];
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int C = C4 * 4;
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = (float)sums[c]; dbeta[c] = (float)sums[C + c]; }
-  if (idx >= P * C4) return;
-  const int c = (int)(idx % C4) * 4; const long long p = idx / C4;
-  const float invP = 1.f / (float)P;
-  float dz[4], y[4], o[4];
-  *reinterpret_cast<float4*>(dz) = *reinterpret_cast<const float4*>(dOut + (size_t)p * ldd + c);
-  *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Y + (size_t)p * ldy + c);
-  if (Out) {
-    *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(Out + (size_t)p * ldo + c);
+  const int cg = threadIdx.x % C4, c = cg * 4;                 // 256 % C4 == 0: a block is whole rows
+  float r[4] = {0.f, 0.f, 0.f, 0.f};
+  if (idx < P * C4) {
+    const long long p = idx / C4;
+    const float invP = 1.f / (float)P;
+    float dz[4], y[4], o[4];
+    *reinterpret_cast<float4*>(dz) = *reinterpret_cast<const float4*>(dOut + (size_t)p * ldd + c);
+    *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Y + (size_t)p * ldy + c);
+    if (Out) {
+      *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(Out + (size_t)p * ldo + c);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) if (!(o[j] > 0.f)) dz[j] = 0.f;
-  }
-  float r[4];
+      for (int j = 0; j < 4; ++j) if (!(o[j] > 0.f)) dz[j] = 0.f;
+    }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float mu = mean_invstd[c + j], is = mean_invstd[C + c + j];
-    const float xhat = (y[j] - mu) * is;
-    r[j] = gamma[c + j] * is * (dz[j] - (float)sums[C + c + j] * invP - xhat * (float)sums[c + j] * invP);
+    for (int j = 0; j < 4; ++j) {
+      const float mu = mean_invstd[c + j], is = mean_invstd[C + c + j];
+      const float xhat = (y[j] - mu) * is;
+      r[j] = gamma[c + j] * is * (dz[j] - (float)sums[C + c + j] * invP - xhat * (float)sums[c + j] * invP);
+    }
+    *reinterpret_cast<float4*>(dY + (size_t)p * lddy + c) = *reinterpret_cast<float4*>(r);
+    if (dRes) *reinterpret_cast<float4*>(dRes + (size_t)p * lddr + c) = *reinterpret_cast<float4*>(dz);
   }
-  *reinterpret_cast<float4*>(dY + (size_t)p * lddy + c) = *reinterpret_cast<float4*>(r);
-  if (dRes) *reinterpret_cast<float4*>(dRes + (size_t)p * lddr + c) = *reinterpret_cast<float4*>(dz);
+  if (dbias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[threadIdx.x][j] = r[j];
+    __syncthreads();
+    if (threadIdx.x < C4) {
+      for (int l = 1; l < 256 / C4; ++l)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] += red[l * C4 + cg][j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(dbias + c + j, r[j]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ heads: losses and their gradients
@@ -596,7 +634,7 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
       YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       max_set = smem;
     }
-    gemm_tf32_kernel<3, true><<<grid, 160, smem, st>>>(g);
+    gemm_tf32_kernel<3, true><<<grid, 288, smem, st>>>(g);
   } else {
     const int smem = 4 * half;
     static int max_set = 0;
@@ -604,7 +642,7 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
       YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       max_set = smem;
     }
-    gemm_tf32_kernel<4, false><<<grid, 160, smem, st>>>(g);
+    gemm_tf32_kernel<4, false><<<grid, 288, smem, st>>>(g);
   }
   YY_LAUNCH_CHECK();
   if (zs > 1) {
@@ -630,16 +668,17 @@ int yy_lrn_im2col_t(const float* X, int ldx, float* colT, int ldo, int64_t posit
   int rc = need_device(); if (rc) return rc;
   if (positions % (rows * cols)) return set_error(YY_ERR_INVALID, "im2col_t: positions must be whole boards");
   if (positions == 0) return YY_OK;
-  dim3 grid((unsigned)((positions + 31) / 32), (unsigned)((C + 31) / 32), 9);
+  dim3 grid((unsigned)((positions + 127) / 128), (unsigned)((C + 31) / 32), 9);
   im2col_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, colT, ldo, (int)positions, rows, cols, C);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
 
-int yy_lrn_conv_weight_t(const float* W, float* Wt, int Cout, int Cin, void* stream) {
+int yy_lrn_conv_weight_t(const float* params, const long long* offsets_dev, int layers, float* Wt, int Cout, int Cin, void* stream) {
   int rc = need_device(); if (rc) return rc;
+  if (layers < 1) return YY_OK;
   const int total = Cout * 9 * Cin;
-  conv_weight_t_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, Wt, Cout, Cin);
+  conv_weight_t_kernel<<<dim3((unsigned)((total + 255) / 256), (unsigned)layers), 256, 0, (cudaStream_t)stream>>>(params, offsets_dev, Wt, Cout, Cin);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -672,29 +711,26 @@ int yy_lrn_bn_forward(const float* Y, int ld, int P, int C, const float* gamma, 
   int rc = need_device(); if (rc) return rc;
   if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
   cudaStream_t st = (cudaStream_t)stream;
-  YY_CUDA_OK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * 2 * C, st));
   bn_reduce_kernel<false><<<(P + 31) / 32, 256, 0, st>>>(Y, ld, nullptr, 0, nullptr, 0, nullptr, P, C, sums_ws);
   YY_LAUNCH_CHECK();
-  bn_finalize_kernel<<<1, 128, 0, st>>>(sums_ws, P, C, eps, momentum, mean_invstd, running_mean, running_var);
-  YY_LAUNCH_CHECK();
   const long long total = (long long)P * (C / 4);
-  bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Y, ld, P, C / 4, mean_invstd, gamma, beta, residual, ldr, out, ldo, relu);
+  bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Y, ld, P, C / 4, sums_ws, eps, momentum, mean_invstd, running_mean, running_var,
+                                                                  gamma, beta, residual, ldr, out, ldo, relu);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
 
 int yy_lrn_bn_backward(const float* dOut, int ldd, const float* Out, int ldo, const float* Y, int ldy, int P, int C,
                        const float* mean_invstd, const float* gamma, double* sums_ws, float* dY, int lddy, float* dRes, int lddr,
-                       float* dgamma, float* dbeta, void* stream) {
+                       float* dgamma, float* dbeta, float* dbias, void* stream) {
   int rc = need_device(); if (rc) return rc;
   if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
   cudaStream_t st = (cudaStream_t)stream;
-  YY_CUDA_OK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * 2 * C, st));
   bn_reduce_kernel<true><<<(P + 31) / 32, 256, 0, st>>>(Y, ldy, dOut, ldd, Out, ldo, mean_invstd, P, C, sums_ws);
   YY_LAUNCH_CHECK();
   const long long total = (long long)P * (C / 4);
   bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dOut, ldd, Out, ldo, Y, ldy, mean_invstd, gamma, sums_ws, P, C / 4,
-                                                                      dY, lddy, dRes, lddr, dgamma, dbeta);
+                                                                      dY, lddy, dRes, lddr, dgamma, dbeta, dbias);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }

@@ -81,8 +81,9 @@ class CudaOps:
         assert tuple(colT.shape) == (9 * C, P)
         _lib.check(self.L.yy_lrn_im2col_t(_p(X), _ld(X), _p(colT), _ld(colT), P, rows, cols, C, self._stream()))
 
-    def conv_weight_t(self, W, Wt, cout, cin):
-        _lib.check(self.L.yy_lrn_conv_weight_t(_p(W), _p(Wt), cout, cin, self._stream()))
+    def conv_weight_t(self, params, offsets, Wt, cout, cin):
+        """Wt[l] = transposed view of the conv weights at params[offsets[l]:] for every layer l (one launch)."""
+        _lib.check(self.L.yy_lrn_conv_weight_t(_p(params), _p(offsets), offsets.numel(), _p(Wt), cout, cin, self._stream()))
 
     def planes_nhwc(self, planes, X0):
         B = planes.shape[0]
@@ -99,11 +100,11 @@ class CudaOps:
                                             _p(out), _ld(out), int(relu), eps, momentum, _p(ws), _p(mean_invstd),
                                             _p(running_mean), _p(running_var), self._stream()))
 
-    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta):
+    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias):
         P, C = Y.shape
         _lib.check(self.L.yy_lrn_bn_backward(_p(dOut), _ld(dOut), _p(Out), _ld(Out) if Out is not None else 0, _p(Y), _ld(Y), P, C,
                                              _p(mean_invstd), _p(gamma), _p(ws), _p(dY), _ld(dY), _p(dRes),
-                                             _ld(dRes) if dRes is not None else 0, _p(dgamma), _p(dbeta), self._stream()))
+                                             _ld(dRes) if dRes is not None else 0, _p(dgamma), _p(dbeta), _p(dbias), self._stream()))
 
     def heads_loss(self, logits, pi, h, w2, b2, z, dlogits, dh, dpre, v, dw2, db2, losses):
         B, A = logits.shape
@@ -257,13 +258,17 @@ class Learner:
         self.logits, self.hid = z(B, A), z(B, VALUE_HID)     # hid: value_fc1 output BEFORE its ReLU
         self.dlogits, self.dhid, self.dpre, self.v_out = z(B, A), z(B, VALUE_HID), z(B), z(B)
         self.losses = z(2)
-        self.ws = torch.zeros(2 * 128, dtype=torch.float64, device=self.dev)
+        self.bn_ws = torch.zeros(2 * len(self._bn), 2 * 128, dtype=torch.float64, device=self.dev)   # one slot per layer and pass
+        self._bn_slot = {pre: i for i, pre in enumerate(self._bn)}
         self.G = [z(P, C) for _ in range(3)]                 # gradients w.r.t. layer outputs (rotating)
         self.dY = z(P, C)
         self.dacth, self.dYh = z(P, HEAD_CH), z(P, HEAD_CH)
         # transposed copies ([channels][positions]) for the weight-gradient GEMMs, whose reduction index is the position
         self.dYT, self.colT, self.trunkT = z(max(C, HEAD_CH) * P), z(9 * C * P), z(C * P)
-        self.Wt = z(C * max(9 * C, HEAD_CH))
+        self.Wt = z(C * HEAD_CH)
+        self.Wt_all = z(max(1, 2 * self.blocks), C, 9 * C)           # backward-data views of the tower's conv weights
+        self.w_offsets = torch.tensor([self.layout.offsets[f"res_blocks.{k}.conv{j}.weight"] for k in range(self.blocks) for j in (1, 2)],
+                                      dtype=torch.int64, device=self.dev)
         kp = (B + 3) // 4 * 4
         self.fcT, self.smallT, self.featT = z(HEAD_CH * A * max(VALUE_HID, A)), z(max(VALUE_HID, A) * kp), z(HEAD_CH * A * kp)
 
@@ -302,7 +307,7 @@ class Learner:
         ops, P = self.ops, self.p
         ops.gemm(x, self.w(wkey), self.Y[li][:P], bias=self.w(bkey), conv=self._geom(x.shape[1]))
         ops.bn_forward(self.Y[li][:P], self.w(bnpre + ".weight"), self.w(bnpre + ".bias"), residual, self.act[li][:P], True, self.bn_eps,
-                       self.bn_momentum, self.ws, self.mi[bnpre], self.running[bnpre][0], self.running[bnpre][1])
+                       self.bn_momentum, self.bn_ws[2 * self._bn_slot[bnpre]], self.mi[bnpre], self.running[bnpre][0], self.running[bnpre][1])
 
     def _conv3_backward(self, dOut, x_in, wkey, bkey, bnpre, li, dRes, dPrev, accumulate):
         """dOut: gradient w.r.t. act[li].  Writes the layer's parameter gradients; dRes (optional) receives the skip share;
@@ -310,9 +315,8 @@ class Learner:
         ops, P, C = self.ops, self.p, self.C
         cin = x_in.shape[1]
         dY = self.dY[:P]
-        ops.bn_backward(dOut, self.act[li][:P], self.Y[li][:P], self.mi[bnpre], self.w(bnpre + ".weight"), self.ws, dY, dRes,
-                        self.g(bnpre + ".weight"), self.g(bnpre + ".bias"))
-        ops.colsum(dY, self.g(bkey))
+        ops.bn_backward(dOut, self.act[li][:P], self.Y[li][:P], self.mi[bnpre], self.w(bnpre + ".weight"), self.bn_ws[2 * self._bn_slot[bnpre] + 1],
+                        dY, dRes, self.g(bnpre + ".weight"), self.g(bnpre + ".bias"), self.g(bkey))
         # dW[co][t*cin+ci] = sum_p dY[p][co] * x_in[p + d(t)][ci]: K = positions, both operands from transposed copies
         dYT, colT = self.dYT[:C * P].view(C, P), self.colT[:9 * cin * P].view(9 * cin, P)
         ops.transpose(dY, dYT)
@@ -320,16 +324,14 @@ class Learner:
         ops.gemm(dYT, colT, self.g(wkey))
         if dPrev is not None:
             # dX[p][ci] = sum_{t,co} dY[p - d(t)][co] * W[co][t*cin+ci]: implicit (mirrored) im2col of dY times Wt
-            Wt = self.Wt[:cin * 9 * C].view(cin, 9 * C)
-            ops.conv_weight_t(self.w(wkey), Wt, C, cin)
-            ops.gemm(dY, Wt, dPrev, accumulate=accumulate, conv=self._geom(C, flip=True))
+            ops.gemm(dY, self.Wt_all[li - 1], dPrev, accumulate=accumulate, conv=self._geom(C, flip=True))
 
     def _head_forward(self, head, trunk):
         ops, P = self.ops, self.p
         ops.gemm(trunk, self.w(f"{head}_conv.weight"), self.Yh[head][:P], bias=self.w(f"{head}_conv.bias"))
         pre = f"{head}_bn"
         ops.bn_forward(self.Yh[head][:P], self.w(pre + ".weight"), self.w(pre + ".bias"), None, self.acth[head][:P], True, self.bn_eps,
-                       self.bn_momentum, self.ws, self.mi[pre], self.running[pre][0], self.running[pre][1])
+                       self.bn_momentum, self.bn_ws[2 * self._bn_slot[pre]], self.mi[pre], self.running[pre][0], self.running[pre][1])
         return self.acth[head][:P].view(self.b, self.A * HEAD_CH)
 
     def _kpad(self):
@@ -358,9 +360,8 @@ class Learner:
         ops, P, C = self.ops, self.p, self.C
         pre = f"{head}_bn"
         dYh = self.dYh[:P]
-        ops.bn_backward(dfeat.view(P, HEAD_CH), self.acth[head][:P], self.Yh[head][:P], self.mi[pre], self.w(pre + ".weight"), self.ws, dYh, None,
-                        self.g(pre + ".weight"), self.g(pre + ".bias"))
-        ops.colsum(dYh, self.g(f"{head}_conv.bias"))
+        ops.bn_backward(dfeat.view(P, HEAD_CH), self.acth[head][:P], self.Yh[head][:P], self.mi[pre], self.w(pre + ".weight"),
+                        self.bn_ws[2 * self._bn_slot[pre] + 1], dYh, None, self.g(pre + ".weight"), self.g(pre + ".bias"), self.g(f"{head}_conv.bias"))
         dYhT = self.dYT[:HEAD_CH * P].view(HEAD_CH, P)
         ops.transpose(dYh, dYhT)
         ops.gemm(dYhT, self.trunkT[:C * P].view(C, P), self.g(f"{head}_conv.weight"))
@@ -371,6 +372,7 @@ class Learner:
     def _run(self):
         ops, nb, b, P, C = self.ops, self.blocks, self.b, self.p, self.C
         self.grads.zero_()
+        self.bn_ws.zero_()
         # ---- forward (neural_network.py:94-123, train mode)
         X0 = self.X0[:P]
         ops.planes_nhwc(self.planes_in[:b], X0)
@@ -391,6 +393,8 @@ class Learner:
         ops.heads_loss(logits, self.pi_in[:b], hid, self.w("value_fc2.weight"), self.w("value_fc2.bias"), self.z_in[:b],
                        dlogits, dhid, self.dpre[:b], self.v_out[:b], self.g("value_fc2.weight"), self.g("value_fc2.bias"), self.losses)
         # ---- backward
+        if nb:
+            ops.conv_weight_t(self.params, self.w_offsets, self.Wt_all, C, C)
         ops.transpose(trunk, self.trunkT[:C * P].view(C, P))
         dfeat = self.dacth[:P].view(b, self.A * HEAD_CH)
         G = [g[:P] for g in self.G]
