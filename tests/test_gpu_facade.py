@@ -230,3 +230,27 @@ def test_cli_train_mode_runs_the_whole_loop(pkg, tmp_path):
     ck = torch.load(os.path.join(md, "checkpoint_1.pth.tar"), map_location="cpu", weights_only=False)["state_dict"]
     assert all(torch.equal(cur[k], ck[k]) for k in ck)                       # the trained checkpoint became the current model
     assert int(ck["bn1.num_batches_tracked"]) > 0                             # the learner actually stepped
+
+
+def test_gui_ai_move_endpoint_body(pkg, tmp_path):
+    """POST /api/ai_move (src/gui/server.py:30-129) without the web server: request / response dictionaries."""
+    import time
+    from yinyang_game_alphazero_b200 import ai_move
+    game = pkg["game"].YinYangGame(6, 6)
+    model = os.path.join(str(tmp_path), "best_model.pth.tar")
+    pkg["network"].YinYangNeuralNetwork(game).save_model(model)
+    req = {"board": [[0] * 6 for _ in range(6)], "currentPlayer": 1, "rows": 6, "cols": 6, "modelPath": model}
+    out = ai_move.get_ai_move(req)
+    assert out["validMove"] is True and 0 <= out["row"] < 6 and 0 <= out["col"] < 6
+    board = np.zeros((6, 6), np.int8); board[0, 0] = 1; board[0, 1] = -1
+    req["board"], req["currentPlayer"] = board.tolist(), -1
+    t0 = time.perf_counter()
+    out = ai_move.get_ai_move(req)
+    dt = time.perf_counter() - t0
+    b = game.getInitBoard(); b.board = board
+    assert out["validMove"] is True and game.getValidMoves(b, -1)[out["row"] * 6 + out["col"]] == 1
+    assert dt < 5.0
+    full = np.ones((6, 6), np.int8)                                   # a pre-existing 2x2: nobody can move
+    req["board"] = full.tolist()
+    assert ai_move.get_ai_move(req) == {"validMove": False, "message": "No valid moves available"}
+    assert "error" in ai_move.get_ai_move({"board": None})

@@ -23,7 +23,7 @@ __all__ = ["build", "YinYangError", "bitboard"]
 
 
 _MODULES = ("engine", "game", "network", "mcts", "self_play", "players", "weights", "distributed", "data_utils", "arena",
-            "learner", "trainer", "training_pipeline", "alphazero")
+            "learner", "trainer", "training_pipeline", "alphazero", "ai_move")
 
 
 def __getattr__(name):
