@@ -234,6 +234,10 @@ def run_b200(args):
     env = bench_env(engine, torch, peaks) if rank == 0 else None
     dataset = bench_dataset(engine, torch, peaks) if rank == 0 else None
     learner_leg = bench_learner(engine, torch, peaks) if rank == 0 else None
+    learner_dp = bench_learner_dp(engine, torch, world) if world > 1 else None     # every rank takes part (NCCL all-reduce)
+    if learner_leg is not None and learner_dp is not None:
+        learner_leg["data_parallel"] = learner_dp
+    ai_move_leg = bench_ai_move() if rank == 0 else None
 
     if rank == 0:
         tower_s = prof["ms"] * 1e-3 / max(1, prof["launches"])
@@ -262,7 +266,7 @@ def run_b200(args):
                 "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "api": "Engine.search_host + next_state_host (numpy in/out)"},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "env": env, "dataset": dataset, "learner": learner_leg,
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "env": env, "dataset": dataset, "learner": learner_leg, "ai_move": ai_move_leg,
                 "moves_per_s_roofline": peaks["bf16_tflops_sustained"] * 1e12 / ((SIMS + 1) * FLOPS_PER_LEAF) * world,
                 "leaf_evals_per_s": (SIMS + 1) * value,
                 "nccl": {"weight_broadcast_s": t_bcast, "replay_gather_s": t_gather, "replay_records_gathered": int(n_records)},
@@ -396,6 +400,65 @@ def bench_dataset(engine, torch, peaks):
             "l2_policy": "outputs (3.2 GB per launch) larger than L2; the timing includes torch's allocation of the outputs"}
 
 
+def bench_learner_dp(engine, torch, world):
+    """Data-parallel learner over all ranks (weak scaling: batch 64 per GPU): every step = backward graph, one NCCL
+    all-reduce of the 14.5 MB flat gradient buffer, Adam graph.  Max over ranks of the device time."""
+    import torch.distributed as dist
+    from yinyang_game_alphazero_b200 import learner as lrn
+    from oracle import port
+    B = 64
+    torch.manual_seed(0)
+    net = port.build_net(ROWS, COLS, 128, 10)
+    rank = dist.get_rank()
+    plies = torch.arange(B, dtype=torch.int32) % 52
+    black, white, _ = engine.random_playout(B, plies, ROWS, COLS, seed=0x1EA2 + rank)
+    counts = torch.randint(0, 800, (B, A), dtype=torch.int16, device="cuda")
+    values = torch.ones(B, device="cuda")
+    planes, pol, val = engine.augment_samples(black, white, ROWS, COLS, counts=counts, values=values)
+    L = lrn.Learner(ROWS, COLS, 128, 10, batch_size=B, state_dict=net.state_dict(), data_parallel=True)
+    for _ in range(4):
+        L.step(planes[:B], pol[:B], val[:B])
+    torch.cuda.synchronize(); dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 32
+    ev0.record()
+    for i in range(steps):
+        j = (i % 8) * B
+        L.step(planes[j:j + B], pol[j:j + B], val[j:j + B])
+    ev1.record(); torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item()) * 1e-3 / steps
+    w0 = L.params[:1024].clone()
+    dist.broadcast(w0, 0)
+    return {"value": world * B / sec, "unit": "samples/s", "ms_per_step": sec * 1e3, "n_gpus": world, "scaling": "weak",
+            "weights_identical_across_ranks": bool(torch.equal(w0, L.params[:1024])),
+            "collective": "one NCCL all-reduce of the flat gradient buffer (%.1f MB) per step" % (L.grads.numel() * 4 / 1e6)}
+
+
+def bench_ai_move():
+    """latency of one AI move as the GUI requests it (src/gui/server.py:30-129: one position, 100 simulations,
+    reference-initialised 128x10 network), through ai_move.get_ai_move with host dictionaries in and out."""
+    import tempfile
+    import numpy as np
+    from yinyang_game_alphazero_b200 import ai_move
+    from yinyang_game_alphazero_b200.game import YinYangGame
+    from yinyang_game_alphazero_b200.network import YinYangNeuralNetwork
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "best_model.pth.tar")
+        YinYangNeuralNetwork(YinYangGame(ROWS, COLS)).save_model(path)
+        board = np.zeros((ROWS, COLS), np.int8); board[3, 3] = 1; board[3, 4] = -1
+        req = {"board": board.tolist(), "currentPlayer": 1, "rows": ROWS, "cols": COLS, "modelPath": path}
+        ai_move.get_ai_move(req)                               # builds the engine, loads the weights
+        times = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            out = ai_move.get_ai_move(req)
+            times.append(time.perf_counter() - t0)
+    return {"metric": "AI move latency (8x8, 100 simulations, one position)", "value": float(np.median(times) * 1e3), "unit": "ms",
+            "higher_is_better": False, "valid_move": bool(out.get("validMove")), "api": "ai_move.get_ai_move (request / response dictionaries of /api/ai_move)"}
+
+
 def bench_learner(engine, torch, peaks):
     """optimisation steps of the reference trainer (trainer.py:120-137; batch 64, Adam) on the 128x10 network,
     8x8 boards: one CUDA-graph replay of the yy_lrn_* kernels per step.  Tensor bound on paper, latency bound in fact."""
@@ -413,7 +476,7 @@ def bench_learner(engine, torch, peaks):
     planes, pol, val = engine.augment_samples(black, white, ROWS, COLS, counts=counts, values=values)   # 2,048 samples
     out = {}
     for precision in ("3xtf32", "tf32"):
-        L = lrn.Learner(ROWS, COLS, 128, 10, batch_size=B, state_dict=net.state_dict(), precision=precision)
+        L = lrn.Learner(ROWS, COLS, 128, 10, batch_size=B, state_dict=net.state_dict(), precision=precision, data_parallel=False)
         l0 = _lib.lib().yy_launch_count()
         first = L.step(planes[:B], pol[:B], val[:B]).clone()
         kernels = (_lib.lib().yy_launch_count() - l0) // 2     # the eager step + its capture pass both count
@@ -437,6 +500,26 @@ def bench_learner(engine, torch, peaks):
                                        "peak_source": "half of the measured sustained bf16 rate (TF32 = half rate)",
                                        "algorithmic_flops_per_step": flops,
                                        "note": "4,096 positions per step: every kernel is microseconds long, the step is launch/latency bound"}}
+    # end to end through the reference-facing trainer: host examples in (boards, policies, values), device dataset
+    # construction + augmentation, shuffled batches, checkpoint-ready weights out
+    from yinyang_game_alphazero_b200 import trainer as trn
+    from yinyang_game_alphazero_b200.game import YinYangGame
+    import tempfile
+    game = YinYangGame(ROWS, COLS)
+    rng = np.random.default_rng(0)
+    grids = (rng.integers(0, 3, (512, ROWS, COLS)) - 1).astype(np.int8)
+    pis = rng.random((512, A)); pis /= pis.sum(1, keepdims=True)
+    examples = [(grids[i], pis[i], float(rng.choice([-1.0, 1.0]))) for i in range(512)]
+    with tempfile.TemporaryDirectory() as d:
+        tr = trn.AlphaZeroTrainer(game, model_dir=d, batch_size=B, data_parallel=False)
+        tr.train(examples[:64], epochs=1, augment=True)        # graph capture
+        t0 = time.perf_counter()
+        m = tr.train(examples, epochs=2, augment=True)         # 4,096 samples x 2 epochs = 128 steps
+        e2e_s = time.perf_counter() - t0
+    out["3xtf32"]["e2e"] = {"value": 2 * 8 * len(examples) / e2e_s, "unit": "samples/s", "steps": 128,
+                            "h2d_bytes_per_step": B * (2 * 8 + 4 * A + 4) // 8, "d2h_bytes_per_step": 0,
+                            "api": "AlphaZeroTrainer.train(examples, epochs=2, augment=True): host examples in, metrics out",
+                            "total_loss_per_epoch": [float(x) for x in m["total_loss"]]}
     res = out["3xtf32"]
     res["metric"] = "training samples/sec (8x8, 128x10 network, batch 64, Adam; one CUDA-graph replay per step)"
     res["single_pass_tf32"] = out["tf32"]

@@ -23,7 +23,7 @@ logger = logging.getLogger("YinYangNN.trainer")
 
 class AlphaZeroTrainer:
     def __init__(self, game, model_dir="models", lr=0.001, batch_size=64, weight_decay=1e-4, device=None,
-                 num_channels=128, num_res_blocks=10, precision="3xtf32"):
+                 num_channels=128, num_res_blocks=10, precision="3xtf32", data_parallel=True):
         self.game = game
         self.model_dir = model_dir
         self.batch_size = batch_size
@@ -33,7 +33,7 @@ class AlphaZeroTrainer:
         self.nnet = YinYangNeuralNetwork(game, num_channels, num_res_blocks)        # reference initialisation (trainer.py:48)
         n, m = game.getBoardSize()
         self.learner = Learner(n, m, num_channels, num_res_blocks, batch_size=batch_size, lr=lr, weight_decay=weight_decay,
-                               state_dict=self.nnet.state_dict(), device=self.device, precision=precision)
+                               state_dict=self.nnet.state_dict(), device=self.device, precision=precision, data_parallel=data_parallel)
         logger.info(f"Training parameters: lr={lr}, batch_size={batch_size}, weight_decay={weight_decay}")
 
     def train(self, examples, epochs=10, augment=True):
