@@ -268,7 +268,9 @@ int yy_augment_samples(int rows, int cols, const uint64_t *black_dev, const uint
  * the single-pass variant (torch's default for fp32 convolutions on a GPU).  accumulate != 0: the product is added to C
  * (a skip connection's share of a gradient).  tile_n: output columns per CTA (16..128, multiple of 16); split_k >= 1
  * slices K over gridDim.z: partial tiles go to ws (>= split*M*N floats) and a reducer adds them in slice order, so
- * results are bit-reproducible.  lda/ldb/ldc/N/K multiples of 4, pointers 16-byte aligned. */
+ * results are bit-reproducible.  bn_sums (optional, float64 [2N], zero on entry, N dividing 128): receives the per-column
+ * sum / sum of squares of the finished C, i.e. the statistics of the batch norm that follows (yy_lrn_bn_forward with
+ * have_sums = 1 then skips its own pass).  lda/ldb/ldc/N/K multiples of 4, pointers 16-byte aligned. */
 #define YY_GEMM_TF32 0
 #define YY_GEMM_3XTF32 1
 #define YY_OP_K 0
@@ -280,7 +282,7 @@ typedef struct {
 } yy_conv_geom;
 int yy_lrn_gemm(const float *A, int lda, int a_mode, const float *B, int ldb, float *C, int ldc, int M, int N, int K,
                 const float *bias, int relu, int accumulate, int tile_n, int split_k, float *ws, int64_t ws_floats,
-                int precision, const yy_conv_geom *conv, void *stream);
+                int precision, const yy_conv_geom *conv, double *bn_sums, void *stream);
 /* Developer tool: while dbg_dev != NULL (>= 128 int64) CTA (0,0,0) of every yy_lrn_gemm launch records clock64 stamps:
  * [0] start, [1] after setup, [4+6k .. 8+6k] producer phases of K-iteration k (start, slot free, copies issued, copies of
  * iteration k-1 landed, iteration k-1 split + published), [2] loop end, [119] accumulator complete, [3] epilogue end. */
@@ -302,10 +304,12 @@ int yy_lrn_colsum(const float *X, int ld, int R, int C, float *out, void *stream
 /* nn.BatchNorm2d in train() (neural_network.py:22-25,44): out = [relu](gamma*(Y-mean)*invstd + beta [+ residual]) with
  * the batch's own mean / biased variance over the P positions; writes mean_invstd float[2C] for the backward pass and
  * updates running_mean / running_var (unbiased variance, `momentum`) in place when not NULL.  sums_ws: float64[2C], ZERO
- * on entry (the host side zeroes one slot per layer and pass with a single memset per step). */
+ * on entry (the host side zeroes one slot per layer and pass with a single memset per step), or -- have_sums != 0 --
+ * already holding the column sums / sums of squares of Y (yy_lrn_gemm's bn_sums). */
 int yy_lrn_bn_forward(const float *Y, int ld, int P, int C, const float *gamma, const float *beta,
                       const float *residual, int ldr, float *out, int ldo, int relu, float eps, float momentum,
-                      double *sums_ws, float *mean_invstd, float *running_mean, float *running_var, void *stream);
+                      double *sums_ws, int have_sums, float *mean_invstd, float *running_mean, float *running_var,
+                      void *stream);
 /* Backward of the above (and of the ReLU after it when Out != NULL: dZ = dOut*[Out > 0]):
  * dY = gamma*invstd*(dZ - mean(dZ) - xhat*mean(dZ*xhat)); dRes (optional) = dZ; dgamma = sum dZ*xhat; dbeta = sum dZ;
  * dbias (optional, zero on entry) += column sums of dY = the bias gradient of the convolution feeding this batch norm.

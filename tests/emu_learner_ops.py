@@ -22,7 +22,7 @@ class TorchEmuOps:
             o[:, xs:xe, ys:ye, t, :] = x[:, xs + dx:xe + dx, ys + dy:ye + dy, :]
         return o.reshape(P, 9 * C)
 
-    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None):
+    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None):
         Ae = A if conv is None else self._im2col(A, conv[0], conv[1], conv[3])
         r = Ae.double() @ B.double().t()
         if bias is not None:
@@ -30,6 +30,9 @@ class TorchEmuOps:
         if accumulate:
             r = r + C.double()
         C.copy_((r.clamp_min(0) if relu else r).float())
+        if bn_sums is not None:
+            N = C.shape[1]
+            bn_sums[:N] += C.double().sum(0); bn_sums[N:2 * N] += (C.double() ** 2).sum(0)
 
     def transpose(self, inp, out):
         out.copy_(inp.t())
@@ -50,10 +53,14 @@ class TorchEmuOps:
     def colsum(self, X, out):
         out.copy_(X.double().sum(0).float())
 
-    def bn_forward(self, Y, gamma, beta, residual, out, relu, eps, momentum, ws, mean_invstd, running_mean, running_var):
+    def bn_forward(self, Y, gamma, beta, residual, out, relu, eps, momentum, ws, mean_invstd, running_mean, running_var, have_sums=False):
         P, C = Y.shape
-        mean = Y.double().mean(0)
-        var = (Y.double() ** 2).mean(0) - mean ** 2
+        if have_sums:
+            mean = ws[:C] / P
+            var = ws[C:2 * C] / P - mean ** 2
+        else:
+            mean = Y.double().mean(0)
+            var = (Y.double() ** 2).mean(0) - mean ** 2
         mean_invstd[:C] = mean.float(); mean_invstd[C:] = (1.0 / torch.sqrt(var + eps)).float()
         if running_mean is not None:
             running_mean.mul_(1 - momentum).add_(momentum * mean.float())

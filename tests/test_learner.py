@@ -151,6 +151,13 @@ def test_convolution_passes_match_their_definition(yy, rows, cols, cin, cout, bo
     y_ref, y = torch.zeros(P, cout), torch.zeros(P, cout).cuda()
     emu.gemm(X, W, y_ref, bias=bias, conv=(rows, cols, cin, 0)); ops.gemm(X.cuda(), W.cuda(), y, bias=bias.cuda(), conv=(rows, cols, cin, 0))
     close(y, y_ref, "forward")
+    # the same product with the following batch norm's statistics taken in the split-K reducer / after the epilogue
+    sums = torch.zeros(256, dtype=torch.float64).cuda()
+    y2 = torch.zeros(P, cout).cuda()
+    ops.gemm(X.cuda(), W.cuda(), y2, bias=bias.cuda(), conv=(rows, cols, cin, 0), bn_sums=sums)
+    assert torch.equal(y2, y)
+    assert (sums[:cout].cpu() - y_ref.double().sum(0)).abs().max() <= 2e-5 * y_ref.double().abs().sum(0).max()
+    assert torch.allclose(sums[cout:2 * cout].cpu(), (y_ref.double() ** 2).sum(0), rtol=2e-5)
     colT_ref, colT = torch.zeros(9 * cin, P), torch.zeros(9 * cin, P).cuda()
     emu.im2col_t(X, colT_ref, rows, cols); ops.im2col_t(X.cuda(), colT, rows, cols)
     assert torch.equal(colT.cpu(), colT_ref)
@@ -217,7 +224,7 @@ def test_kernels_match_their_emulation(yy):
             out, mi, rm, rv = (t.clone().cuda() for t in (out_ref, mi_ref, rm_ref, rv_ref))
             ws = torch.zeros(256, dtype=torch.float64).cuda()       # zero on entry (one slot per layer and pass in the learner)
             emu.bn_forward(Y, gamma, beta, residual, out_ref, relu, 1e-5, 0.1, None, mi_ref, rm_ref, rv_ref)
-            ops.bn_forward(cu(Y), cu(gamma), cu(beta), cu(residual), out, relu, 1e-5, 0.1, ws, mi, rm, rv)
+            ops.bn_forward(cu(Y), cu(gamma), cu(beta), cu(residual), out, relu, 1e-5, 0.1, ws.zero_(), mi, rm, rv)
             assert torch.allclose(out.cpu(), out_ref, rtol=1e-5, atol=1e-5)
             assert torch.allclose(mi.cpu(), mi_ref, rtol=1e-5, atol=1e-6)
             assert torch.allclose(rm.cpu(), rm_ref, rtol=1e-5, atol=1e-6) and torch.allclose(rv.cpu(), rv_ref, rtol=1e-5, atol=1e-6)

@@ -265,9 +265,56 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
   if (warp == 8) tmem_dealloc(tmem_base, ncols);
 }
 
-// C = [C +] bias + sum_z ws[z] [ReLU], slices added in index order (deterministic)
+// C = [C +] bias + sum_z ws[z] [ReLU], slices added in index order (deterministic).  A block finishes 4 slabs of
+// 256/N4 whole rows; bn_sums (optional, float64 [2N], zero on entry) receives the per-column sum / sum of squares of the
+// finished C -- the statistics of the batch norm that follows a convolution, saving its own pass over C.
 __global__ void __launch_bounds__(256) gemm_reduce_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, int ldc, int M, int N4,
-                                                         const float* __restrict__ bias, int relu, int accumulate) {
+                                                         const float* __restrict__ bias, int relu, int accumulate, double* __restrict__ bn_sums) {
+  __shared__ float red[2][256][4];
+  const int cg = threadIdx.x % N4, n = cg * 4, rl = threadIdx.x / N4, lanes = 256 / N4;   // host guarantees 256 % N4 == 0 when bn_sums
+  const size_t slice = (size_t)M * N4 * 4;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  float bi[4] = {0.f, 0.f, 0.f, 0.f};
+  if (bias) { bi[0] = bias[n]; bi[1] = bias[n + 1]; bi[2] = bias[n + 2]; bi[3] = bias[n + 3]; }
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) {
+    const int m = (blockIdx.x * 4 + sl) * lanes + rl;
+    if (m < M && rl < lanes) {
+      float a[4];
+      *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(ws + (size_t)m * N4 * 4 + n);
+      for (int z = 1; z < splits; ++z) {
+        const float4 b = *reinterpret_cast<const float4*>(ws + z * slice + (size_t)m * N4 * 4 + n);
+        a[0] += b.x; a[1] += b.y; a[2] += b.z; a[3] += b.w;
+      }
+      float* c = C + (size_t)m * ldc + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] += bi[j];
+      if (accumulate) { const float4 o = *reinterpret_cast<const float4*>(c); a[0] += o.x; a[1] += o.y; a[2] += o.z; a[3] += o.w; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (relu) a[j] = fmaxf(a[j], 0.f);
+        s1[j] += a[j]; s2[j] += a[j] * a[j];
+      }
+      *reinterpret_cast<float4*>(c) = *reinterpret_cast<float4*>(a);
+    }
+  }
+  if (bn_sums) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[0][threadIdx.x][j] = s1[j]; red[1][threadIdx.x][j] = s2[j]; }
+    __syncthreads();
+    if (threadIdx.x < N4) {
+      for (int l = 1; l < lanes; ++l)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s1[j] += red[0][l * N4 + cg][j]; s2[j] += red[1][l * N4 + cg][j]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { atomicAdd(&bn_sums[n + j], (double)s1[j]); atomicAdd(&bn_sums[4 * N4 + n + j], (double)s2[j]); }
+    }
+  }
+}
+
+// the same reduction for column counts that do not tile a 256-thread block
+__global__ void __launch_bounds__(256) gemm_reduce_flat_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, int ldc, int M, int N4,
+                                                              const float* __restrict__ bias, int relu, int accumulate) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)M * N4) return;
   const int m = (int)(idx / N4), n = (int)(idx % N4) * 4;
@@ -470,42 +517,50 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                           float* __restrict__ dY, int lddy, float* __restrict__ dRes, int lddr,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
   __shared__ float red[256][4];
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int C = C4 * 4;
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = (float)sums[c]; dbeta[c] = (float)sums[C + c]; }
-  const int cg = threadIdx.x % C4, c = cg * 4;                 // 256 % C4 == 0: a block is whole rows
-  float r[4] = {0.f, 0.f, 0.f, 0.f};
-  if (idx < P * C4) {
-    const long long p = idx / C4;
-    const float invP = 1.f / (float)P;
-    float dz[4], y[4], o[4];
-    *reinterpret_cast<float4*>(dz) = *reinterpret_cast<const float4*>(dOut + (size_t)p * ldd + c);
-    *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Y + (size_t)p * ldy + c);
-    if (Out) {
-      *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(Out + (size_t)p * ldo + c);
+  const int cg = threadIdx.x % C4, c = cg * 4;                 // 256 % C4 == 0: a block is whole rows (kBnSlabs slabs of them)
+  const float invP = 1.f / (float)P;
+  float mu[4], is[4], ga[4], sg[4], sb[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (!(o[j] > 0.f)) dz[j] = 0.f;
-    }
+  for (int j = 0; j < 4; ++j) {
+    mu[j] = mean_invstd[c + j]; is[j] = mean_invstd[C + c + j]; ga[j] = gamma[c + j];
+    sg[j] = (float)sums[c + j] * invP; sb[j] = (float)sums[C + c + j] * invP;
+  }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float mu = mean_invstd[c + j], is = mean_invstd[C + c + j];
-      const float xhat = (y[j] - mu) * is;
-      r[j] = gamma[c + j] * is * (dz[j] - (float)sums[C + c + j] * invP - xhat * (float)sums[c + j] * invP);
+  for (int sl = 0; sl < 4; ++sl) {
+    const long long idx = ((long long)blockIdx.x * 4 + sl) * 256 + threadIdx.x;
+    if (idx < P * C4) {
+      const long long p = idx / C4;
+      float dz[4], y[4], o[4], r[4];
+      *reinterpret_cast<float4*>(dz) = *reinterpret_cast<const float4*>(dOut + (size_t)p * ldd + c);
+      *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Y + (size_t)p * ldy + c);
+      if (Out) {
+        *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(Out + (size_t)p * ldo + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (!(o[j] > 0.f)) dz[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xhat = (y[j] - mu[j]) * is[j];
+        r[j] = ga[j] * is[j] * (dz[j] - sb[j] - xhat * sg[j]);
+        acc[j] += r[j];
+      }
+      *reinterpret_cast<float4*>(dY + (size_t)p * lddy + c) = *reinterpret_cast<float4*>(r);
+      if (dRes) *reinterpret_cast<float4*>(dRes + (size_t)p * lddr + c) = *reinterpret_cast<float4*>(dz);
     }
-    *reinterpret_cast<float4*>(dY + (size_t)p * lddy + c) = *reinterpret_cast<float4*>(r);
-    if (dRes) *reinterpret_cast<float4*>(dRes + (size_t)p * lddr + c) = *reinterpret_cast<float4*>(dz);
   }
   if (dbias) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[threadIdx.x][j] = r[j];
+    for (int j = 0; j < 4; ++j) red[threadIdx.x][j] = acc[j];
     __syncthreads();
     if (threadIdx.x < C4) {
       for (int l = 1; l < 256 / C4; ++l)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] += red[l * C4 + cg][j];
+        for (int j = 0; j < 4; ++j) acc[j] += red[l * C4 + cg][j];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(dbias + c + j, r[j]);
+      for (int j = 0; j < 4; ++j) atomicAdd(dbias + c + j, acc[j]);
     }
   }
 }
@@ -604,7 +659,7 @@ extern "C" {
 
 int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                 const float* bias, int relu, int accumulate, int tile_n, int split_k, float* ws, int64_t ws_floats, int precision,
-                const yy_conv_geom* conv, void* stream) {
+                const yy_conv_geom* conv, double* bn_sums, void* stream) {
   int rc = need_device(); if (rc) return rc;
   if (M <= 0 || N <= 0 || K <= 0) return set_error(YY_ERR_INVALID, "gemm: empty problem");
   if ((lda | ldb | ldc | N | K) & 3) return set_error(YY_ERR_INVALID, "gemm: lda, ldb, ldc, N and K must be multiples of 4 floats");
@@ -618,6 +673,7 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
   if (precision != YY_GEMM_TF32 && precision != YY_GEMM_3XTF32) return set_error(YY_ERR_INVALID, "gemm: precision must be YY_GEMM_TF32 or YY_GEMM_3XTF32");
   if (tile_n < 16 || tile_n > 128 || tile_n % 16) return set_error(YY_ERR_INVALID, "gemm: tile_n in [16,128] step 16");
   if (split_k < 1) return set_error(YY_ERR_INVALID, "gemm: split_k >= 1");
+  if (bn_sums && (N > 128 || 128 % N)) return set_error(YY_ERR_INVALID, "gemm: fused batch-norm statistics need N dividing 128");
   int kps = (K + split_k - 1) / split_k;
   kps = (kps + kGemmKStage - 1) / kGemmKStage * kGemmKStage;
   const int zs = (K + kps - 1) / kps;
@@ -646,8 +702,16 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
   }
   YY_LAUNCH_CHECK();
   if (zs > 1) {
-    const long long total = (long long)M * (N / 4);
-    gemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, zs, C, ldc, M, N / 4, bias, relu, accumulate);
+    if (256 % (N / 4) == 0) {
+      const int rows_per_block = 4 * (256 / (N / 4));
+      gemm_reduce_kernel<<<(unsigned)((M + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(ws, zs, C, ldc, M, N / 4, bias, relu, accumulate, bn_sums);
+    } else {
+      const long long total = (long long)M * (N / 4);
+      gemm_reduce_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, zs, C, ldc, M, N / 4, bias, relu, accumulate);
+    }
+    YY_LAUNCH_CHECK();
+  } else if (bn_sums) {
+    bn_reduce_kernel<false><<<(M + 31) / 32, 256, 0, st>>>(C, ldc, nullptr, 0, nullptr, 0, nullptr, M, N, bn_sums);
     YY_LAUNCH_CHECK();
   }
   return YY_OK;
@@ -706,13 +770,15 @@ int yy_lrn_colsum(const float* X, int ld, int R, int C, float* out, void* stream
 static int bn_shape_ok(int C) { return C >= 4 && C <= 128 && 128 % C == 0; }
 
 int yy_lrn_bn_forward(const float* Y, int ld, int P, int C, const float* gamma, const float* beta, const float* residual, int ldr,
-                      float* out, int ldo, int relu, float eps, float momentum, double* sums_ws, float* mean_invstd,
+                      float* out, int ldo, int relu, float eps, float momentum, double* sums_ws, int have_sums, float* mean_invstd,
                       float* running_mean, float* running_var, void* stream) {
   int rc = need_device(); if (rc) return rc;
   if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
   cudaStream_t st = (cudaStream_t)stream;
-  bn_reduce_kernel<false><<<(P + 31) / 32, 256, 0, st>>>(Y, ld, nullptr, 0, nullptr, 0, nullptr, P, C, sums_ws);
-  YY_LAUNCH_CHECK();
+  if (!have_sums) {
+    bn_reduce_kernel<false><<<(P + 31) / 32, 256, 0, st>>>(Y, ld, nullptr, 0, nullptr, 0, nullptr, P, C, sums_ws);
+    YY_LAUNCH_CHECK();
+  }
   const long long total = (long long)P * (C / 4);
   bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Y, ld, P, C / 4, sums_ws, eps, momentum, mean_invstd, running_mean, running_var,
                                                                   gamma, beta, residual, ldr, out, ldo, relu);
@@ -729,7 +795,7 @@ int yy_lrn_bn_backward(const float* dOut, int ldd, const float* Out, int ldo, co
   bn_reduce_kernel<true><<<(P + 31) / 32, 256, 0, st>>>(Y, ldy, dOut, ldd, Out, ldo, mean_invstd, P, C, sums_ws);
   YY_LAUNCH_CHECK();
   const long long total = (long long)P * (C / 4);
-  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dOut, ldd, Out, ldo, Y, ldy, mean_invstd, gamma, sums_ws, P, C / 4,
+  bn_bwd_apply_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(dOut, ldd, Out, ldo, Y, ldy, mean_invstd, gamma, sums_ws, P, C / 4,
                                                                       dY, lddy, dRes, lddr, dgamma, dbeta, dbias);
   YY_LAUNCH_CHECK();
   return YY_OK;

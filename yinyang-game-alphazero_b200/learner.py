@@ -52,9 +52,10 @@ class CudaOps:
     def _stream():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None):
+    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None):
         """C[M,N] = [C +] A @ B^T (+bias) (relu), B = [N,K].  conv = (rows, cols, cin, flip): A is the activation tensor
-        [positions, cin] and the product runs over its implicit im2col (YY_OP_K_CONV)."""
+        [positions, cin] and the product runs over its implicit im2col (YY_OP_K_CONV).  bn_sums (float64 [>= 2N], zero): also
+        accumulate the column sums / sums of squares of C (the statistics of the batch norm that follows)."""
         M, N = C.shape
         K = B.shape[1]
         assert B.shape[0] == N and (conv is not None or A.shape == (M, K))
@@ -69,7 +70,7 @@ class CudaOps:
         geom = ctypes.byref(_lib.ConvGeom(*conv)) if conv is not None else None
         _lib.check(self.L.yy_lrn_gemm(_p(A), _ld(A), OP_K_CONV if conv is not None else OP_K, _p(B), _ld(B), _p(C), _ld(C), M, N, K,
                                       _p(bias), int(relu), int(accumulate), tile_n, split, _p(self.ws), self.ws.numel(), self.precision,
-                                      geom, self._stream()))
+                                      geom, _p(bn_sums), self._stream()))
 
     def transpose(self, inp, out):
         R, C = inp.shape
@@ -94,10 +95,10 @@ class CudaOps:
         R, C = X.shape
         _lib.check(self.L.yy_lrn_colsum(_p(X), _ld(X), R, C, _p(out), self._stream()))
 
-    def bn_forward(self, Y, gamma, beta, residual, out, relu, eps, momentum, ws, mean_invstd, running_mean, running_var):
+    def bn_forward(self, Y, gamma, beta, residual, out, relu, eps, momentum, ws, mean_invstd, running_mean, running_var, have_sums=False):
         P, C = Y.shape
         _lib.check(self.L.yy_lrn_bn_forward(_p(Y), _ld(Y), P, C, _p(gamma), _p(beta), _p(residual), _ld(residual) if residual is not None else 0,
-                                            _p(out), _ld(out), int(relu), eps, momentum, _p(ws), _p(mean_invstd),
+                                            _p(out), _ld(out), int(relu), eps, momentum, _p(ws), int(have_sums), _p(mean_invstd),
                                             _p(running_mean), _p(running_var), self._stream()))
 
     def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias):
@@ -305,9 +306,10 @@ class Learner:
 
     def _conv3_forward(self, x, wkey, bkey, bnpre, li, residual=None):
         ops, P = self.ops, self.p
-        ops.gemm(x, self.w(wkey), self.Y[li][:P], bias=self.w(bkey), conv=self._geom(x.shape[1]))
+        sums = self.bn_ws[2 * self._bn_slot[bnpre]]
+        ops.gemm(x, self.w(wkey), self.Y[li][:P], bias=self.w(bkey), conv=self._geom(x.shape[1]), bn_sums=sums)
         ops.bn_forward(self.Y[li][:P], self.w(bnpre + ".weight"), self.w(bnpre + ".bias"), residual, self.act[li][:P], True, self.bn_eps,
-                       self.bn_momentum, self.bn_ws[2 * self._bn_slot[bnpre]], self.mi[bnpre], self.running[bnpre][0], self.running[bnpre][1])
+                       self.bn_momentum, sums, self.mi[bnpre], self.running[bnpre][0], self.running[bnpre][1], have_sums=True)
 
     def _conv3_backward(self, dOut, x_in, wkey, bkey, bnpre, li, dRes, dPrev, accumulate):
         """dOut: gradient w.r.t. act[li].  Writes the layer's parameter gradients; dRes (optional) receives the skip share;
@@ -328,10 +330,11 @@ class Learner:
 
     def _head_forward(self, head, trunk):
         ops, P = self.ops, self.p
-        ops.gemm(trunk, self.w(f"{head}_conv.weight"), self.Yh[head][:P], bias=self.w(f"{head}_conv.bias"))
         pre = f"{head}_bn"
+        sums = self.bn_ws[2 * self._bn_slot[pre]]
+        ops.gemm(trunk, self.w(f"{head}_conv.weight"), self.Yh[head][:P], bias=self.w(f"{head}_conv.bias"), bn_sums=sums)
         ops.bn_forward(self.Yh[head][:P], self.w(pre + ".weight"), self.w(pre + ".bias"), None, self.acth[head][:P], True, self.bn_eps,
-                       self.bn_momentum, self.bn_ws[2 * self._bn_slot[pre]], self.mi[pre], self.running[pre][0], self.running[pre][1])
+                       self.bn_momentum, sums, self.mi[pre], self.running[pre][0], self.running[pre][1], have_sums=True)
         return self.acth[head][:P].view(self.b, self.A * HEAD_CH)
 
     def _kpad(self):
