@@ -262,7 +262,10 @@ int yy_augment_samples(int rows, int cols, const uint64_t *black_dev, const uint
  *          YY_OP_K_CONV   implicit im2col: A[p][t*cin + ci] = X[p + d(t)][ci], X = [positions][cin] (lda), zero outside
  *                         the board; t = kh*3 + kw of nn.Conv2d(kernel_size=3, padding=1); conv->flip mirrors the taps
  *                         (the gather of the backward-data pass)
- *   B is [N][K] row-major (ldb).
+ *   b_mode YY_OP_K        B is [N][K] row-major (ldb)
+ *          YY_OP_K_CONVT  implicit transposed im2col: B[t*cin + ci][p] = XT[ci][p + d(t)], XT = [cin][positions] (ldb) --
+ *                         the weight gradient of a 3x3 convolution, dW = dY^T * im2col(X), whose reduction index is the
+ *                         position (K = positions, at most 8192 per K slice)
  * precision: YY_GEMM_3XTF32 splits every operand into the 19 bits a TF32 multiplier reads and the remainder and runs
  * three MMAs per K-slice (lo*hi + hi*lo + hi*hi): fp32-level results, what the fp32 reference computes; YY_GEMM_TF32 is
  * the single-pass variant (torch's default for fp32 convolutions on a GPU).  accumulate != 0: the product is added to C
@@ -275,12 +278,13 @@ int yy_augment_samples(int rows, int cols, const uint64_t *black_dev, const uint
 #define YY_GEMM_3XTF32 1
 #define YY_OP_K 0
 #define YY_OP_K_CONV 1
+#define YY_OP_K_CONVT 2
 typedef struct {
   int32_t rows, cols; /* board */
   int32_t cin;        /* channels of the gathered activation tensor (multiple of 4) */
   int32_t flip;       /* mirror the taps                                            */
 } yy_conv_geom;
-int yy_lrn_gemm(const float *A, int lda, int a_mode, const float *B, int ldb, float *C, int ldc, int M, int N, int K,
+int yy_lrn_gemm(const float *A, int lda, int a_mode, const float *B, int ldb, int b_mode, float *C, int ldc, int M, int N, int K,
                 const float *bias, int relu, int accumulate, int tile_n, int split_k, float *ws, int64_t ws_floats,
                 int precision, const yy_conv_geom *conv, double *bn_sums, void *stream);
 /* Developer tool: while dbg_dev != NULL (>= 128 int64) CTA (0,0,0) of every yy_lrn_gemm launch records clock64 stamps:

@@ -167,6 +167,11 @@ def test_convolution_passes_match_their_definition(yy, rows, cols, cin, cout, bo
     dw_ref, dw = torch.zeros(cout, 9 * cin), torch.zeros(cout, 9 * cin).cuda()
     emu.gemm(dY.t().contiguous(), colT_ref, dw_ref); ops.gemm(dYT, colT, dw)
     close(dw, dw_ref, "weight gradient")
+    if (rows * cols) % 4 == 0:                      # the same from the transposed activation alone (implicit transposed im2col)
+        XT, dw2 = torch.zeros(cin, P).cuda(), torch.zeros(cout, 9 * cin).cuda()
+        ops.transpose(X.cuda(), XT)
+        ops.gemm(dYT, XT, dw2, conv_t=(rows, cols, cin, 0))
+        close(dw2, dw_ref, "weight gradient, implicit")
     # two layers' weights inside one flat buffer -> both transposed views in one launch
     flat = torch.cat([rn(12), W.flatten(), rn(8), (W * 2).flatten()])
     offs = torch.tensor([12, 12 + W.numel() + 8], dtype=torch.int64)

@@ -42,11 +42,11 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 constexpr int kGemmKStage = 32;                     // K-values per stage = 4 K-slices of 8
 constexpr int kPlaneA = 128 * 16 + 16;
 constexpr int kRegionA = 8 * kPlaneA;               // bytes of a stage's A tile
-enum { OP_K = YY_OP_K, OP_K_CONV = YY_OP_K_CONV };
+enum { OP_K = YY_OP_K, OP_K_CONV = YY_OP_K_CONV, OP_K_CONVT = YY_OP_K_CONVT };
 
 struct GemmArgs {
   const float* A; const float* B; float* C; const float* bias; float* ws;
-  int lda, ldb, ldc, M, N, K, tile_n, k_per_split, relu, accumulate, a_mode;
+  int lda, ldb, ldc, M, N, K, tile_n, k_per_split, relu, accumulate, a_mode, b_mode;
   int rows, cols, cin, flip;                        // convolution geometry of the implicit A operand (cin: gathered channels)
   long long* dbg;                                   // developer tool: clock64 stamps of CTA 0 (yy_lrn_gemm_debug_stamps)
 };
@@ -92,6 +92,13 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), ncols);
+  // OP_K_CONVT: per position of this CTA's K range, which neighbours of its cell are on the board (same 4 bits as below)
+  uint8_t* edge_s = smem + (size_t)S * stage_bytes;
+  if (g.b_mode == OP_K_CONVT)
+    for (int i = tid; i < k_end - k_begin; i += blockDim.x) {
+      const int cell = (k_begin + i) % (g.rows * g.cols), x = cell / g.cols, y = cell - x * g.cols;
+      edge_s[i] = (uint8_t)((x > 0 ? 1u : 0u) | (x < g.rows - 1 ? 2u : 0u) | (y > 0 ? 4u : 0u) | (y < g.cols - 1 ? 8u : 0u));
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -153,6 +160,22 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
     }
     const int npairs = g.tile_n >> 2;                         // (row group, half stage) pairs of B; this warp owns q = warp + 8j
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // OP_K_CONVT: B row n = tap*cin + ci is row ci of the transposed activation shifted by d(tap) positions
+    const bool convB = g.b_mode == OP_K_CONVT;
+    const float* bptr[4] = {g.B, g.B, g.B, g.B};
+    uint32_t bneed = 0, bok = 0;
+    if (convB) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = warp + 8 * j, n = n0 + 8 * (q >> 1) + r8;
+        if (q < npairs && n < g.N) {
+          const int tap = n / g.cin, ci = n - tap * g.cin, dx = tap / 3 - 1, dy = tap - (tap / 3) * 3 - 1;
+          bok |= 1u << j;
+          bneed |= ((dx < 0 ? 1u : 0u) | (dx > 0 ? 2u : 0u) | (dy < 0 ? 4u : 0u) | (dy > 0 ? 8u : 0u)) << (4 * j);
+          bptr[j] = g.B + (long long)ci * g.ldb + (dx * g.cols + dy);
+        }
+      }
+    }
     // global -> registers (read-only path), zeros past the edges / outside the board
     auto load_regs = [&](float4 (&ra)[4], float4 (&rb)[4], int kt) {
       const int kc = k_begin + kt * kGemmKStage;
@@ -174,11 +197,27 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
           ra[gi] = ok ? __ldg(reinterpret_cast<const float4*>(arow0 + (size_t)(8 * gi) * g.lda + aoff)) : zero4;
         }
       }
+      if (convB) {
+        const int k = kc + (c4 + 4 * (warp & 1)) * 4;         // q & 1 == warp & 1 for every q = warp + 8j
+        uint32_t e4 = 0;                                      // edge bits of the chunk's 4 positions
+        if (k < k_end) e4 = *reinterpret_cast<const uint32_t*>(edge_s + (k - k_begin));   // K is a multiple of 4: whole chunks
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int q = warp + 8 * j, gB = q >> 1, k = kc + (c4 + 4 * (q & 1)) * 4;
-        const bool ok = q < npairs && k < k_end && (n0 + 8 * gB + r8) < g.N;
-        rb[j] = ok ? __ldg(reinterpret_cast<const float4*>(brow0 + (size_t)(8 * gB) * g.ldb + k)) : zero4;
+        for (int j = 0; j < 4; ++j) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool ok = ((bok >> j) & 1u) && (k + e) < k_end && (((bneed >> (4 * j)) & ~(e4 >> (8 * e))) & 15u) == 0;
+            v[e] = ok ? __ldg(bptr[j] + k + e) : 0.f;
+          }
+          rb[j] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int q = warp + 8 * j, gB = q >> 1, k = kc + (c4 + 4 * (q & 1)) * 4;
+          const bool ok = q < npairs && k < k_end && (n0 + 8 * gB + r8) < g.N;
+          rb[j] = ok ? __ldg(reinterpret_cast<const float4*>(brow0 + (size_t)(8 * gB) * g.ldb + k)) : zero4;
+        }
       }
     };
     // registers -> the stage's core-matrix layout (hi / lo copies for 3xTF32), then publish the stage
@@ -657,7 +696,7 @@ using namespace yy;
 
 extern "C" {
 
-int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, int b_mode, float* C, int ldc, int M, int N, int K,
                 const float* bias, int relu, int accumulate, int tile_n, int split_k, float* ws, int64_t ws_floats, int precision,
                 const yy_conv_geom* conv, double* bn_sums, void* stream) {
   int rc = need_device(); if (rc) return rc;
@@ -665,10 +704,13 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
   if ((lda | ldb | ldc | N | K) & 3) return set_error(YY_ERR_INVALID, "gemm: lda, ldb, ldc, N and K must be multiples of 4 floats");
   if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C | (uintptr_t)ws) & 15) return set_error(YY_ERR_INVALID, "gemm: operands must be 16-byte aligned");
   if (a_mode != YY_OP_K && a_mode != YY_OP_K_CONV) return set_error(YY_ERR_INVALID, "gemm: bad a_mode");
-  if (a_mode == YY_OP_K_CONV) {
-    if (!conv || conv->rows < 1 || conv->cols < 1 || conv->cin < 4 || (conv->cin & 3))
-      return set_error(YY_ERR_INVALID, "gemm: the implicit convolution operand needs a geometry with cin a multiple of 4");
-    if (K != 9 * conv->cin || M % (conv->rows * conv->cols)) return set_error(YY_ERR_INVALID, "gemm: conv A needs K = 9*cin and whole boards");
+  if (b_mode != YY_OP_K && b_mode != YY_OP_K_CONVT) return set_error(YY_ERR_INVALID, "gemm: bad b_mode");
+  if (a_mode == YY_OP_K_CONV || b_mode == YY_OP_K_CONVT) {
+    if (!conv || conv->rows < 1 || conv->cols < 1 || conv->cin < 4 || (conv->cin & 3) || (a_mode == YY_OP_K_CONV && b_mode == YY_OP_K_CONVT))
+      return set_error(YY_ERR_INVALID, "gemm: an implicit convolution operand (one per call) needs a geometry with cin a multiple of 4");
+    if (a_mode == YY_OP_K_CONV && (K != 9 * conv->cin || M % (conv->rows * conv->cols))) return set_error(YY_ERR_INVALID, "gemm: conv A needs K = 9*cin and whole boards");
+    if (b_mode == YY_OP_K_CONVT && (N != 9 * conv->cin || K % (conv->rows * conv->cols) || ((conv->rows * conv->cols) & 3)))
+      return set_error(YY_ERR_INVALID, "gemm: conv B needs N = 9*cin and K = whole boards of a multiple of 4 cells");
   }
   if (precision != YY_GEMM_TF32 && precision != YY_GEMM_3XTF32) return set_error(YY_ERR_INVALID, "gemm: precision must be YY_GEMM_TF32 or YY_GEMM_3XTF32");
   if (tile_n < 16 || tile_n > 128 || tile_n % 16) return set_error(YY_ERR_INVALID, "gemm: tile_n in [16,128] step 16");
@@ -678,13 +720,15 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
   kps = (kps + kGemmKStage - 1) / kGemmKStage * kGemmKStage;
   const int zs = (K + kps - 1) / kps;
   if (zs > 1 && (!ws || ws_floats < (int64_t)zs * M * N)) return set_error(YY_ERR_INVALID, "gemm: split-K needs a workspace of split*M*N floats");
-  GemmArgs g{A, B, C, bias, ws, lda, ldb, ldc, M, N, K, tile_n, kps, relu, accumulate, a_mode,
+  if (b_mode == YY_OP_K_CONVT && kps > 8192) return set_error(YY_ERR_INVALID, "gemm: conv B supports at most 8192 positions per K slice (raise split_k)");
+  const int edge_bytes = b_mode == YY_OP_K_CONVT ? (kps + 15) / 16 * 16 : 0;
+  GemmArgs g{A, B, C, bias, ws, lda, ldb, ldc, M, N, K, tile_n, kps, relu, accumulate, a_mode, b_mode,
              conv ? conv->rows : 1, conv ? conv->cols : 1, conv ? conv->cin : 4, conv ? conv->flip : 0, g_gemm_dbg};
   dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + tile_n - 1) / tile_n), (unsigned)zs);
   const int half = kRegionA + 8 * (tile_n * 16 + 16);
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == YY_GEMM_3XTF32) {
-    const int smem = 3 * 2 * half;
+    const int smem = 3 * 2 * half + edge_bytes;
     static int max_set = 0;
     if (smem > max_set) {
       YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -692,7 +736,7 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, fl
     }
     gemm_tf32_kernel<3, true><<<grid, 288, smem, st>>>(g);
   } else {
-    const int smem = 4 * half;
+    const int smem = 4 * half + edge_bytes;
     static int max_set = 0;
     if (smem > max_set) {
       YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

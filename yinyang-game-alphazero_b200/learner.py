@@ -24,7 +24,7 @@ from . import _lib
 HEAD_CH = 32      # policy_conv / value_conv output channels (neural_network.py:58,63)
 VALUE_HID = 256   # value_fc1 width (:65)
 STEM_CIN = 8      # the 5 input planes padded to 8 channels (16-byte rows)
-OP_K, OP_K_CONV = 0, 1   # YY_OP_* A-operand modes of yy_lrn_gemm
+OP_K, OP_K_CONV, OP_K_CONVT = 0, 1, 2   # YY_OP_* operand modes of yy_lrn_gemm
 
 
 # --------------------------------------------------------------------------------------------- device ops
@@ -52,13 +52,15 @@ class CudaOps:
     def _stream():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None):
+    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None, conv_t=None):
         """C[M,N] = [C +] A @ B^T (+bias) (relu), B = [N,K].  conv = (rows, cols, cin, flip): A is the activation tensor
         [positions, cin] and the product runs over its implicit im2col (YY_OP_K_CONV).  bn_sums (float64 [>= 2N], zero): also
-        accumulate the column sums / sums of squares of C (the statistics of the batch norm that follows)."""
+        accumulate the column sums / sums of squares of C (the statistics of the batch norm that follows).
+        conv_t = (rows, cols, cin, 0): B is the TRANSPOSED activation tensor [cin, positions] and stands for its transposed
+        im2col [9*cin, positions] (YY_OP_K_CONVT; the weight gradient of a convolution)."""
         M, N = C.shape
         K = B.shape[1]
-        assert B.shape[0] == N and (conv is not None or A.shape == (M, K))
+        assert (B.shape[0] == N or conv_t is not None) and (conv is not None or A.shape == (M, K))
         tiles_m = (M + 127) // 128
         tile_n = min(128, (N + 15) // 16 * 16)
         ctas = tiles_m * ((N + tile_n - 1) // tile_n)
@@ -67,8 +69,12 @@ class CudaOps:
             split = max(1, min(self.sm_count // ctas, K // 256))
         if split > 1 and split * M * N > self.ws.numel():
             split = max(1, self.ws.numel() // (M * N))
-        geom = ctypes.byref(_lib.ConvGeom(*conv)) if conv is not None else None
-        _lib.check(self.L.yy_lrn_gemm(_p(A), _ld(A), OP_K_CONV if conv is not None else OP_K, _p(B), _ld(B), _p(C), _ld(C), M, N, K,
+        if conv_t is not None:
+            split = max(split, (K + 8191) // 8192)
+        cg = conv if conv is not None else conv_t
+        geom = ctypes.byref(_lib.ConvGeom(*cg)) if cg is not None else None
+        _lib.check(self.L.yy_lrn_gemm(_p(A), _ld(A), OP_K_CONV if conv is not None else OP_K, _p(B), _ld(B),
+                                      OP_K_CONVT if conv_t is not None else OP_K, _p(C), _ld(C), M, N, K,
                                       _p(bias), int(relu), int(accumulate), tile_n, split, _p(self.ws), self.ws.numel(), self.precision,
                                       geom, _p(bn_sums), self._stream()))
 
@@ -265,7 +271,7 @@ class Learner:
         self.dY = z(P, C)
         self.dacth, self.dYh = z(P, HEAD_CH), z(P, HEAD_CH)
         # transposed copies ([channels][positions]) for the weight-gradient GEMMs, whose reduction index is the position
-        self.dYT, self.colT, self.trunkT = z(max(C, HEAD_CH) * P), z(9 * C * P), z(C * P)
+        self.dYT, self.XT, self.trunkT = z(max(C, HEAD_CH) * P), z(C * P), z(C * P)
         self.Wt = z(C * HEAD_CH)
         self.Wt_all = z(max(1, 2 * self.blocks), C, 9 * C)           # backward-data views of the tower's conv weights
         self.w_offsets = torch.tensor([self.layout.offsets[f"res_blocks.{k}.conv{j}.weight"] for k in range(self.blocks) for j in (1, 2)],
@@ -320,10 +326,10 @@ class Learner:
         ops.bn_backward(dOut, self.act[li][:P], self.Y[li][:P], self.mi[bnpre], self.w(bnpre + ".weight"), self.bn_ws[2 * self._bn_slot[bnpre] + 1],
                         dY, dRes, self.g(bnpre + ".weight"), self.g(bnpre + ".bias"), self.g(bkey))
         # dW[co][t*cin+ci] = sum_p dY[p][co] * x_in[p + d(t)][ci]: K = positions, both operands from transposed copies
-        dYT, colT = self.dYT[:C * P].view(C, P), self.colT[:9 * cin * P].view(9 * cin, P)
+        dYT, XT = self.dYT[:C * P].view(C, P), self.XT[:cin * P].view(cin, P)
         ops.transpose(dY, dYT)
-        ops.im2col_t(x_in, colT, self.rows, self.cols)
-        ops.gemm(dYT, colT, self.g(wkey))
+        ops.transpose(x_in, XT)
+        ops.gemm(dYT, XT, self.g(wkey), conv_t=self._geom(cin))              # B = implicit transposed im2col of x_in
         if dPrev is not None:
             # dX[p][ci] = sum_{t,co} dY[p - d(t)][co] * W[co][t*cin+ci]: implicit (mirrored) im2col of dY times Wt
             ops.gemm(dY, self.Wt_all[li - 1], dPrev, accumulate=accumulate, conv=self._geom(C, flip=True))
