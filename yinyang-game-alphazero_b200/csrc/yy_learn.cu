@@ -244,6 +244,9 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&full_bar[s]));
     };
+    // (Tried: three rotating register sets = two stages of loads in flight: 168 registers, spills in the 3xTF32 variant and
+    // no gain -- the K-iteration takes ~3,000 cycles whatever the number of CTAs (32..288, tools/gemm_phases.py): it is
+    // bounded by the L1 request path of the 64 LDG.128 per stage, 8 cache lines each, not by bytes in flight or by L2.)
     float4 ra[4], rb[4], na[4], nb[4];
     if (KT > 0) load_regs(ra, rb, 0);
     for (int kt = 0; kt < KT; ++kt) {
