@@ -137,19 +137,19 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ producers
-    // Chunk ownership: lane = (row within an 8-row group) + 8 * (k-chunk within a half stage); one cp.async of a warp
-    // fills 4 whole 128-byte lines of the core-matrix layout and reads 64 contiguous bytes of 8 rows.  A thread owns 4
-    // chunks of A (4 row groups of one half stage) and tile_n/32 of B.
-    const int r8 = lane & 7, c4 = lane >> 3, wq = warp & 3, wh = warp >> 2;
-    const int nB = g.tile_n >> 4;
+    // Chunk ownership: lane = (k-chunk of the stage, 0..7) + 8 * (row within a 4-row group): one LDG.128 of a warp reads
+    // 128 contiguous bytes of 4 rows (4 cache lines; 64 bytes of 8 rows cost twice the L1 tag lookups) and its STS.128
+    // fills 64 bytes in each of the 8 chunk planes (conflict free: plane pitch = 16 mod 128).  Warp w owns A rows
+    // 16w..16w+15 (4 chunks per thread) and B rows 4(w + 8j) + r4.
+    const int c8 = lane & 7, r4 = lane >> 3, wq = warp & 3, wh = warp >> 2;
     const bool convA = g.a_mode == OP_K_CONV;
-    const float* arow0 = g.A + (size_t)(m0 + 32 * wq + r8) * g.lda;     // row group gi adds 8*gi rows
-    const float* brow0 = g.B + (size_t)(n0 + r8) * g.ldb;
+    const float* arow0 = g.A + (size_t)(m0 + 16 * warp + r4) * g.lda;     // row group gi adds 4*gi rows
+    const float* brow0 = g.B + (size_t)(n0 + 4 * warp + r4) * g.ldb;      // row group j adds 32*j rows
     // per owned A row (gi = 0..3): bit 4gi+0/1/2/3 = the neighbour above / below / left / right of its cell is on the board
     uint32_t edge = 0, rowok = 0;
 #pragma unroll
     for (int gi = 0; gi < 4; ++gi) {
-      const int p = m0 + 32 * wq + 8 * gi + r8;
+      const int p = m0 + 16 * warp + 4 * gi + r4;
       if (p < g.M) {
         rowok |= 1u << gi;
         if (convA) {
@@ -158,19 +158,18 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
         }
       }
     }
-    const int npairs = g.tile_n >> 2;                         // (row group, half stage) pairs of B; this warp owns q = warp + 8j
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // OP_K_CONVT: B row n = tap*cin + ci is row ci of the transposed activation shifted by d(tap) positions
     const bool convB = g.b_mode == OP_K_CONVT;
     const float* bptr[4] = {g.B, g.B, g.B, g.B};
-    uint32_t bneed = 0, bok = 0;
-    if (convB) {
+    uint32_t bneed = 0, bok = 0;                              // bok bit j: B row 4(w+8j)+r4 is inside the tile and inside N
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int q = warp + 8 * j, n = n0 + 8 * (q >> 1) + r8;
-        if (q < npairs && n < g.N) {
+    for (int j = 0; j < 4; ++j) {
+      const int row = 4 * (warp + 8 * j) + r4, n = n0 + row;
+      if (row < g.tile_n && n < g.N) {
+        bok |= 1u << j;
+        if (convB) {
           const int tap = n / g.cin, ci = n - tap * g.cin, dx = tap / 3 - 1, dy = tap - (tap / 3) * 3 - 1;
-          bok |= 1u << j;
           bneed |= ((dx < 0 ? 1u : 0u) | (dx > 0 ? 2u : 0u) | (dy < 0 ? 4u : 0u) | (dy > 0 ? 8u : 0u)) << (4 * j);
           bptr[j] = g.B + (long long)ci * g.ldb + (dx * g.cols + dy);
         }
@@ -178,10 +177,9 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
     }
     // global -> registers (read-only path), zeros past the edges / outside the board
     auto load_regs = [&](float4 (&ra)[4], float4 (&rb)[4], int kt) {
-      const int kc = k_begin + kt * kGemmKStage;
+      const int k = k_begin + kt * kGemmKStage + c8 * 4;      // this thread's k-chunk of every row it owns
+      const bool kok = k < k_end;
       {
-        const int k = kc + (c4 + 4 * wh) * 4;
-        const bool kok = k < k_end;
         long long aoff = k;                                   // element offset added to a row's base
         uint32_t need = 0;                                    // edge bits this tap needs
         if (convA) {
@@ -194,13 +192,12 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
           const bool ok = kok && ((rowok >> gi) & 1u) && ((need & ~(edge >> (4 * gi))) & 15u) == 0;
-          ra[gi] = ok ? __ldg(reinterpret_cast<const float4*>(arow0 + (size_t)(8 * gi) * g.lda + aoff)) : zero4;
+          ra[gi] = ok ? __ldg(reinterpret_cast<const float4*>(arow0 + (size_t)(4 * gi) * g.lda + aoff)) : zero4;
         }
       }
       if (convB) {
-        const int k = kc + (c4 + 4 * (warp & 1)) * 4;         // q & 1 == warp & 1 for every q = warp + 8j
         uint32_t e4 = 0;                                      // edge bits of the chunk's 4 positions
-        if (k < k_end) e4 = *reinterpret_cast<const uint32_t*>(edge_s + (k - k_begin));   // K is a multiple of 4: whole chunks
+        if (kok) e4 = *reinterpret_cast<const uint32_t*>(edge_s + (k - k_begin));   // K is a multiple of 4: whole chunks
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float v[4];
@@ -214,9 +211,8 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int q = warp + 8 * j, gB = q >> 1, k = kc + (c4 + 4 * (q & 1)) * 4;
-          const bool ok = q < npairs && k < k_end && (n0 + 8 * gB + r8) < g.N;
-          rb[j] = ok ? __ldg(reinterpret_cast<const float4*>(brow0 + (size_t)(8 * gB) * g.ldb + k)) : zero4;
+          const bool ok = kok && ((bok >> j) & 1u);
+          rb[j] = ok ? __ldg(reinterpret_cast<const float4*>(brow0 + (size_t)(32 * j) * g.ldb + k)) : zero4;
         }
       }
     };
@@ -233,14 +229,13 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
     };
     auto store_stage = [&](const float4 (&ra)[4], const float4 (&rb)[4], int s) {
       uint8_t* st = smem + (size_t)s * stage_bytes;
-      uint8_t* a = st + (c4 + 4 * wh) * planeA + (32 * wq + r8) * 16;
+      uint8_t* a = st + c8 * planeA + (16 * warp + r4) * 16;
 #pragma unroll
-      for (int gi = 0; gi < 4; ++gi) put(a + gi * 128, ra[gi]);
+      for (int gi = 0; gi < 4; ++gi) put(a + gi * 64, ra[gi]);
+      uint8_t* b = st + kRegionA + c8 * planeB + (4 * warp + r4) * 16;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int q = warp + 8 * j;
-        if (q < npairs) put(st + kRegionA + (c4 + 4 * (q & 1)) * planeB + (8 * (q >> 1) + r8) * 16, rb[j]);
-      }
+      for (int j = 0; j < 4; ++j)
+        if (4 * (warp + 8 * j) + r4 < g.tile_n) put(b + j * 512, rb[j]);
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&full_bar[s]));
     };
