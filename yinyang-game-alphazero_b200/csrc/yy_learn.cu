@@ -265,34 +265,37 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
     tc_fence_after();
     YY_STAMP(119);
 
-    // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane.  With split-K the tile goes to the workspace
-    // ([slice][M][N]) and gemm_reduce_kernel finishes it; otherwise bias / skip share / ReLU are applied here.
-    const int row = m0 + wq * 32 + lane;
-    const bool partial = gridDim.z > 1;
-    float* crow = partial ? g.ws + ((size_t)blockIdx.z * g.M + row) * g.N : g.C + (size_t)row * g.ldc;
-    for (int c = 16 * wh; c < g.tile_n; c += 32) {
-      uint32_t r[16];
-      if (KT > 0) {
+    // epilogue: warps w and w+4 read TMEM lanes 32(w&3).. (alternate 16-column chunks) and park the tile in shared memory
+    // (the stages are free now; row pitch tile_n+4 floats keeps both sides conflict free); then every warp writes whole
+    // rows, 512 contiguous bytes per instruction.  With split-K the tile goes to the workspace ([slice][M][N]) and
+    // gemm_reduce_kernel finishes it; otherwise bias / skip share / ReLU are applied here.
+    float* tile = reinterpret_cast<float*>(smem);
+    const int pitch = g.tile_n + 4;
+    if (KT > 0) {
+      for (int c = 16 * wh; c < g.tile_n; c += 32) {
+        uint32_t r[16];
         tc_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, r);
         tc_wait_ld();
-      } else {
+        float* dst = tile + (wq * 32 + lane) * pitch + c;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = 0u;
+        for (int j4 = 0; j4 < 16; j4 += 4)
+          *reinterpret_cast<float4*>(dst + j4) = make_float4(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]));
       }
-      if (row < g.M) {
-#pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          const int n = n0 + c + j4;
-          if (n < g.N) {                               // N is a multiple of 4
-            float4 v = make_float4(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]));
-            if (!partial) {
-              if (g.bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
-              if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(crow + n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-              if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            }
-            *reinterpret_cast<float4*>(crow + n) = v;
-          }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 producer / epilogue warps
+    const bool partial = gridDim.z > 1;
+    const int n4 = g.tile_n >> 2;                               // float4 columns of the tile
+    for (int idx = tid; idx < 128 * n4; idx += 256) {
+      const int rr = idx / n4, cc = (idx - rr * n4) * 4, row = m0 + rr, n = n0 + cc;
+      if (row < g.M && n < g.N) {                              // N is a multiple of 4
+        float4 v = KT > 0 ? *reinterpret_cast<const float4*>(tile + rr * pitch + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float* crow = partial ? g.ws + ((size_t)blockIdx.z * g.M + row) * g.N : g.C + (size_t)row * g.ldc;
+        if (!partial) {
+          if (g.bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
+          if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(crow + n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+          if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         }
+        *reinterpret_cast<float4*>(crow + n) = v;
       }
     }
     YY_STAMP(3);
