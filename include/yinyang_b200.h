@@ -270,8 +270,9 @@ int yy_augment_samples(int rows, int cols, const uint64_t *black_dev, const uint
  * three MMAs per K-slice (lo*hi + hi*lo + hi*hi): fp32-level results, what the fp32 reference computes; YY_GEMM_TF32 is
  * the single-pass variant (torch's default for fp32 convolutions on a GPU).  accumulate != 0: the product is added to C
  * (a skip connection's share of a gradient).  tile_n: output columns per CTA (16..128, multiple of 16); split_k >= 1
- * slices K over gridDim.z: partial tiles go to ws (>= split*M*N floats) and a reducer adds them in slice order, so
- * results are bit-reproducible.  bn_sums (optional, float64 [2N], zero on entry, N dividing 128): receives the per-column
+ * slices K over gridDim.z: the partial tiles of up to 8 consecutive slices are summed on chip by a thread-block cluster
+ * (distributed shared memory, rank order); with more slices the clusters' sums go to ws (>= (split/cluster)*M*N floats)
+ * and a reducer adds them in order, so results are bit-reproducible.  bn_sums (optional, float64 [2N], zero on entry, N dividing 128): receives the per-column
  * sum / sum of squares of the finished C, i.e. the statistics of the batch norm that follows (yy_lrn_bn_forward with
  * have_sums = 1 then skips its own pass).  lda/ldb/ldc/N/K multiples of 4, pointers 16-byte aligned. */
 #define YY_GEMM_TF32 0

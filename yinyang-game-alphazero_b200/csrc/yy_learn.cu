@@ -15,6 +15,7 @@
 // microsecond-sized kernels in one CUDA graph (learner.py).
 #include "yy_common.cuh"
 #include "yy_ptx.cuh"
+#include <stdlib.h>
 
 namespace yy {
 using namespace ptx;
@@ -48,6 +49,8 @@ struct GemmArgs {
   const float* A; const float* B; float* C; const float* bias; float* ws;
   int lda, ldb, ldc, M, N, K, tile_n, k_per_split, relu, accumulate, a_mode, b_mode;
   int rows, cols, cin, flip;                        // convolution geometry of the implicit A operand (cin: gathered channels)
+  int cz;                                           // CTAs per cluster along z: the K slices whose partial tiles are summed on chip
+  double* bn_sums;                                  // fused batch-norm statistics when the cluster produces the final C
   long long* dbg;                                   // developer tool: clock64 stamps of CTA 0 (yy_lrn_gemm_debug_stamps)
 };
 
@@ -283,22 +286,79 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 producer / epilogue warps
-    const bool partial = gridDim.z > 1;
     const int n4 = g.tile_n >> 2;                               // float4 columns of the tile
-    for (int idx = tid; idx < 128 * n4; idx += 256) {
-      const int rr = idx / n4, cc = (idx - rr * n4) * 4, row = m0 + rr, n = n0 + cc;
-      if (row < g.M && n < g.N) {                              // N is a multiple of 4
-        float4 v = KT > 0 ? *reinterpret_cast<const float4*>(tile + rr * pitch + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float* crow = partial ? g.ws + ((size_t)blockIdx.z * g.M + row) * g.N : g.C + (size_t)row * g.ldc;
-        if (!partial) {
-          if (g.bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
-          if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(crow + n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-          if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (g.cz == 1) {
+      const bool partial = gridDim.z > 1;
+      for (int idx = tid; idx < 128 * n4; idx += 256) {
+        const int rr = idx / n4, cc = (idx - rr * n4) * 4, row = m0 + rr, n = n0 + cc;
+        if (row < g.M && n < g.N) {                            // N is a multiple of 4
+          float4 v = KT > 0 ? *reinterpret_cast<const float4*>(tile + rr * pitch + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float* crow = partial ? g.ws + ((size_t)blockIdx.z * g.M + row) * g.N : g.C + (size_t)row * g.ldc;
+          if (!partial) {
+            if (g.bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
+            if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(crow + n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          }
+          *reinterpret_cast<float4*>(crow + n) = v;
         }
-        *reinterpret_cast<float4*>(crow + n) = v;
       }
     }
     YY_STAMP(3);
+  }
+  if (g.cz > 1) {
+    // Split-K inside a thread-block cluster: the cz CTAs of a cluster hold the partial tiles of cz consecutive K slices in
+    // their shared memory; CTA r finishes rows [r*128/cz, (r+1)*128/cz) of the tile by reading all cz partials through
+    // distributed shared memory in rank order (deterministic), so no workspace round trip and no reducer launch.  With
+    // more slices than a cluster holds (gridDim.z > cz) the cluster's sum goes to the workspace as ONE slice.
+    cluster_sync_all();
+    if (warp < 8) {
+      const float* tile = reinterpret_cast<const float*>(smem);
+      const uint32_t tile_s = smem_u32(smem);
+      const int pitch = g.tile_n + 4, n4 = g.tile_n >> 2, rows_per = 128 / g.cz;
+      const uint32_t rank = cluster_ctarank();
+      const int groups = gridDim.z / g.cz, grp = blockIdx.z / g.cz;
+      const bool partial = groups > 1;
+      __shared__ float red[2][256][4];
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int idx = tid; idx < rows_per * n4; idx += 256) {
+        const int rr = (int)rank * rows_per + idx / n4, cc = (idx % n4) * 4, row = m0 + rr, n = n0 + cc;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t off = (uint32_t)((rr * pitch + cc) * 4);
+        for (int j = 0; j < g.cz; ++j) {
+          float4 pv;
+          const uint32_t addr = mapa_u32(tile_s + off, (uint32_t)j);
+          asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pv.x), "=f"(pv.y), "=f"(pv.z), "=f"(pv.w) : "r"(addr) : "memory");
+          v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+        }
+        if (row < g.M && n < g.N) {
+          float* crow = partial ? g.ws + ((size_t)grp * g.M + row) * g.N : g.C + (size_t)row * g.ldc;
+          if (!partial) {
+            if (g.bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
+            if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(crow + n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+            s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+          }
+          *reinterpret_cast<float4*>(crow + n) = v;
+        }
+      }
+      (void)tile;
+      if (g.bn_sums && !partial) {                             // host guarantees 256 % n4 == 0: a thread keeps one column group
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { red[0][tid][j] = s1[j]; red[1][tid][j] = s2[j]; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid < n4) {
+          for (int l = 1; l < 256 / n4; ++l)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s1[j] += red[0][l * n4 + tid][j]; s2[j] += red[1][l * n4 + tid][j]; }
+          const int n = n0 + tid * 4;
+          if (n < g.N)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { atomicAdd(&g.bn_sums[n + j], (double)s1[j]); atomicAdd(&g.bn_sums[g.N + n + j], (double)s2[j]); }
+        }
+      }
+    }
+    cluster_sync_all();                                        // nobody leaves while its tile is still being read
   }
   tc_fence_before();
   __syncthreads();
@@ -720,42 +780,71 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
   int kps = (K + split_k - 1) / split_k;
   kps = (kps + kGemmKStage - 1) / kGemmKStage * kGemmKStage;
   const int zs = (K + kps - 1) / kps;
-  if (zs > 1 && (!ws || ws_floats < (int64_t)zs * M * N)) return set_error(YY_ERR_INVALID, "gemm: split-K needs a workspace of split*M*N floats");
   if (b_mode == YY_OP_K_CONVT && kps > 8192) return set_error(YY_ERR_INVALID, "gemm: conv B supports at most 8192 positions per K slice (raise split_k)");
   const int edge_bytes = b_mode == YY_OP_K_CONVT ? (kps + 15) / 16 * 16 : 0;
-  GemmArgs g{A, B, C, bias, ws, lda, ldb, ldc, M, N, K, tile_n, kps, relu, accumulate, a_mode, b_mode,
-             conv ? conv->rows : 1, conv ? conv->cols : 1, conv ? conv->cin : 4, conv ? conv->flip : 0, g_gemm_dbg};
-  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + tile_n - 1) / tile_n), (unsigned)zs);
+  // K slices are summed on chip inside clusters of cz = 8, 4 or 2 CTAs (distributed shared memory) -- the largest size
+  // whose clusters are all co-resident (one wave; a cluster needs its SMs in one GPC); what is left (groups = zs / cz > 1
+  // slices) goes through the workspace and the ordered reducer.
   const int half = kRegionA + 8 * (tile_n * 16 + 16);
+  const int smem_bytes = (precision == YY_GEMM_3XTF32 ? 3 * 2 * half : 4 * half) + edge_bytes;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == YY_GEMM_3XTF32) {
-    const int smem = 3 * 2 * half + edge_bytes;
-    static int max_set = 0;
-    if (smem > max_set) {
-      YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      max_set = smem;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((M + 127) / 128), (unsigned)((N + tile_n - 1) / tile_n), (unsigned)zs);
+  cfg.blockDim = dim3(288); cfg.stream = st; cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  {
+    static int max_set[2] = {0, 0};
+    const int v = precision == YY_GEMM_3XTF32 ? 1 : 0;
+    if (smem_bytes > max_set[v]) {
+      if (v) YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      else YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      max_set[v] = smem_bytes;
     }
-    gemm_tf32_kernel<3, true><<<grid, 288, smem, st>>>(g);
-  } else {
-    const int smem = 4 * half + edge_bytes;
-    static int max_set = 0;
-    if (smem > max_set) {
-      YY_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      max_set = smem;
-    }
-    gemm_tf32_kernel<4, false><<<grid, 288, smem, st>>>(g);
   }
+  int cz = 1;
+  if (zs > 1 && tile_n % 4 == 0 && 256 % (tile_n / 4) == 0) {
+    static int active[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // max co-resident clusters of 1 / 2 / 4 / 8 CTAs (largest tile), per precision
+    const int v = precision == YY_GEMM_3XTF32 ? 1 : 0;
+    const long long ctas = (long long)cfg.gridDim.x * cfg.gridDim.y * zs;
+    for (int c = 8, i = 3; c >= 2; c >>= 1, --i) {
+      if (zs % c) continue;
+      if (!active[v][i]) {
+        cudaLaunchConfig_t q = cfg;
+        cudaLaunchAttribute qa[1] = {attr[0]};
+        qa[0].val.clusterDim.z = (unsigned)c; q.attrs = qa;
+        q.dynamicSmemBytes = (size_t)smem_bytes;               // queried once per size class with the first caller's tile
+        q.gridDim = dim3(1, 1, (unsigned)c);
+        int n = 0;
+        cudaError_t e = v ? cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<3, true>, &q) : cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<4, false>, &q);
+        if (e != cudaSuccess) { cudaGetLastError(); n = -1; }
+        active[v][i] = n > 0 ? n : -1;
+        if (getenv("YY_GEMM_DEBUG")) fprintf(stderr, "[yy_lrn_gemm] max co-resident clusters of %d CTAs: %d\n", c, n);
+      }
+      if (active[v][i] > 0 && ctas / c <= active[v][i]) { cz = c; break; }
+    }
+  }
+  attr[0].val.clusterDim.z = (unsigned)cz;
+  const int groups = zs / cz;
+  if (groups > 1 && (!ws || ws_floats < (int64_t)groups * M * N)) return set_error(YY_ERR_INVALID, "gemm: split-K beyond one cluster needs a workspace of (split/cluster)*M*N floats");
+  const bool fuse_stats = bn_sums && cz > 1 && groups == 1 && N <= tile_n;
+  GemmArgs g{A, B, C, bias, ws, lda, ldb, ldc, M, N, K, tile_n, kps, relu, accumulate, a_mode, b_mode,
+             conv ? conv->rows : 1, conv ? conv->cols : 1, conv ? conv->cin : 4, conv ? conv->flip : 0, cz, fuse_stats ? bn_sums : nullptr, g_gemm_dbg};
+  if (precision == YY_GEMM_3XTF32) YY_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<3, true>, g));
+  else YY_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<4, false>, g));
   YY_LAUNCH_CHECK();
-  if (zs > 1) {
+  if (groups > 1) {
     if (256 % (N / 4) == 0) {
       const int rows_per_block = 4 * (256 / (N / 4));
-      gemm_reduce_kernel<<<(unsigned)((M + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(ws, zs, C, ldc, M, N / 4, bias, relu, accumulate, bn_sums);
+      gemm_reduce_kernel<<<(unsigned)((M + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(ws, groups, C, ldc, M, N / 4, bias, relu, accumulate, bn_sums);
     } else {
       const long long total = (long long)M * (N / 4);
-      gemm_reduce_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, zs, C, ldc, M, N / 4, bias, relu, accumulate);
+      gemm_reduce_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, groups, C, ldc, M, N / 4, bias, relu, accumulate);
     }
     YY_LAUNCH_CHECK();
-  } else if (bn_sums) {
+  } else if (bn_sums && !fuse_stats) {
     bn_reduce_kernel<false><<<(M + 31) / 32, 256, 0, st>>>(C, ldc, nullptr, 0, nullptr, 0, nullptr, M, N, bn_sums);
     YY_LAUNCH_CHECK();
   }
