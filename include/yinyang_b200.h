@@ -292,8 +292,9 @@ int yy_lrn_gemm(const float *A, int lda, int a_mode, const float *B, int ldb, in
  * [0] start, [1] after setup, [4+6k .. 8+6k] producer phases of K-iteration k (start, slot free, copies issued, copies of
  * iteration k-1 landed, iteration k-1 split + published), [2] loop end, [119] accumulator complete, [3] epilogue end. */
 int yy_lrn_gemm_debug_stamps(long long *dbg_dev);
-/* out[c][r] = in[r][c] */
-int yy_lrn_transpose(const float *in, int ldi, float *out, int ldo, int R, int C, void *stream);
+/* out[c][r] = in[r][c] for `batch` matrices `in_stride` / `out_stride` floats apart (batch = 1: strides ignored). */
+int yy_lrn_transpose(const float *in, int ldi, float *out, int ldo, int R, int C, int batch, int64_t in_stride,
+                     int64_t out_stride, void *stream);
 /* colT[t*C + c][p] = X[p + d(t)][c], zero outside the board: the transposed im2col the weight gradient of a 3x3
  * convolution reads (dW = dY^T * colT^T; the reduction index is the position). */
 int yy_lrn_im2col_t(const float *X, int ldx, float *colT, int ldo, int64_t positions, int rows, int cols, int C,
@@ -318,10 +319,12 @@ int yy_lrn_bn_forward(const float *Y, int ld, int P, int C, const float *gamma, 
 /* Backward of the above (and of the ReLU after it when Out != NULL: dZ = dOut*[Out > 0]):
  * dY = gamma*invstd*(dZ - mean(dZ) - xhat*mean(dZ*xhat)); dRes (optional) = dZ; dgamma = sum dZ*xhat; dbeta = sum dZ;
  * dbias (optional, zero on entry) += column sums of dY = the bias gradient of the convolution feeding this batch norm.
+ * dYT (optional): also the transposed copy dYT[c][p] = dY[p][c] (ldt) the weight-gradient GEMM reads.
  * sums_ws: float64[2C], zero on entry. */
 int yy_lrn_bn_backward(const float *dOut, int ldd, const float *Out, int ldo, const float *Y, int ldy, int P, int C,
                        const float *mean_invstd, const float *gamma, double *sums_ws, float *dY, int lddy,
-                       float *dRes, int lddr, float *dgamma, float *dbeta, float *dbias, void *stream);
+                       float *dRes, int lddr, float *dgamma, float *dbeta, float *dbias, float *dYT, int ldt,
+                       void *stream);
 /* Both losses and their gradients at the heads (trainer.py:131-133; value head tail neural_network.py:119-121):
  * losses[0] = CrossEntropyLoss(logits, pi) with probability targets, losses[1] = MSELoss(tanh(relu(h).w2 + b2), z),
  * h = value_fc1's output before its ReLU; dlogits, dh (through that ReLU), dpre[B], v_out[B], dw2[H], db2[1]. */

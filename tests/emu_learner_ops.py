@@ -36,7 +36,7 @@ class TorchEmuOps:
             bn_sums[:N] += C.double().sum(0); bn_sums[N:2 * N] += (C.double() ** 2).sum(0)
 
     def transpose(self, inp, out):
-        out.copy_(inp.t())
+        out.copy_(inp.transpose(-1, -2))
 
     def im2col_t(self, X, colT, rows, cols):
         colT.copy_(self._im2col(X, rows, cols, False).t())
@@ -71,7 +71,7 @@ class TorchEmuOps:
             o = o + residual
         out.copy_(o.clamp_min(0) if relu else o)
 
-    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias=None):
+    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias=None, dYT=None):
         P, C = Y.shape
         dz = dOut * (Out > 0) if Out is not None else dOut.clone()
         xhat = (Y - mean_invstd[:C]) * mean_invstd[C:]
@@ -82,6 +82,8 @@ class TorchEmuOps:
             dRes.copy_(dz)
         if dbias is not None:
             dbias.add_(dY.double().sum(0).float())
+        if dYT is not None:
+            dYT.copy_(dY.t())
 
     def heads_loss(self, logits, pi, h, w2, b2, z, dlogits, dh, dpre, v, dw2, db2, losses):
         B = logits.shape[0]

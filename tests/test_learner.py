@@ -237,9 +237,13 @@ def test_kernels_match_their_emulation(yy):
             for want_res in (False, True):
                 dy_ref, dr_ref, dg_ref, db_ref, dbi_ref = torch.zeros(P, C), torch.zeros(P, C), torch.zeros(C), torch.zeros(C), torch.zeros(C)
                 dy, dr, dg, db, dbi = (t.clone().cuda() for t in (dy_ref, dr_ref, dg_ref, db_ref, dbi_ref))
+                dyt = torch.zeros(C, P).cuda()
                 emu.bn_backward(dOut, out_ref if relu else None, Y, mi_ref, gamma, None, dy_ref, dr_ref if want_res else None, dg_ref, db_ref, dbi_ref)
-                ops.bn_backward(cu(dOut), out if relu else None, cu(Y), mi, cu(gamma), ws.zero_(), dy, dr if want_res else None, dg, db, dbi)
+                ops.bn_backward(cu(dOut), out if relu else None, cu(Y), mi, cu(gamma), ws.zero_(), dy, dr if want_res else None, dg, db, dbi,
+                                dYT=dyt if want_res else None)
                 assert torch.allclose(dy.cpu(), dy_ref, rtol=1e-4, atol=1e-5)
+                if want_res:
+                    assert torch.equal(dyt.t(), dy)                 # the fused transposed copy
                 assert torch.allclose(dbi.cpu(), dy_ref.double().sum(0).float(), atol=1e-4 * dy_ref.abs().sum(0).max().item())
                 assert torch.allclose(dg.cpu(), dg_ref, rtol=1e-4, atol=1e-4) and torch.allclose(db.cpu(), db_ref, rtol=1e-4, atol=1e-4)
                 if want_res:

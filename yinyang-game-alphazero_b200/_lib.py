@@ -129,13 +129,13 @@ SIGNATURES = {
     "yy_augment_samples": (_I, [_I, _I, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "yy_lrn_gemm": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I64, _I, _P, _P, _P]),
     "yy_lrn_gemm_debug_stamps": (_I, [_P]),
-    "yy_lrn_transpose": (_I, [_P, _I, _P, _I, _I, _I, _P]),
+    "yy_lrn_transpose": (_I, [_P, _I, _P, _I, _I, _I, _I, _I64, _I64, _P]),
     "yy_lrn_im2col_t": (_I, [_P, _I, _P, _I, _I64, _I, _I, _I, _P]),
     "yy_lrn_conv_weight_t": (_I, [_P, _P, _I, _P, _I, _I, _P]),
     "yy_lrn_planes_nhwc": (_I, [_P, _P, _I64, _I, _P]),
     "yy_lrn_colsum": (_I, [_P, _I, _I, _I, _P, _P]),
     "yy_lrn_bn_forward": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _F, _F, _P, _I, _P, _P, _P, _P]),
-    "yy_lrn_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
+    "yy_lrn_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P]),
     "yy_lrn_heads_loss": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
     "yy_lrn_adam": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _P, _P]),
     "yy_probe_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),

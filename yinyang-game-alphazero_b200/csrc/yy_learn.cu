@@ -432,9 +432,11 @@ __global__ void __launch_bounds__(256) gemm_reduce_flat_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------ layout / reduction kernels
-// out[c][r] = in[r][c]
-__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, int R, int C) {
+// out[c][r] = in[r][c], for blockIdx.z = 0..batch-1 matrices at fixed strides (all layer inputs of the tower in one launch)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, int R, int C,
+                                                       long long in_stride, long long out_stride) {
   __shared__ float tile[32][33];
+  in += (size_t)blockIdx.z * in_stride; out += (size_t)blockIdx.z * out_stride;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int j = ty; j < 32; j += 8) {
@@ -615,8 +617,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                           const float* __restrict__ Y, int ldy, const float* __restrict__ mean_invstd,
                                                           const float* __restrict__ gamma, const double* __restrict__ sums, long long P, int C4,
                                                           float* __restrict__ dY, int lddy, float* __restrict__ dRes, int lddr,
-                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                          float* __restrict__ dYT, int ldt) {
   __shared__ float red[256][4];
+  __shared__ float tile[4608];                                 // the block's rows x (C+1): 32 x 129, 128 x 33 or 512 x 9
   const int C = C4 * 4;
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = (float)sums[c]; dbeta[c] = (float)sums[C + c]; }
@@ -649,7 +653,19 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
       }
       *reinterpret_cast<float4*>(dY + (size_t)p * lddy + c) = *reinterpret_cast<float4*>(r);
       if (dRes) *reinterpret_cast<float4*>(dRes + (size_t)p * lddr + c) = *reinterpret_cast<float4*>(dz);
+      if (dYT) {
+        float* t = tile + (sl * (256 / C4) + threadIdx.x / C4) * (C + 1) + c;
+        t[0] = r[0]; t[1] = r[1]; t[2] = r[2]; t[3] = r[3];
+      }
     }
+  }
+  if (dYT) {                                                   // dYT[c][p] = dY[p][c]: 128 contiguous bytes per warp store
+    __syncthreads();
+    const int rb = 4 * (256 / C4);
+    const long long p0 = (long long)blockIdx.x * rb;
+    for (int cc = threadIdx.x >> 5; cc < C; cc += 8)
+      for (int i = threadIdx.x & 31; i < rb; i += 32)
+        if (p0 + i < P) dYT[(size_t)cc * ldt + p0 + i] = tile[i * (C + 1) + cc];
   }
   if (dbias) {
 #pragma unroll
@@ -853,11 +869,11 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
 
 int yy_lrn_gemm_debug_stamps(long long* dbg_dev) { g_gemm_dbg = dbg_dev; return YY_OK; }
 
-int yy_lrn_transpose(const float* in, int ldi, float* out, int ldo, int R, int C, void* stream) {
+int yy_lrn_transpose(const float* in, int ldi, float* out, int ldo, int R, int C, int batch, int64_t in_stride, int64_t out_stride, void* stream) {
   int rc = need_device(); if (rc) return rc;
-  if (R <= 0 || C <= 0) return YY_OK;
-  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32));
-  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ldi, out, ldo, R, C);
+  if (R <= 0 || C <= 0 || batch <= 0) return YY_OK;
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)batch);
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ldi, out, ldo, R, C, in_stride, out_stride);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -922,7 +938,7 @@ int yy_lrn_bn_forward(const float* Y, int ld, int P, int C, const float* gamma, 
 
 int yy_lrn_bn_backward(const float* dOut, int ldd, const float* Out, int ldo, const float* Y, int ldy, int P, int C,
                        const float* mean_invstd, const float* gamma, double* sums_ws, float* dY, int lddy, float* dRes, int lddr,
-                       float* dgamma, float* dbeta, float* dbias, void* stream) {
+                       float* dgamma, float* dbeta, float* dbias, float* dYT, int ldt, void* stream) {
   int rc = need_device(); if (rc) return rc;
   if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
   cudaStream_t st = (cudaStream_t)stream;
@@ -930,7 +946,7 @@ int yy_lrn_bn_backward(const float* dOut, int ldd, const float* Out, int ldo, co
   YY_LAUNCH_CHECK();
   const long long total = (long long)P * (C / 4);
   bn_bwd_apply_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(dOut, ldd, Out, ldo, Y, ldy, mean_invstd, gamma, sums_ws, P, C / 4,
-                                                                      dY, lddy, dRes, lddr, dgamma, dbeta, dbias);
+                                                                      dY, lddy, dRes, lddr, dgamma, dbeta, dbias, dYT, ldt);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }

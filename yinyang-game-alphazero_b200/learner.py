@@ -79,9 +79,15 @@ class CudaOps:
                                       geom, _p(bn_sums), self._stream()))
 
     def transpose(self, inp, out):
+        """out = inp^T; 3-D tensors [batch, R, C] -> [batch, C, R] are transposed matrix by matrix in one launch."""
+        if inp.dim() == 3:
+            n, R, C = inp.shape
+            assert tuple(out.shape) == (n, C, R) and inp.stride(2) == 1 and out.stride(2) == 1
+            _lib.check(self.L.yy_lrn_transpose(_p(inp), inp.stride(1), _p(out), out.stride(1), R, C, n, inp.stride(0), out.stride(0), self._stream()))
+            return
         R, C = inp.shape
         assert tuple(out.shape) == (C, R)
-        _lib.check(self.L.yy_lrn_transpose(_p(inp), _ld(inp), _p(out), _ld(out), R, C, self._stream()))
+        _lib.check(self.L.yy_lrn_transpose(_p(inp), _ld(inp), _p(out), _ld(out), R, C, 1, 0, 0, self._stream()))
 
     def im2col_t(self, X, colT, rows, cols):
         P, C = X.shape
@@ -107,11 +113,12 @@ class CudaOps:
                                             _p(out), _ld(out), int(relu), eps, momentum, _p(ws), int(have_sums), _p(mean_invstd),
                                             _p(running_mean), _p(running_var), self._stream()))
 
-    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias):
+    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias, dYT=None):
         P, C = Y.shape
         _lib.check(self.L.yy_lrn_bn_backward(_p(dOut), _ld(dOut), _p(Out), _ld(Out) if Out is not None else 0, _p(Y), _ld(Y), P, C,
                                              _p(mean_invstd), _p(gamma), _p(ws), _p(dY), _ld(dY), _p(dRes),
-                                             _ld(dRes) if dRes is not None else 0, _p(dgamma), _p(dbeta), _p(dbias), self._stream()))
+                                             _ld(dRes) if dRes is not None else 0, _p(dgamma), _p(dbeta), _p(dbias), _p(dYT),
+                                             _ld(dYT) if dYT is not None else 0, self._stream()))
 
     def heads_loss(self, logits, pi, h, w2, b2, z, dlogits, dh, dpre, v, dw2, db2, losses):
         B, A = logits.shape
@@ -258,7 +265,8 @@ class Learner:
         self.planes_in, self.pi_in, self.z_in = z(B, 5, self.rows, self.cols), z(B, A), z(B)
         self.X0 = z(P, STEM_CIN)
         self.Y = [z(P, C) for _ in range(n_conv)]            # convolution outputs (batch-norm inputs), kept for backward
-        self.act = [z(P, C) for _ in range(n_conv)]          # layer outputs
+        self.act_all = z(n_conv, P, C)                       # layer outputs (one tensor: their transposes are one launch)
+        self.act = [self.act_all[i] for i in range(n_conv)]
         self.mi = {pre: z(2 * (HEAD_CH if pre in ("policy_bn", "value_bn") else C)) for pre in self._bn}
         self.Yh = {h: z(P, HEAD_CH) for h in ("policy", "value")}
         self.acth = {h: z(P, HEAD_CH) for h in ("policy", "value")}
@@ -271,7 +279,7 @@ class Learner:
         self.dY = z(P, C)
         self.dacth, self.dYh = z(P, HEAD_CH), z(P, HEAD_CH)
         # transposed copies ([channels][positions]) for the weight-gradient GEMMs, whose reduction index is the position
-        self.dYT, self.XT, self.trunkT = z(max(C, HEAD_CH) * P), z(C * P), z(C * P)
+        self.dYT, self.XT, self.XT_all = z(max(C, HEAD_CH) * P), z(C * P), z(n_conv, C, P)
         self.Wt = z(C * HEAD_CH)
         self.Wt_all = z(max(1, 2 * self.blocks), C, 9 * C)           # backward-data views of the tower's conv weights
         self.w_offsets = torch.tensor([self.layout.offsets[f"res_blocks.{k}.conv{j}.weight"] for k in range(self.blocks) for j in (1, 2)],
@@ -323,12 +331,15 @@ class Learner:
         ops, P, C = self.ops, self.p, self.C
         cin = x_in.shape[1]
         dY = self.dY[:P]
+        dYT = self.dYT[:C * P].view(C, P)
         ops.bn_backward(dOut, self.act[li][:P], self.Y[li][:P], self.mi[bnpre], self.w(bnpre + ".weight"), self.bn_ws[2 * self._bn_slot[bnpre] + 1],
-                        dY, dRes, self.g(bnpre + ".weight"), self.g(bnpre + ".bias"), self.g(bkey))
+                        dY, dRes, self.g(bnpre + ".weight"), self.g(bnpre + ".bias"), self.g(bkey), dYT=dYT)
         # dW[co][t*cin+ci] = sum_p dY[p][co] * x_in[p + d(t)][ci]: K = positions, both operands from transposed copies
-        dYT, XT = self.dYT[:C * P].view(C, P), self.XT[:cin * P].view(cin, P)
-        ops.transpose(dY, dYT)
-        ops.transpose(x_in, XT)
+        if li == 0:
+            XT = self.XT[:cin * P].view(cin, P)
+            ops.transpose(x_in, XT)
+        else:
+            XT = self._xt_all[li - 1]                                        # transposed in one launch with all layer inputs
         ops.gemm(dYT, XT, self.g(wkey), conv_t=self._geom(cin))              # B = implicit transposed im2col of x_in
         if dPrev is not None:
             # dX[p][ci] = sum_{t,co} dY[p - d(t)][co] * W[co][t*cin+ci]: implicit (mirrored) im2col of dY times Wt
@@ -369,11 +380,11 @@ class Learner:
         ops, P, C = self.ops, self.p, self.C
         pre = f"{head}_bn"
         dYh = self.dYh[:P]
-        ops.bn_backward(dfeat.view(P, HEAD_CH), self.acth[head][:P], self.Yh[head][:P], self.mi[pre], self.w(pre + ".weight"),
-                        self.bn_ws[2 * self._bn_slot[pre] + 1], dYh, None, self.g(pre + ".weight"), self.g(pre + ".bias"), self.g(f"{head}_conv.bias"))
         dYhT = self.dYT[:HEAD_CH * P].view(HEAD_CH, P)
-        ops.transpose(dYh, dYhT)
-        ops.gemm(dYhT, self.trunkT[:C * P].view(C, P), self.g(f"{head}_conv.weight"))
+        ops.bn_backward(dfeat.view(P, HEAD_CH), self.acth[head][:P], self.Yh[head][:P], self.mi[pre], self.w(pre + ".weight"),
+                        self.bn_ws[2 * self._bn_slot[pre] + 1], dYh, None, self.g(pre + ".weight"), self.g(pre + ".bias"), self.g(f"{head}_conv.bias"),
+                        dYT=dYhT)
+        ops.gemm(dYhT, self._xt_all[2 * self.blocks], self.g(f"{head}_conv.weight"))
         WT = self.Wt[:C * HEAD_CH].view(C, HEAD_CH)
         ops.transpose(self.w(f"{head}_conv.weight"), WT)
         ops.gemm(dYh, WT, dTrunk, accumulate=accumulate)
@@ -404,7 +415,9 @@ class Learner:
         # ---- backward
         if nb:
             ops.conv_weight_t(self.params, self.w_offsets, self.Wt_all, C, C)
-        ops.transpose(trunk, self.trunkT[:C * P].view(C, P))
+        # every layer output transposed ([C][P]) in one launch: inputs of the weight-gradient GEMMs (the last one = the trunk)
+        self._xt_all = self.XT_all.view(-1)[:self.XT_all.shape[0] * C * P].view(-1, C, P)
+        ops.transpose(self.act_all[:, :P, :], self._xt_all)
         dfeat = self.dacth[:P].view(b, self.A * HEAD_CH)
         G = [g[:P] for g in self.G]
         self._fc_backward(dlogits, fp, "policy_fc.weight", "policy_fc.bias", dfeat)
