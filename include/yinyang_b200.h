@@ -281,13 +281,21 @@ int yy_augment_samples(int rows, int cols, const uint64_t *black_dev, const uint
 #define YY_OP_K_CONV 1
 #define YY_OP_K_CONVT 2
 typedef struct {
+  double *sums;             /* float64 [2N], zero on entry                                    */
+  const float *out;         /* NULL: forward statistics; else the layer's output (ReLU mask)  */
+  int32_t ldo;
+  const float *y;           /* the layer's batch-norm input                                   */
+  int32_t ldy;
+  const float *mean_invstd; /* float [2N] written by yy_lrn_bn_forward                        */
+} yy_gemm_stats;
+typedef struct {
   int32_t rows, cols; /* board */
   int32_t cin;        /* channels of the gathered activation tensor (multiple of 4) */
   int32_t flip;       /* mirror the taps                                            */
 } yy_conv_geom;
 int yy_lrn_gemm(const float *A, int lda, int a_mode, const float *B, int ldb, int b_mode, float *C, int ldc, int M, int N, int K,
                 const float *bias, int relu, int accumulate, int tile_n, int split_k, float *ws, int64_t ws_floats,
-                int precision, const yy_conv_geom *conv, double *bn_sums, void *stream);
+                int precision, const yy_conv_geom *conv, const yy_gemm_stats *stats, void *stream);
 /* Developer tool: while dbg_dev != NULL (>= 128 int64) CTA (0,0,0) of every yy_lrn_gemm launch records clock64 stamps:
  * [0] start, [1] after setup, [4+6k .. 8+6k] producer phases of K-iteration k (start, slot free, copies issued, copies of
  * iteration k-1 landed, iteration k-1 split + published), [2] loop end, [119] accumulator complete, [3] epilogue end. */
@@ -320,11 +328,11 @@ int yy_lrn_bn_forward(const float *Y, int ld, int P, int C, const float *gamma, 
  * dY = gamma*invstd*(dZ - mean(dZ) - xhat*mean(dZ*xhat)); dRes (optional) = dZ; dgamma = sum dZ*xhat; dbeta = sum dZ;
  * dbias (optional, zero on entry) += column sums of dY = the bias gradient of the convolution feeding this batch norm.
  * dYT (optional): also the transposed copy dYT[c][p] = dY[p][c] (ldt) the weight-gradient GEMM reads.
- * sums_ws: float64[2C], zero on entry. */
+ * sums_ws: float64[2C], zero on entry, or -- have_sums != 0 -- already holding sum dZ*xhat / sum dZ (yy_lrn_gemm's stats). */
 int yy_lrn_bn_backward(const float *dOut, int ldd, const float *Out, int ldo, const float *Y, int ldy, int P, int C,
                        const float *mean_invstd, const float *gamma, double *sums_ws, float *dY, int lddy,
                        float *dRes, int lddr, float *dgamma, float *dbeta, float *dbias, float *dYT, int ldt,
-                       void *stream);
+                       int have_sums, void *stream);
 /* Both losses and their gradients at the heads (trainer.py:131-133; value head tail neural_network.py:119-121):
  * losses[0] = CrossEntropyLoss(logits, pi) with probability targets, losses[1] = MSELoss(tanh(relu(h).w2 + b2), z),
  * h = value_fc1's output before its ReLU; dlogits, dh (through that ReLU), dpre[B], v_out[B], dw2[H], db2[1]. */

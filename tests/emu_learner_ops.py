@@ -22,7 +22,7 @@ class TorchEmuOps:
             o[:, xs:xe, ys:ye, t, :] = x[:, xs + dx:xe + dx, ys + dy:ye + dy, :]
         return o.reshape(P, 9 * C)
 
-    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None, conv_t=None):
+    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None, conv_t=None, bn_bwd=None):
         Ae = A if conv is None else self._im2col(A, conv[0], conv[1], conv[3])
         Be = B if conv_t is None else self._im2col(B.t().contiguous(), conv_t[0], conv_t[1], False).t()
         r = Ae.double() @ Be.double().t()
@@ -33,7 +33,13 @@ class TorchEmuOps:
         C.copy_((r.clamp_min(0) if relu else r).float())
         if bn_sums is not None:
             N = C.shape[1]
-            bn_sums[:N] += C.double().sum(0); bn_sums[N:2 * N] += (C.double() ** 2).sum(0)
+            if bn_bwd is None:
+                bn_sums[:N] += C.double().sum(0); bn_sums[N:2 * N] += (C.double() ** 2).sum(0)
+            else:
+                Out, Y, mi = bn_bwd
+                dz = (C * (Out > 0)).double()
+                xhat = ((Y - mi[:N]) * mi[N:]).double()
+                bn_sums[:N] += (dz * xhat).sum(0); bn_sums[N:2 * N] += dz.sum(0)
 
     def transpose(self, inp, out):
         out.copy_(inp.transpose(-1, -2))
@@ -71,11 +77,14 @@ class TorchEmuOps:
             o = o + residual
         out.copy_(o.clamp_min(0) if relu else o)
 
-    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias=None, dYT=None):
+    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias=None, dYT=None, have_sums=False):
         P, C = Y.shape
         dz = dOut * (Out > 0) if Out is not None else dOut.clone()
         xhat = (Y - mean_invstd[:C]) * mean_invstd[C:]
-        dg = (dz.double() * xhat.double()).sum(0); db = dz.double().sum(0)
+        if have_sums:                                   # taken by the GEMM that produced dOut
+            dg, db = ws[:C].clone(), ws[C:2 * C].clone()
+        else:
+            dg = (dz.double() * xhat.double()).sum(0); db = dz.double().sum(0)
         dgamma.copy_(dg.float()); dbeta.copy_(db.float())
         dY.copy_(gamma * mean_invstd[C:] * (dz - db.float() / P - xhat * dg.float() / P))
         if dRes is not None:

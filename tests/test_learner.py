@@ -183,6 +183,16 @@ def test_convolution_passes_match_their_definition(yy, rows, cols, cin, cout, bo
     dx_ref, dx = skip.clone(), skip.clone().cuda()
     emu.gemm(dY, wt_ref, dx_ref, accumulate=True, conv=(rows, cols, cout, 1)); ops.gemm(dY.cuda(), wt, dx, accumulate=True, conv=(rows, cols, cout, 1))
     close(dx, dx_ref, "backward data")
+    if cin == cout:
+        # the same GEMM also taking the batch-norm backward statistics of the layer whose output gradient it produces
+        Out, Yp, mi = rn(P, cin), rn(P, cin), torch.cat([rn(cin) * 0.1, rn(cin).abs() + 0.5])
+        sums_ref, sums = torch.zeros(256, dtype=torch.float64), torch.zeros(256, dtype=torch.float64).cuda()
+        dx2_ref, dx2 = skip.clone(), skip.clone().cuda()
+        emu.gemm(dY, wt_ref, dx2_ref, accumulate=True, conv=(rows, cols, cout, 1), bn_sums=sums_ref, bn_bwd=(Out, Yp, mi))
+        ops.gemm(dY.cuda(), wt, dx2, accumulate=True, conv=(rows, cols, cout, 1), bn_sums=sums, bn_bwd=(Out.cuda(), Yp.cuda(), mi.cuda()))
+        assert torch.equal(dx2, dx)
+        scale = (dx_ref.abs().double().sum(0).max() * 4).item()
+        assert (sums[:2 * cin].cpu() - sums_ref[:2 * cin]).abs().max().item() <= 1e-5 * scale
     xt = X.view(boards, rows, cols, cin).permute(0, 3, 1, 2).clone().requires_grad_(True)
     wt4 = W.view(cout, 3, 3, cin).permute(0, 3, 1, 2).clone().requires_grad_(True)
     yt = torch.nn.functional.conv2d(xt, wt4, bias, padding=1)

@@ -74,6 +74,12 @@ class SelfPlayStats(ctypes.Structure):
                 ("max_depth", ctypes.c_int32)]
 
 
+class GemmStats(ctypes.Structure):
+    """yy_gemm_stats (include/yinyang_b200.h)."""
+    _fields_ = [("sums", ctypes.c_void_p), ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32), ("y", ctypes.c_void_p),
+                ("ldy", ctypes.c_int32), ("mean_invstd", ctypes.c_void_p)]
+
+
 class ConvGeom(ctypes.Structure):
     """yy_conv_geom (include/yinyang_b200.h)."""
     _fields_ = [("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("cin", ctypes.c_int32), ("flip", ctypes.c_int32)]
@@ -135,7 +141,7 @@ SIGNATURES = {
     "yy_lrn_planes_nhwc": (_I, [_P, _P, _I64, _I, _P]),
     "yy_lrn_colsum": (_I, [_P, _I, _I, _I, _P, _P]),
     "yy_lrn_bn_forward": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _F, _F, _P, _I, _P, _P, _P, _P]),
-    "yy_lrn_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P]),
+    "yy_lrn_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "yy_lrn_heads_loss": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
     "yy_lrn_adam": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _P, _P]),
     "yy_probe_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -51,6 +51,7 @@ struct GemmArgs {
   int rows, cols, cin, flip;                        // convolution geometry of the implicit A operand (cin: gathered channels)
   int cz;                                           // CTAs per cluster along z: the K slices whose partial tiles are summed on chip
   double* bn_sums;                                  // fused batch-norm statistics when the cluster produces the final C
+  const float* st_out; const float* st_y; const float* st_mi; int st_ldo, st_ldy;   // st_out != NULL: backward statistics of C (a gradient)
   long long* dbg;                                   // developer tool: clock64 stamps of CTA 0 (yy_lrn_gemm_debug_stamps)
 };
 
@@ -336,8 +337,20 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
             if (g.bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
             if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(crow + n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
             if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
-            s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+            if (g.bn_sums) {
+              if (g.st_out == nullptr) {                       // forward: sum, sum of squares of C
+                s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+                s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+              } else {                                         // backward: C is dOut of a batch norm + ReLU: sum dZ*xhat, sum dZ
+                const float4 o = *reinterpret_cast<const float4*>(g.st_out + (size_t)row * g.st_ldo + n);
+                const float4 y = *reinterpret_cast<const float4*>(g.st_y + (size_t)row * g.st_ldy + n);
+                const float4 mu = *reinterpret_cast<const float4*>(g.st_mi + n), is = *reinterpret_cast<const float4*>(g.st_mi + g.N + n);
+                const float dz0 = o.x > 0.f ? v.x : 0.f, dz1 = o.y > 0.f ? v.y : 0.f, dz2 = o.z > 0.f ? v.z : 0.f, dz3 = o.w > 0.f ? v.w : 0.f;
+                s1[0] += dz0 * ((y.x - mu.x) * is.x); s1[1] += dz1 * ((y.y - mu.y) * is.y);
+                s1[2] += dz2 * ((y.z - mu.z) * is.z); s1[3] += dz3 * ((y.w - mu.w) * is.w);
+                s2[0] += dz0; s2[1] += dz1; s2[2] += dz2; s2[3] += dz3;
+              }
+            }
           }
           *reinterpret_cast<float4*>(crow + n) = v;
         }
@@ -775,7 +788,7 @@ extern "C" {
 
 int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, int b_mode, float* C, int ldc, int M, int N, int K,
                 const float* bias, int relu, int accumulate, int tile_n, int split_k, float* ws, int64_t ws_floats, int precision,
-                const yy_conv_geom* conv, double* bn_sums, void* stream) {
+                const yy_conv_geom* conv, const yy_gemm_stats* stats, void* stream) {
   int rc = need_device(); if (rc) return rc;
   if (M <= 0 || N <= 0 || K <= 0) return set_error(YY_ERR_INVALID, "gemm: empty problem");
   if ((lda | ldb | ldc | N | K) & 3) return set_error(YY_ERR_INVALID, "gemm: lda, ldb, ldc, N and K must be multiples of 4 floats");
@@ -792,7 +805,10 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
   if (precision != YY_GEMM_TF32 && precision != YY_GEMM_3XTF32) return set_error(YY_ERR_INVALID, "gemm: precision must be YY_GEMM_TF32 or YY_GEMM_3XTF32");
   if (tile_n < 16 || tile_n > 128 || tile_n % 16) return set_error(YY_ERR_INVALID, "gemm: tile_n in [16,128] step 16");
   if (split_k < 1) return set_error(YY_ERR_INVALID, "gemm: split_k >= 1");
+  double* bn_sums = stats ? stats->sums : nullptr;
+  const bool bwd_stats = stats && stats->out != nullptr;
   if (bn_sums && (N > 128 || 128 % N)) return set_error(YY_ERR_INVALID, "gemm: fused batch-norm statistics need N dividing 128");
+  if (bwd_stats && (!stats->y || !stats->mean_invstd || (stats->ldo & 3) || (stats->ldy & 3))) return set_error(YY_ERR_INVALID, "gemm: backward statistics need out, y and mean_invstd");
   int kps = (K + split_k - 1) / split_k;
   kps = (kps + kGemmKStage - 1) / kGemmKStage * kGemmKStage;
   const int zs = (K + kps - 1) / kps;
@@ -847,21 +863,28 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
   if (groups > 1 && (!ws || ws_floats < (int64_t)groups * M * N)) return set_error(YY_ERR_INVALID, "gemm: split-K beyond one cluster needs a workspace of (split/cluster)*M*N floats");
   const bool fuse_stats = bn_sums && cz > 1 && groups == 1 && N <= tile_n;
   GemmArgs g{A, B, C, bias, ws, lda, ldb, ldc, M, N, K, tile_n, kps, relu, accumulate, a_mode, b_mode,
-             conv ? conv->rows : 1, conv ? conv->cols : 1, conv ? conv->cin : 4, conv ? conv->flip : 0, cz, fuse_stats ? bn_sums : nullptr, g_gemm_dbg};
+             conv ? conv->rows : 1, conv ? conv->cols : 1, conv ? conv->cin : 4, conv ? conv->flip : 0, cz, fuse_stats ? bn_sums : nullptr,
+             bwd_stats ? stats->out : nullptr, bwd_stats ? stats->y : nullptr, bwd_stats ? stats->mean_invstd : nullptr,
+             bwd_stats ? stats->ldo : 0, bwd_stats ? stats->ldy : 0, g_gemm_dbg};
   if (precision == YY_GEMM_3XTF32) YY_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<3, true>, g));
   else YY_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<4, false>, g));
   YY_LAUNCH_CHECK();
   if (groups > 1) {
     if (256 % (N / 4) == 0) {
       const int rows_per_block = 4 * (256 / (N / 4));
-      gemm_reduce_kernel<<<(unsigned)((M + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(ws, groups, C, ldc, M, N / 4, bias, relu, accumulate, bn_sums);
+      gemm_reduce_kernel<<<(unsigned)((M + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(ws, groups, C, ldc, M, N / 4, bias, relu, accumulate,
+                                                                                                   bwd_stats ? nullptr : bn_sums);
     } else {
       const long long total = (long long)M * (N / 4);
       gemm_reduce_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, groups, C, ldc, M, N / 4, bias, relu, accumulate);
     }
     YY_LAUNCH_CHECK();
-  } else if (bn_sums && !fuse_stats) {
+  } else if (bn_sums && !fuse_stats && !bwd_stats) {
     bn_reduce_kernel<false><<<(M + 31) / 32, 256, 0, st>>>(C, ldc, nullptr, 0, nullptr, 0, nullptr, M, N, bn_sums);
+    YY_LAUNCH_CHECK();
+  }
+  if (bwd_stats && !fuse_stats) {                             // not finished inside one cluster: a pass of its own over the finished C
+    bn_reduce_kernel<true><<<(M + 31) / 32, 256, 0, st>>>(stats->y, stats->ldy, C, ldc, stats->out, stats->ldo, stats->mean_invstd, M, N, bn_sums);
     YY_LAUNCH_CHECK();
   }
   return YY_OK;
@@ -938,12 +961,14 @@ int yy_lrn_bn_forward(const float* Y, int ld, int P, int C, const float* gamma, 
 
 int yy_lrn_bn_backward(const float* dOut, int ldd, const float* Out, int ldo, const float* Y, int ldy, int P, int C,
                        const float* mean_invstd, const float* gamma, double* sums_ws, float* dY, int lddy, float* dRes, int lddr,
-                       float* dgamma, float* dbeta, float* dbias, float* dYT, int ldt, void* stream) {
+                       float* dgamma, float* dbeta, float* dbias, float* dYT, int ldt, int have_sums, void* stream) {
   int rc = need_device(); if (rc) return rc;
   if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
   cudaStream_t st = (cudaStream_t)stream;
-  bn_reduce_kernel<true><<<(P + 31) / 32, 256, 0, st>>>(Y, ldy, dOut, ldd, Out, ldo, mean_invstd, P, C, sums_ws);
-  YY_LAUNCH_CHECK();
+  if (!have_sums) {
+    bn_reduce_kernel<true><<<(P + 31) / 32, 256, 0, st>>>(Y, ldy, dOut, ldd, Out, ldo, mean_invstd, P, C, sums_ws);
+    YY_LAUNCH_CHECK();
+  }
   const long long total = (long long)P * (C / 4);
   bn_bwd_apply_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(dOut, ldd, Out, ldo, Y, ldy, mean_invstd, gamma, sums_ws, P, C / 4,
                                                                       dY, lddy, dRes, lddr, dgamma, dbeta, dbias, dYT, ldt);

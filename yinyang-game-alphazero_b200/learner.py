@@ -52,12 +52,14 @@ class CudaOps:
     def _stream():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None, conv_t=None):
+    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None, conv_t=None, bn_bwd=None):
         """C[M,N] = [C +] A @ B^T (+bias) (relu), B = [N,K].  conv = (rows, cols, cin, flip): A is the activation tensor
         [positions, cin] and the product runs over its implicit im2col (YY_OP_K_CONV).  bn_sums (float64 [>= 2N], zero): also
         accumulate the column sums / sums of squares of C (the statistics of the batch norm that follows).
         conv_t = (rows, cols, cin, 0): B is the TRANSPOSED activation tensor [cin, positions] and stands for its transposed
-        im2col [9*cin, positions] (YY_OP_K_CONVT; the weight gradient of a convolution)."""
+        im2col [9*cin, positions] (YY_OP_K_CONVT; the weight gradient of a convolution).
+        bn_bwd = (Out, Y, mean_invstd) with bn_sums: C is the gradient at Out = relu(bn(Y)); accumulate that layer's
+        backward statistics (sum dZ*xhat, sum dZ) into bn_sums."""
         M, N = C.shape
         K = B.shape[1]
         assert (B.shape[0] == N or conv_t is not None) and (conv is not None or A.shape == (M, K))
@@ -71,12 +73,19 @@ class CudaOps:
             split = max(1, self.ws.numel() // (M * N))
         if conv_t is not None:
             split = max(split, (K + 8191) // 8192)
+        stats = None
+        if bn_sums is not None:
+            st = _lib.GemmStats(bn_sums.data_ptr(), None, 0, None, 0, None)
+            if bn_bwd is not None:
+                o, y, mi = bn_bwd
+                st = _lib.GemmStats(bn_sums.data_ptr(), o.data_ptr(), _ld(o), y.data_ptr(), _ld(y), mi.data_ptr())
+            stats = ctypes.byref(st)
         cg = conv if conv is not None else conv_t
         geom = ctypes.byref(_lib.ConvGeom(*cg)) if cg is not None else None
         _lib.check(self.L.yy_lrn_gemm(_p(A), _ld(A), OP_K_CONV if conv is not None else OP_K, _p(B), _ld(B),
                                       OP_K_CONVT if conv_t is not None else OP_K, _p(C), _ld(C), M, N, K,
                                       _p(bias), int(relu), int(accumulate), tile_n, split, _p(self.ws), self.ws.numel(), self.precision,
-                                      geom, _p(bn_sums), self._stream()))
+                                      geom, stats, self._stream()))
 
     def transpose(self, inp, out):
         """out = inp^T; 3-D tensors [batch, R, C] -> [batch, C, R] are transposed matrix by matrix in one launch."""
@@ -113,12 +122,12 @@ class CudaOps:
                                             _p(out), _ld(out), int(relu), eps, momentum, _p(ws), int(have_sums), _p(mean_invstd),
                                             _p(running_mean), _p(running_var), self._stream()))
 
-    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias, dYT=None):
+    def bn_backward(self, dOut, Out, Y, mean_invstd, gamma, ws, dY, dRes, dgamma, dbeta, dbias, dYT=None, have_sums=False):
         P, C = Y.shape
         _lib.check(self.L.yy_lrn_bn_backward(_p(dOut), _ld(dOut), _p(Out), _ld(Out) if Out is not None else 0, _p(Y), _ld(Y), P, C,
                                              _p(mean_invstd), _p(gamma), _p(ws), _p(dY), _ld(dY), _p(dRes),
                                              _ld(dRes) if dRes is not None else 0, _p(dgamma), _p(dbeta), _p(dbias), _p(dYT),
-                                             _ld(dYT) if dYT is not None else 0, self._stream()))
+                                             _ld(dYT) if dYT is not None else 0, int(have_sums), self._stream()))
 
     def heads_loss(self, logits, pi, h, w2, b2, z, dlogits, dh, dpre, v, dw2, db2, losses):
         B, A = logits.shape
@@ -333,7 +342,7 @@ class Learner:
         dY = self.dY[:P]
         dYT = self.dYT[:C * P].view(C, P)
         ops.bn_backward(dOut, self.act[li][:P], self.Y[li][:P], self.mi[bnpre], self.w(bnpre + ".weight"), self.bn_ws[2 * self._bn_slot[bnpre] + 1],
-                        dY, dRes, self.g(bnpre + ".weight"), self.g(bnpre + ".bias"), self.g(bkey), dYT=dYT)
+                        dY, dRes, self.g(bnpre + ".weight"), self.g(bnpre + ".bias"), self.g(bkey), dYT=dYT, have_sums=self._bwd_sums_ready.get(li, False))
         # dW[co][t*cin+ci] = sum_p dY[p][co] * x_in[p + d(t)][ci]: K = positions, both operands from transposed copies
         if li == 0:
             XT = self.XT[:cin * P].view(cin, P)
@@ -343,7 +352,11 @@ class Learner:
         ops.gemm(dYT, XT, self.g(wkey), conv_t=self._geom(cin))              # B = implicit transposed im2col of x_in
         if dPrev is not None:
             # dX[p][ci] = sum_{t,co} dY[p - d(t)][co] * W[co][t*cin+ci]: implicit (mirrored) im2col of dY times Wt
-            ops.gemm(dY, self.Wt_all[li - 1], dPrev, accumulate=accumulate, conv=self._geom(C, flip=True))
+            # ... which is the complete gradient at act[li-1]: that layer's batch-norm backward statistics are taken in the same GEMM
+            prev = self._bn[li - 1]
+            ops.gemm(dY, self.Wt_all[li - 1], dPrev, accumulate=accumulate, conv=self._geom(C, flip=True),
+                     bn_sums=self.bn_ws[2 * self._bn_slot[prev] + 1], bn_bwd=(self.act[li - 1][:P], self.Y[li - 1][:P], self.mi[prev]))
+            self._bwd_sums_ready[li - 1] = True
 
     def _head_forward(self, head, trunk):
         ops, P = self.ops, self.p
@@ -393,6 +406,7 @@ class Learner:
         ops, nb, b, P, C = self.ops, self.blocks, self.b, self.p, self.C
         self.grads.zero_()
         self.bn_ws.zero_()
+        self._bwd_sums_ready = {}
         # ---- forward (neural_network.py:94-123, train mode)
         X0 = self.X0[:P]
         ops.planes_nhwc(self.planes_in[:b], X0)
