@@ -295,7 +295,13 @@ typedef struct {
 } yy_conv_geom;
 int yy_lrn_gemm(const float *A, int lda, int a_mode, const float *B, int ldb, int b_mode, float *C, int ldc, int M, int N, int K,
                 const float *bias, int relu, int accumulate, int tile_n, int split_k, float *ws, int64_t ws_floats,
-                int precision, const yy_conv_geom *conv, const yy_gemm_stats *stats, void *stream);
+                int precision, const yy_conv_geom *conv, const yy_gemm_stats *stats, const void *b_packed, void *stream);
+/* The weights of `layers` layers ([128][K] row-major; layer l at base + offsets_dev[l], or base + l*layer_stride when
+ * offsets_dev is NULL) -> out + l*yy_lrn_pack_b_bytes(128, K): per K stage of 32 the hi and lo operand tiles of the 3xTF32
+ * GEMM in its shared-memory layout.  Once per optimisation step for the whole tower. */
+int yy_lrn_pack_b(const float *base, const long long *offsets_dev, int64_t layer_stride, int layers, int N, int K, void *out,
+                  void *stream);
+int64_t yy_lrn_pack_b_bytes(int N, int K);
 /* Developer tool: while dbg_dev != NULL (>= 128 int64) CTA (0,0,0) of every yy_lrn_gemm launch records clock64 stamps:
  * [0] start, [1] after setup, [4+6k .. 8+6k] producer phases of K-iteration k (start, slot free, copies issued, copies of
  * iteration k-1 landed, iteration k-1 split + published), [2] loop end, [119] accumulator complete, [3] epilogue end. */

@@ -22,7 +22,7 @@ class TorchEmuOps:
             o[:, xs:xe, ys:ye, t, :] = x[:, xs + dx:xe + dx, ys + dy:ye + dy, :]
         return o.reshape(P, 9 * C)
 
-    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None, conv_t=None, bn_bwd=None):
+    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None, conv_t=None, bn_bwd=None, b_packed=None):
         Ae = A if conv is None else self._im2col(A, conv[0], conv[1], conv[3])
         Be = B if conv_t is None else self._im2col(B.t().contiguous(), conv_t[0], conv_t[1], False).t()
         r = Ae.double() @ Be.double().t()

@@ -156,6 +156,12 @@ def test_convolution_passes_match_their_definition(yy, rows, cols, cin, cout, bo
     y2 = torch.zeros(P, cout).cuda()
     ops.gemm(X.cuda(), W.cuda(), y2, bias=bias.cuda(), conv=(rows, cols, cin, 0), bn_sums=sums)
     assert torch.equal(y2, y)
+    if cout == 128 and (9 * cin) % 32 == 0:                 # the weights streamed as a packed operand: bit-identical product
+        packed = torch.empty(ops.packed_b_bytes(128, 9 * cin), dtype=torch.uint8).cuda()
+        ops.pack_b(W.cuda(), None, 0, 1, 128, 9 * cin, packed)
+        y3 = torch.zeros(P, cout).cuda()
+        ops.gemm(X.cuda(), W.cuda(), y3, bias=bias.cuda(), conv=(rows, cols, cin, 0), b_packed=packed)
+        assert torch.equal(y3, y)
     assert (sums[:cout].cpu() - y_ref.double().sum(0)).abs().max() <= 2e-5 * y_ref.double().abs().sum(0).max()
     assert torch.allclose(sums[cout:2 * cout].cpu(), (y_ref.double() ** 2).sum(0), rtol=2e-5)
     colT_ref, colT = torch.zeros(9 * cin, P), torch.zeros(9 * cin, P).cuda()

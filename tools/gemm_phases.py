@@ -1,5 +1,5 @@
 """Developer tool: clock64 phase stamps of CTA 0 of one learner GEMM (yy_lrn_gemm_debug_stamps).
-usage: gemm_phases.py [3xtf32|tf32] [split_k]"""
+usage: gemm_phases.py [3xtf32|tf32] [split_k] [packed]"""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,12 +12,17 @@ L = _lib.lib()
 dbg = torch.zeros(128, dtype=torch.int64, device="cuda")
 X, W, Y = torch.randn(4096, 128).cuda(), torch.randn(128, 1152).cuda(), torch.zeros(4096, 128).cuda()
 geom = _lib.ConvGeom(8, 8, 128, 0)
+packed = torch.empty(max(1, ops.packed_b_bytes(128, 1152)), dtype=torch.uint8, device="cuda")
+use_packed = len(sys.argv) > 3 and sys.argv[3] == "packed" and ops.precision == 1
+if use_packed:
+    ops.pack_b(W, None, 0, 1, 128, 1152, packed)
+bp = ctypes.c_void_p(packed.data_ptr()) if use_packed else None
 p = lambda t: ctypes.c_void_p(t.data_ptr())
 
 
 def run():
     _lib.check(L.yy_lrn_gemm(p(X), 128, 1, p(W), 1152, 0, p(Y), 128, 4096, 128, 1152, None, 0, 0, 128, split, p(ops.ws), ops.ws.numel(),
-                             ops.precision, ctypes.byref(geom), None, None))
+                             ops.precision, ctypes.byref(geom), None, bp, None))
 
 
 for _ in range(3):

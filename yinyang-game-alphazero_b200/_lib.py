@@ -133,7 +133,9 @@ SIGNATURES = {
     "yy_engine_game_white": (_P, [_P]),
     "yy_engine_game_player": (_P, [_P]),
     "yy_augment_samples": (_I, [_I, _I, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
-    "yy_lrn_gemm": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I64, _I, _P, _P, _P]),
+    "yy_lrn_gemm": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I64, _I, _P, _P, _P, _P]),
+    "yy_lrn_pack_b": (_I, [_P, _P, _I64, _I, _I, _I, _P, _P]),
+    "yy_lrn_pack_b_bytes": (_I64, [_I, _I]),
     "yy_lrn_gemm_debug_stamps": (_I, [_P]),
     "yy_lrn_transpose": (_I, [_P, _I, _P, _I, _I, _I, _I, _I64, _I64, _P]),
     "yy_lrn_im2col_t": (_I, [_P, _I, _P, _I, _I64, _I, _I, _I, _P]),

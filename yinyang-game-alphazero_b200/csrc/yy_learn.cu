@@ -47,6 +47,7 @@ enum { OP_K = YY_OP_K, OP_K_CONV = YY_OP_K_CONV, OP_K_CONVT = YY_OP_K_CONVT };
 
 struct GemmArgs {
   const float* A; const float* B; float* C; const float* bias; float* ws;
+  const uint8_t* Bpack;                             // B pre-split (hi / lo) and pre-tiled per K stage by yy_lrn_pack_b (3xTF32, N = tile_n = 128)
   int lda, ldb, ldc, M, N, K, tile_n, k_per_split, relu, accumulate, a_mode, b_mode;
   int rows, cols, cin, flip;                        // convolution geometry of the implicit A operand (cin: gathered channels)
   int cz;                                           // CTAs per cluster along z: the K slices whose partial tiles are summed on chip
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
   uint32_t ncols = 32; while ((int)ncols < g.tile_n) ncols <<= 1;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&full_bar[s]), 256); mbar_init(smem_u32(&free_bar[s]), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&full_bar[s]), g.Bpack ? 257 : 256); mbar_init(smem_u32(&free_bar[s]), 1); }
     mbar_init(smem_u32(&done_bar), 1);
     fence_barrier_init();
   }
@@ -165,6 +166,18 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // OP_K_CONVT: B row n = tap*cin + ci is row ci of the transposed activation shifted by d(tap) positions
     const bool convB = g.b_mode == OP_K_CONVT;
+    const bool packedB = X3 && g.Bpack != nullptr;
+    // packed B: one thread streams the stage's hi and lo tiles (2 x 16.5 KB, already in the core-matrix layout) with two bulk
+    // async copies that complete on the stage's full barrier -- no LSU requests, no split work for the weights
+    auto bulk_b = [&](int kt) {
+      const int s = kt % S;
+      const uint32_t bar = smem_u32(&full_bar[s]);
+      const uint32_t dst = smem0 + (uint32_t)(s * stage_bytes + kRegionA);
+      const uint8_t* src = g.Bpack + (size_t)(k_begin / kGemmKStage + kt) * (2 * kRegionA);
+      mbar_arrive_expect_tx(bar, 2u * kRegionA);
+      bulk_g2s(dst, src, kRegionA, bar);
+      bulk_g2s(dst + (uint32_t)half_bytes, src + kRegionA, kRegionA, bar);
+    };
     const float* bptr[4] = {g.B, g.B, g.B, g.B};
     uint32_t bneed = 0, bok = 0;                              // bok bit j: B row 4(w+8j)+r4 is inside the tile and inside N
 #pragma unroll
@@ -199,7 +212,9 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
           ra[gi] = ok ? __ldg(reinterpret_cast<const float4*>(arow0 + (size_t)(4 * gi) * g.lda + aoff)) : zero4;
         }
       }
-      if (convB) {
+      if (packedB) {
+        // B arrives by bulk copy (below)
+      } else if (convB) {
         uint32_t e4 = 0;                                      // edge bits of the chunk's 4 positions
         if (kok) e4 = *reinterpret_cast<const uint32_t*>(edge_s + (k - k_begin));   // K is a multiple of 4: whole chunks
 #pragma unroll
@@ -237,9 +252,11 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
 #pragma unroll
       for (int gi = 0; gi < 4; ++gi) put(a + gi * 64, ra[gi]);
       uint8_t* b = st + kRegionA + c8 * planeB + (4 * warp + r4) * 16;
+      if (!packedB) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (4 * (warp + 8 * j) + r4 < g.tile_n) put(b + j * 512, rb[j]);
+        for (int j = 0; j < 4; ++j)
+          if (4 * (warp + 8 * j) + r4 < g.tile_n) put(b + j * 512, rb[j]);
+      }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&full_bar[s]));
     };
@@ -248,14 +265,18 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
     // bounded by the L1 request path of the 64 LDG.128 per stage, 8 cache lines each, not by bytes in flight or by L2.)
     float4 ra[4], rb[4], na[4], nb[4];
     if (KT > 0) load_regs(ra, rb, 0);
+    if (packedB && tid == 0 && KT > 0) bulk_b(0);
     for (int kt = 0; kt < KT; ++kt) {
       const int s = kt % S;
       YY_STAMP(4 + 6 * kt);
       if (kt + 1 < KT) load_regs(na, nb, kt + 1);             // next stage's loads in flight while this one is stored
       YY_STAMP(5 + 6 * kt);
-      if (kt >= S) {                                          // the MMAs that read this slot S iterations ago
-        if (lane == 0) mbar_wait(smem_u32(&free_bar[s]), (uint32_t)(((kt / S) - 1) & 1));
-        __syncwarp();
+      if (kt + 1 < KT) {                                      // the slot of stage kt+1: the MMAs that read it S iterations earlier
+        if (kt + 1 >= S) {
+          if (lane == 0) mbar_wait(smem_u32(&free_bar[(kt + 1) % S]), (uint32_t)((((kt + 1) / S) - 1) & 1));
+          __syncwarp();
+        }
+        if (packedB && tid == 0) bulk_b(kt + 1);
       }
       YY_STAMP(6 + 6 * kt);
       store_stage(ra, rb, s);
@@ -505,6 +526,24 @@ __global__ void __launch_bounds__(256) conv_weight_t_kernel(const float* __restr
   const int co = idx % Cout, t = (idx / Cout) % 9, ci = idx / (9 * Cout);
   Wt[(size_t)blockIdx.y * Cout * 9 * Cin + idx] = W[(size_t)co * 9 * Cin + t * Cin + ci];
 }
+// Weights of `layers` layers ([128][K] row-major, layer l at base + (offsets ? offsets[l] : l*layer_stride)) -> per layer and
+// K stage of 32 the two B tiles of the 3xTF32 GEMM, hi then lo, each [8 chunk planes][128 rows][16 B] with the plane pitch of
+// the shared-memory layout: what gemm_tf32_kernel streams with bulk copies (GemmArgs::Bpack).
+__global__ void __launch_bounds__(256) pack_b_kernel(const float* __restrict__ base, const long long* __restrict__ offsets, long long layer_stride,
+                                                    int K, uint8_t* __restrict__ out) {
+  const int stages = K / kGemmKStage;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte chunk: (stage, plane, row)
+  if (idx >= stages * 8 * 128) return;
+  const int row = idx & 127, plane = (idx >> 7) & 7, st = idx >> 10, l = blockIdx.y;
+  const float* W = base + (offsets ? offsets[l] : (long long)l * layer_stride);
+  const float4 v = *reinterpret_cast<const float4*>(W + (size_t)row * K + st * kGemmKStage + plane * 4);
+  const float4 h = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                               __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+  uint8_t* o = out + ((size_t)l * stages + st) * (2 * kRegionA) + plane * kPlaneA + row * 16;
+  *reinterpret_cast<float4*>(o) = h;
+  *reinterpret_cast<float4*>(o + kRegionA) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
 // planes float32 [B][5][cells] (board_to_input, neural_network.py:156-196) -> X0 [B*cells][8] (channels 5..7 zero)
 __global__ void __launch_bounds__(256) planes_nhwc_kernel(const float* __restrict__ planes, float* __restrict__ X0, long long P, int cells) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -788,7 +827,7 @@ extern "C" {
 
 int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, int b_mode, float* C, int ldc, int M, int N, int K,
                 const float* bias, int relu, int accumulate, int tile_n, int split_k, float* ws, int64_t ws_floats, int precision,
-                const yy_conv_geom* conv, const yy_gemm_stats* stats, void* stream) {
+                const yy_conv_geom* conv, const yy_gemm_stats* stats, const void* b_packed, void* stream) {
   int rc = need_device(); if (rc) return rc;
   if (M <= 0 || N <= 0 || K <= 0) return set_error(YY_ERR_INVALID, "gemm: empty problem");
   if ((lda | ldb | ldc | N | K) & 3) return set_error(YY_ERR_INVALID, "gemm: lda, ldb, ldc, N and K must be multiples of 4 floats");
@@ -805,6 +844,8 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
   if (precision != YY_GEMM_TF32 && precision != YY_GEMM_3XTF32) return set_error(YY_ERR_INVALID, "gemm: precision must be YY_GEMM_TF32 or YY_GEMM_3XTF32");
   if (tile_n < 16 || tile_n > 128 || tile_n % 16) return set_error(YY_ERR_INVALID, "gemm: tile_n in [16,128] step 16");
   if (split_k < 1) return set_error(YY_ERR_INVALID, "gemm: split_k >= 1");
+  if (b_packed && (precision != YY_GEMM_3XTF32 || N != 128 || tile_n != 128 || (K % kGemmKStage) || b_mode != YY_OP_K || ((uintptr_t)b_packed & 15)))
+    return set_error(YY_ERR_INVALID, "gemm: a packed B needs 3xTF32, N = tile_n = 128 and K a multiple of 32");
   double* bn_sums = stats ? stats->sums : nullptr;
   const bool bwd_stats = stats && stats->out != nullptr;
   if (bn_sums && (N > 128 || 128 % N)) return set_error(YY_ERR_INVALID, "gemm: fused batch-norm statistics need N dividing 128");
@@ -862,7 +903,7 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
   const int groups = zs / cz;
   if (groups > 1 && (!ws || ws_floats < (int64_t)groups * M * N)) return set_error(YY_ERR_INVALID, "gemm: split-K beyond one cluster needs a workspace of (split/cluster)*M*N floats");
   const bool fuse_stats = bn_sums && cz > 1 && groups == 1 && N <= tile_n;
-  GemmArgs g{A, B, C, bias, ws, lda, ldb, ldc, M, N, K, tile_n, kps, relu, accumulate, a_mode, b_mode,
+  GemmArgs g{A, B, C, bias, ws, (const uint8_t*)b_packed, lda, ldb, ldc, M, N, K, tile_n, kps, relu, accumulate, a_mode, b_mode,
              conv ? conv->rows : 1, conv ? conv->cols : 1, conv ? conv->cin : 4, conv ? conv->flip : 0, cz, fuse_stats ? bn_sums : nullptr,
              bwd_stats ? stats->out : nullptr, bwd_stats ? stats->y : nullptr, bwd_stats ? stats->mean_invstd : nullptr,
              bwd_stats ? stats->ldo : 0, bwd_stats ? stats->ldy : 0, g_gemm_dbg};
@@ -889,6 +930,17 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
   }
   return YY_OK;
 }
+
+int yy_lrn_pack_b(const float* base, const long long* offsets_dev, int64_t layer_stride, int layers, int N, int K, void* out, void* stream) {
+  int rc = need_device(); if (rc) return rc;
+  if (N != 128 || K <= 0 || (K % kGemmKStage) || ((uintptr_t)out & 15)) return set_error(YY_ERR_INVALID, "pack_b: N = 128, K a multiple of 32");
+  if (layers < 1) return YY_OK;
+  const int chunks = (K / kGemmKStage) * 8 * 128;
+  pack_b_kernel<<<dim3((unsigned)((chunks + 255) / 256), (unsigned)layers), 256, 0, (cudaStream_t)stream>>>(base, offsets_dev, layer_stride, K, (uint8_t*)out);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+int64_t yy_lrn_pack_b_bytes(int N, int K) { return N == 128 && K % kGemmKStage == 0 ? (int64_t)(K / kGemmKStage) * 2 * kRegionA : -1; }
 
 int yy_lrn_gemm_debug_stamps(long long* dbg_dev) { g_gemm_dbg = dbg_dev; return YY_OK; }
 

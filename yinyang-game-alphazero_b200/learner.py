@@ -52,14 +52,15 @@ class CudaOps:
     def _stream():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None, conv_t=None, bn_bwd=None):
+    def gemm(self, A, B, C, bias=None, relu=False, accumulate=False, conv=None, bn_sums=None, conv_t=None, bn_bwd=None, b_packed=None):
         """C[M,N] = [C +] A @ B^T (+bias) (relu), B = [N,K].  conv = (rows, cols, cin, flip): A is the activation tensor
         [positions, cin] and the product runs over its implicit im2col (YY_OP_K_CONV).  bn_sums (float64 [>= 2N], zero): also
         accumulate the column sums / sums of squares of C (the statistics of the batch norm that follows).
         conv_t = (rows, cols, cin, 0): B is the TRANSPOSED activation tensor [cin, positions] and stands for its transposed
         im2col [9*cin, positions] (YY_OP_K_CONVT; the weight gradient of a convolution).
         bn_bwd = (Out, Y, mean_invstd) with bn_sums: C is the gradient at Out = relu(bn(Y)); accumulate that layer's
-        backward statistics (sum dZ*xhat, sum dZ) into bn_sums."""
+        backward statistics (sum dZ*xhat, sum dZ) into bn_sums.
+        b_packed: B as tiled by pack_b (streamed with bulk copies instead of being loaded and split by the producer warps)."""
         M, N = C.shape
         K = B.shape[1]
         assert (B.shape[0] == N or conv_t is not None) and (conv is not None or A.shape == (M, K))
@@ -85,7 +86,14 @@ class CudaOps:
         _lib.check(self.L.yy_lrn_gemm(_p(A), _ld(A), OP_K_CONV if conv is not None else OP_K, _p(B), _ld(B),
                                       OP_K_CONVT if conv_t is not None else OP_K, _p(C), _ld(C), M, N, K,
                                       _p(bias), int(relu), int(accumulate), tile_n, split, _p(self.ws), self.ws.numel(), self.precision,
-                                      geom, stats, self._stream()))
+                                      geom, stats, _p(b_packed), self._stream()))
+
+    def packed_b_bytes(self, N, K):
+        """Bytes per layer of the packed weight operand, or -1 when this GEMM configuration has none."""
+        return int(self.L.yy_lrn_pack_b_bytes(N, K)) if self.precision == 1 else -1
+
+    def pack_b(self, base, offsets, layer_stride, layers, N, K, out):
+        _lib.check(self.L.yy_lrn_pack_b(_p(base), _p(offsets), layer_stride, layers, N, K, _p(out), self._stream()))
 
     def transpose(self, inp, out):
         """out = inp^T; 3-D tensors [batch, R, C] -> [batch, C, R] are transposed matrix by matrix in one launch."""
@@ -291,6 +299,11 @@ class Learner:
         self.dYT, self.XT, self.XT_all = z(max(C, HEAD_CH) * P), z(C * P), z(n_conv, C, P)
         self.Wt = z(C * HEAD_CH)
         self.Wt_all = z(max(1, 2 * self.blocks), C, 9 * C)           # backward-data views of the tower's conv weights
+        pb = self.ops.packed_b_bytes(C, 9 * C) if hasattr(self.ops, "packed_b_bytes") else -1
+        self.Bp_fwd = self.Bp_bwd = None                             # tower weights / their backward-data views, tiled for bulk copies
+        if pb > 0 and self.blocks:
+            self.Bp_fwd = torch.empty(2 * self.blocks, pb, dtype=torch.uint8, device=self.dev)
+            self.Bp_bwd = torch.empty(2 * self.blocks, pb, dtype=torch.uint8, device=self.dev)
         self.w_offsets = torch.tensor([self.layout.offsets[f"res_blocks.{k}.conv{j}.weight"] for k in range(self.blocks) for j in (1, 2)],
                                       dtype=torch.int64, device=self.dev)
         kp = (B + 3) // 4 * 4
@@ -330,7 +343,8 @@ class Learner:
     def _conv3_forward(self, x, wkey, bkey, bnpre, li, residual=None):
         ops, P = self.ops, self.p
         sums = self.bn_ws[2 * self._bn_slot[bnpre]]
-        ops.gemm(x, self.w(wkey), self.Y[li][:P], bias=self.w(bkey), conv=self._geom(x.shape[1]), bn_sums=sums)
+        ops.gemm(x, self.w(wkey), self.Y[li][:P], bias=self.w(bkey), conv=self._geom(x.shape[1]), bn_sums=sums,
+                 b_packed=self.Bp_fwd[li - 1] if (self.Bp_fwd is not None and li >= 1) else None)
         ops.bn_forward(self.Y[li][:P], self.w(bnpre + ".weight"), self.w(bnpre + ".bias"), residual, self.act[li][:P], True, self.bn_eps,
                        self.bn_momentum, sums, self.mi[bnpre], self.running[bnpre][0], self.running[bnpre][1], have_sums=True)
 
@@ -355,7 +369,8 @@ class Learner:
             # ... which is the complete gradient at act[li-1]: that layer's batch-norm backward statistics are taken in the same GEMM
             prev = self._bn[li - 1]
             ops.gemm(dY, self.Wt_all[li - 1], dPrev, accumulate=accumulate, conv=self._geom(C, flip=True),
-                     bn_sums=self.bn_ws[2 * self._bn_slot[prev] + 1], bn_bwd=(self.act[li - 1][:P], self.Y[li - 1][:P], self.mi[prev]))
+                     bn_sums=self.bn_ws[2 * self._bn_slot[prev] + 1], bn_bwd=(self.act[li - 1][:P], self.Y[li - 1][:P], self.mi[prev]),
+                     b_packed=self.Bp_bwd[li - 1] if self.Bp_bwd is not None else None)
             self._bwd_sums_ready[li - 1] = True
 
     def _head_forward(self, head, trunk):
@@ -407,6 +422,8 @@ class Learner:
         self.grads.zero_()
         self.bn_ws.zero_()
         self._bwd_sums_ready = {}
+        if self.Bp_fwd is not None:                              # the tower's weights, split and tiled once per step
+            ops.pack_b(self.params, self.w_offsets, 0, 2 * nb, C, 9 * C, self.Bp_fwd)
         # ---- forward (neural_network.py:94-123, train mode)
         X0 = self.X0[:P]
         ops.planes_nhwc(self.planes_in[:b], X0)
@@ -429,6 +446,8 @@ class Learner:
         # ---- backward
         if nb:
             ops.conv_weight_t(self.params, self.w_offsets, self.Wt_all, C, C)
+            if self.Bp_bwd is not None:
+                ops.pack_b(self.Wt_all, None, C * 9 * C, 2 * nb, C, 9 * C, self.Bp_bwd)
         # every layer output transposed ([C][P]) in one launch: inputs of the weight-gradient GEMMs (the last one = the trunk)
         self._xt_all = self.XT_all.view(-1)[:self.XT_all.shape[0] * C * P].view(-1, C, P)
         ops.transpose(self.act_all[:, :P, :], self._xt_all)
