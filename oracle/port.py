@@ -302,3 +302,20 @@ def env_steps(n, m, n_steps, seed=0):
         if res != 0:
             board, player = game.getInitBoard(), 1
     return done
+
+
+def training_step(net, optimizer, planes, policies, values):
+    """One optimisation step exactly as the inner loop of AlphaZeroTrainer.train runs it (src/yin_yang/ai/trainer.py:120-137):
+    train() mode forward, CrossEntropyLoss with probability targets + MSELoss, backward, optimizer.step().  Returns
+    (policy_loss, value_loss, {name: gradient}).  TEST INFRASTRUCTURE (the checker of the CUDA learner step)."""
+    import torch
+    net.train()
+    optimizer.zero_grad()
+    policy_logits, value_preds = net(planes)
+    policy_loss = torch.nn.CrossEntropyLoss()(policy_logits, policies)
+    value_loss = torch.nn.MSELoss()(value_preds.view(-1), values)
+    (policy_loss + value_loss).backward()
+    grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    optimizer.step()
+    return policy_loss.item(), value_loss.item(), grads
+

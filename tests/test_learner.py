@@ -39,15 +39,63 @@ def _batch(net, n, m, B, seed):
 
 
 def _torch_step(net, opt, planes, pi, z):
-    net.train()
-    opt.zero_grad()
-    lg, v = net(planes)
-    lp = torch.nn.CrossEntropyLoss()(lg, pi)               # trainer.py:61,131
-    lv = torch.nn.MSELoss()(v.view(-1), z)                 # trainer.py:60,132
-    (lp + lv).backward()
-    grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
-    opt.step()
-    return lp.item(), lv.item(), grads
+    from oracle import port
+    return port.training_step(net, opt, planes, pi, z)       # trainer.py:120-137 restated
+
+
+def _check_against_reference_golden(L, g, to_dev, grad_tol, state_tol, state_mean_tol):
+    """tests/golden/learner_*.npz: three steps of the UNMODIFIED reference trainer (make_golden_learner.py)."""
+    planes, pi, z = (torch.from_numpy(g[k]) for k in ("planes", "pi", "z"))
+    names = [str(n) for n in g["names"]]
+    for k, b in enumerate(g["sizes"]):
+        b = int(b)
+        losses = L.step(to_dev(planes[:b]), to_dev(pi[:b]), to_dev(z[:b])).cpu()
+        assert abs(losses[0].item() - g["loss_p"][k]) <= 2e-4 * abs(g["loss_p"][k]) + 1e-5, (k, losses.tolist(), g["loss_p"][k])
+        assert abs(losses[1].item() - g["loss_v"][k]) <= 2e-4 * abs(g["loss_v"][k]) + 1e-5, (k, losses.tolist(), g["loss_v"][k])
+        got = L.grad_dict()
+        for j, name in enumerate(names):
+            if _is_conv_bias(name):
+                continue
+            if k == 0:
+                ref = torch.from_numpy(g["grad0." + name])
+                assert (got[name] - ref).norm() <= grad_tol * ref.norm() + 1e-7, (name, (got[name] - ref).norm().item(), ref.norm().item())
+            assert abs(got[name].norm().item() - g["gnorm"][k][j]) <= 10 * grad_tol * g["gnorm"][k][j] + 1e-6, (k, name)
+    sd = L.state_dict()
+    for key in g.files:
+        if key.startswith("after."):
+            name = key[6:]
+            if _is_conv_bias(name):
+                continue
+            ref = torch.from_numpy(np.asarray(g[key]))
+            assert sd[name].shape == ref.shape, name
+            if "num_batches" in name:
+                assert int(sd[name]) == int(ref)
+            else:
+                # Adam moves an entry whose gradient is rounding-level by up to lr per step in either direction: a hard bound of
+                # 2*lr*steps on every entry, a tight bound on the mean
+                d = (sd[name].float() - ref.float()).abs()
+                assert d.max() <= state_tol and d.mean() <= state_mean_tol, (name, d.max().item(), d.mean().item())
+
+
+def _golden_learner(yy, **kw):
+    from conftest import load_golden
+    from yinyang_game_alphazero_b200 import learner
+    g = load_golden("learner_4x4_c8_b2.npz")
+    sd = {k[5:]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith("init.")}
+    return g, learner.Learner(4, 4, int(g["channels"]), int(g["blocks"]), batch_size=int(g["sizes"][0]), state_dict=sd, **kw)
+
+
+def test_learner_sequence_matches_the_unmodified_reference_trainer(yy):
+    """The reference's own AlphaZeroTrainer objects stepped three times (fixture made by importing /root/reference):
+    losses, first-step gradients, per-step gradient norms and the final state_dict, with the kernels emulated in torch."""
+    g, L = _golden_learner(yy, _ops=TorchEmuOps())
+    _check_against_reference_golden(L, g, lambda t: t, grad_tol=1e-4, state_tol=3e-4, state_mean_tol=1e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_learner_matches_the_unmodified_reference_trainer(yy):
+    g, L = _golden_learner(yy)
+    _check_against_reference_golden(L, g, lambda t: t.cuda(), grad_tol=2e-3, state_tol=6.5e-3, state_mean_tol=1e-4)
 
 
 def _is_conv_bias(k):
