@@ -350,7 +350,7 @@ def bench_env(engine, torch, peaks):
             "timing": "8 launches replayed from a CUDA graph, CUDA events around the replay",
             "per_call": {"value": ENV_BOARDS / api_launch_s, "unit": "steps/s", "us_per_launch": api_launch_s * 1e6,
                          "note": "one engine.env_step() Python/ctypes call per launch, device-resident tensors"},
-            "e2e": {"value": e2e, "unit": "steps/s", "api": "env_step_host (int8 numpy boards in/out, pack/unpack on host)"},
+            "e2e": {"value": e2e, "unit": "steps/s", "api": "env_step_host (int8 numpy boards in/out; bit packing on the device)"},
             "roofline": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs / peaks["hbm_gbs"], "traffic": None,
                          "note": "3.4 MB of algorithmic traffic per launch: latency bound at this batch size (two lanes per board, "

@@ -84,6 +84,14 @@ int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t *black_dev, ui
                 int8_t *players_dev, const int32_t *actions_dev, uint64_t *out_mask_dev, int8_t *out_result_dev,
                 int64_t count, void *stream);
 
+/* The reference's board arrays on the device: int8 [count][n*m] with 0 empty / +1 black / -1 white (YinYangLogic.board,
+ * yin_yang_logic.py:14-22) -> bitboards, and back (out_boards) / a legal-move mask -> uint8 [count][n*m] of 0/1 (out_mask, the
+ * layout of getValidMoves, yin_yang_game.py:60-78).  Either output of yy_unpack_boards may be NULL. */
+int yy_pack_boards(int rows, int cols, const int8_t *boards_dev, uint64_t *black_dev, uint64_t *white_dev, int64_t count,
+                   void *stream);
+int yy_unpack_boards(int rows, int cols, const uint64_t *black_dev, const uint64_t *white_dev, const uint64_t *mask_dev,
+                     int8_t *out_boards_dev, uint8_t *out_mask_dev, int64_t count, void *stream);
+
 /* Synthetic-board generator of SURVEY 8d / BASELINE.json configs[1]: board i = empty board
  * advanced by plies[i] uniformly random legal plies (passes as in the rules), Philox stream
  * keyed by (seed, i).  Also the random-play opponent of evaluate mode (RandomPlayer.play,

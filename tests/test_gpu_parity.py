@@ -377,3 +377,20 @@ def test_selfplay_reference_player_semantics(eng, oracle_mod):
         r = oracle_mod.mcts_search(rp["boards"][i], 1, n, m, sims)       # searched as black whatever the mover
         assert np.array_equal(rp["counts"][i].astype(np.int32), r["counts"]), i
     e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m", [(8, 8), (6, 6), (5, 7), (16, 16), (9, 11)])
+def test_device_pack_unpack_matches_host_packing(yy, n, m):
+    """yy_pack_boards / yy_unpack_boards (the int8 <-> bitboard conversion of the host-buffer entry points) against the numpy
+    packing of bitboard.py, including the last partial word."""
+    from yinyang_game_alphazero_b200 import engine, bitboard
+    rng = np.random.default_rng(n * 100 + m)
+    boards = rng.integers(-1, 2, (700, n, m)).astype(np.int8)
+    b, w = engine.pack_boards_dev(boards, n, m)
+    hb, hw = bitboard.pack_boards(boards, n, m)
+    assert np.array_equal(b.cpu().numpy().view(np.uint64), hb) and np.array_equal(w.cpu().numpy().view(np.uint64), hw)
+    back, bits = engine.unpack_boards_dev(n, m, b, w, mask=b)
+    assert np.array_equal(back, boards) and np.array_equal(bits, (boards == 1).reshape(700, -1).astype(np.uint8))
+    only_mask = engine.unpack_boards_dev(n, m, mask=w)
+    assert only_mask[0] is None and np.array_equal(only_mask[1], (boards == -1).reshape(700, -1).astype(np.uint8))

@@ -107,6 +107,8 @@ SIGNATURES = {
     "yy_step": (_I, [_I, _I, _U32, _P, _P, _P, _P, _I64, _P]),
     "yy_ended": (_I, [_I, _I, _U32, _P, _P, _P, _P, _I64, _P]),
     "yy_env_step": (_I, [_I, _I, _U32, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "yy_pack_boards": (_I, [_I, _I, _P, _P, _P, _I64, _P]),
+    "yy_unpack_boards": (_I, [_I, _I, _P, _P, _P, _P, _P, _I64, _P]),
     "yy_random_playout": (_I, [_I, _I, _U32, ctypes.c_uint64, _P, _P, _P, _P, _I64, _P]),
     "yy_engine_workspace_bytes": (_I64, [ctypes.POINTER(EngineConfig)]),
     "yy_engine_create": (_P, [ctypes.POINTER(EngineConfig), _P, _I64]),

@@ -172,6 +172,31 @@ random_playout_kernel(Geo<NW> g, int W, uint64_t seed, const int32_t* __restrict
   players[i] = (int8_t)p;
 }
 
+// int8 boards (0 / +1 / -1, yin_yang_logic.py:14-22) <-> bitboards, on the device: the host-buffer entry points copy the
+// reference's own board arrays and leave the bit packing to the GPU.  One thread per (board, word).
+__global__ void __launch_bounds__(256) pack_boards_kernel(const int8_t* __restrict__ boards, int cells, int W, uint64_t* __restrict__ black,
+                                                         uint64_t* __restrict__ white, long long count) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count * W) return;
+  const long long i = idx / W; const int w = (int)(idx % W);
+  const int8_t* b = boards + i * cells + w * 64;
+  const int n = min(64, cells - w * 64);
+  uint64_t bk = 0, wh = 0;
+  for (int k = 0; k < n; ++k) { const int v = b[k]; bk |= (uint64_t)(v == 1) << k; wh |= (uint64_t)(v == -1) << k; }
+  black[idx] = bk; white[idx] = wh;
+}
+// out_boards (optional) int8 [count][cells] = black - white; out_mask (optional) uint8 [count][cells] = bits of `mask`.  One thread per cell.
+__global__ void __launch_bounds__(256) unpack_boards_kernel(const uint64_t* __restrict__ black, const uint64_t* __restrict__ white,
+                                                           const uint64_t* __restrict__ mask, int cells, int W, int8_t* __restrict__ out_boards,
+                                                           uint8_t* __restrict__ out_mask, long long count) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count * cells) return;
+  const long long i = idx / cells; const int a = (int)(idx % cells);
+  const long long wi = i * W + (a >> 6); const int bit = a & 63;
+  if (out_boards) out_boards[idx] = (int8_t)((int)((black[wi] >> bit) & 1ull) - (int)((white[wi] >> bit) & 1ull));
+  if (out_mask) out_mask[idx] = (uint8_t)((mask[wi] >> bit) & 1ull);
+}
+
 static int check_rules_args(int rows, int cols, long long count) {
   if (!board_supported(rows, cols)) return set_error(YY_ERR_INVALID, "unsupported board %dx%d (need <=32 per side, <=256 cells)", rows, cols);
   if (count < 0) return set_error(YY_ERR_INVALID, "negative count");
@@ -246,6 +271,26 @@ int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64
     YY_DISPATCH_NW(cells, env_step_kernel<NW, 256><<<grid, 256, 0, (cudaStream_t)stream>>>(
         make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count));
   }
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_pack_boards(int rows, int cols, const int8_t* boards, uint64_t* black, uint64_t* white, int64_t count, void* stream) {
+  int rc = check_rules_args(rows, cols, count); if (rc) return rc;
+  if (count == 0) return YY_OK;
+  const int cells = rows * cols, W = words_for_cells(cells);
+  pack_boards_kernel<<<(unsigned)((count * W + 255) / 256), 256, 0, (cudaStream_t)stream>>>(boards, cells, W, black, white, count);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
+
+int yy_unpack_boards(int rows, int cols, const uint64_t* black, const uint64_t* white, const uint64_t* mask, int8_t* out_boards,
+                     uint8_t* out_mask, int64_t count, void* stream) {
+  int rc = check_rules_args(rows, cols, count); if (rc) return rc;
+  if (count == 0 || (!out_boards && !out_mask)) return YY_OK;
+  if ((out_boards && (!black || !white)) || (out_mask && !mask)) return set_error(YY_ERR_INVALID, "unpack: missing source words");
+  const int cells = rows * cols, W = words_for_cells(cells);
+  unpack_boards_kernel<<<(unsigned)((count * cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(black, white, mask, cells, W, out_boards, out_mask, count);
   YY_LAUNCH_CHECK();
   return YY_OK;
 }

@@ -154,26 +154,58 @@ def _to_dev(a, dtype):
     return t.pin_memory().to("cuda", non_blocking=True).view(dtype) if t.numel() else t.to("cuda").view(dtype)
 
 
+_DEVICE_PACK_MIN = 512      # from this many boards on, the int8 <-> bitboard conversion runs on the GPU
+
+
+def pack_boards_dev(boards, rows, cols):
+    """numpy int8[B,n,m] -> device bitboards (black int64[B,W], white int64[B,W]); the packing itself on the GPU."""
+    B, W = int(np.asarray(boards).shape[0]), bitboard.words_for(rows, cols)
+    bd_i8 = torch.from_numpy(np.ascontiguousarray(boards, dtype=np.int8).reshape(B, rows * cols)).cuda()
+    black = torch.empty((B, W), dtype=torch.int64, device="cuda"); white = torch.empty_like(black)
+    _lib.check(_lib.lib().yy_pack_boards(rows, cols, _ptr(bd_i8), _ptr(black), _ptr(white), B, _stream()))
+    return black, white
+
+
+def unpack_boards_dev(rows, cols, black=None, white=None, mask=None):
+    """Device bitboards -> (numpy int8[B,n,m] boards or None, numpy uint8[B,A] mask bits or None); unpacked on the GPU."""
+    ref = black if black is not None else mask
+    B, A = ref.shape[0], rows * cols
+    ob = torch.empty((B, A), dtype=torch.int8, device="cuda") if black is not None else None
+    om = torch.empty((B, A), dtype=torch.uint8, device="cuda") if mask is not None else None
+    _lib.check(_lib.lib().yy_unpack_boards(rows, cols, _ptr(black), _ptr(white), _ptr(mask), _ptr(ob), _ptr(om), B, _stream()))
+    return (ob.cpu().numpy().reshape(B, rows, cols) if ob is not None else None, om.cpu().numpy() if om is not None else None)
+
+
+def _boards_to_dev(boards, rows, cols):
+    if np.asarray(boards).shape[0] >= _DEVICE_PACK_MIN:
+        return pack_boards_dev(boards, rows, cols)
+    b, w = bitboard.pack_boards(boards, rows, cols)
+    return _to_dev(b, torch.int64), _to_dev(w, torch.int64)
+
+
 def legal_mask_host(boards, players, rows, cols, rule_flags=0):
     """numpy int8[B,n,m] boards, int8[B] players -> uint8[B, A] masks.  H2D + kernel + D2H."""
     _require_cuda()
-    b, w = bitboard.pack_boards(boards, rows, cols)
-    mask = legal_mask(_to_dev(b, torch.int64), _to_dev(w, torch.int64),
-                      _to_dev(np.asarray(players, np.int8), torch.int8), rows, cols, rule_flags)
+    bd, wd = _boards_to_dev(boards, rows, cols)
+    mask = legal_mask(bd, wd, _to_dev(np.asarray(players, np.int8), torch.int8), rows, cols, rule_flags)
+    if mask.shape[0] >= _DEVICE_PACK_MIN:
+        return unpack_boards_dev(rows, cols, mask=mask)[1]
     return bitboard.unpack_bits(mask.cpu().numpy().view(np.uint64), rows, cols)
 
 
 def env_step_host(boards, players, actions, rows, cols, rule_flags=0):
     """Host-buffer env step: returns (masks uint8[B,A], boards' int8[B,n,m], players' int8[B], results f64[B])."""
     _require_cuda()
-    b, w = bitboard.pack_boards(boards, rows, cols)
-    bd, wd = _to_dev(b, torch.int64), _to_dev(w, torch.int64)
+    bd, wd = _boards_to_dev(boards, rows, cols)
     pd = _to_dev(np.asarray(players, np.int8), torch.int8)
     ad = _to_dev(np.asarray(actions, np.int32), torch.int32)
     mask, res = env_step(bd, wd, pd, ad, rows, cols, rule_flags)
-    return (bitboard.unpack_bits(mask.cpu().numpy().view(np.uint64), rows, cols),
-            bitboard.unpack_boards(bd.cpu().numpy().view(np.uint64), wd.cpu().numpy().view(np.uint64), rows, cols),
-            pd.cpu().numpy(), result_from_code(res.cpu().numpy()))
+    if mask.shape[0] >= _DEVICE_PACK_MIN:
+        nb, bits = unpack_boards_dev(rows, cols, bd, wd, mask)
+    else:
+        bits = bitboard.unpack_bits(mask.cpu().numpy().view(np.uint64), rows, cols)
+        nb = bitboard.unpack_boards(bd.cpu().numpy().view(np.uint64), wd.cpu().numpy().view(np.uint64), rows, cols)
+    return bits, nb, pd.cpu().numpy(), result_from_code(res.cpu().numpy())
 
 
 def next_state_host(boards, players, actions, rows, cols, rule_flags=0):
