@@ -153,6 +153,10 @@ void yy_engine_destroy(yy_engine *e);
  * uploaded by the caller; the engine keeps the pointer.  Layout: csrc/yy_nn.cuh. */
 int64_t yy_nn_weight_bytes(int rows, int cols, int channels, int blocks);
 int yy_engine_load_weights(yy_engine *e, const void *weights_dev, int64_t bytes);
+/* Section offsets of that image for the host-side packer: out[0..8] = conv_stream, conv_bias, fc_policy_w, fc_policy_b,
+ * fc_value1_w, fc_value1_b, fc_value2_w, fc_value2_b, total bytes; out[9] = policy rows padded to 16; out[10], out[11] =
+ * offset / bytes of the stage-ordered FC stream; out[12] = conv stream with N-halved stages (CTA-pair kernel).  13 values. */
+int yy_nn_weight_layout(int rows, int cols, int channels, int blocks, int64_t *out);
 
 /* MCTS.search (mcts.py:275-343) for all games at once.  Roots: one board per game.
  * noise_dev (may be NULL): float64 [n_games][A], one Dirichlet sample per legal root action in
