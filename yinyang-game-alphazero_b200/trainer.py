@@ -46,11 +46,12 @@ class AlphaZeroTrainer:
         for epoch in range(epochs):
             t0 = time.time()
             perm = torch.randperm(n, device=planes.device)
+            pl, po, va = planes[perm], policies[perm], values[perm]    # one gather per epoch; batches are contiguous slices
             acc = torch.zeros(2, dtype=torch.float64, device=planes.device)
             for i in range(0, n, self.batch_size):
-                idx = perm[i:i + self.batch_size]
-                losses = self.learner.step(planes[idx], policies[idx], values[idx])
-                acc += losses.double() * idx.numel()                   # stays on the device: no sync per batch
+                j = min(n, i + self.batch_size)
+                losses = self.learner.step(pl[i:j], po[i:j], va[i:j])
+                acc += losses.double() * (j - i)                       # stays on the device: no sync per batch
             pl, vl = (acc / max(n, 1)).tolist()
             metrics["policy_loss"].append(pl); metrics["value_loss"].append(vl); metrics["total_loss"].append(pl + vl)
             logger.info(f"Epoch {epoch + 1}/{epochs} - Policy Loss: {pl:.4f}, Value Loss: {vl:.4f}, "
