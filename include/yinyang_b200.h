@@ -367,6 +367,11 @@ int yy_lrn_adam(float *params, const float *grads, float *m, float *v, int64_t n
 int yy_probe_umma(const void *a_dev, const void *b_dev, float *c_dev, int M, int N, int K, int a_row_offset,
                   int swap_lbo_sbo, void *stream);
 
+/* Developer tool: kind::tf32 MMA with a TRANSPOSED ("MN-major") A operand staged in the canonical layout of a swizzle mode
+ * (variant 0 none, 1 SWIZZLE_128B, 2 the same bytes declared SWIZZLE_128B_BASE32B); B K-major.  At [K][128], B [N][K], C [128][N].
+ * Layout: csrc/yy_probe.cu. */
+int yy_probe_tf32_mn(const float *at_dev, const float *b_dev, float *c_dev, int N, int K, int variant, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

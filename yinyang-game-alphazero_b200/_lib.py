@@ -148,6 +148,7 @@ SIGNATURES = {
     "yy_lrn_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "yy_lrn_heads_loss": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
     "yy_lrn_adam": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _P, _P]),
+    "yy_probe_tf32_mn": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "yy_probe_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 

@@ -188,3 +188,81 @@ extern "C" int yy_l2_stream(const void* src_dev, long long src_bytes, long long 
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ tf32 MN-major probe
+// Developer tool: C[128,N] = A * B^T with kind::tf32 where A is given TRANSPOSED in memory (At [K][128], "MN-major") and staged
+// in shared memory in the canonical MN-major layout of the chosen swizzle mode; B [N][K] is K-major, no swizzle (known good).
+//   variant 0: no swizzle       [k/8][m/4][8 k][16 B]                    SBO = 128 (m groups), LBO = 4096 (k groups)
+//   variant 1: SWIZZLE_128B     [k/8][m/32][8 k][128 B], 16-byte chunk c of k-row r stored at chunk c ^ r; LBO = 1024 (m groups of 32),
+//                               SBO = 4096 (k groups)
+//   variant 2: the layout of variant 1 with layout type SWIZZLE_128B_BASE32B (rejected by the entry point: illegal memory access)
+// Result on B200 (round 1): variants 0 and 1 complete and return C == 0 for every K and N tried, i.e. with these layouts the tf32
+// MMA does not read a transposed A; the learner therefore stages transposed copies (yy_learn.cu).
+namespace yy {
+__global__ void __launch_bounds__(128) probe_tf32_mn_kernel(const float* __restrict__ At, const float* __restrict__ B, float* __restrict__ C,
+                                                           int N, int K, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* a_s = smem;                                   // K/8 groups x 4096 B
+  uint8_t* b_s = smem + (size_t)(K / 8) * 4096;          // K-major: [K/4 planes][N rows][16 B]
+  for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {   // chunk (k, m4)
+    const int k = i / 32, m4 = i % 32;
+    const float4 v = *reinterpret_cast<const float4*>(At + (size_t)k * 128 + m4 * 4);
+    const int kg = k >> 3, kr = k & 7;
+    size_t off;
+    if (variant == 0) off = (size_t)kg * 4096 + m4 * 128 + kr * 16;
+    else { const int ng = m4 >> 3, c = m4 & 7; off = (size_t)kg * 4096 + ng * 1024 + kr * 128 + ((c ^ kr) * 16); }
+    *reinterpret_cast<float4*>(a_s + off) = v;
+  }
+  for (int i = threadIdx.x; i < (K / 4) * N; i += blockDim.x) {
+    const int kc = i / N, r = i % N;
+    *reinterpret_cast<float4*>(b_s + (size_t)i * 16) = *reinterpret_cast<const float4*>(B + (size_t)r * K + kc * 4);
+  }
+  uint32_t ncols = 32; while ((int)ncols < N) ncols <<= 1;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&tmem_base_s), ncols);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t lt = variant == 0 ? 0ull : (variant == 1 ? 2ull : 1ull);
+    for (int k8 = 0; k8 < K / 8; ++k8) {
+      const uint32_t a_addr = smem_u32(a_s) + (uint32_t)(k8 * 4096);
+      const uint32_t b_addr = smem_u32(b_s) + (uint32_t)(2 * k8 * N * 16);
+      const uint64_t ad = (variant == 0 ? smem_desc(a_addr, 4096, 128) : smem_desc(a_addr, 1024, 4096)) | (lt << 61);
+      const uint64_t bd = smem_desc(b_addr, N * 16, 128);
+      asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                   ::"r"(tmem_base), "l"(ad), "l"(bd), "r"(idesc), "r"(k8 > 0 ? 1u : 0u) : "memory");
+    }
+    tc_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = 0; c < N; c += 16) {
+    uint32_t r[16];
+    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, r);
+    tc_wait_ld();
+    for (int j = 0; j < 16; ++j) C[(size_t)(warp * 32 + lane) * N + c + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem_base, ncols);
+}
+}  // namespace yy
+
+extern "C" int yy_probe_tf32_mn(const float* at_dev, const float* b_dev, float* c_dev, int N, int K, int variant, void* stream) {
+  using namespace yy;
+  if (yy_device_count() == 0) return set_error(YY_ERR_NO_DEVICE, "no CUDA device");
+  if (N < 16 || N > 256 || N % 16 || K < 8 || K % 8 || K > 128) return set_error(YY_ERR_INVALID, "probe: N in [16,256] step 16, K multiple of 8 up to 128");
+  if (variant != 0 && variant != 1) return set_error(YY_ERR_INVALID, "probe: variant 0 or 1 (variant 2 raised an illegal memory access on sm_100a)");
+  const size_t smem = (size_t)(K / 8) * 4096 + (size_t)(K / 4) * N * 16 + 1024;
+  YY_CUDA_OK(cudaFuncSetAttribute(probe_tf32_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_tf32_mn_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(at_dev, b_dev, c_dev, N, K, variant);
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
