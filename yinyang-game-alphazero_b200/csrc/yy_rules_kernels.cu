@@ -65,7 +65,7 @@ ended_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint64_
 // shared memory, so the lanes of a warp get boards of similar cost; results go back to the boards' own slots.
 constexpr int kEnvBins = 64;
 
-template <int NW, int BLOCK>
+template <int NW, int BLOCK, bool SORT>
 __global__ void __launch_bounds__(BLOCK)
 env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __restrict__ white,
                 int8_t* __restrict__ players, const int32_t* __restrict__ actions, uint64_t* __restrict__ out_mask,
@@ -77,37 +77,39 @@ env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __rest
   __shared__ uint16_t s_order[BOARDS];        // sorted position -> board of this block
   const int tid = threadIdx.x;
   const long long base = (long long)blockIdx.x * BOARDS;
-  if (tid <= kEnvBins) s_hist[tid] = 0;
-  __syncthreads();
-  int key = kEnvBins, rank = 0;               // boards past the end sort last
-  if (tid < BOARDS) {
-    const long long mine = base + tid;
-    if (mine < count) {
-      int stones = 0;
-      for (int k = 0; k < W; ++k) stones += popc64(black[mine * W + k] | white[mine * W + k]);
-      key = stones * kEnvBins / (g.cells + 1);
+  if (SORT) {
+    if (tid <= kEnvBins) s_hist[tid] = 0;
+    __syncthreads();
+    int key = kEnvBins, rank = 0;               // boards past the end sort last
+    if (tid < BOARDS) {
+      const long long mine = base + tid;
+      if (mine < count) {
+        int stones = 0;
+        for (int k = 0; k < W; ++k) stones += popc64(black[mine * W + k] | white[mine * W + k]);
+        key = stones * kEnvBins / (g.cells + 1);
+      }
+      rank = atomicAdd(&s_hist[key], 1);
     }
-    rank = atomicAdd(&s_hist[key], 1);
-  }
-  __syncthreads();
-  if (tid < 32) {                             // exclusive scan of the 65 bins by one warp
-    int v0 = s_hist[tid], v1 = s_hist[tid + 32], v2 = tid == 0 ? s_hist[64] : 0;
-    int i0 = v0, i1 = v1;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int t0 = __shfl_up_sync(0xffffffffu, i0, d), t1 = __shfl_up_sync(0xffffffffu, i1, d);
-      if (tid >= d) { i0 += t0; i1 += t1; }
+    __syncthreads();
+    if (tid < 32) {                             // exclusive scan of the 65 bins by one warp
+      int v0 = s_hist[tid], v1 = s_hist[tid + 32], v2 = tid == 0 ? s_hist[64] : 0;
+      int i0 = v0, i1 = v1;
+  #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int t0 = __shfl_up_sync(0xffffffffu, i0, d), t1 = __shfl_up_sync(0xffffffffu, i1, d);
+        if (tid >= d) { i0 += t0; i1 += t1; }
+      }
+      int tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+      s_off[tid] = i0 - v0; s_off[tid + 32] = tot0 + i1 - v1;
+      if (tid == 0) { s_off[64] = tot0 + tot1; (void)v2; }
     }
-    int tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
-    s_off[tid] = i0 - v0; s_off[tid + 32] = tot0 + i1 - v1;
-    if (tid == 0) { s_off[64] = tot0 + tot1; (void)v2; }
+    __syncthreads();
+    if (tid < BOARDS) s_order[s_off[key] + rank] = (uint16_t)tid;
+    __syncthreads();
   }
-  __syncthreads();
-  if (tid < BOARDS) s_order[s_off[key] + rank] = (uint16_t)tid;
-  __syncthreads();
 
   const int side = tid & 1;                   // 0: the mover's colour, 1: the other colour
-  const long long i = base + s_order[tid >> 1];
+  const long long i = base + (SORT ? (int)s_order[tid >> 1] : (tid >> 1));
   const bool live = i < count;                // both lanes of a pair agree; nobody leaves before the shuffles
   BB<NW> b = bb_zero<NW>(), w = bb_zero<NW>();
   int praw = 1, a = -1;
@@ -261,14 +263,16 @@ int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64
   int rc = check_rules_args(rows, cols, count); if (rc) return rc;
   if (count == 0) return YY_OK;
   int cells = rows * cols, W = words_for_cells(cells);
-  static const int block = [] { const char* e = getenv("YY_ENV_BLOCK"); return e ? atoi(e) : 256; }();  // developer A/B switch
-  if (block == 512) {
-    unsigned grid = (unsigned)((count + 255) / 256);
-    YY_DISPATCH_NW(cells, env_step_kernel<NW, 512><<<grid, 512, 0, (cudaStream_t)stream>>>(
+  // Blocks counting-sort their boards by stone count so that a warp's lanes run fills of similar length; YY_ENV_SORT=0/1
+  // forces the choice (developer A/B switch).
+  static const int force = [] { const char* e = getenv("YY_ENV_SORT"); return e ? atoi(e) : -1; }();
+  const bool sort = force < 0 ? true : force != 0;
+  unsigned grid = (unsigned)((count + 127) / 128);
+  if (sort) {
+    YY_DISPATCH_NW(cells, env_step_kernel<NW, 256, true><<<grid, 256, 0, (cudaStream_t)stream>>>(
         make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count));
   } else {
-    unsigned grid = (unsigned)((count + 127) / 128);
-    YY_DISPATCH_NW(cells, env_step_kernel<NW, 256><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    YY_DISPATCH_NW(cells, env_step_kernel<NW, 256, false><<<grid, 256, 0, (cudaStream_t)stream>>>(
         make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count));
   }
   YY_LAUNCH_CHECK();
