@@ -402,3 +402,30 @@ def test_training_on_a_fixed_batch_reduces_the_loss(yy):
     last = last.cpu()
     assert torch.isfinite(last).all()
     assert last.sum() < 0.7 * first.sum(), (first.tolist(), last.tolist())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m,b", [(8, 8, 1), (8, 8, 2), (6, 6, 7), (4, 8, 5)])
+def test_cuda_step_on_tiny_and_odd_batches(yy, n, m, b):
+    """Batches far below one 128-row tile, odd sizes and a non-square board: losses and gradients against the fp32 torch step."""
+    from oracle import port
+    from yinyang_game_alphazero_b200 import learner
+    torch.manual_seed(n * 10 + b)
+    net = port.build_net(n, m, 32, 1)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if "bn" in k or k.endswith("bias"):
+                p.add_(torch.randn_like(p) * 0.2)
+    L = learner.Learner(n, m, 32, 1, batch_size=8, state_dict=net.state_dict())
+    g = torch.Generator().manual_seed(b)
+    grids = torch.randint(-1, 2, (b, n, m), generator=g).numpy().astype(np.int8)
+    planes = torch.as_tensor(net.planes(grids))
+    pi = torch.softmax(torch.randn(b, n * m, generator=g), 1); z = torch.rand(b, generator=g) * 2 - 1
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
+    lp, lv, ref = _torch_step(net, opt, planes, pi, z)
+    losses = L.step(planes.cuda(), pi.cuda(), z.cuda()).cpu()
+    assert abs(losses[0].item() - lp) <= 2e-4 * abs(lp) + 1e-5 and abs(losses[1].item() - lv) <= 2e-4 * abs(lv) + 1e-5
+    got = L.grad_dict()
+    for k, gr in ref.items():
+        if not _is_conv_bias(k):
+            assert (got[k] - gr).norm() <= 2e-2 * gr.norm() + 1e-6, (k, (got[k] - gr).norm().item(), gr.norm().item())
