@@ -628,39 +628,40 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                       float eps, float momentum, float* __restrict__ mean_invstd, float* __restrict__ running_mean,
                                                       float* __restrict__ running_var, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ residual, int ldr, float* __restrict__ out, int ldo, int relu) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float s_mu[128], s_is[128];
   const int C = C4 * 4;
-  if (blockIdx.x == 0)
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const double mean = sums[c] / P;
-      double var = sums[C + c] / P - mean * mean;
-      if (var < 0.0) var = 0.0;
-      mean_invstd[c] = (float)mean;
-      mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
-      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-      if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(P > 1 ? var * P / (P - 1) : var);
-    }
-  if (idx >= P * C4) return;
-  const int c = (int)(idx % C4) * 4; const long long p = idx / C4;
-  float y[4], o[4];
-  *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Y + (size_t)p * ld + c);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const double mean = sums[c + j] / P;
-    double var = sums[C + c + j] / P - mean * mean;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {         // the float64 arithmetic once per channel and block
+    const double mean = sums[c] / P;
+    double var = sums[C + c] / P - mean * mean;
     if (var < 0.0) var = 0.0;
     const float mu = (float)mean, is = (float)(1.0 / sqrt(var + (double)eps));
-    o[j] = (y[j] - mu) * is * gamma[c + j] + beta[c + j];
+    s_mu[c] = mu; s_is[c] = is;
+    if (blockIdx.x == 0) {
+      mean_invstd[c] = mu; mean_invstd[C + c] = is;
+      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+      if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(P > 1 ? var * P / (P - 1) : var);
+    }
   }
+  __syncthreads();
+  const long long total = P * C4, i0 = (long long)blockIdx.x * 512 + threadIdx.x, i1 = i0 + 256;   // two float4 per thread, loads first
+  const bool ok0 = i0 < total, ok1 = i1 < total;
+  const long long p0 = i0 / C4, p1 = i1 / C4;
+  const int c0 = (int)(i0 % C4) * 4, c1 = (int)(i1 % C4) * 4;
+  float y0[4] = {0.f, 0.f, 0.f, 0.f}, y1[4] = {0.f, 0.f, 0.f, 0.f}, r0[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ok0) *reinterpret_cast<float4*>(y0) = *reinterpret_cast<const float4*>(Y + (size_t)p0 * ld + c0);
+  if (ok1) *reinterpret_cast<float4*>(y1) = *reinterpret_cast<const float4*>(Y + (size_t)p1 * ld + c1);
   if (residual) {
-    const float4 r = *reinterpret_cast<const float4*>(residual + (size_t)p * ldr + c);
-    o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+    if (ok0) *reinterpret_cast<float4*>(r0) = *reinterpret_cast<const float4*>(residual + (size_t)p0 * ldr + c0);
+    if (ok1) *reinterpret_cast<float4*>(r1) = *reinterpret_cast<const float4*>(residual + (size_t)p1 * ldr + c1);
   }
-  if (relu) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+  for (int j = 0; j < 4; ++j) {
+    y0[j] = (y0[j] - s_mu[c0 + j]) * s_is[c0 + j] * gamma[c0 + j] + beta[c0 + j] + r0[j];
+    y1[j] = (y1[j] - s_mu[c1 + j]) * s_is[c1 + j] * gamma[c1 + j] + beta[c1 + j] + r1[j];
+    if (relu) { y0[j] = fmaxf(y0[j], 0.f); y1[j] = fmaxf(y1[j], 0.f); }
   }
-  *reinterpret_cast<float4*>(out + (size_t)p * ldo + c) = *reinterpret_cast<float4*>(o);
+  if (ok0) *reinterpret_cast<float4*>(out + (size_t)p0 * ldo + c0) = *reinterpret_cast<float4*>(y0);
+  if (ok1) *reinterpret_cast<float4*>(out + (size_t)p1 * ldo + c1) = *reinterpret_cast<float4*>(y1);
 }
 // backward, pass 2: dY = gamma*invstd*(dZ - dbeta/P - xhat*dgamma/P); optional dRes = dZ (the skip connection's share);
 // block 0 also writes d gamma / d beta into the gradient buffer; dbias (optional, zero on entry) += column sums of dY --
@@ -685,22 +686,27 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     mu[j] = mean_invstd[c + j]; is[j] = mean_invstd[C + c + j]; ga[j] = gamma[c + j];
     sg[j] = (float)sums[c + j] * invP; sb[j] = (float)sums[C + c + j] * invP;
   }
+  float dzv[4][4], yv[4][4], ov[4][4];                           // all loads of the block's 4 row slabs first
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) {
+    const long long idx = ((long long)blockIdx.x * 4 + sl) * 256 + threadIdx.x;
+    const bool ok = idx < P * C4;
+    const long long p = ok ? idx / C4 : 0;
+    *reinterpret_cast<float4*>(dzv[sl]) = ok ? *reinterpret_cast<const float4*>(dOut + (size_t)p * ldd + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(yv[sl]) = ok ? *reinterpret_cast<const float4*>(Y + (size_t)p * ldy + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(ov[sl]) = (ok && Out) ? *reinterpret_cast<const float4*>(Out + (size_t)p * ldo + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
 #pragma unroll
   for (int sl = 0; sl < 4; ++sl) {
     const long long idx = ((long long)blockIdx.x * 4 + sl) * 256 + threadIdx.x;
     if (idx < P * C4) {
       const long long p = idx / C4;
-      float dz[4], y[4], o[4], r[4];
-      *reinterpret_cast<float4*>(dz) = *reinterpret_cast<const float4*>(dOut + (size_t)p * ldd + c);
-      *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Y + (size_t)p * ldy + c);
-      if (Out) {
-        *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(Out + (size_t)p * ldo + c);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (!(o[j] > 0.f)) dz[j] = 0.f;
-      }
+      float r[4];
+      float* dz = dzv[sl];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float xhat = (y[j] - mu[j]) * is[j];
+        if (!(ov[sl][j] > 0.f)) dz[j] = 0.f;
+        const float xhat = (yv[sl][j] - mu[j]) * is[j];
         r[j] = ga[j] * is[j] * (dz[j] - sb[j] - xhat * sg[j]);
         acc[j] += r[j];
       }
@@ -1006,7 +1012,7 @@ int yy_lrn_bn_forward(const float* Y, int ld, int P, int C, const float* gamma, 
     YY_LAUNCH_CHECK();
   }
   const long long total = (long long)P * (C / 4);
-  bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Y, ld, P, C / 4, sums_ws, eps, momentum, mean_invstd, running_mean, running_var,
+  bn_apply_kernel<<<(unsigned)((total + 511) / 512), 256, 0, st>>>(Y, ld, P, C / 4, sums_ws, eps, momentum, mean_invstd, running_mean, running_var,
                                                                   gamma, beta, residual, ldr, out, ldo, relu);
   YY_LAUNCH_CHECK();
   return YY_OK;
