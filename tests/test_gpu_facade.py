@@ -254,3 +254,24 @@ def test_gui_ai_move_endpoint_body(pkg, tmp_path):
     req["board"] = full.tolist()
     assert ai_move.get_ai_move(req) == {"validMove": False, "message": "No valid moves available"}
     assert "error" in ai_move.get_ai_move({"board": None})
+
+
+def test_cli_train_mode_under_torchrun_two_gpus(pkg, tmp_path):
+    """torchrun --nproc-per-node 2 train_alphazero.py --mode train: every rank self-plays its share into its own data file, the
+    learner trains data parallel, rank 0 writes checkpoints and plays the arena (needs two GPUs; skipped on a one-GPU box)."""
+    import subprocess, sys, glob, socket
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md, dd = str(tmp_path / "models"), str(tmp_path / "data")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "train_alphazero.py"), "--mode", "train", "--rows", "6", "--cols", "6",
+                        "--iterations", "1", "--episodes", "16", "--simulations", "16", "--epochs", "1", "--arena-games", "4",
+                        "--model-dir", md, "--data-dir", dd], capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(glob.glob(os.path.join(dd, "self_play_data_*_r0.npz"))) == 1 and len(glob.glob(os.path.join(dd, "self_play_data_*_r1.npz"))) == 1
+    cur = torch.load(os.path.join(md, "current_model.pth.tar"), map_location="cpu", weights_only=False)["state_dict"]
+    ck = torch.load(os.path.join(md, "checkpoint_1.pth.tar"), map_location="cpu", weights_only=False)["state_dict"]
+    assert all(torch.equal(cur[k], ck[k]) for k in ck) and int(ck["bn1.num_batches_tracked"]) > 0

@@ -62,10 +62,19 @@ def main(argv=None):
     model_path = os.path.join(args.model_dir, args.output_model)
     if args.mode == "train":                                             # train_alphazero.py:86-101
         from yinyang_game_alphazero_b200.alphazero import AlphaZero
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world > 1:                                                    # torchrun: one process per GPU
+            import torch
+            import torch.distributed as dist
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         AlphaZero(game=game, model_dir=args.model_dir, data_dir=args.data_dir, num_iterations=args.iterations,
                   num_episodes=args.episodes, num_simulations=args.simulations, num_epochs=args.epochs,
                   num_workers=args.workers, mcts_threads=args.mcts_threads, eval_games=args.arena_games,
                   batch_size=args.batch_size, lr=args.lr).run()
+        if world > 1:
+            dist.destroy_process_group()
         logger.info("Training completed!")
         return 0
     if not os.path.exists(model_path):

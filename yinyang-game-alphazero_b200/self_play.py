@@ -186,15 +186,15 @@ def _reference_board_class():
         return cls, created
 
 
-def generate_self_play_data(game, model_path, output_dir, num_games=100, num_workers=1, num_simulations=800, wire="native"):
-    """self_play.py:337-387.  Returns the path of the written .npz (``wire``: see save_examples)."""
-    if not os.path.exists(output_dir):
-        os.makedirs(output_dir)
+def generate_self_play_data(game, model_path, output_dir, num_games=100, num_workers=1, num_simulations=800, wire="native", file_tag=""):
+    """self_play.py:337-387.  Returns the path of the written .npz (``wire``: see save_examples; ``file_tag``: suffix that keeps
+    the files of several ranks apart)."""
+    os.makedirs(output_dir, exist_ok=True)
     games_per_worker = max(1, num_games // num_workers)          # self_play.py:355
     manager = SelfPlayManager(game=game, model_path=model_path, num_workers=num_workers, games_per_worker=games_per_worker,
                               num_simulations=num_simulations)
     examples = manager.generate_games_parallel()
-    filename = os.path.join(output_dir, f"self_play_data_{int(time.time())}.npz")
+    filename = os.path.join(output_dir, f"self_play_data_{int(time.time())}{file_tag}.npz")
     save_examples(filename, examples, game.getActionSize(), wire)
     logger.info(f"Saved {len(examples)} examples to {filename}")
     return filename

@@ -18,6 +18,14 @@ from .trainer import AlphaZeroTrainer
 logger = logging.getLogger("YinYangTraining")
 
 
+def _rank():
+    try:
+        import torch.distributed as dist
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    except Exception:
+        return 0
+
+
 class TrainingDataQueue:  # training_pipeline.py:23-106
     def __init__(self, max_size=500000, sample_size=10000):
         self.max_size = max_size
@@ -72,7 +80,7 @@ class TrainingPipeline:  # training_pipeline.py:108-287
         self.iteration = latest
 
     def load_data(self):
-        files = glob.glob(os.path.join(self.data_dir, "self_play_data_*.npz"))
+        files = sorted(glob.glob(os.path.join(self.data_dir, "self_play_data_*.npz")))
         if not files:
             logger.warning("No data files found.")
             return
@@ -86,7 +94,7 @@ class TrainingPipeline:  # training_pipeline.py:108-287
             return {}
         metrics = self.trainer.train(examples=examples, epochs=self.epochs_per_iteration, augment=True)
         self.iteration += 1
-        if self.iteration % self.checkpoint_interval == 0:
+        if self.iteration % self.checkpoint_interval == 0 and _rank() == 0:      # data parallel: identical weights, one writer
             self.trainer.save_checkpoint(iteration=self.iteration)
         logger.info(f"Iteration {self.iteration} completed. Policy Loss: {metrics['policy_loss'][-1]:.4f}, "
                     f"Value Loss: {metrics['value_loss'][-1]:.4f}, Total Loss: {metrics['total_loss'][-1]:.4f}")
