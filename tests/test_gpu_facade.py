@@ -275,3 +275,23 @@ def test_cli_train_mode_under_torchrun_two_gpus(pkg, tmp_path):
     cur = torch.load(os.path.join(md, "current_model.pth.tar"), map_location="cpu", weights_only=False)["state_dict"]
     ck = torch.load(os.path.join(md, "checkpoint_1.pth.tar"), map_location="cpu", weights_only=False)["state_dict"]
     assert all(torch.equal(cur[k], ck[k]) for k in ck) and int(ck["bn1.num_batches_tracked"]) > 0
+
+
+def test_mcts_num_threads_is_k_leaves_per_step(pkg):
+    """MCTS(num_threads=K) (mcts.py:320-321: simulations on K threads) = K leaves per game per step with virtual loss: every
+    simulation is accounted for and the choice agrees with the sequential search on a clear-cut position more often than not."""
+    game = pkg["game"].YinYangGame(6, 6)
+    net = pkg["network"].HashStubEvaluator(game)
+    seq = pkg["mcts"].MCTS(game, net, num_simulations=128, dirichlet_noise=False, verbose=0)
+    par = pkg["mcts"].MCTS(game, net, num_simulations=128, num_threads=8, dirichlet_noise=False, verbose=0)
+    rng = np.random.default_rng(3)
+    boards = np.zeros((6, 6, 6), np.int8)
+    for i in range(6):
+        boards[i, rng.integers(0, 6), rng.integers(0, 6)] = 1
+    players = -np.ones(6, np.int8)
+    c1, _ = seq.search_batch(boards, players)
+    c8, _ = par.search_batch(boards, players)
+    assert np.array_equal(c8.sum(axis=1), c1.sum(axis=1)) and np.all(c8.sum(axis=1) == 128)
+    top3 = [len(set(np.argsort(-c1[i])[:3]) & set(np.argsort(-c8[i])[:3])) for i in range(6)]
+    assert np.mean(top3) >= 1.5
+    seq.close(); par.close()

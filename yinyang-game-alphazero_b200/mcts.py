@@ -69,7 +69,10 @@ class MCTS:
                  dirichlet_noise=True, dirichlet_alpha=0.3, dirichlet_epsilon=0.25, verbose=1):
         self.game, self.neural_net = game, neural_net
         self.num_simulations, self.cpuct, self.temperature = num_simulations, cpuct, temperature
-        self.num_threads = max(1, num_threads)  # accepted for compatibility; the GPU search is sequential per game
+        # mcts.py:320-321,414-426 runs the simulations of a search on `num_threads` threads; here num_threads = K > 1 selects
+        # K leaves per game per step with virtual loss (Engine(leaves_per_step=K)): K simulations share one network batch,
+        # which cuts the latency of a single-position search; 1 (default) = the exact sequential search
+        self.num_threads = max(1, num_threads)
         self.use_dirichlet, self.dirichlet_alpha, self.dirichlet_epsilon = dirichlet_noise, dirichlet_alpha, dirichlet_epsilon
         self._engines = {}
         logger.setLevel({0: logging.ERROR, 1: logging.INFO}.get(verbose, logging.DEBUG))
@@ -91,6 +94,8 @@ class MCTS:
                       dirichlet_epsilon=self.dirichlet_epsilon)
             if self._mode() == "nn":
                 kw["state_dict"] = self.neural_net.state_dict()
+            if self.num_threads > 1 and self._mode() != "external":
+                kw["leaves_per_step"] = self.num_threads
             e = self._engines[n_games] = _engine.Engine(**kw)
         return e
 
