@@ -545,6 +545,18 @@ def bench_learner(engine, torch, peaks):
                             "h2d_bytes_per_step": B * (2 * 8 + 4 * A + 4) // 8, "d2h_bytes_per_step": 0,
                             "api": "AlphaZeroTrainer.train(examples, epochs=2, augment=True): host examples in, metrics out",
                             "total_loss_per_epoch": [float(x) for x in m["total_loss"]]}
+    # CPU baseline: the same step as the reference runs it (oracle/port.py training_step = trainer.py:120-137 in fp32 torch),
+    # on this box's host cores with torch's own intra-op threading
+    cpu_net = port.build_net(ROWS, COLS, 128, 10)
+    cpu_opt = torch.optim.Adam(cpu_net.parameters(), lr=1e-3, weight_decay=1e-4)
+    hp, hq, hv = planes[:B].cpu(), pol[:B].cpu(), val[:B].cpu()
+    port.training_step(cpu_net, cpu_opt, hp, hq, hv)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        port.training_step(cpu_net, cpu_opt, hp, hq, hv)
+    cpu_s = (time.perf_counter() - t0) / 3
+    out["3xtf32"]["cpu_baseline"] = {"value": B / cpu_s, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                     "sample": "3 optimisation steps of batch 64 (fp32 torch on the host, intra-op threads = cores)"}
     res = out["3xtf32"]
     res["metric"] = "training samples/sec (8x8, 128x10 network, batch 64, Adam; one CUDA-graph replay per step)"
     res["single_pass_tf32"] = out["tf32"]
