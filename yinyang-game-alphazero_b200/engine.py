@@ -154,13 +154,29 @@ def _to_dev(a, dtype):
     return t.pin_memory().to("cuda", non_blocking=True).view(dtype) if t.numel() else t.to("cuda").view(dtype)
 
 
+def _to_host(*tensors):
+    """Device tensors -> numpy arrays through pinned buffers of torch's caching host allocator: the copies run at the
+    PCIe rate on the current stream (no pageable staging, no first-touch page faults), one synchronisation for all.
+    Each array owns its buffer (returned to the allocator's cache when the array dies)."""
+    hosts = []
+    for t in tensors:
+        if t is None or t.numel() == 0:
+            hosts.append(None if t is None else t.cpu())
+            continue
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        hosts.append(h)
+    torch.cuda.current_stream().synchronize()
+    return tuple(None if h is None else h.numpy() for h in hosts)
+
+
 _DEVICE_PACK_MIN = 512      # from this many boards on, the int8 <-> bitboard conversion runs on the GPU
 
 
 def pack_boards_dev(boards, rows, cols):
     """numpy int8[B,n,m] -> device bitboards (black int64[B,W], white int64[B,W]); the packing itself on the GPU."""
     B, W = int(np.asarray(boards).shape[0]), bitboard.words_for(rows, cols)
-    bd_i8 = torch.from_numpy(np.ascontiguousarray(boards, dtype=np.int8).reshape(B, rows * cols)).cuda()
+    bd_i8 = _to_dev(np.ascontiguousarray(boards, dtype=np.int8).reshape(B, rows * cols), torch.int8)
     black = torch.empty((B, W), dtype=torch.int64, device="cuda"); white = torch.empty_like(black)
     _lib.check(_lib.lib().yy_pack_boards(rows, cols, _ptr(bd_i8), _ptr(black), _ptr(white), B, _stream()))
     return black, white
@@ -173,7 +189,8 @@ def unpack_boards_dev(rows, cols, black=None, white=None, mask=None):
     ob = torch.empty((B, A), dtype=torch.int8, device="cuda") if black is not None else None
     om = torch.empty((B, A), dtype=torch.uint8, device="cuda") if mask is not None else None
     _lib.check(_lib.lib().yy_unpack_boards(rows, cols, _ptr(black), _ptr(white), _ptr(mask), _ptr(ob), _ptr(om), B, _stream()))
-    return (ob.cpu().numpy().reshape(B, rows, cols) if ob is not None else None, om.cpu().numpy() if om is not None else None)
+    hb, hm = _to_host(ob, om)
+    return (hb.reshape(B, rows, cols) if hb is not None else None, hm)
 
 
 def _boards_to_dev(boards, rows, cols):
@@ -205,7 +222,8 @@ def env_step_host(boards, players, actions, rows, cols, rule_flags=0):
     else:
         bits = bitboard.unpack_bits(mask.cpu().numpy().view(np.uint64), rows, cols)
         nb = bitboard.unpack_boards(bd.cpu().numpy().view(np.uint64), wd.cpu().numpy().view(np.uint64), rows, cols)
-    return bits, nb, pd.cpu().numpy(), result_from_code(res.cpu().numpy())
+    hp, hr = _to_host(pd, res)
+    return bits, nb, hp, result_from_code(hr)
 
 
 def next_state_host(boards, players, actions, rows, cols, rule_flags=0):
@@ -345,7 +363,7 @@ class Engine:
         cw = torch.empty((self.n_games, self.A), dtype=torch.float32, device=self.tdev)
         c2 = torch.empty_like(counts)
         _lib.check(self.L.yy_search_counts(self.handle, _ptr(c2), _ptr(cw), _stream()))
-        return counts.cpu().numpy(), cw.cpu().numpy()
+        return _to_host(counts, cw)
 
     # -- external-evaluator stepping
     def search_begin(self, black, white, players, noise=None, noise_mask=None):
