@@ -154,7 +154,7 @@ def run_b200(args):
     import torch.distributed as dist
     import yy_b200  # noqa: F401
     from yinyang_game_alphazero_b200 import engine, weights, distributed as yyd
-    from oracle import port  # only build_net (the reference initialisation) and the cpu_baseline leg use it
+    from yinyang_game_alphazero_b200 import network
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -166,7 +166,7 @@ def run_b200(args):
 
     # weights: reference init on rank 0, packed, broadcast over NCCL (north star: weights broadcast)
     torch.manual_seed(0)
-    sd = port.build_net(ROWS, COLS, CHANNELS, BLOCKS).state_dict()
+    sd = network._Params(ROWS, COLS, CHANNELS, BLOCKS).state_dict()   # reference layout + initialisation (neural_network.py:39-92)
     eng = engine.Engine(rows=ROWS, cols=COLS, n_games=GAMES_PER_GPU, n_sims=SIMS, evaluator="nn", state_dict=sd,
                         seed=0xC0FFEE + rank, replay_capacity=GAMES_PER_GPU * (args.steps + args.warmup + 2))
     t_bcast = yyd.broadcast_weights(eng) if world > 1 else 0.0
@@ -404,11 +404,10 @@ def bench_learner_dp(engine, torch, world):
     """Data-parallel learner over all ranks (weak scaling: batch 64 per GPU): every step = backward graph, one NCCL
     all-reduce of the 14.5 MB flat gradient buffer, Adam graph.  Max over ranks of the device time."""
     import torch.distributed as dist
-    from yinyang_game_alphazero_b200 import learner as lrn
-    from oracle import port
+    from yinyang_game_alphazero_b200 import learner as lrn, network
     B = 64
     torch.manual_seed(0)
-    net = port.build_net(ROWS, COLS, 128, 10)
+    net = network._Params(ROWS, COLS, 128, 10)
     rank = dist.get_rank()
     plies = torch.arange(B, dtype=torch.int32) % 52
     black, white, _ = engine.random_playout(B, plies, ROWS, COLS, seed=0x1EA2 + rank)
@@ -471,11 +470,10 @@ def bench_learner(engine, torch, peaks):
     """optimisation steps of the reference trainer (trainer.py:120-137; batch 64, Adam) on the 128x10 network,
     8x8 boards: one CUDA-graph replay of the yy_lrn_* kernels per step.  Tensor bound on paper, latency bound in fact."""
     import numpy as np
-    from yinyang_game_alphazero_b200 import learner as lrn, _lib
-    from oracle import port
+    from yinyang_game_alphazero_b200 import learner as lrn, _lib, network
     B = 64
     torch.manual_seed(0)
-    net = port.build_net(ROWS, COLS, 128, 10)                  # reference initialisation only
+    net = network._Params(ROWS, COLS, 128, 10)                 # reference layout + initialisation
     n_rec = 256
     plies = torch.arange(n_rec, dtype=torch.int32) % 52
     black, white, _ = engine.random_playout(n_rec, plies, ROWS, COLS, seed=0x1EA2)
@@ -547,6 +545,7 @@ def bench_learner(engine, torch, peaks):
                             "total_loss_per_epoch": [float(x) for x in m["total_loss"]]}
     # CPU baseline: the same step as the reference runs it (oracle/port.py training_step = trainer.py:120-137 in fp32 torch),
     # on this box's host cores with torch's own intra-op threading
+    from oracle import port                                    # cpu_baseline leg: the one place the bench runs the oracle
     cpu_net = port.build_net(ROWS, COLS, 128, 10)
     cpu_opt = torch.optim.Adam(cpu_net.parameters(), lr=1e-3, weight_decay=1e-4)
     hp, hq, hv = planes[:B].cpu(), pol[:B].cpu(), val[:B].cpu()

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import yy_b200  # noqa
 from yinyang_game_alphazero_b200 import engine
-from oracle import port
+from yinyang_game_alphazero_b200 import network
 
 FLOPS_PER_LEAF = {(8, 8): 380584448, (6, 6): 214014464, (16, 16): 1525481984}
 n = m = int(os.environ.get("YY_N", 16))
@@ -13,7 +13,7 @@ games = int(os.environ.get("YY_GAMES", 592))
 sims = int(os.environ.get("YY_SIMS", 1600))
 plies = int(os.environ.get("YY_PLIES", 2))
 torch.manual_seed(0)
-net = port.build_net(n, m, 128, 10).eval()
+net = network._Params(n, m, 128, 10).eval()
 e = engine.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="nn", state_dict=net.state_dict(), seed=1)
 e.selfplay_run(1)
 torch.cuda.synchronize()

@@ -5,13 +5,13 @@ import numpy as np
 import torch
 import yy_b200  # noqa
 from yinyang_game_alphazero_b200 import engine
-from oracle import port
+from yinyang_game_alphazero_b200 import network
 
 n = m = 8
 games = int(os.environ.get("YY_GAMES", 4096))
 sims = int(os.environ.get("YY_SIMS", 200))
 torch.manual_seed(0)
-net = port.build_net(n, m, 128, 10).eval()
+net = network._Params(n, m, 128, 10).eval()
 e = engine.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="nn", state_dict=net.state_dict(), seed=1)
 e.selfplay_run(int(os.environ.get("YY_PLIES", 3)))
 torch.cuda.synchronize()

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 import yy_b200  # noqa
 from yinyang_game_alphazero_b200 import engine
-from oracle import port
+from yinyang_game_alphazero_b200 import network
 
 FLOPS_PER_LEAF = {(8, 8): 380584448, (6, 6): 214014464, (16, 16): 1525481984}
 
@@ -15,7 +15,7 @@ def main():
     games = int(os.environ.get("YY_GAMES", 4096))
     sims = int(os.environ.get("YY_SIMS", 64))
     torch.manual_seed(0)
-    net = port.build_net(n, m, 128, 10).eval()
+    net = network._Params(n, m, 128, 10).eval()
     e = engine.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="nn", state_dict=net.state_dict(), seed=1)
     plies = torch.arange(games, dtype=torch.int32) % (n * m * 4 // 5)
     black, white, players = engine.random_playout(games, plies, n, m)

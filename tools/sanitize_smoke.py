@@ -1,6 +1,7 @@
-"""Developer tool: one small invocation of every kernel family, meant to be run under compute-sanitizer
-(`compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitize_smoke.py [part ...]`).
-Sizes are tiny because the sanitizer slows kernels down 10-100x; correctness of the results is the job of tests/.
+"""Developer tool: one small invocation of every kernel family at odd sizes (partial blocks, non-square and 16x16
+boards, remainder batches) -- a quick crash / overflow check after a kernel change, and the driver for
+`compute-sanitizer --tool memcheck python tools/sanitize_smoke.py [part ...]` where the sanitizer may be run (it is closed
+on the round-1 GPU pool: gpurun refuses it).  Correctness of the results is the job of tests/.
 Parts: rules, dataset, tree, nn, selfplay, learner (default: all)."""
 import os
 import sys

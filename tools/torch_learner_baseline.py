@@ -3,11 +3,12 @@ eager, TF32 convolutions on/off) -- a library baseline next to the hand-written 
 import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import port
+import yy_b200  # noqa
+from yinyang_game_alphazero_b200 import network
 
 torch.manual_seed(0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-net = port.build_net(8, 8, 128, 10).cuda().train()
+net = network._Params(8, 8, 128, 10).cuda().train()
 opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
 planes = torch.rand(B, 5, 8, 8, device="cuda"); pi = torch.softmax(torch.randn(B, 64, device="cuda"), 1); z = torch.rand(B, device="cuda") * 2 - 1
 ce, mse = torch.nn.CrossEntropyLoss(), torch.nn.MSELoss()
