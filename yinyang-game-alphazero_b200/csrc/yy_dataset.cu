@@ -9,29 +9,43 @@
 // float64 quotients rounded to float32 (Python float -> torch.float32), the forms are pure permutations => bit-exact.
 //
 // Roofline: HBM, write bound.  Algorithmic bytes per record = 16W + 2A + 4 read, 8*(6A + 1)*4 written
-// (12,452 B at 8x8).  One warp per record; every store instruction writes 32 consecutive floats.
+// (12,468 B at 8x8).  One warp per record; every store instruction writes 32 consecutive floats.
 #include "yy_common.cuh"
 
 namespace yy {
 
 constexpr int kDatasetBlock = 256;   // 8 records per CTA
+constexpr int kDatasetWarps = kDatasetBlock / 32;
 
-template <int NW>
-__global__ void __launch_bounds__(kDatasetBlock)
+// One warp per record, two phases.  (1) The six source planes of the record (empty, black, white, row fill, column
+// fill, policy) are computed ONCE per cell into the warp's slice of shared memory -- this is where the float64
+// quotients are.  (2) The 8 forms are pure permutations of those planes: every output element is one shared-memory
+// load and one streaming store (32 consecutive floats per store instruction; the output is written once and far
+// exceeds L2).  The first version recomputed the quotients for each of the 8 forms and was bound by FP64 issue, not HBM.
+__host__ __device__ inline int dataset_smem_floats(int A) { return 6 * A + 64; }   // per warp: planes + row / column fractions
+
+// M = board side when it is one of the common sizes (all offsets become immediates), 0 = read it from g.
+template <int NW, int M>
+__global__ void __launch_bounds__(kDatasetBlock, 4)
 augment_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint64_t* __restrict__ white,
                const uint16_t* __restrict__ counts, const float* __restrict__ policy_in, const float* __restrict__ values,
                long long count, float* __restrict__ out_planes, float* __restrict__ out_policy, float* __restrict__ out_values) {
-  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (r >= count) return;
-  const int n = g.rows, m = g.cols, A = g.cells;
+  extern __shared__ float s_dataset[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * kDatasetWarps + warp;
+  if (r >= count) return;                       // whole warps leave; only warp-level synchronisation below
+  const int n = M ? M : g.rows, m = M ? M : g.cols, A = M ? M * M : g.cells;
+  float* src = s_dataset + warp * dataset_smem_floats(A);
+  float* rowv = src + 6 * A;                    // [32] fill fraction of row x
+  float* colv = rowv + 32;                      // [32] fill fraction of column y
   const BB<NW> b = load_bb<NW>(black, r, W) & g.full, w = load_bb<NW>(white, r, W) & g.full;
   const BB<NW> occ = b | w;
-  // row / column fill fractions (neural_network.py:183-194): lane x holds row x's, lane y column y's  (n, m <= 32)
+  // row / column fill fractions (neural_network.py:183-194): lane x computes row x's, lane y column y's  (n, m <= 32)
   int rc = 0, cc = 0;
   for (int y = 0; y < m; ++y) rc += (lane < n && test(occ, lane * m + y)) ? 1 : 0;
   for (int x = 0; x < n; ++x) cc += (lane < m && test(occ, x * m + lane)) ? 1 : 0;
-  const float rowf = (float)((double)rc / (double)m), colf = (float)((double)cc / (double)n);
+  rowv[lane] = (float)((double)rc / (double)m);
+  colv[lane] = (float)((double)cc / (double)n);
   // policy = visit counts / their sum in float64 (uniform when there is no visit, mcts.py:209-213), then float32
   unsigned total = 0;
   if (counts) {
@@ -39,16 +53,29 @@ augment_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint6
     for (int off = 16; off; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
   }
   const float uniform = (float)(1.0 / (double)A);
-  const float v = values ? values[r] : 0.0f;
-  if (lane < 8 && out_values) out_values[r * 8 + lane] = v;
-  for (int f = 0; f < 8; ++f) {
-    float* planes = out_planes + (r * 8 + f) * 5ll * A;
-    float* pol = out_policy + (r * 8 + f) * (long long)A;
-    for (int a0 = 0; a0 < A; a0 += 32) {
-      const int a = a0 + lane;
-      const bool live = a < A;
-      const int i = live ? a / m : 0, j = live ? a - i * m : 0;
-      int sx, sy;   // source cell of output cell (i, j)   (square boards: n == m)
+  if (lane < 8 && out_values) out_values[r * 8 + lane] = values ? values[r] : 0.0f;
+  __syncwarp();
+  for (int s = lane; s < A; s += 32) {          // phase 1: the identity form, once per cell
+    const int sx = s / m, sy = s - sx * m;
+    const bool isb = test(b, s), isw = test(w, s);
+    src[s] = (isb || isw) ? 0.0f : 1.0f;
+    src[A + s] = isb ? 1.0f : 0.0f;
+    src[2 * A + s] = isw ? 1.0f : 0.0f;
+    src[3 * A + s] = rowv[sx];
+    src[4 * A + s] = colv[sy];
+    float p;
+    if (counts) p = total ? (float)((double)counts[r * A + s] / (double)total) : uniform;
+    else p = policy_in[r * A + s];
+    src[5 * A + s] = p;
+  }
+  __syncwarp();
+  float* planes0 = out_planes + r * 40ll * A;   // [8 forms][5 planes][A]
+  float* pol0 = out_policy + r * 8ll * A;       // [8 forms][A]
+  for (int a = lane; a < A; a += 32) {          // phase 2: output cell (i, j) of form f <- source cell (sx, sy)
+    const int i = a / m, j = a - i * m;         // (square boards: n == m)
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+      int sx, sy;
       switch (f) {
         case 0: sx = i; sy = j; break;
         case 1: sx = j; sy = m - 1 - i; break;             // np.rot90(S, 1)[i][j] = S[j][m-1-i]
@@ -59,20 +86,11 @@ augment_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint6
         case 6: sx = j; sy = i; break;                     // transpose
         default: sx = n - 1 - j; sy = m - 1 - i; break;    // flip(transpose, both axes)
       }
-      const int s = sx * m + sy;
-      const float rf = __shfl_sync(0xffffffffu, rowf, sx), cf = __shfl_sync(0xffffffffu, colf, sy);
-      if (live) {
-        const bool isb = test(b, s), isw = test(w, s);
-        planes[a] = (isb || isw) ? 0.0f : 1.0f;
-        planes[A + a] = isb ? 1.0f : 0.0f;
-        planes[2 * A + a] = isw ? 1.0f : 0.0f;
-        planes[3 * A + a] = rf;
-        planes[4 * A + a] = cf;
-        float p;
-        if (counts) p = total ? (float)((double)counts[r * A + s] / (double)total) : uniform;
-        else p = policy_in[r * A + s];
-        pol[a] = p;
-      }
+      const float* sp = src + (sx * m + sy);
+      float* planes = planes0 + f * 5 * A + a;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) __stcs(planes + k * A, sp[k * A]);
+      __stcs(pol0 + f * A + a, sp[5 * A]);
     }
   }
 }
@@ -91,9 +109,20 @@ extern "C" int yy_augment_samples(int rows, int cols, const uint64_t* black, con
   if (count == 0) return YY_OK;     // empty replay buffer: nothing to write (pointers may be null)
   if (!black || !white || (!counts && !policy) || !out_planes || !out_policy) return set_error(YY_ERR_INVALID, "null argument");
   const int cells = rows * cols, W = words_for_cells(cells);
-  const unsigned grid = (unsigned)((count * 32 + kDatasetBlock - 1) / kDatasetBlock);
-  YY_DISPATCH_NW(cells, augment_kernel<NW><<<grid, kDatasetBlock, 0, (cudaStream_t)stream>>>(
-      make_geo<NW>(rows, cols, 0), W, black, white, counts, policy, values, count, out_planes, out_policy, out_values));
+  const unsigned grid = (unsigned)((count + kDatasetWarps - 1) / kDatasetWarps);
+  const size_t smem = (size_t)kDatasetWarps * dataset_smem_floats(cells) * sizeof(float);   // <= 50,176 B at 256 cells
+#define YY_AUGMENT_LAUNCH(NWV, MV)                                                                                      \
+  do {                                                                                                                  \
+    if (smem > 48 * 1024)                                                                                               \
+      cudaFuncSetAttribute(augment_kernel<NWV, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+    augment_kernel<NWV, MV><<<grid, kDatasetBlock, smem, (cudaStream_t)stream>>>(                                       \
+        make_geo<NWV>(rows, cols, 0), W, black, white, counts, policy, values, count, out_planes, out_policy, out_values); \
+  } while (0)
+  if (rows == 8) YY_AUGMENT_LAUNCH(1, 8);
+  else if (rows == 6) YY_AUGMENT_LAUNCH(1, 6);
+  else if (rows == 16) YY_AUGMENT_LAUNCH(4, 16);
+  else YY_DISPATCH_NW(cells, YY_AUGMENT_LAUNCH(NW, 0));
+#undef YY_AUGMENT_LAUNCH
   YY_LAUNCH_CHECK();
   return YY_OK;
 }

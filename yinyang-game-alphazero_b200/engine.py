@@ -94,20 +94,27 @@ def env_step(black, white, players, actions, rows, cols, rule_flags=0, out_mask=
     return out_mask, out_result
 
 
-def augment_samples(black, white, rows, cols, counts=None, policy=None, values=None):
+def augment_samples(black, white, rows, cols, counts=None, policy=None, values=None, out=None):
     """Replay records -> training tensors with the reference's 8-fold augmentation (yy_augment_samples; replaces
     data_utils.create_dataset_from_games).  Device tensors in: black/white int64[N,W], counts int16/uint16[N,A] (visit
     counts) or policy float32[N,A], values float32[N] (optional).  Returns device tensors
-    (planes float32[8N,5,n,m], policy float32[8N,A], values float32[8N] or None); sample 8r+f = form f of record r."""
+    (planes float32[8N,5,n,m], policy float32[8N,A], values float32[8N] or None); sample 8r+f = form f of record r.
+    ``out`` = a previous call's result tuple of the same sizes: written in place (no allocation of the 12 KB per record)."""
     _require_cuda()
     if (counts is None) == (policy is None):
         raise ValueError("give exactly one of counts / policy")
     n = black.shape[0]
     A = rows * cols
     dev = black.device
-    planes = torch.empty((8 * n, 5, rows, cols), dtype=torch.float32, device=dev)
-    pol = torch.empty((8 * n, A), dtype=torch.float32, device=dev)
-    vals = torch.empty(8 * n, dtype=torch.float32, device=dev) if values is not None else None
+    if out is not None:
+        planes, pol, vals = out
+        assert planes.is_contiguous() and pol.is_contiguous() and planes.dtype == pol.dtype == torch.float32
+        assert planes.numel() == 8 * n * 5 * A and pol.numel() == 8 * n * A and planes.device == pol.device == dev
+        assert (vals is None) == (values is None) and (vals is None or (vals.numel() == 8 * n and vals.dtype == torch.float32))
+    else:
+        planes = torch.empty((8 * n, 5, rows, cols), dtype=torch.float32, device=dev)
+        pol = torch.empty((8 * n, A), dtype=torch.float32, device=dev)
+        vals = torch.empty(8 * n, dtype=torch.float32, device=dev) if values is not None else None
     if counts is not None:
         counts = counts.contiguous()
         assert counts.element_size() == 2 and counts.numel() == n * A
