@@ -297,6 +297,40 @@ def test_network_search_persistent_vs_step_kernels(eng, oracle_mod):
     assert np.array_equal(c0, c1) and np.array_equal(w0, w1)
 
 
+def test_search_full_config3_replica_properties(eng, oracle_mod):
+    """BASELINE.json configs[2] at full size (8x8, 800 simulations, 4,096 concurrent games, 128x10 network) through
+    size-independent properties: 64 distinct positions are each given to 64 of the 4,096 slots in a shuffled order.
+    (1) every replica of a position returns the same visit counts and child value sums bit for bit, whichever slot /
+    CTA pair / SM searched it; (2) the same 64 positions searched by a 64-game engine give those counts too (batch-size
+    independence); (3) every search with a legal move spends exactly 800 simulations on legal actions only."""
+    import torch
+    from oracle import port
+    n = m = 8
+    games, sims, distinct = 4096, 800, 64
+    torch.manual_seed(5)
+    net = randomise_bn(port.build_net(n, m, 128, 10))
+    base_b, base_p = random_play_boards(oracle_mod, n, m, distinct, seed=123, max_frac=0.7)
+    base_b[0] = 0; base_p[0] = 1                                  # the empty board (the benchmark's root) is one of them
+    slot_pos = np.random.default_rng(9).permutation(np.repeat(np.arange(distinct), games // distinct))
+    e = eng.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="nn", state_dict=net.state_dict())
+    counts, cw = e.search_host(base_b[slot_pos], base_p[slot_pos])
+    st = e.stats()
+    e.close()
+    assert st.overflow == 0
+    legal = oracle_mod.legal_mask(base_b, base_p, n, m).astype(bool)
+    for k in range(distinct):
+        rep = np.flatnonzero(slot_pos == k)
+        assert np.all(counts[rep] == counts[rep[0]]), f"position {k}: replicas disagree on visit counts"
+        assert np.all(cw[rep] == cw[rep[0]]), f"position {k}: replicas disagree on value sums"
+        c = counts[rep[0]]
+        assert c.sum() == (sims if legal[k].any() else 0) and not c[~legal[k]].any()
+    small = eng.Engine(rows=n, cols=m, n_games=distinct, n_sims=sims, evaluator="nn", state_dict=net.state_dict())
+    c2, w2 = small.search_host(base_b, base_p)
+    small.close()
+    first = np.array([np.flatnonzero(slot_pos == k)[0] for k in range(distinct)])
+    assert np.array_equal(c2, counts[first]) and np.array_equal(w2, cw[first])
+
+
 # ------------------------------------------------------------------------------------------------ dataset / augmentation
 @pytest.mark.parametrize("name", golden_files("augment_"))
 def test_augmentation_matches_reference_golden(eng, name):
