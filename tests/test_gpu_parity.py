@@ -297,16 +297,19 @@ def test_network_search_persistent_vs_step_kernels(eng, oracle_mod):
     assert np.array_equal(c0, c1) and np.array_equal(w0, w1)
 
 
-def test_search_full_config3_replica_properties(eng, oracle_mod):
-    """BASELINE.json configs[2] at full size (8x8, 800 simulations, 4,096 concurrent games, 128x10 network) through
+@pytest.mark.parametrize("n,sims", [(8, 800), (16, 1600), (6, 100)])
+def test_search_full_config_replica_properties(eng, oracle_mod, n, sims):
+    """BASELINE.json configs[2] at full size (8x8, 800 simulations, 4,096 concurrent games, 128x10 network), configs[4]'s
+    per-GPU share (16x16, 1,600 simulations, 4,096 of the 32,768 games) and configs[0]'s board and budget (6x6, 100
+    simulations) at 4,096 games, through
     size-independent properties: 64 distinct positions are each given to 64 of the 4,096 slots in a shuffled order.
     (1) every replica of a position returns the same visit counts and child value sums bit for bit, whichever slot /
     CTA pair / SM searched it; (2) the same 64 positions searched by a 64-game engine give those counts too (batch-size
     independence); (3) every search with a legal move spends exactly 800 simulations on legal actions only."""
     import torch
     from oracle import port
-    n = m = 8
-    games, sims, distinct = 4096, 800, 64
+    m = n
+    games, distinct = 4096, 64
     torch.manual_seed(5)
     net = randomise_bn(port.build_net(n, m, 128, 10))
     base_b, base_p = random_play_boards(oracle_mod, n, m, distinct, seed=123, max_frac=0.7)
