@@ -65,13 +65,21 @@ ended_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint64_
 // shared memory, so the lanes of a warp get boards of similar cost; results go back to the boards' own slots.
 constexpr int kEnvBins = 64;
 
-template <int NW, int BLOCK, bool SORT>
+// SIDE = n for the common square boards (6, 8, 16): rows, cols and cells become compile-time constants, so the
+// row shifts of the dilations are immediate funnel shifts (a 64-bit shift by a run-time count costs three times as many
+// instructions) and the per-word loops have known trip counts; SIDE = 0 reads the geometry from g.
+template <int NW, int BLOCK, bool SORT, int SIDE>
 __global__ void __launch_bounds__(BLOCK)
 env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __restrict__ white,
                 int8_t* __restrict__ players, const int32_t* __restrict__ actions, uint64_t* __restrict__ out_mask,
                 int8_t* __restrict__ out_result, long long count) {
   constexpr int BOARDS = BLOCK / 2;
   static_assert(BOARDS > kEnvBins, "one thread per histogram bin");
+  if (SIDE) {
+    g.rows = SIDE; g.cols = SIDE; g.cells = SIDE * SIDE;
+    if (SIDE * SIDE == 64 * NW) for (int k = 0; k < NW; ++k) g.full.w[k] = ~0ull;
+  }
+  if (NW <= 2) W = NW;                          // words_for_cells == NW unless the board has 129..192 cells
   __shared__ int s_hist[kEnvBins + 1];
   __shared__ int s_off[kEnvBins + 1];
   __shared__ uint16_t s_order[BOARDS];        // sorted position -> board of this block
@@ -268,13 +276,20 @@ int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64
   static const int force = [] { const char* e = getenv("YY_ENV_SORT"); return e ? atoi(e) : -1; }();
   const bool sort = force < 0 ? true : force != 0;
   unsigned grid = (unsigned)((count + 127) / 128);
+#define YY_ENV_LAUNCH(NWV, SORTV, SIDEV)                                                              \
+  env_step_kernel<NWV, 256, SORTV, SIDEV><<<grid, 256, 0, (cudaStream_t)stream>>>(                      \
+      make_geo<NWV>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count)
+  const int side = rows == cols ? rows : 0;
   if (sort) {
-    YY_DISPATCH_NW(cells, env_step_kernel<NW, 256, true><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count));
+    if (side == 8) YY_ENV_LAUNCH(1, true, 8);
+    else if (side == 6) YY_ENV_LAUNCH(1, true, 6);
+    else if (side == 16) YY_ENV_LAUNCH(4, true, 16);
+    else YY_DISPATCH_NW(cells, YY_ENV_LAUNCH(NW, true, 0));
   } else {
-    YY_DISPATCH_NW(cells, env_step_kernel<NW, 256, false><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count));
+    if (side == 8) YY_ENV_LAUNCH(1, false, 8);
+    else YY_DISPATCH_NW(cells, YY_ENV_LAUNCH(NW, false, 0));
   }
+#undef YY_ENV_LAUNCH
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
