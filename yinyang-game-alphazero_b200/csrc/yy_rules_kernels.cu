@@ -63,7 +63,7 @@ ended_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint64_
 // number of stones) and a batch usually mixes game stages: in input order only 9 of 32 lanes were active per issued
 // instruction (ncu, BASELINE configs[1]).  Each block therefore first counting-sorts its boards by stone count in
 // shared memory, so the lanes of a warp get boards of similar cost; results go back to the boards' own slots.
-constexpr int kEnvBins = 64;
+constexpr int kEnvMaxBins = 64;
 
 // SIDE = n for the common square boards (6, 8, 16): rows, cols and cells become compile-time constants, so the
 // row shifts of the dilations are immediate funnel shifts (a 64-bit shift by a run-time count costs three times as many
@@ -74,7 +74,8 @@ env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __rest
                 int8_t* __restrict__ players, const int32_t* __restrict__ actions, uint64_t* __restrict__ out_mask,
                 int8_t* __restrict__ out_result, long long count) {
   constexpr int BOARDS = BLOCK / 2;
-  static_assert(BOARDS > kEnvBins, "one thread per histogram bin");
+  constexpr int kEnvBins = BOARDS > kEnvMaxBins ? kEnvMaxBins : 32;   // + one bin for the boards past the end
+  static_assert(BLOCK > kEnvBins && kEnvBins % 32 == 0, "one thread per histogram bin");
   if (SIDE) {
     g.rows = SIDE; g.cols = SIDE; g.cells = SIDE * SIDE;
     if (SIDE * SIDE == 64 * NW) for (int k = 0; k < NW; ++k) g.full.w[k] = ~0ull;
@@ -99,17 +100,21 @@ env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __rest
       rank = atomicAdd(&s_hist[key], 1);
     }
     __syncthreads();
-    if (tid < 32) {                             // exclusive scan of the 65 bins by one warp
-      int v0 = s_hist[tid], v1 = s_hist[tid + 32], v2 = tid == 0 ? s_hist[64] : 0;
-      int i0 = v0, i1 = v1;
+    if (tid < 32) {                             // exclusive scan of the kEnvBins + 1 bins by one warp, 32 bins at a time
+      int run = 0;
   #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int t0 = __shfl_up_sync(0xffffffffu, i0, d), t1 = __shfl_up_sync(0xffffffffu, i1, d);
-        if (tid >= d) { i0 += t0; i1 += t1; }
+      for (int seg = 0; seg <= kEnvBins / 32; ++seg) {
+        const int idx = seg * 32 + tid;
+        const int v = idx <= kEnvBins ? s_hist[idx] : 0;
+        int inc = v;
+  #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, d);
+          if (tid >= d) inc += t;
+        }
+        if (idx <= kEnvBins) s_off[idx] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
       }
-      int tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
-      s_off[tid] = i0 - v0; s_off[tid + 32] = tot0 + i1 - v1;
-      if (tid == 0) { s_off[64] = tot0 + tot1; (void)v2; }
     }
     __syncthreads();
     if (tid < BOARDS) s_order[s_off[key] + rank] = (uint16_t)tid;
@@ -275,10 +280,16 @@ int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64
   // forces the choice (developer A/B switch).
   static const int force = [] { const char* e = getenv("YY_ENV_SORT"); return e ? atoi(e) : -1; }();
   const bool sort = force < 0 ? true : force != 0;
-  unsigned grid = (unsigned)((count + 127) / 128);
-#define YY_ENV_LAUNCH(NWV, SORTV, SIDEV)                                                              \
-  env_step_kernel<NWV, 256, SORTV, SIDEV><<<grid, 256, 0, (cudaStream_t)stream>>>(                      \
+#define YY_ENV_LAUNCH_B(NWV, BLOCKV, SORTV, SIDEV)                                                          \
+  env_step_kernel<NWV, BLOCKV, SORTV, SIDEV><<<(unsigned)((count + BLOCKV / 2 - 1) / (BLOCKV / 2)), BLOCKV, 0, (cudaStream_t)stream>>>( \
       make_geo<NWV>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count)
+#define YY_ENV_LAUNCH(NWV, SORTV, SIDEV)                                                                     \
+  do { if (block == 128) YY_ENV_LAUNCH_B(NWV, 128, SORTV, SIDEV); else YY_ENV_LAUNCH_B(NWV, 256, SORTV, SIDEV); } while (0)
+  // 64 boards per block spread a batch more evenly over the 148 SMs than 128 (65,536 boards: 6.9 blocks per SM instead of
+  // 3.5, i.e. the fullest SM holds 1 % more than the average instead of 15 %): 6.5 against 7.1 us per launch, and still
+  // 4 % ahead at 1 M boards.  YY_ENV_BLOCK=128/256 forces the block size (developer A/B switch).
+  static const int force_block = [] { const char* e = getenv("YY_ENV_BLOCK"); return e ? atoi(e) : 0; }();
+  const int block = force_block == 256 ? 256 : 128;
   const int side = rows == cols ? rows : 0;
   if (sort) {
     if (side == 8) YY_ENV_LAUNCH(1, true, 8);
@@ -289,6 +300,7 @@ int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64
     if (side == 8) YY_ENV_LAUNCH(1, false, 8);
     else YY_DISPATCH_NW(cells, YY_ENV_LAUNCH(NW, false, 0));
   }
+#undef YY_ENV_LAUNCH_B
 #undef YY_ENV_LAUNCH
   YY_LAUNCH_CHECK();
   return YY_OK;
