@@ -84,20 +84,32 @@ env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __rest
   __shared__ int s_hist[kEnvBins + 1];
   __shared__ int s_off[kEnvBins + 1];
   __shared__ uint16_t s_order[BOARDS];        // sorted position -> board of this block
+  // everything a board needs is fetched in ONE round trip to DRAM, before the sort, and staged in shared memory: the
+  // lanes that analyse the board after the sort read it from there (a second dependent miss for players / actions
+  // would sit on the critical path of a 6 us kernel)
+  __shared__ uint64_t s_black[SORT ? BOARDS * NW : 1], s_white[SORT ? BOARDS * NW : 1];
+  __shared__ int32_t s_action[SORT ? BOARDS : 1];
+  __shared__ int8_t s_player[SORT ? BOARDS : 1];
   const int tid = threadIdx.x;
   const long long base = (long long)blockIdx.x * BOARDS;
   if (SORT) {
+    BB<NW> mb = bb_zero<NW>(), mw = bb_zero<NW>();
+    int mp = 1, ma = -1;
+    const bool mlive = tid < BOARDS && base + tid < count;
+    if (mlive) {
+      const long long mine = base + tid;
+      mb = load_bb<NW>(black, mine, W); mw = load_bb<NW>(white, mine, W);
+      mp = players[mine]; ma = actions[mine];
+    }
     if (tid <= kEnvBins) s_hist[tid] = 0;
     __syncthreads();
     int key = kEnvBins, rank = 0;               // boards past the end sort last
     if (tid < BOARDS) {
-      const long long mine = base + tid;
-      if (mine < count) {
-        int stones = 0;
-        for (int k = 0; k < W; ++k) stones += popc64(black[mine * W + k] | white[mine * W + k]);
-        key = stones * kEnvBins / (g.cells + 1);
-      }
+      if (mlive) key = popcount(mb | mw) * kEnvBins / (g.cells + 1);
       rank = atomicAdd(&s_hist[key], 1);
+  #pragma unroll
+      for (int k = 0; k < NW; ++k) { s_black[tid * NW + k] = mb.w[k]; s_white[tid * NW + k] = mw.w[k]; }
+      s_player[tid] = (int8_t)mp; s_action[tid] = ma;
     }
     __syncthreads();
     if (tid < 32) {                             // exclusive scan of the kEnvBins + 1 bins by one warp, 32 bins at a time
@@ -122,13 +134,21 @@ env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __rest
   }
 
   const int side = tid & 1;                   // 0: the mover's colour, 1: the other colour
-  const long long i = base + (SORT ? (int)s_order[tid >> 1] : (tid >> 1));
+  const int loc = SORT ? (int)s_order[tid >> 1] : (tid >> 1);
+  const long long i = base + loc;
   const bool live = i < count;                // both lanes of a pair agree; nobody leaves before the shuffles
   BB<NW> b = bb_zero<NW>(), w = bb_zero<NW>();
   int praw = 1, a = -1;
   if (live) {
-    b = load_bb<NW>(black, i, W) & g.full; w = load_bb<NW>(white, i, W) & g.full;
-    praw = players[i]; a = actions[i];
+    if (SORT) {
+  #pragma unroll
+      for (int k = 0; k < NW; ++k) { b.w[k] = s_black[loc * NW + k]; w.w[k] = s_white[loc * NW + k]; }
+      b = b & g.full; w = w & g.full;
+      praw = s_player[loc]; a = s_action[loc];
+    } else {
+      b = load_bb<NW>(black, i, W) & g.full; w = load_bb<NW>(white, i, W) & g.full;
+      praw = players[i]; a = actions[i];
+    }
   }
   const int p = praw == 1 ? 1 : -1;
   const bool mine_black = (p == 1) == (side == 0);
