@@ -53,8 +53,16 @@ template <int NW> YY_HD BB<NW> andnot(BB<NW> a, BB<NW> b) { for (int i = 0; i < 
 template <int NW> YY_HD bool any(BB<NW> a) { uint64_t o = 0; for (int i = 0; i < NW; ++i) o |= a.w[i]; return o != 0; }
 template <int NW> YY_HD bool same(BB<NW> a, BB<NW> b) { uint64_t o = 0; for (int i = 0; i < NW; ++i) o |= a.w[i] ^ b.w[i]; return o == 0; }
 template <int NW> YY_HD int popcount(BB<NW> a) { int c = 0; for (int i = 0; i < NW; ++i) c += popc64(a.w[i]); return c; }
-template <int NW> YY_HD bool test(const BB<NW>& a, int bit) { return (a.w[bit >> 6] >> (bit & 63)) & 1ull; }
-template <int NW> YY_HD void setbit(BB<NW>& a, int bit) { a.w[bit >> 6] |= 1ull << (bit & 63); }
+// The word is picked by a chain of selects, not by indexing: a run-time index would put the board in local memory.
+template <int NW> YY_HD bool test(const BB<NW>& a, int bit) {
+  uint64_t word = a.w[0];
+  for (int i = 1; i < NW; ++i) word = (bit >> 6) == i ? a.w[i] : word;
+  return (word >> (bit & 63)) & 1ull;
+}
+template <int NW> YY_HD void setbit(BB<NW>& a, int bit) {
+  const uint64_t one = 1ull << (bit & 63);
+  for (int i = 0; i < NW; ++i) a.w[i] |= (bit >> 6) == i ? one : 0ull;
+}
 // lowest set bit as a one-bit board (a must be non-zero)
 template <int NW> YY_HD BB<NW> lowest(BB<NW> a) {
   BB<NW> r = bb_zero<NW>();
