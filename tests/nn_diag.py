@@ -1,7 +1,8 @@
-"""Developer diagnostic: kernel vs numpy emulation vs fp32 torch, error statistics per configuration."""
+"""Developer diagnostic (test infrastructure: it runs the oracle as the checker, so it lives under tests/): kernel vs numpy
+emulation vs fp32 torch, error statistics per configuration.  Run by hand on a GPU box: `python tests/nn_diag.py`."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np, torch
 import yy_b200  # noqa
 from yinyang_game_alphazero_b200 import engine, weights
