@@ -120,6 +120,11 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import oracle|from oracle)|#include\s*[\"<][^\n]*oracle|dlopen[^\n]*oracle",
                                      src, flags=re.M), f
+    # developer tools and the CLI are not checkers either: only tests/, smoke() and bench.py's CPU legs run the oracle
+    extra = [os.path.join(ROOT, "train_alphazero.py"), os.path.join(ROOT, "yy_b200.py")]
+    extra += [os.path.join(ROOT, "tools", f) for f in os.listdir(os.path.join(ROOT, "tools")) if f.endswith(".py")]
+    for path in extra:
+        assert not re.search(r"^\s*(import oracle|from oracle)", open(path).read(), flags=re.M), path
 
 
 @pytest.mark.parametrize("cfg", [(6, 6, 16, 2), (8, 8, 128, 1), (5, 7, 32, 1)])
