@@ -68,8 +68,11 @@ def play_games(game, state_dict, num_games, num_simulations=800, temperature_thr
         eng.close()
     games = []
     order = np.lexsort((rp["ply"], rp["game_serial"]))
+    serial_sorted = rp["game_serial"][order]
+    lo = np.searchsorted(serial_sorted, np.arange(num_games), side="left")     # records of game g: order[lo[g]:hi[g]]
+    hi = np.searchsorted(serial_sorted, np.arange(num_games), side="right")
     for g in range(num_games):
-        idx = order[rp["game_serial"][order] == g]
+        idx = order[lo[g]:hi[g]]
         ex = []
         for i in idx:
             if not rp["finished"][i]:
