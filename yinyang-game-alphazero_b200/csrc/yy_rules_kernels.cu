@@ -235,8 +235,7 @@ __global__ void __launch_bounds__(256) unpack_boards_kernel(const uint64_t* __re
 static int check_rules_args(int rows, int cols, long long count) {
   if (!board_supported(rows, cols)) return set_error(YY_ERR_INVALID, "unsupported board %dx%d (need <=32 per side, <=256 cells)", rows, cols);
   if (count < 0) return set_error(YY_ERR_INVALID, "negative count");
-  int nd = 0;
-  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) { cudaGetLastError(); return set_error(YY_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback"); }
+  if (yy_device_count() == 0) return set_error(YY_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
   return YY_OK;
 }
 
@@ -249,8 +248,12 @@ extern "C" {
 int yy_abi_version(void) { return YY_ABI_VERSION; }
 const char* yy_last_error(void) { return yy::error_buffer(); }
 int yy_device_count(void) {
-  int n = 0;
+  static std::atomic<int> seen{0};              // a positive answer is final: every entry point asks, once is enough
+  int n = seen.load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (n > 0) seen.store(n, std::memory_order_relaxed);
   return n;
 }
 int64_t yy_launch_count(void) { return (int64_t)yy::g_launches.load(); }

@@ -25,9 +25,16 @@ RESULT_DRAW_CODE = 2
 DRAW_VALUE = 0.0001  # yin_yang_game.py:107
 
 
+_cuda_seen = False
+
+
 def _require_cuda():
+    global _cuda_seen
+    if _cuda_seen:                               # a device that was there stays there: ask once, not on every call
+        return
     if not torch.cuda.is_available() or _lib.lib().yy_device_count() == 0:
         raise _lib.YinYangError("no CUDA device: the B200 engine has no CPU fallback")
+    _cuda_seen = True
 
 
 def _ptr(t):
