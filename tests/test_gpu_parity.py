@@ -366,6 +366,25 @@ def test_augmentation_matches_oracle(eng, oracle_mod, shape, count):
         np.testing.assert_allclose(pol.sum(axis=1), 1.0, atol=1e-5)
 
 
+def test_augmentation_into_caller_buffers(eng, oracle_mod):
+    """out= : the second call writes into the first call's tensors (caller-allocated outputs, as over the C ABI)."""
+    import torch
+    n = 8
+    rng = np.random.default_rng(4)
+    b1, p1 = random_play_boards(oracle_mod, n, n, 300, seed=31)
+    b2, p2 = random_play_boards(oracle_mod, n, n, 300, seed=32)
+    c1 = rng.integers(0, 800, size=(300, n * n)).astype(np.uint16); c2 = rng.integers(0, 800, size=(300, n * n)).astype(np.uint16)
+    v = torch.ones(300, device="cuda")
+    dev = lambda boards: eng.pack_boards_dev(boards, n, n)
+    cnt = lambda c: torch.from_numpy(c.view(np.int16)).cuda()
+    out = eng.augment_samples(*dev(b1), n, n, counts=cnt(c1), values=v)
+    ptrs = [t.data_ptr() for t in out]
+    out2 = eng.augment_samples(*dev(b2), n, n, counts=cnt(c2), values=v, out=out)
+    assert [t.data_ptr() for t in out2] == ptrs
+    rp, rq, rv = oracle_mod.augment_dataset(b2, c2, np.ones(300), n, n)
+    assert np.array_equal(out2[0].cpu().numpy(), rp) and np.array_equal(out2[1].cpu().numpy(), rq) and np.array_equal(out2[2].cpu().numpy(), rv)
+
+
 def test_augmentation_rejects_non_square(eng):
     from yinyang_game_alphazero_b200 import YinYangError
     with pytest.raises(YinYangError):
