@@ -207,3 +207,20 @@ def test_cli_imports_in_a_fresh_process(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(root, "train_alphazero.py"), "--mode", "self-play", "--model-dir", str(tmp_path / "m"),
                         "--data-dir", str(tmp_path / "d")], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert r.returncode == 1 and "ImportError" not in r.stderr, r.stderr[-1500:]
+
+
+def test_bench_reference_arm_prints_the_contract_line(tmp_path):
+    """`bench.py --impl reference` (the driver's reference arm) runs on host cores only and prints ONE JSON line with the
+    same metric / unit / config keys as the B200 arm plus impl, cpu_baseline and an e2e object with zero copy bytes."""
+    import json, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "moves/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"].startswith("self-play moves/sec") and "configs[2]" in d["config"]["workload"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["steps"] == 1
