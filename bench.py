@@ -168,7 +168,7 @@ def run_b200(args):
     torch.manual_seed(0)
     sd = network._Params(ROWS, COLS, CHANNELS, BLOCKS).state_dict()   # reference layout + initialisation (neural_network.py:39-92)
     eng = engine.Engine(rows=ROWS, cols=COLS, n_games=GAMES_PER_GPU, n_sims=SIMS, evaluator="nn", state_dict=sd,
-                        seed=0xC0FFEE + rank, replay_capacity=GAMES_PER_GPU * (args.steps + args.warmup + 2))
+                        seed=0xC0FFEE + rank, replay_capacity=GAMES_PER_GPU * (2 * (args.steps + args.warmup) + 8))
     t_bcast = yyd.broadcast_weights(eng) if world > 1 else 0.0
 
     def barrier():
@@ -176,10 +176,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches0 = engine._lib.lib().yy_launch_count()
+    # one step = ONE launch of the persistent kernel: SIMS + 1 evaluation steps (the budget of one full search) for every
+    # game slot.  The games are rolling: a slot whose search is complete makes its move and roots the next search at once,
+    # so the moves a step completes are COUNTED (device counter), not assumed.
+    iters = SIMS + 1
     for _ in range(args.warmup):
-        eng.selfplay_run(1)
+        eng.selfplay_advance(iters)
     barrier()
+    st0 = eng.stats()
     sampler = ClockSampler(local)
     sampler.start()
     eng.set_profiling(True)
@@ -187,7 +191,7 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        eng.selfplay_run(1)
+        eng.selfplay_advance(iters)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -196,11 +200,15 @@ def run_b200(args):
     clocks = sampler.stop()
     launches = engine._lib.lib().yy_launch_count() - launches1
     st = eng.stats()
+    moves = st.moves - st0.moves                         # searches completed inside the timed region, this rank
+    evals_timed = st.tower_evals - st0.tower_evals       # boards the kernel evaluated, every one a pending leaf
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    moves = GAMES_PER_GPU * world * args.steps
+        t = torch.tensor([moves], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        moves = int(t.item())
     value = moves / (ms * 1e-3)
 
     # replay gather (north star: gather replay samples over NCCL), outside the timed region
@@ -242,7 +250,7 @@ def run_b200(args):
 
     if rank == 0:
         tower_s = prof["ms"] * 1e-3 / max(1, prof["launches"])
-        boards_per_launch = prof["boards"] / max(1, prof["launches"])
+        boards_per_launch = evals_timed / max(1, prof["launches"])      # required evaluations (device counter), not slots x steps
         # the persistent search kernel runs tower + FC heads + tree steps of every simulation: one launch per move step
         achieved = FLOPS_PER_LEAF * boards_per_launch / tower_s / 1e12 if prof["launches"] else None
         traffic = None
@@ -269,7 +277,7 @@ def run_b200(args):
                         "steps": e2e_steps, "api": "Engine.search_host + next_state_host (numpy in/out)"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "env": env, "dataset": dataset, "learner": learner_leg, "ai_move": ai_move_leg,
                 "moves_per_s_roofline": peaks["bf16_tflops_sustained"] * 1e12 / ((SIMS + 1) * FLOPS_PER_LEAF) * world,
-                "leaf_evals_per_s": (SIMS + 1) * value,
+                "leaf_evals_per_s": evals_timed / (ms * 1e-3), "moves_timed": int(moves), "evals_per_move": evals_timed * world / max(1, moves),
                 "nccl": {"weight_broadcast_s": t_bcast, "replay_gather_s": t_gather, "replay_records_gathered": int(n_records)},
                 "selfplay_stats": st.__dict__}
         emit(line)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define YY_ABI_VERSION 1
+#define YY_ABI_VERSION 2
 
 typedef enum {
   YY_OK = 0,
@@ -137,6 +137,10 @@ typedef struct {
   int32_t leaves_per_step;  /* K: leaves selected per game per step. 1 (default) = deterministic mode,
                                exact sequential MCTS; K>1 = throughput mode with virtual loss */
   float cpuct;              /* mcts.py:231 (default 1.0; weak-promoted to float32)        */
+  int32_t descents_per_step; /* persistent kernel: simulations a game may start per evaluation step when they keep
+                               ending in revisited terminals (no predict call, mcts.py:365-367); the search resumes in
+                               the next step.  Bounds the latency one game adds to its CTA pair's step; the search result
+                               does not depend on it.  0 = default (4); < 0 = unbounded */
   double dirichlet_alpha;   /* mcts.py:233 (0.3)                                          */
   double dirichlet_epsilon; /* mcts.py:233 (0.25; used in float64, mcts.py:309-311)       */
   uint64_t seed;            /* Philox key for noise / action sampling                     */
@@ -203,12 +207,37 @@ int yy_engine_get_profile(yy_engine *e, int64_t *tower_launches, double *tower_m
  * each phase (tower, FC heads, softmax + tree step, barrier, re-zero, ...) at dbg_dev[600 ..] / [760 ..]. */
 int yy_engine_set_debug_stamps(yy_engine *e, long long *dbg_dev);
 
-/* Self-play driver (SelfPlayWorker.play_game, self_play.py:72-192, for n_games games in
- * lock-step; finished games restart from the empty board).  Plays `n_moves` moves per game
- * slot (one move = one full search + action selection + state update).  Examples are appended
- * to the replay ring. */
+/* Self-play driver (SelfPlayWorker.play_game, self_play.py:72-192) for n_games game slots; a slot whose game ends
+ * starts the next game from the empty board (generate_games, self_play.py:194-216).  One move = one full search +
+ * action selection + state update; examples are appended to the replay ring.
+ *
+ * With the persistent search kernel (the default: STUB / NN evaluator, leaves_per_step 1) the games are ROLLING: one
+ * launch plays them all, and a slot whose search is complete makes its move and roots its next search in the same
+ * evaluation step, independently of the other slots -- a search that ends early (revisited terminal leaves need no
+ * evaluation, mcts.py:365-367) never waits for the slowest search of the batch, and only games with a pending leaf
+ * occupy tensor-core tiles.  Each game is still the exact sequential search of the reference.
+ *   yy_selfplay_run      every slot makes exactly n_moves moves (the launch ends when the last slot has).
+ *   yy_selfplay_advance  runs `iterations` evaluation steps (one leaf per game slot per step); searches in progress at
+ *                        the end of the call continue in the next one.  Moves completed: yy_selfplay_get_stats.
+ *   yy_selfplay_set_quota  at most total_games games are started since the last reset (< 0: unlimited); slots that
+ *                        would need a game beyond the quota idle.  Game serial s is the same game whichever slot plays
+ *                        it: all its random draws are keyed by (seed, s, ply).
+ * yy_selfplay_run also works in the per-step-kernel modes (lock-step: prepare, search, move kernels per move). */
 int yy_selfplay_reset(yy_engine *e, void *stream);
 int yy_selfplay_run(yy_engine *e, int32_t n_moves, void *stream);
+int yy_selfplay_advance(yy_engine *e, int64_t iterations, void *stream);
+int yy_selfplay_set_quota(yy_engine *e, int64_t total_games);
+/* Recorded random stream instead of the engine's Philox draws (parity seam: the reference draws from the global
+ * np.random state -- np.random.choice, self_play.py:143-160; np.random.dirichlet, mcts.py:303-306):
+ *   uniforms_dev float64[n_games][n_plies]  the uniform draw behind the action choice of game s at ply p: temperature 1 =
+ *                the first action whose cumulative visit share exceeds u; temperature 0 = entry floor(u*k) of the k most
+ *                visited actions in ascending order
+ *   noise_dev    float64[n_games][A]        the Dirichlet sample mixed into the root priors of game s at ply 0, one
+ *                value per legal action in ascending action order
+ * Either may be NULL (= Philox).  Games / plies beyond the recorded range fall back to Philox.  The arrays stay owned
+ * by the caller and must outlive the self-play calls. */
+int yy_selfplay_set_random_stream(yy_engine *e, const double *uniforms_dev, const double *noise_dev, int32_t n_games,
+                                  int32_t n_plies);
 
 typedef struct {
   int64_t moves;          /* searches completed                         */
@@ -218,6 +247,7 @@ typedef struct {
   int64_t sims;           /* simulations completed                      */
   int32_t overflow;       /* non-zero if a tree arena overflowed        */
   int32_t max_depth;
+  int64_t tower_evals;    /* boards evaluated by the persistent kernel (each a pending leaf or root) */
 } yy_selfplay_stats;
 int yy_selfplay_get_stats(yy_engine *e, yy_selfplay_stats *out, void *stream);
 

@@ -221,24 +221,18 @@ def test_mcts_external_evaluator_seam(eng, oracle_mod):
                                  (8, 8, 128, 1, 40, True), (6, 6, 128, 3, 64, True), (8, 8, 32, 2, 50, True),
                                  (16, 16, 128, 1, 9, True), (5, 7, 64, 2, 33, True), (8, 8, 128, 1, 37, True),
                                  (16, 16, 64, 2, 35, False), (8, 8, 128, 2, 1000, False)])
-@pytest.mark.parametrize("pair", [True, False])
-def test_network_matches_fp32_reference(eng, oracle_mod, cfg, pair):
+def test_network_matches_fp32_reference(eng, oracle_mod, cfg):
     """bf16 tcgen05 tower + heads vs the fp32 torch network (reference semantics, neural_network.py:94-154).
     Stated tolerance (bf16 weights + bf16 inter-layer activations, fp32 accumulate), measured headroom ~2x:
         logits  max|err| <= 0.015 * max|logit| + 0.01      value  max|err| <= 0.06
         policy  total-variation distance <= 0.05           top-1 agreement >= 80 %
     cfg[-1] False = reference initialisation (xavier weights, identity BN), True = random BN statistics.
-    pair = True is the default CTA-pair kernel (tcgen05 cta_group::2); False cannot be selected per engine (the library
-    reads YY_CTA_PAIR once per process), so that leg only runs when the suite is started with YY_CTA_PAIR=0.
     Shallow nets (<= 1 block) are also compared with the numpy emulation of the kernel's own dataflow from the
     same packed image at 2e-3: there only the fp32 summation order differs, so this pins the kernel logic."""
     import torch
     import emulate_tower as emu
     from oracle import port
     from yinyang_game_alphazero_b200 import weights
-    import os
-    if pair == (os.environ.get("YY_CTA_PAIR", "1") == "0"):
-        pytest.skip("kernel variant is chosen per process by YY_CTA_PAIR")
     n, m, C, blocks, count, rnd = cfg
     torch.manual_seed(0)
     net = port.build_net(n, m, C, blocks)
@@ -435,7 +429,75 @@ def test_selfplay_reference_player_semantics(eng, oracle_mod):
     e.close()
 
 
-@pytest.mark.gpu
+def _games_by_serial(rp):
+    """replay dict -> {serial: [(ply, board bytes, counts bytes, player)] sorted by ply}, {serial: z} of finished games"""
+    games, z = {}, {}
+    for i in np.lexsort((rp["ply"], rp["game_serial"])):
+        s = int(rp["game_serial"][i])
+        games.setdefault(s, []).append((int(rp["ply"][i]), rp["boards"][i].tobytes(), rp["counts"][i].tobytes(), int(rp["player"][i])))
+        if rp["finished"][i]:
+            z[s] = float(rp["z"][i])
+    return games, z
+
+
+@pytest.mark.parametrize("evaluator", ["stub", "nn"])
+def test_selfplay_rolling_games_do_not_depend_on_the_slot(eng, oracle_mod, evaluator):
+    """Rolling self-play (yy_selfplay_advance + yy_selfplay_set_quota): game serial s is the same game -- positions, visit
+    counts, Dirichlet noise, sampled actions, result -- whether 40 games are played by 8 slots (5 generations per slot,
+    slots restart at different steps) or by 40 slots at once, with a launch boundary in the middle of searches."""
+    import torch
+    from oracle import port
+    n = m = 6
+    total, sims = 40, 30
+    kw = {}
+    if evaluator == "nn":
+        torch.manual_seed(11)
+        kw["state_dict"] = randomise_bn(port.build_net(n, m, 128, 1)).state_dict()
+    runs = []
+    for slots, chunk in ((8, 97), (40, 1000)):
+        e = eng.Engine(rows=n, cols=m, n_games=slots, n_sims=sims, evaluator=evaluator, seed=77, replay_capacity=total * 400, **kw)
+        e.selfplay_set_quota(total)
+        for _ in range(4000):
+            e.selfplay_advance(chunk)
+            st = e.stats()
+            if st.games_finished >= total:
+                break
+        assert st.games_finished == total and st.overflow == 0 and st.examples <= total * 400
+        e.selfplay_advance(50)                           # quota used up: every slot idles, nothing more happens
+        st2 = e.stats()
+        assert (st2.moves, st2.examples, st2.tower_evals) == (st.moves, st.examples, st.tower_evals)
+        assert st.tower_evals == st.evals + st.moves     # every evaluated board was a pending leaf (or a root)
+        runs.append(_games_by_serial(e.replay()))
+        e.close()
+    (g8, z8), (g40, z40) = runs
+    assert sorted(g8) == list(range(total)) and g8 == g40 and z8 == z40 and len(z8) == total
+
+
+def test_selfplay_rolling_matches_lockstep_kernels(eng, oracle_mod):
+    """The persistent kernel playing the games itself (one launch, slots advance independently) against the lock-step
+    driver (prepare / noise / root / per-simulation step / move kernels, YY_MODE_STEP_KERNELS): every (game, ply) that
+    both played has the same position, visit counts and mover."""
+    n = m = 6
+    slots, sims, moves = 24, 40, 45
+    runs = []
+    for sk in (False, True):
+        e = eng.Engine(rows=n, cols=m, n_games=slots, n_sims=sims, evaluator="stub", seed=5, step_kernels=sk)
+        e.selfplay_run(moves)
+        st = e.stats()
+        assert st.moves == slots * moves and st.overflow == 0
+        runs.append(_games_by_serial(e.replay()))
+        e.close()
+    (ga, za), (gb, zb) = runs
+    common = 0
+    for s in set(ga) & set(gb):
+        k = min(len(ga[s]), len(gb[s]))
+        assert ga[s][:k] == gb[s][:k], s
+        common += k
+        if s in za and s in zb:
+            assert za[s] == zb[s]
+    assert common >= slots * moves // 2
+
+
 @pytest.mark.parametrize("n,m", [(8, 8), (6, 6), (5, 7), (16, 16), (9, 11)])
 def test_device_pack_unpack_matches_host_packing(yy, n, m):
     """yy_pack_boards / yy_unpack_boards (the int8 <-> bitboard conversion of the host-buffer entry points) against the numpy

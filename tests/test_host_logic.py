@@ -92,7 +92,7 @@ def test_abi_exports_every_declared_symbol(yy):
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, missing
     assert set(yy._lib.SIGNATURES) >= declared - {"yy_nn_weight_layout"} | {"yy_nn_weight_layout"}
-    assert lib.yy_abi_version() == 1
+    assert lib.yy_abi_version() == 2
     assert ctypes.sizeof(yy._lib.EngineConfig) == 88
 
 

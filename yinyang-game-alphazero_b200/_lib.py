@@ -63,7 +63,8 @@ class EngineConfig(ctypes.Structure):
         ("rule_flags", ctypes.c_uint32), ("mode_flags", ctypes.c_uint32), ("evaluator", ctypes.c_int32),
         ("edges_per_game", ctypes.c_int32), ("temperature_threshold", ctypes.c_int32),
         ("replay_capacity", ctypes.c_int32), ("nn_channels", ctypes.c_int32), ("nn_blocks", ctypes.c_int32),
-        ("device", ctypes.c_int32), ("leaves_per_step", ctypes.c_int32), ("cpuct", ctypes.c_float), ("dirichlet_alpha", ctypes.c_double),
+        ("device", ctypes.c_int32), ("leaves_per_step", ctypes.c_int32), ("cpuct", ctypes.c_float), ("descents_per_step", ctypes.c_int32),
+        ("dirichlet_alpha", ctypes.c_double),
         ("dirichlet_epsilon", ctypes.c_double), ("seed", ctypes.c_uint64),
     ]
 
@@ -71,7 +72,7 @@ class EngineConfig(ctypes.Structure):
 class SelfPlayStats(ctypes.Structure):
     _fields_ = [("moves", ctypes.c_int64), ("evals", ctypes.c_int64), ("games_finished", ctypes.c_int64),
                 ("examples", ctypes.c_int64), ("sims", ctypes.c_int64), ("overflow", ctypes.c_int32),
-                ("max_depth", ctypes.c_int32)]
+                ("max_depth", ctypes.c_int32), ("tower_evals", ctypes.c_int64)]
 
 
 class GemmStats(ctypes.Structure):
@@ -129,6 +130,9 @@ SIGNATURES = {
     "yy_engine_set_debug_stamps": (_I, [_P, _P]),
     "yy_selfplay_reset": (_I, [_P, _P]),
     "yy_selfplay_run": (_I, [_P, ctypes.c_int32, _P]),
+    "yy_selfplay_advance": (_I, [_P, _I64, _P]),
+    "yy_selfplay_set_quota": (_I, [_P, _I64]),
+    "yy_selfplay_set_random_stream": (_I, [_P, _P, _P, ctypes.c_int32, ctypes.c_int32]),
     "yy_selfplay_get_stats": (_I, [_P, ctypes.POINTER(SelfPlayStats), _P]),
     "yy_selfplay_replay": (_I, [_P, ctypes.POINTER(ReplayView)]),
     "yy_engine_game_black": (_P, [_P]),

@@ -18,12 +18,14 @@ enum : uint8_t { NODE_EXPANDED = 1, NODE_TERMINAL = 2, NODE_NOCHILD = 4 };
 struct Stats {  // device counters (unsigned long long for atomicAdd)
   unsigned long long moves, evals, games_finished, examples, sims;
   int overflow, max_depth;
+  unsigned long long tower_evals;   // boards the persistent kernel evaluated (every one of them a pending leaf)
 };
 
 struct EngineDev {
   // geometry / config
   int rows, cols, A, W;
   int n_games, n_sims, max_nodes, edges_cap, max_depth;
+  int max_descents; // persistent kernel: simulations a game may start per step (0 = until a leaf needs an evaluation)
   int K, n_slots;   // leaves per game per step (1 = deterministic mode), evaluation slots = n_games * K
   float cpuct;
   float keep_f32;   // f32(1 - eps)            (mcts.py:309-311 under numpy>=2)
@@ -39,7 +41,8 @@ struct EngineDev {
   // edges
   int32_t* edge_N; float* edge_W; float* edge_P; uint64_t* edge_cmeta; uint8_t* edge_action;
   // per game search state
-  int32_t* g_n_nodes; int32_t* g_n_edges; int32_t* g_sims_done; int32_t* g_npending;
+  int32_t* g_n_nodes; int32_t* g_n_edges; int32_t* g_sims_done;
+  int32_t* g_npending;   // leaves waiting for the evaluator; 0 = no search in progress; -1 = search in progress, no leaf this step
   // pending leaf batch (evaluator input), slot = game*K + k: node id, recorded path, state, rules result
   int32_t* leaf_node; int32_t* leaf_path_len; int32_t* leaf_path;
   uint64_t* leaf_black; uint64_t* leaf_white; uint64_t* leaf_mask; int8_t* leaf_code; uint8_t* leaf_active;
@@ -53,6 +56,15 @@ struct EngineDev {
   uint64_t* sp_black; uint64_t* sp_white; int8_t* sp_player; int32_t* sp_step; int32_t* sp_passes; int32_t* sp_serial;
   uint8_t* sp_new_game;
   int32_t* sp_next_serial;
+  // rolling self-play inside the persistent kernel (yy_fused.cu): a slot whose search is complete makes its move and
+  // roots the next search at once, independently of the other slots
+  uint8_t* sp_phase;        // 1 = the slot's tree belongs to a self-play search in progress / just completed
+  int32_t* sp_moves_left;   // moves the slot may still make in this launch (INT_MAX = unlimited)
+  long long game_quota;     // games that may be started in total since the last reset; < 0 = unlimited
+  int32_t* act_list;        // [n_games] per CTA run: the games with a pending leaf, compacted, for the current iteration
+  // recorded random stream (test seam; replaces the np.random.choice / np.random.dirichlet draws of self_play.py:143-160
+  // and mcts.py:303-306): uniforms [hook_games][hook_plies], Dirichlet samples [hook_games][A]; nullptr = Philox
+  const double* hook_uniform; const double* hook_noise; int hook_games, hook_plies;
   // replay ring
   int replay_cap; int results_cap;
   uint64_t* rp_black; uint64_t* rp_white; uint16_t* rp_counts; int32_t* rp_serial; int16_t* rp_ply; int8_t* rp_player;

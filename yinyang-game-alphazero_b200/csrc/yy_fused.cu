@@ -14,11 +14,9 @@
 //
 // Warp roles (as in tower_kernel): warp 0 weight producer, warp 1 MMA issuer, warps 2-17 epilogue / heads / tree.
 // Roofline: tensor (the tower's conv MMAs are > 99 % of the FLOPs; see yy_nn.cu for the tower layout).
-#include <stdlib.h>
-
 #include "yy_nn.cuh"
 #include "yy_tower.cuh"
-#include "yy_tree_dev.cuh"
+#include "yy_selfplay_dev.cuh"
 
 namespace yy {
 using namespace ptx;
@@ -36,11 +34,15 @@ struct FusedArgs {
   int batch_boards;            // <= FC_N boards per heads pass; a multiple of g.Gb
   __nv_bfloat16* headfeat;     // [count][64*A] head-conv features, index c*A + cell (L2-resident round trip)
   float* policy; float* value; float* logits;     // [count][A], [count], optional [count][A]
-  int iterations;              // 1 = plain forward; n_sims + 1 = whole search
-  int do_tree;                 // run tree_step_game after every evaluation
+  int iterations;              // 1 = plain forward; n_sims + 1 = whole search; rolling self-play: any number of steps
+  int mode;                    // YY_FUSED_FORWARD / YY_FUSED_SEARCH (tree step after every evaluation) / YY_FUSED_SELFPLAY
   int use_nn;                  // 0 = deterministic-prior (stub) evaluator: tree steps only
   long long* dbg;
 };
+
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
 
 constexpr int kEpiBarrier = 1;   // named barrier of the 16 epilogue warps
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(TW_EPI_THREADS) : "memory"); }
@@ -101,25 +103,38 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   if (a.dbg && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.dbg[128 + 2 * blockIdx.x] = (long long)gt; }
   const uint32_t act_base = smem_u32(smem + SM_ACT);
   const uint32_t ring_base = smem_u32(smem + SM_RING);
-  // this CTA's run of boards [run_lo, run_hi), walked in batches of <= FC_N boards; a batch in groups of Gb boards
-  // In a pair both CTAs must walk the same batches / groups / tiles: the loop structure comes from the leader's run
-  // (never shorter than the follower's); boards past this CTA's own run are simply not real.
+  // This CTA owns the run of boards [run_lo, run_lo + my_len).  A plain forward walks the whole run; a search / self-play
+  // step walks only the games that have a pending leaf, compacted into e.act_list by the epilogue warps at the end of the
+  // previous step (a game whose remaining simulations ended in revisited terminals has none: mcts.py:365-367 makes no
+  // predict call there, so no tensor time is spent on it).  The walk goes in batches of <= FC_N boards, a batch in groups
+  // of Gb boards.  In a pair both CTAs must walk the same batches / groups / tiles: the structure comes from the larger of
+  // the two counts; entries past a CTA's own count are padding.
   auto clampl = [](long long v, long long hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
   const long long run_lo = (long long)blockIdx.x * a.boards_per_cta;
-  const long long my_len = clampl(a.count - run_lo, a.boards_per_cta);
-  const long long st_len = clampl(a.count - (long long)(blockIdx.x - rank) * a.boards_per_cta, a.boards_per_cta);
-  const long long run_hi = run_lo + my_len;      // my real boards
-  const long long run_end = run_lo + st_len;     // structural end of the walk
-  // tiles a group starting at board b0 needs when its batch ends at `lim`
+  const int my_len = (int)clampl(a.count - run_lo, a.boards_per_cta);
+  const int st_len = (int)clampl(a.count - (long long)(blockIdx.x - rank) * a.boards_per_cta, a.boards_per_cta);
+  const bool dyn = a.mode != YY_FUSED_FORWARD;
+  volatile int* cnt_s = reinterpret_cast<volatile int*>(smem + SM_CNT);   // [step parity][cluster rank][leaves, selecting]
+  int n_mine = my_len, n_struct = st_len;        // my real entries / structural length of this step's walk
+  int n_sel = 0;                                 // my games whose search continues without a leaf in this step
+  bool any_work = true;
+  // every thread of the CTA (pair): wait for the counts of step `iter` (written by the compaction of the step before)
+  auto fetch_counts = [&](int iter) {
+    if (CG == 2) cluster_sync_all(); else asm volatile("bar.sync 0;" ::: "memory");
+    volatile int* c = cnt_s + (iter & 1) * 4;
+    const int c0 = c[0], c1 = CG == 2 ? c[2] : 0, s0 = c[1], s1 = CG == 2 ? c[3] : 0;
+    n_mine = rank ? c1 : c0; n_struct = c0 > c1 ? c0 : c1; n_sel = rank ? s1 : s0;
+    any_work = (c0 | c1 | s0 | s1) != 0;
+  };
+  // tiles a group starting at entry b0 needs when its batch ends at `lim`
   // (+pitch+1: the taps of the last real position read that far; rows beyond the group's tiles may be stale)
-  auto tiles_for = [&](long long b0, long long lim) {
-    long long nb = lim - b0; if (nb > g.Gb) nb = g.Gb;
-    int t = g.row_aligned == 3 ? (int)((nb + 1) >> 1) : g.row_aligned == 2 ? (int)(2 * nb)
-          : g.row_aligned ? (int)((nb * g.rows_per_board + 15) >> 4) : (int)((nb * g.PB + g.pitch + 1 + 127) >> 7);
+  auto tiles_for = [&](int b0, int lim) {
+    int nb = lim - b0; if (nb > g.Gb) nb = g.Gb;
+    int t = g.row_aligned == 3 ? ((nb + 1) >> 1) : g.row_aligned == 2 ? (2 * nb)
+          : g.row_aligned ? ((nb * g.rows_per_board + 15) >> 4) : ((nb * g.PB + g.pitch + 1 + 127) >> 7);
     return t < g.T ? t : g.T;
   };
-  auto batch_end = [&](long long bb0) { return (bb0 + a.batch_boards < run_end) ? bb0 + a.batch_boards : run_end; };   // structural
-  auto real_end = [&](long long slim) { return slim < run_hi ? slim : run_hi; };                                         // my boards
+  auto batch_end = [&](int bb0) { return (bb0 + a.batch_boards < n_struct) ? bb0 + a.batch_boards : n_struct; };   // structural
   // FC stage geometry: rows of M tile t of head h
   auto fc_tiles = [&](int h) { return h ? 2 : fc.Tp; };
   auto fc_rows = [&](int h, int t) { return (h || t < fc.Tp - 1) ? 128 : fc.Rp_last; };
@@ -136,7 +151,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   if (warp == 0) {
     // =========================================================== weight producer (whole warp walks the loop with
     // warp-uniform state; one elected lane issues the bulk copies -- keeps everything on the uniform datapath)
-    if (a.use_nn) {
+    if (!a.use_nn) {
+      for (int iter = 0; dyn && iter < a.iterations; ++iter) { fetch_counts(iter); if (!any_work) break; }
+    } else {
       uint32_t ci = 0, used = 0, ephase = 0, acc_n = 0;     // conv stage counter, slots used so far, empty-phase bits, commits so far
       auto push = [&](uint32_t slot, const uint8_t* src, uint32_t bytes) {
         if ((used >> slot) & 1u) { mbar_wait(empty_bar(slot), (ephase >> slot) & 1u); ephase ^= 1u << slot; }
@@ -161,9 +178,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         __syncwarp();
       };
       for (int iter = 0; iter < a.iterations; ++iter) {
-        for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
-          const long long slim = batch_end(bb0);
-          for (long long b0 = bb0; b0 < slim; b0 += g.Gb) {
+        if (dyn) { fetch_counts(iter); if (!any_work) break; }
+        for (int bb0 = 0; bb0 < n_struct; bb0 += a.batch_boards) {
+          const int slim = batch_end(bb0);
+          for (int b0 = bb0; b0 < slim; b0 += g.Gb) {
             for (int l = 0; l < L; ++l, ++acc_n) {
               const LayerInfo li = layer_info(l, g.blocks, CG);
               const uint32_t bytes = (uint32_t)li.stage_bytes / CG;     // pair: my half of the stage's output channels
@@ -196,7 +214,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   } else if (warp == 1) {
     // =========================================================== MMA issuer (whole warp runs the control flow, the
     // tcgen05.mma / commit instructions are issued by one elected lane; descriptors are base + constant deltas)
-    if (a.use_nn && rank != 0) {
+    if (!a.use_nn) {
+      for (int iter = 0; dyn && iter < a.iterations; ++iter) { fetch_counts(iter); if (!any_work) break; }
+    } else if (rank != 0) {
       // follower of a pair: no MMAs to issue -- relay "my half of stage s has landed" to the leader's peer-full ring
       uint32_t ci = 0, fphase = 0;
       auto relay = [&](uint32_t slot) {
@@ -205,9 +225,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         __syncwarp();
       };
       for (int iter = 0; iter < a.iterations; ++iter) {
-        for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
-          const long long slim = batch_end(bb0);
-          for (long long b0 = bb0; b0 < slim; b0 += g.Gb)
+        if (dyn) { fetch_counts(iter); if (!any_work) break; }
+        for (int bb0 = 0; bb0 < n_struct; bb0 += a.batch_boards) {
+          const int slim = batch_end(bb0);
+          for (int b0 = bb0; b0 < slim; b0 += g.Gb)
             for (int l = 0; l < L; ++l) { const int ns = layer_info(l, g.blocks, CG).n_stages; for (int j = 0; j < ns; ++j, ++ci) relay(ci % TW_STAGES); }
           uint32_t fi = 0;
           for (int h = 0; h < 2; ++h)
@@ -218,7 +239,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
               }
         }
       }
-    } else if (a.use_nn) {
+    } else {
       uint32_t ci = 0, fphase = 0, act_phase = 0;
       auto wait_stage = [&](uint32_t slot) {
         const uint32_t parity = (fphase >> slot) & 1u;
@@ -238,9 +259,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
       constexpr uint64_t kK16DeltaA = (2u * TW_ROWS * 16u) >> 4;   // next K=16 slice: +2 channel chunks
       constexpr uint64_t kK16DeltaF = (2u * FC_LBO) >> 4;          // same for the FC feature panel
       for (int iter = 0; iter < a.iterations; ++iter) {
-        for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
-          const long long slim = batch_end(bb0);
-          for (long long b0 = bb0; b0 < slim; b0 += g.Gb) {
+        if (dyn) { fetch_counts(iter); if (!any_work) break; }
+        for (int bb0 = 0; bb0 < n_struct; bb0 += a.batch_boards) {
+          const int slim = batch_end(bb0);
+          for (int b0 = bb0; b0 < slim; b0 += g.Gb) {
             const int T = tiles_for(b0, slim);
             for (int l = 0; l < L; ++l) {
               const LayerInfo li = layer_info(l, g.blocks, CG);
@@ -344,13 +366,60 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
       tc_fence_after();
     };
     auto arrive_act = [&]() { if (CG == 2) mbar_arrive_cluster(act_ready_leader); else mbar_arrive(act_ready); };
+    // entry i of this step's walk -> board (search / self-play: the i-th game of my run that has a pending leaf)
+    int32_t* my_list = dyn ? e.act_list + run_lo : nullptr;
+    auto board_of = [&](int i) -> long long { return dyn ? (long long)my_list[i] : run_lo + i; };
+    // One warp compacts the games of my run that have a pending leaf (from the front of my_list) and those still
+    // selecting (from its back), and publishes both counts for step `iter_next` to every thread of the CTA (pair) --
+    // read after the barrier in fetch_counts.
+    auto compact = [&](int iter_next) {
+      if (ew != 0) return;
+      int n = 0, ns = 0;
+      for (int base = 0; base < my_len; base += 32) {
+        const int i = base + lane;
+        const int np = i < my_len ? e.g_npending[run_lo + i] : 0;
+        const unsigned m = __ballot_sync(kFull, np > 0), ms = __ballot_sync(kFull, np < 0);
+        const unsigned below = (1u << lane) - 1u;
+        if (np > 0) my_list[n + __popc(m & below)] = (int)(run_lo + i);
+        if (np < 0) my_list[my_len - 1 - ns - __popc(ms & below)] = (int)(run_lo + i);
+        n += __popc(m); ns += __popc(ms);
+      }
+      if (lane == 0) {
+        volatile int* slot = cnt_s + (iter_next & 1) * 4 + rank * 2;
+        slot[0] = n; slot[1] = ns;
+        if (CG == 2) {
+          const uint32_t peer = mapa_u32(smem_u32(const_cast<int*>(slot)), (uint32_t)(rank ^ 1));
+          st_cluster_u32(peer, (uint32_t)n); st_cluster_u32(peer + 4, (uint32_t)ns);
+        }
+      }
+    };
+    if (dyn) {
+      // self-play: slots without a search in progress (after a reset, or stopped on their move budget) get their next root
+      if (a.mode == YY_FUSED_SELFPLAY)
+        for (int b = ew; b < my_len; b += TW_EPI_WARPS)
+          if (e.g_npending[run_lo + b] == 0) sp_advance_game<NW>(e, geo, (int)(run_lo + b), lane);
+      epi_sync();
+      compact(0);
+    }
+    // games whose last simulations all ended in revisited terminals (max_descents): no evaluation in this step, the
+    // selection goes on -- in the same phase as the tree steps of the evaluated games, on the warps those left idle
+    auto run_selecting = [&]() {
+      for (int k = (ew + TW_EPI_WARPS - n_mine % TW_EPI_WARPS) % TW_EPI_WARPS; k < n_sel; k += TW_EPI_WARPS) {
+        const int gi = my_list[my_len - 1 - k];
+        const int np = tree_step_game<NW>(e, geo, gi, lane, nullptr, e.max_descents);
+        if (np == 0 && a.mode == YY_FUSED_SELFPLAY) sp_advance_game<NW>(e, geo, gi, lane);
+      }
+    };
+    unsigned long long evals_here = 0;
     for (int iter = 0; iter < a.iterations; ++iter) {
-      for (long long bb0 = run_lo; bb0 < run_end; bb0 += a.batch_boards) {
-        const long long slim = batch_end(bb0);
-        const long long lim = real_end(slim);                    // boards at or past `lim` are padding of the walk
-        const int nbb = lim > bb0 ? (int)(lim - bb0) : 0;
+      if (dyn) { fetch_counts(iter); if (!any_work) break; }
+      evals_here += (unsigned long long)n_mine;
+      for (int bb0 = 0; bb0 < n_struct; bb0 += a.batch_boards) {
+        const int slim = batch_end(bb0);
+        const int lim = slim < n_mine ? slim : n_mine;           // entries at or past `lim` are padding of the walk
+        const int nbb = lim > bb0 ? lim - bb0 : 0;
         if (a.use_nn) {
-          for (long long b0 = bb0; b0 < slim; b0 += g.Gb) {
+          for (int b0 = bb0; b0 < slim; b0 += g.Gb) {
             const int T = tiles_for(b0, slim);
             // ---- stem input planes (board_to_input, neural_network.py:156-196) for my rows ----
             for (int t = tile0; t < T; t += kTileStride) {
@@ -358,8 +427,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
               const int p = pos_p[mi];
               const int info = pos_tab[mi];
               uint4 c0 = make_uint4(0, 0, 0, 0);
-              const long long board = b0 + (info >= 0 ? (info >> 8) : 0);
-              if (info >= 0 && board < lim) {
+              const int entry = b0 + (info >= 0 ? (info >> 8) : 0);
+              if (info >= 0 && entry < lim) {
+                const long long board = board_of(entry);
                 const int cell = info & 255, y = cell / g.m, x = cell % g.m;
                 const uint64_t* bb = a.black + board * g.W; const uint64_t* wb = a.white + board * g.W;
                 auto bit = [&](const uint64_t* v, int c) { return (int)((v[c >> 6] >> (c & 63)) & 1ull); };
@@ -394,8 +464,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                 const int mi = t * 128 + quarter * 32 + lane;
                 const int p = pos_p[mi];
                 const int info = pos_tab[mi];
-                const long long board = b0 + (info >= 0 ? (info >> 8) : 0);
-                const bool real = info >= 0 && board < lim;
+                const int entry = b0 + (info >= 0 ? (info >> 8) : 0);
+                const bool real = info >= 0 && entry < lim;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 128);
                 uint8_t* rowp = act + (size_t)(TW_PAD + p) * 16;
                 if (!is_head) {
@@ -442,7 +512,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                   }
                   if (is_conv1) tc_wait_st();
                 } else {
-                  __nv_bfloat16* dst = a.headfeat + (size_t)board * (TW_HEADC * g.A) + (info & 255);
+                  __nv_bfloat16* dst = a.headfeat + (size_t)(run_lo + entry) * (TW_HEADC * g.A) + (info & 255);   // by walk entry
 #pragma unroll 1
                   for (int cc = 0; cc < TW_HEADC / 16; ++cc) {
                     uint32_t r[16];
@@ -473,7 +543,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
             if (q > 0) { wait_acc(); sub(6); }   // previous panel consumed
             const int nchunks = panel_stages(p) * 8;
             const int kbase = p * FC_PANEL_STAGES * 64;
-            const __nv_bfloat16* src0 = a.headfeat + (size_t)bb0 * (TW_HEADC * g.A) + (size_t)h * fc.Kh + kbase;
+            const __nv_bfloat16* src0 = a.headfeat + (size_t)(run_lo + bb0) * (TW_HEADC * g.A) + (size_t)h * fc.Kh + kbase;
             for (int idx = etid; idx < nbb * nchunks; idx += TW_EPI_THREADS) {
               const int b = idx / nchunks, j = idx - b * nchunks;
               const bool valid = kbase + j * 8 < fc.Kh;      // K padding up to the stage boundary must be zero
@@ -521,7 +591,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
 
         // ---- per board: softmax over all A logits (predict, neural_network.py:152), value_fc2 + tanh (:121), tree step
         for (int b = ew; b < nbb; b += TW_EPI_WARPS) {
-          const long long board = bb0 + b;
+          const long long board = board_of(bb0 + b);
           if (a.use_nn) {
             const float* lg = sc_logit + b * 256;
             float mx = -INFINITY;
@@ -540,8 +610,13 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
             if (lane == 0) a.value[board] = tanhf(acc + __ldg(a.fc_value2_b));
             __syncwarp();
           }
-          if (a.do_tree) tree_step_game<NW>(e, geo, (int)board, lane, nullptr);
+          if (dyn) {
+            const int np = tree_step_game<NW>(e, geo, (int)board, lane, nullptr, e.max_descents);
+            // search complete: the game makes its move and roots its next search now (self_play.py:139-190, :91-137)
+            if (np == 0 && a.mode == YY_FUSED_SELFPLAY) sp_advance_game<NW>(e, geo, (int)board, lane);
+          }
         }
+        if (slim == n_struct) run_selecting();       // with the last batch of the step
         phase(2);
         if (a.use_nn) {
           epi_sync();     // scratch consumed, new leaves published
@@ -551,7 +626,13 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           phase(4);
         }
       }
+      if (n_struct == 0) run_selecting();
+      if (dyn && iter + 1 < a.iterations) {
+        epi_sync();       // every game of my run has had its tree step
+        compact(iter + 1);
+      }
     }
+    if (dyn && etid == 0 && evals_here) atomicAdd(&e.stats->tower_evals, evals_here);
     if (a.dbg && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 100))
       for (int k = 0; k < 8; ++k) a.dbg[600 + (blockIdx.x ? 160 : 0) + ew * 8 + k] = ph_acc[k];
   }
@@ -590,15 +671,14 @@ static int launch_fused(NNState& nn, const FusedArgs& fa, const EngineDev& dev, 
 //   dev == nullptr : plain forward (do_tree off); policy/value/logits are the caller's output arrays.
 //   dev != nullptr : whole search over dev->leaf_* / eval_* (slot = game; leaves_per_step must be 1).
 int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const uint64_t* black, const uint64_t* white, int64_t count,
-                 float* policy, float* value, float* logits, int iterations, bool use_nn, cudaStream_t s) {
+                 float* policy, float* value, float* logits, int iterations, bool use_nn, int mode, cudaStream_t s) {
   if (use_nn) {
     if (!nn.attrs_set) return set_error(YY_ERR_STATE, "engine was not created with the NN evaluator");
     if (!nn.weights) return set_error(YY_ERR_STATE, "no weights loaded (yy_engine_load_weights)");
   }
   if (count <= 0 || iterations <= 0) return YY_OK;
   if (count > nn.max_boards) return set_error(YY_ERR_INVALID, "fused run: %lld boards exceed the head-feature scratch (%d)", (long long)count, nn.max_boards);
-  static const bool pair_default = [] { const char* v = getenv("YY_CTA_PAIR"); return !(v && v[0] == '0'); }();
-  const bool pair = pair_default;
+  if ((mode != YY_FUSED_FORWARD) != (dev != nullptr)) return set_error(YY_ERR_INVALID, "fused run: mode / engine state mismatch");
   FusedArgs fa{};
   fa.g = make_tower_geo(nn.rows, nn.cols, nn.blocks);
   if (fa.g.Gb > FC_N) fa.g.Gb = FC_N;
@@ -606,7 +686,7 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
   if (use_nn) {
     const WeightLayout wl = weight_layout(nn.rows, nn.cols, nn.blocks);
     const uint8_t* wimg = static_cast<const uint8_t*>(nn.weights);
-    fa.conv_stream = wimg + (pair ? wl.conv_stream_pair : wl.conv_stream);
+    fa.conv_stream = wimg + wl.conv_stream_pair;     // stages split in two N halves, one per CTA of the pair
     fa.conv_bias = reinterpret_cast<const float*>(wimg + wl.conv_bias);
     fa.fc_stream = wimg + wl.fc_stream;
     fa.fc_policy_b = reinterpret_cast<const float*>(wimg + wl.fc_policy_b);
@@ -617,7 +697,7 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
   }
   fa.black = black; fa.white = white; fa.count = count;
   fa.policy = policy; fa.value = value; fa.logits = logits;
-  fa.iterations = iterations; fa.do_tree = dev ? 1 : 0; fa.use_nn = use_nn ? 1 : 0;
+  fa.iterations = iterations; fa.mode = mode; fa.use_nn = use_nn ? 1 : 0;
   fa.dbg = nn.dbg;
   fa.batch_boards = fused_batch_boards(fa.g);
   // equal contiguous runs of boards per CTA (a search keeps its games on the same SM from the first to the last simulation)
@@ -627,7 +707,7 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
   if (per < 1) per = 1;
   fa.boards_per_cta = (int)per;
   int grid = (int)((count + per - 1) / per);
-  if (pair) grid = (grid + 1) & ~1;      // whole pairs; a trailing follower without boards only mirrors its leader's walk
+  grid = (grid + 1) & ~1;                // whole CTA pairs; a trailing follower without boards only mirrors its leader's walk
   EngineDev d{};
   if (dev) d = *dev;
   if (nn.profiling) {
@@ -635,12 +715,11 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
     YY_CUDA_OK(cudaEventRecord(nn.ev[2 * nn.ev_used], s));
   }
   int rc = YY_OK;
-  if (pair) { YY_DISPATCH_NW(nn.A, rc = (launch_fused<NW, 2>(nn, fa, d, rule_flags, grid, s))); }
-  else { YY_DISPATCH_NW(nn.A, rc = (launch_fused<NW, 1>(nn, fa, d, rule_flags, grid, s))); }
+  YY_DISPATCH_NW(nn.A, rc = (launch_fused<NW, 2>(nn, fa, d, rule_flags, grid, s)));
   if (rc) return rc;
   if (nn.profiling) {
     YY_CUDA_OK(cudaEventRecord(nn.ev[2 * nn.ev_used + 1], s));
-    ++nn.ev_used; ++nn.tower_launches; nn.tower_boards += count * iterations;
+    ++nn.ev_used; ++nn.tower_launches; nn.tower_boards += count * iterations;   // upper bound; the executed number is Stats::tower_evals
   }
   return YY_OK;
 }

@@ -31,10 +31,15 @@ int nn_set_profiling(NNState& nn, int enable);
 // drains recorded event pairs (synchronises) and returns totals since profiling was enabled
 int nn_get_profile(NNState& nn, long long* launches, double* total_ms, long long* boards);
 struct EngineDev;
-// Persistent kernel (yy_fused.cu): `iterations` x (network forward on boards [0,count) -> heads -> optional tree step)
-// in ONE launch.  dev == nullptr: plain forward into policy/value/logits.  dev != nullptr: whole search over the
-// engine's leaf batch (slot = game), use_nn = false runs the deterministic-prior evaluator (tree steps only).
+// Persistent kernel (yy_fused.cu): up to `iterations` x (network forward on the pending leaves -> heads -> tree step) in
+// ONE launch.
+//   YY_FUSED_FORWARD  (dev == nullptr): one plain forward of boards [0, count) into policy/value/logits.
+//   YY_FUSED_SEARCH   whole search over the engine's leaf batch (slot = game); ends when no game has a pending leaf.
+//   YY_FUSED_SELFPLAY rolling self-play: a game whose search is complete makes its move and roots its next search in
+//                     the same step (sp_advance_game), within its move budget and the game quota.
+// use_nn = false runs the deterministic-prior evaluator (tree steps only).
+enum { YY_FUSED_FORWARD = 0, YY_FUSED_SEARCH = 1, YY_FUSED_SELFPLAY = 2 };
 int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const uint64_t* black, const uint64_t* white,
-                 int64_t count, float* policy, float* value, float* logits, int iterations, bool use_nn, cudaStream_t stream);
+                 int64_t count, float* policy, float* value, float* logits, int iterations, bool use_nn, int mode, cudaStream_t stream);
 
 }  // namespace yy

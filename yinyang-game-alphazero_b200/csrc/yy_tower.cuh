@@ -41,7 +41,8 @@ constexpr int TW_FC_SLOTS = 5;          // weight slots during the FC heads: the
 constexpr int TW_FC_EXTRA_OFF = 136 * 1024;   // (the FC feature panel ends at 135,168 B)
 constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_FC_SLOTS + 2);   // full, empty, peer-full per slot + acc_full, act_ready
 constexpr int SM_BIAS = (SM_TMEM + 16 + 15) & ~15;                                 // current / next layer's 128 fp32 biases (double buffer)
-constexpr int SM_TOTAL = SM_BIAS + 2 * TW_C * 4;
+constexpr int SM_CNT = SM_BIAS + 2 * TW_C * 4;            // counts of the CTA (pair): [step parity][cluster rank][pending leaves, selecting]
+constexpr int SM_TOTAL = SM_CNT + 32;
 static_assert(SM_TOTAL <= 232448, "persistent kernel exceeds the 227 KB opt-in shared memory of sm_100");
 static_assert(TW_FC_EXTRA_OFF + (TW_FC_SLOTS - TW_STAGES) * TW_STAGE_BYTES <= TW_CHUNKS * TW_ROWS * 16, "FC slots exceed the activation region");
 

@@ -13,7 +13,7 @@
 // Roofline: HBM (latency-bound pointer chasing in practice).  Algorithmic bytes per simulation:
 // sum over levels of 12*A_l (N,W,P per child read) + 17*A_leaf (edge slots written) + 8 per path edge
 // (N,W read-modify-write) + 2*16*W node state -- ~1.5-4 KB at 8x8.
-#include "yy_tree_dev.cuh"
+#include "yy_selfplay_dev.cuh"
 #include "yy_nn.cuh"
 
 #include <new>
@@ -27,13 +27,8 @@ template <int NW>
 __global__ void __launch_bounds__(kTreeBlock) tree_root_kernel(EngineDev e, Geo<NW> g) {
   int gi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (gi >= e.n_games) return;
-  BB<NW> b = load_bb<NW>(e.root_black, gi, e.W) & g.full, w = load_bb<NW>(e.root_white, gi, e.W) & g.full;
-  int player = e.root_player[gi] == 1 ? 1 : -1;
-  if (lane == 0) {
-    e.g_n_nodes[gi] = 1; e.g_n_edges[gi] = 0; e.g_sims_done[gi] = 0; e.g_npending[gi] = 1;
-    for (int k = 1; k < e.K; ++k) e.leaf_active[gi * e.K + k] = 0;
-  }
-  publish_leaf<NW>(e, g, gi, lane, gi * e.K, 0, b, w, player, 0);
+  tree_root_game<NW>(e, g, gi, lane);
+  if (lane == 0) e.sp_phase[gi] = 0;      // the tree no longer belongs to a rolling self-play search (sp_advance_game)
   if (gi == 0 && lane == 0) { e.active_count[0] = e.n_games; e.active_count[1] = 0; }
 }
 
@@ -76,125 +71,30 @@ __global__ void stub_eval_kernel(Geo<NW> g, int W, const uint64_t* black, const 
 }
 
 // ------------------------------------------------------------------------------------------------ self-play
-__device__ __forceinline__ void finish_game(const EngineDev& e, int gi, int code) {
-  int serial = e.sp_serial[gi];
-  if (serial >= 0) e.rp_results[serial % e.results_cap] = (int8_t)code;
-  atomicAdd(&e.stats->games_finished, 1ull);
-  e.sp_new_game[gi] = 1;
-}
-
-// Top of the play_game loop (self_play.py:91-125): new game if needed, pass / double-pass handling, then the
-// root of the next search.  search player = 1 always under YY_MODE_SEARCH_AS_BLACK (self_play.py:99,135-137).
+// Lock-step episode driver (one thread per game; the device functions live in yy_selfplay_dev.cuh).  Used when the
+// search runs as per-step kernels (YY_MODE_STEP_KERNELS, leaves_per_step > 1); otherwise the persistent kernel plays
+// the games itself (yy_fused.cu, sp_advance_game).
 template <int NW>
 __global__ void __launch_bounds__(128) sp_prepare_kernel(EngineDev e, Geo<NW> g) {
   int gi = blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= e.n_games) return;
-  BB<NW> b = load_bb<NW>(e.sp_black, gi, e.W), w = load_bb<NW>(e.sp_white, gi, e.W);
-  int player = e.sp_player[gi], step = e.sp_step[gi], passes = e.sp_passes[gi];
-  int sp = 1;
-  for (;;) {
-    if (e.sp_new_game[gi]) {
-      b = bb_zero<NW>(); w = bb_zero<NW>(); player = 1; step = 0; passes = 0;
-      e.sp_serial[gi] = atomicAdd(e.sp_next_serial, 1);
-      e.sp_new_game[gi] = 0;
-    }
-    sp = (e.mode_flags & YY_MODE_SEARCH_AS_BLACK) ? 1 : player;
-    if (any(legal_for(g, b, w, sp))) { passes = 0; break; }
-    ++passes;                                             // self_play.py:103-106
-    if (passes >= 2) {                                    // self_play.py:108-121
-      int code = ended_code(g, b, w, player);
-      if (code == 0) code = YY_RESULT_DRAW;
-      finish_game(e, gi, code);
-      continue;
-    }
-    player = -player;                                     // self_play.py:124-125
-  }
-  store_bb<NW>(e.sp_black, gi, e.W, b); store_bb<NW>(e.sp_white, gi, e.W, w);
-  e.sp_player[gi] = (int8_t)player; e.sp_step[gi] = step; e.sp_passes[gi] = passes;
-  store_bb<NW>(e.root_black, gi, e.W, b); store_bb<NW>(e.root_white, gi, e.W, w);
-  e.root_player[gi] = (int8_t)sp;
-  e.noise_mask[gi] = (step == 0) ? 1 : 0;                 // add_noise = (step == 0), self_play.py:131
+  sp_prepare_one<NW>(e, g, gi);
 }
-
-__device__ inline double gamma_sample(Philox& rng, double a) {
-  // Marsaglia-Tsang; for a < 1: G(a) = G(a+1) * U^(1/a)
-  double boost = 1.0;
-  if (a < 1.0) { boost = pow(rng.uniform(), 1.0 / a); a += 1.0; }
-  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
-  for (;;) {
-    double u1 = rng.uniform(), u2 = rng.uniform();
-    double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
-    double v = 1.0 + c * x;
-    if (v <= 0.0) continue;
-    v = v * v * v;
-    double u = rng.uniform();
-    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
-  }
-}
-
-// np.random.dirichlet([alpha]*k) for the legal root actions of games at step 0 (mcts.py:303-306)
 template <int NW>
 __global__ void __launch_bounds__(128) sp_noise_kernel(EngineDev e, Geo<NW> g) {
   int gi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= e.n_games || !e.noise_mask[gi]) return;
-  BB<NW> b = load_bb<NW>(e.root_black, gi, e.W), w = load_bb<NW>(e.root_white, gi, e.W);
-  int k = popcount(legal_for(g, b, w, e.root_player[gi]));
-  Philox rng(e.seed, (uint64_t)(uint32_t)e.sp_serial[gi], 0x6e6f697365ull);
-  double sum = 0.0;
-  double* out = e.noise + (long long)gi * e.A;
-  for (int i = 0; i < k; ++i) { double x = gamma_sample(rng, e.alpha); out[i] = x; sum += x; }
-  if (sum <= 0.0) { for (int i = 0; i < k; ++i) out[i] = 1.0 / k; }
-  else { for (int i = 0; i < k; ++i) out[i] /= sum; }
+  if (gi >= e.n_games) return;
+  sp_noise_one<NW>(e, g, gi);
 }
-
-// After the search (self_play.py:139-190): store the example, pick the action (temperature 1 for the first
-// `temperature_threshold` moves, then argmax with random tie-break), apply it with the REAL player
-// (illegal -> silently dropped, yin_yang_logic.py:24-29), test for the end of the game.
 template <int NW>
 __global__ void __launch_bounds__(128) sp_move_kernel(EngineDev e, Geo<NW> g) {
   int gi = blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= e.n_games) return;
-  const long long nb = (long long)gi * e.max_nodes, eb = (long long)gi * e.edges_cap;
-  BB<NW> b = load_bb<NW>(e.sp_black, gi, e.W), w = load_bb<NW>(e.sp_white, gi, e.W);
-  int player = e.sp_player[gi], step = e.sp_step[gi];
-  const int base = e.node_edge_base[nb], cnt = (e.node_flags[nb] & NODE_EXPANDED) ? e.node_n_edges[nb] : 0;
-  // example record (board before the move, visit counts; pi = counts/sum on the host in float64)
-  unsigned long long slot64 = atomicAdd(&e.stats->examples, 1ull);
-  long long slot = (long long)(slot64 % (unsigned long long)e.replay_cap);
-  store_bb<NW>(e.rp_black, slot, e.W, b); store_bb<NW>(e.rp_white, slot, e.W, w);
-  uint16_t* rc = e.rp_counts + slot * e.A;
-  for (int a = 0; a < e.A; ++a) rc[a] = 0;
-  long long total = 0; int maxn = -1, nmax = 0;
-  for (int k = 0; k < cnt; ++k) {
-    int n = e.edge_N[eb + base + k];
-    rc[e.edge_action[eb + base + k]] = (uint16_t)(n > 65535 ? 65535 : n);
-    total += n;
-    if (n > maxn) { maxn = n; nmax = 1; } else if (n == maxn) ++nmax;
-  }
-  e.rp_serial[slot] = e.sp_serial[gi]; e.rp_ply[slot] = (int16_t)step; e.rp_player[slot] = (int8_t)player;
-  // action selection
-  Philox rng(e.seed, (uint64_t)(uint32_t)e.sp_serial[gi], 0x1000ull + (uint64_t)step);
-  int action = -1;
-  if (cnt > 0) {
-    if (step < e.temperature_threshold && total > 0) {       // temperature 1: sample proportional to visits
-      long long r = (long long)(rng.uniform() * (double)total);
-      if (r >= total) r = total - 1;
-      long long acc = 0;
-      for (int k = 0; k < cnt; ++k) { acc += e.edge_N[eb + base + k]; if (r < acc) { action = e.edge_action[eb + base + k]; break; } }
-    } else if (total > 0) {                                    // temperature 0: random choice among the maxima
-      int pick = (int)rng.below((uint32_t)nmax);
-      for (int k = 0; k < cnt; ++k) if (e.edge_N[eb + base + k] == maxn) { if (pick-- == 0) { action = e.edge_action[eb + base + k]; break; } }
-    } else {                                                   // no visits at all: uniform over legal moves
-      action = e.edge_action[eb + base + (int)rng.below((uint32_t)cnt)];
-    }
-  }
-  if (action >= 0) apply_action(g, b, w, player, action);    // getNextState with the real player (self_play.py:163)
-  player = -player; ++step;
-  store_bb<NW>(e.sp_black, gi, e.W, b); store_bb<NW>(e.sp_white, gi, e.W, w);
-  e.sp_player[gi] = (int8_t)player; e.sp_step[gi] = step;
-  atomicAdd(&e.stats->moves, 1ull);
-  int code = ended_code(g, b, w, player);                    // self_play.py:167-168
-  if (code != 0) finish_game(e, gi, code);
+  sp_move_one<NW>(e, g, gi);
+}
+__global__ void sp_budget_kernel(EngineDev e, int moves) {
+  int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi < e.n_games) e.sp_moves_left[gi] = moves;
 }
 
 __global__ void sp_reset_kernel(EngineDev e) {
@@ -202,6 +102,7 @@ __global__ void sp_reset_kernel(EngineDev e) {
   if (gi == 0) { *e.sp_next_serial = 0; Stats z = {}; *e.stats = z; }
   if (gi >= e.n_games) return;
   e.sp_new_game[gi] = 1; e.sp_serial[gi] = -1; e.sp_step[gi] = 0; e.sp_passes[gi] = 0; e.sp_player[gi] = 1;
+  e.sp_phase[gi] = 0; e.sp_moves_left[gi] = 0; e.g_npending[gi] = 0;
   for (int k = 0; k < e.W; ++k) { e.sp_black[(long long)gi * e.W + k] = 0; e.sp_white[(long long)gi * e.W + k] = 0; }
 }
 
@@ -256,6 +157,8 @@ static void carve(const yy_engine_config& c, Carver& k, EngineDev& d) {
   d.sp_black = k.take<uint64_t>(G * W); d.sp_white = k.take<uint64_t>(G * W); d.sp_player = k.take<int8_t>(G);
   d.sp_step = k.take<int32_t>(G); d.sp_passes = k.take<int32_t>(G); d.sp_serial = k.take<int32_t>(G);
   d.sp_new_game = k.take<uint8_t>(G); d.sp_next_serial = k.take<int32_t>(1);
+  d.sp_phase = k.take<uint8_t>(G); d.sp_moves_left = k.take<int32_t>(G); d.act_list = k.take<int32_t>(G);
+  d.game_quota = -1; d.hook_uniform = nullptr; d.hook_noise = nullptr; d.hook_games = 0; d.hook_plies = 0;
   const size_t RC = (size_t)c.replay_capacity;
   d.replay_cap = (int)RC; d.results_cap = (int)(RC + G + 16);
   d.rp_black = k.take<uint64_t>(RC * W); d.rp_white = k.take<uint64_t>(RC * W); d.rp_counts = k.take<uint16_t>(RC * A);
@@ -303,7 +206,7 @@ int engine_forward(yy_engine* e, const uint64_t* black, const uint64_t* white, i
   for (int64_t done = 0; done < count; done += e->nn.max_boards) {
     const int64_t n = (count - done) < e->nn.max_boards ? (count - done) : e->nn.max_boards;
     int rc = nn_fused_run(e->nn, nullptr, e->cfg.rule_flags, black + done * e->dev.W, white + done * e->dev.W, n, policy + done * e->dev.A,
-                          value + done, logits ? logits + done * e->dev.A : nullptr, 1, true, s);
+                          value + done, logits ? logits + done * e->dev.A : nullptr, 1, true, YY_FUSED_FORWARD, s);
     if (rc) return rc;
   }
   return YY_OK;
@@ -321,7 +224,7 @@ int search_core(yy_engine* e, cudaStream_t s) {
   if (e->cfg.leaves_per_step <= 1 && !(e->cfg.mode_flags & YY_MODE_STEP_KERNELS) && e->cfg.evaluator != YY_EVAL_EXTERNAL) {
     // the whole search in ONE persistent kernel: every CTA owns a run of games from the first to the last simulation
     return nn_fused_run(e->nn, &e->dev, e->cfg.rule_flags, e->dev.leaf_black, e->dev.leaf_white, e->dev.n_slots, e->dev.eval_prior,
-                        e->dev.eval_value, nullptr, e->cfg.n_sims + 1, e->cfg.evaluator == YY_EVAL_NN, s);
+                        e->dev.eval_value, nullptr, e->cfg.n_sims + 1, e->cfg.evaluator == YY_EVAL_NN, YY_FUSED_SEARCH, s);
   }
   if (e->cfg.leaves_per_step <= 1) {      // deterministic mode: exactly n_sims + 1 lock-steps, no host synchronisation
     for (int i = 0; i <= e->cfg.n_sims; ++i) {
@@ -392,6 +295,7 @@ yy_engine* yy_engine_create(const yy_engine_config* cfg, void* workspace, int64_
   e->dev.keep_f32 = (float)(1.0 - (double)c.dirichlet_epsilon);
   e->dev.evaluator = c.evaluator; e->dev.mode_flags = c.mode_flags; e->dev.temperature_threshold = c.temperature_threshold;
   e->dev.seed = c.seed;
+  e->dev.max_descents = c.descents_per_step == 0 ? 4 : (c.descents_per_step < 0 ? 0 : c.descents_per_step);
   size_t off = (k.off + 255) & ~(size_t)255;
   if (nn_init(e->nn, c, (char*)workspace + off) != YY_OK) { delete e; return nullptr; }
   sp_reset_kernel<<<thread_grid(c.n_games, 128), 128>>>(e->dev);
@@ -506,24 +410,56 @@ int yy_selfplay_reset(yy_engine* e, void* stream) {
   return YY_OK;
 }
 
+// the persistent kernel plays the games itself unless the search has to run as per-step kernels
+static bool rolling_capable(const yy_engine* e) {
+  return e->cfg.leaves_per_step <= 1 && !(e->cfg.mode_flags & YY_MODE_STEP_KERNELS) && e->cfg.evaluator != YY_EVAL_EXTERNAL;
+}
+static int launch_rolling(yy_engine* e, int moves_per_slot, long long iterations, cudaStream_t s) {
+  sp_budget_kernel<<<thread_grid(e->dev.n_games, 128), 128, 0, s>>>(e->dev, moves_per_slot);
+  YY_LAUNCH_CHECK();
+  if (iterations > 0x7fffffffll) iterations = 0x7fffffffll;
+  return nn_fused_run(e->nn, &e->dev, e->cfg.rule_flags, e->dev.leaf_black, e->dev.leaf_white, e->dev.n_slots, e->dev.eval_prior,
+                      e->dev.eval_value, nullptr, (int)iterations, e->cfg.evaluator == YY_EVAL_NN, YY_FUSED_SELFPLAY, s);
+}
+
 int yy_selfplay_run(yy_engine* e, int32_t n_moves, void* stream) {
   if (!e) return set_error(YY_ERR_INVALID, "null engine");
   if (e->cfg.evaluator == YY_EVAL_EXTERNAL) return set_error(YY_ERR_STATE, "self-play needs the STUB or NN evaluator");
   cudaStream_t s = (cudaStream_t)stream;
+  if (n_moves <= 0) return YY_OK;
+  // ONE launch: every slot makes n_moves moves at its own pace (a search needs at most n_sims + 1 evaluation steps)
+  if (rolling_capable(e)) return launch_rolling(e, n_moves, (long long)n_moves * (e->cfg.n_sims + 1), s);
+  if (e->dev.game_quota >= 0) return set_error(YY_ERR_STATE, "a game quota needs the persistent kernel (leaves_per_step 1, no YY_MODE_STEP_KERNELS)");
   const unsigned grid = thread_grid(e->dev.n_games, 128);
   for (int mv = 0; mv < n_moves; ++mv) {
     YY_DISPATCH_NW(e->dev.A, sp_prepare_kernel<NW><<<grid, 128, 0, s>>>(e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
     YY_LAUNCH_CHECK();
-    if (e->cfg.dirichlet_epsilon > 0.0) {
-      YY_DISPATCH_NW(e->dev.A, sp_noise_kernel<NW><<<grid, 128, 0, s>>>(e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
-      YY_LAUNCH_CHECK();
-    } else {
-      YY_CUDA_OK(cudaMemsetAsync(e->dev.noise_mask, 0, (size_t)e->dev.n_games, s));
-    }
+    YY_DISPATCH_NW(e->dev.A, sp_noise_kernel<NW><<<grid, 128, 0, s>>>(e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
+    YY_LAUNCH_CHECK();
     int rc = search_core(e, s); if (rc) return rc;
     YY_DISPATCH_NW(e->dev.A, sp_move_kernel<NW><<<grid, 128, 0, s>>>(e->dev, make_geo<NW>(e->cfg.rows, e->cfg.cols, e->cfg.rule_flags)));
     YY_LAUNCH_CHECK();
   }
+  return YY_OK;
+}
+
+int yy_selfplay_advance(yy_engine* e, int64_t iterations, void* stream) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  if (!rolling_capable(e)) return set_error(YY_ERR_STATE, "yy_selfplay_advance needs the persistent kernel (STUB or NN evaluator, leaves_per_step 1)");
+  if (iterations <= 0) return YY_OK;
+  return launch_rolling(e, kMovesUnlimited, iterations, (cudaStream_t)stream);
+}
+
+int yy_selfplay_set_quota(yy_engine* e, int64_t total_games) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  e->dev.game_quota = total_games < 0 ? -1 : (long long)total_games;
+  return YY_OK;
+}
+
+int yy_selfplay_set_random_stream(yy_engine* e, const double* uniforms_dev, const double* noise_dev, int32_t n_games, int32_t n_plies) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  if ((uniforms_dev || noise_dev) && (n_games <= 0 || n_plies <= 0)) return set_error(YY_ERR_INVALID, "recorded stream needs n_games, n_plies > 0");
+  e->dev.hook_uniform = uniforms_dev; e->dev.hook_noise = noise_dev; e->dev.hook_games = n_games; e->dev.hook_plies = n_plies;
   return YY_OK;
 }
 
@@ -534,6 +470,7 @@ int yy_selfplay_get_stats(yy_engine* e, yy_selfplay_stats* out, void* stream) {
   YY_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
   out->moves = (int64_t)h.moves; out->evals = (int64_t)h.evals; out->games_finished = (int64_t)h.games_finished;
   out->examples = (int64_t)h.examples; out->sims = (int64_t)h.sims; out->overflow = h.overflow; out->max_depth = h.max_depth;
+  out->tower_evals = (int64_t)h.tower_evals;
   if (h.overflow) return set_error(YY_ERR_CAPACITY, "a tree arena overflowed: raise edges_per_game");
   return YY_OK;
 }

@@ -145,8 +145,13 @@ __device__ __forceinline__ void expand_and_backup(const EngineDev& e, const Geo<
 //   K  > 1 : throughput mode -- each in-flight simulation leaves a virtual visit and a virtual loss on its path so
 //            that the next descent of the same step diverges; a descent that runs into an in-flight node stops.
 // `pending_counter` (nullable): incremented by the number of leaves this game published.
+// `max_descents` > 0 bounds the simulations started in this call: a game whose simulations keep ending in revisited
+// terminals would otherwise hold its warp (and, in the persistent kernel, its whole CTA pair) for many dependent
+// descents; it resumes in the next step instead, without a leaf in between (g_npending = -1: "still selecting").
+// Returns the number of leaves published; 0 = the search is complete; -1 = still selecting.
 template <int NW>
-__device__ __forceinline__ void tree_step_game(const EngineDev& e, const Geo<NW>& g, int gi, int lane, int32_t* pending_counter) {
+__device__ __forceinline__ int tree_step_game(const EngineDev& e, const Geo<NW>& g, int gi, int lane, int32_t* pending_counter,
+                                              int max_descents = 0) {
   const long long nb = (long long)gi * e.max_nodes;
   const long long eb = (long long)gi * e.edges_cap;
   const bool multi = e.K > 1;
@@ -163,9 +168,10 @@ __device__ __forceinline__ void tree_step_game(const EngineDev& e, const Geo<NW>
   }
 
   // ---------------------------------------------------------------- (2) select
-  int np = 0;
+  int np = 0, descents = 0;
   bool blocked = false;
   while (sims_done + np < e.n_sims && np < e.K && !blocked) {
+    if (max_descents > 0 && descents++ >= max_descents) break;
     const int slot = gi * e.K + np;
     int32_t* path = e.leaf_path + (long long)slot * e.max_depth;
     int node = 0, depth = 0;
@@ -243,14 +249,16 @@ __device__ __forceinline__ void tree_step_game(const EngineDev& e, const Geo<NW>
     }
   }
   __syncwarp();
+  const bool selecting = np == 0 && !blocked && sims_done < e.n_sims;     // stopped by max_descents
   if (lane == 0) {
     e.g_sims_done[gi] = sims_done;
-    e.g_npending[gi] = np;
+    e.g_npending[gi] = selecting ? -1 : np;
     if (np && pending_counter) atomicAdd(pending_counter, np);
     if (sims_here) atomicAdd(&e.stats->sims, (unsigned long long)sims_here);
     if (evals_here) atomicAdd(&e.stats->evals, (unsigned long long)evals_here);
     if (deepest > e.stats->max_depth) atomicMax(&e.stats->max_depth, deepest);
   }
+  return selecting ? -1 : np;
 }
 
 }  // namespace yy

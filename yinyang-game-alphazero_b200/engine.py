@@ -268,6 +268,7 @@ class Stats:
     sims: int
     overflow: int
     max_depth: int
+    tower_evals: int = 0
 
 
 class Engine:
@@ -276,7 +277,7 @@ class Engine:
     def __init__(self, rows=8, cols=8, n_games=1, n_sims=800, evaluator="stub", cpuct=1.0, rule_flags=0,
                  search_as_black=True, edges_per_game=0, dirichlet_alpha=0.3, dirichlet_epsilon=0.25,
                  temperature_threshold=10, seed=0, replay_capacity=0, state_dict=None, nn_channels=128, nn_blocks=10,
-                 device=None, leaves_per_step=1, step_kernels=False):
+                 device=None, leaves_per_step=1, step_kernels=False, descents_per_step=0):
         _require_cuda()
         self.L = _lib.lib()
         self.rows, self.cols, self.A, self.W = rows, cols, rows * cols, bitboard.words_for(rows, cols)
@@ -298,7 +299,8 @@ class Engine:
                                      mode_flags=(MODE_SEARCH_AS_BLACK if search_as_black else 0) | (MODE_STEP_KERNELS if step_kernels else 0), evaluator=ev,
                                      edges_per_game=edges_per_game, temperature_threshold=temperature_threshold,
                                      replay_capacity=replay_capacity, nn_channels=nn_channels, nn_blocks=nn_blocks,
-                                     device=self.device, leaves_per_step=self.leaves_per_step, cpuct=cpuct, dirichlet_alpha=dirichlet_alpha,
+                                     device=self.device, leaves_per_step=self.leaves_per_step, cpuct=cpuct, descents_per_step=int(descents_per_step),
+                                     dirichlet_alpha=dirichlet_alpha,
                                      dirichlet_epsilon=dirichlet_epsilon, seed=seed)
         need = self.L.yy_engine_workspace_bytes(ctypes.byref(self.cfg))
         if need < 0:
@@ -435,13 +437,41 @@ class Engine:
         _lib.check(self.L.yy_selfplay_reset(self.handle, _stream()))
 
     def selfplay_run(self, n_moves: int):
-        """Asynchronous: enqueues n_moves full searches + moves per game slot on the current stream."""
+        """Asynchronous: enqueues n_moves full searches + moves per game slot on the current stream (one launch of the
+        persistent kernel; the slots advance independently)."""
         _lib.check(self.L.yy_selfplay_run(self.handle, int(n_moves), _stream()))
+
+    def selfplay_advance(self, iterations: int):
+        """Rolling self-play: `iterations` evaluation steps (one leaf per game slot per step) in one launch; searches in
+        progress continue with the next call.  Completed moves / games: stats()."""
+        _lib.check(self.L.yy_selfplay_advance(self.handle, int(iterations), _stream()))
+
+    def selfplay_set_quota(self, total_games):
+        """At most total_games games are started since the last reset (None / negative: unlimited)."""
+        _lib.check(self.L.yy_selfplay_set_quota(self.handle, -1 if total_games is None else int(total_games)))
+
+    def selfplay_set_random_stream(self, uniforms=None, noise=None):
+        """Recorded random stream (yy_selfplay_set_random_stream): uniforms float64[n_games, n_plies], noise float64[n_games, A]
+        (numpy or device tensors).  None, None restores Philox."""
+        def dev(x):
+            if x is None:
+                return None
+            t = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+            return t.to(device=self.tdev, dtype=torch.float64).contiguous()
+        u, z = dev(uniforms), dev(noise)
+        if z is not None:
+            assert z.shape[1] == self.A
+        ng = int(u.shape[0]) if u is not None else (int(z.shape[0]) if z is not None else 0)
+        if u is not None and z is not None:
+            assert u.shape[0] == z.shape[0]
+        npl = int(u.shape[1]) if u is not None else (1 if z is not None else 0)
+        self._random_stream = (u, z)                                   # the engine keeps the pointers: keep them alive
+        _lib.check(self.L.yy_selfplay_set_random_stream(self.handle, _ptr(u), _ptr(z), ng, npl))
 
     def stats(self) -> Stats:
         s = _lib.SelfPlayStats()
         _lib.check(self.L.yy_selfplay_get_stats(self.handle, ctypes.byref(s), _stream()))
-        return Stats(s.moves, s.evals, s.games_finished, s.examples, s.sims, s.overflow, s.max_depth)
+        return Stats(s.moves, s.evals, s.games_finished, s.examples, s.sims, s.overflow, s.max_depth, s.tower_evals)
 
     def replay(self):
         """Copies the replay ring to the host: dict(boards int8[N,n,m], counts uint16[N,A], pi float64[N,A],
