@@ -12,7 +12,9 @@
 // Nothing returns to the host between simulations: a search is one launch instead of 4 x (n_sims + 1).
 // The same kernel with iterations = 1 and the tree step off is the batched network forward (yy_evaluate).
 //
-// Warp roles (as in tower_kernel): warp 0 weight producer, warp 1 MMA issuer, warps 2-17 epilogue / heads / tree.
+// Warp roles: warp 0 weight producer, warp 1 MMA issuer, warps 2-17 epilogue / heads / tree, warps 18-19 background
+// selection (simulations that end in revisited terminals need no evaluation, mcts.py:365-367: games in such a stretch
+// are advanced here, concurrently with the tower, instead of holding up the tree phase of their CTA pair).
 // Roofline: tensor (the tower's conv MMAs are > 99 % of the FLOPs; see yy_nn.cu for the tower layout).
 #include "yy_nn.cuh"
 #include "yy_tower.cuh"
@@ -45,7 +47,9 @@ __device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v
 }
 
 constexpr int kEpiBarrier = 1;   // named barrier of the 16 epilogue warps
+constexpr int kTreeBarrier = 2;  // epilogue + background selection warps: every tree step of the CTA is done
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(TW_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void tree_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kTreeBarrier), "n"(TW_EPI_THREADS + 32 * TW_BG_WARPS) : "memory"); }
 
 // CG = 1: one CTA per SM, M = 128 MMAs.  CG = 2: CTA pairs (cluster of 2, tcgen05 cta_group::2): the leader issues M = 256
 // MMAs over both CTAs' activation tiles, each CTA stages only its half of the weight slice's output channels -- halves
@@ -339,6 +343,29 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         }
       }
     }
+  } else if (warp >= 2 + TW_EPI_WARPS) {
+    // =========================================================== background selection warps: while the tower runs, they
+    // advance the games of my run that are "still selecting" (tree_step_game stopped on max_descents without reaching a
+    // leaf that needs an evaluation), one simulation at a time, until the game has a leaf (or has completed its search:
+    // then its move and the root of its next search) or the epilogue warps reach this step's tree phase.
+    const int bw = warp - 2 - TW_EPI_WARPS;
+    volatile int* stop = cnt_s + 8;
+    for (int iter = 0; dyn && iter < a.iterations; ++iter) {
+      fetch_counts(iter);
+      if (!any_work) break;
+      if (n_struct > 0) {       // (without a tower pass the epilogue warps take these games themselves)
+        const int32_t* sel = e.act_list + run_lo + my_len - 1;
+        for (int k = bw; k < n_sel; k += TW_BG_WARPS) {
+          const int gi = sel[-k];
+          do {      // at least one simulation per game and step: a search of S simulations ends within 2 (S + 1) steps
+            const int np = tree_step_game<NW>(e, geo, gi, lane, nullptr, 1);
+            if (np == 0 && a.mode == YY_FUSED_SELFPLAY) sp_advance_game<NW>(e, geo, gi, lane);
+            if (np != -1) break;
+          } while (*stop != iter + 1);
+        }
+      }
+      if (iter + 1 < a.iterations) tree_sync();
+    }
   } else {
     // =========================================================== epilogue warps (2..17): warp -> (tile, lane quarter)
     const int ew = warp - 2;
@@ -401,10 +428,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
       epi_sync();
       compact(0);
     }
-    // games whose last simulations all ended in revisited terminals (max_descents): no evaluation in this step, the
-    // selection goes on -- in the same phase as the tree steps of the evaluated games, on the warps those left idle
+    // a step without a tower pass (no game of the pair has a pending leaf): the epilogue warps advance the games that
+    // are still selecting themselves
     auto run_selecting = [&]() {
-      for (int k = (ew + TW_EPI_WARPS - n_mine % TW_EPI_WARPS) % TW_EPI_WARPS; k < n_sel; k += TW_EPI_WARPS) {
+      for (int k = ew; k < n_sel; k += TW_EPI_WARPS) {
         const int gi = my_list[my_len - 1 - k];
         const int np = tree_step_game<NW>(e, geo, gi, lane, nullptr, e.max_descents);
         if (np == 0 && a.mode == YY_FUSED_SELFPLAY) sp_advance_game<NW>(e, geo, gi, lane);
@@ -590,6 +617,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         }
 
         // ---- per board: softmax over all A logits (predict, neural_network.py:152), value_fc2 + tanh (:121), tree step
+        if (dyn && slim == n_struct && etid == 0) *(cnt_s + 8) = iter + 1;    // last tree phase of the step: background warps wind up
         for (int b = ew; b < nbb; b += TW_EPI_WARPS) {
           const long long board = board_of(bb0 + b);
           if (a.use_nn) {
@@ -616,7 +644,6 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
             if (np == 0 && a.mode == YY_FUSED_SELFPLAY) sp_advance_game<NW>(e, geo, (int)board, lane);
           }
         }
-        if (slim == n_struct) run_selecting();       // with the last batch of the step
         phase(2);
         if (a.use_nn) {
           epi_sync();     // scratch consumed, new leaves published
@@ -628,7 +655,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
       }
       if (n_struct == 0) run_selecting();
       if (dyn && iter + 1 < a.iterations) {
-        epi_sync();       // every game of my run has had its tree step
+        tree_sync();      // every tree step of this CTA is done (epilogue and background warps)
         compact(iter + 1);
       }
     }

@@ -30,7 +30,8 @@ constexpr int TW_ROWS = 680;            // activation rows: flat 512+2*24, row-a
 constexpr int TW_STAGES = 3;
 constexpr int TW_STAGE_BYTES = 16384;
 constexpr int TW_EPI_WARPS = 16;           // one (tile, TMEM-lane-quarter) pair per warp
-constexpr int TW_THREADS = 64 + 32 * TW_EPI_WARPS;
+constexpr int TW_BG_WARPS = 2;             // background selection warps (games whose simulations end without an evaluation)
+constexpr int TW_THREADS = 64 + 32 * TW_EPI_WARPS + 32 * TW_BG_WARPS;
 constexpr int TW_EPI_THREADS = 32 * TW_EPI_WARPS;
 
 constexpr int SM_ACT = 0;
@@ -42,7 +43,7 @@ constexpr int TW_FC_EXTRA_OFF = 136 * 1024;   // (the FC feature panel ends at 1
 constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_FC_SLOTS + 2);   // full, empty, peer-full per slot + acc_full, act_ready
 constexpr int SM_BIAS = (SM_TMEM + 16 + 15) & ~15;                                 // current / next layer's 128 fp32 biases (double buffer)
 constexpr int SM_CNT = SM_BIAS + 2 * TW_C * 4;            // counts of the CTA (pair): [step parity][cluster rank][pending leaves, selecting]
-constexpr int SM_TOTAL = SM_CNT + 32;
+constexpr int SM_TOTAL = SM_CNT + 48;                    // 8 counts + the background warps' stop flag
 static_assert(SM_TOTAL <= 232448, "persistent kernel exceeds the 227 KB opt-in shared memory of sm_100");
 static_assert(TW_FC_EXTRA_OFF + (TW_FC_SLOTS - TW_STAGES) * TW_STAGE_BYTES <= TW_CHUNKS * TW_ROWS * 16, "FC slots exceed the activation region");
 

@@ -223,8 +223,9 @@ int search_core(yy_engine* e, cudaStream_t s) {
   int rc = launch_root(e, s); if (rc) return rc;
   if (e->cfg.leaves_per_step <= 1 && !(e->cfg.mode_flags & YY_MODE_STEP_KERNELS) && e->cfg.evaluator != YY_EVAL_EXTERNAL) {
     // the whole search in ONE persistent kernel: every CTA owns a run of games from the first to the last simulation
+    // (the launch ends as soon as no game has work left; a game advances by at least one simulation every two steps)
     return nn_fused_run(e->nn, &e->dev, e->cfg.rule_flags, e->dev.leaf_black, e->dev.leaf_white, e->dev.n_slots, e->dev.eval_prior,
-                        e->dev.eval_value, nullptr, e->cfg.n_sims + 1, e->cfg.evaluator == YY_EVAL_NN, YY_FUSED_SEARCH, s);
+                        e->dev.eval_value, nullptr, 2 * (e->cfg.n_sims + 1), e->cfg.evaluator == YY_EVAL_NN, YY_FUSED_SEARCH, s);
   }
   if (e->cfg.leaves_per_step <= 1) {      // deterministic mode: exactly n_sims + 1 lock-steps, no host synchronisation
     for (int i = 0; i <= e->cfg.n_sims; ++i) {
@@ -427,8 +428,9 @@ int yy_selfplay_run(yy_engine* e, int32_t n_moves, void* stream) {
   if (e->cfg.evaluator == YY_EVAL_EXTERNAL) return set_error(YY_ERR_STATE, "self-play needs the STUB or NN evaluator");
   cudaStream_t s = (cudaStream_t)stream;
   if (n_moves <= 0) return YY_OK;
-  // ONE launch: every slot makes n_moves moves at its own pace (a search needs at most n_sims + 1 evaluation steps)
-  if (rolling_capable(e)) return launch_rolling(e, n_moves, (long long)n_moves * (e->cfg.n_sims + 1), s);
+  // ONE launch: every slot makes n_moves moves at its own pace (a search needs at most 2 (n_sims + 1) steps, usually
+  // n_sims + 1 or fewer); the launch ends when the last slot has made its moves
+  if (rolling_capable(e)) return launch_rolling(e, n_moves, 2ll * n_moves * (e->cfg.n_sims + 1), s);
   if (e->dev.game_quota >= 0) return set_error(YY_ERR_STATE, "a game quota needs the persistent kernel (leaves_per_step 1, no YY_MODE_STEP_KERNELS)");
   const unsigned grid = thread_grid(e->dev.n_games, 128);
   for (int mv = 0; mv < n_moves; ++mv) {
