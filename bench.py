@@ -30,8 +30,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ROWS = COLS = 8
-GAMES_PER_GPU = int(os.environ.get("YY_BENCH_GAMES", 4096))
-SIMS = int(os.environ.get("YY_BENCH_SIMS", 800))
+GAMES_PER_GPU = 4096
+SIMS = 800
 CHANNELS, BLOCKS = 128, 10
 A = ROWS * COLS
 # algorithmic FLOPs (2*MAC) per leaf evaluation, SURVEY 8d / BASELINE.md section 3
@@ -96,16 +96,36 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
-def cpu_selfplay_sample(workers, searches_per_worker=1, sims=SIMS):
-    """(moves/s, cores, description): oracle port, one process per core, 1 torch thread each, empty 8x8 root."""
+PLY_SPREAD = 25        # CPU samples search positions after 0..24 random plies: the plies the GPU arm's timed region covers
+
+
+def cpu_selfplay_sample(workers, searches_per_worker=1, sims=SIMS, rows=ROWS, cols=COLS):
+    """(moves/s, cores, description): oracle port, one process per core, 1 torch thread each.  Worker i searches (as
+    player 1, like self_play.py:135) the position reached after (i * 25) // workers uniformly random legal plies."""
     from oracle import port
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
+    jobs = [(rows, cols, sims, searches_per_worker, CHANNELS, BLOCKS, 1, i, (i * PLY_SPREAD) // workers) for i in range(workers)]
     with ctx.Pool(workers) as pool:
-        times = pool.map(port._worker, [(ROWS, COLS, sims, searches_per_worker, CHANNELS, BLOCKS, 1, i) for i in range(workers)])
+        times = pool.map(port._worker, jobs)
     total = workers * searches_per_worker
-    return total / max(times), workers, (f"{total} searches of {sims} sims from the empty 8x8 board, {workers} worker processes x 1 torch thread "
-                                        f"(reference scaling axis: --workers), slowest worker {max(times):.1f}s")
+    return total / max(times), workers, (f"{total} searches of {sims} sims on {rows}x{cols} from random-play positions at plies 0..{PLY_SPREAD - 1} "
+                                        f"(one per worker), {workers} worker processes x 1 torch thread (reference scaling axis: --workers), "
+                                        f"slowest worker {max(times):.1f}s, fastest {min(times):.1f}s")
+
+
+def cpu_env_sample(workers, steps_per_worker=1500):
+    """(steps/s one core, steps/s all cores): the reference's Python env loop (getValidMoves + getNextState + getGameEnded,
+    random play; oracle/port.py env_steps) on one core and on one process per core."""
+    from oracle import port
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    port.env_steps(ROWS, COLS, steps_per_worker, seed=0)
+    one = steps_per_worker / (time.perf_counter() - t0)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        times = pool.map(port._env_worker, [(ROWS, COLS, steps_per_worker, i) for i in range(workers)])
+    return one, workers * steps_per_worker / max(times)
 
 
 def cpu_cores():
@@ -115,16 +135,19 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
+def cpu_workers():
+    return max(1, min(cpu_cores(), 64))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    workers = max(1, min(cpu_cores(), int(os.environ.get("YY_CPU_WORKERS", 64))))
-    sims = SIMS
+    workers = cpu_workers()
     vals = []
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_selfplay_sample(workers, 1, sims)
+        v, cores, sample = cpu_selfplay_sample(workers, 1, SIMS)
         if i >= args.warmup:
             vals.append(v)
     value = sum(vals) / len(vals)
@@ -143,11 +166,65 @@ def workload_config(n_gpus):
                         f"128ch x 10 residual blocks, reference random init (torch.manual_seed(0)); weak scaling",
             "board": "8x8", "sims_per_move": SIMS, "games_per_gpu": GAMES_PER_GPU, "global_games": GAMES_PER_GPU * n_gpus,
             "network": "128x10", "parallelism": f"games sharded over {n_gpus} GPU(s), no data-path collective",
+            "step": f"one launch of the persistent kernel = {SIMS + 1} evaluation steps (the budget of one full search) for every game slot; "
+                    "games are rolling (a slot whose search is complete makes its move and starts the next search at once), so the moves a "
+                    "step completes are counted by the device, not assumed",
             "semantics": "deterministic sequential MCTS per game (1 leaf/game/step), search-as-black (reference self_play.py:99,135)",
             "l2_policy": "inputs larger than L2: per step the kernels stream 801 x 7.3 MB of weights from L2 and the tree arenas (3.8 GB) live in HBM"}
 
 
+def flops_per_leaf(rows, cols):
+    A_ = rows * cols
+    return 2 * A_ * (9 * 5 * CHANNELS + BLOCKS * 2 * 9 * CHANNELS * CHANNELS + CHANNELS * 64) + 2 * (32 * A_ * A_ + 32 * A_ * 256 + 256)
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
+def timed_rolling(eng, torch, dist, world, iters, warmup, steps, barrier):
+    """warmup + steps launches of `iters` evaluation steps; returns (ms max over ranks, moves of all ranks, evaluations of
+    this rank, kernel profile of this rank), all inside the timed region."""
+    for _ in range(warmup):
+        eng.selfplay_advance(iters)
+    barrier()
+    st0 = eng.stats()
+    eng.set_profiling(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        eng.selfplay_advance(iters)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = eng.get_profile()
+    eng.set_profiling(False)
+    st = eng.stats()
+    moves, evals = st.moves - st0.moves, st.tower_evals - st0.tower_evals
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        t = torch.tensor([moves], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        moves = int(t.item())
+    return ms, moves, evals, prof, st
+
+
+def tensor_roofline(peaks, evals, prof, ms, flops_leaf, extra=None):
+    tower_s = prof["ms"] * 1e-3 / max(1, prof["launches"])
+    per_launch = evals / max(1, prof["launches"])
+    achieved = flops_leaf * per_launch / tower_s / 1e12 if prof["launches"] else None
+    roof = {"bound": "tensor", "kernel": "fused_kernel (persistent search: tower + FC heads + tree step + episode driver, yy_fused.cu)",
+            "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": (achieved / peaks["bf16_tflops_sustained"]) if achieved else None,
+            "peak_source": f"bf16_tflops_sustained of {peaks['source']} (kernel timed inside a long step)",
+            "launches_timed": prof["launches"], "avg_launch_ms": tower_s * 1e3, "share_of_step": prof["ms"] / ms if ms else None,
+            "algorithmic_flops_per_launch": flops_leaf * per_launch, "leaf_evaluations_per_launch": per_launch,
+            "evaluations": "required ones only: the kernel evaluates a board only when a game has a pending leaf (device counter "
+                           "tower_evals = leaves requested by the searches + their roots)"}
+    if extra:
+        roof.update(extra)
+    return roof
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -164,80 +241,104 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = measured_peaks()
 
-    # weights: reference init on rank 0, packed, broadcast over NCCL (north star: weights broadcast)
-    torch.manual_seed(0)
-    sd = network._Params(ROWS, COLS, CHANNELS, BLOCKS).state_dict()   # reference layout + initialisation (neural_network.py:39-92)
-    eng = engine.Engine(rows=ROWS, cols=COLS, n_games=GAMES_PER_GPU, n_sims=SIMS, evaluator="nn", state_dict=sd,
-                        seed=0xC0FFEE + rank, replay_capacity=GAMES_PER_GPU * (2 * (args.steps + args.warmup) + 8))
-    t_bcast = yyd.broadcast_weights(eng) if world > 1 else 0.0
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # one step = ONE launch of the persistent kernel: SIMS + 1 evaluation steps (the budget of one full search) for every
-    # game slot.  The games are rolling: a slot whose search is complete makes its move and roots the next search at once,
-    # so the moves a step completes are COUNTED (device counter), not assumed.
+    # weights: reference init on rank 0, packed, broadcast over NCCL (north star: weights broadcast)
+    torch.manual_seed(0)
+    sd = network._Params(ROWS, COLS, CHANNELS, BLOCKS).state_dict()   # reference layout + initialisation (neural_network.py:39-92)
     iters = SIMS + 1
-    for _ in range(args.warmup):
-        eng.selfplay_advance(iters)
-    barrier()
-    st0 = eng.stats()
+    eng = engine.Engine(rows=ROWS, cols=COLS, n_games=GAMES_PER_GPU, n_sims=SIMS, evaluator="nn", state_dict=sd,
+                        seed=0xC0FFEE + rank, replay_capacity=GAMES_PER_GPU * (2 * (args.steps + args.warmup) + 8))
+    t_bcast = t_bcast_first = 0.0
+    if world > 1:
+        t_bcast_first = yyd.broadcast_weights(eng)     # first collective of the process: NCCL sets its communicator up here
+        t_bcast = yyd.broadcast_weights(eng)           # the 7.3 MB broadcast itself
+
+    launches1 = engine._lib.lib().yy_launch_count()
     sampler = ClockSampler(local)
     sampler.start()
-    eng.set_profiling(True)
-    launches1 = engine._lib.lib().yy_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        eng.selfplay_advance(iters)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    prof = eng.get_profile()
-    eng.set_profiling(False)
+    ms, moves, evals_timed, prof, st = timed_rolling(eng, torch, dist, world, iters, args.warmup, args.steps, barrier)
     clocks = sampler.stop()
-    launches = engine._lib.lib().yy_launch_count() - launches1
-    st = eng.stats()
-    moves = st.moves - st0.moves                         # searches completed inside the timed region, this rank
-    evals_timed = st.tower_evals - st0.tower_evals       # boards the kernel evaluated, every one a pending leaf
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        t = torch.tensor([moves], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        moves = int(t.item())
+    launches = engine._lib.lib().yy_launch_count() - launches1 - 2 * args.warmup
     value = moves / (ms * 1e-3)
 
     # replay gather (north star: gather replay samples over NCCL), outside the timed region
     t_gather, n_records = (yyd.gather_replay_counts(eng) if world > 1 else (0.0, min(st.examples, eng.replay_capacity)))
 
-    # ---- e2e: host-buffer search API, copies inside the timed region
-    e2e_steps = max(1, args.steps)
-    boards, players = eng.live_boards()
-    players_s = np.ones_like(players)            # reference semantics: search as player 1 (self_play.py:135)
-    rng = np.random.default_rng(rank)
-    eng.search_host(boards, players_s)           # one untimed call: pinned staging buffers, host caches
-    h2d = boards.shape[0] * (2 * 8 + 1) * 2 + boards.shape[0] * 4
-    d2h = boards.shape[0] * A * 4 + boards.shape[0] * (2 * 8 + 1)
+    # ---- e2e: the same rolling self-play with HOST buffers: per step the packed weight image goes host -> device (pinned) and every
+    # example the step produced comes back device -> host (positions, visit counts, game ids, results), all inside the timed region.
+    # The read-back of step k runs on a second stream while step k + 1 computes (a stream-ordered snapshot of the device counters
+    # taken right after step k says which records are complete).
+    e2e_steps = max(1, min(args.steps, 10))
+    img_host = weights.pack_state_dict(sd, ROWS, COLS)
+    pinned = torch.from_numpy(img_host).pin_memory()
+    rec_bytes = 2 * 8 * eng.W + 2 * A + 4 + 2 + 1
+    side = torch.cuda.Stream()
+    snaps = [torch.empty(7, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    evs = [torch.cuda.Event() for _ in range(2)]
+    sview = eng.stats_view()
+    state = {"cursor": eng.stats().examples, "d2h": 0, "records": 0}
+
+    def launch(k):
+        eng.weight_image.copy_(pinned, non_blocking=True)           # H2D: this step's input (the network the games are played with)
+        eng.selfplay_advance(iters)
+        snaps[k & 1].copy_(sview, non_blocking=True)                # which records exist once step k is complete
+        evs[k & 1].record()
+
+    def drain(k):
+        evs[k & 1].synchronize()
+        stop = int(snaps[k & 1][3])
+        with torch.cuda.stream(side):
+            rec = eng.replay_window(state["cursor"], stop)          # D2H: the step's examples (pinned staging, side stream)
+            res = engine._to_host(eng.replay_views()["results"])[0]
+        state["d2h"] += (stop - state["cursor"]) * rec_bytes + res.nbytes
+        state["records"] += len(rec["ply"])
+        state["cursor"] = stop
+
+    launch(0); drain(0)                                             # untimed: staging buffers, caches
     barrier()
+    state.update(d2h=0, records=0)
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        counts, _ = eng.search_host(boards, players_s)
-        tot = counts.sum(axis=1)
-        # temperature-1 sampling proportional to the visit counts (self_play.py:145-152), vectorised over the games
-        cdf = np.cumsum(counts, axis=1)
-        acts = np.where(tot > 0, (cdf > (rng.random(len(tot)) * tot)[:, None]).argmax(axis=1), -1).astype(np.int32)
-        boards, players = engine.next_state_host(boards, players, acts, ROWS, COLS)
+    for k in range(e2e_steps):
+        launch(k)
+        if k > 0:
+            drain(k - 1)
+    drain(e2e_steps - 1)
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_moves, d2h = state["records"], state["d2h"]
     if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = GAMES_PER_GPU * world * e2e_steps / e2e_s
+        t = torch.tensor([e2e_moves], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_moves = int(t.item())
+    e2e_value = e2e_moves / e2e_s
+    # the host-buffer SEARCH API (MCTS.search for a batch of positions), lock-step: numpy boards in, visit counts out
+    boards, players = eng.live_boards()
+    players_s = np.ones_like(players)
+    eng.search_host(boards, players_s)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        eng.search_host(boards, players_s)
+    search_api = 2 * GAMES_PER_GPU / (time.perf_counter() - t0)
+    eng.close(); del eng
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations (rank 0; 2 steps each), a strong-scaled configs[3] line, a tree-only leg
+    other = {}
+    if rank == 0:
+        other["configs[0] 6x6/100 sims"] = bench_config(engine, network, torch, peaks, 6, 100, 4096, steps=3, iters=8 * 101)
+        other["configs[4] 16x16/1600 sims (per-GPU share of 32,768 games)"] = bench_config(engine, network, torch, peaks, 16, 1600, 4096, steps=2, iters=801)
+        other["tree only (stub evaluator) 8x8/800"] = bench_tree_only(engine, torch, peaks)
+    strong = None
+    if world > 1:
+        strong = bench_strong(engine, torch, dist, world, rank, sd, peaks, barrier)
 
     # ---- env steps/s (BASELINE.json configs[1]): 65,536 synthetic random-play boards on this GPU
     env = bench_env(engine, torch, peaks) if rank == 0 else None
@@ -249,41 +350,102 @@ def run_b200(args):
     ai_move_leg = bench_ai_move() if rank == 0 else None
 
     if rank == 0:
-        tower_s = prof["ms"] * 1e-3 / max(1, prof["launches"])
-        boards_per_launch = evals_timed / max(1, prof["launches"])      # required evaluations (device counter), not slots x steps
-        # the persistent search kernel runs tower + FC heads + tree steps of every simulation: one launch per move step
-        achieved = FLOPS_PER_LEAF * boards_per_launch / tower_s / 1e12 if prof["launches"] else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "tower_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roof = {"bound": "tensor", "kernel": "fused_kernel (persistent search: tower + FC heads + tree step, yy_fused.cu)", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_tflops_sustained"]) if achieved else None, "traffic": traffic,
-                "peak_source": f"bf16_tflops_sustained of {peaks['source']} (kernel timed inside a long step)",
-                "launches_timed": prof["launches"], "avg_launch_ms": tower_s * 1e3,
-                "share_of_step": prof["ms"] / ms if ms else None,
-                "algorithmic_flops_per_launch": FLOPS_PER_LEAF * boards_per_launch,
-                "leaf_evaluations_per_launch": boards_per_launch}
+        roof = tensor_roofline(peaks, evals_timed, prof, ms, FLOPS_PER_LEAF, {"traffic": traffic})
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            workers = max(1, min(cpu_cores(), int(os.environ.get("YY_CPU_WORKERS", 64))))
-            v, cores, sample = cpu_selfplay_sample(workers, 1, SIMS)
+            v, cores, sample = cpu_selfplay_sample(cpu_workers(), 1, SIMS)
             cpu = {"value": v, "unit": "moves/s", "cores": cores, "kind": "port", "sample": sample}
+            one, allc = cpu_env_sample(cpu_workers())
+            env["cpu_baseline"] = {"value": allc, "unit": "steps/s", "cores": cpu_workers(), "kind": "port", "one_core": one,
+                                   "sample": "1,500 random-play env steps (mask + step + ended) per worker process, oracle/port.py env_steps"}
         line = {"metric": "self-play moves/sec (8x8, 800 sims)", "value": value, "unit": "moves/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(world), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "api": "Engine.search_host + next_state_host (numpy in/out)"},
+                "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": int(img_host.nbytes), "d2h_bytes_per_step": int(d2h // e2e_steps),
+                        "steps": e2e_steps, "moves": int(e2e_moves), "seconds": e2e_s,
+                        "api": "Engine.selfplay_advance with host buffers: weight image H2D from pinned memory, every example of "
+                               "the step D2H (Engine.replay_window + results table) while the next step computes",
+                        "search_api": {"value": search_api, "unit": "moves/s", "api": "Engine.search_host (numpy boards in, visit counts out; lock-step batch of 4,096 searches)"}},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "env": env, "dataset": dataset, "learner": learner_leg, "ai_move": ai_move_leg,
                 "moves_per_s_roofline": peaks["bf16_tflops_sustained"] * 1e12 / ((SIMS + 1) * FLOPS_PER_LEAF) * world,
-                "leaf_evals_per_s": evals_timed / (ms * 1e-3), "moves_timed": int(moves), "evals_per_move": evals_timed * world / max(1, moves),
-                "nccl": {"weight_broadcast_s": t_bcast, "replay_gather_s": t_gather, "replay_records_gathered": int(n_records)},
+                "moves_per_s_roofline_note": "at SIMS + 1 evaluations per move; a search whose simulations revisit terminal nodes needs fewer (evals_per_move)",
+                "leaf_evals_per_s": evals_timed * world / (ms * 1e-3), "moves_timed": int(moves), "evals_per_move": evals_timed * world / max(1, moves),
+                "other_configs": other, "strong_scaling_configs3": strong,
+                "nccl": {"weight_broadcast_s": t_bcast, "first_collective_s": t_bcast_first, "replay_gather_s": t_gather, "replay_records_gathered": int(n_records)},
                 "selfplay_stats": st.__dict__}
         emit(line)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_config(engine, network, torch, peaks, n, sims, games, steps, iters):
+    """Rolling self-play on another BASELINE.json geometry, one GPU: moves/s and the roofline of required evaluations."""
+    torch.manual_seed(0)
+    sd = network._Params(n, n, CHANNELS, BLOCKS).state_dict()
+    eng = engine.Engine(rows=n, cols=n, n_games=games, n_sims=sims, evaluator="nn", state_dict=sd, seed=7,
+                        replay_capacity=games * 64)
+    ms, moves, evals, prof, st = timed_rolling(eng, torch, None, 1, iters, 1, steps, torch.cuda.synchronize)
+    fl = flops_per_leaf(n, n)
+    out = {"board": f"{n}x{n}", "sims_per_move": sims, "games": games, "value": moves / (ms * 1e-3), "unit": "moves/s", "steps": steps,
+           "evaluation_steps_per_launch": iters, "ms_per_step": ms / steps, "evals_per_move": evals / max(1, moves),
+           "roofline": tensor_roofline(peaks, evals, prof, ms, fl), "moves_per_s_roofline_at_sims_plus_1": peaks["bf16_tflops_sustained"] * 1e12 / ((sims + 1) * fl),
+           "arena_gb": eng.workspace_bytes / 1e9, "overflow": st.overflow}
+    eng.close(); del eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_tree_only(engine, torch, peaks):
+    """The tree kernels alone (north star: HBM GB/s for the tree kernels): the same persistent kernel with the deterministic-prior
+    evaluator, i.e. expand + backup + select of 4,096 games per step and nothing else."""
+    eng = engine.Engine(rows=ROWS, cols=COLS, n_games=GAMES_PER_GPU, n_sims=SIMS, evaluator="stub", seed=3, replay_capacity=GAMES_PER_GPU * 64)
+    for _ in range(2):
+        eng.selfplay_advance(SIMS + 1)
+    torch.cuda.synchronize()
+    s0 = eng.stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(4):
+        eng.selfplay_advance(SIMS + 1)
+    ev1.record(); torch.cuda.synchronize()
+    s1 = eng.stats()
+    sec = ev0.elapsed_time(ev1) * 1e-3
+    sims, evals = s1.sims - s0.sims, s1.tower_evals - s0.tower_evals
+    # algorithmic bytes per simulation (DESIGN 3.2): per level 20 B per child read (N, W, P, summary), 21 B per child written at the
+    # expanded leaf, 8 B per path edge updated, node + leaf records; measured average below from the device's own counters is not
+    # available, so the figure uses the survey's mid-game estimate of 3 KB per simulation
+    bytes_per_sim = 3000.0
+    gbs = sims * bytes_per_sim / sec / 1e9
+    eng.close(); del eng
+    torch.cuda.empty_cache()
+    tt = None
+    tp = os.path.join(ROOT, "profiles", "tree_traffic.json")
+    if os.path.exists(tp):
+        tt = json.load(open(tp))
+    return {"value": sims / sec, "unit": "simulations/s", "leaves_per_s": evals / sec, "moves_per_s": (s1.moves - s0.moves) / sec,
+            "roofline": {"bound": "hbm", "kernel": "fused_kernel with the stub evaluator (tree_step_game only)", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": tt,
+                         "note": "~3 KB of algorithmic traffic per simulation (SURVEY 8d); pointer chasing: one dependent round trip per tree "
+                                 "level, latency bound -- inside the real search these steps overlap the tower of the other games"}}
+
+
+def bench_strong(engine, torch, dist, world, rank, sd, peaks, barrier):
+    """BASELINE.json configs[3] as written: 32,768 concurrent games in total, sharded over the N GPUs (16,384 / 8,192 / 4,096 each)."""
+    games = 32768 // world
+    eng = engine.Engine(rows=ROWS, cols=COLS, n_games=games, n_sims=SIMS, evaluator="nn", state_dict=sd, seed=0xBEEF + rank,
+                        replay_capacity=games * 16)
+    ms, moves, evals, prof, st = timed_rolling(eng, torch, dist, world, SIMS + 1, 1, 2, barrier)
+    out = {"total_games": 32768, "games_per_gpu": games, "n_gpus": world, "value": moves / (ms * 1e-3), "unit": "moves/s", "steps": 2,
+           "ms_per_step": ms / 2, "scaling": "strong", "arena_gb_per_gpu": eng.workspace_bytes / 1e9,
+           "roofline_rank0": tensor_roofline(peaks, evals, prof, ms, FLOPS_PER_LEAF), "overflow": st.overflow}
+    eng.close(); del eng
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_env(engine, torch, peaks):

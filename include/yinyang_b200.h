@@ -250,6 +250,10 @@ typedef struct {
   int64_t tower_evals;    /* boards evaluated by the persistent kernel (each a pending leaf or root) */
 } yy_selfplay_stats;
 int yy_selfplay_get_stats(yy_engine *e, yy_selfplay_stats *out, void *stream);
+/* Device address of the live counters: 7 x int64 = moves, evals, games_finished, examples, sims, (overflow | max_depth << 32),
+ * tower_evals.  For stream-ordered snapshots (copy it after a self-play launch, on the same stream) without a
+ * synchronisation: e.g. to drain the records of step k while step k + 1 runs. */
+const void *yy_selfplay_stats_dev(yy_engine *e);
 
 /* Replay record i (i < min(examples, replay_capacity)), struct-of-arrays on the device:
  *   black/white  uint64[cap][W]   position before the move (self_play.py:140)

@@ -196,3 +196,79 @@ def augment_dataset(boards, counts, values, n, m):
     policies = np.stack(_symmetries(grid), axis=1).reshape(N * 8, A)
     vals = np.repeat(np.asarray(values, dtype=np.float64).astype(np.float32), 8)
     return np.ascontiguousarray(planes, dtype=np.float32), np.ascontiguousarray(policies, dtype=np.float32), vals
+
+
+# ---------------------------------------------------------------------------------------- episode driver
+def choice_index(u, p=None, k=None):
+    """The index np.random.choice returns for the uniform draw u (numpy/random/mtrand.pyx, legacy `choice`):
+    with probabilities p it is cdf.searchsorted(u, side='right') over cdf = cumsum(p) / cumsum(p)[-1]; the recorded
+    stream defines the draw without p (np.random.choice(best_moves), self_play.py:146) as floor(u * k)."""
+    if p is None:
+        return min(int(u * k), k - 1)
+    cdf = np.cumsum(np.asarray(p, dtype=np.float64))
+    cdf /= cdf[-1]
+    return int(np.searchsorted(cdf, u, side="right"))
+
+
+def play_game(n, m, num_sims, uniforms, noise=None, cpuct=1.0, eps=0.25, temperature_threshold=10, rule_flags=0,
+              search_as_black=True, max_plies=None):
+    """SelfPlayWorker.play_game (src/yin_yang/ai/self_play.py:72-192) with the hash-stub evaluator and a RECORDED random
+    stream: uniforms[step] is the draw behind the action choice of move `step`, `noise` the Dirichlet sample of the
+    step-0 root (mcts.py:303-306; None = no noise).  Restated line by line, including the reference's quirks: valid moves
+    and the search are always taken for player 1 (:99, :135-137; search_as_black=False searches for the side to move
+    instead), the chosen action is applied with the real player (:163, an action illegal for it is silently dropped),
+    two consecutive positions without a move for the searched colour end the game (:101-121; 1e-4 if the rules do not
+    call it finished), and every example of a game receives the same value (:170-181: the sign is flipped twice per
+    example).  Returns (boards int8[E,n,m], pis float64[E,A], zs float64[E], end) with end in {"ended", "passes", "cut"}."""
+    A = n * m
+    board = np.zeros((n, m), dtype=np.int8)
+    player, step, passes = 1, 0, 0
+    boards, pis = [], []
+
+    def finish(result, kind):
+        zs, value = [], result
+        for i in range(len(boards)):                      # self_play.py:112-115 / :172-181
+            zs.append(value if i % 2 == 0 else -value)
+            value = -value
+        return (np.array(boards, dtype=np.int8).reshape(-1, n, m), np.array(pis, dtype=np.float64).reshape(-1, A),
+                np.array(zs, dtype=np.float64), kind)
+
+    while True:
+        if max_plies is not None and step >= max_plies:
+            return finish(float("nan"), "cut")
+        temperature = 1.0 if step < temperature_threshold else 0
+        sp = 1 if search_as_black else player
+        valid = legal_mask(board[None], np.array([sp], np.int8), n, m, rule_flags)[0].astype(np.float64)
+        idx = np.flatnonzero(valid == 1)
+        if len(idx) == 0:
+            passes += 1
+            if passes >= 2:
+                result = float(game_ended(board[None], np.array([player], np.int8), n, m, rule_flags)[0])
+                if result == 0:
+                    result = 1e-4
+                return finish(result, "passes")
+            player = -player
+            continue
+        passes = 0
+        r = mcts_search(board, sp, n, m, num_sims, cpuct=cpuct, rule_flags=rule_flags,
+                        noise=noise if (step == 0 and noise is not None) else None, eps=eps)
+        counts = r["counts"].astype(np.float64)
+        pi = counts / counts.sum() if counts.sum() > 0 else np.ones(A) / A      # mcts.py:207-213 (temperature 1)
+        boards.append(board.copy()); pis.append(pi)
+        u = float(uniforms[step])
+        if temperature == 0:
+            best = np.flatnonzero(pi == pi.max())
+            action = int(best[choice_index(u, k=len(best))])
+        else:
+            probs = pi * valid
+            if probs.sum() > 0:
+                probs = probs / probs.sum()
+            else:
+                probs = np.zeros_like(valid); probs[idx] = 1.0 / len(idx)
+            action = choice_index(u, p=probs)
+        nb, npl = next_state(board[None], np.array([player], np.int8), np.array([action], np.int32), n, m, rule_flags)
+        board, player = nb[0], int(npl[0])
+        step += 1
+        result = float(game_ended(board[None], np.array([player], np.int8), n, m, rule_flags)[0])
+        if result != 0:
+            return finish(result, "ended")

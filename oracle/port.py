@@ -257,17 +257,32 @@ class HashStubNet:
 
 
 # ------------------------------------------------------------------------------------------------ timed legs
-def time_searches(n, m, num_sims, n_searches, channels=128, blocks=10, threads=1, seed=0):
-    """Wall-clock seconds for n_searches full searches from the empty board (one search = one self-play move)."""
+def random_play_position(game, plies, seed=0):
+    """The board after `plies` uniformly random legal plies from the empty board (a side without a move passes)."""
+    rng = np.random.default_rng(seed)
+    board, player = game.getInitBoard(), 1
+    for _ in range(plies):
+        idx = np.flatnonzero(game.getValidMoves(board, player))
+        if idx.size == 0:
+            player = -player
+            continue
+        board, player = game.getNextState(board, player, int(rng.choice(idx)))
+    return board
+
+
+def time_searches(n, m, num_sims, n_searches, channels=128, blocks=10, threads=1, seed=0, plies=0):
+    """Wall-clock seconds for n_searches full searches (one search = one self-play move) of the position after `plies`
+    random plies, searched as player 1 like the reference's self-play (self_play.py:135); plies = 0: the empty board."""
     import time
     import torch
     torch.set_num_threads(threads)
     torch.manual_seed(seed)
     net = build_net(n, m, channels, blocks)
     game = Game(n, m)
+    root = random_play_position(game, plies, seed)
     t0 = time.perf_counter()
     for _ in range(n_searches):
-        search(game, net, game.getInitBoard(), 1, num_sims)
+        search(game, net, root, 1, num_sims)
     return time.perf_counter() - t0
 
 
@@ -285,6 +300,14 @@ def time_searches_parallel(n, m, num_sims, n_searches_per_worker, workers, chann
     with ctx.Pool(workers) as pool:
         pool.map(_worker, [(n, m, num_sims, n_searches_per_worker, channels, blocks, 1, i) for i in range(workers)])
     return workers * n_searches_per_worker, time.perf_counter() - t0
+
+
+def _env_worker(args):
+    import time
+    n, m, steps, seed = args
+    t0 = time.perf_counter()
+    env_steps(n, m, steps, seed)
+    return time.perf_counter() - t0
 
 
 def env_steps(n, m, n_steps, seed=0):

@@ -141,11 +141,12 @@ def test_mcts_visit_counts_match_reference_golden(eng, name):
 
 @pytest.mark.parametrize("step_kernels", [False, True])
 @pytest.mark.parametrize("shape,sims,games", [((8, 8), 200, 96), ((6, 6), 150, 64), ((4, 4), 300, 64), ((16, 16), 40, 8),
-                                              ((8, 8), 60, 700)])
+                                              ((8, 8), 60, 700), ((8, 8), 800, 40), ((16, 16), 1600, 6), ((6, 6), 100, 48)])
 def test_mcts_matches_oracle_many_games(eng, oracle_mod, shape, sims, games, step_kernels):
     """Both search drivers -- ONE persistent kernel per search (default, csrc/yy_fused.cu) and one tree-step launch
     per simulation (YY_MODE_STEP_KERNELS) -- must reproduce the oracle bit for bit.  700 games: several games per
-    CTA and more than one heads batch per CTA in the persistent kernel."""
+    CTA and more than one heads batch per CTA in the persistent kernel.  8x8 / 800, 16x16 / 1,600 and 6x6 / 100 are the
+    simulation budgets BASELINE.json's configs state, on early, middle and late random-play positions."""
     n, m = shape
     boards, players = random_play_boards(oracle_mod, n, m, games, seed=5 + n)
     rng = np.random.default_rng(1)
@@ -427,6 +428,71 @@ def test_selfplay_reference_player_semantics(eng, oracle_mod):
         r = oracle_mod.mcts_search(rp["boards"][i], 1, n, m, sims)       # searched as black whatever the mover
         assert np.array_equal(rp["counts"][i].astype(np.int32), r["counts"]), i
     e.close()
+
+
+def _engine_games(e, total, chunk=4000):
+    """Runs rolling self-play until `total` games (the quota) are finished; returns {serial: (boards, pi, z)}."""
+    e.selfplay_set_quota(total)
+    for _ in range(2000):
+        e.selfplay_advance(chunk)
+        if e.stats().games_finished >= total:
+            break
+    st = e.stats()
+    assert st.games_finished == total and st.overflow == 0 and st.examples <= e.replay_capacity
+    rp = e.replay()
+    out = {}
+    order = np.lexsort((rp["ply"], rp["game_serial"]))
+    for s in range(total):
+        idx = order[rp["game_serial"][order] == s]
+        assert np.array_equal(rp["ply"][idx], np.arange(len(idx))) and rp["finished"][idx].all()
+        out[s] = (rp["boards"][idx], rp["pi"][idx], rp["z"][idx])
+    return out
+
+
+@pytest.mark.parametrize("name", golden_files("selfplay_"))
+def test_selfplay_episode_matches_reference_golden(eng, name):
+    """a whole game played by the engine's episode driver (prepare / noise / search / move inside the
+    persistent kernel) against the same game played by the UNMODIFIED SelfPlayWorker.play_game on the same recorded
+    random stream (tests/golden/make_golden_selfplay.py): every stored position, pi in float64, and z -- including the
+    pass / double-pass branch (1e-4 for every example), decisive results (+1 / -1 for every example: the double sign
+    flip of self_play.py:172-181), moves silently dropped for the real player, and the argmax branch after the
+    temperature threshold."""
+    g = load_golden(name)
+    n, m, A = int(g["n"]), int(g["m"]), int(g["n"]) * int(g["m"])
+    noise = np.zeros((1, A)); noise[0, :g["noise"].size] = g["noise"]
+    e = eng.Engine(rows=n, cols=m, n_games=1, n_sims=int(g["sims"]), evaluator="stub", cpuct=float(g["cpuct"]),
+                   dirichlet_epsilon=float(g["eps"]), dirichlet_alpha=float(g["alpha"]),
+                   temperature_threshold=int(g["temperature_threshold"]), replay_capacity=4 * A + 64)
+    e.selfplay_set_random_stream(g["uniforms"][None], noise)
+    boards, pi, z = _engine_games(e, 1)[0]
+    e.close()
+    assert np.array_equal(boards, g["boards"])
+    assert np.array_equal(pi, g["pis"])                       # float64, bit for bit
+    assert np.array_equal(z, g["zs"])
+
+
+@pytest.mark.parametrize("n,m,sims,tt,sab", [(4, 4, 50, 3, True), (6, 6, 40, 8, True), (5, 7, 30, 10, True), (8, 8, 24, 10, True),
+                                             (6, 6, 40, 8, False)])
+def test_selfplay_episodes_match_oracle(eng, oracle_mod, n, m, sims, tt, sab):
+    """48 whole games on 16 slots (three generations per slot, rolling) against the oracle's play_game on the same
+    recorded stream -- game s is the same game whichever slot played it.  Also the side-to-move search mode."""
+    A, total, P = n * m, 48, 4 * n * m
+    rng = np.random.default_rng(n * 100 + m)
+    uniforms = rng.random((total, P))
+    noise = np.stack([rng.dirichlet([0.3] * A) for _ in range(total)])
+    e = eng.Engine(rows=n, cols=m, n_games=16, n_sims=sims, evaluator="stub", temperature_threshold=tt, search_as_black=sab,
+                   replay_capacity=total * P)
+    e.selfplay_set_random_stream(uniforms, noise)
+    games = _engine_games(e, total, chunk=701)
+    e.close()
+    kinds = set()
+    for s in range(total):
+        b, pi, z, kind = oracle_mod.play_game(n, m, sims, uniforms[s], noise[s], temperature_threshold=tt, search_as_black=sab)
+        kinds.add((kind, float(z[0])))
+        assert np.array_equal(games[s][0], b), s
+        assert np.array_equal(games[s][1], pi), s
+        assert np.array_equal(games[s][2], z), s
+    assert len(kinds) >= 2
 
 
 def _games_by_serial(rp):

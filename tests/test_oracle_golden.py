@@ -94,3 +94,16 @@ def test_oracle_augmentation_matches_reference(oracle_mod, name):
     assert np.array_equal(planes, g["planes"])
     assert np.array_equal(policies, g["policies"])
     assert np.array_equal(values, g["out_values"])
+
+
+@pytest.mark.parametrize("name", golden_files("selfplay_"))
+def test_oracle_play_game_matches_reference_golden(oracle_mod, name):
+    """The oracle's restatement of SelfPlayWorker.play_game (self_play.py:72-192) against whole games played by the
+    unmodified reference on the same recorded random stream: every stored position, pi (float64) and z."""
+    g = load_golden(name)
+    n, m = int(g["n"]), int(g["m"])
+    noise = g["noise"] if g["noise"].size and float(g["eps"]) > 0 else None
+    b, pi, z, kind = oracle_mod.play_game(n, m, int(g["sims"]), g["uniforms"], noise, cpuct=float(g["cpuct"]), eps=float(g["eps"]),
+                                          temperature_threshold=int(g["temperature_threshold"]))
+    assert np.array_equal(b, g["boards"]) and np.array_equal(pi, g["pis"]) and np.array_equal(z, g["zs"])
+    assert kind in ("ended", "passes")

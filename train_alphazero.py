@@ -42,9 +42,11 @@ def parse_args(argv=None):
     p.add_argument("--init-model", action="store_true", help="create a randomly initialised model file if missing")
     p.add_argument("--eval-games", type=int, default=10)
     p.add_argument("--arena-games", type=int, default=40, help="--mode train: games of current vs best per iteration (alphazero.py:136)")
-    p.add_argument("--replay-wire", choices=["native", "reference"], default="native",
-                   help="'reference': pickle replay boards as src.yin_yang.yin_yang_logic.YinYangLogic so that the "
-                        "reference's own trainer loads the .npz without this package")
+    p.add_argument("--replay-wire", choices=["arrays", "native", "reference"], default="arrays",
+                   help="'arrays' (default): boards as one int8[N,n,m] array under the reference's npz keys; 'native': an object "
+                        "array of this package's YinYangLogic; 'reference': boards pickled as "
+                        "src.yin_yang.yin_yang_logic.YinYangLogic so that the reference's own trainer loads the .npz "
+                        "without this package")
     return p.parse_args(argv)
 
 
@@ -86,10 +88,20 @@ def main(argv=None):
             return 1
     if args.mode == "self-play":
         logger.info(f"Generating self-play data using model: {model_path}")
-        data_file = generate_self_play_data(game=game, model_path=model_path, output_dir=args.data_dir,
-                                            num_games=args.episodes, num_workers=args.workers,
-                                            num_simulations=args.simulations, wire=args.replay_wire)
-        logger.info(f"Self-play data generation completed. Data saved to {data_file}")
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world > 1:
+            # torchrun, one process per GPU (the counterpart of the reference's --workers processes, self_play.py:288-335):
+            # the episodes are sharded over the ranks, the examples gathered to rank 0 over NCCL, ONE file is written
+            from yinyang_game_alphazero_b200.self_play import generate_self_play_data_distributed
+            data_file = generate_self_play_data_distributed(game=game, model_path=model_path, output_dir=args.data_dir,
+                                                            num_games=args.episodes, num_simulations=args.simulations,
+                                                            wire=args.replay_wire)
+        else:
+            data_file = generate_self_play_data(game=game, model_path=model_path, output_dir=args.data_dir,
+                                                num_games=args.episodes, num_workers=args.workers,
+                                                num_simulations=args.simulations, wire=args.replay_wire)
+        if data_file:
+            logger.info(f"Self-play data generation completed. Data saved to {data_file}")
         return 0
     # evaluate: AlphaZero vs random, colours alternate (train_alphazero.py:165-243)
     az = AlphaZeroPlayer(game=game, model_path=model_path, num_simulations=args.simulations, num_threads=args.mcts_threads)

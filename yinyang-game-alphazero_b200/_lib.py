@@ -135,6 +135,7 @@ SIGNATURES = {
     "yy_selfplay_set_random_stream": (_I, [_P, _P, _P, ctypes.c_int32, ctypes.c_int32]),
     "yy_selfplay_get_stats": (_I, [_P, ctypes.POINTER(SelfPlayStats), _P]),
     "yy_selfplay_replay": (_I, [_P, ctypes.POINTER(ReplayView)]),
+    "yy_selfplay_stats_dev": (_P, [_P]),
     "yy_engine_game_black": (_P, [_P]),
     "yy_engine_game_white": (_P, [_P]),
     "yy_engine_game_player": (_P, [_P]),

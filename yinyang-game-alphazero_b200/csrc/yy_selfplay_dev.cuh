@@ -39,6 +39,7 @@ __device__ __forceinline__ bool sp_prepare_one(const EngineDev& e, const Geo<NW>
       b = bb_zero<NW>(); w = bb_zero<NW>(); player = 1; step = 0; passes = 0;
       e.sp_serial[gi] = serial;
       e.sp_new_game[gi] = 0;
+      e.rp_results[serial % e.results_cap] = 0;           // the slot may hold the result of game serial - results_cap
     }
     sp = (e.mode_flags & YY_MODE_SEARCH_AS_BLACK) ? 1 : player;
     if (any(legal_for(g, b, w, sp))) { passes = 0; break; }

@@ -477,6 +477,8 @@ int yy_selfplay_get_stats(yy_engine* e, yy_selfplay_stats* out, void* stream) {
   return YY_OK;
 }
 
+const void* yy_selfplay_stats_dev(yy_engine* e) { return e ? (const void*)e->dev.stats : nullptr; }
+
 int yy_selfplay_replay(yy_engine* e, yy_replay_view* out) {
   if (!e || !out) return set_error(YY_ERR_INVALID, "null argument");
   out->black = e->dev.rp_black; out->white = e->dev.rp_white; out->counts = e->dev.rp_counts;

@@ -473,6 +473,57 @@ class Engine:
         _lib.check(self.L.yy_selfplay_get_stats(self.handle, ctypes.byref(s), _stream()))
         return Stats(s.moves, s.evals, s.games_finished, s.examples, s.sims, s.overflow, s.max_depth, s.tower_evals)
 
+    # -- replay ring: device views and windows
+    def replay_views(self):
+        """Device views (no copy) over the WHOLE replay ring (replay_capacity rows; row = record index % capacity):
+        black / white int64[cap, W], counts int16[cap, A] (uint16 bit pattern), game_serial int32[cap], ply int16[cap],
+        player int8[cap], and the results table int8[results_capacity] (code of game s at [s % results_capacity])."""
+        if getattr(self, "_rviews", None) is None:
+            v = _lib.ReplayView()
+            _lib.check(self.L.yy_selfplay_replay(self.handle, ctypes.byref(v)))
+            base, cap = self.workspace.data_ptr(), self.replay_capacity
+
+            def view(ptr, nbytes, dtype, shape):
+                return self.workspace[ptr - base: ptr - base + nbytes].view(dtype).view(shape)
+            self._rviews = {"black": view(v.black, cap * self.W * 8, torch.int64, (cap, self.W)),
+                            "white": view(v.white, cap * self.W * 8, torch.int64, (cap, self.W)),
+                            "counts": view(v.counts, cap * self.A * 2, torch.int16, (cap, self.A)),
+                            "game_serial": view(v.game_serial, cap * 4, torch.int32, (cap,)),
+                            "ply": view(v.ply, cap * 2, torch.int16, (cap,)),
+                            "player": view(v.player, cap, torch.int8, (cap,)),
+                            "results": view(v.results, v.results_capacity, torch.int8, (v.results_capacity,))}
+            self.results_capacity = int(v.results_capacity)
+        return self._rviews
+
+    def replay_window_dev(self, start, stop):
+        """Device tensors (views when the window does not wrap, else copies) of the records with global indices
+        [start, stop), oldest first; stop - start <= replay_capacity."""
+        rv, cap = self.replay_views(), self.replay_capacity
+        n = stop - start
+        assert 0 <= n <= cap
+        lo, hi = start % cap, start % cap + n
+        keys = ("black", "white", "counts", "game_serial", "ply", "player")
+        if hi <= cap:
+            return {k: rv[k][lo:hi] for k in keys}
+        return {k: torch.cat([rv[k][lo:], rv[k][: hi - cap]], dim=0) for k in keys}
+
+    def replay_window(self, start, stop):
+        """The same window on the host (numpy, through pinned buffers, one synchronisation)."""
+        w = self.replay_window_dev(start, stop)
+        keys = sorted(w)
+        host = _to_host(*[w[k] for k in keys])
+        out = {k: (h if h is not None else np.zeros((0,) + tuple(w[k].shape[1:]), dtype=np.int64)) for k, h in zip(keys, host)}
+        out["black"] = out["black"].view(np.uint64); out["white"] = out["white"].view(np.uint64)
+        out["counts"] = out["counts"].view(np.uint16)
+        return out
+
+    def stats_view(self):
+        """Device view int64[7] of the live counters (moves, evals, games_finished, examples, sims, overflow | max_depth << 32,
+        tower_evals): copy it on the launching stream for a snapshot that is ordered with the self-play launches."""
+        ptr = self.L.yy_selfplay_stats_dev(self.handle)
+        off = ptr - self.workspace.data_ptr()
+        return self.workspace[off: off + 56].view(torch.int64)
+
     def replay(self):
         """Copies the replay ring to the host: dict(boards int8[N,n,m], counts uint16[N,A], pi float64[N,A],
         game_serial, ply, player, z float64[N] (NaN while the game is unfinished))."""
