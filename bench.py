@@ -332,22 +332,23 @@ def run_b200(args):
 
     # ---- the other BASELINE.json configurations (rank 0; 2 steps each), a strong-scaled configs[3] line, a tree-only leg
     other = {}
-    if rank == 0:
+    if rank == 0 and not args.quick:
         other["configs[0] 6x6/100 sims"] = bench_config(engine, network, torch, peaks, 6, 100, 4096, steps=3, iters=8 * 101)
         other["configs[4] 16x16/1600 sims (per-GPU share of 32,768 games)"] = bench_config(engine, network, torch, peaks, 16, 1600, 4096, steps=2, iters=801)
         other["tree only (stub evaluator) 8x8/800"] = bench_tree_only(engine, torch, peaks)
     strong = None
-    if world > 1:
+    if world > 1 and not args.quick:
         strong = bench_strong(engine, torch, dist, world, rank, sd, peaks, barrier)
 
     # ---- env steps/s (BASELINE.json configs[1]): 65,536 synthetic random-play boards on this GPU
-    env = bench_env(engine, torch, peaks) if rank == 0 else None
-    dataset = bench_dataset(engine, torch, peaks) if rank == 0 else None
-    learner_leg = bench_learner(engine, torch, peaks) if rank == 0 else None
-    learner_dp = bench_learner_dp(engine, torch, world) if world > 1 else None     # every rank takes part (NCCL all-reduce)
+    full = rank == 0 and not args.quick
+    env = bench_env(engine, torch, peaks) if full else None
+    dataset = bench_dataset(engine, torch, peaks) if full else None
+    learner_leg = bench_learner(engine, torch, peaks) if full else None
+    learner_dp = bench_learner_dp(engine, torch, world) if world > 1 and not args.quick else None     # every rank takes part (NCCL all-reduce)
     if learner_leg is not None and learner_dp is not None:
         learner_leg["data_parallel"] = learner_dp
-    ai_move_leg = bench_ai_move() if rank == 0 else None
+    ai_move_leg = bench_ai_move() if full else None
 
     if rank == 0:
         traffic = None
@@ -356,7 +357,7 @@ def run_b200(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         roof = tensor_roofline(peaks, evals_timed, prof, ms, FLOPS_PER_LEAF, {"traffic": traffic})
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.quick:
             v, cores, sample = cpu_selfplay_sample(cpu_workers(), 1, SIMS)
             cpu = {"value": v, "unit": "moves/s", "cores": cores, "kind": "port", "sample": sample}
             one, allc = cpu_env_sample(cpu_workers())
@@ -501,6 +502,12 @@ def bench_env(engine, torch, peaks):
     for _ in range(3):
         engine.env_step_host(boards, pl, ac, ROWS, COLS)
     e2e = 3 * ENV_BOARDS / (time.perf_counter() - t0)
+    hbk, hwh = black0.cpu().numpy().view(np.uint64), white0.cpu().numpy().view(np.uint64)
+    engine.env_step_host_packed(hbk, hwh, pl, ac, ROWS, COLS)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        engine.env_step_host_packed(hbk, hwh, pl, ac, ROWS, COLS)
+    e2e_packed = 5 * ENV_BOARDS / (time.perf_counter() - t0)
     gbs = ENV_BYTES_PER_STEP * ENV_BOARDS / per_launch_s / 1e9
     # the same kernel on a batch large enough to fill the machine (16 x the config): throughput rather than latency
     big = 16 * ENV_BOARDS
@@ -521,7 +528,9 @@ def bench_env(engine, torch, peaks):
             "timing": "8 launches replayed from a CUDA graph, CUDA events around the replay",
             "per_call": {"value": ENV_BOARDS / api_launch_s, "unit": "steps/s", "us_per_launch": api_launch_s * 1e6,
                          "note": "one engine.env_step() Python/ctypes call per launch, device-resident tensors"},
-            "e2e": {"value": e2e, "unit": "steps/s", "api": "env_step_host (int8 numpy boards in/out; bit packing on the device)"},
+            "e2e": {"value": e2e_packed, "unit": "steps/s", "api": "env_step_host_packed (packed uint64 boards in host memory in and out: 21 B in, 34 B out per board)",
+                    "h2d_bytes_per_step": 21, "d2h_bytes_per_step": 34,
+                    "int8_arrays": {"value": e2e, "unit": "steps/s", "api": "env_step_host (the reference's int8[n,m] board arrays in/out; bit packing on the device)"}},
             "roofline": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs / peaks["hbm_gbs"], "traffic": 1.403e6,
                          "note": "3.4 MB of algorithmic traffic per launch: latency bound at this batch size (two lanes per board, "
@@ -759,6 +768,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="developer runs: only the self-play legs (value, e2e, roofline)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -183,6 +183,23 @@ int yy_search_begin(yy_engine *e, const uint64_t *root_black_dev, const uint64_t
 int yy_search_advance(yy_engine *e, const float *priors_dev, const float *values_dev, int32_t *out_active,
                       void *stream);
 int yy_search_counts(yy_engine *e, int32_t *out_counts_dev, float *out_child_w_dev, void *stream);
+/* The search trees themselves (Node, mcts.py:28-48), for callers that walk below the root (the reference returns the
+ * root Node from MCTS.search).  Arrays are game-major: node j of game g at [g * max_nodes + j] (node 0 = root), edge slot k
+ * of game g at [g * edges_cap + k].  A reference Node is split in two: its statistics live in its parent's edge slot
+ * (visits = edge_N, value_sum = edge_W, prior = edge_P, action = edge_action), its state in a node record created when a
+ * simulation first expands it.  The children of node j are the n_edges[j] consecutive edge slots from edge_base[j], in
+ * ascending action order; edge_child_meta packs the child summary: bits [32,48) = child node id + 1 (0: not created yet),
+ * [57,60) = flags (1 expanded, 2 terminal, 4 no legal move). */
+typedef struct {
+  int32_t max_nodes, edges_cap, W;
+  const int32_t *n_nodes, *n_edges_used;             /* [n_games] nodes / edge slots in use */
+  const uint64_t *node_black, *node_white;           /* [n_games * max_nodes * W] */
+  const int32_t *node_edge_base; const int16_t *node_n_edges; const int8_t *node_player; const uint8_t *node_flags;
+  const float *node_value;                           /* terminal value / cached value of a child-less node */
+  const int32_t *edge_N; const float *edge_W; const float *edge_P; const uint64_t *edge_child_meta; const uint8_t *edge_action;
+} yy_tree_view;
+int yy_engine_tree_view(yy_engine *e, yy_tree_view *out);
+
 /* Device pointers (owned by the engine) of the pending leaf batch: boards to evaluate and a
  * per-game flag (1 = needs evaluation). */
 const uint64_t *yy_engine_leaf_black(yy_engine *e);
@@ -290,6 +307,13 @@ const int8_t *yy_engine_game_player(yy_engine *e);
  * torch.FloatTensor(policy), data_utils.py:34) or, when counts is NULL, policy float32[count][A] as is.
  * Square boards only (the reference rotates by 90 degrees).  Bit-exact against the reference. */
 int yy_augment_samples(int rows, int cols, const uint64_t *black_dev, const uint64_t *white_dev,
+                       const uint16_t *counts_dev, const float *policy_dev, const float *values_dev, int64_t count,
+                       float *out_planes_dev, float *out_policy_dev, float *out_values_dev, void *stream);
+
+/* The same without augmentation (DataProcessor.preprocess_sample for a whole buffer, data_utils.py:16-37;
+ * create_dataset_from_games(..., augment=False)): out_planes float32[count][5][n][m], out_policy float32[count][A],
+ * out_values float32[count] (optional).  Any supported board shape. */
+int yy_dataset_samples(int rows, int cols, const uint64_t *black_dev, const uint64_t *white_dev,
                        const uint16_t *counts_dev, const float *policy_dev, const float *values_dev, int64_t count,
                        float *out_planes_dev, float *out_policy_dev, float *out_values_dev, void *stream);
 

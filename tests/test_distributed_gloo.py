@@ -83,8 +83,8 @@ def _learner_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        net = _reference_net(4, 4, 8, 1, seed=5)
-        L = learner.Learner(4, 4, 8, 1, batch_size=4, state_dict=net.state_dict(), _ops=TorchEmuOps())
+        net = _reference_net(4, 4, 8, 1, seed=5 + 10 * rank)      # every rank starts from ITS OWN random initialisation ...
+        L = learner.Learner(4, 4, 8, 1, batch_size=4, state_dict=net.state_dict(), _ops=TorchEmuOps())   # ... and adopts rank 0's
         planes, pi, z = _batch(net, 4, 4, 8, seed=6)
         sl = slice(4 * rank, 4 * rank + 4)                  # every rank trains on its own half of the global batch
         for _ in range(2):
@@ -95,8 +95,10 @@ def _learner_worker(rank, world, port, q):
 
 
 def test_data_parallel_learner_world2():
-    """Two ranks, one half batch each: identical weights on both ranks after every step, equal to a single process that
-    averages the two half-batch gradients before Adam (DistributedDataParallel semantics)."""
+    """Two ranks, one half batch each, DIFFERENT random initialisations per rank: the learner broadcasts rank 0's parameters,
+    moments and running statistics when it is built, so both ranks hold identical weights after every step, equal to a
+    single process that starts from rank 0's weights and averages the two half-batch gradients before Adam
+    (DistributedDataParallel semantics)."""
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, os.path.dirname(here)); sys.path.insert(0, here)

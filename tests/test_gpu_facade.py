@@ -295,3 +295,104 @@ def test_mcts_num_threads_is_k_leaves_per_step(pkg):
     top3 = [len(set(np.argsort(-c1[i])[:3]) & set(np.argsort(-c8[i])[:3])) for i in range(6)]
     assert np.mean(top3) >= 1.5
     seq.close(); par.close()
+
+
+def test_mcts_facade_reference_unit_cases(pkg, oracle_mod):
+    """The reference's own MCTS unit cases (src/yin_yang/ai/mcts_tests.py) that are about the search rather than about
+    its fake game, on real boards through the facade: root visits == simulations with and without Dirichlet noise
+    (:215-235), children carry the evaluator's raw priors (mcts.py:77-78), a node's visits are its own first visit plus
+    its children's (:389-416, backpropagation), sharper distributions at lower temperatures (:418-445), a single legal
+    move gets probability 1 (:477-496)."""
+    from conftest import random_play_boards
+    game = pkg["game"].YinYangGame(6, 6)
+    stub = pkg["network"].HashStubEvaluator(game)
+    mcts = pkg["mcts"].MCTS(game, stub, num_simulations=60, verbose=0)
+    board = game.getInitBoard()
+    board.board[2, 2], board.board[2, 3] = 1, -1
+    probs, root = mcts.search(board, 1)
+    assert abs(probs.sum() - 1.0) < 1e-12 and root.is_expanded() and root.visits == 60
+    pol, _ = stub.predict(board)
+    legal = game.getValidMoves(board, 1)
+    assert sorted(root.children) == list(np.flatnonzero(legal))                     # one child per legal action, ascending
+    for a, ch in root.children.items():
+        assert ch.prior == pol[a] and isinstance(ch.value_sum, np.float32)
+        assert ch.parent is root and ch.action == a
+        if ch.visits > 0:
+            assert ch.player == -1 and np.abs(ch.board.board).sum() == 3          # expanded: holds its own position
+            if not ch.is_terminal and ch.children:
+                assert ch.visits == 1 + sum(g.visits for g in ch.children.values())
+        else:
+            assert not ch.is_expanded() and ch.board is None
+    assert sum(ch.visits for ch in root.children.values()) == 60
+    deep = max(root.children.values(), key=lambda c: c.visits)
+    assert any(g.visits > 0 and g.is_expanded() for g in deep.children.values())   # the tree is reachable below depth 1
+    probs_n, root_n = mcts.search(board, 1, add_exploration_noise=True)
+    assert abs(probs_n.sum() - 1.0) < 1e-12 and root_n.visits == 60
+    d1, d2, d3, d4 = (root.get_children_distribution(t) for t in (1.0, 0.5, 0.1, 0))
+    order = np.argsort(-root.get_children_visit_counts())
+    a0, a1 = order[0], order[1]
+    if root.get_children_visit_counts()[a0] > root.get_children_visit_counts()[a1]:
+        assert d1[a0] - d1[a1] < d2[a0] - d2[a1] < d3[a0] - d3[a1] and d4[a0] == 1.0
+    sharp = pkg["mcts"].MCTS(game, stub, num_simulations=60, temperature=0.5, verbose=0)
+    p_sharp, _ = sharp.search(board, 1)
+    assert np.allclose(p_sharp, d2)                                                 # search returns the distribution at MCTS.temperature (mcts.py:323)
+    # a position with exactly one legal move for the side to move
+    boards, players = random_play_boards(oracle_mod, 6, 6, 3000, seed=4)
+    masks = oracle_mod.legal_mask(boards, players, 6, 6)
+    one = np.flatnonzero(masks.sum(axis=1) == 1)
+    assert one.size > 0
+    b1 = game.getInitBoard(); b1.board = boards[one[0]].copy()
+    p1, r1 = mcts.search(b1, int(players[one[0]]))
+    only = int(np.flatnonzero(masks[one[0]])[0])
+    assert np.argmax(p1) == only and abs(p1[only] - 1.0) < 1e-12 and list(r1.children) == [only]
+    mcts.close(); sharp.close()
+
+
+def test_mcts_facade_sees_reloaded_weights(pkg):
+    """The reference MCTS holds the network by reference (mcts.py:249): a search after neural_net.load_state_dict must use
+    the new weights, although the facade's engine keeps its own packed copy on the device."""
+    import torch
+    game = pkg["game"].YinYangGame(4, 4)
+    torch.manual_seed(1)
+    net = pkg["network"].YinYangNeuralNetwork(game, num_channels=32, num_res_blocks=1)
+    mcts = pkg["mcts"].MCTS(game, net, num_simulations=40, dirichlet_noise=False, verbose=0)
+    board = game.getInitBoard()
+    c0 = mcts.search(board, 1)[1].get_children_visit_counts()
+    torch.manual_seed(2)
+    other = pkg["network"].YinYangNeuralNetwork(game, num_channels=32, num_res_blocks=1)
+    fresh = pkg["mcts"].MCTS(game, other, num_simulations=40, dirichlet_noise=False, verbose=0)
+    c_other = fresh.search(board, 1)[1].get_children_visit_counts()
+    net.load_state_dict(other.state_dict())
+    c1 = mcts.search(board, 1)[1].get_children_visit_counts()
+    assert np.array_equal(c1, c_other) and not np.array_equal(c0, c_other)
+    mcts.close(); fresh.close()
+
+
+def test_self_play_array_wire_and_rolling_driver(pkg, tmp_path):
+    """wire='arrays' (boards as one int8 array under the reference's npz keys) loads in this package's TrainingDataQueue;
+    RollingSelfPlay returns whole finished games, keeps the other slots' games in flight across calls (keep_warm)."""
+    import torch
+    from yinyang_game_alphazero_b200.training_pipeline import TrainingDataQueue
+    game = pkg["game"].YinYangGame(4, 4)
+    torch.manual_seed(0)
+    net = pkg["network"].YinYangNeuralNetwork(game, num_channels=32, num_res_blocks=1)
+    model = str(tmp_path / "m" / "best_model.pth.tar")
+    net.save_model(model)
+    path = pkg["self_play"].generate_self_play_data(game, model, str(tmp_path / "d"), num_games=5, num_simulations=12, wire="arrays")
+    d = np.load(path)                                                              # no pickle needed
+    assert d["boards"].dtype == np.int8 and d["boards"].shape[1:] == (4, 4) and len(d["values"]) == len(d["boards"]) >= 5
+    q = TrainingDataQueue()
+    q.push_file(path)
+    assert len(q) == len(d["values"])
+    sp = pkg["self_play"].RollingSelfPlay(game, net.state_dict(), slots=8, num_simulations=12, seed=3)
+    first = sp.play(6, keep_warm=True)
+    second = sp.play(6, keep_warm=True)
+    for ex in (first, second):
+        games = np.unique(ex["game"])
+        assert len(games) >= 6
+        for g in games:
+            sel = ex["game"] == g
+            assert np.array_equal(ex["ply"][sel], np.arange(sel.sum())) and len(set(ex["z"][sel])) == 1   # whole games, one z
+            assert np.abs(ex["boards"][sel][0]).sum() == 0
+    assert not set(np.unique(first["game"])) & set(np.unique(second["game"]))
+    sp.close()

@@ -80,6 +80,32 @@ def test_rules_match_reference_golden(eng, name):
     assert np.array_equal(eng.ended_host(B, -one, n, m), g["ended_white"])
 
 
+@pytest.mark.parametrize("name", golden_files("rowcol_"))
+def test_rowcol_rule_matches_js_transcription_golden(eng, name):
+    """YY_RULE_ROWCOL on the GPU against the literal transcription of the browser game's rule (yin_yang_game.js:186-232,
+    :338-384; tests/golden/make_golden_rowcol.py), both colours, incl. boards with complete and nearly complete lines."""
+    g = load_golden(name)
+    n, m, B = int(g["n"]), int(g["m"]), g["boards"]
+    one = np.ones(len(B), np.int8)
+    assert np.array_equal(eng.legal_mask_host(B, one, n, m, eng.RULE_ROWCOL), g["mask_black"])
+    assert np.array_equal(eng.legal_mask_host(B, -one, n, m, eng.RULE_ROWCOL), g["mask_white"])
+
+
+def test_env_step_packed_host_buffers(eng, oracle_mod):
+    """env_step_host_packed: packed uint64 boards in host memory in and out (the C ABI's own layout)."""
+    from yinyang_game_alphazero_b200 import bitboard
+    n = m = 8
+    boards, players = random_play_boards(oracle_mod, n, m, 3000, seed=77)
+    rng = np.random.default_rng(5)
+    masks_o = oracle_mod.legal_mask(boards, players, n, m)
+    actions = np.array([rng.choice(np.flatnonzero(mk)) if mk.any() else -1 for mk in masks_o], dtype=np.int32)
+    mo, bo, po, ro = oracle_mod.env_step(boards, players, actions, n, m)
+    bk, wh = bitboard.pack_boards(boards, n, m)
+    hm, hb, hw, hp, hr = eng.env_step_host_packed(bk, wh, players, actions, n, m)
+    assert np.array_equal(bitboard.unpack_bits(hm, n, m), mo) and np.array_equal(bitboard.unpack_boards(hb, hw, n, m), bo)
+    assert np.array_equal(hp, po) and np.array_equal(eng.result_from_code(hr), ro)
+
+
 @pytest.mark.parametrize("shape,flags", [((8, 8), 0), ((8, 8), 1), ((6, 6), 0), ((16, 16), 0), ((10, 10), 1), ((5, 7), 0)])
 def test_env_step_matches_oracle(eng, oracle_mod, shape, flags):
     n, m = shape
@@ -378,6 +404,24 @@ def test_augmentation_into_caller_buffers(eng, oracle_mod):
     assert [t.data_ptr() for t in out2] == ptrs
     rp, rq, rv = oracle_mod.augment_dataset(b2, c2, np.ones(300), n, n)
     assert np.array_equal(out2[0].cpu().numpy(), rp) and np.array_equal(out2[1].cpu().numpy(), rq) and np.array_equal(out2[2].cpu().numpy(), rv)
+
+
+@pytest.mark.parametrize("shape", [(5, 7), (8, 8), (3, 9)])
+def test_dataset_without_augmentation_any_shape(eng, oracle_mod, shape):
+    """yy_dataset_samples (create_dataset_from_games(..., augment=False), DataProcessor.preprocess_sample): planes and
+    policies of every record, identity form only -- also on the non-square boards the rotations exclude."""
+    n, m = shape
+    rng = np.random.default_rng(n * 10 + m)
+    boards = rng.integers(-1, 2, size=(200, n, m)).astype(np.int8)
+    counts = rng.integers(0, 500, size=(200, n * m)).astype(np.uint16)
+    counts[::9] = 0
+    values = rng.choice([1.0, -1.0, 0.0001], size=200)
+    planes, pol, vals = eng.augment_samples_host(boards, n, m, counts=counts, values=values, forms=1)
+    ref = oracle_mod.input_planes(boards, n, m)
+    tot = counts.sum(axis=1, keepdims=True).astype(np.float64)
+    rpol = np.where(tot > 0, counts / np.maximum(tot, 1.0), 1.0 / (n * m)).astype(np.float32)
+    assert planes.shape == (200, 5, n, m) and np.array_equal(planes, ref)
+    assert np.array_equal(pol, rpol) and np.array_equal(vals, values.astype(np.float32))
 
 
 def test_augmentation_rejects_non_square(eng):

@@ -107,3 +107,51 @@ def test_oracle_play_game_matches_reference_golden(oracle_mod, name):
                                           temperature_threshold=int(g["temperature_threshold"]))
     assert np.array_equal(b, g["boards"]) and np.array_equal(pi, g["pis"]) and np.array_equal(z, g["zs"])
     assert kind in ("ended", "passes")
+
+
+@pytest.mark.parametrize("name", golden_files("rowcol_"))
+def test_oracle_rowcol_rule_matches_js_transcription(oracle_mod, name):
+    """YY_RULE_ROWCOL against tests/golden/rowcol_*.npz: the browser game's isValidMove (yin_yang_game.js:186-232) with
+    checkRowColumnConstraint (:338-384) transcribed loop for loop on top of the unmodified Python reference's
+    is_valid_move (tests/golden/make_golden_rowcol.py)."""
+    g = load_golden(name)
+    n, m, B = int(g["n"]), int(g["m"]), g["boards"]
+    one = np.ones(len(B), np.int8)
+    assert np.array_equal(oracle_mod.legal_mask(B, one, n, m, 1), g["mask_black"])
+    assert np.array_equal(oracle_mod.legal_mask(B, -one, n, m, 1), g["mask_white"])
+
+
+def test_rowcol_rule_hand_worked_boards(oracle_mod):
+    """Boards worked out by hand from yin_yang_game.js:338-384 ("a row / column with no empty cell and only one colour is
+    a violation", checked on the whole board after the trial placement, :220-227).  X black, O white, . empty, 4x4:
+      A  XXX.   black at (0,3) would fill row 0 with black only          -> banned with the flag, legal without
+         O...   (connectivity: (0,3) touches (0,2); 2x2: no window)
+      B  XXO.   black at (0,3): row 0 = X X O X, two colours              -> legal either way
+      C  X...   black at (3,0) would fill column 0 with black only        -> banned with the flag
+         X...
+         X...
+         ..O.
+      D  OOOO   row 0 is ALREADY all white: the check runs over the whole board after any placement, so with the flag
+         X...   nobody has a legal move anywhere (:338-358 returns false whatever was placed)
+      E  XXX.   white at (0,3): row 0 = X X X O, two colours -> legal for white (it touches white's only stone (1,3))
+         ...O
+    """
+    def board(rows):
+        return np.array([[{"X": 1, "O": -1, ".": 0}[c] for c in r] for r in rows], np.int8)[None]
+    one = np.ones(1, np.int8)
+    A = board(["XXX.", "O...", "....", "...."])
+    assert oracle_mod.legal_mask(A, one, 4, 4, 0)[0, 3] == 1 and oracle_mod.legal_mask(A, one, 4, 4, 1)[0, 3] == 0
+    Bb = board(["XXO.", "....", "....", "...."])
+    assert oracle_mod.legal_mask(Bb, one, 4, 4, 0)[0, 3] == oracle_mod.legal_mask(Bb, one, 4, 4, 1)[0, 3] == 0   # (0,3) does not touch black
+    Bb = board(["XXO.", "...X", "....", "...."])                                   # two black groups: (0,3) joins nothing to (0,0)
+    assert oracle_mod.legal_mask(Bb, one, 4, 4, 1)[0, 3] == 0
+    B2 = board(["XOX.", "XXX.", "....", "...."])                                   # black at (0,3): row X O X X, touches (1,3)? no: (0,2) yes
+    assert oracle_mod.legal_mask(B2, one, 4, 4, 0)[0, 3] == 1 and oracle_mod.legal_mask(B2, one, 4, 4, 1)[0, 3] == 1
+    C = board(["X...", "X...", "X...", "..O."])
+    assert oracle_mod.legal_mask(C, one, 4, 4, 0)[0, 12] == 1 and oracle_mod.legal_mask(C, one, 4, 4, 1)[0, 12] == 0
+    assert oracle_mod.legal_mask(C, one, 4, 4, 1)[0, 1] == 1                       # (0,1): row 0 = X X . . , not full
+    D = board(["OOOO", "X...", "....", "...."])
+    assert oracle_mod.legal_mask(D, one, 4, 4, 0)[0].sum() > 0
+    assert oracle_mod.legal_mask(D, one, 4, 4, 1)[0].sum() == 0 and oracle_mod.legal_mask(D, -one, 4, 4, 1)[0].sum() == 0
+    E = board(["XXX.", "...O", "....", "...."])
+    assert oracle_mod.legal_mask(E, -one, 4, 4, 1)[0, 3] == 1 and oracle_mod.legal_mask(E, one, 4, 4, 1)[0, 3] == 0

@@ -35,24 +35,43 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
+    # One builder at a time (torchrun starts every rank at once on a fresh checkout): the others wait on the lock and then
+    # find the library up to date.  Objects and the library are written under temporary names and renamed into place, so
+    # nobody ever dlopens a half-written file.
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            return _build_locked(nvcc, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(nvcc, verbose):
     objdir = os.path.join(LIB_DIR, "obj")
     os.makedirs(objdir, exist_ok=True)
 
     def one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        tmp = obj + f".tmp{os.getpid()}"
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", tmp]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         if verbose and r.stderr:
             print(r.stderr)
+        os.replace(tmp, obj)
         return obj
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(one, SOURCES))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB_PATH, *objs], capture_output=True, text=True)
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 
@@ -84,6 +103,16 @@ class GemmStats(ctypes.Structure):
 class ConvGeom(ctypes.Structure):
     """yy_conv_geom (include/yinyang_b200.h)."""
     _fields_ = [("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("cin", ctypes.c_int32), ("flip", ctypes.c_int32)]
+
+
+class TreeView(ctypes.Structure):
+    """yy_tree_view (include/yinyang_b200.h)."""
+    _fields_ = [("max_nodes", ctypes.c_int32), ("edges_cap", ctypes.c_int32), ("W", ctypes.c_int32),
+                ("n_nodes", ctypes.c_void_p), ("n_edges_used", ctypes.c_void_p), ("node_black", ctypes.c_void_p),
+                ("node_white", ctypes.c_void_p), ("node_edge_base", ctypes.c_void_p), ("node_n_edges", ctypes.c_void_p),
+                ("node_player", ctypes.c_void_p), ("node_flags", ctypes.c_void_p), ("node_value", ctypes.c_void_p),
+                ("edge_N", ctypes.c_void_p), ("edge_W", ctypes.c_void_p), ("edge_P", ctypes.c_void_p),
+                ("edge_child_meta", ctypes.c_void_p), ("edge_action", ctypes.c_void_p)]
 
 
 class ReplayView(ctypes.Structure):
@@ -121,6 +150,7 @@ SIGNATURES = {
     "yy_search_begin": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "yy_search_advance": (_I, [_P, _P, _P, ctypes.POINTER(ctypes.c_int32), _P]),
     "yy_search_counts": (_I, [_P, _P, _P, _P]),
+    "yy_engine_tree_view": (_I, [_P, ctypes.POINTER(TreeView)]),
     "yy_engine_leaf_black": (_P, [_P]),
     "yy_engine_leaf_white": (_P, [_P]),
     "yy_engine_leaf_active": (_P, [_P]),
@@ -140,6 +170,7 @@ SIGNATURES = {
     "yy_engine_game_white": (_P, [_P]),
     "yy_engine_game_player": (_P, [_P]),
     "yy_augment_samples": (_I, [_I, _I, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "yy_dataset_samples": (_I, [_I, _I, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "yy_lrn_gemm": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I64, _I, _P, _P, _P, _P]),
     "yy_lrn_pack_b": (_I, [_P, _P, _I64, _I, _I, _I, _P, _P]),
     "yy_lrn_pack_b_bytes": (_I64, [_I, _I]),
@@ -161,11 +192,10 @@ _lib = None
 
 
 def lib() -> ctypes.CDLL:
-    """Load (building first if stale) the shared library and attach signatures.  YY_LIB_PATH (developer switch) loads
-    a prebuilt library instead, e.g. to A/B two kernel variants in one GPU session."""
+    """Load (building first if stale) the shared library and attach signatures."""
     global _lib
     if _lib is None:
-        path = os.environ.get("YY_LIB_PATH") or build()
+        path = build()
         L = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)

@@ -25,7 +25,8 @@ constexpr int kDatasetWarps = kDatasetBlock / 32;
 __host__ __device__ inline int dataset_smem_floats(int A) { return 6 * A + 64; }   // per warp: planes + row / column fractions
 
 // M = board side when it is one of the common sizes (all offsets become immediates), 0 = read it from g.
-template <int NW, int M>
+// FORMS = 8: all forms of augment_sample; FORMS = 1: the identity form only (preprocess_sample, any board shape).
+template <int NW, int M, int FORMS = 8>
 __global__ void __launch_bounds__(kDatasetBlock, 4)
 augment_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint64_t* __restrict__ white,
                const uint16_t* __restrict__ counts, const float* __restrict__ policy_in, const float* __restrict__ values,
@@ -53,7 +54,7 @@ augment_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint6
     for (int off = 16; off; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
   }
   const float uniform = (float)(1.0 / (double)A);
-  if (lane < 8 && out_values) out_values[r * 8 + lane] = values ? values[r] : 0.0f;
+  if (lane < FORMS && out_values) out_values[r * FORMS + lane] = values ? values[r] : 0.0f;
   __syncwarp();
   for (int s = lane; s < A; s += 32) {          // phase 1: the identity form, once per cell
     const int sx = s / m, sy = s - sx * m;
@@ -69,12 +70,12 @@ augment_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint6
     src[5 * A + s] = p;
   }
   __syncwarp();
-  float* planes0 = out_planes + r * 40ll * A;   // [8 forms][5 planes][A]
-  float* pol0 = out_policy + r * 8ll * A;       // [8 forms][A]
+  float* planes0 = out_planes + r * (5ll * FORMS) * A;   // [FORMS][5 planes][A]
+  float* pol0 = out_policy + r * (long long)FORMS * A;   // [FORMS][A]
   for (int a = lane; a < A; a += 32) {          // phase 2: output cell (i, j) of form f <- source cell (sx, sy)
     const int i = a / m, j = a - i * m;         // (square boards: n == m)
 #pragma unroll
-    for (int f = 0; f < 8; ++f) {
+    for (int f = 0; f < FORMS; ++f) {
       int sx, sy;
       switch (f) {
         case 0: sx = i; sy = j; break;
@@ -98,6 +99,32 @@ augment_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint6
 }  // namespace yy
 
 using namespace yy;
+
+// DataProcessor.preprocess_sample for a whole buffer (data_utils.py:16-37): planes and policy of every record, no
+// augmentation -- any board shape (create_dataset_from_games(..., augment=False) on a 5 x 7 board).
+extern "C" int yy_dataset_samples(int rows, int cols, const uint64_t* black, const uint64_t* white, const uint16_t* counts,
+                                  const float* policy, const float* values, int64_t count, float* out_planes,
+                                  float* out_policy, float* out_values, void* stream) {
+  if (!board_supported(rows, cols)) return set_error(YY_ERR_INVALID, "unsupported board %dx%d", rows, cols);
+  if (count < 0) return set_error(YY_ERR_INVALID, "negative count");
+  if (yy_device_count() == 0) return set_error(YY_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+  if (count == 0) return YY_OK;
+  if (!black || !white || (!counts && !policy) || !out_planes || !out_policy) return set_error(YY_ERR_INVALID, "null argument");
+  const int cells = rows * cols, W = words_for_cells(cells);
+  const unsigned grid = (unsigned)((count + kDatasetWarps - 1) / kDatasetWarps);
+  const size_t smem = (size_t)kDatasetWarps * dataset_smem_floats(cells) * sizeof(float);
+#define YY_DATASET_LAUNCH(NWV)                                                                                          \
+  do {                                                                                                                  \
+    if (smem > 48 * 1024)                                                                                               \
+      cudaFuncSetAttribute(augment_kernel<NWV, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    augment_kernel<NWV, 0, 1><<<grid, kDatasetBlock, smem, (cudaStream_t)stream>>>(                                     \
+        make_geo<NWV>(rows, cols, 0), W, black, white, counts, policy, values, count, out_planes, out_policy, out_values); \
+  } while (0)
+  YY_DISPATCH_NW(cells, YY_DATASET_LAUNCH(NW));
+#undef YY_DATASET_LAUNCH
+  YY_LAUNCH_CHECK();
+  return YY_OK;
+}
 
 extern "C" int yy_augment_samples(int rows, int cols, const uint64_t* black, const uint64_t* white, const uint16_t* counts,
                                   const float* policy, const float* values, int64_t count, float* out_planes,

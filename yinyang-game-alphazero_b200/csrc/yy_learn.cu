@@ -901,7 +901,6 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
         cudaError_t e = v ? cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<3, true>, &q) : cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<4, false>, &q);
         if (e != cudaSuccess) { cudaGetLastError(); n = -1; }
         active[v][i] = n > 0 ? n : -1;
-        if (getenv("YY_GEMM_DEBUG")) fprintf(stderr, "[yy_lrn_gemm] max co-resident clusters of %d CTAs: %d\n", c, n);
       }
       if (active[v][i] > 0 && ctas / c <= active[v][i]) { cz = c; break; }
     }

@@ -6,7 +6,6 @@
 // ~2,600 dependent integer instructions per warp (flood fills), so at 65,536 boards (14 warps per SM) they are
 // latency bound -- 15 us, of which the SMs are busy 10 -- and at 1 M boards integer-issue bound (10.8 G steps/s).
 #include "yy_common.cuh"
-#include <stdlib.h>
 
 namespace yy {
 
@@ -299,31 +298,19 @@ int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64
   int rc = check_rules_args(rows, cols, count); if (rc) return rc;
   if (count == 0) return YY_OK;
   int cells = rows * cols, W = words_for_cells(cells);
-  // Blocks counting-sort their boards by stone count so that a warp's lanes run fills of similar length; YY_ENV_SORT=0/1
-  // forces the choice (developer A/B switch).
-  static const int force = [] { const char* e = getenv("YY_ENV_SORT"); return e ? atoi(e) : -1; }();
-  const bool sort = force < 0 ? true : force != 0;
-#define YY_ENV_LAUNCH_B(NWV, BLOCKV, SORTV, SIDEV)                                                          \
-  env_step_kernel<NWV, BLOCKV, SORTV, SIDEV><<<(unsigned)((count + BLOCKV / 2 - 1) / (BLOCKV / 2)), BLOCKV, 0, (cudaStream_t)stream>>>( \
-      make_geo<NWV>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count)
-#define YY_ENV_LAUNCH(NWV, SORTV, SIDEV)                                                                     \
-  do { if (block == 128) YY_ENV_LAUNCH_B(NWV, 128, SORTV, SIDEV); else YY_ENV_LAUNCH_B(NWV, 256, SORTV, SIDEV); } while (0)
-  // 64 boards per block spread a batch more evenly over the 148 SMs than 128 (65,536 boards: 6.9 blocks per SM instead of
+  // Blocks counting-sort their boards by stone count so that a warp's lanes run fills of similar length.  64 boards per
+  // block (128 threads) spread a batch more evenly over the 148 SMs than 128 (65,536 boards: 6.9 blocks per SM instead of
   // 3.5, i.e. the fullest SM holds 1 % more than the average instead of 15 %): 6.5 against 7.1 us per launch, and still
-  // 4 % ahead at 1 M boards.  YY_ENV_BLOCK=128/256 forces the block size (developer A/B switch).
-  static const int force_block = [] { const char* e = getenv("YY_ENV_BLOCK"); return e ? atoi(e) : 0; }();
-  const int block = force_block == 256 ? 256 : 128;
+  // 4 % ahead at 1 M boards.
+  constexpr int kBlock = 128;
+#define YY_ENV_LAUNCH(NWV, SIDEV)                                                                            \
+  env_step_kernel<NWV, kBlock, true, SIDEV><<<(unsigned)((count + kBlock / 2 - 1) / (kBlock / 2)), kBlock, 0, (cudaStream_t)stream>>>( \
+      make_geo<NWV>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count)
   const int side = rows == cols ? rows : 0;
-  if (sort) {
-    if (side == 8) YY_ENV_LAUNCH(1, true, 8);
-    else if (side == 6) YY_ENV_LAUNCH(1, true, 6);
-    else if (side == 16) YY_ENV_LAUNCH(4, true, 16);
-    else YY_DISPATCH_NW(cells, YY_ENV_LAUNCH(NW, true, 0));
-  } else {
-    if (side == 8) YY_ENV_LAUNCH(1, false, 8);
-    else YY_DISPATCH_NW(cells, YY_ENV_LAUNCH(NW, false, 0));
-  }
-#undef YY_ENV_LAUNCH_B
+  if (side == 8) YY_ENV_LAUNCH(1, 8);
+  else if (side == 6) YY_ENV_LAUNCH(1, 6);
+  else if (side == 16) YY_ENV_LAUNCH(4, 16);
+  else YY_DISPATCH_NW(cells, YY_ENV_LAUNCH(NW, 0));
 #undef YY_ENV_LAUNCH
   YY_LAUNCH_CHECK();
   return YY_OK;

@@ -362,6 +362,18 @@ int yy_search_counts(yy_engine* e, int32_t* out_counts, float* out_child_w, void
   return YY_OK;
 }
 
+int yy_engine_tree_view(yy_engine* e, yy_tree_view* out) {
+  if (!e || !out) return set_error(YY_ERR_INVALID, "null argument");
+  const EngineDev& d = e->dev;
+  out->max_nodes = d.max_nodes; out->edges_cap = d.edges_cap; out->W = d.W;
+  out->n_nodes = d.g_n_nodes; out->n_edges_used = d.g_n_edges;
+  out->node_black = d.node_black; out->node_white = d.node_white;
+  out->node_edge_base = d.node_edge_base; out->node_n_edges = d.node_n_edges; out->node_player = d.node_player;
+  out->node_flags = d.node_flags; out->node_value = d.node_value;
+  out->edge_N = d.edge_N; out->edge_W = d.edge_W; out->edge_P = d.edge_P; out->edge_child_meta = d.edge_cmeta; out->edge_action = d.edge_action;
+  return YY_OK;
+}
+
 const uint64_t* yy_engine_leaf_black(yy_engine* e) { return e ? e->dev.leaf_black : nullptr; }
 const uint64_t* yy_engine_leaf_white(yy_engine* e) { return e ? e->dev.leaf_white : nullptr; }
 const uint8_t* yy_engine_leaf_active(yy_engine* e) { return e ? e->dev.leaf_active : nullptr; }

@@ -23,7 +23,7 @@ class DataProcessor:
 
     def preprocess_sample(self, board, policy, player):
         n, m = self.board_size
-        planes, pol, _ = _engine.augment_samples_host(_board_array(board)[None], n, m, policy=np.asarray(policy, np.float32)[None])
+        planes, pol, _ = _engine.augment_samples_host(_board_array(board)[None], n, m, policy=np.asarray(policy, np.float32)[None], forms=1)
         return torch.from_numpy(planes[0]), torch.from_numpy(pol[0])
 
     def augment_sample(self, board, policy):
@@ -55,11 +55,8 @@ def dataset_tensors(game_data, game, augment=True):
     val = np.asarray([v for _, _, v in game_data], dtype=np.float64).astype(np.float32)
     b, w = bitboard.pack_boards(boards, n, m)
     bd, wd = _engine._to_dev(b, torch.int64), _engine._to_dev(w, torch.int64)
-    planes, policies, values = _engine.augment_samples(bd, wd, n, m, policy=_engine._to_dev(pol, torch.float32),
-                                                       values=_engine._to_dev(val, torch.float32))
-    if not augment:
-        planes, policies, values = planes[0::8], policies[0::8], values[0::8]
-    return planes, policies, values
+    return _engine.augment_samples(bd, wd, n, m, policy=_engine._to_dev(pol, torch.float32),
+                                   values=_engine._to_dev(val, torch.float32), forms=8 if augment else 1)
 
 
 def create_dataset_from_games(game_data, game, augment=True):

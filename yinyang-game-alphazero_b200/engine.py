@@ -101,7 +101,7 @@ def env_step(black, white, players, actions, rows, cols, rule_flags=0, out_mask=
     return out_mask, out_result
 
 
-def augment_samples(black, white, rows, cols, counts=None, policy=None, values=None, out=None):
+def augment_samples(black, white, rows, cols, counts=None, policy=None, values=None, out=None, forms=8):
     """Replay records -> training tensors with the reference's 8-fold augmentation (yy_augment_samples; replaces
     data_utils.create_dataset_from_games).  Device tensors in: black/white int64[N,W], counts int16/uint16[N,A] (visit
     counts) or policy float32[N,A], values float32[N] (optional).  Returns device tensors
@@ -113,15 +113,16 @@ def augment_samples(black, white, rows, cols, counts=None, policy=None, values=N
     n = black.shape[0]
     A = rows * cols
     dev = black.device
+    assert forms in (1, 8)        # 1: no augmentation (yy_dataset_samples, any board shape); 8: the reference's 8 forms
     if out is not None:
         planes, pol, vals = out
         assert planes.is_contiguous() and pol.is_contiguous() and planes.dtype == pol.dtype == torch.float32
-        assert planes.numel() == 8 * n * 5 * A and pol.numel() == 8 * n * A and planes.device == pol.device == dev
-        assert (vals is None) == (values is None) and (vals is None or (vals.numel() == 8 * n and vals.dtype == torch.float32))
+        assert planes.numel() == forms * n * 5 * A and pol.numel() == forms * n * A and planes.device == pol.device == dev
+        assert (vals is None) == (values is None) and (vals is None or (vals.numel() == forms * n and vals.dtype == torch.float32))
     else:
-        planes = torch.empty((8 * n, 5, rows, cols), dtype=torch.float32, device=dev)
-        pol = torch.empty((8 * n, A), dtype=torch.float32, device=dev)
-        vals = torch.empty(8 * n, dtype=torch.float32, device=dev) if values is not None else None
+        planes = torch.empty((forms * n, 5, rows, cols), dtype=torch.float32, device=dev)
+        pol = torch.empty((forms * n, A), dtype=torch.float32, device=dev)
+        vals = torch.empty(forms * n, dtype=torch.float32, device=dev) if values is not None else None
     if counts is not None:
         counts = counts.contiguous()
         assert counts.element_size() == 2 and counts.numel() == n * A
@@ -130,19 +131,20 @@ def augment_samples(black, white, rows, cols, counts=None, policy=None, values=N
         assert policy.numel() == n * A
     if values is not None:
         values = values.to(torch.float32).contiguous()
-    _lib.check(_lib.lib().yy_augment_samples(rows, cols, _ptr(black), _ptr(white), _ptr(counts), _ptr(policy), _ptr(values),
-                                             n, _ptr(planes), _ptr(pol), _ptr(vals), _stream()))
+    fn = _lib.lib().yy_augment_samples if forms == 8 else _lib.lib().yy_dataset_samples
+    _lib.check(fn(rows, cols, _ptr(black), _ptr(white), _ptr(counts), _ptr(policy), _ptr(values),
+                  n, _ptr(planes), _ptr(pol), _ptr(vals), _stream()))
     return planes, pol, vals
 
 
-def augment_samples_host(boards, rows, cols, counts=None, policy=None, values=None):
+def augment_samples_host(boards, rows, cols, counts=None, policy=None, values=None, forms=8):
     """numpy in / numpy out variant of augment_samples (H2D + kernel + D2H)."""
     _require_cuda()
     b, w = bitboard.pack_boards(boards, rows, cols)
     c = _to_dev(np.ascontiguousarray(counts, dtype=np.uint16).view(np.int16), torch.int16) if counts is not None else None
     p = _to_dev(np.ascontiguousarray(policy, dtype=np.float32), torch.float32) if policy is not None else None
     v = _to_dev(np.ascontiguousarray(values, dtype=np.float64).astype(np.float32), torch.float32) if values is not None else None
-    planes, pol, vals = augment_samples(_to_dev(b, torch.int64), _to_dev(w, torch.int64), rows, cols, counts=c, policy=p, values=v)
+    planes, pol, vals = augment_samples(_to_dev(b, torch.int64), _to_dev(w, torch.int64), rows, cols, counts=c, policy=p, values=v, forms=forms)
     return planes.cpu().numpy(), pol.cpu().numpy(), (vals.cpu().numpy() if vals is not None else None)
 
 
@@ -238,6 +240,19 @@ def env_step_host(boards, players, actions, rows, cols, rule_flags=0):
         nb = bitboard.unpack_boards(bd.cpu().numpy().view(np.uint64), wd.cpu().numpy().view(np.uint64), rows, cols)
     hp, hr = _to_host(pd, res)
     return bits, nb, hp, result_from_code(hr)
+
+
+def env_step_host_packed(black, white, players, actions, rows, cols, rule_flags=0):
+    """Host-buffer env step on PACKED boards (the layout of include/yinyang_b200.h: uint64[B, W] per colour): numpy in,
+    numpy out -- (mask words uint64[B,W], black' uint64[B,W], white' uint64[B,W], players' int8[B], result codes int8[B]).
+    21 bytes in and 26 out per 8x8 board instead of the 69 / 193 of the int8-array entry point."""
+    _require_cuda()
+    bd, wd = _to_dev(np.ascontiguousarray(black, dtype=np.uint64), torch.int64), _to_dev(np.ascontiguousarray(white, dtype=np.uint64), torch.int64)
+    pd = _to_dev(np.asarray(players, np.int8), torch.int8)
+    ad = _to_dev(np.asarray(actions, np.int32), torch.int32)
+    mask, res = env_step(bd, wd, pd, ad, rows, cols, rule_flags)
+    hm, hb, hw, hp, hr = _to_host(mask, bd, wd, pd, res)
+    return hm.view(np.uint64), hb.view(np.uint64), hw.view(np.uint64), hp, hr
 
 
 def next_state_host(boards, players, actions, rows, cols, rule_flags=0):
@@ -362,8 +377,9 @@ class Engine:
         return out_counts
 
     def search_host(self, boards, players, noise=None):
-        """numpy int8[n_games,n,m] boards + players -> (counts int32[n_games,A], child value sums f32)."""
-        b, w = bitboard.pack_boards(boards, self.rows, self.cols)
+        """numpy int8[n_games,n,m] boards (or a (black, white) pair of packed uint64[n_games, W] arrays) + players ->
+        (counts int32[n_games,A], child value sums f32)."""
+        b, w = boards if isinstance(boards, tuple) else bitboard.pack_boards(boards, self.rows, self.cols)
         bd, wd = _to_dev(b, torch.int64), _to_dev(w, torch.int64)
         pd = _to_dev(np.asarray(players, np.int8), torch.int8)
         nz = nm = None
@@ -400,6 +416,36 @@ class Engine:
         return (view(self.L.yy_engine_leaf_black(self.handle), nb, torch.int64).view(self.n_slots, self.W),
                 view(self.L.yy_engine_leaf_white(self.handle), nb, torch.int64).view(self.n_slots, self.W),
                 view(self.L.yy_engine_leaf_active(self.handle), self.n_slots, torch.uint8))
+
+    def tree_host(self, game=0):
+        """The whole search tree of one game as numpy arrays (yy_engine_tree_view): dict(n_nodes, edge_base, n_edges, player,
+        flags, value, black, white per node; N, W, P, child (node id or -1), child_flags, action per edge slot)."""
+        v = _lib.TreeView()
+        _lib.check(self.L.yy_engine_tree_view(self.handle, ctypes.byref(v)))
+        base = self.workspace.data_ptr()
+
+        def grab(ptr, first, count, dtype, itemsize):
+            off = ptr - base + first * itemsize
+            return self.workspace[off: off + count * itemsize].view(dtype)
+        nn = int(grab(v.n_nodes, game, 1, torch.int32, 4).item())
+        ne = int(grab(v.n_edges_used, game, 1, torch.int32, 4).item())
+        n0, e0, W = game * v.max_nodes, game * v.edges_cap, v.W
+        dev = {"edge_base": grab(v.node_edge_base, n0, nn, torch.int32, 4), "n_edges": grab(v.node_n_edges, n0, nn, torch.int16, 2),
+               "player": grab(v.node_player, n0, nn, torch.int8, 1), "flags": grab(v.node_flags, n0, nn, torch.uint8, 1),
+               "value": grab(v.node_value, n0, nn, torch.float32, 4),
+               "black": grab(v.node_black, n0 * W, nn * W, torch.int64, 8), "white": grab(v.node_white, n0 * W, nn * W, torch.int64, 8),
+               "N": grab(v.edge_N, e0, ne, torch.int32, 4), "W": grab(v.edge_W, e0, ne, torch.float32, 4),
+               "P": grab(v.edge_P, e0, ne, torch.float32, 4), "meta": grab(v.edge_child_meta, e0, ne, torch.int64, 8),
+               "action": grab(v.edge_action, e0, ne, torch.uint8, 1)}
+        keys = sorted(dev)
+        host = dict(zip(keys, _to_host(*[dev[k] for k in keys])))
+        host = {k: (h if h is not None else np.zeros(0, dtype=np.int64)) for k, h in host.items()}
+        meta = host.pop("meta").view(np.uint64)
+        host["child"] = ((meta >> np.uint64(32)) & np.uint64(0xFFFF)).astype(np.int64) - 1
+        host["child_flags"] = ((meta >> np.uint64(57)) & np.uint64(7)).astype(np.uint8)
+        host["black"] = host["black"].view(np.uint64).reshape(nn, W); host["white"] = host["white"].view(np.uint64).reshape(nn, W)
+        host["n_nodes"] = nn
+        return host
 
     def search_counts(self):
         counts = torch.empty((self.n_games, self.A), dtype=torch.int32, device=self.tdev)

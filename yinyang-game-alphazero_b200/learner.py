@@ -259,6 +259,8 @@ class Learner:
         self._use_graph = use_graph and _ops is None
         if state_dict is not None:
             self.load_state_dict(state_dict)
+        else:
+            self.sync_from_rank0()
 
     # -- views into the flat buffers
     def _view(self, buf, key):
@@ -317,6 +319,27 @@ class Learner:
         for pre in self._bn:
             self.running[pre][0].copy_(sd[pre + ".running_mean"]); self.running[pre][1].copy_(sd[pre + ".running_var"])
         self.batches_tracked = int(sd.get("bn1.num_batches_tracked", 0))
+        self.sync_from_rank0()
+
+    def sync_from_rank0(self):
+        """Data parallel: every rank adopts rank 0's parameters, Adam moments and batch-norm running statistics (one
+        broadcast each), so that the all-reduced gradients are taken at ONE parameter point from the first step on --
+        whatever each rank's own initialisation or checkpoint was."""
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        for buf in (self.params, self.m, self.v):
+            dist.broadcast(buf, 0)
+        stats = torch.cat([t for pre in self._bn for t in self.running[pre]])
+        dist.broadcast(stats, 0)
+        off = 0
+        for pre in self._bn:
+            for t in self.running[pre]:
+                t.copy_(stats[off:off + t.numel()]); off += t.numel()
+        meta = torch.tensor([self.batches_tracked, int(self.step_count[0].item())], dtype=torch.int64, device=self.dev)
+        dist.broadcast(meta, 0)
+        self.batches_tracked = int(meta[0].item())
+        self.step_count[0] = int(meta[1].item())
 
     def _export(self, buf):
         out = {}

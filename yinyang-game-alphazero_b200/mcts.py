@@ -23,35 +23,73 @@ logger = logging.getLogger("YinYangMCTS")
 CPUCT = 1.0  # mcts.py:26
 
 
-class ChildStats:
-    """The slice of a reference child Node that callers read (mcts.py:38-40)."""
-    __slots__ = ("action", "visits", "value_sum", "parent")
+class Node:
+    """Read-only mirror of the reference's Node (mcts.py:28-225) over the engine's tree arrays (Engine.tree_host): the
+    statistics its callers and tests read -- ``visits``, ``value_sum`` (np.float32), ``prior``, ``children``
+    (dict action -> Node in ascending action order, built on first access, the whole tree is reachable), ``board``,
+    ``player``, ``is_terminal`` / ``terminal_value``, ``is_expanded()``, ``get_children_visit_counts()``,
+    ``get_children_distribution(temperature)``."""
 
-    def __init__(self, action, visits, value_sum):
-        self.action, self.visits, self.value_sum, self.parent = action, int(visits), np.float32(value_sum), None
+    def __init__(self, game, tree, node_id, visits, value_sum=0.0, prior=0.0, action=None, parent=None):
+        self.game, self._t, self._id = game, tree, int(node_id)
+        self.visits, self.value_sum, self.prior = int(visits), np.float32(value_sum), np.float32(prior)
+        self.action, self.parent = action, parent
+        self._children = None
 
-    def get_value(self):
+    # -- state of the node (None / False while no simulation has expanded it: mcts.py:42-48)
+    @property
+    def player(self):
+        return int(self._t["player"][self._id]) if self._id >= 0 else None
+
+    @property
+    def board(self):
+        if self._id < 0:
+            return None
+        from .game import YinYangLogic
+        n, m = self.game.getBoardSize()
+        b = YinYangLogic(n, m, getattr(self.game, "rule_flags", 0))
+        b.board = bitboard.unpack_boards(self._t["black"][self._id][None], self._t["white"][self._id][None], n, m)[0]
+        return b
+
+    @property
+    def is_terminal(self):
+        return self._id >= 0 and bool(self._t["flags"][self._id] & 2)
+
+    @property
+    def terminal_value(self):
+        if not self.is_terminal:
+            return None
+        v = float(self._t["value"][self._id])
+        return int(v) if v in (1.0, -1.0) else 0.0001          # yin_yang_game.py:101-107
+
+    @property
+    def children(self):
+        if self._children is None:
+            self._children = {}
+            if self._id >= 0:
+                t, base, cnt = self._t, int(self._t["edge_base"][self._id]), int(self._t["n_edges"][self._id])
+                for k in range(base, base + cnt):
+                    a = int(t["action"][k])
+                    self._children[a] = Node(self.game, t, t["child"][k], t["N"][k], t["W"][k], t["P"][k], a, self)
+        return self._children
+
+    def is_expanded(self):  # mcts.py:93-95
+        return len(self.children) > 0
+
+    def get_value(self):  # mcts.py:158-162
         return 0.0 if self.visits == 0 else self.value_sum / self.visits
 
     def get_visit_count(self):
         return self.visits
 
-
-class RootView:
-    """What ``MCTS.search`` returns as ``root``: visit statistics of the root's children."""
-
-    def __init__(self, game, counts, child_w, legal):
-        self.game = game
-        self._counts = np.asarray(counts, dtype=np.float64)
-        self.children = {int(a): ChildStats(int(a), counts[a], child_w[a]) for a in np.flatnonzero(legal)}
-        self.visits = int(np.sum(counts))
-        self.is_terminal = False
-
     def get_children_visit_counts(self):  # mcts.py:168-181
-        return self._counts.copy()
+        counts = np.zeros(self.game.getActionSize())
+        for a, ch in self.children.items():
+            counts[a] = ch.visits
+        return counts
 
     def get_children_distribution(self, temperature=1.0):  # mcts.py:183-215
-        counts = self._counts.copy()
+        counts = self.get_children_visit_counts()
         A = counts.size
         if temperature == 0:
             best = np.where(counts == np.max(counts))[0]
@@ -62,6 +100,9 @@ class RootView:
             counts = np.power(counts, 1.0 / temperature)
         s = np.sum(counts)
         return counts / s if s > 0 else np.ones(A) / A
+
+
+ChildStats = RootView = Node      # names of the round-1 facade
 
 
 class MCTS:
@@ -87,6 +128,10 @@ class MCTS:
 
     def _engine(self, n_games):
         e = self._engines.get(n_games)
+        version = getattr(self.neural_net, "weights_version", 0)
+        if e is not None and self._mode() == "nn" and getattr(e, "_weights_version", version) != version:
+            e.load_state_dict(self.neural_net.state_dict())      # the net was reloaded / trained since the engine was built:
+            e._weights_version = version                         # the reference holds the net by reference (mcts.py:249)
         if e is None:
             n, m = self.game.getBoardSize()
             kw = dict(rows=n, cols=m, n_games=n_games, n_sims=self.num_simulations, evaluator=self._mode(), cpuct=self.cpuct,
@@ -97,6 +142,7 @@ class MCTS:
             if self.num_threads > 1 and self._mode() != "external":
                 kw["leaves_per_step"] = self.num_threads
             e = self._engines[n_games] = _engine.Engine(**kw)
+            e._weights_version = version
         return e
 
     # -- batched search: the natural GPU entry point
@@ -149,10 +195,8 @@ class MCTS:
         n, m = self.game.getBoardSize()
         grid = board.get_board()
         counts, cw = self.search_batch(grid[None], [player], add_exploration_noise)
-        legal = counts[0] > 0
-        legal |= _engine.legal_mask_host(grid[None], np.array([player], np.int8), n, m,
-                                         getattr(self.game, "rule_flags", 0))[0].astype(bool)
-        root = RootView(self.game, counts[0], cw[0], legal)
+        # the tree stays in the engine's arenas until the next search: mirror it (root.visits = simulations run, mcts.py:406-412)
+        root = Node(self.game, self._engine(1).tree_host(0), 0, self.num_simulations)
         logger.info("MCTS search completed with %d total visits", root.visits)
         return root.get_children_distribution(self.temperature), root
 

@@ -47,6 +47,12 @@ class _Params(nn.Module):  # parameter layout + initialisation of neural_network
                     nn.init.zeros_(mod.bias)
 
 
+def safe_load(filename):
+    """torch.load restricted to tensors and plain containers (weights_only=True, the default of torch >= 2.6 that the
+    reference's torch.load(filename, map_location='cpu') gets): a checkpoint holds a state_dict, a tuple and an int."""
+    return torch.load(filename, map_location="cpu", weights_only=True)
+
+
 class YinYangNeuralNetwork:
     """Drop-in for the evaluator role of the reference class: predict / load_model / save_model."""
 
@@ -58,6 +64,7 @@ class YinYangNeuralNetwork:
         self.num_channels, self.num_res_blocks = num_channels, num_res_blocks
         self._params = _Params(self.board_size[0], self.board_size[1], num_channels, num_res_blocks)
         self._engine = None
+        self.weights_version = 0           # bumped whenever the parameters change: holders of device copies re-upload
 
     # -- parameters
     def state_dict(self):
@@ -65,6 +72,7 @@ class YinYangNeuralNetwork:
 
     def load_state_dict(self, sd):
         self._params.load_state_dict(sd)
+        self.weights_version += 1
         if self._engine is not None:
             self._engine.load_state_dict(self._params.state_dict())
 
@@ -78,7 +86,7 @@ class YinYangNeuralNetwork:
     def load_model(self, filename):  # neural_network.py:217-237
         if not os.path.exists(filename):
             raise FileNotFoundError(f"Model file {filename} not found")
-        ck = torch.load(filename, map_location="cpu", weights_only=False)
+        ck = safe_load(filename)
         self.load_state_dict(ck["state_dict"])
 
     # -- inference (GPU)

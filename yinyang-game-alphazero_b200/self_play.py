@@ -29,11 +29,17 @@ MAX_CONCURRENT_GAMES = 4096          # game slots per GPU: 28 games per SM keep 
 
 
 def _load_network(game, model_path):
-    net = YinYangNeuralNetwork(game)
+    """self_play.py:54-59; the width / depth of the network are taken from the checkpoint (the reference builds its
+    default 128 x 10 network and fails on anything else)."""
     if os.path.exists(model_path):
-        net.load_model(model_path)
+        from . import weights as _weights
+        from .network import safe_load
+        sd = safe_load(model_path)["state_dict"]
+        net = YinYangNeuralNetwork(game, *_weights.infer_arch(sd))
+        net.load_state_dict(sd)
         logger.info(f"Loaded model from {model_path}")
     else:
+        net = YinYangNeuralNetwork(game)
         logger.warning(f"No model found at {model_path}, using randomly initialized model")  # self_play.py:58-59
     return net
 

@@ -42,6 +42,14 @@ class AlphaZeroTrainer:
         logger.info(f"Training on {len(examples)} examples for {epochs} epochs")
         planes, policies, values = data_utils.dataset_tensors(examples, self.game, augment=augment)
         n = planes.shape[0]
+        if self.learner.world > 1:
+            # data parallel: every step is a collective (one all-reduce of the gradients), so all ranks must run the same
+            # number of steps per epoch -- agree on the smallest dataset and drop the surplus samples of the others
+            import torch.distributed as dist
+            t = torch.tensor([n], dtype=torch.int64, device=planes.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            n = int(t.item())
+            planes, policies, values = planes[:n], policies[:n], values[:n]
         metrics = {"policy_loss": [], "value_loss": [], "total_loss": []}
         for epoch in range(epochs):
             t0 = time.time()

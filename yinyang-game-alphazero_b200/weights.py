@@ -174,7 +174,7 @@ def pack_state_dict(state_dict, rows: int, cols: int) -> np.ndarray:
 def load_checkpoint(path: str):
     """Reads a reference checkpoint file (neural_network.py:209-213) -> dict with 'state_dict'."""
     import torch
-    ck = torch.load(path, map_location="cpu", weights_only=False)
+    ck = torch.load(path, map_location="cpu", weights_only=True)     # tensors and plain containers only
     if "state_dict" not in ck:
         ck = {"state_dict": ck}
     return ck
