@@ -213,17 +213,21 @@ def test_trainer_facade_trains_and_checkpoints(pkg, tmp_path):
     assert p.shape == (36,) and abs(p.sum() - 1) < 1e-3 and -1 <= v <= 1
 
 
-def test_cli_train_mode_runs_the_whole_loop(pkg, tmp_path):
-    """train_alphazero.py --mode train (AlphaZero.run, alphazero.py:248-270): self-play -> learner -> arena -> promotion."""
+@pytest.mark.parametrize("file_loop", [False, True])
+def test_cli_train_mode_runs_the_whole_loop(pkg, tmp_path, file_loop):
+    """train_alphazero.py --mode train (AlphaZero.run, alphazero.py:248-270): self-play -> learner -> arena -> promotion.
+    Default: the examples stay on the GPU between the stages (device_loop.DeviceLoop); --file-loop: the reference's data
+    files between the stages."""
     import subprocess, sys, glob
     import torch
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     md, dd = str(tmp_path / "models"), str(tmp_path / "data")
     r = subprocess.run([sys.executable, os.path.join(root, "train_alphazero.py"), "--mode", "train", "--rows", "6", "--cols", "6",
                         "--iterations", "1", "--episodes", "8", "--simulations", "16", "--epochs", "1", "--arena-games", "4",
-                        "--model-dir", md, "--data-dir", dd], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+                        "--model-dir", md, "--data-dir", dd] + (["--file-loop"] if file_loop else []),
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr[-2000:]
-    assert len(glob.glob(os.path.join(dd, "self_play_data_*.npz"))) == 1
+    assert len(glob.glob(os.path.join(dd, "self_play_data_*.npz"))) == (1 if file_loop else 0)
     for name in ("current_model.pth.tar", "best_model.pth.tar", "checkpoint_1.pth.tar"):
         assert os.path.exists(os.path.join(md, name)), name
     cur = torch.load(os.path.join(md, "current_model.pth.tar"), map_location="cpu", weights_only=False)["state_dict"]
@@ -257,8 +261,9 @@ def test_gui_ai_move_endpoint_body(pkg, tmp_path):
 
 
 def test_cli_train_mode_under_torchrun_two_gpus(pkg, tmp_path):
-    """torchrun --nproc-per-node 2 train_alphazero.py --mode train: every rank self-plays its share into its own data file, the
-    learner trains data parallel, rank 0 writes checkpoints and plays the arena (needs two GPUs; skipped on a one-GPU box)."""
+    """torchrun --nproc-per-node 2 train_alphazero.py --mode train: every rank self-plays its share, the finished games are
+    all-gathered over NCCL into every rank's device replay buffer, the learner trains data parallel, rank 0 writes checkpoints,
+    plays the arena and broadcasts the promoted weights (needs two GPUs; skipped on a one-GPU box)."""
     import subprocess, sys, glob, socket
     import torch
     if torch.cuda.device_count() < 2:
@@ -271,7 +276,7 @@ def test_cli_train_mode_under_torchrun_two_gpus(pkg, tmp_path):
                         "--iterations", "1", "--episodes", "16", "--simulations", "16", "--epochs", "1", "--arena-games", "4",
                         "--model-dir", md, "--data-dir", dd], capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr[-2000:]
-    assert len(glob.glob(os.path.join(dd, "self_play_data_*_r0.npz"))) == 1 and len(glob.glob(os.path.join(dd, "self_play_data_*_r1.npz"))) == 1
+    assert "2 ranks" in r.stderr or "examples" in r.stderr
     cur = torch.load(os.path.join(md, "current_model.pth.tar"), map_location="cpu", weights_only=False)["state_dict"]
     ck = torch.load(os.path.join(md, "checkpoint_1.pth.tar"), map_location="cpu", weights_only=False)["state_dict"]
     assert all(torch.equal(cur[k], ck[k]) for k in ck) and int(ck["bn1.num_batches_tracked"]) > 0
@@ -396,3 +401,44 @@ def test_self_play_array_wire_and_rolling_driver(pkg, tmp_path):
             assert np.abs(ex["boards"][sel][0]).sum() == 0
     assert not set(np.unique(first["game"])) & set(np.unique(second["game"]))
     sp.close()
+
+
+def test_cli_self_play_mode_under_torchrun_two_gpus(pkg, tmp_path):
+    """torchrun --nproc-per-node 2 train_alphazero.py --mode self-play: the episodes are sharded over the ranks, the examples
+    gathered to rank 0 over NCCL, ONE data file is written (needs two GPUs)."""
+    import subprocess, sys, glob, socket
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md, dd = str(tmp_path / "models"), str(tmp_path / "data")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "train_alphazero.py"), "--mode", "self-play", "--rows", "6", "--cols", "6",
+                        "--episodes", "21", "--simulations", "16", "--init-model", "--model-dir", md, "--data-dir", dd],
+                       capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = glob.glob(os.path.join(dd, "self_play_data_*.npz"))
+    assert len(files) == 1
+    d = np.load(files[0])
+    assert d["boards"].shape[1:] == (6, 6) and len(d["values"]) >= 21
+    assert int((np.abs(d["boards"]).sum(axis=(1, 2)) == 0).sum()) == 21          # one empty first position per game: 11 + 10 games
+
+
+def test_device_loop_single_gpu(pkg):
+    """DeviceLoop on one GPU: two iterations, examples go replay ring -> device buffer -> augmentation -> learner without
+    leaving the device; rolling self-play returns at least the requested games; the losses are finite and the weights move."""
+    import torch
+    from yinyang_game_alphazero_b200.device_loop import DeviceLoop
+    game = pkg["game"].YinYangGame(4, 4)
+    torch.manual_seed(0)
+    loop = DeviceLoop(game, num_iterations=2, num_episodes=12, num_simulations=16, num_epochs=1, batch_size=32, sample_size=256,
+                      eval_games=4, num_channels=32, num_res_blocks=1, slots=8, save_files=False, seed=1)
+    w0 = loop.learner.params.clone()
+    hist = loop.run()
+    assert len(hist) == 2 and all(h["examples_global"] > 0 and h["learner_steps"] > 0 for h in hist)
+    assert all(np.isfinite(h["policy_loss"]) and np.isfinite(h["value_loss"]) for h in hist)
+    assert len(loop.buffer) == sum(h["examples_global"] for h in hist)
+    assert not torch.equal(w0, loop.learner.params)
+    assert set(torch.unique(loop.buffer.z[: len(loop.buffer)]).tolist()) <= {1.0, -1.0, float(np.float32(0.0001))}
+    loop.close()

@@ -42,6 +42,9 @@ def parse_args(argv=None):
     p.add_argument("--init-model", action="store_true", help="create a randomly initialised model file if missing")
     p.add_argument("--eval-games", type=int, default=10)
     p.add_argument("--arena-games", type=int, default=40, help="--mode train: games of current vs best per iteration (alphazero.py:136)")
+    p.add_argument("--file-loop", action="store_true",
+                   help="--mode train: exchange self-play data and weights between the stages through files in --data-dir / "
+                        "--model-dir like the reference, instead of keeping the examples on the GPU(s)")
     p.add_argument("--replay-wire", choices=["arrays", "native", "reference"], default="arrays",
                    help="'arrays' (default): boards as one int8[N,n,m] array under the reference's npz keys; 'native': an object "
                         "array of this package's YinYangLogic; 'reference': boards pickled as "
@@ -71,10 +74,14 @@ def main(argv=None):
             local = int(os.environ.get("LOCAL_RANK", "0"))
             torch.cuda.set_device(local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        AlphaZero(game=game, model_dir=args.model_dir, data_dir=args.data_dir, num_iterations=args.iterations,
-                  num_episodes=args.episodes, num_simulations=args.simulations, num_epochs=args.epochs,
-                  num_workers=args.workers, mcts_threads=args.mcts_threads, eval_games=args.arena_games,
-                  batch_size=args.batch_size, lr=args.lr).run()
+        az = AlphaZero(game=game, model_dir=args.model_dir, data_dir=args.data_dir, num_iterations=args.iterations,
+                       num_episodes=args.episodes, num_simulations=args.simulations, num_epochs=args.epochs,
+                       num_workers=args.workers, mcts_threads=args.mcts_threads, eval_games=args.arena_games,
+                       batch_size=args.batch_size, lr=args.lr)
+        if args.file_loop:
+            az.run()                                                     # the reference's loop: data files between the stages
+        else:
+            az.run_device_resident()                                     # examples stay on the GPU(s); NCCL gather / broadcast
         if world > 1:
             dist.destroy_process_group()
         logger.info("Training completed!")

@@ -90,6 +90,25 @@ class AlphaZero:
         logger.info(f"Kept best model with win ratio {win_ratio:.2f} < {self.update_threshold}")
         return False
 
+    def run_device_resident(self, slots=4096, exact_episodes=False):
+        """The same loop with every example staying on the GPU(s) between self-play and the learner (device_loop.DeviceLoop):
+        replay ring -> NCCL all-gather -> device replay buffer -> augmentation kernel -> learner -> NCCL weight broadcast.
+        Starts from best_model.pth.tar, writes current / best / checkpoint files as a side product (rank 0)."""
+        from .device_loop import DeviceLoop
+        from .network import safe_load
+        sd = safe_load(self.best_model_path)["state_dict"]
+        from . import weights as _weights
+        C, B = _weights.infer_arch(sd)
+        loop = DeviceLoop(self.game, model_dir=self.model_dir, num_iterations=self.num_iterations, num_episodes=self.num_episodes,
+                          num_simulations=self.num_simulations, num_epochs=self.num_epochs, batch_size=self.batch_size, lr=self.lr,
+                          update_threshold=self.update_threshold, eval_games=self.eval_games, num_channels=C, num_res_blocks=B,
+                          slots=slots, temperature_threshold=self.temperature_threshold, exact_episodes=exact_episodes,
+                          mcts_threads=self.mcts_threads, state_dict=sd)
+        try:
+            return loop.run()
+        finally:
+            loop.close()
+
     def run(self):  # alphazero.py:248-270
         for iteration in range(self.num_iterations):
             logger.info(f"Starting iteration {iteration + 1}/{self.num_iterations}")

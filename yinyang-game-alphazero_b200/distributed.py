@@ -34,9 +34,10 @@ def broadcast_image(image: torch.Tensor, src: int = 0, group=None) -> torch.Tens
     return image
 
 
-def gather_records(tensors, dst: int = 0, group=None):
+def gather_records(tensors, dst=0, group=None):
     """All ranks pass a dict of equally-keyed tensors whose first dimension is the record count (may differ
-    per rank).  Rank `dst` gets the concatenation over ranks (rank order), the others get None."""
+    per rank).  Rank `dst` gets the concatenation over ranks (rank order), the others get None; dst=None: every
+    rank gets it (the data-parallel learner's ranks all train on the global replay buffer)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     keys = sorted(tensors)
@@ -54,10 +55,10 @@ def gather_records(tensors, dst: int = 0, group=None):
         pad[: raw.shape[0]] = raw
         bufs = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(bufs, pad, group=group)
-        if rank == dst:
+        if dst is None or rank == dst:
             cat = torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0).contiguous()
             out[k] = cat.view(t.dtype).reshape((cat.shape[0],) + row_shape)
-    return out if rank == dst else None
+    return out if (dst is None or rank == dst) else None
 
 
 # ---- engine-level helpers (CUDA) -------------------------------------------------------------------------
