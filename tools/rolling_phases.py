@@ -22,6 +22,7 @@ for desc in [int(x) for x in sys.argv[1:]] or [0]:
     e = engine.Engine(rows=n, cols=m, n_games=games, n_sims=sims, evaluator="nn", state_dict=sd, seed=1, descents_per_step=desc,
                       replay_capacity=games * 3 * (warm + steps + 2))
     iters = sims + 1
+    e.L.yy_engine_set_debug_flags(e.handle, int(os.environ.get("YY_DBG_FLAGS", 0)))
     for _ in range(warm):
         e.selfplay_advance(iters)
     torch.cuda.synchronize()
@@ -48,6 +49,9 @@ for desc in [int(x) for x in sys.argv[1:]] or [0]:
         out[name] = {"phases": "tower, fc, heads+tree, barrier, zero | in fc: panel loads, MMA waits, scatter (cycles per iteration, warp 0 / warp 15)",
                      "w0": (ph[0] / iters).round(0).tolist(), "w15": (ph[15] / iters).round(0).tolist(),
                      "total_w0": float(round(ph[0, :5].sum() / iters))}
+    out["mma_issuer_cta0"] = {"waited_for_weights": int(raw[920]) / iters, "waited_for_activations": int(raw[921]) / iters, "total": int(raw[922]) / iters,
+                              "unit": "cycles per iteration"}
+    out["flags"] = int(os.environ.get("YY_DBG_FLAGS", 0))
     print(json.dumps(out))
     e.close()
     del e

@@ -158,6 +158,7 @@ SIGNATURES = {
     "yy_engine_set_profiling": (_I, [_P, _I]),
     "yy_engine_get_profile": (_I, [_P, ctypes.POINTER(_I64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
     "yy_engine_set_debug_stamps": (_I, [_P, _P]),
+    "yy_engine_set_debug_flags": (_I, [_P, _I]),
     "yy_selfplay_reset": (_I, [_P, _P]),
     "yy_selfplay_run": (_I, [_P, ctypes.c_int32, _P]),
     "yy_selfplay_advance": (_I, [_P, _I64, _P]),

@@ -39,6 +39,11 @@ struct FusedArgs {
   int iterations;              // 1 = plain forward; n_sims + 1 = whole search; rolling self-play: any number of steps
   int mode;                    // YY_FUSED_FORWARD / YY_FUSED_SEARCH (tree step after every evaluation) / YY_FUSED_SELFPLAY
   int use_nn;                  // 0 = deterministic-prior (stub) evaluator: tree steps only
+  int split_halves;            // developer A/B (yy_engine_set_debug_flags bit 0): the two halves of a group ping-pong through the
+                               // tensor cores.  OFF in the product: it hides the epilogue (the MMA issuer's wait for activations
+                               // drops from 513 k to 93 k cycles per step) but every half streams the layer's weights again, and
+                               // the weight stream (~10 B/clk per SM through the 3-slot ring) then stalls the issuer for 735 k
+                               // cycles per step: 1,286 against 1,298 TFLOP/s (profiles/r02_ab_pingpong_*.txt)
   long long* dbg;
 };
 
@@ -66,9 +71,12 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   int16_t* pos_tab = reinterpret_cast<int16_t*>(smem + SM_POS + 128 * TW_MAXT * 2);    // M row -> board*256 + cell, or -1
   const uint32_t bar0 = smem_u32(smem + SM_BAR);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (TW_FC_SLOTS + s); };
-  auto peer_full_bar = [&](int s) { return bar0 + 8u * (2 * TW_FC_SLOTS + s); };   // leader: the follower's stage s landed
-  const uint32_t acc_full = bar0 + 8u * (3 * TW_FC_SLOTS), act_ready = bar0 + 8u * (3 * TW_FC_SLOTS + 1);
+  auto empty_bar = [&](int s) { return bar0 + 8u * (TW_NBAR + s); };
+  auto peer_full_bar = [&](int s) { return bar0 + 8u * (2 * TW_NBAR + s); };   // leader: the follower's stage s landed
+  // accumulators complete / activations ready, one pair per HALF of a group (developer A/B split_halves: the two halves of
+  // a group ping-pong through the tensor cores; the product runs a group as ONE half)
+  auto acc_full = [&](int h) { return bar0 + 8u * (3 * TW_NBAR + 2 * h); };
+  auto act_ready = [&](int h) { return bar0 + 8u * (3 * TW_NBAR + 2 * h + 1); };
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
 
@@ -93,9 +101,11 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     pos_tab[i] = (int16_t)v;
   }
   if (tid == 0) {
-    for (int s = 0; s < TW_FC_SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(peer_full_bar(s), 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(act_ready, CG * TW_EPI_THREADS);   // pair: the leader's barrier also collects the follower's epilogue threads
+    for (int s = 0; s < TW_NBAR; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(peer_full_bar(s), 1); }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(acc_full(h), 1);
+      mbar_init(act_ready(h), CG * TW_EPI_THREADS);   // pair: the leader's barrier also collects the follower's epilogue threads
+    }
     fence_barrier_init();
   }
   if (warp == 1) { if (CG == 2) tmem_alloc2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
@@ -138,6 +148,15 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           : g.row_aligned ? ((nb * g.rows_per_board + 15) >> 4) : ((nb * g.PB + g.pitch + 1 + 127) >> 7);
     return t < g.T ? t : g.T;
   };
+  // A group's tiles split into two halves that are INDEPENDENT through the whole tower (no 3x3 tap of one half reads a
+  // row of the other): interleaved pairs (8x8: a tile = two whole boards, zero row groups between tiles) and half-board
+  // tiles (16x16: two tiles = one board).  Returns the tiles of half 0; == T: one half only (other layouts, tiny groups).
+  auto half_split = [&](int T) {
+    if (!a.split_halves) return T;
+    if (g.row_aligned == 3) return T >= 2 ? (T + 1) >> 1 : T;
+    if (g.row_aligned == 2) return T == 4 ? 2 : T;
+    return T;
+  };
   auto batch_end = [&](int bb0) { return (bb0 + a.batch_boards < n_struct) ? bb0 + a.batch_boards : n_struct; };   // structural
   // FC stage geometry: rows of M tile t of head h
   auto fc_tiles = [&](int h) { return h ? 2 : fc.Tp; };
@@ -151,6 +170,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     return s < (uint32_t)TW_STAGES ? ring_base + s * TW_STAGE_BYTES : act_base + (uint32_t)TW_FC_EXTRA_OFF + (s - TW_STAGES) * TW_STAGE_BYTES;
   };
   auto fc_merge = [&](int h, int t) { return fc_rows(h, t) <= 64 ? 2 : 1; };
+  // the tower's view of the ring: TW_CONV_SLOTS slots of 8 KB; barrier set s serves conv slot s and FC slot s (the two
+  // cycles never overlap in time: the producer waits for the last MMA of one before it starts the other)
+  auto conv_slot_addr = [&](uint32_t s) { return ring_base + s * (uint32_t)TW_CONV_SLOT_BYTES; };
 
   if (warp == 0) {
     // =========================================================== weight producer (whole warp walks the loop with
@@ -158,16 +180,18 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     if (!a.use_nn) {
       for (int iter = 0; dyn && iter < a.iterations; ++iter) { fetch_counts(iter); if (!any_work) break; }
     } else {
-      uint32_t ci = 0, used = 0, ephase = 0, acc_n = 0;     // conv stage counter, slots used so far, empty-phase bits, commits so far
-      auto push = [&](uint32_t slot, const uint8_t* src, uint32_t bytes) {
+      uint32_t ci = 0, used = 0, ephase = 0, acc_n[2] = {0, 0};     // conv stage counter, slots used so far, empty-phase bits, commits so far per half
+      auto push_to = [&](uint32_t slot, uint32_t dst, const uint8_t* src, uint32_t bytes) {
         if ((used >> slot) & 1u) { mbar_wait(empty_bar(slot), (ephase >> slot) & 1u); ephase ^= 1u << slot; }
         used |= 1u << slot;
         if (elect_one()) {
           mbar_arrive_expect_tx(full_bar(slot), bytes);
-          bulk_g2s(slot_addr(slot), src, bytes, full_bar(slot));
+          bulk_g2s(dst, src, bytes, full_bar(slot));
         }
         __syncwarp();
       };
+      auto push = [&](uint32_t slot, const uint8_t* src, uint32_t bytes) { push_to(slot, slot_addr(slot), src, bytes); };
+      bool fc_before = false;
       // pair, FC stages: both CTAs need the SAME weight tile, so the two producers take turns fetching a stage and the
       // copy is multicast into both CTAs' slots (each CTA arms its own barrier) -- halves the L2 reads of the FC phase,
       // which is bound by the aggregate L2 bandwidth (all SMs stream the 1.25 MB at the same time).  A slot is free in
@@ -185,21 +209,33 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         if (dyn) { fetch_counts(iter); if (!any_work) break; }
         for (int bb0 = 0; bb0 < n_struct; bb0 += a.batch_boards) {
           const int slim = batch_end(bb0);
+          int nh = 1;
+          // the FC heads of the previous batch used the ring as 16 KB slots: their last MMA must be complete before 8 KB
+          // conv slots (a different carving of the same memory) are filled again
+          if (TW_CONV_SLOT_BYTES != TW_STAGE_BYTES && fc_before) mbar_wait(acc_full(0), (acc_n[0] - 1) & 1u);
           for (int b0 = bb0; b0 < slim; b0 += g.Gb) {
-            for (int l = 0; l < L; ++l, ++acc_n) {
+            const int T = tiles_for(b0, slim);
+            nh = half_split(T) < T ? 2 : 1;
+            for (int l = 0; l < L; ++l) {
               const LayerInfo li = layer_info(l, g.blocks, CG);
               const uint32_t bytes = (uint32_t)li.stage_bytes / CG;     // pair: my half of the stage's output channels
               const uint8_t* src = a.conv_stream + li.stream_off + (long long)rank * bytes;
-              for (int j = 0; j < li.n_stages; ++j, ++ci) push(ci % TW_STAGES, src + (long long)j * li.stage_bytes, bytes);
+              for (int hh = 0; hh < nh; ++hh) {                          // every half of the group streams the layer's weights
+                ++acc_n[hh];
+                for (int j = 0; j < li.n_stages; ++j, ++ci)
+                  push_to(ci % TW_CONV_SLOTS, conv_slot_addr(ci % TW_CONV_SLOTS), src + (long long)j * li.stage_bytes, bytes);
+              }
             }
           }
-          // the extra FC slots overlay activation rows: wait until the last head conv of the batch has been computed
-          // (commit number acc_n - 1 of acc_full; it cannot be overtaken -- the next commit needs FC stages from me)
-          mbar_wait(acc_full, (acc_n - 1) & 1u);
+          // the extra FC slots overlay activation rows: wait until the last head conv of the batch has been computed, in
+          // both halves (commit number acc_n - 1 of acc_full; it cannot be overtaken -- the next commit needs stages from me)
+          mbar_wait(acc_full(0), (acc_n[0] - 1) & 1u);
+          if (nh == 2) mbar_wait(acc_full(1), (acc_n[1] - 1) & 1u);
           const uint8_t* src = a.fc_stream;
           uint32_t fi = 0;
+          fc_before = true;
           for (int h = 0; h < 2; ++h)
-            for (int p = 0; p < fc.n_panels; ++p, ++acc_n) {
+            for (int p = 0; p < fc.n_panels; ++p, ++acc_n[0]) {
               const int ns = panel_stages(p);
               for (int t = 0; t < fc_tiles(h); ++t) {
                 const uint32_t bytes = 128u * (uint32_t)fc_rows(h, t);
@@ -232,8 +268,11 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         if (dyn) { fetch_counts(iter); if (!any_work) break; }
         for (int bb0 = 0; bb0 < n_struct; bb0 += a.batch_boards) {
           const int slim = batch_end(bb0);
-          for (int b0 = bb0; b0 < slim; b0 += g.Gb)
-            for (int l = 0; l < L; ++l) { const int ns = layer_info(l, g.blocks, CG).n_stages; for (int j = 0; j < ns; ++j, ++ci) relay(ci % TW_STAGES); }
+          for (int b0 = bb0; b0 < slim; b0 += g.Gb) {
+            const int T = tiles_for(b0, slim);
+            const int nh = half_split(T) < T ? 2 : 1;
+            for (int l = 0; l < L; ++l) { const int ns = nh * layer_info(l, g.blocks, CG).n_stages; for (int j = 0; j < ns; ++j, ++ci) relay(ci % TW_CONV_SLOTS); }
+          }
           uint32_t fi = 0;
           for (int h = 0; h < 2; ++h)
             for (int p = 0; p < fc.n_panels; ++p)
@@ -244,14 +283,22 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         }
       }
     } else {
-      uint32_t ci = 0, fphase = 0, act_phase = 0;
+      uint32_t ci = 0, fphase = 0, act_phase[2] = {0, 0};
+      long long stall_w = 0, stall_a = 0, t_start = clock64();     // developer stamps: cycles the issuer waited for weights / activations
       auto wait_stage = [&](uint32_t slot) {
         const uint32_t parity = (fphase >> slot) & 1u;
         fphase ^= 1u << slot;
+        const long long t0 = a.dbg ? clock64() : 0;
         mbar_wait(full_bar(slot), parity);
         if (CG == 2) mbar_wait_cluster(peer_full_bar(slot), parity);
+        if (a.dbg) stall_w += clock64() - t0;
       };
-      auto wait_act = [&](uint32_t parity) { if (CG == 2) mbar_wait_cluster(act_ready, parity); else mbar_wait(act_ready, parity); };
+      auto wait_act = [&](int h) {
+        const long long t0 = a.dbg ? clock64() : 0;
+        if (CG == 2) mbar_wait_cluster(act_ready(h), act_phase[h]); else mbar_wait(act_ready(h), act_phase[h]);
+        act_phase[h] ^= 1;
+        if (a.dbg) stall_a += clock64() - t0;
+      };
       auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
         if (CG == 2) tc_mma_bf16_2(d, ad, bd, idesc, acc); else tc_mma_bf16(d, ad, bd, idesc, acc);
       };
@@ -268,27 +315,30 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           const int slim = batch_end(bb0);
           for (int b0 = bb0; b0 < slim; b0 += g.Gb) {
             const int T = tiles_for(b0, slim);
+            const int T0 = half_split(T), nh = T0 < T ? 2 : 1;
             for (int l = 0; l < L; ++l) {
               const LayerInfo li = layer_info(l, g.blocks, CG);
               const bool preloaded = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 0);  // conv2: accumulator holds the skip input
               const uint32_t idesc = idesc_bf16(128 * CG, li.N);
               const uint32_t nrows_b = (uint32_t)li.N / CG;                          // weight rows staged per CTA
               const uint64_t k16_delta_b = (uint64_t)((2u * nrows_b * 16u) >> 4);
-              wait_act(act_phase); act_phase ^= 1;
+             for (int hh = 0; hh < nh; ++hh) {
+              const int tlo = hh ? T0 : 0, thi = hh ? T : T0;
+              wait_act(hh);
               tc_fence_after();
               for (int j = 0; j < li.n_stages; ++j, ++ci) {
-                const uint32_t slot = ci % TW_STAGES;
+                const uint32_t slot = ci % TW_CONV_SLOTS;
                 int tapshift, chunk0;
                 stage_info(l, j, g.blocks, g.pitch, g.dy_rows, CG, tapshift, chunk0);
                 wait_stage(slot);
                 tc_fence_after();
                 const uint64_t ad0 = smem_desc(act_base + (uint32_t)((chunk0 * TW_ROWS + TW_PAD + tapshift) * 16), TW_ROWS * 16, (uint32_t)g.sbo_bytes);
-                const uint64_t bd0 = smem_desc(slot_addr(slot), nrows_b * 16, 128);
+                const uint64_t bd0 = smem_desc(conv_slot_addr(slot), nrows_b * 16, 128);
                 const uint32_t acc0 = (preloaded || j > 0) ? 1u : 0u;
                 if (elect_one()) {
 #pragma unroll
                   for (int t = 0; t < TW_MAXT; ++t) {
-                    if (t < T) {
+                    if (t >= tlo && t < thi) {
 #pragma unroll
                       for (int k = 0; k < 4 * CG; ++k) {
                         if (k < li.nk16)
@@ -301,8 +351,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                 }
                 __syncwarp();
               }
-              if (elect_one()) commit(acc_full);
+              if (elect_one()) commit(acc_full(hh));
               __syncwarp();
+             }
             }
           }
           // ---- FC heads: D[o][board] (+)= Wfc[o][k] * feat[board][k]; A = weight stage in the ring, B = feature panel
@@ -312,7 +363,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           for (int h = 0; h < 2; ++h)
             for (int p = 0; p < fc.n_panels; ++p) {
               const int ns = panel_stages(p);
-              wait_act(act_phase); act_phase ^= 1;
+              wait_act(0);
               tc_fence_after();
               for (int t = 0; t < fc_tiles(h); ++t) {
                 const uint32_t R = (uint32_t)fc_rows(h, t);
@@ -337,11 +388,12 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                   __syncwarp();
                 }
               }
-              if (elect_one()) commit(acc_full);
+              if (elect_one()) commit(acc_full(0));
               __syncwarp();
             }
         }
       }
+      if (a.dbg && lane == 0 && blockIdx.x == 0) { a.dbg[920] = stall_w; a.dbg[921] = stall_a; a.dbg[922] = clock64() - t_start; }
     }
   } else if (warp >= 2 + TW_EPI_WARPS) {
     // =========================================================== background selection warps: while the tower runs, they
@@ -373,7 +425,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     const int quarter = warp & 3;        // TMEM lanes a warp may touch: 32*(warp_id % 4) ..
     const int tile0 = ew >> 2;           // with 16 warps every tile of the group has its own 4 warps
     constexpr int kTileStride = TW_EPI_WARPS / 4;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase[2] = {0, 0};
     uint8_t* act = smem + SM_ACT;
     float* sc_logit = reinterpret_cast<float*>(act);                 // [FC_N][256] heads scratch (act region is free then)
     float* sc_hidden = reinterpret_cast<float*>(act) + FC_N * 256;   // [FC_N][256] relu(fc1) * w2
@@ -382,17 +434,18 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     long long ph_t = clock64(), ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sub_t = 0;
     auto phase = [&](int k) { if (a.dbg) { const long long now = clock64(); ph_acc[k] += now - ph_t; ph_t = now; sub_t = now; } };
     auto sub = [&](int k) { if (a.dbg) { const long long now = clock64(); ph_acc[k] += now - sub_t; sub_t = now; } };
-    const uint32_t act_ready_leader = CG == 2 ? mapa_u32(act_ready, 0) : act_ready;
+    const uint32_t act_ready_leader[2] = {CG == 2 ? mapa_u32(act_ready(0), 0) : act_ready(0), CG == 2 ? mapa_u32(act_ready(1), 0) : act_ready(1)};
+    const int sub4 = ew >> 2;            // which of the 4 warps that share my TMEM lane quarter
     // Accumulators complete: ONE warp polls the mbarrier, the other 15 block on the hardware named barrier.  (With all
     // 16 warps spinning on try_wait for the 80 % of a layer that the MMAs take, the poll loop was 70 % of all executed
     // instructions of the kernel; measured effect on the step time: within noise, -0.5 % cycles.)
-    auto wait_acc = [&]() {
-      if (ew == 0) mbar_wait(acc_full, acc_phase);
-      acc_phase ^= 1;
+    auto wait_acc = [&](int h = 0) {
+      if (ew == 0) mbar_wait(acc_full(h), acc_phase[h]);
+      acc_phase[h] ^= 1;
       epi_sync();
       tc_fence_after();
     };
-    auto arrive_act = [&]() { if (CG == 2) mbar_arrive_cluster(act_ready_leader); else mbar_arrive(act_ready); };
+    auto arrive_act = [&](int h = 0) { if (CG == 2) mbar_arrive_cluster(act_ready_leader[h]); else mbar_arrive(act_ready(h)); };
     // entry i of this step's walk -> board (search / self-play: the i-th game of my run that has a pending leaf)
     int32_t* my_list = dyn ? e.act_list + run_lo : nullptr;
     auto board_of = [&](int i) -> long long { return dyn ? (long long)my_list[i] : run_lo + i; };
@@ -448,36 +501,50 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         if (a.use_nn) {
           for (int b0 = bb0; b0 < slim; b0 += g.Gb) {
             const int T = tiles_for(b0, slim);
-            // ---- stem input planes (board_to_input, neural_network.py:156-196) for my rows ----
-            for (int t = tile0; t < T; t += kTileStride) {
-              const int mi = t * 128 + quarter * 32 + lane;
-              const int p = pos_p[mi];
-              const int info = pos_tab[mi];
-              uint4 c0 = make_uint4(0, 0, 0, 0);
-              const int entry = b0 + (info >= 0 ? (info >> 8) : 0);
-              if (info >= 0 && entry < lim) {
-                const long long board = board_of(entry);
-                const int cell = info & 255, y = cell / g.m, x = cell % g.m;
-                const uint64_t* bb = a.black + board * g.W; const uint64_t* wb = a.white + board * g.W;
-                auto bit = [&](const uint64_t* v, int c) { return (int)((v[c >> 6] >> (c & 63)) & 1ull); };
-                const int isb = bit(bb, cell), isw = bit(wb, cell);
-                int rc = 0, cc = 0;
-                for (int xx = 0; xx < g.m; ++xx) { int c = y * g.m + xx; rc += bit(bb, c) | bit(wb, c); }
-                for (int yy = 0; yy < g.n; ++yy) { int c = yy * g.m + x; cc += bit(bb, c) | bit(wb, c); }
-                const float rf = (float)((double)rc / (double)g.m), cf = (float)((double)cc / (double)g.n);
-                const float rf_hi = __bfloat162float(__float2bfloat16_rn(rf)), cf_hi = __bfloat162float(__float2bfloat16_rn(cf));
-                // channels: 0 empty, 1 black, 2 white, 3 row fill, 4 col fill, 5/6 = bf16 residuals of 3/4 (same weights)
-                c0.x = pack_bf16x2((isb | isw) ? 0.0f : 1.0f, isb ? 1.0f : 0.0f);
-                c0.y = pack_bf16x2(isw ? 1.0f : 0.0f, rf_hi);
-                c0.z = pack_bf16x2(cf_hi, rf - rf_hi);
-                c0.w = pack_bf16x2(cf - cf_hi, 0.0f);
+            const int T0 = half_split(T), nh = T0 < T ? 2 : 1;
+            // The 4 warps that share a TMEM lane quarter split a half's tiles and, when the half has fewer than 4 tiles, the
+            // 16-column chunks of a tile: with two tiles per half every (tile, quarter) has two warps, 4 chunks each.
+            auto my_share = [&](int hh, int& t, int& c_lo, int& n_c) {
+              const int tlo = hh ? T0 : 0, nt = (hh ? T : T0) - tlo;
+              const int wpt = nt == 1 ? 4 : (nt == 2 ? 2 : 1);              // warps per (tile, quarter)
+              t = tlo + sub4 / wpt;
+              n_c = (TW_C / 16) / wpt;
+              c_lo = (sub4 % wpt) * n_c;
+              return t < tlo + nt;
+            };
+            // ---- stem input planes (board_to_input, neural_network.py:156-196) for my rows, half by half ----
+            for (int hh = 0; hh < nh; ++hh) {
+              int t, c_lo, n_c;
+              if (my_share(hh, t, c_lo, n_c) && c_lo == 0) {
+                const int mi = t * 128 + quarter * 32 + lane;
+                const int p = pos_p[mi];
+                const int info = pos_tab[mi];
+                uint4 c0 = make_uint4(0, 0, 0, 0);
+                const int entry = b0 + (info >= 0 ? (info >> 8) : 0);
+                if (info >= 0 && entry < lim) {
+                  const long long board = board_of(entry);
+                  const int cell = info & 255, y = cell / g.m, x = cell % g.m;
+                  const uint64_t* bb = a.black + board * g.W; const uint64_t* wb = a.white + board * g.W;
+                  auto bit = [&](const uint64_t* v, int c) { return (int)((v[c >> 6] >> (c & 63)) & 1ull); };
+                  const int isb = bit(bb, cell), isw = bit(wb, cell);
+                  int rc = 0, cc = 0;
+                  for (int xx = 0; xx < g.m; ++xx) { int c = y * g.m + xx; rc += bit(bb, c) | bit(wb, c); }
+                  for (int yy = 0; yy < g.n; ++yy) { int c = yy * g.m + x; cc += bit(bb, c) | bit(wb, c); }
+                  const float rf = (float)((double)rc / (double)g.m), cf = (float)((double)cc / (double)g.n);
+                  const float rf_hi = __bfloat162float(__float2bfloat16_rn(rf)), cf_hi = __bfloat162float(__float2bfloat16_rn(cf));
+                  // channels: 0 empty, 1 black, 2 white, 3 row fill, 4 col fill, 5/6 = bf16 residuals of 3/4 (same weights)
+                  c0.x = pack_bf16x2((isb | isw) ? 0.0f : 1.0f, isb ? 1.0f : 0.0f);
+                  c0.y = pack_bf16x2(isw ? 1.0f : 0.0f, rf_hi);
+                  c0.z = pack_bf16x2(cf_hi, rf - rf_hi);
+                  c0.w = pack_bf16x2(cf - cf_hi, 0.0f);
+                }
+                *reinterpret_cast<uint4*>(act + (size_t)(0 * TW_ROWS + TW_PAD + p) * 16) = c0;
+                *reinterpret_cast<uint4*>(act + (size_t)(1 * TW_ROWS + TW_PAD + p) * 16) = make_uint4(0, 0, 0, 0);
               }
-              *reinterpret_cast<uint4*>(act + (size_t)(0 * TW_ROWS + TW_PAD + p) * 16) = c0;
-              *reinterpret_cast<uint4*>(act + (size_t)(1 * TW_ROWS + TW_PAD + p) * 16) = make_uint4(0, 0, 0, 0);
+              tc_fence_before();
+              fence_proxy_async_smem();
+              arrive_act(hh);
             }
-            tc_fence_before();
-            fence_proxy_async_smem();
-            arrive_act();
             if (etid < TW_C) bias_s[etid] = __ldg(a.conv_bias + etid);     // stem biases (buffer 0)
 
             for (int l = 0; l < L; ++l) {
@@ -486,8 +553,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
               // this layer's biases were staged in shared memory while its MMAs ran (an LDG per chunk sat on the
               // epilogue's critical path: 40 % of its stall samples); double buffered by layer parity
               const float* bias = bias_s + (l & 1) * TW_C;
-              wait_acc();
-              for (int t = tile0; t < T; t += kTileStride) {
+             for (int hh = 0; hh < nh; ++hh) {
+              wait_acc(hh);
+              int t, c_lo, n_c;
+              if (my_share(hh, t, c_lo, n_c)) {
                 const int mi = t * 128 + quarter * 32 + lane;
                 const int p = pos_p[mi];
                 const int info = pos_tab[mi];
@@ -525,23 +594,25 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                     *d0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                     *d1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
                   };
-                  // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+                  // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed (n_c is even)
                   uint32_t ra[16], rb[16];
-                  tc_ld16(taddr, ra);
+                  const int c_hi = c_lo + n_c;
+                  tc_ld16(taddr + c_lo * 16, ra);
 #pragma unroll 1
-                  for (int cc = 0; cc < TW_C / 16; cc += 2) {
+                  for (int cc = c_lo; cc < c_hi; cc += 2) {
                     tc_wait_ld();
                     tc_ld16(taddr + (cc + 1) * 16, rb);
                     process(ra, cc);
                     tc_wait_ld();
-                    if (cc + 2 < TW_C / 16) tc_ld16(taddr + (cc + 2) * 16, ra);
+                    if (cc + 2 < c_hi) tc_ld16(taddr + (cc + 2) * 16, ra);
                     process(rb, cc + 1);
                   }
                   if (is_conv1) tc_wait_st();
                 } else {
                   __nv_bfloat16* dst = a.headfeat + (size_t)(run_lo + entry) * (TW_HEADC * g.A) + (info & 255);   // by walk entry
+                  const int h_n = n_c >= 2 ? n_c / 2 : 1, h_lo = n_c >= 2 ? c_lo / 2 : c_lo;   // 4 chunks of 16 head channels over the same warps
 #pragma unroll 1
-                  for (int cc = 0; cc < TW_HEADC / 16; ++cc) {
+                  for (int cc = h_lo; cc < h_lo + h_n && cc < TW_HEADC / 16; ++cc) {
                     uint32_t r[16];
                     tc_ld16(taddr + cc * 16, r);
                     tc_wait_ld();
@@ -556,9 +627,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
               tc_fence_before();
               if (!is_head) {
                 fence_proxy_async_smem();
-                arrive_act();
-                if (etid < TW_C) bias_s[((l + 1) & 1) * TW_C + etid] = __ldg(a.conv_bias + (size_t)(l + 1) * TW_C + etid);
+                arrive_act(hh);
               }
+             }
+              if (!is_head && etid < TW_C) bias_s[((l + 1) & 1) * TW_C + etid] = __ldg(a.conv_bias + (size_t)(l + 1) * TW_C + etid);
             }
           }
 
@@ -726,6 +798,7 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
   fa.policy = policy; fa.value = value; fa.logits = logits;
   fa.iterations = iterations; fa.mode = mode; fa.use_nn = use_nn ? 1 : 0;
   fa.dbg = nn.dbg;
+  fa.split_halves = nn.dbg_flags & 1;
   fa.batch_boards = fused_batch_boards(fa.g);
   // equal contiguous runs of boards per CTA (a search keeps its games on the same SM from the first to the last simulation)
   int sms = nn.num_sms > 0 ? nn.num_sms : 148;

@@ -20,6 +20,7 @@ struct NNState {
   int ev_cap, ev_used;
   long long tower_launches; double tower_ms; long long tower_boards;
   long long* dbg;            // device buffer for per-layer clock stamps (developer tool), usually nullptr
+  int dbg_flags;             // developer A/B switches (yy_engine_set_debug_stamps): bit 0 = ping-pong of group halves
 };
 
 int64_t nn_weight_bytes(int rows, int cols, int channels, int blocks);

@@ -29,6 +29,8 @@ constexpr int TW_PAD = 24;             // zero rows before/after the group's pos
 constexpr int TW_ROWS = 680;            // activation rows: flat 512+2*24, row-aligned 24+64*9+10, half-board 24+2*289+18, interleaved 24+4*162+8
 constexpr int TW_STAGES = 3;
 constexpr int TW_STAGE_BYTES = 16384;
+constexpr int TW_CONV_SLOTS = TW_STAGES;   // the tower's view of the weight ring: whole-tap stages, a CTA's half = 16 KB (measured: 8 KB
+constexpr int TW_CONV_SLOT_BYTES = TW_STAGE_BYTES;   // half-tap stages in 6 slots stream SLOWER -- a bulk copy costs ~900 cycles whatever its size)
 constexpr int TW_EPI_WARPS = 16;           // one (tile, TMEM-lane-quarter) pair per warp
 constexpr int TW_BG_WARPS = 2;             // background selection warps (games whose simulations end without an evaluation)
 constexpr int TW_THREADS = 64 + 32 * TW_EPI_WARPS + 32 * TW_BG_WARPS;
@@ -39,8 +41,9 @@ constexpr int SM_RING = SM_ACT + TW_CHUNKS * TW_ROWS * 16;            // 157696
 constexpr int SM_POS = SM_RING + TW_STAGES * TW_STAGE_BYTES;          // position tables: padded position + (board, cell)
 constexpr int SM_BAR = SM_POS + 2 * 128 * TW_MAXT * 2;
 constexpr int TW_FC_SLOTS = 5;          // weight slots during the FC heads: the ring + 2 in the free tail of the activation region
+constexpr int TW_NBAR = 6;              // barrier sets (full, empty, peer-full): max(TW_CONV_SLOTS, TW_FC_SLOTS)
 constexpr int TW_FC_EXTRA_OFF = 136 * 1024;   // (the FC feature panel ends at 135,168 B)
-constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_FC_SLOTS + 2);   // full, empty, peer-full per slot + acc_full, act_ready
+constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_NBAR + 4);   // full, empty, peer-full per slot + (acc_full, act_ready) per half of a group
 constexpr int SM_BIAS = (SM_TMEM + 16 + 15) & ~15;                                 // current / next layer's 128 fp32 biases (double buffer)
 constexpr int SM_CNT = SM_BIAS + 2 * TW_C * 4;            // counts of the CTA (pair): [step parity][cluster rank][pending leaves, selecting]
 constexpr int SM_TOTAL = SM_CNT + 48;                    // 8 counts + the background warps' stop flag

@@ -406,6 +406,11 @@ int yy_engine_set_debug_stamps(yy_engine* e, long long* dbg_dev) {
   e->nn.dbg = dbg_dev;
   return YY_OK;
 }
+int yy_engine_set_debug_flags(yy_engine* e, int flags) {
+  if (!e) return set_error(YY_ERR_INVALID, "null engine");
+  e->nn.dbg_flags = flags;
+  return YY_OK;
+}
 int yy_engine_get_profile(yy_engine* e, int64_t* tower_launches, double* tower_ms, int64_t* tower_boards) {
   if (!e) return set_error(YY_ERR_INVALID, "null engine");
   long long l = 0, b = 0; double ms = 0.0;
