@@ -332,10 +332,14 @@ def run_b200(args):
 
     # ---- the other BASELINE.json configurations (rank 0; 2 steps each), a strong-scaled configs[3] line, a tree-only leg
     other = {}
-    if rank == 0 and not args.quick:
-        other["configs[0] 6x6/100 sims"] = bench_config(engine, network, torch, peaks, 6, 100, 4096, steps=3, iters=8 * 101)
-        other["configs[4] 16x16/1600 sims (per-GPU share of 32,768 games)"] = bench_config(engine, network, torch, peaks, 16, 1600, 4096, steps=2, iters=801)
-        other["tree only (stub evaluator) 8x8/800"] = bench_tree_only(engine, torch, peaks)
+    if not args.quick:
+        # configs[4] on ALL ranks (16x16, 1,600 sims, 4,096 games per GPU: at 8 GPUs the 32,768 games of the config)
+        c4 = bench_config(engine, network, torch, peaks, 16, 1600, 4096, steps=2, iters=801, dist=dist if world > 1 else None, world=world,
+                          barrier=barrier, seed=7 + rank)
+        if rank == 0:
+            other[f"configs[4] 16x16/1600 sims, 4,096 games per GPU x {world} GPU(s)"] = c4
+            other["configs[0] 6x6/100 sims"] = bench_config(engine, network, torch, peaks, 6, 100, 4096, steps=3, iters=8 * 101)
+            other["tree only (stub evaluator) 8x8/800"] = bench_tree_only(engine, torch, peaks)
     strong = None
     if world > 1 and not args.quick:
         strong = bench_strong(engine, torch, dist, world, rank, sd, peaks, barrier)
@@ -384,17 +388,17 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def bench_config(engine, network, torch, peaks, n, sims, games, steps, iters):
-    """Rolling self-play on another BASELINE.json geometry, one GPU: moves/s and the roofline of required evaluations."""
+def bench_config(engine, network, torch, peaks, n, sims, games, steps, iters, dist=None, world=1, barrier=None, seed=7):
+    """Rolling self-play on another BASELINE.json geometry: moves/s (all ranks) and the roofline of required evaluations (this rank)."""
     torch.manual_seed(0)
     sd = network._Params(n, n, CHANNELS, BLOCKS).state_dict()
-    eng = engine.Engine(rows=n, cols=n, n_games=games, n_sims=sims, evaluator="nn", state_dict=sd, seed=7,
+    eng = engine.Engine(rows=n, cols=n, n_games=games, n_sims=sims, evaluator="nn", state_dict=sd, seed=seed,
                         replay_capacity=games * 64)
-    ms, moves, evals, prof, st = timed_rolling(eng, torch, None, 1, iters, 1, steps, torch.cuda.synchronize)
+    ms, moves, evals, prof, st = timed_rolling(eng, torch, dist, world, iters, 1, steps, barrier or torch.cuda.synchronize)
     fl = flops_per_leaf(n, n)
-    out = {"board": f"{n}x{n}", "sims_per_move": sims, "games": games, "value": moves / (ms * 1e-3), "unit": "moves/s", "steps": steps,
-           "evaluation_steps_per_launch": iters, "ms_per_step": ms / steps, "evals_per_move": evals / max(1, moves),
-           "roofline": tensor_roofline(peaks, evals, prof, ms, fl), "moves_per_s_roofline_at_sims_plus_1": peaks["bf16_tflops_sustained"] * 1e12 / ((sims + 1) * fl),
+    out = {"board": f"{n}x{n}", "sims_per_move": sims, "games": games * world, "n_gpus": world, "value": moves / (ms * 1e-3), "unit": "moves/s", "steps": steps,
+           "evaluation_steps_per_launch": iters, "ms_per_step": ms / steps, "evals_per_move": evals * world / max(1, moves),
+           "roofline": tensor_roofline(peaks, evals, prof, ms, fl), "moves_per_s_roofline_at_sims_plus_1": world * peaks["bf16_tflops_sustained"] * 1e12 / ((sims + 1) * fl),
            "arena_gb": eng.workspace_bytes / 1e9, "overflow": st.overflow}
     eng.close(); del eng
     torch.cuda.empty_cache()
