@@ -536,11 +536,12 @@ def bench_env(engine, torch, peaks):
                     "h2d_bytes_per_step": 21, "d2h_bytes_per_step": 34,
                     "int8_arrays": {"value": e2e, "unit": "steps/s", "api": "env_step_host (the reference's int8[n,m] board arrays in/out; bit packing on the device)"}},
             "roofline": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": gbs / peaks["hbm_gbs"], "traffic": 1.403e6,
-                         "note": "3.4 MB of algorithmic traffic per launch: latency bound at this batch size (two lanes per board, "
-                                 "28 warps per SM, one flood fill per lane); integer-issue bound when the machine is full; traffic = "
-                                 "DRAM bytes of one launch (the boards are read once, the outputs are still in L2 when it ends; "
-                                 "profiles/r01_env_step_v3_ncu_summary.txt)"},
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": 1.384e6,
+                         "note": "3.4 MB of algorithmic traffic per launch; a launch of ONE block costs 2.0-2.2 us (launch + cold-DRAM "
+                                 "latency, tools/env_floor.py), the rest is integer issue (two lanes per board, line-fill connectivity, "
+                                 "437 warp instructions per 16 boards); integer-issue bound when the machine is full; traffic = DRAM "
+                                 "bytes of one launch (the boards are read once, the outputs are still in L2 when it ends; "
+                                 "profiles/r02_env_step_sq_ncu_summary.txt)"},
             "saturated": {"boards": big, "value": big / big_s, "unit": "steps/s", "us_per_launch": big_s * 1e6,
                           "achieved_GBps": ENV_BYTES_PER_STEP * big / big_s / 1e9},
             "l2_policy": "L2 flushed (256 MB write) before each timed group of 8 launches on fresh boards"}

@@ -39,3 +39,37 @@ extern "C" int yyh_rules(int rows, int cols, unsigned flags, const uint64_t* bla
   else return -1;
   return 0;
 }
+
+// The line-fill rules for square one-word boards (yy_rules_sq.cuh), same outputs as yyh_rules (no stub evaluator).
+#include "../../yinyang-game-alphazero_b200/csrc/yy_rules_sq.cuh"
+template <int SIDE>
+static void run_sq(const uint64_t* black, const uint64_t* white, const int8_t* players, const int32_t* actions, long count,
+                   uint64_t* mask_out, uint64_t* nb_out, uint64_t* nw_out, int8_t* np_out, int8_t* ended_out) {
+  typedef Sq<SIDE> Q;
+  for (long i = 0; i < count; ++i) {
+    uint64_t b = black[i] & Q::FULL, w = white[i] & Q::FULL;
+    const bool mb = players[i] == 1;
+    const uint64_t p = mb ? b : w, o = mb ? w : b;
+    const uint64_t lm = Q::legal(p, o);
+    mask_out[i] = lm;
+    int code = 0;
+    if (!lm && !Q::legal(o, p)) { int mc = popc64(p), oc = popc64(o); code = mc > oc ? 1 : (oc > mc ? -1 : 2); }
+    ended_out[i] = (int8_t)code;
+    const int a = actions[i];
+    if (a >= 0 && a < Q::CELLS && ((lm >> a) & 1)) { if (mb) b |= 1ull << a; else w |= 1ull << a; }
+    nb_out[i] = b; nw_out[i] = w; np_out[i] = (int8_t)-players[i];
+  }
+}
+extern "C" int yyh_rules_sq(int side, const uint64_t* black, const uint64_t* white, const int8_t* players,
+                            const int32_t* actions, long count, uint64_t* mask_out, uint64_t* nb_out, uint64_t* nw_out,
+                            int8_t* np_out, int8_t* ended_out) {
+  switch (side) {
+    case 3: run_sq<3>(black, white, players, actions, count, mask_out, nb_out, nw_out, np_out, ended_out); return 0;
+    case 4: run_sq<4>(black, white, players, actions, count, mask_out, nb_out, nw_out, np_out, ended_out); return 0;
+    case 5: run_sq<5>(black, white, players, actions, count, mask_out, nb_out, nw_out, np_out, ended_out); return 0;
+    case 6: run_sq<6>(black, white, players, actions, count, mask_out, nb_out, nw_out, np_out, ended_out); return 0;
+    case 7: run_sq<7>(black, white, players, actions, count, mask_out, nb_out, nw_out, np_out, ended_out); return 0;
+    case 8: run_sq<8>(black, white, players, actions, count, mask_out, nb_out, nw_out, np_out, ended_out); return 0;
+  }
+  return -1;
+}

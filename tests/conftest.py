@@ -54,8 +54,8 @@ def host_rules_lib():
     d = os.path.join(ROOT, "tests", "_host")
     so = os.path.join(d, "librules_host.so")
     src = os.path.join(d, "rules_host_shim.cpp")
-    hdr = os.path.join(ROOT, "yinyang-game-alphazero_b200", "csrc", "yy_rules.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "yinyang-game-alphazero_b200", "csrc", h) for h in ("yy_rules.cuh", "yy_rules_sq.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src, *hdrs]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src], check=True)
     return ctypes.CDLL(so)
 

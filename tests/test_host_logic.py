@@ -25,6 +25,19 @@ def _host_rules(lib, bbm, boards, players, actions, n, m, flags=0, stub=False):
     return bbm.unpack_bits(mask, n, m), bbm.unpack_boards(nb, nw, n, m), npl, ended, st
 
 
+def _host_rules_sq(lib, bbm, boards, players, actions, n):
+    """The line-fill rules of yy_rules_sq.cuh (square one-word boards) through the same host shim."""
+    bl, wh = bbm.pack_boards(boards, n, n)
+    N = bl.shape[0]
+    players = np.ascontiguousarray(players, np.int8)
+    actions = np.ascontiguousarray(actions, np.int32)
+    mask, nb, nw = (np.zeros((N, 1), np.uint64) for _ in range(3))
+    npl, ended = np.zeros(N, np.int8), np.zeros(N, np.int8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    assert lib.yyh_rules_sq(n, p(bl), p(wh), p(players), p(actions), ctypes.c_long(N), p(mask), p(nb), p(nw), p(npl), p(ended)) == 0
+    return bbm.unpack_bits(mask, n, n), bbm.unpack_boards(nb, nw, n, n), npl, ended
+
+
 def _code(e):
     return np.where(e == 0.0001, 2, e).astype(np.int8)
 
@@ -50,6 +63,39 @@ def test_bitboard_rules_match_reference(yy, host_rules_lib, name):
         assert np.array_equal(mask, g[mk]) and np.array_equal(ended, _code(g[ek]))
     _, nb, npl, _, _ = _host_rules(host_rules_lib, yy.bitboard, B, g["players"], g["actions"], n, m)
     assert np.array_equal(nb, g["next_boards"]) and np.array_equal(npl, g["next_players"])
+
+
+@pytest.mark.parametrize("name", ["rules_4x4.npz", "rules_6x6.npz", "rules_8x8.npz"])
+def test_line_fill_rules_match_reference(yy, host_rules_lib, name):
+    """yy_rules_sq.cuh (line fills by carry propagation / Kogge-Stone, pair-based 2x2 test) against the goldens of the
+    unmodified reference: masks and terminal values for both colours, next states."""
+    g = load_golden(name)
+    n, B = int(g["n"]), g["boards"]
+    N = len(B)
+    for pl, mk, ek in ((1, "mask_black", "ended_black"), (-1, "mask_white", "ended_white")):
+        mask, _, _, ended = _host_rules_sq(host_rules_lib, yy.bitboard, B, np.full(N, pl, np.int8), g["actions"], n)
+        assert np.array_equal(mask, g[mk]) and np.array_equal(ended, _code(g[ek]))
+    _, nb, npl, _ = _host_rules_sq(host_rules_lib, yy.bitboard, B, g["players"], g["actions"], n)
+    assert np.array_equal(nb, g["next_boards"]) and np.array_equal(npl, g["next_players"])
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 6, 7, 8])
+def test_line_fill_rules_match_step_fill_rules(yy, host_rules_lib, n):
+    """Every square one-word side: the line-fill rules equal the one-cell-dilation rules of yy_rules.cuh (themselves checked
+    against the oracle below) on arbitrary fills -- many components, holes, existing 2x2 blocks, full boards."""
+    rng = np.random.default_rng(900 + n)
+    N = 20000
+    fill = rng.uniform(0, 1, size=(N, 1, 1))
+    r = rng.random((N, n, n))
+    B = np.where(r < fill / 2, 1, np.where(r < fill, -1, 0)).astype(np.int8)
+    snake = rng.random((N // 4, n, n)) < 0.55                                  # one colour only: long thin components
+    B[: N // 4] = snake.astype(np.int8)
+    pl = rng.choice([1, -1], size=N).astype(np.int8)
+    ac = rng.integers(-1, n * n + 1, size=N).astype(np.int32)
+    a = _host_rules(host_rules_lib, yy.bitboard, B, pl, ac, n, n)[:4]
+    b = _host_rules_sq(host_rules_lib, yy.bitboard, B, pl, ac, n)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
 
 
 @pytest.mark.parametrize("shape", [(3, 3), (6, 6), (8, 8), (7, 9), (10, 10), (16, 16), (8, 32), (32, 8), (1, 5)])

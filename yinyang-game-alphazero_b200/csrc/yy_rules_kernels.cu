@@ -6,6 +6,7 @@
 // ~2,600 dependent integer instructions per warp (flood fills), so at 65,536 boards (14 warps per SM) they are
 // latency bound -- 15 us, of which the SMs are busy 10 -- and at 1 M boards integer-issue bound (10.8 G steps/s).
 #include "yy_common.cuh"
+#include "yy_rules_sq.cuh"
 
 namespace yy {
 
@@ -51,6 +52,48 @@ ended_kernel(Geo<NW> g, int W, const uint64_t* __restrict__ black, const uint64_
   if (i >= count) return;
   BB<NW> b = load_bb<NW>(black, i, W) & g.full, w = load_bb<NW>(white, i, W) & g.full;
   out[i] = (int8_t)ended_code(g, b, w, players[i] == 1 ? 1 : -1);
+}
+
+// One-word square boards without the row/column rule: the line-fill rules of yy_rules_sq.cuh, one thread per board.
+template <int SIDE> __device__ __forceinline__ int sq_ended_code(uint64_t mover, uint64_t other, uint64_t mover_mask) {
+  if (mover_mask || Sq<SIDE>::legal(other, mover)) return 0;
+  const int mc = popc64(mover), oc = popc64(other);
+  return mc > oc ? 1 : (oc > mc ? -1 : 2);
+}
+template <int SIDE>
+__global__ void __launch_bounds__(kRulesBlock)
+legal_mask_sq_kernel(const uint64_t* __restrict__ black, const uint64_t* __restrict__ white, const int8_t* __restrict__ players,
+                     uint64_t* __restrict__ out_mask, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint64_t b = black[i] & Sq<SIDE>::FULL, w = white[i] & Sq<SIDE>::FULL;
+  out_mask[i] = players[i] == 1 ? Sq<SIDE>::legal(b, w) : Sq<SIDE>::legal(w, b);
+}
+template <int SIDE>
+__global__ void __launch_bounds__(kRulesBlock)
+step_sq_kernel(uint64_t* __restrict__ black, uint64_t* __restrict__ white, int8_t* __restrict__ players,
+               const int32_t* __restrict__ actions, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint64_t b = black[i] & Sq<SIDE>::FULL, w = white[i] & Sq<SIDE>::FULL;
+  const int praw = players[i], a = actions[i];
+  if ((unsigned)a < (unsigned)Sq<SIDE>::CELLS) {
+    const uint64_t bit = 1ull << a;
+    const uint64_t lm = praw == 1 ? Sq<SIDE>::legal(b, w) : Sq<SIDE>::legal(w, b);
+    if (lm & bit) (praw == 1 ? black : white)[i] = (praw == 1 ? b : w) | bit;
+  }
+  players[i] = (int8_t)(-praw);  // yin_yang_game.py:58 returns -player whatever it was
+}
+template <int SIDE>
+__global__ void __launch_bounds__(kRulesBlock)
+ended_sq_kernel(const uint64_t* __restrict__ black, const uint64_t* __restrict__ white, const int8_t* __restrict__ players,
+                int8_t* __restrict__ out, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint64_t b = black[i] & Sq<SIDE>::FULL, w = white[i] & Sq<SIDE>::FULL;
+  const bool mover_black = players[i] == 1;
+  const uint64_t p = mover_black ? b : w, o = mover_black ? w : b;
+  out[i] = (int8_t)sq_ended_code<SIDE>(p, o, Sq<SIDE>::legal(p, o));
 }
 
 // Fused getValidMoves + getNextState + getGameEnded.
@@ -183,6 +226,68 @@ env_step_kernel(Geo<NW> g, int W, uint64_t* __restrict__ black, uint64_t* __rest
   }
 }
 
+// The same step for square one-word boards (6x6, 8x8) without the row/column rule: the rules of yy_rules_sq.cuh (line
+// fills, pair-based 2x2 test), two lanes per board, boards in input order.  Nothing is staged or sorted: a line fill
+// converges in 1..5 rounds whatever the number of stones, so the lanes of a warp finish close together without it.
+// What each lane does after its colour's analysis is as short as the rules allow: a legal placement cannot create a
+// 2x2 block, leaves the mover's stones ONE component (its dilation is the successor's "touches every component" set)
+// and only removes a cell from the other colour's mask.
+// The kernel is launched with programmatic stream serialisation: it lets the next launch in the stream start its blocks
+// at once (griddepcontrol.launch_dependents) and itself waits for the previous kernel's memory (griddepcontrol.wait)
+// before the first load, so back-to-back steps overlap launch latency with the previous step's execution.
+template <int SIDE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+env_step_sq_kernel(uint64_t* __restrict__ black, uint64_t* __restrict__ white, int8_t* __restrict__ players,
+                   const int32_t* __restrict__ actions, uint64_t* __restrict__ out_mask, int8_t* __restrict__ out_result,
+                   long long count) {
+  using Q = Sq<SIDE>;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const unsigned tid = threadIdx.x;
+  const unsigned side = tid & 1;              // 0: the mover's colour, 1: the other colour
+  const unsigned i = (blockIdx.x * (unsigned)BLOCK + tid) >> 1;   // the host keeps 2 * count below 2^32 per launch
+  const bool live = i < (unsigned)count;      // both lanes of a pair agree; nobody leaves before the shuffles
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  uint64_t b = 0, w = 0;
+  int praw = 1, a = -1;
+  if (live) { b = black[i] & Q::FULL; w = white[i] & Q::FULL; praw = players[i]; a = actions[i]; }
+  const bool mover_black = praw == 1;
+  const bool mine_black = mover_black == (side == 0);
+  uint64_t x = mine_black ? b : w;            // the colour this lane analyses
+  const uint64_t y = mine_black ? w : b;
+  bool has; uint64_t completes;
+  Q::blocks(x, has, completes);
+  const bool any_block = __shfl_xor_sync(0xffffffffu, (int)has, 1) | (int)has;
+  uint64_t empty = Q::FULL & ~(x | y);
+  uint64_t lm = any_block ? 0ull : (empty & ~completes);
+  if (lm) lm &= Q::touches_all(x, lm);
+  const bool valid_action = (unsigned)a < (unsigned)Q::CELLS;
+  const uint64_t abit = valid_action ? (1ull << (a & 63)) : 0ull;
+  int placed = side == 0 && (lm & abit) != 0;
+  placed = __shfl_sync(0xffffffffu, placed, (tid & 31) & ~1);
+  if (live && side == 0) out_mask[i] = lm;
+  if (placed) {                               // the pair takes this branch together
+    if (side == 0) {
+      x |= abit;
+      (mover_black ? black : white)[i] = x;
+      Q::blocks(x, has, completes);
+      lm = empty & ~abit & ~completes & Q::dilate4(x);
+    } else {
+      lm &= ~abit;
+    }
+  }
+  const int mine_any = lm != 0;
+  const int peer_any = __shfl_xor_sync(0xffffffffu, mine_any, 1);
+  if (live && side == 0) {
+    int code = 0;                             // getGameEnded(successor, -p)
+    if (!mine_any && !peer_any) {
+      const int mc = popc64(x), oc = popc64(y);   // mover's stones (after the move) / the other colour's
+      code = mc > oc ? -1 : (oc > mc ? 1 : 2);    // seen from the player to move next, i.e. the other colour
+    }
+    out_result[i] = (int8_t)code;
+    players[i] = (int8_t)(-praw);             // yin_yang_game.py:58 returns -player whatever it was
+  }
+}
+
 template <int NW>
 __global__ void __launch_bounds__(kRulesBlock)
 random_playout_kernel(Geo<NW> g, int W, uint64_t seed, const int32_t* __restrict__ plies, uint64_t* __restrict__ black,
@@ -231,6 +336,10 @@ __global__ void __launch_bounds__(256) unpack_boards_kernel(const uint64_t* __re
   if (out_mask) out_mask[idx] = (uint8_t)((mask[wi] >> bit) & 1ull);
 }
 
+// side of a square one-word board that the line-fill kernels cover (6 or 8, Python rules only), else 0
+static int sq_side(int rows, int cols, uint32_t rule_flags) {
+  return rows == cols && (rows == 6 || rows == 8) && !(rule_flags & YY_RULE_ROWCOL_BIT) ? rows : 0;
+}
 static int check_rules_args(int rows, int cols, long long count) {
   if (!board_supported(rows, cols)) return set_error(YY_ERR_INVALID, "unsupported board %dx%d (need <=32 per side, <=256 cells)", rows, cols);
   if (count < 0) return set_error(YY_ERR_INVALID, "negative count");
@@ -263,7 +372,10 @@ int yy_legal_mask(int rows, int cols, uint32_t rule_flags, const uint64_t* black
   if (count == 0) return YY_OK;
   int cells = rows * cols, W = words_for_cells(cells);
   unsigned grid = (unsigned)((count + kRulesBlock - 1) / kRulesBlock);
-  YY_DISPATCH_NW(cells, legal_mask_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
+  const int sq = sq_side(rows, cols, rule_flags);
+  if (sq == 8) legal_mask_sq_kernel<8><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(black, white, players, out_mask, count);
+  else if (sq == 6) legal_mask_sq_kernel<6><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(black, white, players, out_mask, count);
+  else YY_DISPATCH_NW(cells, legal_mask_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
       make_geo<NW>(rows, cols, rule_flags), W, black, white, players, out_mask, count));
   YY_LAUNCH_CHECK();
   return YY_OK;
@@ -275,7 +387,10 @@ int yy_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64_t* 
   if (count == 0) return YY_OK;
   int cells = rows * cols, W = words_for_cells(cells);
   unsigned grid = (unsigned)((count + kRulesBlock - 1) / kRulesBlock);
-  YY_DISPATCH_NW(cells, step_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
+  const int sq = sq_side(rows, cols, rule_flags);
+  if (sq == 8) step_sq_kernel<8><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(black, white, players, actions, count);
+  else if (sq == 6) step_sq_kernel<6><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(black, white, players, actions, count);
+  else YY_DISPATCH_NW(cells, step_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
       make_geo<NW>(rows, cols, rule_flags), W, black, white, players, actions, count));
   YY_LAUNCH_CHECK();
   return YY_OK;
@@ -287,7 +402,10 @@ int yy_ended(int rows, int cols, uint32_t rule_flags, const uint64_t* black, con
   if (count == 0) return YY_OK;
   int cells = rows * cols, W = words_for_cells(cells);
   unsigned grid = (unsigned)((count + kRulesBlock - 1) / kRulesBlock);
-  YY_DISPATCH_NW(cells, ended_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
+  const int sq = sq_side(rows, cols, rule_flags);
+  if (sq == 8) ended_sq_kernel<8><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(black, white, players, out_result, count);
+  else if (sq == 6) ended_sq_kernel<6><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(black, white, players, out_result, count);
+  else YY_DISPATCH_NW(cells, ended_kernel<NW><<<grid, kRulesBlock, 0, (cudaStream_t)stream>>>(
       make_geo<NW>(rows, cols, rule_flags), W, black, white, players, out_result, count));
   YY_LAUNCH_CHECK();
   return YY_OK;
@@ -307,7 +425,28 @@ int yy_env_step(int rows, int cols, uint32_t rule_flags, uint64_t* black, uint64
   env_step_kernel<NWV, kBlock, true, SIDEV><<<(unsigned)((count + kBlock / 2 - 1) / (kBlock / 2)), kBlock, 0, (cudaStream_t)stream>>>( \
       make_geo<NWV>(rows, cols, rule_flags), W, black, white, players, actions, out_mask, out_result, count)
   const int side = rows == cols ? rows : 0;
-  if (side == 8) YY_ENV_LAUNCH(1, 8);
+  if (sq_side(rows, cols, rule_flags)) {
+    constexpr int kSqBlock = 128;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kSqBlock);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const long long kChunk = 1ll << 30;        // boards per launch: the kernel indexes its lanes with 32 bits
+    for (long long off = 0; off < count; off += kChunk) {
+      const long long n = count - off < kChunk ? count - off : kChunk;
+      cfg.gridDim = dim3((unsigned)((2 * n + kSqBlock - 1) / kSqBlock));
+      uint64_t *bk = black + off, *wh = white + off, *om = out_mask + off;
+      int8_t *pl = players + off, *res = out_result + off;
+      const int32_t* ac = actions + off;
+      if (side == 8) YY_CUDA_OK(cudaLaunchKernelEx(&cfg, env_step_sq_kernel<8, kSqBlock>, bk, wh, pl, ac, om, res, n));
+      else YY_CUDA_OK(cudaLaunchKernelEx(&cfg, env_step_sq_kernel<6, kSqBlock>, bk, wh, pl, ac, om, res, n));
+      if (off) count_launch();
+    }
+  }
+  else if (side == 8) YY_ENV_LAUNCH(1, 8);
   else if (side == 6) YY_ENV_LAUNCH(1, 6);
   else if (side == 16) YY_ENV_LAUNCH(4, 16);
   else YY_DISPATCH_NW(cells, YY_ENV_LAUNCH(NW, 0));
