@@ -272,7 +272,21 @@ def run_b200(args):
     # example the step produced comes back device -> host (positions, visit counts, game ids, results), all inside the timed region.
     # The read-back of step k runs on a second stream while step k + 1 computes (a stream-ordered snapshot of the device counters
     # taken right after step k says which records are complete).
-    e2e_steps = max(1, min(args.steps, 10))
+    # A fresh engine with the same seed replays the same games, and the timed region covers the same steps as `value` (the rate
+    # depends on the ply: searches late in a game revisit terminal nodes and need fewer evaluations).
+    boards, players = eng.live_boards()
+    players_s = np.ones_like(players)
+    eng.search_host(boards, players_s)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        eng.search_host(boards, players_s)              # the host-buffer SEARCH API (MCTS.search for a batch): numpy boards in, visit counts out
+    search_api = 2 * GAMES_PER_GPU / (time.perf_counter() - t0)
+    eng.close(); del eng
+    torch.cuda.empty_cache()
+    eng = engine.Engine(rows=ROWS, cols=COLS, n_games=GAMES_PER_GPU, n_sims=SIMS, evaluator="nn", state_dict=sd,
+                        seed=0xC0FFEE + rank, replay_capacity=GAMES_PER_GPU * (2 * (args.steps + args.warmup) + 8))
+    e2e_steps = args.steps
     img_host = weights.pack_state_dict(sd, ROWS, COLS)
     pinned = torch.from_numpy(img_host).pin_memory()
     rec_bytes = 2 * 8 * eng.W + 2 * A + 4 + 2 + 1
@@ -298,7 +312,8 @@ def run_b200(args):
         state["records"] += len(rec["ply"])
         state["cursor"] = stop
 
-    launch(0); drain(0)                                             # untimed: staging buffers, caches
+    for k in range(args.warmup):                                    # untimed, like the device leg: the first W moves of the games
+        launch(k); drain(k)
     barrier()
     state.update(d2h=0, records=0)
     t0 = time.perf_counter()
@@ -318,15 +333,6 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         e2e_moves = int(t.item())
     e2e_value = e2e_moves / e2e_s
-    # the host-buffer SEARCH API (MCTS.search for a batch of positions), lock-step: numpy boards in, visit counts out
-    boards, players = eng.live_boards()
-    players_s = np.ones_like(players)
-    eng.search_host(boards, players_s)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(2):
-        eng.search_host(boards, players_s)
-    search_api = 2 * GAMES_PER_GPU / (time.perf_counter() - t0)
     eng.close(); del eng
     torch.cuda.empty_cache()
 
@@ -374,7 +380,8 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": int(img_host.nbytes), "d2h_bytes_per_step": int(d2h // e2e_steps),
                         "steps": e2e_steps, "moves": int(e2e_moves), "seconds": e2e_s,
                         "api": "Engine.selfplay_advance with host buffers: weight image H2D from pinned memory, every example of "
-                               "the step D2H (Engine.replay_window + results table) while the next step computes",
+                               "the step D2H (Engine.replay_window + results table) while the next step computes; same games and "
+                               "the same steps as `value` (fresh engine, same seed, same warm-up)",
                         "search_api": {"value": search_api, "unit": "moves/s", "api": "Engine.search_host (numpy boards in, visit counts out; lock-step batch of 4,096 searches)"}},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "env": env, "dataset": dataset, "learner": learner_leg, "ai_move": ai_move_leg,
                 "moves_per_s_roofline": peaks["bf16_tflops_sustained"] * 1e12 / ((SIMS + 1) * FLOPS_PER_LEAF) * world,
