@@ -1,0 +1,7 @@
+import sys, os, json
+sys.path.insert(0, "/root/repo")
+import torch
+import yy_b200  # noqa
+import bench
+from yinyang_game_alphazero_b200 import engine, network
+print(json.dumps(bench.bench_config(engine, network, torch, bench.measured_peaks(), 6, 100, 4096, steps=3, iters=8 * 101)))

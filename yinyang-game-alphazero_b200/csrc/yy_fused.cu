@@ -33,7 +33,7 @@ struct FusedArgs {
   const uint64_t* black; const uint64_t* white;   // [count][W] boards to evaluate (search: the leaf batch)
   long long count;
   int boards_per_cta;          // contiguous run of boards (= games in a search) owned by a CTA
-  int batch_boards;            // <= FC_N boards per heads pass; a multiple of g.Gb
+  int batch_boards;            // <= FC_N boards per heads pass (whole groups of g.Gb boards, except possibly the last group)
   __nv_bfloat16* headfeat;     // [count][64*A] head-conv features, index c*A + cell (L2-resident round trip)
   float* policy; float* value; float* logits;     // [count][A], [count], optional [count][A]
   int iterations;              // 1 = plain forward; n_sims + 1 = whole search; rolling self-play: any number of steps
@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     if (g.row_aligned == 3) {
       const int t = i >> 7, j = (i & 127) >> 3;
       x = i & 7; b = 2 * t + (j & 1); y = j >> 1; p = t * g.tile_adv + j * g.pitch + x;
+    } else if (g.row_aligned == 4) {
+      const int t = i >> 7, r = i & 127, j = r / g.pitch;
+      x = r % g.pitch; y = j / g.ilv; b = g.ilv * t + j % g.ilv; p = t * g.tile_adv + r;
     } else if (g.row_aligned == 2) {
       const int t = i >> 7, r = i & 127;
       b = t >> 1; y = r >> 3; x = 8 * (t & 1) + (r & 7); p = b * g.PB + y * g.pitch + x;
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   // (+pitch+1: the taps of the last real position read that far; rows beyond the group's tiles may be stale)
   auto tiles_for = [&](int b0, int lim) {
     int nb = lim - b0; if (nb > g.Gb) nb = g.Gb;
-    int t = g.row_aligned == 3 ? ((nb + 1) >> 1) : g.row_aligned == 2 ? (2 * nb)
+    int t = g.row_aligned == 4 ? ((nb + g.ilv - 1) / g.ilv) : g.row_aligned == 3 ? ((nb + 1) >> 1) : g.row_aligned == 2 ? (2 * nb)
           : g.row_aligned ? ((nb * g.rows_per_board + 15) >> 4) : ((nb * g.PB + g.pitch + 1 + 127) >> 7);
     return t < g.T ? t : g.T;
   };
@@ -743,6 +746,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
 
 // ------------------------------------------------------------------------------------------------ host side
 static int fused_batch_boards(const TowerGeo& g) {
+  if (g.row_aligned == 4) return FC_N;   // groups of 12 boards: a heads pass takes 12 + 12 + 8 (the last group of a batch may be partial)
   int per = (FC_N / g.Gb) * g.Gb;
   return per > 0 ? per : g.Gb;
 }
