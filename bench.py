@@ -715,20 +715,22 @@ def bench_learner(engine, torch, peaks):
     # the same step at batch 512 (8 x the positions per kernel): how far the kernels are from their roofline once they are
     # not microseconds long (the reference's batch size stays the headline)
     Bl = 512
-    Ll = lrn.Learner(ROWS, COLS, 128, 10, batch_size=Bl, state_dict=net.state_dict(), data_parallel=False)
-    for i in range(3):
-        Ll.step(planes[i * Bl:(i + 1) * Bl], pol[i * Bl:(i + 1) * Bl], val[i * Bl:(i + 1) * Bl])
-    torch.cuda.synchronize()
-    ev0.record()
-    for i in range(16):
-        j = (i % 4) * Bl
-        Ll.step(planes[j:j + Bl], pol[j:j + Bl], val[j:j + Bl])
-    ev1.record(); torch.cuda.synchronize()
-    sec_l = ev0.elapsed_time(ev1) * 1e-3 / 16
-    tf_l = 3 * Bl * FLOPS_PER_LEAF / sec_l / 1e12
-    out["3xtf32"]["batch_512"] = {"value": Bl / sec_l, "unit": "samples/s", "ms_per_step": sec_l * 1e3, "achieved_tflops": tf_l,
-                                  "frac_of_tf32_roofline": tf_l / (peaks["bf16_tflops_sustained"] / 2)}
-    del Ll
+    for precision in ("3xtf32", "tf32"):
+        Ll = lrn.Learner(ROWS, COLS, 128, 10, batch_size=Bl, state_dict=net.state_dict(), precision=precision, data_parallel=False)
+        for i in range(3):
+            Ll.step(planes[i * Bl:(i + 1) * Bl], pol[i * Bl:(i + 1) * Bl], val[i * Bl:(i + 1) * Bl])
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(16):
+            j = (i % 4) * Bl
+            Ll.step(planes[j:j + Bl], pol[j:j + Bl], val[j:j + Bl])
+        ev1.record(); torch.cuda.synchronize()
+        sec_l = ev0.elapsed_time(ev1) * 1e-3 / 16
+        tf_l = 3 * Bl * FLOPS_PER_LEAF / sec_l / 1e12
+        out[precision]["batch_512"] = {"value": Bl / sec_l, "unit": "samples/s", "ms_per_step": sec_l * 1e3, "achieved_tflops": tf_l,
+                                       "frac_of_tf32_roofline": tf_l / (peaks["bf16_tflops_sustained"] / 2),
+                                       "library_baseline": "stock PyTorch 2.11 eager on the same B200 (tools/torch_learner_baseline.py): 17.8 ms fp32, 7.2 ms with TF32 convolutions"}
+        del Ll
     # end to end through the reference-facing trainer: host examples in (boards, policies, values), device dataset
     # construction + augmentation, shuffled batches, checkpoint-ready weights out
     from yinyang_game_alphazero_b200 import trainer as trn

@@ -40,7 +40,8 @@ torch.cuda.synchronize()
 L.yy_lrn_gemm_debug_stamps(None)
 d = dbg.cpu().tolist()
 t0 = d[0]
-print("setup", d[1] - t0, "loop end", d[2] - t0, "acc complete", d[119] - t0, "epilogue end", d[3] - t0)
+print("kernel entry", d[100] - t0, "predecessors done", d[103] - t0, "| setup", d[1] - t0, "loop end", d[2] - t0, "acc complete", d[119] - t0, "epilogue end", d[3] - t0,
+      "cluster reduction end", d[101] - t0 if d[101] else None, "exit", d[102] - t0)
 names = ["iter start", "next loads issued", "slot free", "stored + published"]
 for k in range(min(10, (1152 // split + 31) // 32)):
     print(k, dict(zip(names, [d[4 + 6 * k + j] - t0 if d[4 + 6 * k + j] else None for j in range(4)])))

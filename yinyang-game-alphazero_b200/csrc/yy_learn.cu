@@ -20,6 +20,25 @@
 namespace yy {
 using namespace ptx;
 
+// Programmatic dependent launch: every kernel of the learner step is launched with programmatic stream serialisation, lets the
+// next kernel of the stream start at once (its blocks become resident as SMs free up and run their prologue) and waits for
+// its predecessors' memory before its first global access.  A step is ~170 dependent microsecond kernels: what PDL hides is
+// the launch latency between them.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, tf32 x tf32 -> fp32 (K = 8 per instruction), issued by ONE thread
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -79,8 +98,9 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
   __shared__ __align__(8) uint64_t free_bar[S];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_base_s;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const bool stamp = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
-  YY_STAMP(0);
+  YY_STAMP(100);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * g.tile_n;
   const int k_begin = blockIdx.z * g.k_per_split;
@@ -104,6 +124,7 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
       const int cell = (k_begin + i) % (g.rows * g.cols), x = cell / g.cols, y = cell - x * g.cols;
       edge_s[i] = (uint8_t)((x > 0 ? 1u : 0u) | (x < g.rows - 1 ? 2u : 0u) | (y > 0 ? 4u : 0u) | (y < g.cols - 1 ? 8u : 0u));
     }
+  YY_STAMP(0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -264,6 +285,10 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
     // (Tried: three rotating register sets = two stages of loads in flight: 168 registers, spills in the 3xTF32 variant and
     // no gain -- the K-iteration takes ~3,000 cycles whatever the number of CTAs (32..288, tools/gemm_phases.py): it is
     // bounded by the L1 request path of the 64 LDG.128 per stage, 8 cache lines each, not by bytes in flight or by L2.)
+    // Everything above (barriers, TMEM, the board coordinates of this thread's rows: ~2,500 cycles of integer division) ran
+    // under the previous kernel's tail; its memory is needed from here on.  Only these warps touch global memory.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    YY_STAMP(103);
     float4 ra[4], rb[4], na[4], nb[4];
     if (KT > 0) load_regs(ra, rb, 0);
     if (packedB && tid == 0 && KT > 0) bulk_b(0);
@@ -343,6 +368,9 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
       const bool partial = groups > 1;
       __shared__ float red[2][256][4];
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+      // The partial tiles of the other CTAs come through distributed shared memory, ~20 B per cycle and SM whatever the number of
+      // loads in flight (measured with 8 per thread: no change): 48 KB of remote partials per CTA make this phase ~5,000 of the
+      // kernel's ~25,000 cycles (tools/gemm_phases.py) -- still cheaper than the workspace round trip + reducer launch it replaced.
       for (int idx = tid; idx < rows_per * n4; idx += 256) {
         const int rr = (int)rank * rows_per + idx / n4, cc = (idx % n4) * 4, row = m0 + rr, n = n0 + cc;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -393,11 +421,13 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
         }
       }
     }
+    YY_STAMP(101);
     cluster_sync_all();                                        // nobody leaves while its tile is still being read
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, ncols);
+  YY_STAMP(102);
 }
 
 // C = [C +] bias + sum_z ws[z] [ReLU], slices added in index order (deterministic).  A block finishes 4 slabs of
@@ -405,6 +435,7 @@ __global__ void __launch_bounds__(288) gemm_tf32_kernel(GemmArgs g) {
 // finished C -- the statistics of the batch norm that follows a convolution, saving its own pass over C.
 __global__ void __launch_bounds__(256) gemm_reduce_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, int ldc, int M, int N4,
                                                          const float* __restrict__ bias, int relu, int accumulate, double* __restrict__ bn_sums) {
+  pdl_enter();
   __shared__ float red[2][256][4];
   const int cg = threadIdx.x % N4, n = cg * 4, rl = threadIdx.x / N4, lanes = 256 / N4;   // host guarantees 256 % N4 == 0 when bn_sums
   const size_t slice = (size_t)M * N4 * 4;
@@ -450,6 +481,7 @@ __global__ void __launch_bounds__(256) gemm_reduce_kernel(const float* __restric
 // the same reduction for column counts that do not tile a 256-thread block
 __global__ void __launch_bounds__(256) gemm_reduce_flat_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, int ldc, int M, int N4,
                                                               const float* __restrict__ bias, int relu, int accumulate) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)M * N4) return;
   const int m = (int)(idx / N4), n = (int)(idx % N4) * 4;
@@ -470,6 +502,7 @@ __global__ void __launch_bounds__(256) gemm_reduce_flat_kernel(const float* __re
 // out[c][r] = in[r][c], for blockIdx.z = 0..batch-1 matrices at fixed strides (all layer inputs of the tower in one launch)
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, int R, int C,
                                                        long long in_stride, long long out_stride) {
+  pdl_enter();
   __shared__ float tile[32][33];
   in += (size_t)blockIdx.z * in_stride; out += (size_t)blockIdx.z * out_stride;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -489,6 +522,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 // transposed stores (128 consecutive positions of one channel row per warp pass).
 __global__ void __launch_bounds__(256) im2col_t_kernel(const float* __restrict__ X, int ldx, float* __restrict__ colT, int ldo, int P, int rows,
                                                       int cols, int C) {
+  pdl_enter();
   __shared__ float tile[128][33];
   const int p0 = blockIdx.x * 128, c0 = blockIdx.y * 32, tap = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -521,6 +555,7 @@ __global__ void __launch_bounds__(256) im2col_t_kernel(const float* __restrict__
 // Layer l = blockIdx.y: W = params + offsets[l] -> Wt + l*Cout*9*Cin (all layers of the tower in one launch).
 __global__ void __launch_bounds__(256) conv_weight_t_kernel(const float* __restrict__ params, const long long* __restrict__ offsets,
                                                            float* __restrict__ Wt, int Cout, int Cin) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * 9 * Cin) return;
   const float* W = params + (offsets ? offsets[blockIdx.y] : 0);
@@ -532,6 +567,7 @@ __global__ void __launch_bounds__(256) conv_weight_t_kernel(const float* __restr
 // the shared-memory layout: what gemm_tf32_kernel streams with bulk copies (GemmArgs::Bpack).
 __global__ void __launch_bounds__(256) pack_b_kernel(const float* __restrict__ base, const long long* __restrict__ offsets, long long layer_stride,
                                                     int K, uint8_t* __restrict__ out) {
+  pdl_enter();
   const int stages = K / kGemmKStage;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte chunk: (stage, plane, row)
   if (idx >= stages * 8 * 128) return;
@@ -547,6 +583,7 @@ __global__ void __launch_bounds__(256) pack_b_kernel(const float* __restrict__ b
 
 // planes float32 [B][5][cells] (board_to_input, neural_network.py:156-196) -> X0 [B*cells][8] (channels 5..7 zero)
 __global__ void __launch_bounds__(256) planes_nhwc_kernel(const float* __restrict__ planes, float* __restrict__ X0, long long P, int cells) {
+  pdl_enter();
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const long long b = p / cells; const int cell = (int)(p % cells);
@@ -560,6 +597,7 @@ __global__ void __launch_bounds__(256) planes_nhwc_kernel(const float* __restric
 // out[c] (+)= sum_r X[r][c] (bias gradients).  One block per 32 columns x 256 rows; with more than one row chunk the
 // chunk sums are added to the (zeroed) output with float atomics.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ld, int R, int C, float* __restrict__ out, int atomic) {
+  pdl_enter();
   __shared__ float part[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -583,6 +621,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ Y, int ldy, const float* __restrict__ dOut, int ldd,
                                                        const float* __restrict__ Out, int ldo, const float* __restrict__ mean_invstd,
                                                        int P, int C, double* __restrict__ sums) {
+  pdl_enter();
   __shared__ float red[2][256][4];
   const int C4 = C >> 2, cg = threadIdx.x % C4, rl = threadIdx.x / C4, lanes = 256 / C4, c = cg * 4;
   const int r0 = blockIdx.x * 32, r1 = min(P, r0 + 32);
@@ -628,6 +667,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                       float eps, float momentum, float* __restrict__ mean_invstd, float* __restrict__ running_mean,
                                                       float* __restrict__ running_var, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ residual, int ldr, float* __restrict__ out, int ldo, int relu) {
+  pdl_enter();
   __shared__ float s_mu[128], s_is[128];
   const int C = C4 * 4;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {         // the float64 arithmetic once per channel and block
@@ -673,6 +713,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                           float* __restrict__ dY, int lddy, float* __restrict__ dRes, int lddr,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                                                           float* __restrict__ dYT, int ldt) {
+  pdl_enter();
   __shared__ float red[256][4];
   __shared__ float tile[4608];                                 // the block's rows x (C+1): 32 x 129, 128 x 33 or 512 x 9
   const int C = C4 * 4;
@@ -750,6 +791,7 @@ __global__ void __launch_bounds__(128) heads_loss_kernel(const float* __restrict
                                                         const float* __restrict__ b2, const float* __restrict__ z, int B,
                                                         float* __restrict__ dlogits, int lddl, float* __restrict__ dh, int lddh,
                                                         float* __restrict__ dpre_out, float* __restrict__ v_out, float* __restrict__ losses) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const float* lg = logits + (size_t)b * ldl;
@@ -782,6 +824,7 @@ __global__ void __launch_bounds__(128) heads_loss_kernel(const float* __restrict
 // dw2[j] = sum_b dpre[b]*h[b][j]; db2 = sum_b dpre[b]
 __global__ void value_fc2_grad_kernel(const float* __restrict__ dpre, const float* __restrict__ h, int ldh, int H, int B,
                                       float* __restrict__ dw2, float* __restrict__ db2) {
+  pdl_enter();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < H) {
     float s = 0.f;
@@ -794,6 +837,7 @@ __global__ void value_fc2_grad_kernel(const float* __restrict__ dpre, const floa
 // ------------------------------------------------------------------------------------------------ Adam (torch.optim.Adam, trainer.py:52-56)
 // step_state: int step counter followed (at float index 2, 3) by lr/(1-beta1^t) and sqrt(1-beta2^t) of the current step
 __global__ void adam_tick_kernel(int* step_state, float lr, float b1, float b2) {
+  pdl_enter();
   const int t = ++step_state[0];
   float* f = reinterpret_cast<float*>(step_state);
   f[2] = (float)((double)lr / (1.0 - pow((double)b1, (double)t)));
@@ -801,6 +845,7 @@ __global__ void adam_tick_kernel(int* step_state, float lr, float b1, float b2) 
 }
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                   long long n4, float b1, float b2, float eps, float wd, const int* __restrict__ step_state) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float step_size = reinterpret_cast<const float*>(step_state)[2], bc2s = reinterpret_cast<const float*>(step_state)[3];
@@ -871,10 +916,12 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((M + 127) / 128), (unsigned)((N + tile_n - 1) / tile_n), (unsigned)zs);
   cfg.blockDim = dim3(288); cfg.stream = st; cfg.dynamicSmemBytes = (size_t)smem_bytes;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 2;
   {
     static int max_set[2] = {0, 0};
     const int v = precision == YY_GEMM_3XTF32 ? 1 : 0;
@@ -894,7 +941,7 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
       if (!active[v][i]) {
         cudaLaunchConfig_t q = cfg;
         cudaLaunchAttribute qa[1] = {attr[0]};
-        qa[0].val.clusterDim.z = (unsigned)c; q.attrs = qa;
+        qa[0].val.clusterDim.z = (unsigned)c; q.attrs = qa; q.numAttrs = 1;
         q.dynamicSmemBytes = (size_t)smem_bytes;               // queried once per size class with the first caller's tile
         q.gridDim = dim3(1, 1, (unsigned)c);
         int n = 0;
@@ -919,19 +966,19 @@ int yy_lrn_gemm(const float* A, int lda, int a_mode, const float* B, int ldb, in
   if (groups > 1) {
     if (256 % (N / 4) == 0) {
       const int rows_per_block = 4 * (256 / (N / 4));
-      gemm_reduce_kernel<<<(unsigned)((M + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(ws, groups, C, ldc, M, N / 4, bias, relu, accumulate,
-                                                                                                   bwd_stats ? nullptr : bn_sums);
+      YY_CUDA_OK(launch_pdl(gemm_reduce_kernel, dim3((unsigned)((M + rows_per_block - 1) / rows_per_block)), dim3(256), 0, st, ws, groups, C, ldc, M, N / 4, bias, relu, accumulate,
+                                                                                                   bwd_stats ? nullptr : bn_sums));
     } else {
       const long long total = (long long)M * (N / 4);
-      gemm_reduce_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, groups, C, ldc, M, N / 4, bias, relu, accumulate);
+      YY_CUDA_OK(launch_pdl(gemm_reduce_flat_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, ws, groups, C, ldc, M, N / 4, bias, relu, accumulate));
     }
     YY_LAUNCH_CHECK();
   } else if (bn_sums && !fuse_stats && !bwd_stats) {
-    bn_reduce_kernel<false><<<(M + 31) / 32, 256, 0, st>>>(C, ldc, nullptr, 0, nullptr, 0, nullptr, M, N, bn_sums);
+    YY_CUDA_OK(launch_pdl(bn_reduce_kernel<false>, dim3((M + 31) / 32), dim3(256), 0, st, C, ldc, nullptr, 0, nullptr, 0, nullptr, M, N, bn_sums));
     YY_LAUNCH_CHECK();
   }
   if (bwd_stats && !fuse_stats) {                             // not finished inside one cluster: a pass of its own over the finished C
-    bn_reduce_kernel<true><<<(M + 31) / 32, 256, 0, st>>>(stats->y, stats->ldy, C, ldc, stats->out, stats->ldo, stats->mean_invstd, M, N, bn_sums);
+    YY_CUDA_OK(launch_pdl(bn_reduce_kernel<true>, dim3((M + 31) / 32), dim3(256), 0, st, stats->y, stats->ldy, C, ldc, stats->out, stats->ldo, stats->mean_invstd, M, N, bn_sums));
     YY_LAUNCH_CHECK();
   }
   return YY_OK;
@@ -942,7 +989,7 @@ int yy_lrn_pack_b(const float* base, const long long* offsets_dev, int64_t layer
   if (N != 128 || K <= 0 || (K % kGemmKStage) || ((uintptr_t)out & 15)) return set_error(YY_ERR_INVALID, "pack_b: N = 128, K a multiple of 32");
   if (layers < 1) return YY_OK;
   const int chunks = (K / kGemmKStage) * 8 * 128;
-  pack_b_kernel<<<dim3((unsigned)((chunks + 255) / 256), (unsigned)layers), 256, 0, (cudaStream_t)stream>>>(base, offsets_dev, layer_stride, K, (uint8_t*)out);
+  YY_CUDA_OK(launch_pdl(pack_b_kernel, dim3(dim3((unsigned)((chunks + 255) / 256), (unsigned)layers)), dim3(256), 0, (cudaStream_t)stream, base, offsets_dev, layer_stride, K, (uint8_t*)out));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -954,7 +1001,7 @@ int yy_lrn_transpose(const float* in, int ldi, float* out, int ldo, int R, int C
   int rc = need_device(); if (rc) return rc;
   if (R <= 0 || C <= 0 || batch <= 0) return YY_OK;
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)batch);
-  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ldi, out, ldo, R, C, in_stride, out_stride);
+  YY_CUDA_OK(launch_pdl(transpose_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, in, ldi, out, ldo, R, C, in_stride, out_stride));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -964,7 +1011,7 @@ int yy_lrn_im2col_t(const float* X, int ldx, float* colT, int ldo, int64_t posit
   if (positions % (rows * cols)) return set_error(YY_ERR_INVALID, "im2col_t: positions must be whole boards");
   if (positions == 0) return YY_OK;
   dim3 grid((unsigned)((positions + 127) / 128), (unsigned)((C + 31) / 32), 9);
-  im2col_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, colT, ldo, (int)positions, rows, cols, C);
+  YY_CUDA_OK(launch_pdl(im2col_t_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, X, ldx, colT, ldo, (int)positions, rows, cols, C));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -973,7 +1020,7 @@ int yy_lrn_conv_weight_t(const float* params, const long long* offsets_dev, int 
   int rc = need_device(); if (rc) return rc;
   if (layers < 1) return YY_OK;
   const int total = Cout * 9 * Cin;
-  conv_weight_t_kernel<<<dim3((unsigned)((total + 255) / 256), (unsigned)layers), 256, 0, (cudaStream_t)stream>>>(params, offsets_dev, Wt, Cout, Cin);
+  YY_CUDA_OK(launch_pdl(conv_weight_t_kernel, dim3(dim3((unsigned)((total + 255) / 256), (unsigned)layers)), dim3(256), 0, (cudaStream_t)stream, params, offsets_dev, Wt, Cout, Cin));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -982,7 +1029,7 @@ int yy_lrn_planes_nhwc(const float* planes, float* X0, int64_t boards, int cells
   int rc = need_device(); if (rc) return rc;
   const long long P = boards * cells;
   if (P == 0) return YY_OK;
-  planes_nhwc_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, X0, P, cells);
+  YY_CUDA_OK(launch_pdl(planes_nhwc_kernel, dim3((unsigned)((P + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, planes, X0, P, cells));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -993,7 +1040,7 @@ int yy_lrn_colsum(const float* X, int ld, int R, int C, float* out, void* stream
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = (R + 255) / 256;
   if (chunks > 1) YY_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
-  colsum_kernel<<<dim3((unsigned)((C + 31) / 32), (unsigned)chunks), 256, 0, st>>>(X, ld, R, C, out, chunks > 1);
+  YY_CUDA_OK(launch_pdl(colsum_kernel, dim3(dim3((unsigned)((C + 31) / 32), (unsigned)chunks)), dim3(256), 0, st, X, ld, R, C, out, chunks > 1));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -1007,12 +1054,12 @@ int yy_lrn_bn_forward(const float* Y, int ld, int P, int C, const float* gamma, 
   if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
   cudaStream_t st = (cudaStream_t)stream;
   if (!have_sums) {
-    bn_reduce_kernel<false><<<(P + 31) / 32, 256, 0, st>>>(Y, ld, nullptr, 0, nullptr, 0, nullptr, P, C, sums_ws);
+    YY_CUDA_OK(launch_pdl(bn_reduce_kernel<false>, dim3((P + 31) / 32), dim3(256), 0, st, Y, ld, nullptr, 0, nullptr, 0, nullptr, P, C, sums_ws));
     YY_LAUNCH_CHECK();
   }
   const long long total = (long long)P * (C / 4);
-  bn_apply_kernel<<<(unsigned)((total + 511) / 512), 256, 0, st>>>(Y, ld, P, C / 4, sums_ws, eps, momentum, mean_invstd, running_mean, running_var,
-                                                                  gamma, beta, residual, ldr, out, ldo, relu);
+  YY_CUDA_OK(launch_pdl(bn_apply_kernel, dim3((unsigned)((total + 511) / 512)), dim3(256), 0, st, Y, ld, P, C / 4, sums_ws, eps, momentum, mean_invstd, running_mean, running_var,
+                                                                  gamma, beta, residual, ldr, out, ldo, relu));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -1024,12 +1071,12 @@ int yy_lrn_bn_backward(const float* dOut, int ldd, const float* Out, int ldo, co
   if (!bn_shape_ok(C)) return set_error(YY_ERR_INVALID, "batch norm: C must divide 128");
   cudaStream_t st = (cudaStream_t)stream;
   if (!have_sums) {
-    bn_reduce_kernel<true><<<(P + 31) / 32, 256, 0, st>>>(Y, ldy, dOut, ldd, Out, ldo, mean_invstd, P, C, sums_ws);
+    YY_CUDA_OK(launch_pdl(bn_reduce_kernel<true>, dim3((P + 31) / 32), dim3(256), 0, st, Y, ldy, dOut, ldd, Out, ldo, mean_invstd, P, C, sums_ws));
     YY_LAUNCH_CHECK();
   }
   const long long total = (long long)P * (C / 4);
-  bn_bwd_apply_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(dOut, ldd, Out, ldo, Y, ldy, mean_invstd, gamma, sums_ws, P, C / 4,
-                                                                      dY, lddy, dRes, lddr, dgamma, dbeta, dbias, dYT, ldt);
+  YY_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3((unsigned)((total + 1023) / 1024)), dim3(256), 0, st, dOut, ldd, Out, ldo, Y, ldy, mean_invstd, gamma, sums_ws, P, C / 4,
+                                                                      dY, lddy, dRes, lddr, dgamma, dbeta, dbias, dYT, ldt));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -1041,9 +1088,9 @@ int yy_lrn_heads_loss(const float* logits, int ldl, const float* pi, int A, cons
   if (B <= 0) return set_error(YY_ERR_INVALID, "heads: empty batch");
   cudaStream_t st = (cudaStream_t)stream;
   YY_CUDA_OK(cudaMemsetAsync(losses, 0, 2 * sizeof(float), st));
-  heads_loss_kernel<<<(B + 3) / 4, 128, 0, st>>>(logits, ldl, pi, A, h, ldh, H, w2, b2, z, B, dlogits, lddl, dh, lddh, dpre, v_out, losses);
+  YY_CUDA_OK(launch_pdl(heads_loss_kernel, dim3((B + 3) / 4), dim3(128), 0, st, logits, ldl, pi, A, h, ldh, H, w2, b2, z, B, dlogits, lddl, dh, lddh, dpre, v_out, losses));
   YY_LAUNCH_CHECK();
-  value_fc2_grad_kernel<<<(H + 127) / 128, 128, 0, st>>>(dpre, h, ldh, H, B, dw2, db2);
+  YY_CUDA_OK(launch_pdl(value_fc2_grad_kernel, dim3((H + 127) / 128), dim3(128), 0, st, dpre, h, ldh, H, B, dw2, db2));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
@@ -1053,9 +1100,9 @@ int yy_lrn_adam(float* params, const float* grads, float* m, float* v, int64_t n
   int rc = need_device(); if (rc) return rc;
   if (n & 3) return set_error(YY_ERR_INVALID, "adam: the flat buffers must hold a multiple of 4 floats");
   cudaStream_t st = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, st>>>(step_state, lr, beta1, beta2);
+  YY_CUDA_OK(launch_pdl(adam_tick_kernel, dim3(1), dim3(1), 0, st, step_state, lr, beta1, beta2));
   YY_LAUNCH_CHECK();
-  adam_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(params, grads, m, v, n / 4, beta1, beta2, eps, weight_decay, step_state);
+  YY_CUDA_OK(launch_pdl(adam_kernel, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, st, params, grads, m, v, n / 4, beta1, beta2, eps, weight_decay, step_state));
   YY_LAUNCH_CHECK();
   return YY_OK;
 }
