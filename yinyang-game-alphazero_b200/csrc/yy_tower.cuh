@@ -43,10 +43,12 @@ constexpr int SM_BAR = SM_POS + 2 * 128 * TW_MAXT * 2;
 constexpr int TW_FC_SLOTS = 5;          // weight slots during the FC heads: the ring + 2 in the free tail of the activation region
 constexpr int TW_NBAR = 6;              // barrier sets (full, empty, peer-full): max(TW_CONV_SLOTS, TW_FC_SLOTS)
 constexpr int TW_FC_EXTRA_OFF = 136 * 1024;   // (the FC feature panel ends at 135,168 B)
-constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_NBAR + 4);   // full, empty, peer-full per slot + (acc_full, act_ready) per half of a group
+constexpr int SM_TMEM = SM_BAR + 8 * (3 * TW_NBAR + 4 + 2 * TW_MAXT);   // full, empty, peer-full per slot + (acc_full, act_ready) per half of a group and per tile
 constexpr int SM_BIAS = (SM_TMEM + 16 + 15) & ~15;                                 // current / next layer's 128 fp32 biases (double buffer)
 constexpr int SM_CNT = SM_BIAS + 2 * TW_C * 4;            // counts of the CTA (pair): [step parity][cluster rank][pending leaves, selecting]
-constexpr int SM_TOTAL = SM_CNT + 48;                    // 8 counts + the background warps' stop flag
+constexpr int SM_BIAS_T = SM_CNT + 48;                   // 8 counts + the background warps' stop flag; then per-tile bias double buffers (skewed tiles)
+constexpr int SM_TOTAL = SM_BIAS_T + TW_MAXT * 2 * TW_C * 4;
+constexpr int TW_SKEW = 3;               // stages at the head and at the tail of a layer that the MMA issuer walks tile by tile (<= TW_STAGES)
 static_assert(SM_TOTAL <= 232448, "persistent kernel exceeds the 227 KB opt-in shared memory of sm_100");
 static_assert(TW_FC_EXTRA_OFF + (TW_FC_SLOTS - TW_STAGES) * TW_STAGE_BYTES <= TW_CHUNKS * TW_ROWS * 16, "FC slots exceed the activation region");
 
