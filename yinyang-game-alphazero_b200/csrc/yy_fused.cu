@@ -39,6 +39,7 @@ struct FusedArgs {
   int iterations;              // 1 = plain forward; n_sims + 1 = whole search; rolling self-play: any number of steps
   int mode;                    // YY_FUSED_FORWARD / YY_FUSED_SEARCH (tree step after every evaluation) / YY_FUSED_SELFPLAY
   int use_nn;                  // 0 = deterministic-prior (stub) evaluator: tree steps only
+  int no_skew;                 // developer A/B (yy_engine_set_debug_flags bit 1): tiles of a group in lock step as in round 1
   int split_halves;            // developer A/B (yy_engine_set_debug_flags bit 0): the two halves of a group ping-pong through the
                                // tensor cores.  OFF in the product: it hides the epilogue (the MMA issuer's wait for activations
                                // drops from 513 k to 93 k cycles per step) but every half streams the layer's weights again, and
@@ -77,6 +78,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   // a group ping-pong through the tensor cores; the product runs a group as ONE half)
   auto acc_full = [&](int h) { return bar0 + 8u * (3 * TW_NBAR + 2 * h); };
   auto act_ready = [&](int h) { return bar0 + 8u * (3 * TW_NBAR + 2 * h + 1); };
+  // the same pair per TILE for groups whose tiles are skewed against each other (see `skewed` below)
+  auto acc_full_t = [&](int t) { return bar0 + 8u * (3 * TW_NBAR + 4 + 2 * t); };
+  auto act_ready_t = [&](int t) { return bar0 + 8u * (3 * TW_NBAR + 4 + 2 * t + 1); };
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
 
@@ -109,6 +113,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
       mbar_init(acc_full(h), 1);
       mbar_init(act_ready(h), CG * TW_EPI_THREADS);   // pair: the leader's barrier also collects the follower's epilogue threads
     }
+    for (int t = 0; t < TW_MAXT; ++t) { mbar_init(acc_full_t(t), 1); mbar_init(act_ready_t(t), CG * 128); }   // a tile has 4 epilogue warps per CTA
     fence_barrier_init();
   }
   if (warp == 1) { if (CG == 2) tmem_alloc2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
@@ -160,6 +165,15 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     if (g.row_aligned == 2) return T == 4 ? 2 : T;
     return T;
   };
+  // Tile skew.  In a layer every weight stage serves all tiles of the group, so the tiles used to finish the layer together: their
+  // epilogues then ran side by side while the tensor cores idled (26 % of a step), and the next layer started for all of them at
+  // once.  When the tiles of a group are independent through the tower (interleaved layouts: no tap of a tile reads a row of
+  // another; half-board tiles: in units of the two halves of a board), the MMA issuer instead walks the LAST and the FIRST TW_SKEW stages of a layer tile by tile (they fit the ring
+  // together) and only the stages in between stage by stage: tile 0 completes the layer TW_SKEW * (T - 1) stage-tiles of MMA time
+  // before tile T-1, its epilogue runs under the other tiles' MMAs, and it starts the next layer as soon as ITS activations are
+  // in place.  Weights are still streamed once per layer and group.  Synchronisation is per tile (acc_full_t / act_ready_t).
+  static_assert(TW_SKEW <= TW_STAGES, "the tile-by-tile stages of a layer must fit the weight ring together");
+  auto skewed = [&](int T) { return !a.split_halves && !a.no_skew && (g.row_aligned == 2 ? T == 4 : (g.row_aligned == 3 || g.row_aligned == 4) && T >= 3); };
   auto batch_end = [&](int bb0) { return (bb0 + a.batch_boards < n_struct) ? bb0 + a.batch_boards : n_struct; };   // structural
   // FC stage geometry: rows of M tile t of head h
   auto fc_tiles = [&](int h) { return h ? 2 : fc.Tp; };
@@ -184,6 +198,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
       for (int iter = 0; dyn && iter < a.iterations; ++iter) { fetch_counts(iter); if (!any_work) break; }
     } else {
       uint32_t ci = 0, used = 0, ephase = 0, acc_n[2] = {0, 0};     // conv stage counter, slots used so far, empty-phase bits, commits so far per half
+      uint32_t acc_nt[TW_MAXT] = {0, 0, 0, 0};                      // commits so far per tile (skewed groups)
+      int last_skew_T = 0;                                          // > 0: the batch's last group was skewed and had this many tiles
       auto push_to = [&](uint32_t slot, uint32_t dst, const uint8_t* src, uint32_t bytes) {
         if ((used >> slot) & 1u) { mbar_wait(empty_bar(slot), (ephase >> slot) & 1u); ephase ^= 1u << slot; }
         used |= 1u << slot;
@@ -219,12 +235,18 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           for (int b0 = bb0; b0 < slim; b0 += g.Gb) {
             const int T = tiles_for(b0, slim);
             nh = half_split(T) < T ? 2 : 1;
+            const bool skew = skewed(T);
+            last_skew_T = skew ? T : 0;
             for (int l = 0; l < L; ++l) {
               const LayerInfo li = layer_info(l, g.blocks, CG);
               const uint32_t bytes = (uint32_t)li.stage_bytes / CG;     // pair: my half of the stage's output channels
               const uint8_t* src = a.conv_stream + li.stream_off + (long long)rank * bytes;
+              if (skew) {
+#pragma unroll
+                for (int t = 0; t < TW_MAXT; ++t) if (t < T) ++acc_nt[t];
+              }
               for (int hh = 0; hh < nh; ++hh) {                          // every half of the group streams the layer's weights
-                ++acc_n[hh];
+                if (!skew) ++acc_n[hh];
                 for (int j = 0; j < li.n_stages; ++j, ++ci)
                   push_to(ci % TW_CONV_SLOTS, conv_slot_addr(ci % TW_CONV_SLOTS), src + (long long)j * li.stage_bytes, bytes);
               }
@@ -232,8 +254,15 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           }
           // the extra FC slots overlay activation rows: wait until the last head conv of the batch has been computed, in
           // both halves (commit number acc_n - 1 of acc_full; it cannot be overtaken -- the next commit needs stages from me)
-          mbar_wait(acc_full(0), (acc_n[0] - 1) & 1u);
-          if (nh == 2) mbar_wait(acc_full(1), (acc_n[1] - 1) & 1u);
+          if (last_skew_T) {                                           // skewed group: its last tile's last commit covers every MMA before it
+            uint32_t n_last = 0;
+#pragma unroll
+            for (int t = 0; t < TW_MAXT; ++t) if (t == last_skew_T - 1) n_last = acc_nt[t];
+            mbar_wait(acc_full_t(last_skew_T - 1), (n_last - 1) & 1u);
+          } else {
+            mbar_wait(acc_full(0), (acc_n[0] - 1) & 1u);
+            if (nh == 2) mbar_wait(acc_full(1), (acc_n[1] - 1) & 1u);
+          }
           const uint8_t* src = a.fc_stream;
           uint32_t fi = 0;
           fc_before = true;
@@ -286,7 +315,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         }
       }
     } else {
-      uint32_t ci = 0, fphase = 0, act_phase[2] = {0, 0};
+      uint32_t ci = 0, fphase = 0, act_phase[2] = {0, 0}, actt_phase = 0;   // actt_phase bit t: parity of act_ready_t(t)
       long long stall_w = 0, stall_a = 0, t_start = clock64();     // developer stamps: cycles the issuer waited for weights / activations
       auto wait_stage = [&](uint32_t slot) {
         const uint32_t parity = (fphase >> slot) & 1u;
@@ -300,6 +329,13 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
         const long long t0 = a.dbg ? clock64() : 0;
         if (CG == 2) mbar_wait_cluster(act_ready(h), act_phase[h]); else mbar_wait(act_ready(h), act_phase[h]);
         act_phase[h] ^= 1;
+        if (a.dbg) stall_a += clock64() - t0;
+      };
+      auto wait_act_t = [&](int t) {
+        const long long t0 = a.dbg ? clock64() : 0;
+        const uint32_t parity = (actt_phase >> t) & 1u;
+        if (CG == 2) mbar_wait_cluster(act_ready_t(t), parity); else mbar_wait(act_ready_t(t), parity);
+        actt_phase ^= 1u << t;
         if (a.dbg) stall_a += clock64() - t0;
       };
       auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
@@ -319,12 +355,66 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
           for (int b0 = bb0; b0 < slim; b0 += g.Gb) {
             const int T = tiles_for(b0, slim);
             const int T0 = half_split(T), nh = T0 < T ? 2 : 1;
+            const bool skew = skewed(T);
             for (int l = 0; l < L; ++l) {
               const LayerInfo li = layer_info(l, g.blocks, CG);
               const bool preloaded = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 0);  // conv2: accumulator holds the skip input
               const uint32_t idesc = idesc_bf16(128 * CG, li.N);
               const uint32_t nrows_b = (uint32_t)li.N / CG;                          // weight rows staged per CTA
               const uint64_t k16_delta_b = (uint64_t)((2u * nrows_b * 16u) >> 4);
+              if (skew) {
+                // stages [0, head) and [NS - tail, NS) tile by tile, the ones in between stage by stage; a short layer (the head
+                // convolution: one stage) is all tail
+                const int NS = li.n_stages;
+                const int head = NS >= 2 * TW_SKEW ? TW_SKEW : 0, tail = NS >= 2 * TW_SKEW ? TW_SKEW : NS;
+                const uint32_t ci0 = ci;
+                uint32_t waited = 0;                                                 // bit j: stage j of this layer has landed (both CTAs)
+                auto stage_ready = [&](int j) {
+                  if (!((waited >> j) & 1u)) { wait_stage((ci0 + (uint32_t)j) % TW_CONV_SLOTS); tc_fence_after(); waited |= 1u << j; }
+                };
+                auto issue = [&](int t, int j) {
+                  const uint32_t slot = (ci0 + (uint32_t)j) % TW_CONV_SLOTS;
+                  int tapshift, chunk0;
+                  stage_info(l, j, g.blocks, g.pitch, g.dy_rows, CG, tapshift, chunk0);
+                  const uint64_t ad0 = smem_desc(act_base + (uint32_t)((chunk0 * TW_ROWS + TW_PAD + tapshift) * 16), TW_ROWS * 16, (uint32_t)g.sbo_bytes) +
+                                       (g.row_aligned == 2 ? (uint64_t)((t >> 1) * g.PB + (t & 1) * 8) : (uint64_t)(t * g.tile_adv));
+                  const uint64_t bd0 = smem_desc(conv_slot_addr(slot), nrows_b * 16, 128);
+                  const uint32_t acc0 = (preloaded || j > 0) ? 1u : 0u;
+                  if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4 * CG; ++k)
+                      if (k < li.nk16)
+                        mma(tmem_base + (uint32_t)(t * 128), ad0 + (uint64_t)k * kK16DeltaA, bd0 + (uint64_t)k * k16_delta_b, idesc, k > 0 ? 1u : acc0);
+                  }
+                  __syncwarp();
+                };
+                auto free_stage = [&](int j) { if (elect_one()) commit(empty_bar((ci0 + (uint32_t)j) % TW_CONV_SLOTS)); __syncwarp(); };
+                // U tiles form a unit that must move together: 1 when tiles are independent, 2 for half-board tiles (a tap of one half
+                // reads the other half's boundary column, and the epilogue overwrites activations in place)
+                const int U = g.row_aligned == 2 ? 2 : 1;
+                for (int u0 = 0; u0 < T && head > 0; u0 += U) {
+                  for (int t = u0; t < u0 + U && t < T; ++t) wait_act_t(t);
+                  tc_fence_after();
+                  for (int t = u0; t < u0 + U && t < T; ++t)
+                    for (int j = 0; j < head; ++j) { stage_ready(j); issue(t, j); if (t == T - 1) free_stage(j); }
+                }
+                for (int j = head; j < NS - tail; ++j) {
+                  stage_ready(j);
+                  for (int t = 0; t < T; ++t) issue(t, j);
+                  free_stage(j);
+                }
+                for (int u0 = 0; u0 < T; u0 += U) {
+                  if (head == 0) {                                                   // the unit's first MMAs of this layer
+                    for (int t = u0; t < u0 + U && t < T; ++t) wait_act_t(t);
+                    tc_fence_after();
+                  }
+                  for (int t = u0; t < u0 + U && t < T; ++t)
+                    for (int j = NS - tail; j < NS; ++j) { stage_ready(j); issue(t, j); if (t == T - 1) free_stage(j); }
+                  for (int t = u0; t < u0 + U && t < T; ++t) { if (elect_one()) commit(acc_full_t(t)); __syncwarp(); }
+                }
+                ci += (uint32_t)NS;
+                continue;
+              }
              for (int hh = 0; hh < nh; ++hh) {
               const int tlo = hh ? T0 : 0, thi = hh ? T : T0;
               wait_act(hh);
@@ -428,7 +518,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
     const int quarter = warp & 3;        // TMEM lanes a warp may touch: 32*(warp_id % 4) ..
     const int tile0 = ew >> 2;           // with 16 warps every tile of the group has its own 4 warps
     constexpr int kTileStride = TW_EPI_WARPS / 4;
-    uint32_t acc_phase[2] = {0, 0};
+    uint32_t acc_phase[2] = {0, 0}, acct_phase = 0;     // acct_phase bit t: parity of acc_full_t(t) (skewed groups)
     uint8_t* act = smem + SM_ACT;
     float* sc_logit = reinterpret_cast<float*>(act);                 // [FC_N][256] heads scratch (act region is free then)
     float* sc_hidden = reinterpret_cast<float*>(act) + FC_N * 256;   // [FC_N][256] relu(fc1) * w2
@@ -515,35 +605,141 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
               c_lo = (sub4 % wpt) * n_c;
               return t < tlo + nt;
             };
-            // ---- stem input planes (board_to_input, neural_network.py:156-196) for my rows, half by half ----
+            // ---- stem input planes (board_to_input, neural_network.py:156-196) for my row of tile t ----
+            auto stem_rows = [&](int t) {
+              const int mi = t * 128 + quarter * 32 + lane;
+              const int p = pos_p[mi];
+              const int info = pos_tab[mi];
+              uint4 c0 = make_uint4(0, 0, 0, 0);
+              const int entry = b0 + (info >= 0 ? (info >> 8) : 0);
+              if (info >= 0 && entry < lim) {
+                const long long board = board_of(entry);
+                const int cell = info & 255, y = cell / g.m, x = cell % g.m;
+                const uint64_t* bb = a.black + board * g.W; const uint64_t* wb = a.white + board * g.W;
+                auto bit = [&](const uint64_t* v, int c) { return (int)((v[c >> 6] >> (c & 63)) & 1ull); };
+                const int isb = bit(bb, cell), isw = bit(wb, cell);
+                int rc = 0, cc = 0;
+                for (int xx = 0; xx < g.m; ++xx) { int c = y * g.m + xx; rc += bit(bb, c) | bit(wb, c); }
+                for (int yy = 0; yy < g.n; ++yy) { int c = yy * g.m + x; cc += bit(bb, c) | bit(wb, c); }
+                const float rf = (float)((double)rc / (double)g.m), cf = (float)((double)cc / (double)g.n);
+                const float rf_hi = __bfloat162float(__float2bfloat16_rn(rf)), cf_hi = __bfloat162float(__float2bfloat16_rn(cf));
+                // channels: 0 empty, 1 black, 2 white, 3 row fill, 4 col fill, 5/6 = bf16 residuals of 3/4 (same weights)
+                c0.x = pack_bf16x2((isb | isw) ? 0.0f : 1.0f, isb ? 1.0f : 0.0f);
+                c0.y = pack_bf16x2(isw ? 1.0f : 0.0f, rf_hi);
+                c0.z = pack_bf16x2(cf_hi, rf - rf_hi);
+                c0.w = pack_bf16x2(cf - cf_hi, 0.0f);
+              }
+              *reinterpret_cast<uint4*>(act + (size_t)(0 * TW_ROWS + TW_PAD + p) * 16) = c0;
+              *reinterpret_cast<uint4*>(act + (size_t)(1 * TW_ROWS + TW_PAD + p) * 16) = make_uint4(0, 0, 0, 0);
+            };
+            // ---- one layer's epilogue for my row of tile t, 16-column chunks [c_lo, c_lo + n_c): accumulator -> bias, ReLU ->
+            // bf16 activations in place (conv1 parks the skip input in TMEM first); head convolution -> head features in L2 ----
+            auto layer_rows = [&](int l, int t, int c_lo, int n_c, const float* bias) {
+              const bool is_head = (l == L - 1);
+              const bool is_conv1 = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 1);
+              const int mi = t * 128 + quarter * 32 + lane;
+              const int p = pos_p[mi];
+              const int info = pos_tab[mi];
+              const int entry = b0 + (info >= 0 ? (info >> 8) : 0);
+              const bool real = info >= 0 && entry < lim;
+              const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 128);
+              uint8_t* rowp = act + (size_t)(TW_PAD + p) * 16;
+              if (!is_head) {
+                // one 16-column chunk: bias + ReLU (+ park the skip input in TMEM) -> two 16-byte channel chunks in place
+                auto process = [&](const uint32_t (&r)[16], int cc) {
+                  uint4* d0 = reinterpret_cast<uint4*>(rowp + (size_t)(2 * cc) * TW_ROWS * 16);
+                  uint4* d1 = reinterpret_cast<uint4*>(rowp + (size_t)(2 * cc + 1) * TW_ROWS * 16);
+                  if (is_conv1) {  // skip connection: conv2 will accumulate on top of the block input
+                    const uint4 x0 = *d0, x1 = *d1;
+                    uint32_t xr[16];
+                    const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { xr[2 * q] = xs[q] << 16; xr[2 * q + 1] = xs[q] & 0xffff0000u; }
+                    tc_st16(taddr + cc * 16, xr);
+                  }
+                  const float4* b4 = reinterpret_cast<const float4*>(bias + cc * 16);
+                  float v[16];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float4 bq = b4[q];
+                    v[4 * q + 0] = fmaxf(__uint_as_float(r[4 * q + 0]) + bq.x, 0.0f);
+                    v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + bq.y, 0.0f);
+                    v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + bq.z, 0.0f);
+                    v[4 * q + 3] = fmaxf(__uint_as_float(r[4 * q + 3]) + bq.w, 0.0f);
+                  }
+                  if (!real) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+                  }
+                  *d0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                  *d1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                };
+                // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed (n_c is even)
+                uint32_t ra[16], rb[16];
+                const int c_hi = c_lo + n_c;
+                tc_ld16(taddr + c_lo * 16, ra);
+#pragma unroll 1
+                for (int cc = c_lo; cc < c_hi; cc += 2) {
+                  tc_wait_ld();
+                  tc_ld16(taddr + (cc + 1) * 16, rb);
+                  process(ra, cc);
+                  tc_wait_ld();
+                  if (cc + 2 < c_hi) tc_ld16(taddr + (cc + 2) * 16, ra);
+                  process(rb, cc + 1);
+                }
+                if (is_conv1) tc_wait_st();
+              } else {
+                __nv_bfloat16* dst = a.headfeat + (size_t)(run_lo + entry) * (TW_HEADC * g.A) + (info & 255);   // by walk entry
+                const int h_n = n_c >= 2 ? n_c / 2 : 1, h_lo = n_c >= 2 ? c_lo / 2 : c_lo;   // 4 chunks of 16 head channels over the same warps
+#pragma unroll 1
+                for (int cc = h_lo; cc < h_lo + h_n && cc < TW_HEADC / 16; ++cc) {
+                  uint32_t r[16];
+                  tc_ld16(taddr + cc * 16, r);
+                  tc_wait_ld();
+                  if (real) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                      dst[(size_t)(cc * 16 + j) * g.A] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + bias[cc * 16 + j], 0.0f));
+                  }
+                }
+              }
+            };
+
+            if (skewed(T)) {
+              // ---- skewed tiles: the 4 warps of tile `sub4` follow THEIR tile through the tower (per-tile barriers, per-tile bias
+              // double buffer, one named barrier of 128 threads per layer); warps without a tile (T == 3) sit the group out ----
+              const int t = sub4;
+              if (t < T) {
+                float* bias_t = reinterpret_cast<float*>(smem + SM_BIAS_T) + t * 2 * TW_C;
+                const int tl = (ew & 3) * 32 + lane;                       // my index among the tile's 128 threads
+                auto tile_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(3 + t) : "memory"); };
+                const uint32_t ready = CG == 2 ? mapa_u32(act_ready_t(t), 0) : act_ready_t(t);
+                auto arrive_t = [&]() { if (CG == 2) mbar_arrive_cluster(ready); else mbar_arrive(ready); };
+                stem_rows(t);
+                bias_t[tl] = __ldg(a.conv_bias + tl);                      // stem biases (buffer 0)
+                tc_fence_before();
+                fence_proxy_async_smem();
+                arrive_t();
+                for (int l = 0; l < L; ++l) {
+                  mbar_wait(acc_full_t(t), (acct_phase >> t) & 1u);
+                  acct_phase ^= 1u << t;
+                  tc_fence_after();
+                  tile_sync();           // this layer's biases are staged by all four warps; the other buffer is free
+                  if (l + 1 < L) bias_t[((l + 1) & 1) * TW_C + tl] = __ldg(a.conv_bias + (size_t)(l + 1) * TW_C + tl);
+                  layer_rows(l, t, 0, TW_C / 16, bias_t + (l & 1) * TW_C);
+                  tc_fence_before();
+                  if (l + 1 < L) {
+                    fence_proxy_async_smem();
+                    arrive_t();
+                  }
+                }
+              }
+              continue;
+            }
+
             for (int hh = 0; hh < nh; ++hh) {
               int t, c_lo, n_c;
-              if (my_share(hh, t, c_lo, n_c) && c_lo == 0) {
-                const int mi = t * 128 + quarter * 32 + lane;
-                const int p = pos_p[mi];
-                const int info = pos_tab[mi];
-                uint4 c0 = make_uint4(0, 0, 0, 0);
-                const int entry = b0 + (info >= 0 ? (info >> 8) : 0);
-                if (info >= 0 && entry < lim) {
-                  const long long board = board_of(entry);
-                  const int cell = info & 255, y = cell / g.m, x = cell % g.m;
-                  const uint64_t* bb = a.black + board * g.W; const uint64_t* wb = a.white + board * g.W;
-                  auto bit = [&](const uint64_t* v, int c) { return (int)((v[c >> 6] >> (c & 63)) & 1ull); };
-                  const int isb = bit(bb, cell), isw = bit(wb, cell);
-                  int rc = 0, cc = 0;
-                  for (int xx = 0; xx < g.m; ++xx) { int c = y * g.m + xx; rc += bit(bb, c) | bit(wb, c); }
-                  for (int yy = 0; yy < g.n; ++yy) { int c = yy * g.m + x; cc += bit(bb, c) | bit(wb, c); }
-                  const float rf = (float)((double)rc / (double)g.m), cf = (float)((double)cc / (double)g.n);
-                  const float rf_hi = __bfloat162float(__float2bfloat16_rn(rf)), cf_hi = __bfloat162float(__float2bfloat16_rn(cf));
-                  // channels: 0 empty, 1 black, 2 white, 3 row fill, 4 col fill, 5/6 = bf16 residuals of 3/4 (same weights)
-                  c0.x = pack_bf16x2((isb | isw) ? 0.0f : 1.0f, isb ? 1.0f : 0.0f);
-                  c0.y = pack_bf16x2(isw ? 1.0f : 0.0f, rf_hi);
-                  c0.z = pack_bf16x2(cf_hi, rf - rf_hi);
-                  c0.w = pack_bf16x2(cf - cf_hi, 0.0f);
-                }
-                *reinterpret_cast<uint4*>(act + (size_t)(0 * TW_ROWS + TW_PAD + p) * 16) = c0;
-                *reinterpret_cast<uint4*>(act + (size_t)(1 * TW_ROWS + TW_PAD + p) * 16) = make_uint4(0, 0, 0, 0);
-              }
+              if (my_share(hh, t, c_lo, n_c) && c_lo == 0) stem_rows(t);
               tc_fence_before();
               fence_proxy_async_smem();
               arrive_act(hh);
@@ -552,87 +748,19 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
 
             for (int l = 0; l < L; ++l) {
               const bool is_head = (l == L - 1);
-              const bool is_conv1 = (l >= 1 && l <= 2 * g.blocks && (l & 1) == 1);
               // this layer's biases were staged in shared memory while its MMAs ran (an LDG per chunk sat on the
               // epilogue's critical path: 40 % of its stall samples); double buffered by layer parity
               const float* bias = bias_s + (l & 1) * TW_C;
-             for (int hh = 0; hh < nh; ++hh) {
-              wait_acc(hh);
-              int t, c_lo, n_c;
-              if (my_share(hh, t, c_lo, n_c)) {
-                const int mi = t * 128 + quarter * 32 + lane;
-                const int p = pos_p[mi];
-                const int info = pos_tab[mi];
-                const int entry = b0 + (info >= 0 ? (info >> 8) : 0);
-                const bool real = info >= 0 && entry < lim;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 128);
-                uint8_t* rowp = act + (size_t)(TW_PAD + p) * 16;
+              for (int hh = 0; hh < nh; ++hh) {
+                wait_acc(hh);
+                int t, c_lo, n_c;
+                if (my_share(hh, t, c_lo, n_c)) layer_rows(l, t, c_lo, n_c, bias);
+                tc_fence_before();
                 if (!is_head) {
-                  // one 16-column chunk: bias + ReLU (+ park the skip input in TMEM) -> two 16-byte channel chunks in place
-                  auto process = [&](const uint32_t (&r)[16], int cc) {
-                    uint4* d0 = reinterpret_cast<uint4*>(rowp + (size_t)(2 * cc) * TW_ROWS * 16);
-                    uint4* d1 = reinterpret_cast<uint4*>(rowp + (size_t)(2 * cc + 1) * TW_ROWS * 16);
-                    if (is_conv1) {  // skip connection: conv2 will accumulate on top of the block input
-                      const uint4 x0 = *d0, x1 = *d1;
-                      uint32_t xr[16];
-                      const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-                      for (int q = 0; q < 8; ++q) { xr[2 * q] = xs[q] << 16; xr[2 * q + 1] = xs[q] & 0xffff0000u; }
-                      tc_st16(taddr + cc * 16, xr);
-                    }
-                    const float4* b4 = reinterpret_cast<const float4*>(bias + cc * 16);
-                    float v[16];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                      const float4 bq = b4[q];
-                      v[4 * q + 0] = fmaxf(__uint_as_float(r[4 * q + 0]) + bq.x, 0.0f);
-                      v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + bq.y, 0.0f);
-                      v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + bq.z, 0.0f);
-                      v[4 * q + 3] = fmaxf(__uint_as_float(r[4 * q + 3]) + bq.w, 0.0f);
-                    }
-                    if (!real) {
-#pragma unroll
-                      for (int j = 0; j < 16; ++j) v[j] = 0.0f;
-                    }
-                    *d0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                    *d1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-                  };
-                  // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed (n_c is even)
-                  uint32_t ra[16], rb[16];
-                  const int c_hi = c_lo + n_c;
-                  tc_ld16(taddr + c_lo * 16, ra);
-#pragma unroll 1
-                  for (int cc = c_lo; cc < c_hi; cc += 2) {
-                    tc_wait_ld();
-                    tc_ld16(taddr + (cc + 1) * 16, rb);
-                    process(ra, cc);
-                    tc_wait_ld();
-                    if (cc + 2 < c_hi) tc_ld16(taddr + (cc + 2) * 16, ra);
-                    process(rb, cc + 1);
-                  }
-                  if (is_conv1) tc_wait_st();
-                } else {
-                  __nv_bfloat16* dst = a.headfeat + (size_t)(run_lo + entry) * (TW_HEADC * g.A) + (info & 255);   // by walk entry
-                  const int h_n = n_c >= 2 ? n_c / 2 : 1, h_lo = n_c >= 2 ? c_lo / 2 : c_lo;   // 4 chunks of 16 head channels over the same warps
-#pragma unroll 1
-                  for (int cc = h_lo; cc < h_lo + h_n && cc < TW_HEADC / 16; ++cc) {
-                    uint32_t r[16];
-                    tc_ld16(taddr + cc * 16, r);
-                    tc_wait_ld();
-                    if (real) {
-#pragma unroll
-                      for (int j = 0; j < 16; ++j)
-                        dst[(size_t)(cc * 16 + j) * g.A] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + bias[cc * 16 + j], 0.0f));
-                    }
-                  }
+                  fence_proxy_async_smem();
+                  arrive_act(hh);
                 }
               }
-              tc_fence_before();
-              if (!is_head) {
-                fence_proxy_async_smem();
-                arrive_act(hh);
-              }
-             }
               if (!is_head && etid < TW_C) bias_s[((l + 1) & 1) * TW_C + etid] = __ldg(a.conv_bias + (size_t)(l + 1) * TW_C + etid);
             }
           }
@@ -803,6 +931,7 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
   fa.iterations = iterations; fa.mode = mode; fa.use_nn = use_nn ? 1 : 0;
   fa.dbg = nn.dbg;
   fa.split_halves = nn.dbg_flags & 1;
+  fa.no_skew = (nn.dbg_flags >> 1) & 1;
   fa.batch_boards = fused_batch_boards(fa.g);
   // equal contiguous runs of boards per CTA (a search keeps its games on the same SM from the first to the last simulation)
   int sms = nn.num_sms > 0 ? nn.num_sms : 148;

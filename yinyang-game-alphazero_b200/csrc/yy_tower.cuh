@@ -48,7 +48,7 @@ constexpr int SM_BIAS = (SM_TMEM + 16 + 15) & ~15;                              
 constexpr int SM_CNT = SM_BIAS + 2 * TW_C * 4;            // counts of the CTA (pair): [step parity][cluster rank][pending leaves, selecting]
 constexpr int SM_BIAS_T = SM_CNT + 48;                   // 8 counts + the background warps' stop flag; then per-tile bias double buffers (skewed tiles)
 constexpr int SM_TOTAL = SM_BIAS_T + TW_MAXT * 2 * TW_C * 4;
-constexpr int TW_SKEW = 3;               // stages at the head and at the tail of a layer that the MMA issuer walks tile by tile (<= TW_STAGES)
+constexpr int TW_SKEW = 2;               // stages at the head and at the tail of a layer that the MMA issuer walks tile by tile (<= TW_STAGES)
 static_assert(SM_TOTAL <= 232448, "persistent kernel exceeds the 227 KB opt-in shared memory of sm_100");
 static_assert(TW_FC_EXTRA_OFF + (TW_FC_SLOTS - TW_STAGES) * TW_STAGE_BYTES <= TW_CHUNKS * TW_ROWS * 16, "FC slots exceed the activation region");
 
