@@ -60,6 +60,21 @@ def host_rules_lib():
     return ctypes.CDLL(so)
 
 
+@pytest.fixture(scope="session")
+def host_tower_lib():
+    """nvcc host build of the tower's layout algebra (yy_tower.cuh) for the structural check (test-only, no GPU needed)."""
+    import ctypes
+    d = os.path.join(ROOT, "tests", "_host")
+    so = os.path.join(d, "libtower_host.so")
+    src = os.path.join(d, "tower_layout_check.cu")
+    hdr = os.path.join(ROOT, "yinyang-game-alphazero_b200", "csrc", "yy_tower.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        subprocess.run([nvcc, "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
+                        "-Wno-deprecated-gpu-targets", "-o", so, src], check=True)
+    return ctypes.CDLL(so)
+
+
 def golden_files(prefix):
     return sorted(f for f in os.listdir(GOLDEN) if f.startswith(prefix) and f.endswith(".npz"))
 

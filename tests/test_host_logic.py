@@ -270,3 +270,17 @@ def test_bench_reference_arm_prints_the_contract_line(tmp_path):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["steps"] == 1
+
+
+@pytest.mark.parametrize("shape,layout,useful", [((8, 8), 3, 1.0), ((6, 6), 4, 0.84), ((16, 16), 2, 1.0), ((7, 8), 1, 0.87), ((5, 7), 0, 0.7),
+                                                 ((4, 4), 0, 0.6), ((10, 10), 0, 0.75), ((12, 12), 0, 0.8), ((9, 14), 0, 0.7), ((3, 3), 0, 0.5)])
+def test_tower_layouts_structural(host_tower_lib, shape, layout, useful):
+    """The padded-position layouts of the tcgen05 tower (yy_tower.cuh), walked on the host: every cell of every board of a
+    group is exactly one MMA row, every 3x3 tap of a cell reads the neighbouring cell of the same board or zero padding,
+    nothing leaves the activation region, and in the layouts whose tiles run skewed no tap reads a cell of another tile."""
+    n, m = shape
+    lay, gb, T = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    u = ctypes.c_double()
+    rc = host_tower_lib.yyh_tower_layout(n, m, ctypes.byref(lay), ctypes.byref(gb), ctypes.byref(T), ctypes.byref(u))
+    assert rc == 0, rc
+    assert lay.value == layout and u.value >= useful and gb.value * n * m <= 128 * T.value

@@ -87,23 +87,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   // ---- one-time setup ----
   for (int i = tid; i < (SM_POS - SM_ACT) / 4; i += TW_THREADS) reinterpret_cast<uint32_t*>(smem + SM_ACT)[i] = 0u;   // act + ring
   for (int i = tid; i < 128 * TW_MAXT; i += TW_THREADS) {
-    int v = -1, p, b, y, x;
-    if (g.row_aligned == 3) {
-      const int t = i >> 7, j = (i & 127) >> 3;
-      x = i & 7; b = 2 * t + (j & 1); y = j >> 1; p = t * g.tile_adv + j * g.pitch + x;
-    } else if (g.row_aligned == 4) {
-      const int t = i >> 7, r = i & 127, j = r / g.pitch;
-      x = r % g.pitch; y = j / g.ilv; b = g.ilv * t + j % g.ilv; p = t * g.tile_adv + r;
-    } else if (g.row_aligned == 2) {
-      const int t = i >> 7, r = i & 127;
-      b = t >> 1; y = r >> 3; x = 8 * (t & 1) + (r & 7); p = b * g.PB + y * g.pitch + x;
-    } else if (g.row_aligned) {
-      const int R = (i >> 7) * 16 + ((i & 127) >> 3);
-      x = i & 7; p = R * g.pitch + x; b = R / g.rows_per_board; y = R % g.rows_per_board;
-    } else {
-      p = i; b = p / g.PB; const int rem = p % g.PB; y = rem / g.pitch; x = rem % g.pitch;
-    }
-    if (b < g.Gb && y < g.n && x < g.m) v = b * 256 + y * g.m + x;
+    int p, v;
+    tower_row(g, i, p, v);
     pos_p[i] = (int16_t)p;
     pos_tab[i] = (int16_t)v;
   }
@@ -152,9 +137,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
   // (+pitch+1: the taps of the last real position read that far; rows beyond the group's tiles may be stale)
   auto tiles_for = [&](int b0, int lim) {
     int nb = lim - b0; if (nb > g.Gb) nb = g.Gb;
-    int t = g.row_aligned == 4 ? ((nb + g.ilv - 1) / g.ilv) : g.row_aligned == 3 ? ((nb + 1) >> 1) : g.row_aligned == 2 ? (2 * nb)
-          : g.row_aligned ? ((nb * g.rows_per_board + 15) >> 4) : ((nb * g.PB + g.pitch + 1 + 127) >> 7);
-    return t < g.T ? t : g.T;
+    return tower_tiles_for(g, nb);
   };
   // A group's tiles split into two halves that are INDEPENDENT through the whole tower (no 3x3 tap of one half reads a
   // row of the other): interleaved pairs (8x8: a tile = two whole boards, zero row groups between tiles) and half-board
@@ -345,7 +328,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
       uint64_t tile_delta[TW_MAXT];                                // start of M=128 tile t, in 16-byte rows
 #pragma unroll
       for (int t = 0; t < TW_MAXT; ++t)
-        tile_delta[t] = g.row_aligned == 2 ? (uint64_t)((t >> 1) * g.PB + (t & 1) * 8) : (uint64_t)(t * g.tile_adv);
+        tile_delta[t] = (uint64_t)tower_tile_start(g, t);
       constexpr uint64_t kK16DeltaA = (2u * TW_ROWS * 16u) >> 4;   // next K=16 slice: +2 channel chunks
       constexpr uint64_t kK16DeltaF = (2u * FC_LBO) >> 4;          // same for the FC feature panel
       for (int iter = 0; iter < a.iterations; ++iter) {
@@ -377,7 +360,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) fused_kernel(const FusedArgs a,
                   int tapshift, chunk0;
                   stage_info(l, j, g.blocks, g.pitch, g.dy_rows, CG, tapshift, chunk0);
                   const uint64_t ad0 = smem_desc(act_base + (uint32_t)((chunk0 * TW_ROWS + TW_PAD + tapshift) * 16), TW_ROWS * 16, (uint32_t)g.sbo_bytes) +
-                                       (g.row_aligned == 2 ? (uint64_t)((t >> 1) * g.PB + (t & 1) * 8) : (uint64_t)(t * g.tile_adv));
+                                       (uint64_t)tower_tile_start(g, t);
                   const uint64_t bd0 = smem_desc(conv_slot_addr(slot), nrows_b * 16, 128);
                   const uint32_t acc0 = (preloaded || j > 0) ? 1u : 0u;
                   if (elect_one()) {

@@ -76,6 +76,38 @@ struct TowerGeo {
   int dy_rows;                // padded positions between vertically adjacent cells (pitch, or 2*pitch when interleaved)
 };
 
+// M row i (tile i / 128, row i % 128) of a group -> its padded position p (in 16-byte activation rows after the TW_PAD zero rows)
+// and v = board * 256 + cell of the board cell it holds, or -1 when the row is padding (zero column / zero row / slack).
+__host__ __device__ inline void tower_row(const TowerGeo& g, int i, int& p, int& v) {
+  int b, y, x;
+  if (g.row_aligned == 3) {
+    const int t = i >> 7, j = (i & 127) >> 3;
+    x = i & 7; b = 2 * t + (j & 1); y = j >> 1; p = t * g.tile_adv + j * g.pitch + x;
+  } else if (g.row_aligned == 4) {
+    const int t = i >> 7, r = i & 127, j = r / g.pitch;
+    x = r % g.pitch; y = j / g.ilv; b = g.ilv * t + j % g.ilv; p = t * g.tile_adv + r;
+  } else if (g.row_aligned == 2) {
+    const int t = i >> 7, r = i & 127;
+    b = t >> 1; y = r >> 3; x = 8 * (t & 1) + (r & 7); p = b * g.PB + y * g.pitch + x;
+  } else if (g.row_aligned) {
+    const int R = (i >> 7) * 16 + ((i & 127) >> 3);
+    x = i & 7; p = R * g.pitch + x; b = R / g.rows_per_board; y = R % g.rows_per_board;
+  } else {
+    p = i; b = p / g.PB; const int rem = p % g.PB; y = rem / g.pitch; x = rem % g.pitch;
+  }
+  v = (b < g.Gb && y < g.n && x < g.m) ? b * 256 + y * g.m + x : -1;
+}
+// first padded position of tile t (what the MMA descriptor of the tile starts at)
+__host__ __device__ inline int tower_tile_start(const TowerGeo& g, int t) {
+  return g.row_aligned == 2 ? (t >> 1) * g.PB + (t & 1) * 8 : t * g.tile_adv;
+}
+// tiles a group of nb boards needs (flat: + pitch + 1, the taps of the last real position read that far)
+__host__ __device__ inline int tower_tiles_for(const TowerGeo& g, int nb) {
+  const int t = g.row_aligned == 4 ? ((nb + g.ilv - 1) / g.ilv) : g.row_aligned == 3 ? ((nb + 1) >> 1) : g.row_aligned == 2 ? (2 * nb)
+              : g.row_aligned ? ((nb * g.rows_per_board + 15) >> 4) : ((nb * g.PB + g.pitch + 1 + 127) >> 7);
+  return t < g.T ? t : g.T;
+}
+
 // ---- weight-stream geometry shared by producer and MMA issuer ----
 struct LayerInfo { int n_stages, stage_bytes, nk16, N; long long stream_off; };
 // `stage_bytes` is what the stream holds per stage; a CTA of a pair (cg = 2) stages half of it (its half of the output
