@@ -224,7 +224,8 @@ int yy_engine_get_profile(yy_engine *e, int64_t *tower_launches, double *tower_m
  * each phase (tower, FC heads, softmax + tree step, barrier, re-zero, ...) at dbg_dev[600 ..] / [760 ..]. */
 int yy_engine_set_debug_stamps(yy_engine *e, long long *dbg_dev);
 /* Developer tool (A/B measurements in tools/): bit 0 = run the tower with the two halves of a group ping-ponging through the
- * tensor cores (epilogue hidden, weights streamed twice; slower in wall clock: profiles/r02_ab_pingpong_*.txt). */
+ * tensor cores (epilogue hidden, weights streamed twice; slower in wall clock: profiles/r02_ab_pingpong_*.txt); bit 1 = the
+ * tiles of a group in lock step through every layer as in round 1 instead of skewed (profiles/r02_ab_tile_*.txt). */
 int yy_engine_set_debug_flags(yy_engine *e, int flags);
 
 /* Self-play driver (SelfPlayWorker.play_game, self_play.py:72-192) for n_games game slots; a slot whose game ends

@@ -12,6 +12,8 @@
 // Nothing returns to the host between simulations: a search is one launch instead of 4 x (n_sims + 1).
 // The same kernel with iterations = 1 and the tree step off is the batched network forward (yy_evaluate).
 //
+// Within a layer the tiles of a group run SKEWED (see `skewed` below): the issuer walks the last and the first two weight stages
+// of a layer tile by tile, so a tile's epilogue runs under the other tiles' MMAs instead of next to their epilogues.
 // Warp roles: warp 0 weight producer, warp 1 MMA issuer, warps 2-17 epilogue / heads / tree, warps 18-19 background
 // selection (simulations that end in revisited terminals need no evaluation, mcts.py:365-367: games in such a stretch
 // are advanced here, concurrently with the tower, instead of holding up the tree phase of their CTA pair).

@@ -1,10 +1,13 @@
-// yy_rules_kernels.cu -- batched, stateless rules entry points of the C ABI (one thread per board).
-// Replaces YinYangGame.getValidMoves / getNextState / getGameEnded (src/yin_yang/yin_yang_game.py:39-110)
-// over YinYangLogic (src/yin_yang/yin_yang_logic.py:24-134).
+// yy_rules_kernels.cu -- batched, stateless rules entry points of the C ABI (one thread per board; the fused env step:
+// two lanes per board).  Replaces YinYangGame.getValidMoves / getNextState / getGameEnded
+// (src/yin_yang/yin_yang_game.py:39-110) over YinYangLogic (src/yin_yang/yin_yang_logic.py:24-134).
+// Square one-word boards under the Python rules (6x6, 8x8) run the line-fill rules of yy_rules_sq.cuh, every other
+// geometry and the row/column rule the generic bitboard rules of yy_rules.cuh.
 //
-// Roofline: HBM.  Algorithmic bytes per env step = 6*ceil(A/8)+4 (52 B at 8x8); the kernels are
-// ~2,600 dependent integer instructions per warp (flood fills), so at 65,536 boards (14 warps per SM) they are
-// latency bound -- 15 us, of which the SMs are busy 10 -- and at 1 M boards integer-issue bound (10.8 G steps/s).
+// Roofline: HBM.  Algorithmic bytes per env step = 6*ceil(A/8)+4 (52 B at 8x8).  8x8, 65,536 boards: one
+// launch is 5.4-5.9 us, of which 2.0 us are the floor of a one-block launch (launch + completion + a cold DRAM round trip)
+// and the rest integer issue (1.79 M warp instructions); with 1 M boards the kernel is integer-issue bound at 22-26 G steps/s
+// (profiles/r02_env_step_sq_ncu_summary.txt).
 #include "yy_common.cuh"
 #include "yy_rules_sq.cuh"
 
