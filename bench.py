@@ -442,8 +442,9 @@ def bench_tree_only(engine, torch, peaks):
     return {"value": sims / sec, "unit": "simulations/s", "leaves_per_s": evals / sec, "moves_per_s": (s1.moves - s0.moves) / sec,
             "roofline": {"bound": "hbm", "kernel": "fused_kernel with the stub evaluator (tree_step_game only)", "achieved": gbs, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": tt,
-                         "note": "~3 KB of algorithmic traffic per simulation (SURVEY 8d); pointer chasing: one dependent round trip per tree "
-                                 "level, latency bound -- inside the real search these steps overlap the tower of the other games"}}
+                         "note": "~3 KB of algorithmic traffic per simulation (SURVEY 8d), served by L2: ncu measures 265 B of DRAM traffic per "
+                                 "simulation (traffic: profiles/tree_traffic.json); pointer chasing, one dependent round trip per tree level, latency "
+                                 "bound -- inside the real search these steps overlap the tower of the other games"}}
 
 
 def bench_strong(engine, torch, dist, world, rank, sd, peaks, barrier):
