@@ -289,6 +289,29 @@ def test_network_matches_fp32_reference(eng, oracle_mod, cfg):
     e.close()
 
 
+@pytest.mark.parametrize("n,count", [(8, 500), (6, 700), (16, 40)])
+def test_tower_tile_skew_is_bit_identical_to_lockstep(eng, oracle_mod, n, count):
+    """The tile skew of the persistent kernel (the MMA issuer walks the first and last stages of a layer tile by tile,
+    per-tile barriers) only reorders WHEN a tile's MMAs and epilogue run, never the order of a tile's own accumulation:
+    logits, policy and value must equal, bit for bit, those of the lock-step walk (developer flag bit 1) and of the
+    half-group ping-pong (bit 0) -- full groups, a partial last group and several heads batches per CTA included."""
+    import torch
+    from oracle import port
+    torch.manual_seed(1)
+    net = randomise_bn(port.build_net(n, n, 128, 2))
+    boards, _ = random_play_boards(oracle_mod, n, n, count, seed=21)
+    e = eng.Engine(rows=n, cols=n, n_games=count, n_sims=1, evaluator="nn", state_dict=net.state_dict())
+    outs = []
+    for flags in (0, 2, 1):
+        e.L.yy_engine_set_debug_flags(e.handle, flags)
+        outs.append(e.evaluate_host(boards, want_logits=True))
+    e.L.yy_engine_set_debug_flags(e.handle, 0)
+    e.close()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+
+
 def test_network_search_persistent_vs_step_kernels(eng, oracle_mod):
     """Network-driven search: ONE persistent launch per search (tower + FC heads + tree step fused) against one
     network launch + one tree-step launch per simulation (YY_MODE_STEP_KERNELS).  Same network code, same tree code:
