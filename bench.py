@@ -96,7 +96,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
-PLY_SPREAD = 25        # CPU samples search positions after 0..24 random plies: the plies the GPU arm's timed region covers
+PLY_SPREAD = 40        # CPU samples search positions after 0..39 random plies: with rolling games the GPU arm's timed region (25 launches of
+                       # one search budget each at the driver's arguments) takes a slot through ~37 moves
 
 
 def cpu_selfplay_sample(workers, searches_per_worker=1, sims=SIMS, rows=ROWS, cols=COLS):
