@@ -920,8 +920,9 @@ int nn_fused_run(NNState& nn, const EngineDev* dev, uint32_t rule_flags, const u
   fa.batch_boards = fused_batch_boards(fa.g);
   // equal contiguous runs of boards per CTA (a search keeps its games on the same SM from the first to the last simulation)
   int sms = nn.num_sms > 0 ? nn.num_sms : 148;
+  // (small batches -- an arena of 16 games, a search of a few hundred positions -- are spread over as many CTAs as there are boards
+  // rather than packed into full groups: fewer tiles per CTA and step, i.e. lower latency, and the SMs would idle otherwise)
   long long per = (count + sms - 1) / sms;
-  if (per < fa.g.Gb && use_nn) per = fa.g.Gb;
   if (per < 1) per = 1;
   fa.boards_per_cta = (int)per;
   int grid = (int)((count + per - 1) / per);
