@@ -1,5 +1,6 @@
+"""Developer tool: the configs[0] leg of bench.py alone (6x6, 100 simulations, 4,096 rolling games)."""
 import sys, os, json
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import yy_b200  # noqa
 import bench

@@ -1,5 +1,7 @@
-import sys, time
-sys.path.insert(0, "/root/repo")
+"""Developer tool: latency of a lock-step search (400 simulations, 128x10 network) for small numbers of positions -- the arena's and the
+players' case; shows the effect of spreading a small batch over the CTAs."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import yy_b200
 from yinyang_game_alphazero_b200 import engine, network
